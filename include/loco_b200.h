@@ -1,0 +1,141 @@
+/*
+ * loco_b200.h -- C ABI of the B200-native LOCO-Edit editing-direction hot path.
+ *
+ * The reference (ChicyChen/LOCO-Edit) is pure Python/PyTorch and has no FFI layer; its boundary for
+ * this path is the set of tensor-valued Python methods of `EditUncondDiffusion`
+ * (src/modules/edit.py:2034-2625) and `YHCustomScheduler` (src/utils/utils.py:305-423).  Each entry
+ * point below names the reference call it replaces.  The Python mirror of those methods
+ * (loco_edit_b200/edit.py, scheduler.py) binds this library with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors in practice); nothing is
+ *     allocated or freed on the device by this library; host handles are created/destroyed here;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
+ *   - return value 0 = ok, non-zero = error (message via loco_last_error()); nothing throws;
+ *   - images / tangents / cotangents cross the ABI in the reference's NCHW fp32 layout;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef LOCO_B200_H_
+#define LOCO_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct loco_unet loco_unet_t;
+typedef struct loco_plan loco_plan_t;
+
+/* Architecture of the DDPM U-Net (reference: DDPM.__init__, src/models/ddpm/diffusion.py:24-126;
+ * hyper-parameters of src/configs/custom_celeba_ddpm.yml:21-30). */
+typedef struct loco_arch {
+  int ch;                  /* base channels (multiple of 128) */
+  int n_levels;            /* len(ch_mult) <= 8 */
+  int ch_mult[8];
+  int num_res_blocks;
+  int n_attn;              /* len(attn_resolutions) <= 4 */
+  int attn_resolutions[4];
+  int resolution;          /* input H = W */
+  int in_ch, out_ch;       /* 3, 3 */
+  float gn_eps;            /* 1e-6 */
+} loco_arch_t;
+
+int loco_abi_version(void);
+const char* loco_last_error(void);
+
+/* ---------------- model: parameters by reference state_dict name ---------------- */
+int loco_unet_create(const loco_arch_t* arch, loco_unet_t** out);
+void loco_unet_destroy(loco_unet_t* m);
+/* size (in floats) of the packed-weight arena the caller must provide */
+long long loco_unet_weight_floats(const loco_unet_t* m);
+int loco_unet_bind_weights(loco_unet_t* m, float* arena);
+int loco_unet_num_params(const loco_unet_t* m);
+/* name/shape of parameter i (same names as DDPM.state_dict()); shape has up to 4 entries */
+int loco_unet_param_info(const loco_unet_t* m, int i, char* name, int name_cap, int* shape, int* ndim);
+/* pack one parameter (torch layout, fp32, device memory) into the arena */
+int loco_unet_load_param(loco_unet_t* m, const char* name, const float* src, long long numel,
+                         void* stream);
+
+/* ---------------- execution plans ---------------- */
+/* n_primal samples, n_tangent probe tangents (JVP rows, need n_primal == 1), n_cotangent rows for
+ * the transposed pass.  (B,0,0) = plain eps_theta(x,t) for the DDIM loops; (1,k,k) = pull-back. */
+int loco_plan_create(const loco_unet_t* m, int n_primal, int n_tangent, int n_cotangent,
+                     loco_plan_t** out);
+void loco_plan_destroy(loco_plan_t* p);
+long long loco_plan_workspace_bytes(const loco_plan_t* p);
+int loco_plan_bind(loco_plan_t* p, void* workspace);
+int loco_plan_info(const loco_plan_t* p, double* fwd_flops, double* vjp_flops, int* fwd_ops,
+                   int* vjp_ops);
+
+/* eps = unet(x, t): replaces `self.unet(xt, t)` (src/modules/edit.py:2151, 2375, 2572).
+ * x, eps: [n_primal + n_tangent, 3, R, R]; tangent rows hold dx on input and d eps on output,
+ * i.e. the forward-mode product torch.func.jacfwd computes at src/modules/edit.py:2455. */
+int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void* stream);
+/* gx[j] = (d eps / d x)^T g_eps[j] at the primal point of the last loco_unet_forward: replaces
+ * the k backward passes of torch.autograd.functional.jacobian (src/modules/edit.py:2479). */
+int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream);
+
+/* ---------------- pull-back (power method) ---------------- */
+long long loco_pullback_scratch_bytes(int k, long long d);
+/* One subspace iteration of local_encoder_decoder_pullback_xt (src/modules/edit.py:2443-2483):
+ *   U = mask o J V^T (JVP), W = J^T U (VJP), (s, V_out) = orthonormalise(W).
+ * xt [d], V [k,d] in; u_full [k,d] (masked, zeros outside the mask), w_out [k,d] (un-orthonormalised
+ * W, may be NULL), V_out [k,d], s_out [k] = sqrt(singular values of W) out.  at = alphas_cumprod[floor t].
+ * align_sign != 0 picks row signs with <V_out_i, V_i> >= 0. */
+int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
+                            const unsigned char* mask, int noise, const float* V, int k, long long d,
+                            int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
+                            void* scratch, void* stream);
+
+/* ---------------- bandwidth-bound pieces ---------------- */
+/* P = (x - eps*sqrt(1-at))/sqrt(at): get_x0 without the mask (src/modules/edit.py:2386) */
+int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream);
+/* Vh and sqrt(singular values) of W [k,d]: torch.linalg.svd at src/modules/edit.py:2482.
+ * scratch >= loco_orthonormalise_scratch_bytes(k). */
+long long loco_orthonormalise_scratch_bytes(int k);
+int loco_orthonormalise(const float* W, int k, long long d, const float* v_prev, float* V,
+                        float* s_out, void* scratch, void* stream);
+/* vT = normalise_rows(vT_mod - (Vn^T (Vn vT_mod^T))^T): src/modules/edit.py:2317-2323.
+ * scratch >= 8*(k_null*k + k) bytes. */
+int loco_nullspace_project(const float* vT_mod, int k, const float* Vn, int k_null, long long d,
+                           int project, float* out, void* scratch, void* stream);
+/* YHCustomScheduler.step (src/utils/utils.py:342-374); x0_pred may be NULL */
+int loco_ddim_step(const float* xt, const float* et, const float* noise, float at, float at_next,
+                   float eta, long long n, float* xt_next, float* x0_pred, void* stream);
+/* x + scale*v: x_space_guidance_direct (src/modules/edit.py:2618-2625) */
+int loco_axpy(const float* x, const float* v, float scale, long long n, float* out, void* stream);
+/* row-major indices of mask != 0 (selection order of `P_xt[:, mask]`, src/modules/edit.py:2390) */
+int loco_mask_indices(const unsigned char* mask, long long d, int* idx, int* count, void* stream);
+int loco_gather_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
+                     void* stream);
+int loco_scatter_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
+                      void* stream);
+int loco_gram(const float* A, int ka, const float* B, int kb, long long d, double* G, void* stream);
+
+/* ---------------- single layers (used by the parity tests) ---------------- */
+/* Channels-last convolution on the tcgen05 path.  kind: 0 = 3x3 s1 p1, 1 = 1x1, 2 = 3x3 s2 pad
+ * (0,1,0,1), 3 = data gradient of kind 0, 4 = data gradient of kind 2.  w is the torch-layout
+ * weight [Cout,Cin,k,k] of the FORWARD conv; wpack is scratch of the same size.  x: [N,H,W,Cx],
+ * y: [N,Ho,Wo,Cy] contiguous.  bias/addend may be NULL. */
+int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, const float* w, int Cout,
+                     int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
+                     int accumulate, float* y, void* stream);
+/* GroupNorm(32)+optional SiLU on [N,H,W,C]; rows >= n_primal are tangents of row 0.
+ * stats: 8*N*64 bytes scratch. */
+int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_primal,
+                            const float* gamma, const float* beta, float eps, int silu, float* y,
+                            void* stats, void* stream);
+/* VJP of the above at primal xp [1,H,W,C] for K cotangent rows gy -> gx. stats: 8*(K+1)*64 bytes. */
+int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* gy, int K,
+                            const float* gamma, const float* beta, float eps, int silu, float* gx,
+                            void* stats, void* stream);
+/* attention core on qkv [N,T,3C]; S scratch [N,T,T]; o [N,T,C] */
+int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, float* S, float* o,
+                       void* stream);
+int loco_attention_vjp(const float* go, int K, int T, int C, const float* qkv0, const float* P0,
+                       float* gP, float* gqkv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCO_B200_H_ */

@@ -1,0 +1,313 @@
+// extern "C" boundary of libloco_b200.so -- see include/loco_b200.h for the contract.
+#include "../../include/loco_b200.h"
+#include <algorithm>
+#include "attention.cuh"
+#include "conv_gemm.cuh"
+#include "layers.cuh"
+#include "pullback.cuh"
+#include "unet.cuh"
+
+using namespace loco;
+
+struct loco_unet { Model* m; };
+struct loco_plan { Plan* p; };
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define GUARD_BEGIN try {
+#define GUARD_END                                            \
+  }                                                          \
+  catch (const std::exception& e) {                          \
+    set_error("exception: %s", e.what());                    \
+    return 99;                                               \
+  }                                                          \
+  catch (...) {                                              \
+    set_error("unknown exception");                          \
+    return 99;                                               \
+  }
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: this library has no CPU fallback (%s)", cudaGetErrorString(e));
+    return 10;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int loco_abi_version(void) { return 1; }
+const char* loco_last_error(void) { return get_error(); }
+
+// ------------------------------------------------------------------------------------------------
+int loco_unet_create(const loco_arch_t* a, loco_unet_t** out) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(a && out, "loco_unet_create: null argument");
+  LOCO_REQUIRE(a->n_levels >= 1 && a->n_levels <= 8 && a->n_attn >= 0 && a->n_attn <= 4,
+               "loco_unet_create: bad level/attention counts");
+  LOCO_REQUIRE(a->in_ch == 3 && a->out_ch == 3, "loco_unet_create: only 3-channel images");
+  LOCO_REQUIRE(a->ch % 128 == 0 && a->ch >= 128, "loco_unet_create: ch must be a multiple of 128");
+  LOCO_REQUIRE((a->resolution >> (a->n_levels - 1)) >= 4 &&
+                   (a->resolution & (a->resolution - 1)) == 0,
+               "loco_unet_create: resolution must be a power of two, >= 4 at the coarsest level");
+  Arch A;
+  A.ch = a->ch; A.n_levels = a->n_levels;
+  for (int i = 0; i < 8; ++i) A.ch_mult[i] = a->ch_mult[i];
+  A.num_res_blocks = a->num_res_blocks; A.n_attn = a->n_attn;
+  for (int i = 0; i < 4; ++i) A.attn_resolutions[i] = a->attn_resolutions[i];
+  A.resolution = a->resolution; A.in_ch = a->in_ch; A.out_ch = a->out_ch; A.gn_eps = a->gn_eps;
+  *out = new loco_unet{new Model(A)};
+  return 0;
+  GUARD_END
+}
+void loco_unet_destroy(loco_unet_t* m) {
+  if (m) { delete m->m; delete m; }
+}
+long long loco_unet_weight_floats(const loco_unet_t* m) { return m ? (long long)m->m->arena_floats : -1; }
+int loco_unet_bind_weights(loco_unet_t* m, float* arena) {
+  LOCO_REQUIRE(m && arena, "loco_unet_bind_weights: null argument");
+  LOCO_REQUIRE(((uintptr_t)arena & 255) == 0, "loco_unet_bind_weights: arena must be 256B aligned");
+  m->m->arena = arena;
+  return 0;
+}
+int loco_unet_num_params(const loco_unet_t* m) { return m ? (int)m->m->slots.size() : -1; }
+int loco_unet_param_info(const loco_unet_t* m, int i, char* name, int name_cap, int* shape, int* ndim) {
+  LOCO_REQUIRE(m && i >= 0 && i < (int)m->m->slots.size(), "loco_unet_param_info: bad index");
+  const ParamSlot& s = m->m->slots[i];
+  if (name && name_cap > 0) {
+    strncpy(name, s.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (ndim) *ndim = (int)s.shape.size();
+  if (shape)
+    for (size_t j = 0; j < s.shape.size() && j < 4; ++j) shape[j] = s.shape[j];
+  return 0;
+}
+int loco_unet_load_param(loco_unet_t* m, const char* name, const float* src, long long numel,
+                         void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(m && name && src, "loco_unet_load_param: null argument");
+  LOCO_TRY(require_device());
+  return m->m->load_param(name, src, numel, ST(stream));
+  GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+int loco_plan_create(const loco_unet_t* m, int n_primal, int n_tangent, int n_cotangent,
+                     loco_plan_t** out) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(m && out, "loco_plan_create: null argument");
+  Plan* p = new Plan(m->m, n_primal, n_tangent, n_cotangent);
+  const int r = p->build(nullptr);
+  if (r != 0) { delete p; return r; }
+  *out = new loco_plan{p};
+  return 0;
+  GUARD_END
+}
+void loco_plan_destroy(loco_plan_t* p) {
+  if (p) { delete p->p; delete p; }
+}
+long long loco_plan_workspace_bytes(const loco_plan_t* p) {
+  return p ? (long long)p->p->workspace_floats * 4 : -1;
+}
+int loco_plan_bind(loco_plan_t* p, void* workspace) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p && workspace, "loco_plan_bind: null argument");
+  LOCO_REQUIRE(((uintptr_t)workspace & 255) == 0, "loco_plan_bind: workspace must be 256B aligned");
+  LOCO_TRY(require_device());
+  LOCO_TRY(p->p->model->check_loaded());
+  return p->p->build(reinterpret_cast<float*>(workspace));
+  GUARD_END
+}
+int loco_plan_info(const loco_plan_t* p, double* fwd_flops, double* vjp_flops, int* fwd_ops,
+                   int* vjp_ops) {
+  LOCO_REQUIRE(p, "loco_plan_info: null plan");
+  if (fwd_flops) *fwd_flops = p->p->fwd_flops;
+  if (vjp_flops) *vjp_flops = p->p->vjp_flops;
+  if (fwd_ops) *fwd_ops = p->p->fwd_launches;
+  if (vjp_ops) *vjp_ops = p->p->vjp_launches;
+  return 0;
+}
+int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p && x && eps, "loco_unet_forward: null argument");
+  return p->p->forward(x, t, eps, ST(stream));
+  GUARD_END
+}
+int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p && g_eps && gx, "loco_unet_vjp: null argument");
+  return p->p->vjp(g_eps, gx, ST(stream));
+  GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+long long loco_orthonormalise_scratch_bytes(int k) { return (long long)sizeof(double) * (3 * k * k + 2 * k); }
+
+long long loco_pullback_scratch_bytes(int k, long long d) {
+  const size_t kd = align_up((size_t)k * d * 4, 256);
+  const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);
+  return (long long)(2 * k1d + 4 * kd + align_up((size_t)loco_orthonormalise_scratch_bytes(k), 256));
+}
+
+int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
+                            const unsigned char* mask, int noise, const float* V, int k, long long d,
+                            int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
+                            void* scratch, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p && xt && V && u_full && V_out && s_out && scratch, "loco_pullback_iteration: null argument");
+  Plan& P = *p->p;
+  LOCO_REQUIRE(P.NP == 1 && P.NT == k && P.NC == k, "loco_pullback_iteration: plan is (%d,%d,%d), need (1,%d,%d)",
+               P.NP, P.NT, P.NC, k, k);
+  const int R = P.model->arch.resolution;
+  LOCO_REQUIRE(d == 3LL * R * R, "loco_pullback_iteration: d=%lld does not match the model", d);
+  cudaStream_t s = ST(stream);
+  const size_t kd = align_up((size_t)k * d * 4, 256);
+  const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);
+  char* sp = reinterpret_cast<char*>(scratch);
+  float* xin = reinterpret_cast<float*>(sp); sp += k1d;
+  float* eps = reinterpret_cast<float*>(sp); sp += k1d;
+  float* g_eps = reinterpret_cast<float*>(sp); sp += kd;
+  float* gx_direct = reinterpret_cast<float*>(sp); sp += kd;
+  float* gx_unet = reinterpret_cast<float*>(sp); sp += kd;
+  float* w_tmp = reinterpret_cast<float*>(sp); sp += kd;
+  double* oscr = reinterpret_cast<double*>(sp);
+  float* w = w_out ? w_out : w_tmp;
+  // batch = [x_t ; v_1 .. v_k]: one fused primal + k-tangent pass
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(xin, xt, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(xin + d, V, sizeof(float) * k * d, cudaMemcpyDeviceToDevice, s));
+  LOCO_TRY(P.forward(xin, t, eps, s));
+  LOCO_TRY(pmp_jvp_epilogue(V, eps + d, mask, at, noise, k, d, u_full, g_eps, gx_direct, s));
+  LOCO_TRY(P.vjp(g_eps, gx_unet, s));
+  LOCO_TRY(axpy(gx_direct, gx_unet, 1.0f, (long long)k * d, w, s));
+  LOCO_TRY(orthonormalise(w, k, d, align_sign ? V : nullptr, V_out, s_out, oscr, s));
+  return 0;
+  GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream) {
+  LOCO_TRY(require_device());
+  return pmp_forward(x, eps, at, n, out, ST(stream));
+}
+int loco_orthonormalise(const float* W, int k, long long d, const float* v_prev, float* V,
+                        float* s_out, void* scratch, void* stream) {
+  LOCO_TRY(require_device());
+  return orthonormalise(W, k, d, v_prev, V, s_out, reinterpret_cast<double*>(scratch), ST(stream));
+}
+int loco_nullspace_project(const float* vT_mod, int k, const float* Vn, int k_null, long long d,
+                           int project, float* out, void* scratch, void* stream) {
+  LOCO_TRY(require_device());
+  return nullspace_project(vT_mod, k, Vn, k_null, d, project, out, reinterpret_cast<double*>(scratch),
+                           ST(stream));
+}
+int loco_ddim_step(const float* xt, const float* et, const float* noise, float at, float at_next,
+                   float eta, long long n, float* xt_next, float* x0_pred, void* stream) {
+  LOCO_TRY(require_device());
+  return ddim_step(xt, et, noise, at, at_next, eta, n, xt_next, x0_pred, ST(stream));
+}
+int loco_axpy(const float* x, const float* v, float scale, long long n, float* out, void* stream) {
+  LOCO_TRY(require_device());
+  return axpy(x, v, scale, n, out, ST(stream));
+}
+int loco_mask_indices(const unsigned char* mask, long long d, int* idx, int* count, void* stream) {
+  LOCO_TRY(require_device());
+  return mask_indices(mask, d, idx, count, ST(stream));
+}
+int loco_gather_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
+                     void* stream) {
+  LOCO_TRY(require_device());
+  return gather_rows(src, rows, d, idx, count, out, ST(stream));
+}
+int loco_scatter_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
+                      void* stream) {
+  LOCO_TRY(require_device());
+  return scatter_rows(src, rows, d, idx, count, out, ST(stream));
+}
+int loco_gram(const float* A, int ka, const float* B, int kb, long long d, double* G, void* stream) {
+  LOCO_TRY(require_device());
+  return gram(A, ka, B, kb, d, G, ST(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, const float* w, int Cout,
+                     int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
+                     int accumulate, float* y, void* stream) {
+  GUARD_BEGIN
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  ConvProblem p;
+  const int ksz = kind == CONV_1x1 ? 1 : 3;
+  int Ho = H, Wo = W, Cy = Cout;
+  if (kind == CONV_3x3 || kind == CONV_1x1 || kind == CONV_3x3_S2) {
+    LOCO_REQUIRE(Cx == Cin, "loco_conv2d_nhwc: x has %d channels, weight expects %d", Cx, Cin);
+    LOCO_TRY(pack_conv_fprop(w, wpack, Cout, Cin, ksz, ksz, s));
+    if (kind == CONV_3x3_S2) { Ho = H / 2; Wo = W / 2; }
+    p.Kc = Cin; p.Ngemm = Cout;
+  } else {
+    LOCO_REQUIRE(Cx == Cout, "loco_conv2d_nhwc: dy has %d channels, weight has Cout=%d", Cx, Cout);
+    LOCO_TRY(pack_conv_dgrad(w, wpack, Cout, Cin, ksz, ksz, Cout, 0, s));
+    if (kind == CONV_3x3_S2_DGRAD) { Ho = 2 * H; Wo = 2 * W; }
+    p.Kc = Cout; p.Ngemm = Cin; Cy = Cin;
+  }
+  p.kind = kind;
+  p.in = make_view(const_cast<float*>(x), N, H, W, Cx);
+  p.out = make_view(y, N, Ho, Wo, Cy);
+  p.wpack = wpack;
+  p.bias = bias; p.bias_rows = bias_rows;
+  View add;
+  if (addend) { add = make_view(const_cast<float*>(addend), N, Ho, Wo, Cy); p.addend = &add; }
+  p.accumulate = accumulate; p.round_out = 0;
+  ConvLaunch L;
+  LOCO_TRY(conv_prepare(p, &L));
+  return conv_run(L, s);
+  GUARD_END
+}
+
+int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_primal,
+                            const float* gamma, const float* beta, float eps, int silu, float* y,
+                            void* stats, void* stream) {
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  View xv = make_view(const_cast<float*>(x), N, H, W, C);
+  View yv = make_view(y, N, H, W, C);
+  LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
+  LOCO_TRY(gn_stats_fwd(xv, n_primal, reinterpret_cast<double*>(stats), s));
+  return gn_apply_fwd(xv, n_primal, reinterpret_cast<double*>(stats), gamma, beta, eps, silu, 0, yv, s);
+}
+int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* gy, int K,
+                            const float* gamma, const float* beta, float eps, int silu, float* gx,
+                            void* stats, void* stream) {
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  View xv = make_view(const_cast<float*>(xp), 1, H, W, C);
+  View gyv = make_view(const_cast<float*>(gy), K, H, W, C);
+  View gxv = make_view(gx, K, H, W, C);
+  double* ps = reinterpret_cast<double*>(stats);
+  double* bs = ps + 64;
+  LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * (K + 1), s));
+  LOCO_TRY(gn_stats_fwd(xv, 1, ps, s));
+  LOCO_TRY(gn_stats_vjp(xv, ps, gyv, gamma, beta, eps, silu, bs, s));
+  return gn_apply_vjp(xv, ps, gyv, bs, gamma, beta, eps, silu, nullptr, 0, 0, gxv, s);
+}
+int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, float* S, float* o,
+                       void* stream) {
+  LOCO_TRY(require_device());
+  View q = make_view(const_cast<float*>(qkv), N, 1, T, 3 * C);
+  View ov = make_view(o, N, 1, T, C);
+  return attention_forward(q, n_primal, S, ov, ST(stream));
+}
+int loco_attention_vjp(const float* go, int K, int T, int C, const float* qkv0, const float* P0,
+                       float* gP, float* gqkv, void* stream) {
+  LOCO_TRY(require_device());
+  View g = make_view(const_cast<float*>(go), K, 1, T, C);
+  View q0 = make_view(const_cast<float*>(qkv0), 1, 1, T, 3 * C);
+  View gq = make_view(gqkv, K, 1, T, 3 * C);
+  return attention_vjp(g, q0, P0, gP, gq, ST(stream));
+}
+
+}  // extern "C"

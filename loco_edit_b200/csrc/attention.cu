@@ -1,0 +1,219 @@
+// Attention core (scores, softmax, value mixing) with JVP and VJP: see attention.cuh.
+#include "attention.cuh"
+#include <math.h>
+
+namespace loco {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256)
+batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long long sCm,
+                    long long sCn, long long sCb, int M, int N, int K, float alpha, float beta,
+                    int round_out, int a_kcontig, int b_ncontig) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* Ab = A.ptr + b * A.sb;
+  const float* Bb = B.ptr + b * B.sb;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;   // 16x16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r;
+      int m, k;
+      if (a_kcontig) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      float v = 0.f;
+      if (m0 + m < M && k0 + k < K) v = Ab[(long long)(m0 + m) * A.s0 + (long long)(k0 + k) * A.s1];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r;
+      int n, k;
+      if (b_ncontig) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+      float v = 0.f;
+      if (n0 + n < N && k0 + k < K) v = Bb[(long long)(k0 + k) * B.s0 + (long long)(n0 + n) * B.s1];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Cb = C + b * sCb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float* cp = Cb + (long long)m * sCm + (long long)n * sCn;
+      float v = alpha * acc[i][j];
+      if (beta != 0.f) v += beta * (*cp);
+      if (round_out) v = round_tf32(v);
+      *cp = v;
+    }
+  }
+}
+
+// One warp per row.
+__global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long rows, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* p = S + row * T;
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) mx = fmaxf(mx, p[j] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = expf(p[j] * scale - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < T; j += 32) p[j] *= inv;
+}
+
+__global__ void softmax_lin_rows_kernel(const float* __restrict__ P0, float* __restrict__ X, int T,
+                                        long long rows, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = P0 + (row % T) * T;
+  float* x = X + row * T;
+  float dot = 0.f;
+  for (int j = lane; j < T; j += 32) dot += p[j] * x[j];
+  dot = warp_sum(dot);
+  for (int j = lane; j < T; j += 32) x[j] = scale * p[j] * (x[j] - dot);
+}
+
+int check_tokens(const View& v, const char* what) {
+  LOCO_REQUIRE(v.sH == (long long)v.W * v.sW, "%s: tokens must be uniformly strided", what);
+  return 0;
+}
+
+}  // namespace
+
+int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
+                 int M, int N, int K, int batch, float alpha, float beta, int round_out,
+                 cudaStream_t s) {
+  if (batch <= 0) return 0;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+  batched_gemm_kernel<<<grid, 256, 0, s>>>(A, B, C, sCm, sCn, sCb, M, N, K, alpha, beta, round_out,
+                                           A.s1 == 1 ? 1 : 0, B.s1 == 1 ? 1 : 0);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int softmax_rows(float* S, int T, int batch, float scale, cudaStream_t s) {
+  if (batch <= 0) return 0;
+  const long long rows = (long long)batch * T;
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, T, rows, scale);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int softmax_lin_rows(const float* P0, float* X, int T, int batch, float scale, cudaStream_t s) {
+  if (batch <= 0) return 0;
+  const long long rows = (long long)batch * T;
+  softmax_lin_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(P0, X, T, rows, scale);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attention_forward(View qkv, int n_primal, float* S, View o, cudaStream_t s) {
+  LOCO_TRY(check_tokens(qkv, "attention_forward(qkv)"));
+  LOCO_TRY(check_tokens(o, "attention_forward(o)"));
+  const int C = qkv.C / 3;
+  const int T = qkv.H * qkv.W;
+  const int N = qkv.N;
+  const int nt = N - n_primal;
+  LOCO_REQUIRE(o.C == C && o.N == N, "attention_forward: shape mismatch");
+  LOCO_REQUIRE(nt == 0 || n_primal == 1, "attention_forward: tangents need exactly one primal row");
+  const float scale = 1.0f / sqrtf((float)C);   // int(c) ** (-0.5)
+  const long long ts = qkv.sW;                  // token stride
+  const long long TT = (long long)T * T;
+  const float* q = qkv.ptr;
+  const float* k = qkv.ptr + C;
+  const float* v = qkv.ptr + 2 * C;
+  // primal rows: S = q k^T ; P = softmax(scale S) ; o = P v
+  LOCO_TRY(batched_gemm({q, ts, 1, qkv.sN}, {k, 1, ts, qkv.sN}, S, T, 1, TT, T, T, C, n_primal, 1.f,
+                        0.f, 0, s));
+  LOCO_TRY(softmax_rows(S, T, n_primal, scale, s));
+  LOCO_TRY(batched_gemm({S, T, 1, TT}, {v, ts, 1, qkv.sN}, o.ptr, o.sW, 1, o.sN, T, C, T, n_primal,
+                        1.f, 0.f, 1, s));
+  if (nt > 0) {
+    const float* qd = q + qkv.sN;
+    const float* kd = k + qkv.sN;
+    const float* vd = v + qkv.sN;
+    float* Sd = S + TT;
+    float* od = o.ptr + o.sN;
+    // dS = dq k0^T + q0 dk^T
+    LOCO_TRY(batched_gemm({qd, ts, 1, qkv.sN}, {k, 1, ts, 0}, Sd, T, 1, TT, T, T, C, nt, 1.f, 0.f, 0, s));
+    LOCO_TRY(batched_gemm({q, ts, 1, 0}, {kd, 1, ts, qkv.sN}, Sd, T, 1, TT, T, T, C, nt, 1.f, 1.f, 0, s));
+    // dP = scale * P0 o (dS - rowsum(P0 o dS))
+    LOCO_TRY(softmax_lin_rows(S, Sd, T, nt, scale, s));
+    // do = P0 dv + dP v0
+    LOCO_TRY(batched_gemm({S, T, 1, 0}, {vd, ts, 1, qkv.sN}, od, o.sW, 1, o.sN, T, C, T, nt, 1.f, 0.f, 0, s));
+    LOCO_TRY(batched_gemm({Sd, T, 1, TT}, {v, ts, 1, 0}, od, o.sW, 1, o.sN, T, C, T, nt, 1.f, 1.f, 1, s));
+  }
+  return 0;
+}
+
+int attention_vjp(View go, View qkv0, const float* P0, float* gP, View gqkv, cudaStream_t s) {
+  LOCO_TRY(check_tokens(go, "attention_vjp(go)"));
+  LOCO_TRY(check_tokens(qkv0, "attention_vjp(qkv0)"));
+  LOCO_TRY(check_tokens(gqkv, "attention_vjp(gqkv)"));
+  const int C = qkv0.C / 3;
+  const int T = qkv0.H * qkv0.W;
+  const int K = go.N;
+  LOCO_REQUIRE(go.C == C && gqkv.C == 3 * C && gqkv.N == K, "attention_vjp: shape mismatch");
+  const float scale = 1.0f / sqrtf((float)C);
+  const long long ts = qkv0.sW, gts = gqkv.sW;
+  const long long TT = (long long)T * T;
+  const float* q0 = qkv0.ptr;
+  const float* k0 = qkv0.ptr + C;
+  const float* v0 = qkv0.ptr + 2 * C;
+  float* gq = gqkv.ptr;
+  float* gk = gqkv.ptr + C;
+  float* gv = gqkv.ptr + 2 * C;
+  // gv = P0^T go      : (j, c) = sum_i P0[i][j] go[i][c]
+  LOCO_TRY(batched_gemm({P0, 1, T, 0}, {go.ptr, go.sW, 1, go.sN}, gv, gts, 1, gqkv.sN, T, C, T, K, 1.f,
+                        0.f, 1, s));
+  // gP = go v0^T      : (i, j) = sum_c go[i][c] v0[j][c]
+  LOCO_TRY(batched_gemm({go.ptr, go.sW, 1, go.sN}, {v0, 1, ts, 0}, gP, T, 1, TT, T, T, C, K, 1.f, 0.f,
+                        0, s));
+  // gS = scale * P0 o (gP - rowsum(P0 o gP))   (gradient w.r.t. the unscaled scores)
+  LOCO_TRY(softmax_lin_rows(P0, gP, T, K, scale, s));
+  // gq = gS k0        : (i, c) = sum_j gS[i][j] k0[j][c]
+  LOCO_TRY(batched_gemm({gP, T, 1, TT}, {k0, ts, 1, 0}, gq, gts, 1, gqkv.sN, T, C, T, K, 1.f, 0.f, 1, s));
+  // gk = gS^T q0      : (j, c) = sum_i gS[i][j] q0[i][c]
+  LOCO_TRY(batched_gemm({gP, 1, T, TT}, {q0, ts, 1, 0}, gk, gts, 1, gqkv.sN, T, C, T, K, 1.f, 0.f, 1, s));
+  return 0;
+}
+
+}  // namespace loco

@@ -1,0 +1,31 @@
+// Single-head self-attention core of the DDPM AttnBlock (reference: ddpm/diffusion.py:941-966) and
+// its JVP / VJP.  The token counts are tiny (256 or 64 tokens x 512 channels, 0.14 % of the U-Net
+// FLOPs) and the reference computes them with fp32 bmm, so this stays on CUDA cores in exact fp32.
+#pragma once
+#include "common.cuh"
+
+namespace loco {
+
+// C[b](m,n) = alpha * sum_k A[b](m,k) * B[b](k,n) + beta * C[b](m,n), arbitrary element strides.
+struct GemmOperand {
+  const float* ptr;
+  long long s0, s1, sb;   // strides of (first index, second index, batch)
+};
+int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
+                 int M, int N, int K, int batch, float alpha, float beta, int round_out,
+                 cudaStream_t s);
+
+// P[b][i][:] = softmax(scale * S[b][i][:]) in place.
+int softmax_rows(float* S, int T, int batch, float scale, cudaStream_t s);
+// X[b][i][:] = scale * P0[i][:] * (X[b][i][:] - sum_j P0[i][j] X[b][i][j])   (softmax JVP and VJP)
+int softmax_lin_rows(const float* P0, float* X, int T, int batch, float scale, cudaStream_t s);
+
+// qkv: [N, T, 3C] (q | k | v along channels), S: [N, T, T] scratch that keeps P afterwards,
+// o: [N, T, C].  Rows < n_primal are ordinary forward passes; the remaining rows are tangents of
+// primal row 0.
+int attention_forward(View qkv, int n_primal, float* S, View o, cudaStream_t s);
+// go: [k, T, C] cotangent of o; qkv0/P0: saved primal row; gP: [k, T, T] scratch;
+// gqkv: [k, T, 3C] result.
+int attention_vjp(View go, View qkv0, const float* P0, float* gP, View gqkv, cudaStream_t s);
+
+}  // namespace loco

@@ -1,0 +1,437 @@
+// Implicit-GEMM convolution for the LOCO-Edit U-Net hot path on Blackwell tensor cores.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + tap_offset, cin] * Wp[cout, tap*Cin + cin]
+//
+// * A tiles (128 pixels x 32 fp32 channels) are fetched by TMA straight from the channels-last
+//   activation tensor as 4-D boxes; out-of-image coordinates are zero-filled by the TMA unit, which
+//   implements the convolution padding (and the reference's asymmetric (0,1,0,1) stride-2 pad,
+//   ddpm/diffusion.py:846-850) without any im2col buffer.
+// * Weight tiles come from a pre-packed K-major matrix.  Both land in 128B-swizzled shared memory
+//   and are consumed by tcgen05.mma.kind::tf32 with the fp32 accumulator in TMEM.
+// * The batch dimension stacks the primal sample and the k probe tangents (JVP) or the k
+//   cotangents (VJP): a convolution is linear, so every row of the batch shares the weight tile.
+// * Warp-specialised persistent CTAs: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+//   allocator, warps 4-7 = epilogue (bias / timestep bias on primal rows, residual add, VJP
+//   accumulation, tf32 rounding).  Two TMEM accumulator stages overlap epilogue and main loop.
+#include "conv_gemm.cuh"
+
+namespace loco {
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kABytes = kConvBlockM * 128;       // 16 KB
+constexpr int kBBytes = kConvMaxBlockN * 128;    // 16 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 256;                   // 2 accumulator stages x 128 fp32 columns
+constexpr int kThreads = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row
+// groups 1024 bytes apart (cute::UMMA::SmemDescriptor layout; version = 1 for sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128.
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // C format = F32
+  d |= 2u << 7;                 // A format = TF32
+  d |= 2u << 10;                // B format = TF32
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(kConvBlockM >> 4) << 24;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.amap[0]);
+    prefetch_tmap(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = tiles_m * p.tiles_co;
+  const int kiters = p.ntaps * p.c_chunks;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * 128u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile % tiles_m;
+        const int tco = tile / tiles_m;
+        const int tx = tm % p.tiles_x;
+        const int ty = (tm / p.tiles_x) % p.tiles_y;
+        const int tn = tm / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, co0 = tco * p.block_n;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const CUtensorMap* am = &p.amap[p.tap_map[tap]];
+          const int xx = x0 + p.tap_dx[tap], yy = y0 + p.tap_dy[tap], wk = p.tap_wk[tap];
+          for (int cc = 0; cc < p.c_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(sa, am, &full_bar[stage], cc * kConvBlockK, xx, yy, n0);
+            tma_load_2d(sa + kABytes, &p.bmap, &full_bar[stage], wk + cc * kConvBlockK, co0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = make_idesc_tf32(p.block_n);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kConvMaxBlockN;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
+            umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (uint32_t)((it | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;              // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;       // row of the 128-pixel tile
+    const int rw = row % p.TW;
+    const int rh = (row / p.TW) % p.TH;
+    const int rn = row / (p.TW * p.TH);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile % tiles_m;
+      const int tco = tile / tiles_m;
+      const int tx = tm % p.tiles_x;
+      const int ty = (tm / p.tiles_x) % p.tiles_y;
+      const int tn = tm / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.TW + rw, y = ty * p.TH + rh, n = tn * p.TN + rn;
+      const int co0 = tco * p.block_n;
+      const bool valid = (n < p.N) && (y < p.Ho) && (x < p.Wo);
+      const bool use_bias = n < p.bias_rows;
+      float* optr = p.out + (long long)n * p.out_sN + (long long)y * p.out_sH +
+                    (long long)x * p.out_sW + co0;
+      const float* aptr = p.addend
+                              ? p.addend + (long long)n * p.add_sN + (long long)y * p.add_sH +
+                                    (long long)x * p.add_sW + co0
+                              : nullptr;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kConvMaxBlockN;
+      for (int ch = 0; ch < p.block_n; ch += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (use_bias) {
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + j));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.bias2) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + j));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+            }
+            if (aptr) {
+              const float4 a = *reinterpret_cast<const float4*>(aptr + ch + j);
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            float4* o = reinterpret_cast<float4*>(optr + ch + j);
+            if (p.accumulate) {
+              const float4 a = *o;
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            if (p.round_out) {
+              v.x = round_tf32(v.x); v.y = round_tf32(v.y);
+              v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+            }
+            *o = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+      set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int encode_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, long long sW,
+                   long long sH, long long sN, int TW, int TH, int TN) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 3;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 4, (cuuint64_t)sH * 4, (cuuint64_t)sN * 4};
+  cuuint32_t box[4] = {(cuuint32_t)kConvBlockK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  LOCO_REQUIRE(((uintptr_t)base & 15) == 0, "activation base not 16B aligned");
+  LOCO_REQUIRE(strides[0] % 16 == 0 && strides[1] % 16 == 0 && strides[2] % 16 == 0,
+               "activation strides must be multiples of 16 bytes");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d N=%d)",
+               (int)r, C, W, H, N);
+  return 0;
+}
+
+int encode_w_map(CUtensorMap* m, const float* base, int Ktot, int Cout, int block_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 3;
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kConvBlockK, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  LOCO_REQUIRE(((uintptr_t)base & 15) == 0, "weight base not 16B aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d Cout=%d)", (int)r,
+               Ktot, Cout);
+  return 0;
+}
+
+void pick_box(int W, int H, int* TW, int* TH, int* TN) {
+  int tw = W < 16 ? W : 16;
+  int th = kConvBlockM / tw;
+  if (th > H) th = H;
+  *TW = tw; *TH = th; *TN = kConvBlockM / (tw * th);
+}
+
+int fill_common(ConvGemmParams& p, const ConvProblem& prob, int N, int Ho, int Wo, float* out,
+                long long osN, long long osH, long long osW, const float* add, long long asN,
+                long long asH, long long asW) {
+  LOCO_REQUIRE(prob.Kc % kConvBlockK == 0, "conv: input channels %d not a multiple of 32", prob.Kc);
+  LOCO_REQUIRE(prob.Ngemm % 32 == 0, "conv: output channels %d not a multiple of 32", prob.Ngemm);
+  p.c_chunks = prob.Kc / kConvBlockK;
+  p.block_n = prob.Ngemm % 128 == 0 ? 128 : (prob.Ngemm % 64 == 0 ? 64 : 32);
+  pick_box(Wo, Ho, &p.TW, &p.TH, &p.TN);
+  LOCO_REQUIRE(Wo % p.TW == 0 && Ho % p.TH == 0, "conv: %dx%d not tileable", Ho, Wo);
+  p.tiles_x = Wo / p.TW; p.tiles_y = Ho / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
+  p.tiles_co = prob.Ngemm / p.block_n;
+  p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = prob.Ngemm;
+  p.out = out; p.out_sN = osN; p.out_sH = osH; p.out_sW = osW;
+  p.addend = add; p.add_sN = asN; p.add_sH = asH; p.add_sW = asW;
+  p.bias = prob.bias; p.bias2 = prob.bias2; p.bias_rows = prob.bias_rows;
+  p.accumulate = prob.accumulate; p.round_out = prob.round_out;
+  LOCO_REQUIRE((osW % 4) == 0 && (osH % 4) == 0 && (osN % 4) == 0 && (((uintptr_t)out) & 15) == 0,
+               "conv: output view not float4-aligned");
+  if (add)
+    LOCO_REQUIRE((asW % 4) == 0 && (asH % 4) == 0 && (asN % 4) == 0 && (((uintptr_t)add) & 15) == 0,
+                 "conv: addend view not float4-aligned");
+  return 0;
+}
+
+}  // namespace
+
+int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
+  memset(L, 0, sizeof(*L));
+  const View& in = prob.in;
+  const View& out = prob.out;
+  const View* ad = prob.addend;
+  LOCO_REQUIRE(in.C == prob.Kc && out.C == prob.Ngemm, "conv: channel mismatch (%d/%d, %d/%d)", in.C,
+               prob.Kc, out.C, prob.Ngemm);
+  LOCO_REQUIRE(in.N == out.N, "conv: batch mismatch");
+  const int sms = num_sms();
+  if (prob.kind == CONV_3x3 || prob.kind == CONV_1x1 || prob.kind == CONV_3x3_DGRAD) {
+    LOCO_REQUIRE(in.H == out.H && in.W == out.W, "conv: stride-1 spatial mismatch");
+    ConvGemmParams& p = L->p[0];
+    LOCO_TRY(fill_common(p, prob, out.N, out.H, out.W, out.ptr, out.sN, out.sH, out.sW,
+                         ad ? ad->ptr : nullptr, ad ? ad->sN : 0, ad ? ad->sH : 0, ad ? ad->sW : 0));
+    LOCO_TRY(encode_act_map(&p.amap[0], in.ptr, in.C, in.W, in.H, in.N, in.sW, in.sH, in.sN, p.TW,
+                            p.TH, p.TN));
+    if (prob.kind == CONV_1x1) {
+      p.ntaps = 1; p.tap_map[0] = 0; p.tap_dy[0] = 0; p.tap_dx[0] = 0; p.tap_wk[0] = 0;
+    } else {
+      p.ntaps = 9;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          const int t = r * 3 + s;
+          p.tap_map[t] = 0;
+          // fprop reads x(y+r-1, x+s-1); dgrad reads dy(y-(r-1), x-(s-1))
+          p.tap_dy[t] = prob.kind == CONV_3x3 ? r - 1 : 1 - r;
+          p.tap_dx[t] = prob.kind == CONV_3x3 ? s - 1 : 1 - s;
+          p.tap_wk[t] = t * prob.Kc;
+        }
+    }
+    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, p.block_n));
+    L->nlaunch = 1;
+  } else if (prob.kind == CONV_3x3_S2) {
+    LOCO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W, "conv: stride-2 spatial mismatch");
+    ConvGemmParams& p = L->p[0];
+    LOCO_TRY(fill_common(p, prob, out.N, out.H, out.W, out.ptr, out.sN, out.sH, out.sW,
+                         ad ? ad->ptr : nullptr, ad ? ad->sN : 0, ad ? ad->sH : 0, ad ? ad->sW : 0));
+    // Four phase views of the input: x[:, pr::2, pc::2, :]
+    for (int pr = 0; pr < 2; ++pr)
+      for (int pc = 0; pc < 2; ++pc)
+        LOCO_TRY(encode_act_map(&p.amap[pr * 2 + pc], in.ptr + pr * in.sH + pc * in.sW, in.C,
+                                in.W / 2, in.H / 2, in.N, 2 * in.sW, 2 * in.sH, in.sN, p.TW, p.TH,
+                                p.TN));
+    p.ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int t = r * 3 + s;
+        // out(y,x) = sum x(2y+r, 2x+s); row 2y+r = phase (r&1), phase-row y + (r>>1)
+        p.tap_map[t] = (r & 1) * 2 + (s & 1);
+        p.tap_dy[t] = r >> 1;
+        p.tap_dx[t] = s >> 1;
+        p.tap_wk[t] = t * prob.Kc;
+      }
+    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n));
+    L->nlaunch = 1;
+  } else if (prob.kind == CONV_3x3_S2_DGRAD) {
+    // in = dy [N,h,w,Cout_fwd], out = dx [N,2h,2w,Cin_fwd]; one launch per output phase.
+    LOCO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W, "conv: stride-2 dgrad spatial mismatch");
+    LOCO_REQUIRE(ad == nullptr, "conv: stride-2 dgrad does not take an addend");
+    int li = 0;
+    for (int pr = 0; pr < 2; ++pr)
+      for (int pc = 0; pc < 2; ++pc) {
+        ConvGemmParams& p = L->p[li];
+        float* obase = out.ptr + pr * out.sH + pc * out.sW;
+        LOCO_TRY(fill_common(p, prob, out.N, in.H, in.W, obase, out.sN, 2 * out.sH, 2 * out.sW,
+                             nullptr, 0, 0, 0));
+        LOCO_TRY(encode_act_map(&p.amap[0], in.ptr, in.C, in.W, in.H, in.N, in.sW, in.sH, in.sN,
+                                p.TW, p.TH, p.TN));
+        int nt = 0;
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) {
+            if ((r & 1) != pr || (s & 1) != pc) continue;
+            // dx(2y'+pr, 2x'+pc) += W[r,s]^T dy(y' - (r-pr)/2, x' - (s-pc)/2)
+            p.tap_map[nt] = 0;
+            p.tap_dy[nt] = -((r - pr) / 2);
+            p.tap_dx[nt] = -((s - pc) / 2);
+            p.tap_wk[nt] = (r * 3 + s) * prob.Kc;
+            ++nt;
+          }
+        p.ntaps = nt;
+        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n));
+        ++li;
+      }
+    L->nlaunch = 4;
+  } else {
+    LOCO_REQUIRE(false, "conv: unknown kind %d", prob.kind);
+  }
+  for (int i = 0; i < L->nlaunch; ++i) {
+    const ConvGemmParams& p = L->p[i];
+    const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_co;
+    L->grid[i] = tiles < sms ? tiles : sms;
+    L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
+  }
+  return 0;
+}
+
+int conv_run(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  for (int i = 0; i < L.nlaunch; ++i) {
+    conv_gemm_tf32_kernel<<<L.grid[i], kThreads, kSmemBytes, stream>>>(L.p[i]);
+  }
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace loco

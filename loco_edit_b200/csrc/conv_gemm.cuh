@@ -1,0 +1,73 @@
+// Implicit-GEMM convolution on tcgen05 (sm_100a): host-side problem description.
+// One kernel serves every GEMM-shaped layer of the U-Net hot path (3x3 stride-1, 3x3 stride-2 with
+// the (0,1,0,1) pad, 1x1, and the matching data-gradient convolutions of the VJP).
+#pragma once
+#include "common.cuh"
+
+namespace loco {
+
+constexpr int kConvMaxTaps = 9;
+constexpr int kConvBlockM = 128;   // output pixels per tile (TMEM lanes)
+constexpr int kConvBlockK = 32;    // fp32 channels per pipeline stage (128-byte swizzle row)
+constexpr int kConvMaxBlockN = 128;
+
+// Device-visible parameters (passed as one __grid_constant__ struct).
+struct ConvGemmParams {
+  CUtensorMap amap[4];   // activation maps: dims (C, W, H, N); [1..3] only for stride-2 phase views
+  CUtensorMap bmap;      // packed weights: dims (Ktot, Cout), box (32, block_n)
+  int ntaps;
+  int tap_map[kConvMaxTaps];
+  int tap_dy[kConvMaxTaps];
+  int tap_dx[kConvMaxTaps];
+  int tap_wk[kConvMaxTaps];   // column offset of the tap in the packed weight matrix
+  int c_chunks;               // input channels / 32
+  int TW, TH, TN;             // pixel box (TW*TH*TN == 128)
+  int tiles_x, tiles_y, tiles_n, tiles_co;
+  int block_n;                // output channels per tile (multiple of 16, <= 128)
+  int N, Ho, Wo, Cout;        // logical output grid
+  float* out;
+  long long out_sN, out_sH, out_sW;
+  const float* addend;        // optional residual, same logical grid
+  long long add_sN, add_sH, add_sW;
+  const float* bias;          // [Cout] or null; applied to batch rows n < bias_rows
+  const float* bias2;         // second per-channel bias (timestep projection), same rule
+  int bias_rows;
+  int accumulate;             // out += result (VJP fan-in)
+  int round_out;              // round stored values to tf32
+};
+
+enum ConvKind {
+  CONV_3x3 = 0,        // stride 1, pad 1
+  CONV_1x1 = 1,
+  CONV_3x3_S2 = 2,     // stride 2, pad (0,1,0,1)  (reference: ddpm/diffusion.py:834-853)
+  CONV_3x3_DGRAD = 3,  // data gradient of CONV_3x3
+  CONV_3x3_S2_DGRAD = 4  // data gradient of CONV_3x3_S2 (four output phases, four launches)
+};
+
+struct ConvProblem {
+  int kind;
+  View in;              // activations feeding the GEMM (x for fprop, dy for dgrad)
+  View out;             // result (y for fprop, dx for dgrad)
+  const float* wpack;   // [Ngemm][ntaps_total * Kc] K-major, tf32-rounded
+  int Kc;               // channels of `in`
+  int Ngemm;            // channels of `out`
+  const float* bias = nullptr;
+  const float* bias2 = nullptr;
+  int bias_rows = 0;
+  const View* addend = nullptr;
+  int accumulate = 0;
+  int round_out = 0;
+};
+
+// A prepared launch: tensor maps encoded, grid sized. Valid while the buffers stay where they are.
+struct ConvLaunch {
+  ConvGemmParams p[4];
+  int nlaunch = 0;
+  int grid[4];
+  double flops = 0;
+};
+
+int conv_prepare(const ConvProblem& prob, ConvLaunch* out);
+int conv_run(const ConvLaunch& l, cudaStream_t stream);
+
+}  // namespace loco

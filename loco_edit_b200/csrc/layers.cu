@@ -1,0 +1,601 @@
+// Bandwidth-bound layer kernels: see layers.cuh.  All activations are channels-last fp32; every
+// kernel moves 16-byte vectors with consecutive threads on consecutive channels (coalesced), does
+// its group reductions with shared-memory + one double atomic per (row, group, block), and sizes
+// its grid from the tensor so large layers launch many waves over the 148 SMs.
+#include "layers.cuh"
+#include <math.h>
+
+namespace loco {
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float u) { return 1.0f / (1.0f + expf(-u)); }
+__device__ __forceinline__ float silu_f(float u) { return u * sigmoidf_(u); }
+// d/du [u * sigmoid(u)]
+__device__ __forceinline__ float silu_grad(float u) {
+  const float s = sigmoidf_(u);
+  return s * (1.0f + u * (1.0f - s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_fprop_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout,
+                                  int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int t = (int)((i / Cin) % taps);
+    const int co = (int)(i / ((long long)Cin * taps));
+    dst[i] = round_tf32(w[((long long)co * Cin + ci) * taps + t]);
+  }
+}
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout,
+                                  int Cin, int taps, int cout_total, int co_off) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int t = (int)((i / Cout) % taps);
+    const int ci = (int)(i / ((long long)Cout * taps));
+    dst[((long long)ci * taps + t) * cout_total + co_off + co] =
+        round_tf32(w[((long long)co * Cin + ci) * taps + t]);
+  }
+}
+__global__ void pack_edge_kernel(const float* __restrict__ w, float* __restrict__ dst, int C,
+                                 int in_is_3) {
+  const int total = 9 * 3 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int j = (i / C) % 3;
+    const int t = i / (3 * C);
+    // conv_in: w[c][j][t]; conv_out: w[j][c][t]
+    dst[i] = in_is_3 ? w[(c * 3 + j) * 9 + t] : w[(j * C + c) * 9 + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge convolutions
+// ------------------------------------------------------------------------------------------------
+__global__ void edge_expand_kernel(const float* __restrict__ in3, const float* __restrict__ We,
+                                   const float* __restrict__ bias, int bias_rows, View out,
+                                   int flip, int round_out) {
+  extern __shared__ float sw[];   // [27][C]
+  const int C = out.C, H = out.H, W = out.W;
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = We[i];
+  __syncthreads();
+  const int cvn = C >> 2;
+  const int ppb = blockDim.x / cvn;
+  const int cv = threadIdx.x % cvn;
+  const long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cvn;
+  const int n = blockIdx.y;
+  if (pix >= (long long)H * W) return;
+  const int y = (int)(pix / W), x = (int)(pix % W);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias && n < bias_rows) acc = *reinterpret_cast<const float4*>(bias + cv * 4);
+  const float* src = in3 + (long long)n * 3 * H * W;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + (flip ? 1 - r : r - 1);
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x + (flip ? 1 - s : s - 1);
+      if (xx < 0 || xx >= W) continue;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float v = __ldg(src + ((long long)j * H + yy) * W + xx);
+        const float4 w = *reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + j) * C + cv * 4]);
+        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y);
+        acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+      }
+    }
+  }
+  if (round_out) {
+    acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y);
+    acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
+  }
+  *reinterpret_cast<float4*>(out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4) = acc;
+}
+
+// One warp per output pixel; lanes stride over channels, three warp reductions per pixel.
+__global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
+                                   const float* __restrict__ bias, int bias_rows,
+                                   float* __restrict__ out3, int flip) {
+  extern __shared__ float sw[];   // [27][C]
+  const int C = in.C, H = in.H, W = in.W;
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = Wr[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int n = blockIdx.y;
+  if (pix >= (long long)H * W) return;
+  const int y = (int)(pix / W), x = (int)(pix % W);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + (flip ? 1 - r : r - 1);
+    if (yy < 0 || yy >= H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x + (flip ? 1 - s : s - 1);
+      if (xx < 0 || xx >= W) continue;
+      const float* src = in.ptr + n * in.sN + yy * in.sH + xx * in.sW;
+      const float* w = &sw[(r * 3 + s) * 3 * C];
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + C + c);
+        const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * C + c);
+        a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+        a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+        a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+      }
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) {
+    const bool ub = bias && n < bias_rows;
+    float* dst = out3 + (long long)n * 3 * H * W + (long long)y * W + x;
+    dst[0] = a0 + (ub ? bias[0] : 0.f);
+    dst[(long long)H * W] = a1 + (ub ? bias[1] : 0.f);
+    dst[2LL * H * W] = a2 + (ub ? bias[2] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+constexpr int kGroups = 32;
+constexpr int kGnVecPerThread = 16;
+
+__host__ __device__ inline int gn_block_dim(int C) { return (256 % (C / 4) == 0) ? 256 : 192; }
+
+struct GnGeom {
+  int block, ppb_step, ppb, nblk;
+};
+inline GnGeom gn_geom(int C, long long HW) {
+  GnGeom g;
+  g.block = gn_block_dim(C);
+  g.ppb_step = g.block / (C / 4);
+  g.ppb = g.ppb_step * kGnVecPerThread;
+  g.nblk = (int)((HW + g.ppb - 1) / g.ppb);
+  return g;
+}
+
+// mode 0: forward/JVP statistics; mode 1: VJP statistics.
+template <int MODE>
+__global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float eps, int silu, double* __restrict__ stats, int ppb) {
+  __shared__ float red[kGroups][2];
+  const int C = x.C;
+  const int cvn = C >> 2;
+  const int cg = C / kGroups;
+  const int cv = threadIdx.x % cvn;
+  const int prow = threadIdx.x / cvn;
+  const int pstep = blockDim.x / cvn;
+  const int g = (cv * 4) / cg;
+  const int n = blockIdx.y;
+  const long long HW = (long long)x.H * x.W;
+  const long long p0 = (long long)blockIdx.x * ppb;
+  const long long p1 = min(HW, p0 + ppb);
+  if (threadIdx.x < kGroups * 2) (&red[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  float s1 = 0.f, s2 = 0.f;
+  if (MODE == 0) {
+    const bool primal = n < n_primal;
+    for (long long p = p0 + prow; p < p1; p += pstep) {
+      const int y = (int)(p / x.W), xx = (int)(p % x.W);
+      const long long off = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
+      const float4 v = *reinterpret_cast<const float4*>(x.ptr + n * x.sN + off);
+      if (primal) {
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      } else {
+        const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + off);
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * x0.x + v.y * x0.y) + (v.z * x0.z + v.w * x0.w);
+      }
+    }
+  } else {
+    const double cnt = (double)HW * cg;
+    const double mu_d = pstats[g * 2] / cnt;
+    const double var_d = pstats[g * 2 + 1] / cnt - mu_d * mu_d;
+    const float mu = (float)mu_d;
+    const float rstd = (float)(1.0 / sqrt((var_d > 0 ? var_d : 0) + (double)eps));
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
+    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
+    for (long long p = p0 + prow; p < p1; p += pstep) {
+      const int y = (int)(p / x.W), xx = (int)(p % x.W);
+      const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + (long long)y * x.sH +
+                                                         (long long)xx * x.sW + cv * 4);
+      const float4 d = *reinterpret_cast<const float4*>(gy.ptr + n * gy.sN + (long long)y * gy.sH +
+                                                        (long long)xx * gy.sW + cv * 4);
+      float a[4];
+      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+      const float ds[4] = {d.x, d.y, d.z, d.w};
+      const float gs[4] = {ga.x, ga.y, ga.z, ga.w};
+      const float bs[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float u = gs[i] * ((xs[i] - mu) * rstd) + bs[i];
+        a[i] = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];
+        s1 += a[i];
+        s2 += a[i] * xs[i];
+      }
+    }
+  }
+  atomicAdd(&red[g][0], s1);
+  atomicAdd(&red[g][1], s2);
+  __syncthreads();
+  if (threadIdx.x < kGroups * 2) {
+    const float v = (&red[0][0])[threadIdx.x];
+    atomicAdd(&stats[(long long)n * kGroups * 2 + threadIdx.x], (double)v);
+  }
+}
+
+// mode 0: forward/JVP apply; mode 1: VJP apply.
+template <int MODE>
+__global__ void gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
+                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu, int round_out,
+                                const float* __restrict__ addend, long long add_sN, long long add_sH,
+                                long long add_sW, int accumulate, View out, int ppb) {
+  const int C = x.C;
+  const int cvn = C >> 2;
+  const int cg = C / kGroups;
+  const int cv = threadIdx.x % cvn;
+  const int prow = threadIdx.x / cvn;
+  const int pstep = blockDim.x / cvn;
+  const int g = (cv * 4) / cg;
+  const int n = blockIdx.y;
+  const long long HW = (long long)x.H * x.W;
+  const long long p0 = (long long)blockIdx.x * ppb;
+  const long long p1 = min(HW, p0 + ppb);
+  const double cnt = (double)HW * cg;
+
+  const bool primal = (MODE == 0) && (n < n_primal);
+  // statistics of the primal row this thread normalises against
+  const double* ps = (MODE == 0) ? stats + (long long)(primal ? n : 0) * kGroups * 2 : pstats;
+  const double mu_d = ps[g * 2] / cnt;
+  const double var_d = ps[g * 2 + 1] / cnt - mu_d * mu_d;
+  const float mu = (float)mu_d;
+  const float rstd = (float)(1.0 / sqrt((var_d > 0 ? var_d : 0) + (double)eps));
+  float m1 = 0.f, m2 = 0.f;
+  if (!primal) {
+    const double* ts = stats + (long long)n * kGroups * 2;
+    const double sa = ts[g * 2], sxa = ts[g * 2 + 1];
+    m1 = (float)(sa / cnt);
+    m2 = (float)((sxa - mu_d * sa) * (double)rstd / cnt);
+  }
+  const float4 ga4 = *reinterpret_cast<const float4*>(gamma + cv * 4);
+  const float4 be4 = *reinterpret_cast<const float4*>(beta + cv * 4);
+  const float gs[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float bs[4] = {be4.x, be4.y, be4.z, be4.w};
+
+  for (long long p = p0 + prow; p < p1; p += pstep) {
+    const int y = (int)(p / x.W), xx = (int)(p % x.W);
+    const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
+    float r[4];
+    if (MODE == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(x.ptr + n * x.sN + xoff);
+      const float vs[4] = {v.x, v.y, v.z, v.w};
+      if (primal) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float u = gs[i] * ((vs[i] - mu) * rstd) + bs[i];
+          r[i] = silu ? silu_f(u) : u;
+        }
+      } else {
+        const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + xoff);
+        const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xh = (xs[i] - mu) * rstd;
+          const float u = gs[i] * xh + bs[i];
+          const float dact = silu ? silu_grad(u) : 1.0f;
+          r[i] = dact * gs[i] * rstd * (vs[i] - m1 - xh * m2);
+        }
+      }
+    } else {
+      const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + xoff);
+      const float4 d = *reinterpret_cast<const float4*>(gy.ptr + n * gy.sN + (long long)y * gy.sH +
+                                                        (long long)xx * gy.sW + cv * 4);
+      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+      const float ds[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xh = (xs[i] - mu) * rstd;
+        const float u = gs[i] * xh + bs[i];
+        const float a = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];
+        r[i] = rstd * (a - m1 - xh * m2);
+      }
+    }
+    float* optr = out.ptr + n * out.sN + (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
+    if (addend) {
+      const float4 a = *reinterpret_cast<const float4*>(addend + n * add_sN + (long long)y * add_sH +
+                                                        (long long)xx * add_sW + cv * 4);
+      r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
+    }
+    if (accumulate) {
+      const float4 a = *reinterpret_cast<const float4*>(optr);
+      r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
+    }
+    if (round_out) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = round_tf32(r[i]);
+    }
+    *reinterpret_cast<float4*>(optr) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resampling / add
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(View in, View out) {
+  const int cvn = out.C >> 2;
+  const long long total = (long long)out.N * out.H * out.W * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int x = (int)(r % out.W); r /= out.W;
+    const int y = (int)(r % out.H);
+    const int n = (int)(r / out.H);
+    const float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + (y >> 1) * in.sH +
+                                                      (x >> 1) * in.sW + cv * 4);
+    *reinterpret_cast<float4*>(out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4) = v;
+  }
+}
+__global__ void sumpool2x_kernel(View in, View out, int accumulate) {
+  const int cvn = out.C >> 2;
+  const long long total = (long long)out.N * out.H * out.W * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int x = (int)(r % out.W); r /= out.W;
+    const int y = (int)(r % out.H);
+    const int n = (int)(r / out.H);
+    const float* b = in.ptr + n * in.sN + (2 * y) * in.sH + (2 * x) * in.sW + cv * 4;
+    const float4 a = *reinterpret_cast<const float4*>(b);
+    const float4 c = *reinterpret_cast<const float4*>(b + in.sW);
+    const float4 d = *reinterpret_cast<const float4*>(b + in.sH);
+    const float4 e = *reinterpret_cast<const float4*>(b + in.sH + in.sW);
+    float4 v = make_float4((a.x + c.x) + (d.x + e.x), (a.y + c.y) + (d.y + e.y),
+                           (a.z + c.z) + (d.z + e.z), (a.w + c.w) + (d.w + e.w));
+    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    if (accumulate) {
+      const float4 p = *reinterpret_cast<const float4*>(o);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    *reinterpret_cast<float4*>(o) = v;
+  }
+}
+__global__ void add_views_kernel(View in, View out, int accumulate) {
+  const int cvn = out.C >> 2;
+  const long long total = (long long)out.N * out.H * out.W * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int x = (int)(r % out.W); r /= out.W;
+    const int y = (int)(r % out.H);
+    const int n = (int)(r / out.H);
+    float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + y * in.sH + x * in.sW + cv * 4);
+    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    if (accumulate) {
+      const float4 p = *reinterpret_cast<const float4*>(o);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    *reinterpret_cast<float4*>(o) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Timestep embedding
+// ------------------------------------------------------------------------------------------------
+// One block. scratch: [0,4ch) = silu(dense0(emb)), [4ch,8ch) = silu(dense1(.)) = temb_act.
+__global__ void temb_kernel(float t, int ch, const float* __restrict__ w0,
+                            const float* __restrict__ b0, const float* __restrict__ w1,
+                            const float* __restrict__ b1, float* __restrict__ scratch) {
+  extern __shared__ float sm[];   // emb[ch] + h[4ch]
+  float* emb = sm;
+  float* h = sm + ch;
+  const int half = ch / 2;
+  const int tch = 4 * ch;
+  const float coef = -(float)(log(10000.0) / (double)(half - 1));
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float w = expf((float)i * coef);
+    const float a = t * w;
+    emb[i] = sinf(a);
+    emb[half + i] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < tch; o += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < ch; i += 32) acc += w0[(long long)o * ch + i] * emb[i];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = silu_f(acc + b0[o]);
+      h[o] = v;
+      scratch[o] = v;
+    }
+  }
+  __syncthreads();
+  for (int o = warp; o < tch; o += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < tch; i += 32) acc += w1[(long long)o * tch + i] * h[i];
+    acc = warp_sum(acc);
+    if (lane == 0) scratch[tch + o] = silu_f(acc + b1[o]);
+  }
+}
+// out[c] = b[c] + W[c,:] . temb_act   (one warp per output)
+__global__ void temb_project_kernel(const float* __restrict__ temb_act, int temb_ch,
+                                    const float* __restrict__ w, const float* __restrict__ b,
+                                    int cout, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= cout) return;
+  float acc = 0.f;
+  for (int i = lane; i < temb_ch; i += 32) acc += w[(long long)o * temb_ch + i] * temb_act[i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[o] = acc + b[o];
+}
+
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int check_gn_view(const View& v, const char* what) {
+  LOCO_REQUIRE(v.C % 128 == 0, "%s: channels %d must be a multiple of 128", what, v.C);
+  LOCO_REQUIRE(v.C <= 1024, "%s: channels %d > 1024", what, v.C);
+  LOCO_REQUIRE((v.sW % 4) == 0 && (v.sH % 4) == 0 && (v.sN % 4) == 0 &&
+                   (((uintptr_t)v.ptr) & 15) == 0,
+               "%s: view not float4-aligned", what);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host launchers
+// ------------------------------------------------------------------------------------------------
+int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * kh * kw;
+  pack_fprop_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int kw, int cout_total,
+                    int co_off, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * kh * kw;
+  pack_dgrad_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw, cout_total,
+                                                        co_off);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t s) {
+  pack_edge_kernel<<<grid_for(27 * C, 256), 256, 0, s>>>(w, dst, C, in_is_3);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int edge_conv_expand(const float* in3, const float* We, const float* bias, int bias_rows, View out,
+                     int flip, int round_out, cudaStream_t s) {
+  LOCO_REQUIRE(out.C % 4 == 0 && 256 % (out.C / 4) == 0, "edge_conv_expand: C=%d unsupported", out.C);
+  const int ppb = 256 / (out.C / 4);
+  const long long HW = (long long)out.H * out.W;
+  dim3 grid((unsigned)((HW + ppb - 1) / ppb), out.N);
+  const size_t smem = 27 * out.C * sizeof(float);
+  LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_expand: C=%d too large", out.C);
+  edge_expand_kernel<<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3,
+                     int flip, cudaStream_t s) {
+  LOCO_REQUIRE(in.C % 4 == 0, "edge_conv_reduce: C=%d unsupported", in.C);
+  const long long HW = (long long)in.H * in.W;
+  dim3 grid((unsigned)((HW + 7) / 8), in.N);
+  const size_t smem = 27 * in.C * sizeof(float);
+  LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_reduce: C=%d too large", in.C);
+  edge_reduce_kernel<<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
+  LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
+  dim3 grid(g.nblk, x.N);
+  gn_stats_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
+                                              stats, g.ppb);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, const float* beta,
+                 float eps, int silu, int round_out, View y, cudaStream_t s) {
+  LOCO_TRY(check_gn_view(x, "gn_apply_fwd"));
+  LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
+  dim3 grid(g.nblk, x.N);
+  gn_apply_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps, silu,
+                                              round_out, nullptr, 0, 0, 0, 0, y, g.ppb);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, const float* beta,
+                 float eps, int silu, double* stats, cudaStream_t s) {
+  LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
+  LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
+  dim3 grid(g.nblk, gy.N);
+  gn_stats_kernel<1><<<grid, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats,
+                                              g.ppb);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, const float* gamma,
+                 const float* beta, float eps, int silu, const View* addend, int accumulate,
+                 int round_out, View gx, cudaStream_t s) {
+  LOCO_TRY(check_gn_view(xp, "gn_apply_vjp"));
+  LOCO_TRY(check_gn_view(gy, "gn_apply_vjp(gy)"));
+  LOCO_TRY(check_gn_view(gx, "gn_apply_vjp(gx)"));
+  if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
+  dim3 grid(g.nblk, gy.N);
+  gn_apply_kernel<1><<<grid, g.block, 0, s>>>(
+      xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
+      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx,
+      g.ppb);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upsample2x(View in, View out, cudaStream_t s) {
+  LOCO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && out.N == in.N,
+               "upsample2x: shape mismatch");
+  const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int sumpool2x(View in, View out, int accumulate, cudaStream_t s) {
+  LOCO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W && out.C == in.C && out.N == in.N,
+               "sumpool2x: shape mismatch");
+  const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
+  sumpool2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int add_views(View in, View out, int accumulate, cudaStream_t s) {
+  LOCO_REQUIRE(in.H == out.H && in.W == out.W && out.C == in.C && out.N == in.N,
+               "add_views: shape mismatch");
+  const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
+  add_views_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int temb_forward(float t, int ch, const float* w0, const float* b0, const float* w1, const float* b1,
+                 float* scratch, cudaStream_t s) {
+  const size_t smem = (size_t)(ch + 4 * ch) * sizeof(float);
+  temb_kernel<<<1, 512, smem, s>>>(t, ch, w0, b0, w1, b1, scratch);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int temb_project(const float* temb_act, int temb_ch, const float* w, const float* b, int cout,
+                 float* out, cudaStream_t s) {
+  temb_project_kernel<<<(cout + 7) / 8, 256, 0, s>>>(temb_act, temb_ch, w, b, cout, out);
+  LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace loco

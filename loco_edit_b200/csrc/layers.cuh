@@ -1,0 +1,60 @@
+// Bandwidth-bound layer kernels of the U-Net hot path (GroupNorm/SiLU and their JVP/VJP, edge
+// convolutions with 3 channels on one side, resampling, timestep embedding, weight packing).
+#pragma once
+#include "common.cuh"
+
+namespace loco {
+
+// ---- weight packing (done once when parameters are loaded) ----
+// torch conv weight [Cout][Cin][kh][kw] -> GEMM operand [Cout][(r*kw+s)*Cin + ci], tf32-rounded.
+int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+// torch conv weight [Cout][Cin][kh][kw] -> data-gradient operand [Cin][(r*kw+s)*Cout + co].
+// cout_total/co_off place the block inside a wider fused operand (q|k|v): row length is
+// kh*kw*cout_total and this weight fills columns [co_off, co_off+Cout) of every tap.
+int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int kw, int cout_total,
+                    int co_off, cudaStream_t s);
+// 3-channel edge convolutions: -> [9][3][C].  in_is_3: weight is [C][3][3][3] (conv_in), else
+// [3][C][3][3] (conv_out).  Kept in full fp32 (these run on CUDA cores).
+int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t s);
+
+// ---- 3-channel edge convolutions (NCHW <-> channels-last boundary of the network) ----
+// out[n,y,x,c] = bias[c]*(n<bias_rows) + sum_{tap,j} We[tap][j][c] * in3[n,j,y+dy,x+dx];
+// flip = 0: (dy,dx) = (r-1,s-1) (conv_in forward); flip = 1: (1-r,1-s) (conv_out data gradient).
+int edge_conv_expand(const float* in3_nchw, const float* We, const float* bias, int bias_rows,
+                     View out, int flip, int round_out, cudaStream_t s);
+// out3[n,j,y,x] = bias[j]*(n<bias_rows) + sum_{tap,c} Wr[tap][j][c] * in[n,y+dy,x+dx,c];
+// flip = 0: conv_out forward; flip = 1: conv_in data gradient.
+int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3_nchw,
+                     int flip, cudaStream_t s);
+
+// ---- GroupNorm(32 groups) + optional SiLU: forward, JVP and VJP ----
+// stats layout: double [rows][32][2].
+// Forward/JVP: rows < n_primal accumulate (sum x, sum x^2); tangent rows (sum dx, sum x0*dx) with
+// x0 = primal row 0.  (reference: Normalize/nonlinearity, ddpm/diffusion.py:806-811)
+int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s);
+int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, const float* beta,
+                 float eps, int silu, int round_out, View y, cudaStream_t s);
+// VJP: xp = saved primal input (1 row), pstats = its (sum x, sum x^2); gy = k cotangent rows of the
+// layer output.  a = gamma * act'(u) * gy;  stats rows accumulate (sum a, sum x*a).
+int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, const float* beta,
+                 float eps, int silu, double* stats, cudaStream_t s);
+// gx (+)= rstd * (a - mean(a) - xhat * mean(xhat a)) + addend
+int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, const float* gamma,
+                 const float* beta, float eps, int silu, const View* addend, int accumulate,
+                 int round_out, View gx, cudaStream_t s);
+
+// ---- resampling ----
+int upsample2x(View in, View out, cudaStream_t s);                 // nearest, out = 2H x 2W
+int sumpool2x(View in, View out, int accumulate, cudaStream_t s);  // VJP of upsample2x
+// out (+)= in   (cotangent fan-in where no producing kernel can fuse it)
+int add_views(View in, View out, int accumulate, cudaStream_t s);
+
+// ---- timestep embedding (reference: get_timestep_embedding + temb.dense, ddpm/diffusion.py:
+// 154-157, 783-804): temb_act = silu(dense1(silu(dense0([sin(t w), cos(t w)])))), then every
+// ResnetBlock's temb_proj Linear(temb_ch -> Cout) evaluated into one packed vector.
+int temb_forward(float t, int ch, const float* w0, const float* b0, const float* w1,
+                 const float* b1, float* scratch /*2*4ch*/, cudaStream_t s);
+int temb_project(const float* temb_act, int temb_ch, const float* w, const float* b, int cout,
+                 float* out, cudaStream_t s);
+
+}  // namespace loco

@@ -1,0 +1,699 @@
+// DDPM U-Net executor: builds static forward / JVP / VJP launch programs (see unet.cuh).
+//
+// Data layout in HBM
+//   * every activation is channels-last fp32 [N, H, W, C]; N stacks the primal rows and the k probe
+//     tangents (forward/JVP program) or the k cotangents (VJP program);
+//   * the skip-connection concat of the decoder is never materialised: each up ResnetBlock owns one
+//     buffer [N, H, W, C_dec + C_skip]; the encoder writes its skip tensor straight into the
+//     channel slice, the decoder writes the other slice; cotangents use the same geometry;
+//   * all buffers live in one caller-provided workspace; every op output has its own region (the
+//     primal rows are what the VJP program re-reads, 180 GB of HBM make recycling unnecessary).
+#include "unet.cuh"
+#include <deque>
+#include <functional>
+#include <stdarg.h>
+
+namespace loco {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing / device info
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Model: parameter registry mirroring the reference module tree (ddpm/diffusion.py:24-126)
+// ------------------------------------------------------------------------------------------------
+size_t Model::alloc(size_t n) {
+  const size_t off = arena_floats;
+  arena_floats += (n + 63) & ~(size_t)63;
+  return off;
+}
+int Model::add_slot(ParamSlot s) {
+  s.numel = 1;
+  for (int d : s.shape) s.numel *= d;
+  slot_index[s.name] = (int)slots.size();
+  slots.push_back(s);
+  return (int)slots.size() - 1;
+}
+ConvRef Model::add_conv(const std::string& prefix, int cin, int cout, int ksz) {
+  ConvRef c;
+  c.cin = cin; c.cout = cout; c.ksz = ksz;
+  c.wf = alloc((size_t)cout * cin * ksz * ksz);
+  c.wd = alloc((size_t)cout * cin * ksz * ksz);
+  c.bias = alloc(cout);
+  ParamSlot w;
+  w.name = prefix + ".weight"; w.shape = {cout, cin, ksz, ksz}; w.kind = ParamSlot::CONV_GEMM;
+  w.off_a = c.wf; w.off_b = c.wd; w.cout = cout; w.cin = cin; w.ksz = ksz;
+  w.row_off = 0; w.rows_total = cout;
+  add_slot(w);
+  ParamSlot b;
+  b.name = prefix + ".bias"; b.shape = {cout}; b.kind = ParamSlot::RAW; b.off_a = c.bias;
+  add_slot(b);
+  return c;
+}
+NormRef Model::add_norm(const std::string& prefix, int C) {
+  NormRef n;
+  n.C = C; n.gamma = alloc(C); n.beta = alloc(C);
+  ParamSlot g; g.name = prefix + ".weight"; g.shape = {C}; g.kind = ParamSlot::RAW; g.off_a = n.gamma;
+  add_slot(g);
+  ParamSlot b; b.name = prefix + ".bias"; b.shape = {C}; b.kind = ParamSlot::RAW; b.off_a = n.beta;
+  add_slot(b);
+  return n;
+}
+ResRef Model::add_res(const std::string& prefix, int cin, int cout) {
+  ResRef r;
+  r.cin = cin; r.cout = cout;
+  r.n1 = add_norm(prefix + ".norm1", cin);
+  r.c1 = add_conv(prefix + ".conv1", cin, cout, 3);
+  r.temb_off = tproj_rows;
+  tproj_rows += cout;
+  {
+    // rows of the stacked projection matrix; arena offsets are fixed up after construction
+    ParamSlot w; w.name = prefix + ".temb_proj.weight"; w.shape = {cout, arch.ch * 4};
+    w.kind = ParamSlot::RAW; w.off_a = (size_t)r.temb_off; w.cout = -1;   // marker: temb matrix row
+    add_slot(w);
+    ParamSlot b; b.name = prefix + ".temb_proj.bias"; b.shape = {cout}; b.kind = ParamSlot::RAW;
+    b.off_a = (size_t)r.temb_off; b.cout = -2;                            // marker: temb bias row
+    add_slot(b);
+  }
+  r.n2 = add_norm(prefix + ".norm2", cout);
+  r.c2 = add_conv(prefix + ".conv2", cout, cout, 3);
+  r.has_nin = cin != cout;
+  if (r.has_nin) r.nin = add_conv(prefix + ".nin_shortcut", cin, cout, 1);
+  return r;
+}
+AttnRef Model::add_attn(const std::string& prefix, int C) {
+  AttnRef a;
+  a.C = C;
+  a.n = add_norm(prefix + ".norm", C);
+  a.qkv.cin = C; a.qkv.cout = 3 * C; a.qkv.ksz = 1;
+  a.qkv.wf = alloc((size_t)3 * C * C);
+  a.qkv.wd = alloc((size_t)3 * C * C);
+  a.qkv.bias = alloc(3 * C);
+  const char* names[3] = {"q", "k", "v"};
+  for (int i = 0; i < 3; ++i) {
+    ParamSlot w;
+    w.name = prefix + "." + names[i] + ".weight"; w.shape = {C, C, 1, 1}; w.kind = ParamSlot::CONV_QKV;
+    w.off_a = a.qkv.wf; w.off_b = a.qkv.wd; w.cout = C; w.cin = C; w.ksz = 1;
+    w.row_off = i * C; w.rows_total = 3 * C;
+    add_slot(w);
+    ParamSlot b;
+    b.name = prefix + "." + names[i] + ".bias"; b.shape = {C}; b.kind = ParamSlot::BIAS_QKV;
+    b.off_a = a.qkv.bias; b.row_off = i * C;
+    add_slot(b);
+  }
+  a.proj = add_conv(prefix + ".proj_out", C, C, 1);
+  return a;
+}
+
+static bool in_list(const int* lst, int n, int v) {
+  for (int i = 0; i < n; ++i)
+    if (lst[i] == v) return true;
+  return false;
+}
+
+Model::Model(const Arch& a) : arch(a) {
+  const int ch = a.ch, temb_ch = 4 * a.ch, L = a.n_levels;
+  temb_w0 = alloc((size_t)temb_ch * ch); temb_b0 = alloc(temb_ch);
+  temb_w1 = alloc((size_t)temb_ch * temb_ch); temb_b1 = alloc(temb_ch);
+  {
+    ParamSlot s;
+    s.kind = ParamSlot::RAW;
+    s.name = "temb.dense.0.weight"; s.shape = {temb_ch, ch}; s.off_a = temb_w0; add_slot(s);
+    s.name = "temb.dense.0.bias"; s.shape = {temb_ch}; s.off_a = temb_b0; add_slot(s);
+    s.name = "temb.dense.1.weight"; s.shape = {temb_ch, temb_ch}; s.off_a = temb_w1; add_slot(s);
+    s.name = "temb.dense.1.bias"; s.shape = {temb_ch}; s.off_a = temb_b1; add_slot(s);
+  }
+  conv_in_w = alloc(27 * ch); conv_in_b = alloc(ch);
+  {
+    ParamSlot s;
+    s.name = "conv_in.weight"; s.shape = {ch, a.in_ch, 3, 3}; s.kind = ParamSlot::CONV_EDGE_IN;
+    s.off_a = conv_in_w; s.cout = ch; add_slot(s);
+    ParamSlot b; b.name = "conv_in.bias"; b.shape = {ch}; b.kind = ParamSlot::RAW; b.off_a = conv_in_b;
+    add_slot(b);
+  }
+  int curr_res = a.resolution;
+  int block_in = ch;
+  down_res.resize(L); down_attn.resize(L); down_sample.resize(L);
+  up_res.resize(L); up_attn.resize(L); up_sample.resize(L);
+  for (int l = 0; l < L; ++l) {
+    block_in = ch * (l == 0 ? 1 : a.ch_mult[l - 1]);
+    const int block_out = ch * a.ch_mult[l];
+    for (int b = 0; b < a.num_res_blocks; ++b) {
+      const std::string p = "down." + std::to_string(l) + ".block." + std::to_string(b);
+      down_res[l].push_back(add_res(p, block_in, block_out));
+      block_in = block_out;
+      if (in_list(a.attn_resolutions, a.n_attn, curr_res))
+        down_attn[l].push_back(
+            add_attn("down." + std::to_string(l) + ".attn." + std::to_string(b), block_in));
+    }
+    if (l != L - 1) {
+      down_sample[l] = add_conv("down." + std::to_string(l) + ".downsample.conv", block_in, block_in, 3);
+      curr_res /= 2;
+    }
+  }
+  mid1 = add_res("mid.block_1", block_in, block_in);
+  mid_attn = add_attn("mid.attn_1", block_in);
+  mid2 = add_res("mid.block_2", block_in, block_in);
+  for (int l = L - 1; l >= 0; --l) {
+    const int block_out = ch * a.ch_mult[l];
+    int skip_in = ch * a.ch_mult[l];
+    for (int b = 0; b < a.num_res_blocks + 1; ++b) {
+      if (b == a.num_res_blocks) skip_in = ch * (l == 0 ? 1 : a.ch_mult[l - 1]);
+      const std::string p = "up." + std::to_string(l) + ".block." + std::to_string(b);
+      up_res[l].push_back(add_res(p, block_in + skip_in, block_out));
+      block_in = block_out;
+      if (in_list(a.attn_resolutions, a.n_attn, curr_res))
+        up_attn[l].push_back(
+            add_attn("up." + std::to_string(l) + ".attn." + std::to_string(b), block_in));
+    }
+    if (l != 0) {
+      up_sample[l] = add_conv("up." + std::to_string(l) + ".upsample.conv", block_in, block_in, 3);
+      curr_res *= 2;
+    }
+  }
+  norm_out = add_norm("norm_out", block_in);
+  conv_out_w = alloc(27 * block_in); conv_out_b = alloc(64);
+  {
+    ParamSlot s;
+    s.name = "conv_out.weight"; s.shape = {a.out_ch, block_in, 3, 3}; s.kind = ParamSlot::CONV_EDGE_OUT;
+    s.off_a = conv_out_w; s.cin = block_in; add_slot(s);
+    ParamSlot b; b.name = "conv_out.bias"; b.shape = {a.out_ch}; b.kind = ParamSlot::RAW;
+    b.off_a = conv_out_b; add_slot(b);
+  }
+  // stacked timestep projections
+  tproj_w = alloc((size_t)tproj_rows * temb_ch);
+  tproj_b = alloc(tproj_rows);
+  for (auto& s : slots) {
+    if (s.kind == ParamSlot::RAW && s.cout == -1) s.off_a = tproj_w + s.off_a * (size_t)temb_ch;
+    if (s.kind == ParamSlot::RAW && s.cout == -2) s.off_a = tproj_b + s.off_a;
+  }
+}
+
+int Model::load_param(const char* name, const float* src, long long numel, cudaStream_t s) {
+  LOCO_REQUIRE(arena != nullptr, "load_param: weight arena not bound");
+  auto it = slot_index.find(name);
+  LOCO_REQUIRE(it != slot_index.end(), "load_param: unknown parameter '%s'", name);
+  ParamSlot& sl = slots[it->second];
+  LOCO_REQUIRE(sl.numel == numel, "load_param: '%s' expects %lld elements, got %lld", name, sl.numel,
+               numel);
+  switch (sl.kind) {
+    case ParamSlot::RAW:
+      LOCO_CHECK_CUDA(cudaMemcpyAsync(w(sl.off_a), src, sizeof(float) * numel,
+                                      cudaMemcpyDeviceToDevice, s));
+      break;
+    case ParamSlot::BIAS_QKV:
+      LOCO_CHECK_CUDA(cudaMemcpyAsync(w(sl.off_a) + sl.row_off, src, sizeof(float) * numel,
+                                      cudaMemcpyDeviceToDevice, s));
+      break;
+    case ParamSlot::CONV_GEMM:
+    case ParamSlot::CONV_QKV:
+      LOCO_TRY(pack_conv_fprop(src, w(sl.off_a) + (size_t)sl.row_off * sl.cin * sl.ksz * sl.ksz,
+                               sl.cout, sl.cin, sl.ksz, sl.ksz, s));
+      LOCO_TRY(pack_conv_dgrad(src, w(sl.off_b), sl.cout, sl.cin, sl.ksz, sl.ksz, sl.rows_total,
+                               sl.row_off, s));
+      break;
+    case ParamSlot::CONV_EDGE_IN:
+      LOCO_TRY(pack_conv_edge(src, w(sl.off_a), sl.cout, 1, s));
+      break;
+    case ParamSlot::CONV_EDGE_OUT:
+      LOCO_TRY(pack_conv_edge(src, w(sl.off_a), sl.cin, 0, s));
+      break;
+  }
+  sl.loaded = true;
+  return 0;
+}
+
+int Model::check_loaded() const {
+  for (const auto& s : slots) LOCO_REQUIRE(s.loaded, "parameter '%s' was never loaded", s.name.c_str());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plan
+// ------------------------------------------------------------------------------------------------
+typedef std::function<int(cudaStream_t)> Fn;
+
+struct TH {                 // a forward tensor and the cotangent buffer that mirrors it
+  View v;                   // [NP+NT, H, W, C]
+  View g;                   // [NC, H, W, C]
+  std::vector<int> ids;     // cotangent region ids (two for a full concat buffer)
+};
+
+struct Plan::Impl {
+  // call-time arguments read by the closures
+  const float* cur_x = nullptr;
+  float cur_t = 0.f;
+  float* cur_eps = nullptr;
+  const float* cur_geps = nullptr;
+  float* cur_gx = nullptr;
+
+  std::vector<Fn> fwd;
+  std::vector<std::vector<Fn>> bwd_groups;
+  std::vector<Fn> bwd;      // flattened in execution order
+  std::deque<ConvLaunch> launches;
+
+  // region sizes (floats) from the dry run
+  size_t act_floats = 0, fstat_floats = 0, bstat_floats = 0;
+  bool sized = false;
+  // cotangent writer bookkeeping
+  struct Writer { std::vector<int> ids; int group, pos; };
+  std::vector<Writer> writers;
+  std::vector<int> acc_flags;
+  int n_ids = 0;
+  double* fstats = nullptr; size_t fstat_bytes = 0;
+  double* bstats = nullptr; size_t bstat_bytes = 0;
+};
+
+int Plan::build(float* workspace) {
+  if (!impl) impl = std::make_shared<Impl>();
+  Impl& I = *impl;
+  const bool dry = workspace == nullptr;
+  LOCO_REQUIRE(dry || I.sized, "plan: size query must precede binding");
+  LOCO_REQUIRE(NP >= 1 && NT >= 0 && NC >= 0, "plan: bad batch configuration");
+  LOCO_REQUIRE((NT == 0 && NC == 0) || NP == 1, "plan: tangents/cotangents need exactly one primal row");
+  const Model& M = *model;
+  const Arch& A = M.arch;
+  const int NB = NP + NT;
+  const int L = A.n_levels;
+  LOCO_REQUIRE(A.ch % 128 == 0, "plan: base channel count %d must be a multiple of 128", A.ch);
+  if (!dry) LOCO_REQUIRE(M.arena != nullptr, "plan: model weights not bound");
+
+  I.fwd.clear(); I.bwd_groups.clear(); I.bwd.clear(); I.launches.clear(); I.writers.clear();
+  I.n_ids = 0;
+  fwd_flops = vjp_flops = 0;
+  base = workspace;
+
+  // ---- bump allocators over three regions: activations | forward stats | backward stats ----
+  size_t act_off = 0, fs_off = 0, bs_off = 0;
+  uintptr_t act_base = (uintptr_t)workspace;
+  uintptr_t fs_base = act_base + I.act_floats * 4;
+  uintptr_t bs_base = fs_base + I.fstat_floats * 4;
+  auto alloc_act = [&](size_t n) -> float* {
+    float* p = (float*)(act_base + act_off * 4);
+    act_off += (n + 63) & ~(size_t)63;
+    return p;
+  };
+  auto alloc_fstat = [&](int rows) -> double* {
+    double* p = (double*)(fs_base + fs_off * 4);
+    fs_off += (size_t)rows * 32 * 2 * 2;   // doubles -> float units
+    return p;
+  };
+  auto alloc_bstat = [&](int rows) -> double* {
+    double* p = (double*)(bs_base + bs_off * 4);
+    bs_off += (size_t)rows * 32 * 2 * 2;
+    return p;
+  };
+  auto Tf = [&](int H, int W, int C) { return make_view(alloc_act((size_t)NB * H * W * C), NB, H, W, C); };
+  auto Tg = [&](int H, int W, int C) {
+    if (NC == 0) return make_view(nullptr, 0, H, W, C);
+    return make_view(alloc_act((size_t)NC * H * W * C), NC, H, W, C);
+  };
+  auto new_tensor = [&](int H, int W, int C) {
+    TH t; t.v = Tf(H, W, C); t.g = Tg(H, W, C); t.ids = {I.n_ids++};
+    return t;
+  };
+  auto row0 = [](const View& v) { return slice_n(v, 0, 1); };
+
+  // ---- cotangent writer flags (resolved by the dry run) ----
+  int writer_counter = 0;
+  int cur_group = -1;
+  auto begin_group = [&]() { I.bwd_groups.emplace_back(); cur_group = (int)I.bwd_groups.size() - 1; };
+  auto push_b = [&](Fn f) { I.bwd_groups[cur_group].push_back(std::move(f)); };
+  auto writer_flag = [&](const std::vector<int>& ids) -> int {
+    const int idx = writer_counter++;
+    if (dry) {
+      Impl::Writer w; w.ids = ids; w.group = cur_group; w.pos = (int)I.bwd_groups[cur_group].size();
+      I.writers.push_back(w);
+      return 0;
+    }
+    return I.acc_flags[idx];
+  };
+
+  int err = 0;
+  auto mk_conv = [&](ConvProblem prob, bool is_bwd) -> ConvLaunch* {
+    I.launches.emplace_back();
+    ConvLaunch* L_ = &I.launches.back();
+    const double fl = 2.0 * prob.out.N * prob.out.H * prob.out.W * (double)prob.Ngemm * prob.Kc *
+                      (prob.kind == CONV_1x1 ? 1 : 9) / (prob.kind == CONV_3x3_S2_DGRAD ? 4 : 1);
+    (is_bwd ? vjp_flops : fwd_flops) += fl;
+    if (!dry) {
+      const int r = conv_prepare(prob, L_);
+      if (r != 0 && err == 0) err = r;
+    }
+    return L_;
+  };
+  auto conv_fwd = [&](int kind, View in, View out, const ConvRef& c, const float* bias2,
+                      const View* addend) {
+    ConvProblem p;
+    p.kind = kind; p.in = in; p.out = out; p.wpack = dry ? nullptr : M.w(c.wf);
+    p.Kc = c.cin; p.Ngemm = c.cout;
+    p.bias = dry ? nullptr : M.w(c.bias); p.bias2 = bias2; p.bias_rows = NP;
+    p.addend = addend; p.accumulate = 0; p.round_out = 1;
+    ConvLaunch* l = mk_conv(p, false);
+    I.fwd.push_back([l](cudaStream_t s) { return conv_run(*l, s); });
+  };
+  // data-gradient convolution: gy [NC,..,cout] -> gx [NC,..,cin]
+  auto conv_bwd = [&](int fwd_kind, View gy, View gx, const ConvRef& c, int accumulate) {
+    ConvProblem p;
+    p.kind = fwd_kind == CONV_3x3 ? CONV_3x3_DGRAD
+                                  : (fwd_kind == CONV_3x3_S2 ? CONV_3x3_S2_DGRAD : CONV_1x1);
+    p.in = gy; p.out = gx; p.wpack = dry ? nullptr : M.w(c.wd);
+    p.Kc = c.cout; p.Ngemm = c.cin;
+    p.accumulate = accumulate; p.round_out = 1;
+    ConvLaunch* l = mk_conv(p, true);
+    push_b([l](cudaStream_t s) { return conv_run(*l, s); });
+  };
+  const float eps = A.gn_eps;
+  auto gn_fwd = [&](View x, const NormRef& n, int silu, int round_out, View y) -> double* {
+    double* st = alloc_fstat(NB);
+    const float* ga = dry ? nullptr : M.w(n.gamma);
+    const float* be = dry ? nullptr : M.w(n.beta);
+    const int np = NP;
+    I.fwd.push_back([=](cudaStream_t s) {
+      LOCO_TRY(gn_stats_fwd(x, np, st, s));
+      return gn_apply_fwd(x, np, st, ga, be, eps, silu, round_out, y, s);
+    });
+    return st;
+  };
+  auto gn_bwd = [&](View xp, const double* pstats, View gy, const NormRef& n, int silu,
+                    const View* addend, int accumulate, int round_out, View gx) {
+    double* st = alloc_bstat(NC);
+    const float* ga = dry ? nullptr : M.w(n.gamma);
+    const float* be = dry ? nullptr : M.w(n.beta);
+    const bool has_add = addend != nullptr;
+    const View add = has_add ? *addend : View();
+    push_b([=](cudaStream_t s) {
+      LOCO_TRY(gn_stats_vjp(xp, pstats, gy, ga, be, eps, silu, st, s));
+      return gn_apply_vjp(xp, pstats, gy, st, ga, be, eps, silu, has_add ? &add : nullptr, accumulate,
+                          round_out, gx, s);
+    });
+  };
+
+  // ---- timestep embedding ----
+  const int temb_ch = 4 * A.ch;
+  float* temb_scratch = alloc_act(2 * temb_ch);
+  float* tproj = alloc_act(M.tproj_rows);
+  if (!dry) {
+    const Model* Mp = model;
+    Impl* Ip = impl.get();
+    I.fwd.push_back([=](cudaStream_t s) {
+      LOCO_TRY(temb_forward(Ip->cur_t, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
+                            Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, s));
+      return temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
+                          Mp->tproj_rows, tproj, s);
+    });
+  } else {
+    I.fwd.push_back([](cudaStream_t) { return 0; });
+  }
+
+  // ---- blocks ----
+  auto resblock = [&](const ResRef& R, const TH& x, const TH& out) {
+    const int H = x.v.H, W = x.v.W;
+    View a1 = Tf(H, W, R.cin);
+    double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1);
+    View h1 = Tf(H, W, R.cout);
+    conv_fwd(CONV_3x3, a1, h1, R.c1, tproj + R.temb_off, nullptr);
+    View a2 = Tf(H, W, R.cout);
+    double* st2 = gn_fwd(h1, R.n2, 1, 1, a2);
+    View sc;
+    if (R.has_nin) {
+      sc = Tf(H, W, R.cout);
+      conv_fwd(CONV_1x1, x.v, sc, R.nin, nullptr, nullptr);
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &sc);
+    } else {
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &x.v);
+    }
+    if (NC > 0) {
+      begin_group();
+      View ga2 = Tg(H, W, R.cout);
+      conv_bwd(CONV_3x3, out.g, ga2, R.c2, 0);
+      View gh1 = Tg(H, W, R.cout);
+      gn_bwd(row0(h1), st2, ga2, R.n2, 1, nullptr, 0, 1, gh1);
+      View ga1 = Tg(H, W, R.cin);
+      conv_bwd(CONV_3x3, gh1, ga1, R.c1, 0);
+      const int f1 = writer_flag(x.ids);
+      gn_bwd(row0(x.v), st1, ga1, R.n1, 1, R.has_nin ? nullptr : &out.g, f1, 1, x.g);
+      if (R.has_nin) {
+        const int f2 = writer_flag(x.ids);
+        conv_bwd(CONV_1x1, out.g, x.g, R.nin, f2);
+      }
+    }
+  };
+  auto attnblock = [&](const AttnRef& R, const TH& x, const TH& out) {
+    const int H = x.v.H, W = x.v.W, C = R.C, T = H * W;
+    View hn = Tf(H, W, C);
+    double* st = gn_fwd(x.v, R.n, 0, 1, hn);
+    View qkv = Tf(H, W, 3 * C);
+    conv_fwd(CONV_1x1, hn, qkv, R.qkv, nullptr, nullptr);
+    float* S = alloc_act((size_t)NB * T * T);
+    View o = Tf(H, W, C);
+    const int np = NP;
+    I.fwd.push_back([=](cudaStream_t s) { return attention_forward(qkv, np, S, o, s); });
+    conv_fwd(CONV_1x1, o, out.v, R.proj, nullptr, &x.v);
+    if (NC > 0) {
+      begin_group();
+      View go = Tg(H, W, C);
+      conv_bwd(CONV_1x1, out.g, go, R.proj, 0);
+      View gqkv = Tg(H, W, 3 * C);
+      float* gP = alloc_act((size_t)NC * T * T);
+      View qkv0 = row0(qkv);
+      push_b([=](cudaStream_t s) { return attention_vjp(go, qkv0, S, gP, gqkv, s); });
+      View ghn = Tg(H, W, C);
+      conv_bwd(CONV_1x1, gqkv, ghn, R.qkv, 0);
+      const int f = writer_flag(x.ids);
+      gn_bwd(row0(x.v), st, ghn, R.n, 0, &out.g, f, 1, x.g);
+    }
+  };
+
+  // ---- topology (reference: PullBackDDPM.forward, ddpm/diffusion.py:145-200) ----
+  // simulate the encoder to learn the skip stack, then size the decoder concat buffers
+  struct HsInfo { int C, res; };
+  std::vector<HsInfo> hs_info;
+  {
+    int res = A.resolution;
+    hs_info.push_back({A.ch, res});
+    for (int l = 0; l < L; ++l) {
+      const int bo = A.ch * A.ch_mult[l];
+      for (int b = 0; b < A.num_res_blocks; ++b) hs_info.push_back({bo, res});
+      if (l != L - 1) { res /= 2; hs_info.push_back({bo, res}); }
+    }
+  }
+  const int n_hs = (int)hs_info.size();
+  LOCO_REQUIRE(n_hs == L * (A.num_res_blocks + 1), "plan: skip stack size mismatch");
+  struct CB { TH full, dec, skip; };
+  std::vector<CB> cbs(n_hs);
+  {
+    int block_in = A.ch * A.ch_mult[L - 1];
+    int u = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const int bo = A.ch * A.ch_mult[l];
+      for (int b = 0; b < A.num_res_blocks + 1; ++b, ++u) {
+        const HsInfo& h = hs_info[n_hs - 1 - u];
+        const int C0 = block_in, C1 = h.C;
+        CB& cb = cbs[u];
+        cb.full.v = Tf(h.res, h.res, C0 + C1);
+        cb.full.g = Tg(h.res, h.res, C0 + C1);
+        const int id_d = I.n_ids++, id_s = I.n_ids++;
+        cb.full.ids = {id_d, id_s};
+        cb.dec.v = slice_c(cb.full.v, 0, C0); cb.dec.g = slice_c(cb.full.g, 0, C0); cb.dec.ids = {id_d};
+        cb.skip.v = slice_c(cb.full.v, C0, C1); cb.skip.g = slice_c(cb.full.g, C0, C1); cb.skip.ids = {id_s};
+        block_in = bo;
+      }
+    }
+  }
+  auto hs_slot = [&](int i) -> TH& { return cbs[n_hs - 1 - i].skip; };
+
+  // conv_in
+  {
+    TH& h0 = hs_slot(0);
+    Impl* Ip = impl.get();
+    const float* wi = dry ? nullptr : M.w(M.conv_in_w);
+    const float* bi = dry ? nullptr : M.w(M.conv_in_b);
+    const View hv = h0.v, hg = h0.g;
+    const int np = NP;
+    I.fwd.push_back([=](cudaStream_t s) { return edge_conv_expand(Ip->cur_x, wi, bi, np, hv, 0, 1, s); });
+    if (NC > 0) {
+      begin_group();
+      push_b([=](cudaStream_t s) { return edge_conv_reduce(hg, wi, nullptr, 0, Ip->cur_gx, 1, s); });
+    }
+  }
+  // encoder
+  int hs_top = 0;   // index of the last pushed skip tensor
+  {
+    int res = A.resolution;
+    for (int l = 0; l < L; ++l) {
+      for (int b = 0; b < A.num_res_blocks; ++b) {
+        const ResRef& R = M.down_res[l][b];
+        TH& x = hs_slot(hs_top);
+        TH& out = hs_slot(hs_top + 1);
+        if (!M.down_attn[l].empty()) {
+          TH tmp = new_tensor(res, res, R.cout);
+          resblock(R, x, tmp);
+          attnblock(M.down_attn[l][b], tmp, out);
+        } else {
+          resblock(R, x, out);
+        }
+        ++hs_top;
+      }
+      if (l != L - 1) {
+        TH& x = hs_slot(hs_top);
+        TH& out = hs_slot(hs_top + 1);
+        const ConvRef& c = M.down_sample[l];
+        conv_fwd(CONV_3x3_S2, x.v, out.v, c, nullptr, nullptr);
+        if (NC > 0) {
+          begin_group();
+          const int f = writer_flag(x.ids);
+          conv_bwd(CONV_3x3_S2, out.g, x.g, c, f);
+        }
+        ++hs_top;
+        res /= 2;
+      }
+    }
+  }
+  // middle
+  {
+    TH& x = hs_slot(hs_top);
+    const int res = x.v.H;
+    TH m1 = new_tensor(res, res, M.mid1.cout);
+    resblock(M.mid1, x, m1);
+    TH m2 = new_tensor(res, res, M.mid1.cout);
+    attnblock(M.mid_attn, m1, m2);
+    resblock(M.mid2, m2, cbs[0].dec);
+  }
+  // decoder
+  TH hfin;
+  {
+    int u = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      for (int b = 0; b < A.num_res_blocks + 1; ++b, ++u) {
+        const ResRef& R = M.up_res[l][b];
+        const int res = cbs[u].full.v.H;
+        const bool has_attn = !M.up_attn[l].empty();
+        const bool last_in_level = b == A.num_res_blocks;
+        const bool needs_up = last_in_level && l != 0;
+        const bool very_last = last_in_level && l == 0;
+        TH target;
+        if (needs_up || very_last) target = new_tensor(res, res, R.cout);
+        else target = cbs[u + 1].dec;
+        if (has_attn) {
+          TH tmp = new_tensor(res, res, R.cout);
+          resblock(R, cbs[u].full, tmp);
+          attnblock(M.up_attn[l][b], tmp, target);
+        } else {
+          resblock(R, cbs[u].full, target);
+        }
+        if (needs_up) {
+          const ConvRef& c = M.up_sample[l];
+          View hu = Tf(2 * res, 2 * res, R.cout);
+          const View tv = target.v;
+          I.fwd.push_back([=](cudaStream_t s) { return upsample2x(tv, hu, s); });
+          TH& nxt = cbs[u + 1].dec;
+          conv_fwd(CONV_3x3, hu, nxt.v, c, nullptr, nullptr);
+          if (NC > 0) {
+            begin_group();
+            View ghu = Tg(2 * res, 2 * res, R.cout);
+            conv_bwd(CONV_3x3, nxt.g, ghu, c, 0);
+            const int f = writer_flag(target.ids);
+            const View tg = target.g;
+            push_b([=](cudaStream_t s) { return sumpool2x(ghu, tg, f, s); });
+          }
+        }
+        if (very_last) hfin = target;
+      }
+    }
+  }
+  // head
+  {
+    const int res = hfin.v.H, C = hfin.v.C;
+    View a = Tf(res, res, C);
+    double* st = gn_fwd(hfin.v, M.norm_out, 1, 0, a);
+    Impl* Ip = impl.get();
+    const float* wo = dry ? nullptr : M.w(M.conv_out_w);
+    const float* bo = dry ? nullptr : M.w(M.conv_out_b);
+    const int np = NP;
+    I.fwd.push_back([=](cudaStream_t s) { return edge_conv_reduce(a, wo, bo, np, Ip->cur_eps, 0, s); });
+    if (NC > 0) {
+      begin_group();
+      View ga = Tg(res, res, C);
+      push_b([=](cudaStream_t s) { return edge_conv_expand(Ip->cur_geps, wo, nullptr, 0, ga, 1, 0, s); });
+      const int f = writer_flag(hfin.ids);
+      gn_bwd(row0(hfin.v), st, ga, M.norm_out, 1, nullptr, f, 1, hfin.g);
+    }
+  }
+  if (err != 0) return err;
+
+  if (dry) {
+    I.act_floats = act_off; I.fstat_floats = fs_off; I.bstat_floats = bs_off;
+    workspace_floats = act_off + fs_off + bs_off + 64;
+    // resolve accumulate flags in backward execution order (groups reversed, ops in order)
+    std::vector<int> order(I.writers.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const auto& wa = I.writers[a]; const auto& wb = I.writers[b];
+      if (wa.group != wb.group) return wa.group > wb.group;
+      return wa.pos < wb.pos;
+    });
+    std::vector<char> init(I.n_ids, 0);
+    I.acc_flags.assign(I.writers.size(), 0);
+    for (int wi : order) {
+      const auto& w = I.writers[wi];
+      int n_init = 0;
+      for (int id : w.ids) n_init += init[id];
+      LOCO_REQUIRE(n_init == 0 || n_init == (int)w.ids.size(),
+                   "plan: inconsistent cotangent initialisation (writer %d)", wi);
+      I.acc_flags[wi] = n_init ? 1 : 0;
+      for (int id : w.ids) init[id] = 1;
+    }
+    I.sized = true;
+  } else {
+    LOCO_REQUIRE(act_off == I.act_floats && fs_off == I.fstat_floats && bs_off == I.bstat_floats,
+                 "plan: non-deterministic layout between size query and binding");
+    I.fstats = (double*)fs_base; I.fstat_bytes = fs_off * 4;
+    I.bstats = (double*)bs_base; I.bstat_bytes = bs_off * 4;
+    for (int g = (int)I.bwd_groups.size() - 1; g >= 0; --g)
+      for (auto& f : I.bwd_groups[g]) I.bwd.push_back(f);
+  }
+  fwd_launches = (int)I.fwd.size();
+  vjp_launches = (int)I.bwd.size();
+  return 0;
+}
+
+int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
+  LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
+  Impl& I = *impl;
+  I.cur_x = x; I.cur_t = t; I.cur_eps = eps_out;
+  if (I.fstat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(I.fstats, 0, I.fstat_bytes, s));
+  for (auto& f : I.fwd) LOCO_TRY(f(s));
+  return 0;
+}
+
+int Plan::vjp(const float* g_eps, float* gx, cudaStream_t s) {
+  LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
+  LOCO_REQUIRE(NC > 0, "plan: built without cotangent rows");
+  Impl& I = *impl;
+  I.cur_geps = g_eps; I.cur_gx = gx;
+  if (I.bstat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(I.bstats, 0, I.bstat_bytes, s));
+  for (auto& f : I.bwd) LOCO_TRY(f(s));
+  return 0;
+}
+
+}  // namespace loco

@@ -1,0 +1,108 @@
+// DDPM U-Net executor (architecture of the reference's models/ddpm/diffusion.py:22-200, i.e.
+// google/ddpm-ema-celebahq-256): forward, fused primal+k-tangent forward (JVP) and k-cotangent
+// backward (VJP) as static launch programs over a caller-provided workspace.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "attention.cuh"
+#include "common.cuh"
+#include "conv_gemm.cuh"
+#include "layers.cuh"
+
+namespace loco {
+
+struct Arch {
+  int ch = 128;
+  int n_levels = 6;
+  int ch_mult[8] = {1, 1, 2, 2, 4, 4, 0, 0};
+  int num_res_blocks = 2;
+  int n_attn = 1;
+  int attn_resolutions[4] = {16, 0, 0, 0};
+  int resolution = 256;
+  int in_ch = 3;
+  int out_ch = 3;
+  float gn_eps = 1e-6f;
+};
+
+// One named parameter of the reference state_dict and where its packed forms live in the arena.
+struct ParamSlot {
+  std::string name;
+  std::vector<int> shape;
+  long long numel;
+  enum Kind { RAW, CONV_GEMM, CONV_QKV, CONV_EDGE_IN, CONV_EDGE_OUT, BIAS_QKV } kind;
+  size_t off_a = 0;   // RAW: copy; CONV_GEMM/QKV: fprop pack; EDGE: [9][3][C] pack
+  size_t off_b = 0;   // CONV_GEMM/QKV: dgrad pack
+  int cout = 0, cin = 0, ksz = 0;
+  int row_off = 0, rows_total = 0;   // QKV fusion: rows [row_off, row_off+cout) of rows_total
+  bool loaded = false;
+};
+
+struct ConvRef { int cin = 0, cout = 0, ksz = 0; size_t wf = 0, wd = 0, bias = 0; };
+struct NormRef { int C = 0; size_t gamma = 0, beta = 0; };
+struct ResRef {
+  int cin = 0, cout = 0;
+  NormRef n1, n2;
+  ConvRef c1, c2, nin;
+  bool has_nin = false;
+  int temb_off = 0;    // offset into the packed timestep-projection vector
+};
+struct AttnRef { int C = 0; NormRef n; ConvRef qkv, proj; };
+
+class Model {
+ public:
+  explicit Model(const Arch& a);
+  Arch arch;
+  std::vector<ParamSlot> slots;
+  std::map<std::string, int> slot_index;
+  size_t arena_floats = 0;
+  float* arena = nullptr;
+
+  // layer references (offsets into the arena)
+  size_t temb_w0 = 0, temb_b0 = 0, temb_w1 = 0, temb_b1 = 0;
+  size_t tproj_w = 0, tproj_b = 0;   // all temb_proj layers stacked: [tproj_rows][temb_ch]
+  int tproj_rows = 0;
+  size_t conv_in_w = 0, conv_in_b = 0, conv_out_w = 0, conv_out_b = 0;
+  NormRef norm_out;
+  std::vector<std::vector<ResRef>> down_res, up_res;
+  std::vector<std::vector<AttnRef>> down_attn, up_attn;
+  std::vector<ConvRef> down_sample, up_sample;   // per level (cin == 0 when absent)
+  ResRef mid1, mid2;
+  AttnRef mid_attn;
+
+  int load_param(const char* name, const float* dev_src, long long numel, cudaStream_t s);
+  int check_loaded() const;
+  float* w(size_t off) const { return arena + off; }
+
+ private:
+  size_t alloc(size_t n);
+  int add_slot(ParamSlot s);
+  ConvRef add_conv(const std::string& prefix, int cin, int cout, int ksz);
+  NormRef add_norm(const std::string& prefix, int C);
+  ResRef add_res(const std::string& prefix, int cin, int cout);
+  AttnRef add_attn(const std::string& prefix, int C);
+};
+
+class Plan {
+ public:
+  Plan(const Model* m, int n_primal, int n_tangent, int n_cot)
+      : model(m), NP(n_primal), NT(n_tangent), NC(n_cot) {}
+  const Model* model;
+  int NP, NT, NC;
+  size_t workspace_floats = 0;
+  float* base = nullptr;
+  double fwd_flops = 0, vjp_flops = 0;
+  int fwd_launches = 0, vjp_launches = 0;
+
+  int build(float* workspace);   // workspace == nullptr: size query only
+  // x: [NP+NT, 3, R, R] (row 0.. primal samples, then tangents); eps: same shape.
+  int forward(const float* x_nchw, float t, float* eps_nchw, cudaStream_t s);
+  // g_eps: [NC, 3, R, R] cotangents of eps; gx: [NC, 3, R, R] = J_eps^T g_eps.
+  int vjp(const float* g_eps_nchw, float* gx_nchw, cudaStream_t s);
+
+  struct Impl;
+  std::shared_ptr<Impl> impl;
+};
+
+}  // namespace loco

@@ -1,0 +1,157 @@
+"""Host-side handle of the B200 U-Net executor.
+
+`B200UNet` is what the Edit classes hold as `self.unet`: calling it evaluates eps_theta(x, t) like
+the reference's `self.unet(xt, t)` (src/modules/edit.py:2151, 2375, 2572); `jvp`/`vjp` expose the
+fused primal+tangent and transposed passes the power method is built from.  All arithmetic runs in
+libloco_b200.so; torch only owns the device memory and the stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Arch, check, ptr, stream_ptr
+
+
+def _make_arch(a):
+    s = Arch()
+    s.ch = a["ch"]
+    mult = tuple(a["ch_mult"])
+    s.n_levels = len(mult)
+    for i, m in enumerate(mult):
+        s.ch_mult[i] = m
+    s.num_res_blocks = a["num_res_blocks"]
+    attn = tuple(a["attn_resolutions"])
+    s.n_attn = len(attn)
+    for i, r in enumerate(attn):
+        s.attn_resolutions[i] = r
+    s.resolution = a["resolution"]
+    s.in_ch = a.get("in_ch", 3)
+    s.out_ch = a.get("out_ch", 3)
+    s.gn_eps = a.get("gn_eps", 1e-6)
+    return s
+
+
+class Plan:
+    """A static launch program for a fixed (n_primal, n_tangent, n_cotangent) batch."""
+
+    def __init__(self, unet, n_primal, n_tangent, n_cot):
+        self.lib = _lib.load()
+        self.unet = unet
+        self.shape = (n_primal, n_tangent, n_cot)
+        h = C.c_void_p()
+        check(self.lib.loco_plan_create(unet.handle, n_primal, n_tangent, n_cot, C.byref(h)),
+              "loco_plan_create")
+        self.handle = h
+        nbytes = self.lib.loco_plan_workspace_bytes(h)
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=unet.device)
+        off = (-self.workspace.data_ptr()) % 256
+        self._ws_ptr = C.c_void_p(self.workspace.data_ptr() + off)
+        check(self.lib.loco_plan_bind(h, self._ws_ptr), "loco_plan_bind")
+        ff, vf = C.c_double(), C.c_double()
+        fo, vo = C.c_int(), C.c_int()
+        check(self.lib.loco_plan_info(h, C.byref(ff), C.byref(vf), C.byref(fo), C.byref(vo)))
+        self.fwd_flops, self.vjp_flops = ff.value, vf.value
+        self.fwd_ops, self.vjp_ops = fo.value, vo.value
+
+    def forward(self, x, t, out=None):
+        n = self.shape[0] + self.shape[1]
+        R = self.unet.arch["resolution"]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert tuple(x.shape) == (n, 3, R, R), (tuple(x.shape), n, R)
+        if out is None:
+            out = torch.empty_like(x)
+        check(self.lib.loco_unet_forward(self.handle, ptr(x), float(t), ptr(out), stream_ptr()),
+              "loco_unet_forward")
+        return out
+
+    def vjp(self, g_eps, out=None):
+        k = self.shape[2]
+        R = self.unet.arch["resolution"]
+        assert g_eps.is_cuda and g_eps.dtype == torch.float32 and g_eps.is_contiguous()
+        assert tuple(g_eps.shape) == (k, 3, R, R)
+        if out is None:
+            out = torch.empty_like(g_eps)
+        check(self.lib.loco_unet_vjp(self.handle, ptr(g_eps), ptr(out), stream_ptr()), "loco_unet_vjp")
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.loco_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class B200UNet:
+    def __init__(self, arch, state_dict, device="cuda:0"):
+        self.lib = _lib.load()
+        self.arch = dict(arch)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.LocoError("B200UNet needs a CUDA device; there is no CPU fallback")
+        self._arch_struct = _make_arch(arch)
+        h = C.c_void_p()
+        check(self.lib.loco_unet_create(C.byref(self._arch_struct), C.byref(h)), "loco_unet_create")
+        self.handle = h
+        n = self.lib.loco_unet_weight_floats(h)
+        self.arena = torch.zeros(n + 64, dtype=torch.float32, device=self.device)
+        off = ((-self.arena.data_ptr()) % 256) // 4
+        check(self.lib.loco_unet_bind_weights(h, C.c_void_p(self.arena.data_ptr() + 4 * off)))
+        self._plans = {}
+        self.load_state_dict(state_dict)
+
+    def param_shapes(self):
+        out = {}
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        nd = C.c_int()
+        for i in range(self.lib.loco_unet_num_params(self.handle)):
+            check(self.lib.loco_unet_param_info(self.handle, i, buf, 256, shape, C.byref(nd)))
+            out[buf.value.decode()] = tuple(shape[j] for j in range(nd.value))
+        return out
+
+    def load_state_dict(self, sd):
+        shapes = self.param_shapes()
+        missing = [k for k in shapes if k not in sd]
+        if missing:
+            raise _lib.LocoError("state_dict lacks %d parameters, e.g. %s" % (len(missing), missing[:3]))
+        with torch.cuda.device(self.device):
+            for name, shape in shapes.items():
+                w = sd[name]
+                if tuple(w.shape) != shape:
+                    raise _lib.LocoError("parameter %s has shape %s, expected %s" % (name, tuple(w.shape), shape))
+                wd = w.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                check(self.lib.loco_unet_load_param(self.handle, name.encode(), ptr(wd), wd.numel(),
+                                                    stream_ptr()), "loco_unet_load_param(%s)" % name)
+            torch.cuda.current_stream().synchronize()
+
+    def plan(self, n_primal, n_tangent=0, n_cot=0):
+        key = (n_primal, n_tangent, n_cot)
+        if key not in self._plans:
+            with torch.cuda.device(self.device):
+                self._plans[key] = Plan(self, *key)
+        return self._plans[key]
+
+    def __call__(self, x, t):
+        """eps = unet(x, t); x [B,3,R,R] fp32 on the device, t scalar (tensor or float)."""
+        x = x.contiguous()
+        return self.plan(x.shape[0]).forward(x, float(t))
+
+    def jvp(self, x, t, V):
+        """(eps, d_eps) for tangents V [k,3,R,R] at x [1,3,R,R] in one fused pass."""
+        k = V.shape[0]
+        p = self.plan(1, k, k)
+        xin = torch.cat([x.reshape(1, *V.shape[1:]), V], 0).contiguous()
+        out = p.forward(xin, float(t))
+        return out[:1], out[1:]
+
+    def vjp(self, k, g_eps):
+        """J_eps^T g for k cotangents at the primal point of the last jvp() call."""
+        return self.plan(1, k, k).vjp(g_eps.contiguous())
+
+    def __del__(self):
+        try:
+            self._plans.clear()
+            self.lib.loco_unet_destroy(self.handle)
+        except Exception:
+            pass

@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  Tolerances are fp32 round-off of two implementations of the same
+arithmetic on the same CPU (different op fusion / summation order only)."""
+import json
+import os
+
+import pytest
+import torch
+
+from loco_edit_b200.weights import DDPM256, ddpm_param_shapes, random_state_dict
+from oracle import ddpm_ref, pullback_ref
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_param_shapes_match_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "ddpm_param_shapes.json")))
+    mine = ddpm_param_shapes(DDPM256)
+    assert sorted(mine.keys()) == sorted(ref.keys())
+    for k in ref:
+        assert list(mine[k]) == ref[k], k
+    n = 0
+    for s in mine.values():
+        c = 1
+        for d in s:
+            c *= d
+        n += c
+    assert n == 113673219
+
+
+def test_unet_forward_matches_reference(golden_dir):
+    g = _load(golden_dir, "unet_tiny.pt")
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    with torch.no_grad():
+        eps = ddpm_ref.unet_forward(sd, g["arch"], g["x"], g["t"])
+    assert torch.allclose(eps, g["eps"], atol=2e-5, rtol=1e-5), float((eps - g["eps"]).abs().max())
+
+
+def test_scheduler_matches_reference(golden_dir):
+    g = _load(golden_dir, "scheduler.pt")
+    s = pullback_ref.RefScheduler()
+    s.set_timesteps(100)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.timesteps_next, g["timesteps_next"])
+    assert torch.equal(s.alphas_cumprod, g["alphas_cumprod"])
+    for idx, o in g["steps"].items():
+        t = s.timesteps[idx]
+        xn, x0 = s.step(g["et"], t, g["xt"], eta=0)
+        assert torch.equal(xn, o["eta0"]) and torch.equal(x0, o["x0"])
+        xn1, _ = s.step(g["et"], t, g["xt"], eta=1, noise=o["noise"])
+        assert torch.equal(xn1, o["eta1"])
+    s.set_timesteps(100, is_inversion=True)
+    assert torch.equal(s.timesteps, g["inv_timesteps"])
+    assert torch.equal(s.timesteps_next, g["inv_timesteps_next"])
+    for idx, o in g["inv_steps"].items():
+        xn, _ = s.step(g["et"], s.timesteps[idx], g["xt"], eta=0)
+        assert torch.equal(xn, o)
+
+
+def _principal_angle_deg(A, B):
+    qa, _ = torch.linalg.qr(A.double().T)
+    qb, _ = torch.linalg.qr(B.double().T)
+    sv = torch.linalg.svdvals(qa.T @ qb).clamp(max=1.0)
+    return float(torch.rad2deg(torch.acos(sv.min())))
+
+
+@pytest.mark.parametrize("case", ["mask_k2", "notmask_k3", "nomask_k2", "noise_k2"])
+def test_local_basis_matches_reference(golden_dir, case):
+    g = _load(golden_dir, "pullback_tiny.pt")
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    unet = ddpm_ref.RefUNet(g["arch"], sd)
+    sched = pullback_ref.RefScheduler()
+    sched.set_timesteps(100)
+    kw = {"mask_k2": dict(mask=g["mask"], k=2), "notmask_k3": dict(mask=~g["mask"], k=3),
+          "nomask_k2": dict(mask=None, k=2), "noise_k2": dict(mask=g["mask"], k=2, noise=True)}[case]
+    k = kw.pop("k")
+    d = g["xt"].numel()
+    torch.manual_seed(g["v0_seed"])                      # modules/edit.py:2435-2437
+    v0, _ = torch.linalg.qr(torch.randn(d, k))
+    for n_iter in (1, 3):
+        u, s, vT = pullback_ref.local_basis(unet, sched, g["xt"], g["t"], v0.T, n_iter, **kw)
+        ref = g["cases"][case][n_iter]
+        assert torch.allclose(s, ref["s"], rtol=1e-4), (s, ref["s"])
+        assert _principal_angle_deg(vT, ref["vT"]) < 0.05
+        # rows equal up to sign
+        dots = (vT * ref["vT"]).sum(1).abs()
+        assert float((1 - dots).abs().max()) < 1e-3, dots
+        uref = ref["u"].reshape(ref["u"].shape[0], -1)
+        assert u.shape == uref.shape
+        assert torch.allclose(u, uref, atol=1e-4 * float(uref.abs().max()) + 1e-6)
