@@ -1,0 +1,374 @@
+"""Host-side mirror of the reference's `EditUncondDiffusion` hot path (src/modules/edit.py:2034-2625).
+
+Method names, argument lists, file names and return values follow the reference so the class is a
+drop-in for that path; the arithmetic runs in libloco_b200.so (no PyTorch fallback):
+
+  reference (PyTorch)                                    here
+  -----------------------------------------------------  -----------------------------------------
+  torch.func.jacfwd over chunks of v       (:2449-2458)   one fused primal+k-tangent U-Net pass
+  fresh forward + k sequential backwards   (:2460-2480)   one k-cotangent VJP pass over the saved
+                                                          primal activations of the JVP pass
+  torch.linalg.svd(v_)                     (:2482)        Gram + k x k Jacobi eigensolver kernel
+  vT_null.T @ (vT_null @ vT_modify.T)      (:2317-2323)   nullspace_project kernels
+  scheduler.step / unet per DDIM step      (:2544-2593)   graph-friendly kernels, no host staging
+
+Deliberate deviations (documented in DESIGN.md): no CPU staging of latents (`buffer_device`,
+:2562-2584) and of U (:2456-2458); row signs of the basis are aligned with the previous iterate so
+the reference's convergence test (:2489-2494) is not defeated by SVD sign flips (`align_sign`);
+`v0=` lets a caller inject the initial basis for deterministic parity runs.
+"""
+import os
+
+import torch
+
+from . import ops
+from .scheduler import YHCustomScheduler
+
+
+def _pb_workspace(unet, k):
+    cache = unet.__dict__.setdefault("_pb_cache", {})
+    if k not in cache:
+        cache[k] = ops.PullbackWorkspace(unet, k)
+    return cache[k]
+
+
+def local_basis(unet, scheduler, x, t, pca_rank, v0=None, min_iter=10, max_iter=100,
+                convergence_threshold=1e-3, mask=None, noise=False, align_sign=True, verbose=True,
+                chunk_size=None):
+    """Power-method local basis of the (masked) PMP Jacobian at x_t.
+
+    Restates `local_encoder_decoder_pullback_xt` (src/modules/edit.py:2406-2504): returns
+    (u [l_o,k] = J V^T of the last iterate, s [k] = sqrt(svdvals(U^T J)), vT [k,d]).
+    `chunk_size` is accepted for signature compatibility; all k tangents run in one fused pass."""
+    k = int(pca_rank)
+    ws = _pb_workspace(unet, k)
+    d = ws.d
+    dev = unet.device
+    x = x.to(device=dev, dtype=torch.float32).contiguous().reshape(1, -1)
+    assert x.numel() == d
+    t_host = float(t)
+    at = scheduler.alpha_at(t_host)
+    mask_u8 = None
+    if mask is not None:
+        mask_u8 = mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
+        assert mask_u8.numel() == d, "mask must cover (c, h, w) of x"
+    if v0 is None:
+        # Algorithm 1 init (src/modules/edit.py:2435-2438)
+        vT = torch.randn(d, k, device=dev, dtype=torch.float)
+        vT, _ = torch.linalg.qr(vT)
+        v0 = vT.T.contiguous()
+    cur, nxt = ws.V
+    cur.copy_(v0.reshape(k, d))
+    for i in range(max_iter):
+        ws.iterate(x, t_host, at, mask_u8, noise, cur, nxt, align_sign=align_sign)
+        need_check = i > min_iter
+        if verbose or need_check:
+            convergence = torch.dist(cur, nxt).item()                       # :2489
+            if verbose:
+                print(f'power method : {i}-th step convergence : ', convergence)
+        cur, nxt = nxt, cur
+        if need_check and torch.allclose(nxt, cur, atol=convergence_threshold):   # :2492
+            if verbose:
+                print('reach convergence threshold : ', convergence)
+            break
+    ws.V = [cur, nxt]
+    vT = cur.clone()
+    s = ws.s.clone()
+    if mask_u8 is None:
+        u = ws.u_full.clone()
+    else:
+        idx = ops.mask_indices(mask_u8)
+        u = ops.gather_rows(ws.u_full, idx)
+    return u.T, s, vT
+
+
+class SyntheticDataset(object):
+    """Seeded stand-in for the reference's datasets (src/utils/utils.py:472-672,
+    src/dataset/celeba_hq_dataloader.py): `ds[idx] -> [1,3,R,R]` in [-1,1], `getmask -> bool[3,R,R]`.
+    (image clamp(0.5*randn,-1,1) seeded by idx; rectangle mask.)"""
+
+    def __init__(self, resolution=256):
+        self.R = resolution
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(int(idx))
+        return (0.5 * torch.randn(1, 3, self.R, self.R, generator=g)).clamp(-1, 1)
+
+    def getmask(self, idx=0, choose_sem=None):
+        R = self.R
+        m = torch.zeros(3, R, R, dtype=torch.bool)
+        m[:, (3 * R) // 8:(5 * R) // 8, R // 4:(3 * R) // 4] = True
+        return m
+
+
+class EditUncondDiffusion(object):
+    """Drop-in for the reference class of the same name (src/modules/edit.py:2034-2625).
+
+    `unet` / `dataset` may be injected (random-init synthetic weights otherwise: there is no
+    network for checkpoints); everything else is read from `args` exactly like the reference."""
+
+    def __init__(self, args, unet=None, dataset=None):
+        self.pca_device = getattr(args, "pca_device", "cpu")
+        self.buffer_device = getattr(args, "buffer_device", "cpu")     # accepted, unused (no staging)
+        self.memory_bound = getattr(args, "memory_bound", 50)
+        self.device = torch.device(args.device)
+        self.dtype = args.dtype
+        self.seed = getattr(args, "seed", 0)
+        self.save_result_as = getattr(args, "save_result_as", "image")
+        self.model_name = getattr(args, "model_name", "")
+        self.image_size = getattr(args, "image_size", 256)
+        self.c_in = 3
+        if self.dtype != torch.float32:
+            raise NotImplementedError("the uncond hot path runs in fp32/TF32 (all reference scripts use --dtype fp32)")
+        if unet is None:
+            from .unet import B200UNet
+            from .weights import DDPM256, random_state_dict
+            arch = dict(DDPM256, resolution=self.image_size)
+            wp = getattr(args, "weights_path", "")
+            sd = torch.load(wp, map_location="cpu") if wp else random_state_dict(arch, seed=1234)
+            unet = B200UNet(arch, sd, device=self.device)
+        self.unet = unet
+        self.scheduler = YHCustomScheduler(args, device=self.device)
+        self.dataset = dataset if dataset is not None else SyntheticDataset(self.image_size)
+        self.dataset_name = getattr(args, "dataset_name", "CelebA_HQ_mask")
+        self.for_steps = args.for_steps
+        self.inv_steps = args.inv_steps
+        self.use_yh_custom_scheduler = getattr(args, "use_yh_custom_scheduler", True)
+        self.edit_t = args.edit_t
+        self.scheduler.set_timesteps(self.for_steps, device=self.device)
+        # src/modules/edit.py:2072-2073
+        self.edit_t_idx = int((self.scheduler.timesteps - self.edit_t * 1000).abs().argmin())
+        pbt = getattr(args, "performance_boosting_t", 0.0)
+        self.performance_boosting_t_idx = int((self.scheduler.timesteps - pbt * 1000).abs().argmin()) if pbt > 0 else 1000
+        self.use_x_space_guidance = getattr(args, "use_x_space_guidance", False)
+        self.x_space_guidance_edit_step = getattr(args, "x_space_guidance_edit_step", 1)
+        self.x_space_guidance_scale = getattr(args, "x_space_guidance_scale", 0)
+        self.x_space_guidance_num_step = getattr(args, "x_space_guidance_num_step", 0)
+        rf = getattr(args, "result_folder", "./runs/")
+        if self.dataset_name == "Random":
+            self.result_folder = os.path.join(rf, f"sample_seed{self.seed}")
+        else:
+            self.result_folder = os.path.join(rf, f"sample_idx{getattr(args, 'sample_idx', 0)}")
+        os.makedirs(self.result_folder, exist_ok=True)
+        self.obs_folder = getattr(args, "obs_folder", self.result_folder)
+        self.vT_path = getattr(args, "vT_path", "")
+        self.vT1_path = getattr(args, "vT1_path", "")
+        self.mask_type = getattr(args, "mask_type", "SAM")
+        self.args = args
+        self.verbose = getattr(args, "verbose", True)
+        self.save_images = getattr(args, "save_images", True)
+        self.align_sign = getattr(args, "align_sign", True)
+        self.v0 = None            # optional injected initial basis (parity runs)
+        self.noise_fn = None      # optional callable(i, xt) -> eta=1 noise (parity runs)
+        self.last_images = []     # outputs of the performance-boosted DDIM passes
+
+    # ------------------------------------------------------------------ simple experiments
+    @torch.no_grad()
+    def run_DDIMforward(self, num_samples=5):
+        self.EXP_NAME = 'DDIMforward'
+        xT = torch.randn(num_samples, self.c_in, self.image_size, self.image_size, device=self.device, dtype=self.dtype)
+        return self.DDIMforwardsteps(xT, t_start_idx=0, t_end_idx=-1, vis_psd=False)
+
+    @torch.no_grad()
+    def run_DDIMinversion(self, idx):
+        """src/modules/edit.py:2117-2167."""
+        EXP_NAME = f'DDIMinversion-{self.dataset_name}_{idx}'
+        self.scheduler.set_timesteps(self.inv_steps, device=self.device, is_inversion=True)
+        n = len(self.scheduler._ts_host)
+        x0 = self.dataset[idx]
+        self._save_image(x0, 'original.png')
+        xt = x0.to(self.device, dtype=self.dtype).contiguous()
+        for i in range(n):
+            if i == n - 1:
+                break
+            t = self.scheduler._ts_host[i]
+            et = self.unet(xt, t)
+            xt = self.scheduler.step(et, t, xt, eta=0, t_idx=i).prev_sample
+        self._save_image(xt, f'xT-{EXP_NAME}.png')
+        return xt
+
+    # ------------------------------------------------------------------ editing drivers
+    @torch.no_grad()
+    def group_edit_null_space_projection(self, idx, **kwargs):
+        """src/modules/edit.py:2171-2212 (two directions, cumulative; `vT_paths=` generalises to n)."""
+        if self.dataset_name == 'Random':
+            xT = torch.randn(1, 3, self.image_size, self.image_size, dtype=self.dtype, device=self.device)
+        else:
+            xT = self.run_DDIMinversion(idx=idx)
+        xt, t, t_idx = self.DDIMforwardsteps(xT, t_start_idx=0, t_end_idx=self.edit_t_idx)
+        assert t_idx == self.edit_t_idx
+        paths = kwargs.get("vT_paths") or [self.vT_path, self.vT1_path]
+        vT_list = [torch.load(p, map_location=self.device) for p in paths]
+        BASIS_NAME = f"load-basis-{len(vT_list)}"
+        xt_temp = xt.detach().clone()
+        xt_vis_list = [xt_temp]
+        for vT in vT_list:
+            vk = vT[0, :].view(-1, *xt.shape[1:]).to(self.dtype).contiguous()
+            xt_temp = ops.axpy(xt_temp, vk, self.x_space_guidance_scale * self.x_space_guidance_num_step)
+            xt_vis_list.append(xt_temp)
+        self.EXP_NAME = f'{idx}-Edit_xt-noise-{BASIS_NAME}'
+        xt_vis = torch.cat(xt_vis_list, dim=0)
+        self.DDIMforwardsteps(xt_vis, t_start_idx=self.edit_t_idx, t_end_idx=-1, performance_boosting=True)
+        return xt
+
+    def _get_masks(self, idx, use_mask):
+        """Mask sources of src/modules/edit.py:2234-2267 without the SAM network: the dataset's
+        ground-truth mask, or a cached `mask/mask.pt` (bool [n,res,res], mask_segmentation.py:23-25)."""
+        mpath = os.path.join(self.result_folder, "mask/mask.pt")
+        if self.dataset_name == "CelebA_HQ_mask" or not os.path.exists(mpath):
+            return self.dataset.getmask(idx=getattr(self.args, "sample_idx", idx),
+                                        choose_sem=getattr(self.args, "choose_sem", None))
+        if not use_mask:
+            return None
+        masks = torch.load(mpath)
+        return masks[getattr(self.args, "mask_index", 0)].squeeze(dim=0).repeat(3, 1, 1)
+
+    @torch.no_grad()
+    def run_edit_null_space_projection(
+            self, idx, vis_num, vis_num_pc=5, pca_rank=50, pca_rank_null=10, op='mid', block_idx=0,
+            null_space_projection=True, encoder_decoder_by_et=False, use_mask=True, random_edit=False,
+            **kwargs):
+        """src/modules/edit.py:2216-2366."""
+        if self.dataset_name == 'Random':
+            xT = torch.randn(1, self.c_in, self.image_size, self.image_size, dtype=self.dtype, device=self.device)
+        else:
+            xT = self.run_DDIMinversion(idx=idx)
+        mask = self._get_masks(idx, use_mask)
+        if getattr(self.args, "sampling_mode", False):
+            return None
+        if mask is not None:
+            mask = mask.to(self.device)
+
+        xt, t, t_idx = self.DDIMforwardsteps(xT, t_start_idx=0, t_end_idx=self.edit_t_idx)
+        assert t_idx == self.edit_t_idx
+
+        sem = getattr(self.args, "choose_sem", None) if self.dataset_name == "CelebA_HQ_mask" else getattr(self.args, "mask_index", 0)
+        if not os.path.exists(self.vT_path):
+            save_dir = os.path.join(self.result_folder, "basis", f'local_basis-{self.edit_t}T-select-mask-{sem}')
+            os.makedirs(save_dir, exist_ok=True)
+            vT_modify_path = os.path.join(save_dir, f'vT-modify-pca-rank-{pca_rank}.pt')
+            vT_null_path = os.path.join(save_dir, f'vT-null-{pca_rank_null}.pt')
+            if os.path.exists(vT_modify_path):
+                vT_modify = torch.load(vT_modify_path, map_location=self.device).type(self.dtype)
+            else:
+                u_modify, s_modify, vT_modify = self.local_encoder_decoder_pullback_xt(
+                    x=xt, t=t, op=op, block_idx=block_idx, pca_rank=pca_rank,
+                    min_iter=10, max_iter=50, convergence_threshold=1e-4, mask=mask, noise=encoder_decoder_by_et)
+                torch.save(vT_modify, vT_modify_path)
+            if null_space_projection and os.path.exists(vT_null_path):
+                vT_null = torch.load(vT_null_path, map_location=self.device).type(self.dtype)
+            elif not null_space_projection:
+                vT_null = None
+            else:
+                u_null, s_null, vT_null = self.local_encoder_decoder_pullback_xt(
+                    x=xt, t=t, op=op, block_idx=block_idx, pca_rank=pca_rank_null,
+                    min_iter=10, max_iter=50, convergence_threshold=1e-4,
+                    mask=(~mask if mask is not None else None), noise=encoder_decoder_by_et)
+                torch.save(vT_null, vT_null_path)
+            if random_edit:
+                vT_modify = torch.randn_like(vT_modify)
+            # :2317-2323
+            if not null_space_projection:
+                vT = ops.nullspace_project(vT_modify.contiguous(), None, project=False)
+            else:
+                vT = ops.nullspace_project(vT_modify.contiguous(), vT_null[:pca_rank_null, :].contiguous(), project=True)
+            BASIS_NAME = f"{encoder_decoder_by_et}_{sem}-edit_{self.edit_t}T_null_proj_{null_space_projection}_rank{pca_rank_null}_scale_{self.x_space_guidance_scale}"
+            for pc_idx in range(max(vis_num_pc, vT.shape[0])):        # :2329 (IndexError if > k, as in the reference)
+                self.EXP_NAME = f'{idx}-Edit_xt-noise-{BASIS_NAME}-pc_{pc_idx:0=3d}'
+                torch.save(vT[[pc_idx], :], os.path.join(save_dir, f'{self.EXP_NAME}-vT.pt'))
+        else:
+            vT = torch.load(self.vT_path, map_location=self.device).type(self.dtype)
+            BASIS_NAME = f"edit_{self.edit_t}T-load-basis-'{os.path.basename(self.vT_path)}'"
+
+        # edit (:2339-2364)
+        original_xt = xt.detach()
+        self.last_images = []
+        for pc_idx in range(min(vis_num_pc, vT.shape[0])):
+            self.EXP_NAME = f'{idx}-Edit-random{random_edit}_xt-noise-{BASIS_NAME}-pc_{pc_idx:0=3d}'
+            xt = self.build_edit_batch(original_xt, vT[pc_idx, :], vis_num)
+            self.DDIMforwardsteps(xt, t_start_idx=self.edit_t_idx, t_end_idx=-1, performance_boosting=True)
+        return xt
+
+    def build_edit_batch(self, original_xt, v_row, vis_num):
+        """src/modules/edit.py:2341-2363: +/- direction, num_step cumulative edits, subsample."""
+        xts = {}
+        for direction in [1, -1]:
+            vk = (direction * v_row).view(-1, *original_xt.shape[1:]).contiguous()
+            xt_list = [original_xt.clone()]
+            for _ in range(self.x_space_guidance_num_step):
+                xt_list.append(self.x_space_guidance_direct(
+                    xt_list[-1], t_idx=self.edit_t_idx, vk=vk, single_edit_step=self.x_space_guidance_edit_step))
+            xt = torch.cat(xt_list, dim=0)
+            xt = xt[[0, -1], :] if vis_num == 1 else xt[::(xt.size(0) // vis_num)]
+            xts[direction] = xt
+        return torch.cat([(xts[-1].flip(dims=[0]))[:-1], xts[1]], dim=0).contiguous()
+
+    # ------------------------------------------------------------------ hot-path pieces
+    def get_x0(self, t, x, mask=None):
+        """src/modules/edit.py:2369-2391."""
+        et = self.unet(x.contiguous(), float(t))
+        P_xt = ops.pmp_forward(x.contiguous(), et, self.scheduler.alpha_at(float(t)))
+        if mask is not None:
+            idx = ops.mask_indices(mask.to(self.device))
+            P_xt = ops.gather_rows(P_xt.reshape(P_xt.shape[0], -1), idx)
+        return P_xt
+
+    def get_et(self, t, x, mask=None):
+        """src/modules/edit.py:2394-2403."""
+        et = self.unet(x.contiguous(), float(t))
+        if mask is not None:
+            idx = ops.mask_indices(mask.to(self.device))
+            et = ops.gather_rows(et.reshape(et.shape[0], -1), idx)
+        return et
+
+    def local_encoder_decoder_pullback_xt(
+            self, x, t, op=None, block_idx=None,
+            pca_rank=50, chunk_size=25, min_iter=10, max_iter=100, convergence_threshold=1e-3,
+            mask=None, noise=False, v0=None):
+        """src/modules/edit.py:2406-2504; `op`/`block_idx` are accepted and ignored like there."""
+        return local_basis(self.unet, self.scheduler, x, t, pca_rank, v0=v0 if v0 is not None else self.v0,
+                           min_iter=min_iter, max_iter=max_iter, convergence_threshold=convergence_threshold,
+                           mask=mask, noise=noise, align_sign=self.align_sign, verbose=self.verbose,
+                           chunk_size=chunk_size)
+
+    @torch.no_grad()
+    def DDIMforwardsteps(self, xt, t_start_idx, t_end_idx, vis_psd=False, save_image=True,
+                         return_xt=True, performance_boosting=False):
+        """src/modules/edit.py:2508-2614 (batch chunking by memory_bound and CPU staging dropped)."""
+        assert (t_start_idx < self.for_steps) & (t_end_idx <= self.for_steps)
+        self.scheduler.set_timesteps(self.for_steps, device=self.device)
+        ts = self.scheduler._ts_host
+        n = len(ts)
+        xt = xt.to(device=self.device, dtype=self.dtype).contiguous()
+        for i in range(n):
+            if t_end_idx == i:
+                return xt, self.scheduler.timesteps[i], i
+            elif i < t_start_idx:
+                continue
+            boost = performance_boosting and (self.performance_boosting_t_idx <= i) and \
+                (self.performance_boosting_t_idx != n - 1)
+            eta = 1 if boost else 0
+            et = self.unet(xt, ts[i])
+            noise = self.noise_fn(i, xt) if (eta and self.noise_fn is not None) else None
+            xt = self.scheduler.step(et, ts[i], xt, eta=eta, t_idx=i, noise=noise).prev_sample
+        if performance_boosting:
+            self.last_images.append(xt)
+        if save_image:
+            self._save_image(xt, f'{getattr(self, "EXP_NAME", "DDIMforward")}.png', nrow=xt.size(0))
+        if return_xt:
+            return xt
+        return
+
+    @torch.no_grad()
+    def x_space_guidance_direct(self, xt, t_idx, vk, single_edit_step):
+        """src/modules/edit.py:2618-2625."""
+        return ops.axpy(xt.contiguous(), vk.expand_as(xt).contiguous(), self.x_space_guidance_scale * single_edit_step)
+
+    def _save_image(self, x, name, nrow=8):
+        if not self.save_images:
+            return
+        try:
+            import torchvision.utils as tvu
+            tvu.save_image((x / 2 + 0.5).clamp(0, 1), os.path.join(self.result_folder, name), nrow=nrow)
+        except Exception as e:   # image writing is I/O polish, never fatal for the hot path
+            print("image not written:", e)

@@ -1,0 +1,203 @@
+"""Thin torch-facing wrappers over the C ABI (include/loco_b200.h).  Every function enqueues CUDA
+kernels of libloco_b200.so on torch's current stream; none of them has a PyTorch fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _f32(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    return t
+
+
+def _scratch(nbytes, device):
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned(buf):
+    off = (-buf.data_ptr()) % 256
+    return C.c_void_p(buf.data_ptr() + off)
+
+
+def pmp_forward(x, eps, at):
+    """(x - eps*sqrt(1-at))/sqrt(at) -- get_x0 without mask (reference modules/edit.py:2386)."""
+    out = torch.empty_like(_f32(x))
+    check(_lib.load().loco_pmp_forward(ptr(x), ptr(_f32(eps)), float(at), x.numel(), ptr(out), stream_ptr()),
+          "loco_pmp_forward")
+    return out
+
+
+def orthonormalise(W, v_prev=None):
+    """(V, s): V = Vh of svd(W) (rows, up to sign), s = sqrt(singular values)
+    (reference modules/edit.py:2482, 2499-2502)."""
+    lib = _lib.load()
+    W = _f32(W)
+    k, d = W.shape
+    V = torch.empty_like(W)
+    s = torch.empty(k, dtype=torch.float32, device=W.device)
+    scr = _scratch(lib.loco_orthonormalise_scratch_bytes(k), W.device)
+    check(lib.loco_orthonormalise(ptr(W), k, d, ptr(_f32(v_prev)) if v_prev is not None else None,
+                                  ptr(V), ptr(s), _aligned(scr), stream_ptr()), "loco_orthonormalise")
+    return V, s
+
+
+def nullspace_project(vT_mod, vT_null, project=True):
+    """normalise_rows(vT_mod - (Vn^T (Vn vT_mod^T))^T) (reference modules/edit.py:2317-2323)."""
+    lib = _lib.load()
+    vT_mod = _f32(vT_mod)
+    k, d = vT_mod.shape
+    kn = 0 if vT_null is None else vT_null.shape[0]
+    out = torch.empty_like(vT_mod)
+    scr = _scratch(8 * (kn * k + k), vT_mod.device)
+    check(lib.loco_nullspace_project(ptr(vT_mod), k, ptr(_f32(vT_null)) if kn else None, kn, d,
+                                     1 if (project and kn) else 0, ptr(out), _aligned(scr), stream_ptr()),
+          "loco_nullspace_project")
+    return out
+
+
+def ddim_step(xt, et, at, at_next, eta=0.0, noise=None, want_x0=False):
+    """YHCustomScheduler.step arithmetic (reference utils/utils.py:357-374)."""
+    xt = _f32(xt)
+    out = torch.empty_like(xt)
+    x0 = torch.empty_like(xt) if want_x0 else None
+    check(_lib.load().loco_ddim_step(ptr(xt), ptr(_f32(et)), ptr(_f32(noise)) if noise is not None else None,
+                                     float(at), float(at_next), float(eta), xt.numel(), ptr(out),
+                                     ptr(x0), stream_ptr()), "loco_ddim_step")
+    return (out, x0) if want_x0 else out
+
+
+def axpy(x, v, scale):
+    """x + scale * v (reference modules/edit.py:2623)."""
+    x = _f32(x)
+    out = torch.empty_like(x)
+    check(_lib.load().loco_axpy(ptr(x), ptr(_f32(v)), float(scale), x.numel(), ptr(out), stream_ptr()),
+          "loco_axpy")
+    return out
+
+
+def mask_indices(mask):
+    """Row-major indices of True entries: the selection order of `P_xt[:, mask]`
+    (reference modules/edit.py:2390).  Returns an int32 tensor (one host sync for the count)."""
+    m = mask.to(torch.uint8).contiguous().reshape(-1)
+    assert m.is_cuda
+    idx = torch.empty(m.numel(), dtype=torch.int32, device=m.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=m.device)
+    check(_lib.load().loco_mask_indices(ptr(m), m.numel(), ptr(idx), ptr(cnt), stream_ptr()),
+          "loco_mask_indices")
+    return idx[: int(cnt.item())]
+
+
+def gather_rows(src, idx):
+    src = _f32(src)
+    rows, d = src.shape
+    out = torch.empty(rows, idx.numel(), dtype=torch.float32, device=src.device)
+    check(_lib.load().loco_gather_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr()),
+          "loco_gather_rows")
+    return out
+
+
+def scatter_rows(src, idx, d):
+    src = _f32(src)
+    rows = src.shape[0]
+    out = torch.empty(rows, d, dtype=torch.float32, device=src.device)
+    check(_lib.load().loco_scatter_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr()),
+          "loco_scatter_rows")
+    return out
+
+
+def gram(A, B):
+    A, B = _f32(A), _f32(B)
+    G = torch.zeros(A.shape[0], B.shape[0], dtype=torch.float64, device=A.device)
+    check(_lib.load().loco_gram(ptr(A), A.shape[0], ptr(B), B.shape[0], A.shape[1], ptr(G), stream_ptr()),
+          "loco_gram")
+    return G
+
+
+class PullbackWorkspace:
+    """Buffers of one rank-k power method on a B200UNet (plan (1,k,k) + iteration scratch)."""
+
+    def __init__(self, unet, k):
+        self.lib = _lib.load()
+        self.unet, self.k = unet, k
+        R = unet.arch["resolution"]
+        self.d = 3 * R * R
+        self.plan = unet.plan(1, k, k)
+        dev = unet.device
+        self.scratch = _scratch(self.lib.loco_pullback_scratch_bytes(k, self.d), dev)
+        self.u_full = torch.empty(k, self.d, dtype=torch.float32, device=dev)
+        self.w = torch.empty(k, self.d, dtype=torch.float32, device=dev)
+        self.s = torch.empty(k, dtype=torch.float32, device=dev)
+        self.V = [torch.empty(k, self.d, dtype=torch.float32, device=dev) for _ in range(2)]
+
+    def iterate(self, xt, t, at, mask_u8, noise, V_in, V_out, align_sign=False):
+        check(self.lib.loco_pullback_iteration(
+            self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8) if mask_u8 is not None else None,
+            1 if noise else 0, ptr(V_in), self.k, self.d, 1 if align_sign else 0, ptr(self.u_full),
+            ptr(self.w), ptr(V_out), ptr(self.s), _aligned(self.scratch), stream_ptr()),
+            "loco_pullback_iteration")
+
+
+# ---------------------------------------------------------------------------------------------
+# single layers (parity tests)
+# ---------------------------------------------------------------------------------------------
+def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=False, out=None):
+    """kind: 0 3x3 | 1 1x1 | 2 3x3 stride-2 pad(0,1,0,1) | 3 dgrad of 0 | 4 dgrad of 2.
+    x: [N,H,W,C] channels-last contiguous; w: torch conv weight [Cout,Cin,k,k] of the forward conv."""
+    x, w = _f32(x), _f32(w)
+    N, H, W_, Cx = x.shape
+    Cout, Cin = w.shape[0], w.shape[1]
+    Ho, Wo = (H // 2, W_ // 2) if kind == 2 else ((2 * H, 2 * W_) if kind == 4 else (H, W_))
+    Cy = Cout if kind in (0, 1, 2) else Cin
+    if out is None:
+        out = torch.zeros(N, Ho, Wo, Cy, dtype=torch.float32, device=x.device)
+    wpack = torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+    check(_lib.load().loco_conv2d_nhwc(kind, ptr(x), N, H, W_, Cx, ptr(w), Cout, Cin, ptr(wpack),
+                                       ptr(bias), bias_rows, ptr(addend), 1 if accumulate else 0,
+                                       ptr(out), stream_ptr()), "loco_conv2d_nhwc")
+    return out
+
+
+def groupnorm_silu_fwd(x, n_primal, gamma, beta, eps, silu):
+    x = _f32(x)
+    N, H, W_, Cc = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(64 * N, dtype=torch.float64, device=x.device)
+    check(_lib.load().loco_groupnorm_silu_fwd(ptr(x), N, H, W_, Cc, n_primal, ptr(_f32(gamma)),
+                                              ptr(_f32(beta)), float(eps), 1 if silu else 0, ptr(y),
+                                              ptr(stats), stream_ptr()), "loco_groupnorm_silu_fwd")
+    return y
+
+
+def groupnorm_silu_vjp(xp, gy, gamma, beta, eps, silu):
+    xp, gy = _f32(xp), _f32(gy)
+    K, H, W_, Cc = gy.shape
+    gx = torch.empty_like(gy)
+    stats = torch.empty(64 * (K + 1), dtype=torch.float64, device=gy.device)
+    check(_lib.load().loco_groupnorm_silu_vjp(ptr(xp), H, W_, Cc, ptr(gy), K, ptr(_f32(gamma)),
+                                              ptr(_f32(beta)), float(eps), 1 if silu else 0, ptr(gx),
+                                              ptr(stats), stream_ptr()), "loco_groupnorm_silu_vjp")
+    return gx
+
+
+def attention_fwd(qkv, n_primal):
+    qkv = _f32(qkv)
+    N, T, C3 = qkv.shape
+    Cc = C3 // 3
+    S = torch.empty(N, T, T, dtype=torch.float32, device=qkv.device)
+    o = torch.empty(N, T, Cc, dtype=torch.float32, device=qkv.device)
+    check(_lib.load().loco_attention_fwd(ptr(qkv), N, T, Cc, n_primal, ptr(S), ptr(o), stream_ptr()),
+          "loco_attention_fwd")
+    return o, S
+
+
+def attention_vjp(go, qkv0, P0):
+    go = _f32(go)
+    K, T, Cc = go.shape
+    gP = torch.empty(K, T, T, dtype=torch.float32, device=go.device)
+    gqkv = torch.empty(K, T, 3 * Cc, dtype=torch.float32, device=go.device)
+    check(_lib.load().loco_attention_vjp(ptr(go), K, T, Cc, ptr(_f32(qkv0)), ptr(_f32(P0)), ptr(gP),
+                                         ptr(gqkv), stream_ptr()), "loco_attention_vjp")
+    return gqkv

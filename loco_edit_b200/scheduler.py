@@ -1,0 +1,84 @@
+"""Mirror of the reference's `YHCustomScheduler` (src/utils/utils.py:305-423) with the update
+arithmetic running in the `loco_ddim_step` CUDA kernel.
+
+Same protocol: `.set_timesteps(n, device=None, is_inversion=False)`, `.timesteps`,
+`.timesteps_next`, `.step(et, t, xt, eta=0.0, **kw) -> obj(.prev_sample, .x0)`, `.get_timesteps(t)`,
+`.return_alphas_cumprod()`.  Differences (host-sync removal only, same numbers):
+  * a host copy of the timestep list is kept, so `step` finds its index without `.tolist()` on a
+    device tensor; callers that know the index may pass `t_idx=` and skip the lookup entirely;
+  * alpha_bar values are read from a host copy of the fp32 table (the reference gathers them on the
+    device with `extract`, utils.py:444-461).
+"""
+import torch
+
+from . import ops
+
+
+class SchedulerOutput(object):
+    """src/utils/utils.py:300-303."""
+
+    def __init__(self, xt_next, P_xt):
+        self.prev_sample = xt_next
+        self.x0 = P_xt
+
+
+class YHCustomScheduler(object):
+    def __init__(self, args=None, device=None, dtype=torch.float32):
+        self.t_max = 999
+        ns = getattr(args, "noise_schedule", None) if args is not None else None
+        self.noise_schedule = "linear" if ns is None else ns
+        if self.noise_schedule != "linear":
+            raise NotImplementedError("only the linear schedule is used by the uncond hot path")
+        self.device = torch.device(device if device is not None else getattr(args, "device", "cuda:0"))
+        self.dtype = getattr(args, "dtype", dtype) if args is not None else dtype
+        self.timesteps = None
+        self.timesteps_next = None
+        self.learn_sigma = False
+        # utils.py:385-406: fp64 linspace betas -> cumprod -> cast to args.dtype
+        betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+        self.betas = betas.to(device=self.device, dtype=self.dtype)
+        acp = torch.cumprod(1.0 - betas, dim=0).to(self.dtype)
+        self._acp_host = acp.float().tolist()
+        self.alphas_cumprod = acp.to(self.device)
+
+    def set_timesteps(self, num_inferences, device=None, is_inversion=False):
+        # utils.py:316-329; built on the host in fp32, then moved (values identical to torch CPU)
+        seq = torch.linspace(0, 1, num_inferences) * self.t_max
+        if is_inversion:
+            seq = seq + 1e-6
+            seq_prev = torch.cat([torch.tensor([-1.0]), seq[:-1]], dim=0)
+            ts, tn = seq_prev[1:], seq[1:]
+        else:
+            seq_prev = torch.cat([torch.tensor([-1.0]), seq[:-1]], dim=0)
+            ts, tn = torch.flip(seq[1:], dims=[0]), torch.flip(seq_prev[1:], dims=[0])
+        self._ts_host, self._tn_host = ts.tolist(), tn.tolist()
+        dev = self.device if device is None else device
+        self.timesteps = ts.to(dev)
+        self.timesteps_next = tn.to(dev)
+
+    def get_timesteps(self, t):
+        # utils.py:331-337
+        t_idx = torch.where(self.timesteps == t)
+        return self.timesteps_next[t_idx]
+
+    def return_alphas_cumprod(self):
+        return self.alphas_cumprod
+
+    def alpha_at(self, t):
+        """extract(alphas_cumprod, t, .) for a scalar t: table entry at t.long() (utils.py:458)."""
+        return self._acp_host[int(float(t))]
+
+    def index_of(self, t):
+        return self._ts_host.index(float(t))      # exact float equality, like utils.py:353
+
+    def step(self, et, t, xt, eta=0.0, t_idx=None, noise=None, **kwargs):
+        assert et.shape == xt.shape, "et, xt shape should be same"
+        if t_idx is None:
+            t_idx = self.index_of(t)
+        at = self.alpha_at(self._ts_host[t_idx])
+        at_next = self.alpha_at(self._tn_host[t_idx])
+        if eta != 0 and noise is None:
+            noise = torch.randn_like(xt)                      # utils.py:374
+        xn, x0 = ops.ddim_step(xt.contiguous(), et.contiguous(), at, at_next, float(eta),
+                               noise=noise, want_x0=True)
+        return SchedulerOutput(xn, x0)

@@ -1,0 +1,282 @@
+"""GPU parity of single kernels (through the C ABI) against plain fp32/fp64 PyTorch references of
+the same op.  Tolerances are stated per test:
+  * tensor-core convs on tf32-representable inputs: products are exact, accumulation fp32 ->
+    relative error 1e-5 of the output norm;
+  * on arbitrary fp32 inputs the tensor core drops 13 mantissa bits of each operand -> 2e-3;
+  * CUDA-core kernels: fp32 round-off, 1e-5 relative;
+  * integer / index work and the DDIM update: bit-exact.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import max_err, nchw, nhwc, rel_err, tf32_round
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _conv_ref(kind, x_nchw, w, bias=None):
+    xd, wd = x_nchw.double(), w.double()
+    b = bias.double() if bias is not None else None
+    if kind == 0:
+        return F.conv2d(xd, wd, b, padding=1)
+    if kind == 1:
+        return F.conv2d(xd, wd, b)
+    if kind == 2:
+        return F.conv2d(F.pad(xd, (0, 1, 0, 1)), wd, b, stride=2)
+    if kind == 3:   # data gradient of a 3x3 pad-1 conv
+        return F.conv_transpose2d(xd, wd, padding=1)
+    if kind == 4:   # data gradient of pad(0,1,0,1) + stride-2 conv
+        N, _, h, w_ = xd.shape
+        full = F.conv_transpose2d(xd, wd, stride=2)          # [N, Cin, 2h+1, 2w+1]
+        return full[:, :, : 2 * h, : 2 * w_]
+    raise ValueError(kind)
+
+
+CONV_CASES = [
+    # kind, N, H, W, Cin, Cout
+    (0, 1, 16, 16, 128, 128),
+    (0, 6, 32, 32, 128, 128),
+    (0, 3, 8, 8, 256, 128),      # two samples per tile, odd batch
+    (0, 2, 64, 64, 256, 256),    # two output-channel tiles
+    (0, 5, 16, 16, 384, 128),
+    (1, 6, 32, 32, 256, 128),
+    (1, 2, 16, 16, 128, 384),    # fused q|k|v shape
+    (2, 4, 32, 32, 128, 128),
+    (2, 1, 16, 16, 256, 256),
+    (3, 5, 32, 32, 128, 256),    # dy has Cout=256 channels -> dx has 128
+    (3, 2, 8, 8, 256, 128),
+    (4, 3, 16, 16, 128, 128),    # dy [3,16,16,128] -> dx [3,32,32,128]
+    (4, 5, 8, 8, 256, 256),
+]
+
+
+@pytest.mark.parametrize("kind,N,H,W,Cin,Cout", CONV_CASES)
+def test_conv_tcgen05_exact_inputs(dev, kind, N, H, W, Cin, Cout):
+    from loco_edit_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(kind * 1000 + N * 100 + H)
+    ksz = 1 if kind == 1 else 3
+    w = tf32_round(torch.randn(Cout, Cin, ksz, ksz, generator=g) / (Cin * ksz * ksz) ** 0.5).to(dev)
+    cx = Cin if kind in (0, 1, 2) else Cout
+    x = tf32_round(torch.randn(N, cx, H, W, generator=g)).to(dev)
+    ref = _conv_ref(kind, x, w)
+    y = ops.conv2d_nhwc(kind, nhwc(x), w)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(y), ref)
+    print(f"conv kind={kind} N={N} {H}x{W} {Cin}->{Cout}: rel_err={e:.3e} max={max_err(nchw(y), ref):.3e}")
+    assert e < 1e-5
+
+
+def test_conv_epilogue_bias_addend_accumulate(dev):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cin, Cout = 4, 16, 16, 128, 256
+    w = tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / 34.0).to(dev)
+    x = tf32_round(torch.randn(N, Cin, H, W, generator=g)).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    add = torch.randn(N, Cout, H, W, generator=g).to(dev)
+    base = torch.randn(N, Cout, H, W, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.double(), padding=1) + add.double() + base.double()
+    ref[:2] += bias.double()[None, :, None, None]                  # bias on the first 2 rows only
+    out = nhwc(base).clone()
+    ops.conv2d_nhwc(0, nhwc(x), w, bias=bias, bias_rows=2, addend=nhwc(add), accumulate=True, out=out)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out), ref) < 1e-5
+
+
+def test_conv_tcgen05_fp32_inputs_tf32_tolerance(dev):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    N, H, W, Cin, Cout = 2, 32, 32, 128, 128
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / 34.0).to(dev)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    y = ops.conv2d_nhwc(0, nhwc(x), w)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(y), ref)
+    print("tf32 conv on raw fp32 inputs: rel_err", e)
+    assert e < 2e-3
+
+
+def _gn_silu(x, gamma, beta, eps, silu):
+    y = F.group_norm(x, 32, gamma, beta, eps)
+    return y * torch.sigmoid(y) if silu else y
+
+
+@pytest.mark.parametrize("C,H,silu", [(128, 32, True), (384, 16, True), (512, 8, False), (768, 8, True)])
+def test_groupnorm_silu_fwd_jvp(dev, C, H, silu):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    k = 3
+    x = (torch.randn(1, C, H, H, generator=g) * 1.5 + 0.3).to(dev)
+    dx = torch.randn(k, C, H, H, generator=g).to(dev)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev)
+    eps = 1e-6
+    f = lambda z: _gn_silu(z, gamma.double(), beta.double(), eps, silu)
+    yref = f(x.double())
+    dys = [torch.func.jvp(f, (x.double(),), (dx[j:j + 1].double(),))[1] for j in range(k)]
+    ref = torch.cat([yref] + dys, 0)
+    y = ops.groupnorm_silu_fwd(nhwc(torch.cat([x, dx], 0)), 1, gamma, beta, eps, silu)
+    torch.cuda.synchronize()
+    e0, e1 = rel_err(nchw(y)[:1], ref[:1]), rel_err(nchw(y)[1:], ref[1:])
+    print(f"gn C={C} H={H} silu={silu}: primal {e0:.2e} tangent {e1:.2e}")
+    assert e0 < 1e-5 and e1 < 1e-5
+    # plain forward over a batch of primal rows
+    xb = torch.randn(3, C, H, H, generator=g).to(dev)
+    yb = ops.groupnorm_silu_fwd(nhwc(xb), 3, gamma, beta, eps, silu)
+    assert rel_err(nchw(yb), f(xb.double())) < 1e-5
+
+
+@pytest.mark.parametrize("C,H,silu", [(128, 32, True), (512, 8, False), (384, 16, True)])
+def test_groupnorm_silu_vjp(dev, C, H, silu):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(C * 3 + H)
+    k = 3
+    x = (torch.randn(1, C, H, H, generator=g) * 1.5 + 0.3).to(dev)
+    gy = torch.randn(k, C, H, H, generator=g).to(dev)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev)
+    eps = 1e-6
+    xd = x.double().requires_grad_(True)
+    y = _gn_silu(xd, gamma.double(), beta.double(), eps, silu)
+    ref = torch.cat([torch.autograd.grad(y, xd, gy[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
+    gx = ops.groupnorm_silu_vjp(nhwc(x), nhwc(gy), gamma, beta, eps, silu)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(gx), ref)
+    print(f"gn vjp C={C} H={H} silu={silu}: {e:.2e}")
+    assert e < 1e-5
+
+
+def _attn_core(qkv):   # qkv [N, T, 3C] -> o [N, T, C]   (reference ddpm/diffusion.py:950-962)
+    C = qkv.shape[-1] // 3
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    w = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (int(C) ** -0.5), dim=2)
+    return torch.bmm(w, v)
+
+
+@pytest.mark.parametrize("T,C", [(64, 128), (256, 512)])
+def test_attention_fwd_jvp_vjp(dev, T, C):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(T + C)
+    k = 2
+    qkv = torch.randn(1, T, 3 * C, generator=g).to(dev)
+    dq = torch.randn(k, T, 3 * C, generator=g).to(dev)
+    oref = _attn_core(qkv.double())
+    dref = torch.cat([torch.func.jvp(_attn_core, (qkv.double(),), (dq[j:j + 1].double(),))[1] for j in range(k)], 0)
+    o, S = ops.attention_fwd(torch.cat([qkv, dq], 0).contiguous(), 1)
+    torch.cuda.synchronize()
+    # the stored o is rounded to tf32 for the following tensor-core projection: 2^-11 relative
+    assert rel_err(o[:1], oref) < 5e-4 and rel_err(o[1:], dref) < 5e-4
+    go = torch.randn(k, T, C, generator=g).to(dev)
+    qd = qkv.double().requires_grad_(True)
+    od = _attn_core(qd)
+    gref = torch.cat([torch.autograd.grad(od, qd, go[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
+    gq = ops.attention_vjp(go, qkv, S[0].contiguous())
+    torch.cuda.synchronize()
+    e = rel_err(gq, gref)
+    print(f"attention T={T} C={C}: vjp rel_err {e:.2e}")
+    assert e < 5e-4
+    # batch of primal rows only
+    qb = torch.randn(3, T, 3 * C, generator=g).to(dev)
+    ob, _ = ops.attention_fwd(qb, 3)
+    assert rel_err(ob, _attn_core(qb.double())) < 5e-4
+
+
+@pytest.mark.parametrize("k,d", [(1, 3072), (5, 196608), (22, 12288), (64, 49152)])
+def test_orthonormalise_matches_svd(dev, k, d):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(k)
+    W = torch.randn(k, d, generator=g)
+    W = (W * torch.linspace(3.0, 1.0, k)[:, None]).to(dev)
+    V, s = ops.orthonormalise(W)
+    torch.cuda.synchronize()
+    _, sv, vh = torch.linalg.svd(W.double().cpu(), full_matrices=False)
+    assert torch.allclose(s.cpu().double(), sv.sqrt(), rtol=1e-4)       # reference returns s.sqrt()
+    gram = (V.double() @ V.double().T).cpu()
+    assert float((gram - torch.eye(k, dtype=torch.float64)).abs().max()) < 1e-4
+    dots = (V.double().cpu() * vh).sum(1).abs()
+    assert float((1 - dots).max()) < 1e-3, dots
+    # sign alignment against a previous basis
+    Vp = (-V).contiguous()
+    V2, _ = ops.orthonormalise(W, v_prev=Vp)
+    assert float(((V2 * Vp).sum(1)).min()) > 0.99
+
+
+@pytest.mark.parametrize("k,kn,d,project", [(5, 5, 196608, True), (2, 3, 3072, True), (3, 10, 12288, True), (4, 5, 3072, False)])
+def test_nullspace_project(dev, k, kn, d, project):
+    from loco_edit_b200 import ops
+    from oracle import pullback_ref
+    g = torch.Generator().manual_seed(k * 7 + kn)
+    vm = torch.randn(k, d, generator=g)
+    vn, _ = torch.linalg.qr(torch.randn(d, kn, generator=g))
+    vn = vn.T.contiguous()
+    ref = pullback_ref.nullspace_project(vm, vn, kn, project)
+    out = ops.nullspace_project(vm.to(dev), vn.to(dev), project)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu(), ref) < 1e-5
+    if project:
+        assert float((out.cpu().double() @ vn.double().T).abs().max()) < 1e-5
+
+
+def test_ddim_step_bit_exact(dev):
+    from loco_edit_b200 import ops
+    from oracle import pullback_ref
+    s = pullback_ref.RefScheduler()
+    g = torch.Generator().manual_seed(2)
+    xt = torch.randn(2, 3, 32, 32, generator=g)
+    et = torch.randn(2, 3, 32, 32, generator=g)
+    nz = torch.randn(2, 3, 32, 32, generator=g)
+    for inv in (False, True):
+        s.set_timesteps(100, is_inversion=inv)
+        for idx in (0, 17, 40, 79, 98):
+            t, tn = s.timesteps[idx], s.timesteps_next[idx]
+            at, atn = float(s.alpha(t)), float(s.alpha(tn))
+            ref, p = s.step(et, t, xt, eta=0)
+            out, x0 = ops.ddim_step(xt.to(dev), et.to(dev), at, atn, 0.0, want_x0=True)
+            assert torch.equal(out.cpu(), ref) and torch.equal(x0.cpu(), p), (inv, idx)
+            if not inv:
+                ref1, _ = s.step(et, t, xt, eta=1, noise=nz)
+                out1 = ops.ddim_step(xt.to(dev), et.to(dev), at, atn, 1.0, noise=nz.to(dev))
+                assert torch.equal(out1.cpu(), ref1), (inv, idx)
+    # PMP and edit step share the op order
+    at = float(s.alphas_cumprod[595])
+    pm = ops.pmp_forward(xt.to(dev), et.to(dev), at)
+    a = s.alphas_cumprod[595]
+    assert torch.equal(pm.cpu(), (xt - et * (1 - a).sqrt()) / a.sqrt())
+    ed = ops.axpy(xt.to(dev), et.to(dev), 0.5)
+    assert torch.equal(ed.cpu(), xt + 0.5 * 1.0 * et)
+
+
+def test_mask_selection_bit_exact(dev):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for shape in [(3, 32, 32), (3, 256, 256), (3, 7, 5)]:
+        for mask in [torch.rand(shape, generator=g) < 0.3, torch.zeros(shape, dtype=torch.bool),
+                     torch.ones(shape, dtype=torch.bool)]:
+            idx = ops.mask_indices(mask.to(dev))
+            ref = mask.reshape(-1).nonzero().reshape(-1)
+            assert torch.equal(idx.cpu().long(), ref)
+            x = torch.randn(4, *shape, generator=g)
+            sel = ops.gather_rows(x.reshape(4, -1).to(dev), idx)
+            assert torch.equal(sel.cpu(), x[:, mask])                 # P_xt[:, mask] order
+            back = ops.scatter_rows(sel, idx, x[0].numel())
+            assert torch.equal(back.cpu(), (x * mask).reshape(4, -1))
+
+
+def test_gram(dev):
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for ka, kb, d in [(5, 5, 196608), (3, 7, 1000), (40, 64, 8192), (9, 2, 333)]:
+        A, B = torch.randn(ka, d, generator=g), torch.randn(kb, d, generator=g)
+        G = ops.gram(A.to(dev), B.to(dev))
+        ref = A.double() @ B.double().T
+        assert float((G.cpu() - ref).abs().max()) < 1e-3 * (d ** 0.5) * 1e-2

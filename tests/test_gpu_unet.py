@@ -1,0 +1,158 @@
+"""GPU parity of the U-Net executor (forward, fused primal+tangent JVP, VJP) and of one full
+power iteration against the CPU oracle and the reference-generated golden fixtures.
+
+Tolerances: the tensor-core convolutions run in TF32 (10-bit mantissa operands, fp32 accumulate),
+which is also what the reference's own GPU path uses (torch default cudnn.allow_tf32=True), while
+the oracle is exact fp32 on CPU.  Measured spread is ~1e-3 relative per pass; asserted bounds:
+  eps / JVP / VJP fields: relative L2 error < 5e-3
+  <Jv, g> == <v, J^T g> (same kernels both ways): relative 2e-3
+  singular values: 1e-3 relative; principal angles < 1 degree   (north_star tolerances)
+"""
+import os
+
+import pytest
+import torch
+
+from gpu_util import principal_angles_deg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ARCHS = {
+    "two_level_attn16": dict(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1),
+    "three_level_attn8": dict(resolution=32, ch_mult=(1, 1, 2), attn_resolutions=(8,), num_res_blocks=2),
+}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _setup(name, dev, perturb=0.1, seed=1234):
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict, tiny_arch
+    from oracle import ddpm_ref
+    arch = tiny_arch(**ARCHS[name])
+    sd = random_state_dict(arch, seed=seed, perturb_norm=perturb)
+    return arch, sd, B200UNet(arch, sd, device=dev), ddpm_ref.RefUNet(arch, sd)
+
+
+@pytest.mark.parametrize("name", list(ARCHS))
+def test_unet_forward_matches_oracle(dev, name):
+    arch, sd, net, ref = _setup(name, dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 3, arch["resolution"], arch["resolution"], generator=g)
+    t = torch.tensor(595.3636)
+    with torch.no_grad():
+        eref = ref(x, t)
+    e = net(x.to(dev), t)
+    torch.cuda.synchronize()
+    err = rel_err(e.cpu(), eref)
+    print(f"{name}: forward rel_err {err:.3e}")
+    assert torch.isfinite(e).all()
+    assert err < 5e-3
+
+
+@pytest.mark.parametrize("name", list(ARCHS))
+def test_unet_jvp_vjp_match_oracle(dev, name):
+    arch, sd, net, ref = _setup(name, dev)
+    R = arch["resolution"]
+    g = torch.Generator().manual_seed(1)
+    k = 3
+    x = torch.randn(1, 3, R, R, generator=g)
+    V = torch.randn(k, 3, R, R, generator=g)
+    G = torch.randn(k, 3, R, R, generator=g)
+    t = torch.tensor(595.3636)
+    f = lambda z: ref(z, t)
+    eref, dref = [], []
+    for j in range(k):
+        e0, de = torch.func.jvp(f, (x,), (V[j:j + 1],))
+        dref.append(de)
+    dref = torch.cat(dref, 0)
+    xg = x.clone().requires_grad_(True)
+    out = f(xg)
+    gref = torch.cat([torch.autograd.grad(out, xg, G[j:j + 1], retain_graph=True)[0] for j in range(k)], 0)
+    eps, deps = net.jvp(x.to(dev), t, V.to(dev))
+    gx = net.vjp(k, G.to(dev))
+    torch.cuda.synchronize()
+    e_p, e_t, e_g = rel_err(eps.cpu(), e0), rel_err(deps.cpu(), dref), rel_err(gx.cpu(), gref)
+    print(f"{name}: primal {e_p:.3e} jvp {e_t:.3e} vjp {e_g:.3e}")
+    assert e_p < 5e-3 and e_t < 5e-3 and e_g < 5e-3
+    # adjoint identity between the two CUDA passes
+    lhs = (deps.double() * G.to(dev).double()).sum(dim=(1, 2, 3))
+    rhs = (V.to(dev).double() * gx.double()).sum(dim=(1, 2, 3))
+    scale = deps.double().flatten(1).norm(dim=1) * G.to(dev).double().flatten(1).norm(dim=1)
+    print("adjoint gap / (|Jv||g|):", ((lhs - rhs).abs() / scale).tolist())
+    assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
+
+
+@pytest.mark.parametrize("case", ["mask_k2", "notmask_k3", "nomask_k2", "noise_k2"])
+def test_power_iteration_matches_reference_golden(dev, golden_dir, case):
+    """Same weights, x_t, t, mask and V0 as the reference run in tests/golden/make_golden.py."""
+    from loco_edit_b200.edit import local_basis
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict
+    g = torch.load(os.path.join(golden_dir, "pullback_tiny.pt"), weights_only=False)
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    net = B200UNet(g["arch"], sd, device=dev)
+    kw = {"mask_k2": dict(mask=g["mask"], k=2), "notmask_k3": dict(mask=~g["mask"], k=3),
+          "nomask_k2": dict(mask=None, k=2), "noise_k2": dict(mask=g["mask"], k=2, noise=True)}[case]
+    k = kw.pop("k")
+    d = g["xt"].numel()
+    torch.manual_seed(g["v0_seed"])
+    v0, _ = torch.linalg.qr(torch.randn(d, k))
+    from loco_edit_b200.scheduler import YHCustomScheduler
+    sched = YHCustomScheduler(device=dev)
+    for n_iter in (1, 3):
+        ref = g["cases"][case][n_iter]
+        mask = kw.get("mask")
+        u, s, vT = local_basis(net, sched, g["xt"].to(dev), g["t"], k, v0=v0.T.contiguous().to(dev),
+                               min_iter=10 ** 6, max_iter=n_iter, mask=None if mask is None else mask.to(dev),
+                               noise=kw.get("noise", False), verbose=False)
+        torch.cuda.synchronize()
+        srel = float(((s.cpu() - ref["s"]).abs() / ref["s"]).max())
+        ang = float(principal_angles_deg(vT, ref["vT"]).max())
+        print(f"{case} N={n_iter}: s rel {srel:.2e}, max principal angle {ang:.3f} deg")
+        assert srel < 1e-3
+        assert ang < 1.0
+        uref = ref["u"].reshape(ref["u"].shape[0], -1)
+        assert tuple(u.shape) == tuple(uref.shape)
+        assert rel_err(u.cpu(), uref) < 5e-3
+
+
+def test_full_size_ddpm256_properties(dev):
+    """BASELINE config-1 size (256x256, 113.7 M parameters): properties that need no CPU oracle run."""
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import DDPM256, random_state_dict
+    sd = random_state_dict(DDPM256, seed=1234)
+    net = B200UNet(DDPM256, sd, device=dev)
+    g = torch.Generator().manual_seed(0)
+    k = 5
+    x = (0.5 * torch.randn(1, 3, 256, 256, generator=g)).clamp(-1, 1).to(dev)
+    V = torch.randn(k, 3, 256, 256, generator=g).to(dev)
+    G = torch.randn(k, 3, 256, 256, generator=g).to(dev)
+    t = 595.3636
+    eps, deps = net.jvp(x, t, V)
+    gx = net.vjp(k, G)
+    e1 = net(x, t)
+    torch.cuda.synchronize()
+    assert torch.isfinite(eps).all() and torch.isfinite(deps).all() and torch.isfinite(gx).all()
+    # primal row of the fused pass == plain forward
+    assert rel_err(eps, e1) < 1e-5
+    # linearity of the tangent rows: J(2 v0 - v1) = 2 J v0 - J v1
+    V2 = V.clone()
+    V2[2] = 2 * V[0] - V[1]
+    _, d2 = net.jvp(x, t, V2)
+    assert rel_err(d2[2], 2 * deps[0] - deps[1]) < 2e-3
+    # adjoint identity
+    lhs = (deps.double() * G.double()).sum(dim=(1, 2, 3))
+    rhs = (V.double() * gx.double()).sum(dim=(1, 2, 3))
+    scale = deps.double().flatten(1).norm(dim=1) * G.double().flatten(1).norm(dim=1)
+    print("256^2 adjoint gap:", ((lhs - rhs).abs() / scale).tolist())
+    assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
+    # batch of primal rows == row-by-row
+    xb = torch.randn(3, 3, 256, 256, generator=g).to(dev)
+    eb = net(xb, t)
+    e0 = net(xb[1:2].contiguous(), t)
+    assert rel_err(eb[1:2], e0) < 1e-5
