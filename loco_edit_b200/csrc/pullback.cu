@@ -415,6 +415,12 @@ int orthonormalise(const float* W, int k, long long d, const float* v_prev, floa
   LOCO_TRY(gram(W, k, W, k, d, scratch, s));
   if (v_prev) LOCO_TRY(gram(W, k, v_prev, k, d, scratch + k * k, s));
   const size_t smem = sizeof(double) * (size_t)(2 * k * k + k) + sizeof(int) * (size_t)k;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(eig_transform_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
   eig_transform_kernel<<<1, 64, smem, s>>>(scratch, k, v_prev ? 1 : 0, s_out);
   LOCO_CHECK_CUDA(cudaGetLastError());
   apply_transform_kernel<<<grid_for(d, 256), 256, sizeof(float) * (size_t)(k * k), s>>>(

