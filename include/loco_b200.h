@@ -42,6 +42,12 @@ typedef struct loco_arch {
 
 int loco_abi_version(void);
 const char* loco_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process */
+long long loco_launch_count(void);
+/* per-kernel-family CUDA-event timing (family 0 = tcgen05 conv GEMM [work = FLOPs], 1 = GroupNorm
+ * [work = algorithmic bytes], 2 = other): enable, run the workload, then collect (device sync). */
+int loco_profile_enable(int on);
+int loco_profile_collect(double* ms, double* work, long long* launches, int nfam);
 
 /* ---------------- model: parameters by reference state_dict name ---------------- */
 int loco_unet_create(const loco_arch_t* arch, loco_unet_t** out);

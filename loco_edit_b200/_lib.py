@@ -32,6 +32,9 @@ _F = C.c_float
 PROTOTYPES = {
     "loco_abi_version": (_I, []),
     "loco_last_error": (C.c_char_p, []),
+    "loco_launch_count": (_LL, []),
+    "loco_profile_enable": (_I, [_I]),
+    "loco_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL), _I]),
     "loco_unet_create": (_I, [C.POINTER(Arch), C.POINTER(_P)]),
     "loco_unet_destroy": (None, [_P]),
     "loco_unet_weight_floats": (_LL, [_P]),

@@ -39,6 +39,11 @@ static int require_device() {
 extern "C" {
 
 int loco_abi_version(void) { return 1; }
+long long loco_launch_count(void) { return launch_count(); }
+int loco_profile_enable(int on) { profile_enable(on != 0); return 0; }
+int loco_profile_collect(double* ms, double* work, long long* launches, int nfam) {
+  return profile_collect(ms, work, launches, nfam);
+}
 const char* loco_last_error(void) { return get_error(); }
 
 // ------------------------------------------------------------------------------------------------

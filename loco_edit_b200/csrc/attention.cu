@@ -126,7 +126,7 @@ int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long lon
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
   batched_gemm_kernel<<<grid, 256, 0, s>>>(A, B, C, sCm, sCn, sCb, M, N, K, alpha, beta, round_out,
                                            A.s1 == 1 ? 1 : 0, B.s1 == 1 ? 1 : 0);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -134,14 +134,14 @@ int softmax_rows(float* S, int T, int batch, float scale, cudaStream_t s) {
   if (batch <= 0) return 0;
   const long long rows = (long long)batch * T;
   softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, T, rows, scale);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int softmax_lin_rows(const float* P0, float* X, int T, int batch, float scale, cudaStream_t s) {
   if (batch <= 0) return 0;
   const long long rows = (long long)batch * T;
   softmax_lin_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(P0, X, T, rows, scale);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -64,6 +64,19 @@ inline View slice_n(const View& v, int n0, int N) {
 
 int num_sms();
 
+// Launch accounting (bench.py's `gpu_launches`) and optional per-kernel-family event timing
+// (bench.py's roofline leg).  Families: 0 = tcgen05 conv GEMM, 1 = GroupNorm, 2 = other.
+void count_launch(int n = 1);
+long long launch_count();
+struct ProfScope {   // records a start/stop event pair around a launch when profiling is on
+  ProfScope(int family, double work, cudaStream_t s);
+  ~ProfScope();
+  int family; cudaStream_t stream; int slot;
+};
+void profile_enable(bool on);
+// sums elapsed ms / work / launches per family since profile_enable(true); synchronises the device
+int profile_collect(double* ms, double* work, long long* launches, int nfam);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // Device-side PTX wrappers

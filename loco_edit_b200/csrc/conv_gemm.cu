@@ -427,8 +427,12 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  for (int i = 0; i < L.nlaunch; ++i) {
-    conv_gemm_tf32_kernel<<<L.grid[i], kThreads, kSmemBytes, stream>>>(L.p[i]);
+  {
+    ProfScope prof(0, L.flops, stream);
+    for (int i = 0; i < L.nlaunch; ++i) {
+      conv_gemm_tf32_kernel<<<L.grid[i], kThreads, kSmemBytes, stream>>>(L.p[i]);
+    }
+    count_launch(L.nlaunch);
   }
   LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -168,7 +168,7 @@ template <int MODE>
 __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float eps, int silu, double* __restrict__ stats, int ppb) {
-  __shared__ float red[kGroups][2];
+  __shared__ float part[2][256];
   const int C = x.C;
   const int cvn = C >> 2;
   const int cg = C / kGroups;
@@ -180,9 +180,6 @@ __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __r
   const long long HW = (long long)x.H * x.W;
   const long long p0 = (long long)blockIdx.x * ppb;
   const long long p1 = min(HW, p0 + ppb);
-  if (threadIdx.x < kGroups * 2) (&red[0][0])[threadIdx.x] = 0.f;
-  __syncthreads();
-
   float s1 = 0.f, s2 = 0.f;
   if (MODE == 0) {
     const bool primal = n < n_primal;
@@ -227,11 +224,16 @@ __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __r
       }
     }
   }
-  atomicAdd(&red[g][0], s1);
-  atomicAdd(&red[g][1], s2);
+  // fixed-order block reduction (bit-reproducible per block); fp64 atomics across blocks
+  part[0][threadIdx.x] = s1;
+  part[1][threadIdx.x] = s2;
   __syncthreads();
   if (threadIdx.x < kGroups * 2) {
-    const float v = (&red[0][0])[threadIdx.x];
+    const int gg = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int cv0 = gg * (cg >> 2), cv1 = cv0 + (cg >> 2);
+    float v = 0.f;
+    for (int pr = 0; pr < pstep; ++pr)
+      for (int c = cv0; c < cv1; ++c) v += part[which][pr * cvn + c];
     atomicAdd(&stats[(long long)n * kGroups * 2 + threadIdx.x], (double)v);
   }
 }
@@ -470,7 +472,7 @@ int check_gn_view(const View& v, const char* what) {
 int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * kh * kw;
   pack_fprop_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int kw, int cout_total,
@@ -478,12 +480,12 @@ int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int k
   const long long total = (long long)Cout * Cin * kh * kw;
   pack_dgrad_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw, cout_total,
                                                         co_off);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t s) {
   pack_edge_kernel<<<grid_for(27 * C, 256), 256, 0, s>>>(w, dst, C, in_is_3);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -496,7 +498,7 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
   const size_t smem = 27 * out.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_expand: C=%d too large", out.C);
   edge_expand_kernel<<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3,
@@ -507,7 +509,7 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   const size_t smem = 27 * in.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_reduce: C=%d too large", in.C);
   edge_reduce_kernel<<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -515,9 +517,10 @@ int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
   const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
   dim3 grid(g.nblk, x.N);
+  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 2 : 1), s);
   gn_stats_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
                                               stats, g.ppb);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, const float* beta,
@@ -526,9 +529,10 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
   const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
   dim3 grid(g.nblk, x.N);
+  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 3 : 2), s);
   gn_apply_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps, silu,
                                               round_out, nullptr, 0, 0, 0, 0, y, g.ppb);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, const float* beta,
@@ -537,9 +541,10 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
   const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
   dim3 grid(g.nblk, gy.N);
+  ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * 2, s);
   gn_stats_kernel<1><<<grid, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats,
                                               g.ppb);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, const float* gamma,
@@ -551,11 +556,12 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
   const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
   dim3 grid(g.nblk, gy.N);
+  ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * (addend ? 4 : 3), s);
   gn_apply_kernel<1><<<grid, g.block, 0, s>>>(
       xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
       addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx,
       g.ppb);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -564,7 +570,7 @@ int upsample2x(View in, View out, cudaStream_t s) {
                "upsample2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
   upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int sumpool2x(View in, View out, int accumulate, cudaStream_t s) {
@@ -572,7 +578,7 @@ int sumpool2x(View in, View out, int accumulate, cudaStream_t s) {
                "sumpool2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
   sumpool2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int add_views(View in, View out, int accumulate, cudaStream_t s) {
@@ -580,7 +586,7 @@ int add_views(View in, View out, int accumulate, cudaStream_t s) {
                "add_views: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
   add_views_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -588,13 +594,13 @@ int temb_forward(float t, int ch, const float* w0, const float* b0, const float*
                  float* scratch, cudaStream_t s) {
   const size_t smem = (size_t)(ch + 4 * ch) * sizeof(float);
   temb_kernel<<<1, 512, smem, s>>>(t, ch, w0, b0, w1, b1, scratch);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int temb_project(const float* temb_act, int temb_ch, const float* w, const float* b, int cout,
                  float* out, cudaStream_t s) {
   temb_project_kernel<<<(cout + 7) / 8, 256, 0, s>>>(temb_act, temb_ch, w, b, cout, out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -381,13 +381,13 @@ int pmp_jvp_epilogue(const float* v, const float* eps_dot, const unsigned char* 
                      cudaStream_t s) {
   pmp_jvp_kernel<<<grid_for((long long)k * d, 256), 256, 0, s>>>(v, eps_dot, mask, at, noise, k, d, u,
                                                                 g_eps, gx_direct);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pmp_forward(const float* x, const float* eps, float at, long long n, float* out,
                 cudaStream_t s) {
   pmp_fwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, eps, at, n, out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -404,7 +404,7 @@ int gram(const float* A, int ka, const float* B, int kb, long long d, double* G,
     const int blocks = (int)((slabs + spb - 1) / spb);
     gram_big_kernel<<<blocks, 256, 0, s>>>(A, ka, B, kb, d, G, spb);
   }
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -422,10 +422,10 @@ int orthonormalise(const float* W, int k, long long d, const float* v_prev, floa
     attr_set = true;
   }
   eig_transform_kernel<<<1, 64, smem, s>>>(scratch, k, v_prev ? 1 : 0, s_out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   apply_transform_kernel<<<grid_for(d, 256), 256, sizeof(float) * (size_t)(k * k), s>>>(
       W, scratch + 2 * k * k, k, d, V);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -438,9 +438,9 @@ int nullspace_project(const float* vT_mod, int k, const float* Vn, int k_null, l
   if (project && k_null > 0) LOCO_TRY(gram(Vn, k_null, vT_mod, k, d, C, s));
   nullproj_kernel<<<grid_for(d, 256), 256, sizeof(float) * (size_t)(k_null * k + 1), s>>>(
       vT_mod, k, Vn, k_null, d, C, (project && k_null > 0) ? 1 : 0, out, norms);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   scale_rows_kernel<<<grid_for((long long)k * d, 256), 256, 0, s>>>(out, k, d, norms);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -449,19 +449,19 @@ int ddim_step(const float* xt, const float* et, const float* noise, float at, fl
   LOCO_REQUIRE(eta == 0.f || noise != nullptr, "ddim_step: eta > 0 needs a noise tensor");
   ddim_step_kernel<<<grid_for(n, 256), 256, 0, s>>>(xt, et, noise, at, at_next, eta, n, xt_next,
                                                    x0_pred);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int axpy(const float* x, const float* v, float scale, long long n, float* out, cudaStream_t s) {
   axpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, v, scale, n, out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mask_indices(const unsigned char* mask, long long d, int* idx, int* count_out, cudaStream_t s) {
   LOCO_REQUIRE(d < (1LL << 31), "mask_indices: d too large");
   mask_indices_kernel<<<1, 1024, 0, s>>>(mask, d, idx, count_out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int gather_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
@@ -469,7 +469,7 @@ int gather_rows(const float* src, int rows, long long d, const int* idx, int cou
   if (count == 0 || rows == 0) return 0;
   gather_rows_kernel<<<grid_for((long long)rows * count, 256), 256, 0, s>>>(src, rows, d, idx, count,
                                                                            out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int scatter_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
@@ -478,7 +478,7 @@ int scatter_rows(const float* src, int rows, long long d, const int* idx, int co
   if (count == 0 || rows == 0) return 0;
   scatter_rows_kernel<<<grid_for((long long)rows * count, 256), 256, 0, s>>>(src, rows, d, idx,
                                                                             count, out);
-  LOCO_CHECK_CUDA(cudaGetLastError());
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -27,6 +27,42 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; int family; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+void profile_enable(bool on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on;
+}
+ProfScope::ProfScope(int fam, double work, cudaStream_t s) : family(fam), stream(s), slot(-1) {
+  if (!g_prof_on) return;
+  ProfRec r; r.family = fam; r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+int profile_collect(double* ms, double* work, long long* launches, int nfam) {
+  LOCO_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < nfam; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    if (r.family < nfam) { ms[r.family] += t; work[r.family] += r.work; launches[r.family] += 1; }
+  }
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -1,0 +1,86 @@
+"""In-memory editing pipeline: the BASELINE config-1 "edit" as one call.
+
+    images = EditPipeline(unet).edit(x0, mask)
+
+runs, for one image, exactly the sequence of the reference's `run_edit_null_space_projection`
+(src/modules/edit.py:2216-2366) for one principal direction:
+  DDIM inversion (98 U-Net calls) -> forward to t = edit_t (40 calls) -> rank-k local basis of the
+  masked PMP Jacobian (n_iter power iterations) -> rank-k_null basis of the complement mask ->
+  null-space projection -> +/- edits along direction `pc` -> 59 DDIM steps on the batch of 2*vis_num-1
+  latents with eta = 1 for t <= 0.2 T.
+Nothing is written to disk here (the file-producing driver is `EditUncondDiffusion`); host tensors
+go in and come out, so the call is the unit bench.py times end to end.
+"""
+import types
+
+import torch
+
+from . import ops
+from .edit import EditUncondDiffusion, local_basis
+
+
+class EditPipeline(object):
+    def __init__(self, unet, k=5, k_null=5, edit_t=0.6, n_iter=12, scale=0.5, num_step=16, vis_num=2,
+                 for_steps=100, inv_steps=100, boost_t=0.2, result_folder="/tmp/loco_b200_runs"):
+        self.unet = unet
+        self.device = unet.device
+        self.k, self.k_null, self.n_iter = k, k_null, n_iter
+        self.vis_num = vis_num
+        args = types.SimpleNamespace(
+            device=self.device, dtype=torch.float32, seed=1, model_name="CelebA_HQ_HF",
+            dataset_name="CelebA_HQ_mask", image_size=unet.arch["resolution"], for_steps=for_steps,
+            inv_steps=inv_steps, edit_t=edit_t, performance_boosting_t=boost_t,
+            x_space_guidance_edit_step=1.0, x_space_guidance_scale=scale,
+            x_space_guidance_num_step=num_step, result_folder=result_folder, sample_idx=0,
+            verbose=False, save_images=False, noise_schedule=None)
+        self.driver = EditUncondDiffusion(args, unet=unet)
+        self.R = unet.arch["resolution"]
+
+    def _v0(self, k, gen):
+        d = 3 * self.R * self.R
+        # Algorithm-1 init (reference modules/edit.py:2435-2437): orthonormalised Gaussian block
+        g = torch.randn(d, k, device=self.device, dtype=torch.float32, generator=gen)
+        V, _ = ops.orthonormalise(g.T.contiguous())
+        return V
+
+    @torch.no_grad()
+    def edit_device(self, x0, mask, pc=0, gen=None, v0_mod=None, v0_null=None, noises=None):
+        """x0 [1,3,R,R] fp32 and mask bool [3,R,R], both already on the device."""
+        drv = self.driver
+        # inversion: reference run_DDIMinversion (:2117-2167) with the image injected
+        sched = drv.scheduler
+        sched.set_timesteps(drv.inv_steps, device=self.device, is_inversion=True)
+        xt = x0.contiguous()
+        n = len(sched._ts_host)
+        for i in range(n - 1):
+            t = sched._ts_host[i]
+            xt = sched.step(self.unet(xt, t), t, xt, eta=0, t_idx=i).prev_sample
+        xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
+        t_host = sched._ts_host[t_idx]
+        kw = dict(min_iter=10 ** 9, max_iter=self.n_iter, convergence_threshold=1e-4, verbose=False,
+                  align_sign=True)
+        _, s_mod, vT_mod = local_basis(self.unet, sched, xt, t_host, self.k, mask=mask,
+                                       v0=v0_mod if v0_mod is not None else self._v0(self.k, gen), **kw)
+        _, s_null, vT_null = local_basis(self.unet, sched, xt, t_host, self.k_null, mask=~mask,
+                                         v0=v0_null if v0_null is not None else self._v0(self.k_null, gen), **kw)
+        vT = ops.nullspace_project(vT_mod, vT_null, project=True)
+        batch = drv.build_edit_batch(xt, vT[pc], self.vis_num)
+        if noises is not None:
+            drv.noise_fn = lambda i, x: noises[i]
+        elif gen is not None:
+            drv.noise_fn = lambda i, x: torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=gen)
+        else:
+            drv.noise_fn = None
+        imgs = drv.DDIMforwardsteps(batch, t_start_idx=drv.edit_t_idx, t_end_idx=-1, save_image=False,
+                                    performance_boosting=True)
+        return dict(images=imgs, vT=vT, vT_modify=vT_mod, vT_null=vT_null, s_modify=s_mod, s_null=s_null,
+                    xt=xt)
+
+    @torch.no_grad()
+    def edit(self, x0_host, mask_host, pc=0, gen=None, **kw):
+        """Host tensors in (pinned for async copies), edited images [2*vis_num-1,3,R,R] back on the host."""
+        x0 = x0_host.to(self.device, non_blocking=True)
+        mask = mask_host.to(self.device, non_blocking=True)
+        out = self.edit_device(x0, mask, pc=pc, gen=gen, **kw)
+        imgs = out["images"].to("cpu", non_blocking=False)
+        return imgs
