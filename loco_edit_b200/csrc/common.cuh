@@ -74,6 +74,7 @@ struct ProfScope {   // records a start/stop event pair around a launch when pro
   int family; cudaStream_t stream; int slot;
 };
 void profile_enable(bool on);
+bool profile_is_on();
 // sums elapsed ms / work / launches per family since profile_enable(true); synchronises the device
 int profile_collect(double* ms, double* work, long long* launches, int nfam);
 

@@ -25,7 +25,8 @@ constexpr int kBBytes = kConvMaxBlockN * 128;    // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 256;                   // 2 accumulator stages x 128 fp32 columns
 constexpr int kThreads = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiBytes = 4 * 32 * 33 * 4;         // per-epilogue-warp transpose buffers
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row
 // groups 1024 bytes apart (cute::UMMA::SmemDescriptor layout; version = 1 for sm_100).
@@ -60,6 +61,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,11 +157,14 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
+    // TMEM gives each thread one pixel row; a padded shared-memory transpose turns that into
+    // "8 lanes x float4 = 128 contiguous bytes of one pixel" so every global load/store of the
+    // residual / accumulate / output streams is a fully used 128-byte segment.
     const int q = warp & 3;              // TMEM lane quarter owned by this warp
-    const int row = q * 32 + lane;       // row of the 128-pixel tile
-    const int rw = row % p.TW;
-    const int rh = (row / p.TW) % p.TH;
-    const int rn = row / (p.TW * p.TH);
+    float* tbuf = epi_smem + q * (32 * 33);
+    const int pr = lane >> 3;            // pixel sub-row handled by this lane (0..3)
+    const int cq = lane & 7;             // channel quad within the 32-column chunk
+    const int lTW = p.log_tw, lTH = p.log_th;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -168,16 +173,20 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int tx = tm % p.tiles_x;
       const int ty = (tm / p.tiles_x) % p.tiles_y;
       const int tn = tm / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.TW + rw, y = ty * p.TH + rh, n = tn * p.TN + rn;
       const int co0 = tco * p.block_n;
-      const bool valid = (n < p.N) && (y < p.Ho) && (x < p.Wo);
-      const bool use_bias = n < p.bias_rows;
-      float* optr = p.out + (long long)n * p.out_sN + (long long)y * p.out_sH +
-                    (long long)x * p.out_sW + co0;
-      const float* aptr = p.addend
-                              ? p.addend + (long long)n * p.add_sN + (long long)y * p.add_sH +
-                                    (long long)x * p.add_sW + co0
-                              : nullptr;
+      long long ooff[8], aoff[8];
+      uint32_t vmask = 0, bmask = 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int R = q * 32 + it * 4 + pr;
+        const int x = tx * p.TW + (R & (p.TW - 1));
+        const int y = ty * p.TH + ((R >> lTW) & (p.TH - 1));
+        const int n = tn * p.TN + (R >> (lTW + lTH));
+        if (n < p.N && y < p.Ho && x < p.Wo) vmask |= 1u << it;
+        if (n < p.bias_rows) bmask |= 1u << it;
+        ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
+        aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kConvMaxBlockN;
@@ -185,36 +194,51 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + ch, r);
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            if (use_bias) {
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + j));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              if (p.bias2) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + j));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-            }
-            if (aptr) {
-              const float4 a = *reinterpret_cast<const float4*>(aptr + ch + j);
-              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-            float4* o = reinterpret_cast<float4*>(optr + ch + j);
-            if (p.accumulate) {
-              const float4 a = *o;
-              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-            if (p.round_out) {
-              v.x = round_tf32(v.x); v.y = round_tf32(v.y);
-              v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-            }
-            *o = v;
+        for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+        __syncwarp();
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
+          v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+        }
+        __syncwarp();
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
+        if (p.bias2) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
+          bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+        if (p.addend) {
+          float4 a[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+        }
+        if (p.accumulate) {
+          float4 a[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (!((vmask >> it) & 1u)) continue;
+          float4 o = v[it];
+          if (p.round_out) {
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
           }
+          *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
         }
       }
       tc_fence_before();
@@ -306,6 +330,9 @@ int fill_common(ConvGemmParams& p, const ConvProblem& prob, int N, int Ho, int W
   p.c_chunks = prob.Kc / kConvBlockK;
   p.block_n = prob.Ngemm % 128 == 0 ? 128 : (prob.Ngemm % 64 == 0 ? 64 : 32);
   pick_box(Wo, Ho, &p.TW, &p.TH, &p.TN);
+  LOCO_REQUIRE((p.TW & (p.TW - 1)) == 0 && (p.TH & (p.TH - 1)) == 0, "conv: tile dims must be powers of two");
+  p.log_tw = 0; while ((1 << p.log_tw) < p.TW) ++p.log_tw;
+  p.log_th = 0; while ((1 << p.log_th) < p.TH) ++p.log_th;
   LOCO_REQUIRE(Wo % p.TW == 0 && Ho % p.TH == 0, "conv: %dx%d not tileable", Ho, Wo);
   p.tiles_x = Wo / p.TW; p.tiles_y = Ho / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
   p.tiles_co = prob.Ngemm / p.block_n;
@@ -420,13 +447,18 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
   return 0;
 }
 
-int conv_run(const ConvLaunch& L, cudaStream_t stream) {
+int conv_init() {
   static bool attr_set = false;
   if (!attr_set) {
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
+  return 0;
+}
+
+int conv_run(const ConvLaunch& L, cudaStream_t stream) {
+  LOCO_TRY(conv_init());
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {

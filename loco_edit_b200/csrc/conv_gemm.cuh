@@ -21,7 +21,8 @@ struct ConvGemmParams {
   int tap_dx[kConvMaxTaps];
   int tap_wk[kConvMaxTaps];   // column offset of the tap in the packed weight matrix
   int c_chunks;               // input channels / 32
-  int TW, TH, TN;             // pixel box (TW*TH*TN == 128)
+  int TW, TH, TN;             // pixel box (TW*TH*TN == 128), TW and TH powers of two
+  int log_tw, log_th;
   int tiles_x, tiles_y, tiles_n, tiles_co;
   int block_n;                // output channels per tile (multiple of 16, <= 128)
   int N, Ho, Wo, Cout;        // logical output grid
@@ -67,6 +68,7 @@ struct ConvLaunch {
   double flops = 0;
 };
 
+int conv_init();   // one-time kernel attribute setup (must not happen inside a stream capture)
 int conv_prepare(const ConvProblem& prob, ConvLaunch* out);
 int conv_run(const ConvLaunch& l, cudaStream_t stream);
 

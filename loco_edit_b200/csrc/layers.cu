@@ -147,27 +147,31 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
 // GroupNorm
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroups = 32;
-constexpr int kGnVecPerThread = 16;
 
 __host__ __device__ inline int gn_block_dim(int C) { return (256 % (C / 4) == 0) ? 256 : 192; }
 
 struct GnGeom {
   int block, ppb_step, ppb, nblk;
 };
-inline GnGeom gn_geom(int C, long long HW) {
+// Every thread owns one channel quad and `vec` pixels; all its loads are issued before the first
+// use (memory-level parallelism instead of a serial load->use chain).
+inline GnGeom gn_geom(int C, long long HW, int vec) {
   GnGeom g;
   g.block = gn_block_dim(C);
   g.ppb_step = g.block / (C / 4);
-  g.ppb = g.ppb_step * kGnVecPerThread;
+  g.ppb = g.ppb_step * vec;
   g.nblk = (int)((HW + g.ppb - 1) / g.ppb);
   return g;
 }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
 // mode 0: forward/JVP statistics; mode 1: VJP statistics.
-template <int MODE>
-__global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                float eps, int silu, double* __restrict__ stats, int ppb) {
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                double* __restrict__ stats) {
   __shared__ float part[2][256];
   const int C = x.C;
   const int cvn = C >> 2;
@@ -178,23 +182,29 @@ __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __r
   const int g = (cv * 4) / cg;
   const int n = blockIdx.y;
   const long long HW = (long long)x.H * x.W;
-  const long long p0 = (long long)blockIdx.x * ppb;
-  const long long p1 = min(HW, p0 + ppb);
+  const long long p0 = (long long)blockIdx.x * (pstep * VEC) + prow;
+  const bool primal = (MODE == 0) && (n < n_primal);
+  const View& src = (MODE == 0) ? x : gy;
+  float4 a[VEC], b[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const long long p = p0 + (long long)j * pstep;
+    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[j] = a[j];
+    if (p < HW) {
+      const int y = (int)(p / x.W), xx = (int)(p % x.W);
+      a[j] = ld4(src.ptr + n * src.sN + (long long)y * src.sH + (long long)xx * src.sW + cv * 4);
+      if (!primal) b[j] = ld4(x.ptr + (long long)y * x.sH + (long long)xx * x.sW + cv * 4);
+    }
+  }
   float s1 = 0.f, s2 = 0.f;
   if (MODE == 0) {
-    const bool primal = n < n_primal;
-    for (long long p = p0 + prow; p < p1; p += pstep) {
-      const int y = (int)(p / x.W), xx = (int)(p % x.W);
-      const long long off = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
-      const float4 v = *reinterpret_cast<const float4*>(x.ptr + n * x.sN + off);
-      if (primal) {
-        s1 += (v.x + v.y) + (v.z + v.w);
-        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      } else {
-        const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + off);
-        s1 += (v.x + v.y) + (v.z + v.w);
-        s2 += (v.x * x0.x + v.y * x0.y) + (v.z * x0.z + v.w * x0.w);
-      }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float4 v = a[j];
+      const float4 w = primal ? v : b[j];
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * w.x + v.y * w.y) + (v.z * w.z + v.w * w.w);
     }
   } else {
     const double cnt = (double)HW * cg;
@@ -202,25 +212,20 @@ __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __r
     const double var_d = pstats[g * 2 + 1] / cnt - mu_d * mu_d;
     const float mu = (float)mu_d;
     const float rstd = (float)(1.0 / sqrt((var_d > 0 ? var_d : 0) + (double)eps));
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
-    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
-    for (long long p = p0 + prow; p < p1; p += pstep) {
-      const int y = (int)(p / x.W), xx = (int)(p % x.W);
-      const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + (long long)y * x.sH +
-                                                         (long long)xx * x.sW + cv * 4);
-      const float4 d = *reinterpret_cast<const float4*>(gy.ptr + n * gy.sN + (long long)y * gy.sH +
-                                                        (long long)xx * gy.sW + cv * 4);
-      float a[4];
-      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
-      const float ds[4] = {d.x, d.y, d.z, d.w};
-      const float gs[4] = {ga.x, ga.y, ga.z, ga.w};
-      const float bs[4] = {be.x, be.y, be.z, be.w};
+    const float4 ga = ld4(gamma + cv * 4);
+    const float4 be = ld4(beta + cv * 4);
+    const float gs[4] = {ga.x, ga.y, ga.z, ga.w};
+    const float bs[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float xs[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
+      const float ds[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float u = gs[i] * ((xs[i] - mu) * rstd) + bs[i];
-        a[i] = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];
-        s1 += a[i];
-        s2 += a[i] * xs[i];
+        const float av = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];   // ds = 0 outside the image
+        s1 += av;
+        s2 += av * xs[i];
       }
     }
   }
@@ -239,12 +244,13 @@ __global__ void gn_stats_kernel(View x, int n_primal, View gy, const double* __r
 }
 
 // mode 0: forward/JVP apply; mode 1: VJP apply.
-template <int MODE>
-__global__ void gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu, int round_out,
-                                const float* __restrict__ addend, long long add_sN, long long add_sH,
-                                long long add_sW, int accumulate, View out, int ppb) {
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
+                const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int silu, int round_out,
+                const float* __restrict__ addend, long long add_sN, long long add_sH,
+                long long add_sW, int accumulate, View out) {
   const int C = x.C;
   const int cvn = C >> 2;
   const int cg = C / kGroups;
@@ -254,8 +260,7 @@ __global__ void gn_apply_kernel(View x, int n_primal, View gy, const double* __r
   const int g = (cv * 4) / cg;
   const int n = blockIdx.y;
   const long long HW = (long long)x.H * x.W;
-  const long long p0 = (long long)blockIdx.x * ppb;
-  const long long p1 = min(HW, p0 + ppb);
+  const long long p0 = (long long)blockIdx.x * (pstep * VEC) + prow;
   const double cnt = (double)HW * cg;
 
   const bool primal = (MODE == 0) && (n < n_primal);
@@ -272,64 +277,58 @@ __global__ void gn_apply_kernel(View x, int n_primal, View gy, const double* __r
     m1 = (float)(sa / cnt);
     m2 = (float)((sxa - mu_d * sa) * (double)rstd / cnt);
   }
-  const float4 ga4 = *reinterpret_cast<const float4*>(gamma + cv * 4);
-  const float4 be4 = *reinterpret_cast<const float4*>(beta + cv * 4);
+  const float4 ga4 = ld4(gamma + cv * 4);
+  const float4 be4 = ld4(beta + cv * 4);
   const float gs[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
   const float bs[4] = {be4.x, be4.y, be4.z, be4.w};
+  const View& src = (MODE == 0) ? x : gy;
 
-  for (long long p = p0 + prow; p < p1; p += pstep) {
-    const int y = (int)(p / x.W), xx = (int)(p % x.W);
-    const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
-    float r[4];
-    if (MODE == 0) {
-      const float4 v = *reinterpret_cast<const float4*>(x.ptr + n * x.sN + xoff);
-      const float vs[4] = {v.x, v.y, v.z, v.w};
-      if (primal) {
+  // ---- load phase ----
+  float4 a[VEC], b[VEC], e[VEC];
+  long long ooff[VEC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float u = gs[i] * ((vs[i] - mu) * rstd) + bs[i];
-          r[i] = silu ? silu_f(u) : u;
-        }
-      } else {
-        const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + xoff);
-        const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float xh = (xs[i] - mu) * rstd;
-          const float u = gs[i] * xh + bs[i];
-          const float dact = silu ? silu_grad(u) : 1.0f;
-          r[i] = dact * gs[i] * rstd * (vs[i] - m1 - xh * m2);
-        }
+  for (int j = 0; j < VEC; ++j) {
+    const long long p = p0 + (long long)j * pstep;
+    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[j] = a[j];
+    e[j] = a[j];
+    ooff[j] = -1;
+    if (p < HW) {
+      const int y = (int)(p / x.W), xx = (int)(p % x.W);
+      a[j] = ld4(src.ptr + n * src.sN + (long long)y * src.sH + (long long)xx * src.sW + cv * 4);
+      if (!primal) b[j] = ld4(x.ptr + (long long)y * x.sH + (long long)xx * x.sW + cv * 4);
+      ooff[j] = n * out.sN + (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
+      if (MODE == 1 && addend) e[j] = ld4(addend + n * add_sN + (long long)y * add_sH + (long long)xx * add_sW + cv * 4);
+      if (MODE == 1 && accumulate) {
+        const float4 c = ld4(out.ptr + ooff[j]);
+        e[j].x += c.x; e[j].y += c.y; e[j].z += c.z; e[j].w += c.w;
       }
-    } else {
-      const float4 x0 = *reinterpret_cast<const float4*>(x.ptr + xoff);
-      const float4 d = *reinterpret_cast<const float4*>(gy.ptr + n * gy.sN + (long long)y * gy.sH +
-                                                        (long long)xx * gy.sW + cv * 4);
-      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
-      const float ds[4] = {d.x, d.y, d.z, d.w};
+    }
+  }
+  // ---- compute + store phase ----
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+  for (int j = 0; j < VEC; ++j) {
+    if (ooff[j] < 0) continue;
+    const float vs[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+    const float xs[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
+    const float es[4] = {e[j].x, e[j].y, e[j].z, e[j].w};
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (MODE == 0 && primal) {
+        const float u = gs[i] * ((vs[i] - mu) * rstd) + bs[i];
+        r[i] = silu ? silu_f(u) : u;
+      } else {
         const float xh = (xs[i] - mu) * rstd;
         const float u = gs[i] * xh + bs[i];
-        const float a = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];
-        r[i] = rstd * (a - m1 - xh * m2);
+        const float dact = silu ? silu_grad(u) : 1.0f;
+        if (MODE == 0) r[i] = dact * gs[i] * rstd * (vs[i] - m1 - xh * m2);
+        else r[i] = rstd * (gs[i] * dact * vs[i] - m1 - xh * m2);
       }
+      if (MODE == 1) r[i] += es[i];
+      if (round_out) r[i] = round_tf32(r[i]);
     }
-    float* optr = out.ptr + n * out.sN + (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
-    if (addend) {
-      const float4 a = *reinterpret_cast<const float4*>(addend + n * add_sN + (long long)y * add_sH +
-                                                        (long long)xx * add_sW + cv * 4);
-      r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
-    }
-    if (accumulate) {
-      const float4 a = *reinterpret_cast<const float4*>(optr);
-      r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
-    }
-    if (round_out) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = round_tf32(r[i]);
-    }
-    *reinterpret_cast<float4*>(optr) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(out.ptr + ooff[j]) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -400,12 +399,14 @@ __global__ void add_views_kernel(View in, View out, int accumulate) {
 // Timestep embedding
 // ------------------------------------------------------------------------------------------------
 // One block. scratch: [0,4ch) = silu(dense0(emb)), [4ch,8ch) = silu(dense1(.)) = temb_act.
-__global__ void temb_kernel(float t, int ch, const float* __restrict__ w0,
+__global__ void set_scalar_kernel(float* dst, float v) { *dst = v; }
+__global__ void temb_kernel(const float* __restrict__ t_dev, int ch, const float* __restrict__ w0,
                             const float* __restrict__ b0, const float* __restrict__ w1,
                             const float* __restrict__ b1, float* __restrict__ scratch) {
   extern __shared__ float sm[];   // emb[ch] + h[4ch]
   float* emb = sm;
   float* h = sm + ch;
+  const float t = *t_dev;
   const int half = ch / 2;
   const int tch = 4 * ch;
   const float coef = -(float)(log(10000.0) / (double)(half - 1));
@@ -515,11 +516,11 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
 
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, 8);
   dim3 grid(g.nblk, x.N);
   ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 2 : 1), s);
-  gn_stats_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
-                                              stats, g.ppb);
+  gn_stats_kernel<0, 8><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
+                                                 stats);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -527,11 +528,11 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
                  float eps, int silu, int round_out, View y, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_apply_fwd"));
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, 8);
   dim3 grid(g.nblk, x.N);
   ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 3 : 2), s);
-  gn_apply_kernel<0><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps, silu,
-                                              round_out, nullptr, 0, 0, 0, 0, y, g.ppb);
+  gn_apply_kernel<0, 8><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                                 silu, round_out, nullptr, 0, 0, 0, 0, y);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -539,11 +540,10 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
                  float eps, int silu, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, 8);
   dim3 grid(g.nblk, gy.N);
   ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * 2, s);
-  gn_stats_kernel<1><<<grid, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats,
-                                              g.ppb);
+  gn_stats_kernel<1, 8><<<grid, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -554,13 +554,12 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   LOCO_TRY(check_gn_view(gy, "gn_apply_vjp(gy)"));
   LOCO_TRY(check_gn_view(gx, "gn_apply_vjp(gx)"));
   if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, 4);
   dim3 grid(g.nblk, gy.N);
   ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * (addend ? 4 : 3), s);
-  gn_apply_kernel<1><<<grid, g.block, 0, s>>>(
+  gn_apply_kernel<1, 4><<<grid, g.block, 0, s>>>(
       xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx,
-      g.ppb);
+      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -590,10 +589,15 @@ int add_views(View in, View out, int accumulate, cudaStream_t s) {
   return 0;
 }
 
-int temb_forward(float t, int ch, const float* w0, const float* b0, const float* w1, const float* b1,
-                 float* scratch, cudaStream_t s) {
+int set_scalar(float* dst, float v, cudaStream_t s) {
+  set_scalar_kernel<<<1, 1, 0, s>>>(dst, v);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int temb_forward(const float* t_dev, int ch, const float* w0, const float* b0, const float* w1,
+                 const float* b1, float* scratch, cudaStream_t s) {
   const size_t smem = (size_t)(ch + 4 * ch) * sizeof(float);
-  temb_kernel<<<1, 512, smem, s>>>(t, ch, w0, b0, w1, b1, scratch);
+  temb_kernel<<<1, 512, smem, s>>>(t_dev, ch, w0, b0, w1, b1, scratch);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -52,8 +52,10 @@ int add_views(View in, View out, int accumulate, cudaStream_t s);
 // ---- timestep embedding (reference: get_timestep_embedding + temb.dense, ddpm/diffusion.py:
 // 154-157, 783-804): temb_act = silu(dense1(silu(dense0([sin(t w), cos(t w)])))), then every
 // ResnetBlock's temb_proj Linear(temb_ch -> Cout) evaluated into one packed vector.
-int temb_forward(float t, int ch, const float* w0, const float* b0, const float* w1,
+// t is read from device memory so a captured CUDA graph can be replayed for any timestep.
+int temb_forward(const float* t_dev, int ch, const float* w0, const float* b0, const float* w1,
                  const float* b1, float* scratch /*2*4ch*/, cudaStream_t s);
+int set_scalar(float* dst, float v, cudaStream_t s);
 int temb_project(const float* temb_act, int temb_ch, const float* w, const float* b, int cout,
                  float* out, cudaStream_t s);
 

@@ -36,6 +36,7 @@ struct ProfRec { cudaEvent_t a, b; int family; double work; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }  // namespace
+bool profile_is_on() { return g_prof_on; }
 void profile_enable(bool on) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
@@ -295,12 +296,20 @@ struct TH {                 // a forward tensor and the cotangent buffer that mi
 };
 
 struct Plan::Impl {
-  // call-time arguments read by the closures
+  // call-time arguments read by the closures (plan-owned staging buffers, so that the launch
+  // programs can be captured once into CUDA graphs and replayed for any caller pointers / t)
   const float* cur_x = nullptr;
-  float cur_t = 0.f;
+  float* t_dev = nullptr;
   float* cur_eps = nullptr;
   const float* cur_geps = nullptr;
   float* cur_gx = nullptr;
+  float *in_buf = nullptr, *out_buf = nullptr, *gin_buf = nullptr, *gout_buf = nullptr;
+  cudaGraphExec_t fwd_graph = nullptr, bwd_graph = nullptr;
+  long long fwd_graph_launches = 0, bwd_graph_launches = 0;
+  ~Impl() {
+    if (fwd_graph) cudaGraphExecDestroy(fwd_graph);
+    if (bwd_graph) cudaGraphExecDestroy(bwd_graph);
+  }
 
   std::vector<Fn> fwd;
   std::vector<std::vector<Fn>> bwd_groups;
@@ -332,6 +341,7 @@ int Plan::build(float* workspace) {
   const int L = A.n_levels;
   LOCO_REQUIRE(A.ch % 128 == 0, "plan: base channel count %d must be a multiple of 128", A.ch);
   if (!dry) LOCO_REQUIRE(M.arena != nullptr, "plan: model weights not bound");
+  if (!dry) LOCO_TRY(conv_init());
 
   I.fwd.clear(); I.bwd_groups.clear(); I.bwd.clear(); I.launches.clear(); I.writers.clear();
   I.n_ids = 0;
@@ -444,6 +454,17 @@ int Plan::build(float* workspace) {
     });
   };
 
+  // ---- staging buffers (NCHW images at the ABI) ----
+  {
+    const size_t img = (size_t)3 * A.resolution * A.resolution;
+    I.in_buf = alloc_act((size_t)NB * img);
+    I.out_buf = alloc_act((size_t)NB * img);
+    I.gin_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
+    I.gout_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
+    I.t_dev = alloc_act(64);
+    if (I.fwd_graph) { cudaGraphExecDestroy(I.fwd_graph); I.fwd_graph = nullptr; }
+    if (I.bwd_graph) { cudaGraphExecDestroy(I.bwd_graph); I.bwd_graph = nullptr; }
+  }
   // ---- timestep embedding ----
   const int temb_ch = 4 * A.ch;
   float* temb_scratch = alloc_act(2 * temb_ch);
@@ -452,7 +473,7 @@ int Plan::build(float* workspace) {
     const Model* Mp = model;
     Impl* Ip = impl.get();
     I.fwd.push_back([=](cudaStream_t s) {
-      LOCO_TRY(temb_forward(Ip->cur_t, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
+      LOCO_TRY(temb_forward(Ip->t_dev, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
                             Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, s));
       return temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
                           Mp->tproj_rows, tproj, s);
@@ -713,12 +734,53 @@ int Plan::build(float* workspace) {
   return 0;
 }
 
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOCO_NO_GRAPH");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1 && !profile_is_on();
+}
+
+// Run `ops` on `s`, through a CUDA graph captured on first use (the program is static: same
+// kernels, same buffers every call; only the staging buffers' contents and *t_dev change).
+static int run_program(std::vector<Fn>& ops, double* stats, size_t stat_bytes, cudaGraphExec_t* exec,
+                       long long* graph_launches, cudaStream_t s) {
+  auto direct = [&]() -> int {
+    if (stat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, stat_bytes, s));
+    for (auto& f : ops) LOCO_TRY(f(s));
+    return 0;
+  };
+  if (!graphs_enabled()) return direct();
+  if (*exec == nullptr) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = launch_count();
+    LOCO_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int r = direct();
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    LOCO_CHECK_CUDA(e);
+    *graph_launches = launch_count() - l0;
+    count_launch((int)-(*graph_launches));   // capture enqueued nothing
+    const cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LOCO_CHECK_CUDA(ie);
+  }
+  LOCO_CHECK_CUDA(cudaGraphLaunch(*exec, s));
+  count_launch((int)*graph_launches);
+  return 0;
+}
+
 int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
   Impl& I = *impl;
-  I.cur_x = x; I.cur_t = t; I.cur_eps = eps_out;
-  if (I.fstat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(I.fstats, 0, I.fstat_bytes, s));
-  for (auto& f : I.fwd) LOCO_TRY(f(s));
+  const size_t bytes = sizeof(float) * (size_t)(NP + NT) * 3 * model->arch.resolution * model->arch.resolution;
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(I.in_buf, x, bytes, cudaMemcpyDeviceToDevice, s));
+  LOCO_TRY(set_scalar(I.t_dev, t, s));
+  I.cur_x = I.in_buf; I.cur_eps = I.out_buf;
+  LOCO_TRY(run_program(I.fwd, I.fstats, I.fstat_bytes, &I.fwd_graph, &I.fwd_graph_launches, s));
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, bytes, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
@@ -726,9 +788,11 @@ int Plan::vjp(const float* g_eps, float* gx, cudaStream_t s) {
   LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
   LOCO_REQUIRE(NC > 0, "plan: built without cotangent rows");
   Impl& I = *impl;
-  I.cur_geps = g_eps; I.cur_gx = gx;
-  if (I.bstat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(I.bstats, 0, I.bstat_bytes, s));
-  for (auto& f : I.bwd) LOCO_TRY(f(s));
+  const size_t bytes = sizeof(float) * (size_t)NC * 3 * model->arch.resolution * model->arch.resolution;
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(I.gin_buf, g_eps, bytes, cudaMemcpyDeviceToDevice, s));
+  I.cur_geps = I.gin_buf; I.cur_gx = I.gout_buf;
+  LOCO_TRY(run_program(I.bwd, I.bstats, I.bstat_bytes, &I.bwd_graph, &I.bwd_graph_launches, s));
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(gx, I.gout_buf, bytes, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
