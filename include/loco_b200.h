@@ -93,6 +93,13 @@ int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
                             int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
                             void* scratch, void* stream);
 
+/* The two Jacobian products of one iteration without the orthonormalisation: rows of
+ * U = mask o J V^T and W = J^T U for the k given rows of V.  This is the unit a rank runs on its
+ * shard of the probe tangents before the all-gather of W (multi-GPU power method). */
+int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, const unsigned char* mask,
+                        int noise, const float* V, int k, long long d, float* u_full, float* w_out,
+                        void* scratch, void* stream);
+
 /* ---------------- bandwidth-bound pieces ---------------- */
 /* P = (x - eps*sqrt(1-at))/sqrt(at): get_x0 without the mask (src/modules/edit.py:2386) */
 int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream);

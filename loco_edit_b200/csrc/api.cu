@@ -159,17 +159,16 @@ long long loco_pullback_scratch_bytes(int k, long long d) {
   return (long long)(2 * k1d + 4 * kd + align_up((size_t)loco_orthonormalise_scratch_bytes(k), 256));
 }
 
-int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
-                            const unsigned char* mask, int noise, const float* V, int k, long long d,
-                            int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
-                            void* scratch, void* stream) {
+int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, const unsigned char* mask,
+                        int noise, const float* V, int k, long long d, float* u_full, float* w_out,
+                        void* scratch, void* stream) {
   GUARD_BEGIN
-  LOCO_REQUIRE(p && xt && V && u_full && V_out && s_out && scratch, "loco_pullback_iteration: null argument");
+  LOCO_REQUIRE(p && xt && V && u_full && w_out && scratch, "loco_pullback_probe: null argument");
   Plan& P = *p->p;
-  LOCO_REQUIRE(P.NP == 1 && P.NT == k && P.NC == k, "loco_pullback_iteration: plan is (%d,%d,%d), need (1,%d,%d)",
+  LOCO_REQUIRE(P.NP == 1 && P.NT == k && P.NC == k, "loco_pullback_probe: plan is (%d,%d,%d), need (1,%d,%d)",
                P.NP, P.NT, P.NC, k, k);
   const int R = P.model->arch.resolution;
-  LOCO_REQUIRE(d == 3LL * R * R, "loco_pullback_iteration: d=%lld does not match the model", d);
+  LOCO_REQUIRE(d == 3LL * R * R, "loco_pullback_probe: d=%lld does not match the model", d);
   cudaStream_t s = ST(stream);
   const size_t kd = align_up((size_t)k * d * 4, 256);
   const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);
@@ -179,17 +178,31 @@ int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
   float* g_eps = reinterpret_cast<float*>(sp); sp += kd;
   float* gx_direct = reinterpret_cast<float*>(sp); sp += kd;
   float* gx_unet = reinterpret_cast<float*>(sp); sp += kd;
-  float* w_tmp = reinterpret_cast<float*>(sp); sp += kd;
-  double* oscr = reinterpret_cast<double*>(sp);
-  float* w = w_out ? w_out : w_tmp;
   // batch = [x_t ; v_1 .. v_k]: one fused primal + k-tangent pass
   LOCO_CHECK_CUDA(cudaMemcpyAsync(xin, xt, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(xin + d, V, sizeof(float) * k * d, cudaMemcpyDeviceToDevice, s));
   LOCO_TRY(P.forward(xin, t, eps, s));
   LOCO_TRY(pmp_jvp_epilogue(V, eps + d, mask, at, noise, k, d, u_full, g_eps, gx_direct, s));
   LOCO_TRY(P.vjp(g_eps, gx_unet, s));
-  LOCO_TRY(axpy(gx_direct, gx_unet, 1.0f, (long long)k * d, w, s));
-  LOCO_TRY(orthonormalise(w, k, d, align_sign ? V : nullptr, V_out, s_out, oscr, s));
+  LOCO_TRY(axpy(gx_direct, gx_unet, 1.0f, (long long)k * d, w_out, s));
+  return 0;
+  GUARD_END
+}
+
+int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
+                            const unsigned char* mask, int noise, const float* V, int k, long long d,
+                            int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
+                            void* scratch, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(V_out && s_out && scratch, "loco_pullback_iteration: null argument");
+  const size_t kd = align_up((size_t)k * d * 4, 256);
+  const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);
+  char* sp = reinterpret_cast<char*>(scratch) + 2 * k1d + 3 * kd;
+  float* w_tmp = reinterpret_cast<float*>(sp); sp += kd;
+  double* oscr = reinterpret_cast<double*>(sp);
+  float* w = w_out ? w_out : w_tmp;
+  LOCO_TRY(loco_pullback_probe(p, xt, t, at, mask, noise, V, k, d, u_full, w, scratch, stream));
+  LOCO_TRY(orthonormalise(w, k, d, align_sign ? V : nullptr, V_out, s_out, oscr, ST(stream)));
   return 0;
   GUARD_END
 }

@@ -747,18 +747,22 @@ static bool graphs_enabled() {
 // kernels, same buffers every call; only the staging buffers' contents and *t_dev change).
 static int run_program(std::vector<Fn>& ops, double* stats, size_t stat_bytes, cudaGraphExec_t* exec,
                        long long* graph_launches, cudaStream_t s) {
-  auto direct = [&]() -> int {
-    if (stat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, stat_bytes, s));
-    for (auto& f : ops) LOCO_TRY(f(s));
+  auto direct = [&](cudaStream_t st) -> int {
+    if (stat_bytes) LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, stat_bytes, st));
+    for (auto& f : ops) LOCO_TRY(f(st));
     return 0;
   };
-  if (!graphs_enabled()) return direct();
+  if (!graphs_enabled()) return direct(s);
   if (*exec == nullptr) {
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot
+    // be captured); nothing executes during capture, the graph is then launched on `s`
+    static cudaStream_t cap = nullptr;
+    if (!cap) LOCO_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     const long long l0 = launch_count();
-    LOCO_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int r = direct();
-    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    LOCO_CHECK_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    const int r = direct(cap);
+    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
     LOCO_CHECK_CUDA(e);
     *graph_launches = launch_count() - l0;

@@ -140,6 +140,15 @@ class PullbackWorkspace:
             "loco_pullback_iteration")
 
 
+    def probe(self, xt, t, at, mask_u8, noise, V_in):
+        """Rows of U (masked J V^T) and W (J^T U) for the k rows of V_in, no orthonormalisation."""
+        check(self.lib.loco_pullback_probe(
+            self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8) if mask_u8 is not None else None,
+            1 if noise else 0, ptr(V_in), self.k, self.d, ptr(self.u_full), ptr(self.w),
+            _aligned(self.scratch), stream_ptr()), "loco_pullback_probe")
+        return self.u_full, self.w
+
+
 # ---------------------------------------------------------------------------------------------
 # single layers (parity tests)
 # ---------------------------------------------------------------------------------------------

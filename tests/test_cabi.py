@@ -1,0 +1,89 @@
+"""CPU: the C-ABI library loads, exports every symbol include/loco_b200.h declares, builds the model
+registry without a GPU, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from loco_edit_b200 import _lib
+from loco_edit_b200.weights import DDPM256, ddpm_param_shapes
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "loco_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(loco_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libloco_b200.so does not export %s" % n
+        assert n in _lib.PROTOTYPES, "python binding lacks a prototype for %s" % n
+    assert lib.loco_abi_version() == 1
+
+
+def test_model_registry_matches_reference_state_dict(golden_dir):
+    """Parameter names/shapes the C library expects == DDPM.state_dict() of the reference."""
+    from loco_edit_b200.unet import _make_arch
+    lib = _lib.load()
+    h = C.c_void_p()
+    arch = _make_arch(DDPM256)
+    _lib.check(lib.loco_unet_create(C.byref(arch), C.byref(h)))
+    try:
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        nd = C.c_int()
+        got = {}
+        for i in range(lib.loco_unet_num_params(h)):
+            _lib.check(lib.loco_unet_param_info(h, i, buf, 256, shape, C.byref(nd)))
+            got[buf.value.decode()] = [shape[j] for j in range(nd.value)]
+        ref = json.load(open(os.path.join(golden_dir, "ddpm_param_shapes.json")))
+        assert got == ref
+        assert got == {k: list(v) for k, v in ddpm_param_shapes(DDPM256).items()}
+        # packed arena: fprop + dgrad packs of every GEMM conv + raw vectors
+        assert lib.loco_unet_weight_floats(h) > 200_000_000
+        # plan sizing is pure host logic
+        p = C.c_void_p()
+        _lib.check(lib.loco_plan_create(h, 1, 5, 5, C.byref(p)))
+        nbytes = lib.loco_plan_workspace_bytes(p)
+        assert 8e9 < nbytes < 40e9
+        ff, vf = C.c_double(), C.c_double()
+        fo, vo = C.c_int(), C.c_int()
+        _lib.check(lib.loco_plan_info(p, C.byref(ff), C.byref(vf), C.byref(fo), C.byref(vo)))
+        # conv FLOPs of the tensor-core layers: 6 rows x (F - edge convs - attention)
+        assert abs(ff.value / 6 - 0.4953e12) / 0.4953e12 < 0.01
+        assert abs(vf.value / 5 - 0.4953e12) / 0.4953e12 < 0.01
+        lib.loco_plan_destroy(p)
+    finally:
+        lib.loco_unet_destroy(h)
+
+
+def test_bad_arguments_are_reported_not_thrown():
+    lib = _lib.load()
+    from loco_edit_b200.unet import _make_arch
+    h = C.c_void_p()
+    bad = _make_arch(dict(DDPM256, ch=96))
+    assert lib.loco_unet_create(C.byref(bad), C.byref(h)) != 0
+    assert b"multiple of 128" in lib.loco_last_error()
+    with pytest.raises(_lib.LocoError):
+        _lib.check(lib.loco_unet_create(C.byref(bad), C.byref(h)), "create")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    lib = _lib.load()
+    x = torch.zeros(16)
+    rc = lib.loco_axpy(C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), 1.0, 16,
+                       C.c_void_p(x.data_ptr()), None)
+    assert rc != 0 and b"no CUDA device" in lib.loco_last_error()
+    from loco_edit_b200.unet import B200UNet
+    with pytest.raises(_lib.LocoError):
+        B200UNet(DDPM256, {}, device="cpu")
