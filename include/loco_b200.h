@@ -129,10 +129,17 @@ int loco_gram(const float* A, int ka, const float* B, int kb, long long d, doubl
 /* Channels-last convolution on the tcgen05 path.  kind: 0 = 3x3 s1 p1, 1 = 1x1, 2 = 3x3 s2 pad
  * (0,1,0,1), 3 = data gradient of kind 0, 4 = data gradient of kind 2.  w is the torch-layout
  * weight [Cout,Cin,k,k] of the FORWARD conv; wpack is scratch of the same size.  x: [N,H,W,Cx],
- * y: [N,Ho,Wo,Cy] contiguous.  bias/addend may be NULL. */
+ * y: [N,Ho,Wo,Cy] contiguous.  bias/addend may be NULL.  splitk_scratch (optional, >= 1 MiB, first
+ * 16 KiB zeroed) enables the split-K path for layers with fewer tiles than SMs. */
 int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, const float* w, int Cout,
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
-                     int accumulate, float* y, void* stream);
+                     int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
+                     void* stream);
+/* micro-benchmark of one prepared conv launch (wpack must already hold packed weights):
+ * average device ms over `reps` back-to-back launches; reports the split-K factor / grid used. */
+int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
+                    float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
+                    float* ms_out, int* ksplit_out, int* grid_out, void* stream);
 /* GroupNorm(32)+optional SiLU on [N,H,W,C]; rows >= n_primal are tangents of row 0.
  * stats: 8*N*64 bytes scratch. */
 int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_primal,

@@ -62,7 +62,9 @@ PROTOTYPES = {
     "loco_gather_rows": (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     "loco_scatter_rows": (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     "loco_gram": (_I, [_P, _I, _P, _I, _LL, _P, _P]),
-    "loco_conv2d_nhwc": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P]),
+    "loco_conv2d_nhwc": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _LL, _P]),
+    "loco_conv_bench": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, C.POINTER(_F),
+                             C.POINTER(_I), C.POINTER(_I), _P]),
     "loco_groupnorm_silu_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_groupnorm_silu_vjp": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),

@@ -254,7 +254,8 @@ int loco_gram(const float* A, int ka, const float* B, int kb, long long d, doubl
 // ------------------------------------------------------------------------------------------------
 int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, const float* w, int Cout,
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
-                     int accumulate, float* y, void* stream) {
+                     int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
+                     void* stream) {
   GUARD_BEGIN
   LOCO_TRY(require_device());
   cudaStream_t s = ST(stream);
@@ -280,9 +281,69 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
   View add;
   if (addend) { add = make_view(const_cast<float*>(addend), N, Ho, Wo, Cy); p.addend = &add; }
   p.accumulate = accumulate; p.round_out = 0;
+  if (splitk_scratch && splitk_bytes >= (1 << 20)) {
+    // layout: [4096 int counters (zeroed by the caller)] [partial tiles]
+    p.splitk_counters = reinterpret_cast<int*>(splitk_scratch);
+    p.splitk_max_tiles = 2048;   // arrive [0,2048) + done [2048,4096)
+    p.splitk_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(splitk_scratch) + 4096 * 4);
+    p.splitk_partial_floats = (splitk_bytes - 4096 * 4) / 4;
+  }
   ConvLaunch L;
   LOCO_TRY(conv_prepare(p, &L));
   return conv_run(L, s);
+  GUARD_END
+}
+
+// Micro-benchmark of one prepared conv launch: `reps` back-to-back launches between two events.
+int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
+                    float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
+                    float* ms_out, int* ksplit_out, int* grid_out, void* stream) {
+  GUARD_BEGIN
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  ConvProblem p;
+  int Ho = H, Wo = W, Cy = Cout;
+  if (kind == CONV_3x3 || kind == CONV_1x1 || kind == CONV_3x3_S2) {
+    if (kind == CONV_3x3_S2) { Ho = H / 2; Wo = W / 2; }
+    p.Kc = Cin; p.Ngemm = Cout;
+  } else {
+    if (kind == CONV_3x3_S2_DGRAD) { Ho = 2 * H; Wo = 2 * W; }
+    p.Kc = Cout; p.Ngemm = Cin; Cy = Cin;
+  }
+  p.kind = kind;
+  p.in = make_view(x, N, H, W, Cx);
+  p.out = make_view(y, N, Ho, Wo, Cy);
+  p.wpack = wpack;
+  p.round_out = 1;
+  if (splitk_scratch && max_ksplit > 1) {
+    p.splitk_counters = reinterpret_cast<int*>(splitk_scratch);
+    p.splitk_max_tiles = 2048;   // arrive [0,2048) + done [2048,4096)
+    p.splitk_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(splitk_scratch) + 4096 * 4);
+    p.splitk_partial_floats = (splitk_bytes - 4096 * 4) / 4;
+  }
+  ConvLaunch L;
+  LOCO_TRY(conv_prepare(p, &L));
+  for (int i = 0; i < L.nlaunch; ++i)
+    if (L.p[i].ksplit > max_ksplit) {
+      L.p[i].ksplit = max_ksplit;
+      const int items = L.p[i].tiles_x * L.p[i].tiles_y * L.p[i].tiles_n * L.p[i].tiles_co * max_ksplit;
+      L.grid[i] = items < num_sms() ? items : num_sms();
+    }
+  if (ksplit_out) *ksplit_out = L.p[0].ksplit;
+  if (grid_out) *grid_out = L.grid[0];
+  cudaEvent_t a, b;
+  LOCO_CHECK_CUDA(cudaEventCreate(&a));
+  LOCO_CHECK_CUDA(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) LOCO_TRY(conv_run(L, s));
+  LOCO_CHECK_CUDA(cudaEventRecord(a, s));
+  for (int i = 0; i < reps; ++i) LOCO_TRY(conv_run(L, s));
+  LOCO_CHECK_CUDA(cudaEventRecord(b, s));
+  LOCO_CHECK_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  LOCO_CHECK_CUDA(cudaEventElapsedTime(&ms, a, b));
+  *ms_out = ms / reps;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
   GUARD_END
 }
 

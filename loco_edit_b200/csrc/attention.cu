@@ -6,9 +6,14 @@ namespace loco {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 32, BN = 64, BK = 16;
+constexpr int kGemmThreads = 128;
 
-__global__ void __launch_bounds__(256)
+// 32x64 output tile per 128-thread block (8x16 threads, 4x4 outputs each); the next K slab is
+// prefetched into registers while the current one is multiplied out of shared memory, so the
+// global/L2 latency of the tiny attention operands overlaps the FMAs, and the small tile keeps
+// >= 160 blocks in flight for a 256x256 product.
+__global__ void __launch_bounds__(kGemmThreads)
 batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long long sCm,
                     long long sCn, long long sCb, int M, int N, int K, float alpha, float beta,
                     int round_out, int a_kcontig, int b_ncontig) {
@@ -19,33 +24,51 @@ batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long lo
   const float* Ab = A.ptr + b * A.sb;
   const float* Bb = B.ptr + b * B.sb;
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;   // 16x16 threads, 4x4 outputs each
+  const int tx = tid % 16, ty = tid / 16;   // 8x16 threads, 4x4 outputs each
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  float ra[4], rb[8];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int e = tid + 256 * r;
+      const int e = tid + kGemmThreads * r;
       int m, k;
       if (a_kcontig) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
-      float v = 0.f;
-      if (m0 + m < M && k0 + k < K) v = Ab[(long long)(m0 + m) * A.s0 + (long long)(k0 + k) * A.s1];
-      As[k][m] = v;
+      ra[r] = (m0 + m < M && k0 + k < K) ? Ab[(long long)(m0 + m) * A.s0 + (long long)(k0 + k) * A.s1] : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int e = tid + 256 * r;
+    for (int r = 0; r < 8; ++r) {
+      const int e = tid + kGemmThreads * r;
       int n, k;
       if (b_ncontig) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
-      float v = 0.f;
-      if (n0 + n < N && k0 + k < K) v = Bb[(long long)(k0 + k) * B.s0 + (long long)(n0 + n) * B.s1];
-      Bs[k][n] = v;
+      rb[r] = (n0 + n < N && k0 + k < K) ? Bb[(long long)(k0 + k) * B.s0 + (long long)(n0 + n) * B.s1] : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + kGemmThreads * r;
+      int m, k;
+      if (a_kcontig) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      As[k][m] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = tid + kGemmThreads * r;
+      int n, k;
+      if (b_ncontig) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+      Bs[k][n] = rb[r];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    stash();
     __syncthreads();
+    if (k0 + BK < K) fetch(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[4], bb[4];
@@ -119,12 +142,23 @@ int check_tokens(const View& v, const char* what) {
 
 }  // namespace
 
+int attention_init() {
+  static bool done = false;
+  if (done) return 0;
+  const int co = cudaSharedmemCarveoutMaxShared;
+  LOCO_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+  LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+  LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_lin_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+  done = true;
+  return 0;
+}
+
 int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
                  int M, int N, int K, int batch, float alpha, float beta, int round_out,
                  cudaStream_t s) {
   if (batch <= 0) return 0;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
-  batched_gemm_kernel<<<grid, 256, 0, s>>>(A, B, C, sCm, sCn, sCb, M, N, K, alpha, beta, round_out,
+  batched_gemm_kernel<<<grid, kGemmThreads, 0, s>>>(A, B, C, sCm, sCn, sCb, M, N, K, alpha, beta, round_out,
                                            A.s1 == 1 ? 1 : 0, B.s1 == 1 ? 1 : 0);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;

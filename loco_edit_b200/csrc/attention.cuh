@@ -6,6 +6,8 @@
 
 namespace loco {
 
+int attention_init();   // one-time kernel attribute setup
+
 // C[b](m,n) = alpha * sum_k A[b](m,k) * B[b](k,n) + beta * C[b](m,n), arbitrary element strides.
 struct GemmOperand {
   const float* ptr;

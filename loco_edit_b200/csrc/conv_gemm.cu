@@ -53,6 +53,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
+  if (p.debug == 1) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -61,6 +62,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
   float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -93,6 +95,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = tiles_m * p.tiles_co;
   const int kiters = p.ntaps * p.c_chunks;
+  // Work item = (tile, K split).  Layers with fewer tiles than SMs split their K loop over several
+  // CTAs; the last CTA to finish a tile sums the partial tiles in fixed order and runs the epilogue.
+  const int ksplit = p.ksplit;
+  const int total_items = p.debug == 2 ? 0 : total_tiles * ksplit;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -100,24 +106,27 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * 128u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int tile = w % total_tiles;
+        const int split = w / total_tiles;
+        const int k0 = (int)((long long)kiters * split / ksplit);
+        const int k1 = (int)((long long)kiters * (split + 1) / ksplit);
         const int tm = tile % tiles_m;
         const int tco = tile / tiles_m;
         const int tx = tm % p.tiles_x;
         const int ty = (tm / p.tiles_x) % p.tiles_y;
         const int tn = tm / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, co0 = tco * p.block_n;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const CUtensorMap* am = &p.amap[p.tap_map[tap]];
-          const int xx = x0 + p.tap_dx[tap], yy = y0 + p.tap_dy[tap], wk = p.tap_wk[tap];
-          for (int cc = 0; cc < p.c_chunks; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(sa, am, &full_bar[stage], cc * kConvBlockK, xx, yy, n0);
-            tma_load_2d(sa + kABytes, &p.bmap, &full_bar[stage], wk + cc * kConvBlockK, co0);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
+        int tap = k0 / p.c_chunks, cc = k0 % p.c_chunks;
+        for (int it = k0; it < k1; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(sa, &p.amap[p.tap_map[tap]], &full_bar[stage], cc * kConvBlockK,
+                      x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n0);
+          tma_load_2d(sa + kABytes, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++cc == p.c_chunks) { cc = 0; ++tap; }
         }
       }
     }
@@ -130,11 +139,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc_tf32(p.block_n);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int split = w / total_tiles;
+        const int nk = (int)((long long)kiters * (split + 1) / ksplit) - (int)((long long)kiters * split / ksplit);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kConvMaxBlockN;
-        for (int it = 0; it < kiters; ++it) {
+        for (int it = 0; it < nk; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -159,7 +170,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------ epilogue ------------------------------
     // TMEM gives each thread one pixel row; a padded shared-memory transpose turns that into
     // "8 lanes x float4 = 128 contiguous bytes of one pixel" so every global load/store of the
-    // residual / accumulate / output streams is a fully used 128-byte segment.
+    // residual / accumulate / output / split-K partial streams is a fully used 128-byte segment.
     const int q = warp & 3;              // TMEM lane quarter owned by this warp
     float* tbuf = epi_smem + q * (32 * 33);
     const int pr = lane >> 3;            // pixel sub-row handled by this lane (0..3)
@@ -167,7 +178,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     const int lTW = p.log_tw, lTH = p.log_th;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int tile = w % total_tiles;
+      const int split = w / total_tiles;
       const int tm = tile % tiles_m;
       const int tco = tile / tiles_m;
       const int tx = tm % p.tiles_x;
@@ -187,63 +200,137 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
         aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
       }
+      // partial tile of this (tile, split): [128 rows][block_n] fp32, row-major
+      float* pbase = p.partial + ((long long)tile * ksplit) * (kConvBlockM * p.block_n);
+      float* pmine = pbase + (long long)split * (kConvBlockM * p.block_n) +
+                     (long long)(q * 32 + pr) * p.block_n + cq * 4;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kConvMaxBlockN;
-      for (int ch = 0; ch < p.block_n; ch += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + ch, r);
-        tmem_ld_wait();
+      const bool finalize = true;
+      if (ksplit > 1) {
+        // ---- phase 1: publish the raw accumulators of this K slice ----
+        for (int ch = 0; ch < p.block_n; ch += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
-        __syncwarp();
-        float4 v[8];
+          for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+          __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
-          v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
-        }
-        __syncwarp();
-        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
-        if (p.bias2) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
-          bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it)
-          if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
-        if (p.addend) {
-          float4 a[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-        }
-        if (p.accumulate) {
-          float4 a[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (!((vmask >> it) & 1u)) continue;
-          float4 o = v[it];
-          if (p.round_out) {
-            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+          for (int it = 0; it < 8; ++it) {
+            const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
+            __stcg(reinterpret_cast<float4*>(pmine + (long long)(it * 4) * p.block_n + ch),
+                   make_float4(tp[0], tp[1], tp[2], tp[3]));
           }
-          *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator stage is free again
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          // publish, then wait until every K slice of this tile is in L2.  All items of a split
+          // layer are co-resident (items <= #SMs, one per CTA), so this cannot deadlock; the
+          // bound turns a protocol bug into a launch error instead of a hang.
+          atomicAdd(&p.counters[tile], 1);
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile int*>(&p.counters[tile]) < ksplit) {
+            __nanosleep(64);
+            if (++spins > (1u << 22)) { printf("loco: split-K wait timeout tile %d\n", tile); __trap(); }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __threadfence();
+      }
+      if (finalize) {
+        for (int ch = 0; ch < p.block_n; ch += 32) {
+          // split-K: the (column chunk, lane quarter) units of the tile are dealt round-robin to
+          // the ksplit CTAs, so the final reduction + epilogue is spread over all of them
+          if (ksplit > 1 && (((ch >> 5) * 4 + q) % ksplit) != split) continue;
+          float4 v[8];
+          if (ksplit > 1) {
+            // ---- phase 2: fixed-order sum of the K slices (bit-reproducible) ----
+#pragma unroll
+            for (int it = 0; it < 8; ++it) v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* pr0 = pbase + (long long)(q * 32 + pr) * p.block_n + cq * 4 + ch;
+            for (int sidx = 0; sidx < ksplit; ++sidx) {
+              float4 t[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                t[it] = __ldcg(reinterpret_cast<const float4*>(
+                    pr0 + (long long)sidx * (kConvBlockM * p.block_n) + (long long)(it * 4) * p.block_n));
+#pragma unroll
+              for (int it = 0; it < 8; ++it) { v[it].x += t[it].x; v[it].y += t[it].y; v[it].z += t[it].z; v[it].w += t[it].w; }
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + ch, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
+              v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+            }
+            __syncwarp();
+          }
+          float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
+          if (p.bias2) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
+            bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+          if (p.addend) {
+            float4 a[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+          }
+          if (p.accumulate) {
+            float4 a[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (!((vmask >> it) & 1u)) continue;
+            float4 o = v[it];
+            if (p.round_out) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            }
+            *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (ksplit == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else {
+        // last CTA out resets the counters for the next launch
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int old = atomicAdd(&p.counters[p.counter_stride + tile], 1);
+          if (old == ksplit - 1) {
+            p.counters[tile] = 0;
+            p.counters[p.counter_stride + tile] = 0;
+          }
+        }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -439,9 +526,28 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     LOCO_REQUIRE(false, "conv: unknown kind %d", prob.kind);
   }
   for (int i = 0; i < L->nlaunch; ++i) {
-    const ConvGemmParams& p = L->p[i];
+    ConvGemmParams& p = L->p[i];
     const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_co;
-    L->grid[i] = tiles < sms ? tiles : sms;
+    // split the K loop when the layer has fewer tiles than SMs (small-resolution layers)
+    int ks = 1;
+    if (prob.splitk_partial && prob.splitk_counters && tiles <= prob.splitk_max_tiles && tiles * 2 <= sms) {
+      const int kiters = p.ntaps * p.c_chunks;
+      ks = sms / tiles;
+      if (ks > 16) ks = 16;
+      if (ks > kiters / 4) ks = kiters / 4;
+      if (ks < 1) ks = 1;
+      while (ks > 1 && (long long)tiles * ks * kConvBlockM * p.block_n > prob.splitk_partial_floats) --ks;
+    }
+    p.ksplit = ks;
+    {
+      const char* e = getenv("LOCO_CONV_DEBUG");
+      p.debug = e ? atoi(e) : 0;
+    }
+    p.partial = prob.splitk_partial;
+    p.counters = prob.splitk_counters;
+    p.counter_stride = prob.splitk_max_tiles;
+    const int items = tiles * ks;
+    L->grid[i] = items < sms ? items : sms;
     L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
   }
   return 0;

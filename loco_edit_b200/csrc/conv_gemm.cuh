@@ -33,6 +33,11 @@ struct ConvGemmParams {
   const float* bias;          // [Cout] or null; applied to batch rows n < bias_rows
   const float* bias2;         // second per-channel bias (timestep projection), same rule
   int bias_rows;
+  int debug;                  // profiling aid: 1 = exit at entry, 2 = setup/teardown only
+  int ksplit;                 // K-loop split factor (1 = none)
+  float* partial;             // split-K partial tiles [tile][split][128][block_n]
+  int* counters;              // split-K arrival [tile] and done [counter_stride + tile] counters
+  int counter_stride;
   int accumulate;             // out += result (VJP fan-in)
   int round_out;              // round stored values to tf32
 };
@@ -58,6 +63,11 @@ struct ConvProblem {
   const View* addend = nullptr;
   int accumulate = 0;
   int round_out = 0;
+  // optional split-K scratch shared by all launches of a stream (partials + zeroed counters)
+  float* splitk_partial = nullptr;
+  long long splitk_partial_floats = 0;
+  int* splitk_counters = nullptr;
+  int splitk_max_tiles = 0;
 };
 
 // A prepared launch: tensor maps encoded, grid sized. Valid while the buffers stay where they are.

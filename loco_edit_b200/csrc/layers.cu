@@ -58,6 +58,7 @@ __global__ void pack_edge_kernel(const float* __restrict__ w, float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Edge convolutions
 // ------------------------------------------------------------------------------------------------
+constexpr int kEdgeIters = 16;
 __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* __restrict__ We,
                                    const float* __restrict__ bias, int bias_rows, View out,
                                    int flip, int round_out) {
@@ -68,8 +69,10 @@ __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* _
   const int cvn = C >> 2;
   const int ppb = blockDim.x / cvn;
   const int cv = threadIdx.x % cvn;
-  const long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cvn;
   const int n = blockIdx.y;
+  // the 27 x C weight slab is staged once per block and amortised over kEdgeIters pixel groups
+  for (int it = 0; it < kEdgeIters; ++it) {
+  const long long pix = ((long long)blockIdx.x * kEdgeIters + it) * ppb + threadIdx.x / cvn;
   if (pix >= (long long)H * W) return;
   const int y = (int)(pix / W), x = (int)(pix % W);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -97,6 +100,7 @@ __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* _
     acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
   }
   *reinterpret_cast<float4*>(out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4) = acc;
+  }
 }
 
 // One warp per output pixel; lanes stride over channels, three warp reductions per pixel.
@@ -109,8 +113,9 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  const long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
   const int n = blockIdx.y;
+  for (int it = 0; it < kEdgeIters; ++it) {
+  const long long pix = ((long long)blockIdx.x * kEdgeIters + it) * wpb + (threadIdx.x >> 5);
   if (pix >= (long long)H * W) return;
   const int y = (int)(pix / W), x = (int)(pix % W);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -141,38 +146,52 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
     dst[(long long)H * W] = a1 + (ub ? bias[1] : 0.f);
     dst[2LL * H * W] = a2 + (ub ? bias[2] : 0.f);
   }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroups = 32;
+constexpr int kRC = 6;          // batch rows processed per register chunk (1 primal + 5 tangents)
+constexpr int kGnMaxRows = 96;  // rows whose per-group scalars fit the shared table
 
 __host__ __device__ inline int gn_block_dim(int C) { return (256 % (C / 4) == 0) ? 256 : 192; }
 
 struct GnGeom {
-  int block, ppb_step, ppb, nblk;
+  int block, pstep, ppb, nblk;
 };
-// Every thread owns one channel quad and `vec` pixels; all its loads are issued before the first
-// use (memory-level parallelism instead of a serial load->use chain).
-inline GnGeom gn_geom(int C, long long HW, int vec) {
+// A thread owns one channel quad of `pv` pixels and walks ALL batch rows of those pixels: the
+// primal value is loaded (and its sigmoid evaluated) once and shared by the k tangent / cotangent
+// rows, and the loads of a row chunk are issued together.
+inline GnGeom gn_geom(int C, long long HW, int pv) {
   GnGeom g;
   g.block = gn_block_dim(C);
-  g.ppb_step = g.block / (C / 4);
-  g.ppb = g.ppb_step * vec;
+  g.pstep = g.block / (C / 4);
+  g.ppb = g.pstep * pv;
   g.nblk = (int)((HW + g.ppb - 1) / g.ppb);
   return g;
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float fast_sigmoid(float u) { return __fdividef(1.0f, 1.0f + __expf(-u)); }
 
-// mode 0: forward/JVP statistics; mode 1: VJP statistics.
-template <int MODE, int VEC>
+// (mean, rstd) of a primal row's group from its (sum x, sum x^2)
+__device__ __forceinline__ float2 mean_rstd(const double* st, double cnt, float eps) {
+  const double mu = st[0] / cnt;
+  const double var = st[1] / cnt - mu * mu;
+  return make_float2((float)mu, (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps)));
+}
+
+// ---- statistics ---------------------------------------------------------------------------------
+// mode 0 (forward/JVP): rows < n_primal: (sum x, sum x^2); tangent rows: (sum dx, sum x0 dx).
+// mode 1 (VJP): a = gamma * act'(u) * gy;  rows: (sum a, sum x a), x = primal input (x has 1 row).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                double* __restrict__ stats) {
-  __shared__ float part[2][256];
+                double* __restrict__ stats, int pv) {
+  __shared__ float part[2 * kRC][256];
   const int C = x.C;
   const int cvn = C >> 2;
   const int cg = C / kGroups;
@@ -180,77 +199,102 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   const int prow = threadIdx.x / cvn;
   const int pstep = blockDim.x / cvn;
   const int g = (cv * 4) / cg;
-  const int n = blockIdx.y;
   const long long HW = (long long)x.H * x.W;
-  const long long p0 = (long long)blockIdx.x * (pstep * VEC) + prow;
-  const bool primal = (MODE == 0) && (n < n_primal);
-  const View& src = (MODE == 0) ? x : gy;
-  float4 a[VEC], b[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const long long p = p0 + (long long)j * pstep;
-    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    b[j] = a[j];
-    if (p < HW) {
-      const int y = (int)(p / x.W), xx = (int)(p % x.W);
-      a[j] = ld4(src.ptr + n * src.sN + (long long)y * src.sH + (long long)xx * src.sW + cv * 4);
-      if (!primal) b[j] = ld4(x.ptr + (long long)y * x.sH + (long long)xx * x.sW + cv * 4);
-    }
+  const long long pbase = (long long)blockIdx.x * (pstep * pv) + prow;
+  const View& rows = (MODE == 0) ? x : gy;
+  const int N = rows.N;
+  const bool jvp = (MODE == 0) && (n_primal < N);   // row 0 primal, rows 1.. tangents
+
+  // per-element factors of the primal point (VJP: a = fac * gy)
+  float fac[4] = {1.f, 1.f, 1.f, 1.f};
+  float mu = 0.f, rstd = 1.f;
+  float gs[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 1) {
+    const float2 mr = mean_rstd(pstats + g * 2, (double)HW * cg, eps);
+    mu = mr.x; rstd = mr.y;
+    const float4 ga = ld4(gamma + cv * 4), be = ld4(beta + cv * 4);
+    gs[0] = ga.x; gs[1] = ga.y; gs[2] = ga.z; gs[3] = ga.w;
+    bs[0] = be.x; bs[1] = be.y; bs[2] = be.z; bs[3] = be.w;
   }
-  float s1 = 0.f, s2 = 0.f;
-  if (MODE == 0) {
+
+  for (int n0 = 0; n0 < N; n0 += kRC) {
+    float s1[kRC], s2[kRC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float4 v = a[j];
-      const float4 w = primal ? v : b[j];
-      s1 += (v.x + v.y) + (v.z + v.w);
-      s2 += (v.x * w.x + v.y * w.y) + (v.z * w.z + v.w * w.w);
-    }
-  } else {
-    const double cnt = (double)HW * cg;
-    const double mu_d = pstats[g * 2] / cnt;
-    const double var_d = pstats[g * 2 + 1] / cnt - mu_d * mu_d;
-    const float mu = (float)mu_d;
-    const float rstd = (float)(1.0 / sqrt((var_d > 0 ? var_d : 0) + (double)eps));
-    const float4 ga = ld4(gamma + cv * 4);
-    const float4 be = ld4(beta + cv * 4);
-    const float gs[4] = {ga.x, ga.y, ga.z, ga.w};
-    const float bs[4] = {be.x, be.y, be.z, be.w};
+    for (int r = 0; r < kRC; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
+    for (int j = 0; j < pv; ++j) {
+      const long long p = pbase + (long long)j * pstep;
+      if (p >= HW) break;
+      const int y = (int)(p / x.W), xx = (int)(p % x.W);
+      const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
+      const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * 4;
+      float4 v[kRC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float xs[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
-      const float ds[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+      for (int r = 0; r < kRC; ++r)
+        v[r] = (n0 + r < N) ? ld4(rows.ptr + (long long)(n0 + r) * rows.sN + roff)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      float xs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (jvp || MODE == 1) {
+        const float4 x0 = (MODE == 0 && n0 == 0) ? v[0] : ld4(x.ptr + xoff);
+        xs[0] = x0.x; xs[1] = x0.y; xs[2] = x0.z; xs[3] = x0.w;
+      }
+      if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float u = gs[i] * ((xs[i] - mu) * rstd) + bs[i];
-        const float av = gs[i] * (silu ? silu_grad(u) : 1.0f) * ds[i];   // ds = 0 outside the image
-        s1 += av;
-        s2 += av * xs[i];
+        for (int i = 0; i < 4; ++i) {
+          const float u = gs[i] * ((xs[i] - mu) * rstd) + bs[i];
+          float d = 1.0f;
+          if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
+          fac[i] = gs[i] * d;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRC; ++r) {
+        const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        const bool tangent = jvp && (n0 + r >= n_primal);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (MODE == 0) {
+            s1[r] += vs[i];
+            s2[r] += vs[i] * (tangent ? xs[i] : vs[i]);
+          } else {
+            const float av = fac[i] * vs[i];
+            s1[r] += av;
+            s2[r] += av * xs[i];
+          }
+        }
       }
     }
-  }
-  // fixed-order block reduction (bit-reproducible per block); fp64 atomics across blocks
-  part[0][threadIdx.x] = s1;
-  part[1][threadIdx.x] = s2;
-  __syncthreads();
-  if (threadIdx.x < kGroups * 2) {
-    const int gg = threadIdx.x >> 1, which = threadIdx.x & 1;
-    const int cv0 = gg * (cg >> 2), cv1 = cv0 + (cg >> 2);
-    float v = 0.f;
-    for (int pr = 0; pr < pstep; ++pr)
-      for (int c = cv0; c < cv1; ++c) v += part[which][pr * cvn + c];
-    atomicAdd(&stats[(long long)n * kGroups * 2 + threadIdx.x], (double)v);
+    // fixed-order block reduction (bit-reproducible per block); fp64 atomics across blocks
+#pragma unroll
+    for (int r = 0; r < kRC; ++r) {
+      part[2 * r][threadIdx.x] = s1[r];
+      part[2 * r + 1][threadIdx.x] = s2[r];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kRC * kGroups * 2; e += blockDim.x) {
+      const int r = e / (kGroups * 2), gw = e % (kGroups * 2);
+      if (n0 + r >= N) continue;
+      const int gg = gw >> 1, which = gw & 1;
+      const int cv0 = gg * (cg >> 2), cv1 = cv0 + (cg >> 2);
+      float acc = 0.f;
+      for (int pr2 = 0; pr2 < pstep; ++pr2)
+        for (int c = cv0; c < cv1; ++c) acc += part[2 * r + which][pr2 * cvn + c];
+      atomicAdd(&stats[(long long)(n0 + r) * kGroups * 2 + gw], (double)acc);
+    }
+    __syncthreads();
   }
 }
 
-// mode 0: forward/JVP apply; mode 1: VJP apply.
-template <int MODE, int VEC>
+// ---- apply ----------------------------------------------------------------------------------------
+// mode 0: y = act(gn(x)) for primal rows, JVP rule for tangent rows.  mode 1: VJP rule.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const double* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int silu, int round_out,
                 const float* __restrict__ addend, long long add_sN, long long add_sH,
-                long long add_sW, int accumulate, View out) {
+                long long add_sW, int accumulate, View out, int pv) {
+  // per (row, group) scalars: primal rows (mean, rstd); tangent / cotangent rows (m1, m2)
+  __shared__ float2 tab[kGnMaxRows][kGroups];
   const int C = x.C;
   const int cvn = C >> 2;
   const int cg = C / kGroups;
@@ -258,77 +302,98 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   const int prow = threadIdx.x / cvn;
   const int pstep = blockDim.x / cvn;
   const int g = (cv * 4) / cg;
-  const int n = blockIdx.y;
   const long long HW = (long long)x.H * x.W;
-  const long long p0 = (long long)blockIdx.x * (pstep * VEC) + prow;
   const double cnt = (double)HW * cg;
-
-  const bool primal = (MODE == 0) && (n < n_primal);
-  // statistics of the primal row this thread normalises against
-  const double* ps = (MODE == 0) ? stats + (long long)(primal ? n : 0) * kGroups * 2 : pstats;
-  const double mu_d = ps[g * 2] / cnt;
-  const double var_d = ps[g * 2 + 1] / cnt - mu_d * mu_d;
-  const float mu = (float)mu_d;
-  const float rstd = (float)(1.0 / sqrt((var_d > 0 ? var_d : 0) + (double)eps));
-  float m1 = 0.f, m2 = 0.f;
-  if (!primal) {
-    const double* ts = stats + (long long)n * kGroups * 2;
-    const double sa = ts[g * 2], sxa = ts[g * 2 + 1];
-    m1 = (float)(sa / cnt);
-    m2 = (float)((sxa - mu_d * sa) * (double)rstd / cnt);
+  const View& rows = (MODE == 0) ? x : gy;
+  const int N = rows.N;
+  const bool jvp = (MODE == 0) && (n_primal < N);
+  const double* prim = (MODE == 0) ? stats : pstats;    // statistics of primal row 0
+  for (int e = threadIdx.x; e < N * kGroups; e += blockDim.x) {
+    const int n = e / kGroups, gg = e % kGroups;
+    const bool is_primal = (MODE == 0) && (n < n_primal);
+    if (is_primal) {
+      tab[n][gg] = mean_rstd(stats + ((long long)n * kGroups + gg) * 2, cnt, eps);
+    } else {
+      const float2 mr = mean_rstd(prim + gg * 2, cnt, eps);
+      const double sa = stats[((long long)n * kGroups + gg) * 2];
+      const double sxa = stats[((long long)n * kGroups + gg) * 2 + 1];
+      tab[n][gg] = make_float2((float)(sa / cnt),
+                               (float)((sxa - (double)mr.x * sa) * (double)mr.y / cnt));
+    }
   }
-  const float4 ga4 = ld4(gamma + cv * 4);
-  const float4 be4 = ld4(beta + cv * 4);
+  __syncthreads();
+  const float4 ga4 = ld4(gamma + cv * 4), be4 = ld4(beta + cv * 4);
   const float gs[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
   const float bs[4] = {be4.x, be4.y, be4.z, be4.w};
-  const View& src = (MODE == 0) ? x : gy;
+  float2 mr0 = make_float2(0.f, 1.f);
+  if (jvp || MODE == 1) mr0 = (MODE == 0) ? tab[0][g] : mean_rstd(pstats + g * 2, cnt, eps);
 
-  // ---- load phase ----
-  float4 a[VEC], b[VEC], e[VEC];
-  long long ooff[VEC];
+  const long long pbase = (long long)blockIdx.x * (pstep * pv) + prow;
+  for (int j = 0; j < pv; ++j) {
+    const long long p = pbase + (long long)j * pstep;
+    if (p >= HW) break;
+    const int y = (int)(p / x.W), xx = (int)(p % x.W);
+    const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
+    const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * 4;
+    const long long ooff = (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
+    const long long aoff = (long long)y * add_sH + (long long)xx * add_sW + cv * 4;
+    // primal-point quantities shared by every tangent / cotangent row of this pixel
+    float xh[4] = {0.f, 0.f, 0.f, 0.f}, coef[4] = {1.f, 1.f, 1.f, 1.f};
+    if (jvp || MODE == 1) {
+      const float4 x0 = ld4(x.ptr + xoff);
+      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const long long p = p0 + (long long)j * pstep;
-    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    b[j] = a[j];
-    e[j] = a[j];
-    ooff[j] = -1;
-    if (p < HW) {
-      const int y = (int)(p / x.W), xx = (int)(p % x.W);
-      a[j] = ld4(src.ptr + n * src.sN + (long long)y * src.sH + (long long)xx * src.sW + cv * 4);
-      if (!primal) b[j] = ld4(x.ptr + (long long)y * x.sH + (long long)xx * x.sW + cv * 4);
-      ooff[j] = n * out.sN + (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
-      if (MODE == 1 && addend) e[j] = ld4(addend + n * add_sN + (long long)y * add_sH + (long long)xx * add_sW + cv * 4);
-      if (MODE == 1 && accumulate) {
-        const float4 c = ld4(out.ptr + ooff[j]);
-        e[j].x += c.x; e[j].y += c.y; e[j].z += c.z; e[j].w += c.w;
+      for (int i = 0; i < 4; ++i) {
+        xh[i] = (xs[i] - mr0.x) * mr0.y;
+        const float u = gs[i] * xh[i] + bs[i];
+        float d = 1.0f;
+        if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
+        coef[i] = d * gs[i];          // act'(u) * gamma
       }
     }
-  }
-  // ---- compute + store phase ----
+    for (int n0 = 0; n0 < N; n0 += kRC) {
+      float4 v[kRC], e[kRC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    if (ooff[j] < 0) continue;
-    const float vs[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
-    const float xs[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
-    const float es[4] = {e[j].x, e[j].y, e[j].z, e[j].w};
-    float r[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (MODE == 0 && primal) {
-        const float u = gs[i] * ((vs[i] - mu) * rstd) + bs[i];
-        r[i] = silu ? silu_f(u) : u;
-      } else {
-        const float xh = (xs[i] - mu) * rstd;
-        const float u = gs[i] * xh + bs[i];
-        const float dact = silu ? silu_grad(u) : 1.0f;
-        if (MODE == 0) r[i] = dact * gs[i] * rstd * (vs[i] - m1 - xh * m2);
-        else r[i] = rstd * (gs[i] * dact * vs[i] - m1 - xh * m2);
+      for (int r = 0; r < kRC; ++r) {
+        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        e[r] = v[r];
+        if (n0 + r < N) {
+          v[r] = ld4(rows.ptr + (long long)(n0 + r) * rows.sN + roff);
+          if (MODE == 1 && addend) e[r] = ld4(addend + (long long)(n0 + r) * add_sN + aoff);
+          if (MODE == 1 && accumulate) {
+            const float4 c = ld4(out.ptr + (long long)(n0 + r) * out.sN + ooff);
+            e[r].x += c.x; e[r].y += c.y; e[r].z += c.z; e[r].w += c.w;
+          }
+        }
       }
-      if (MODE == 1) r[i] += es[i];
-      if (round_out) r[i] = round_tf32(r[i]);
+#pragma unroll
+      for (int r = 0; r < kRC; ++r) {
+        const int n = n0 + r;
+        if (n >= N) break;
+        const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        const float es[4] = {e[r].x, e[r].y, e[r].z, e[r].w};
+        const float2 t2 = tab[n][g];
+        float o[4];
+        if (MODE == 0 && n < n_primal) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float u = gs[i] * ((vs[i] - t2.x) * t2.y) + bs[i];
+            o[i] = silu ? u * fast_sigmoid(u) : u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (MODE == 0) o[i] = coef[i] * mr0.y * (vs[i] - t2.x - xh[i] * t2.y);
+            else o[i] = mr0.y * (coef[i] * vs[i] - t2.x - xh[i] * t2.y) + es[i];
+          }
+        }
+        if (round_out) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = round_tf32(o[i]);
+        }
+        *reinterpret_cast<float4*>(out.ptr + (long long)n * out.sN + ooff) = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
-    *reinterpret_cast<float4*>(out.ptr + ooff[j]) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -495,7 +560,8 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
   LOCO_REQUIRE(out.C % 4 == 0 && 256 % (out.C / 4) == 0, "edge_conv_expand: C=%d unsupported", out.C);
   const int ppb = 256 / (out.C / 4);
   const long long HW = (long long)out.H * out.W;
-  dim3 grid((unsigned)((HW + ppb - 1) / ppb), out.N);
+  const long long ppb_all = (long long)ppb * kEdgeIters;
+  dim3 grid((unsigned)((HW + ppb_all - 1) / ppb_all), out.N);
   const size_t smem = 27 * out.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_expand: C=%d too large", out.C);
   edge_expand_kernel<<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
@@ -506,7 +572,7 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
                      int flip, cudaStream_t s) {
   LOCO_REQUIRE(in.C % 4 == 0, "edge_conv_reduce: C=%d unsupported", in.C);
   const long long HW = (long long)in.H * in.W;
-  dim3 grid((unsigned)((HW + 7) / 8), in.N);
+  dim3 grid((unsigned)((HW + 8 * kEdgeIters - 1) / (8 * kEdgeIters)), in.N);
   const size_t smem = 27 * in.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_reduce: C=%d too large", in.C);
   edge_reduce_kernel<<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
@@ -514,13 +580,40 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   return 0;
 }
 
+// All kernels of the U-Net programs ask for the same (maximum shared memory) L1/smem split as the
+// tcgen05 conv kernel, so the SMs never have to re-partition between consecutive launches.
+int layers_init() {
+  static bool done = false;
+  if (done) return 0;
+  const int co = cudaSharedmemCarveoutMaxShared;
+#define LOCO_CARVE(k) LOCO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co))
+  LOCO_CARVE(gn_stats_kernel<0>); LOCO_CARVE(gn_stats_kernel<1>);
+  LOCO_CARVE(gn_apply_kernel<0>); LOCO_CARVE(gn_apply_kernel<1>);
+  LOCO_CARVE(edge_expand_kernel); LOCO_CARVE(edge_reduce_kernel);
+  LOCO_CARVE(upsample2x_kernel); LOCO_CARVE(sumpool2x_kernel); LOCO_CARVE(add_views_kernel);
+  LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
+#undef LOCO_CARVE
+  done = true;
+  return 0;
+}
+
+static int gn_pv(int C, long long HW) {
+  // pixels per thread: enough blocks for >= 2 waves on large tensors, short chains on small ones
+  const int pstep = gn_block_dim(C) / (C / 4);
+  const long long blocks1 = (HW + pstep - 1) / pstep;
+  int pv = (int)(blocks1 / (148 * 4));
+  if (pv < 1) pv = 1;
+  if (pv > 8) pv = 8;
+  return pv;
+}
+
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, 8);
-  dim3 grid(g.nblk, x.N);
-  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 2 : 1), s);
-  gn_stats_kernel<0, 8><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
-                                                 stats);
+  const int pv = gn_pv(x.C, (long long)x.H * x.W);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, pv);
+  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C, s);
+  gn_stats_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
+                                               stats, pv);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -528,11 +621,12 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
                  float eps, int silu, int round_out, View y, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_apply_fwd"));
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, 8);
-  dim3 grid(g.nblk, x.N);
-  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C * (n_primal < x.N ? 3 : 2), s);
-  gn_apply_kernel<0, 8><<<grid, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
-                                                 silu, round_out, nullptr, 0, 0, 0, 0, y);
+  LOCO_REQUIRE(x.N <= kGnMaxRows, "gn_apply_fwd: batch %d > %d rows", x.N, kGnMaxRows);
+  const int pv = gn_pv(x.C, (long long)x.H * x.W);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, pv);
+  ProfScope prof(1, 8.0 * x.N * x.H * x.W * x.C, s);
+  gn_apply_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                               silu, round_out, nullptr, 0, 0, 0, 0, y, pv);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -540,10 +634,10 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
                  float eps, int silu, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, 8);
-  dim3 grid(g.nblk, gy.N);
-  ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * 2, s);
-  gn_stats_kernel<1, 8><<<grid, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats);
+  const int pv = gn_pv(xp.C, (long long)xp.H * xp.W);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, pv);
+  ProfScope prof(1, 4.0 * (gy.N + 1) * gy.H * gy.W * gy.C, s);
+  gn_stats_kernel<1><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, pv);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -554,12 +648,13 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   LOCO_TRY(check_gn_view(gy, "gn_apply_vjp(gy)"));
   LOCO_TRY(check_gn_view(gx, "gn_apply_vjp(gx)"));
   if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, 4);
-  dim3 grid(g.nblk, gy.N);
-  ProfScope prof(1, 4.0 * gy.N * gy.H * gy.W * gy.C * (addend ? 4 : 3), s);
-  gn_apply_kernel<1, 4><<<grid, g.block, 0, s>>>(
+  LOCO_REQUIRE(gy.N <= kGnMaxRows, "gn_apply_vjp: batch %d > %d rows", gy.N, kGnMaxRows);
+  const int pv = gn_pv(xp.C, (long long)xp.H * xp.W);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, pv);
+  ProfScope prof(1, 4.0 * gy.H * gy.W * gy.C * (1 + gy.N * (2 + (addend ? 1 : 0) + (accumulate ? 1 : 0))), s);
+  gn_apply_kernel<1><<<g.nblk, g.block, 0, s>>>(
       xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx);
+      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, pv);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

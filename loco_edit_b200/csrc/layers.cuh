@@ -5,6 +5,8 @@
 
 namespace loco {
 
+int layers_init();   // one-time kernel attribute setup
+
 // ---- weight packing (done once when parameters are loaded) ----
 // torch conv weight [Cout][Cin][kh][kw] -> GEMM operand [Cout][(r*kw+s)*Cin + ci], tf32-rounded.
 int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s);

@@ -341,7 +341,7 @@ int Plan::build(float* workspace) {
   const int L = A.n_levels;
   LOCO_REQUIRE(A.ch % 128 == 0, "plan: base channel count %d must be a multiple of 128", A.ch);
   if (!dry) LOCO_REQUIRE(M.arena != nullptr, "plan: model weights not bound");
-  if (!dry) LOCO_TRY(conv_init());
+  if (!dry) { LOCO_TRY(conv_init()); LOCO_TRY(layers_init()); LOCO_TRY(attention_init()); }
 
   I.fwd.clear(); I.bwd_groups.clear(); I.bwd.clear(); I.launches.clear(); I.writers.clear();
   I.n_ids = 0;
@@ -394,6 +394,15 @@ int Plan::build(float* workspace) {
     return I.acc_flags[idx];
   };
 
+  // ---- split-K scratch shared by every conv launch of this plan (same stream => serialised) ----
+  const long long splitk_floats = 4LL << 20;          // 16 MB of partial tiles
+  const int splitk_tiles = 4096;
+  float* splitk_partial = alloc_act((size_t)splitk_floats);
+  int* splitk_counters = reinterpret_cast<int*>(alloc_act(2 * splitk_tiles));   // arrive + done
+  if (!dry) {
+    const cudaError_t ce = cudaMemset(splitk_counters, 0, sizeof(int) * 2 * splitk_tiles);
+    LOCO_REQUIRE(ce == cudaSuccess, "plan: cudaMemset(counters) failed: %s", cudaGetErrorString(ce));
+  }
   int err = 0;
   auto mk_conv = [&](ConvProblem prob, bool is_bwd) -> ConvLaunch* {
     I.launches.emplace_back();
@@ -401,6 +410,8 @@ int Plan::build(float* workspace) {
     const double fl = 2.0 * prob.out.N * prob.out.H * prob.out.W * (double)prob.Ngemm * prob.Kc *
                       (prob.kind == CONV_1x1 ? 1 : 9) / (prob.kind == CONV_3x3_S2_DGRAD ? 4 : 1);
     (is_bwd ? vjp_flops : fwd_flops) += fl;
+    prob.splitk_partial = splitk_partial; prob.splitk_partial_floats = splitk_floats;
+    prob.splitk_counters = splitk_counters; prob.splitk_max_tiles = splitk_tiles;
     if (!dry) {
       const int r = conv_prepare(prob, L_);
       if (r != 0 && err == 0) err = r;

@@ -152,7 +152,7 @@ class PullbackWorkspace:
 # ---------------------------------------------------------------------------------------------
 # single layers (parity tests)
 # ---------------------------------------------------------------------------------------------
-def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=False, out=None):
+def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=False, out=None, splitk=True):
     """kind: 0 3x3 | 1 1x1 | 2 3x3 stride-2 pad(0,1,0,1) | 3 dgrad of 0 | 4 dgrad of 2.
     x: [N,H,W,C] channels-last contiguous; w: torch conv weight [Cout,Cin,k,k] of the forward conv."""
     x, w = _f32(x), _f32(w)
@@ -163,9 +163,11 @@ def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=Fals
     if out is None:
         out = torch.zeros(N, Ho, Wo, Cy, dtype=torch.float32, device=x.device)
     wpack = torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+    scr = torch.zeros(16 << 20, dtype=torch.uint8, device=x.device) if splitk else None
     check(_lib.load().loco_conv2d_nhwc(kind, ptr(x), N, H, W_, Cx, ptr(w), Cout, Cin, ptr(wpack),
                                        ptr(bias), bias_rows, ptr(addend), 1 if accumulate else 0,
-                                       ptr(out), stream_ptr()), "loco_conv2d_nhwc")
+                                       ptr(out), ptr(scr), scr.numel() if splitk else 0, stream_ptr()),
+          "loco_conv2d_nhwc")
     return out
 
 
