@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- LOCO-Edit editing-direction hot path on B200 (contract: see the task statement).
 
-One step = one BASELINE config-1 "edit" of one synthetic 256x256 image on the DDPM-256 U-Net
+One "edit" = the BASELINE config-1 pipeline for one synthetic 256x256 image on the DDPM-256 U-Net
 (random-init, seed 1234): DDIM inversion (98 U-Net calls) + forward to t=0.6T (40) + rank-5 local
 basis of the masked PMP Jacobian (12 power iterations) + rank-5 null basis (12) + null-space
 projection + 59 DDIM steps on the 5-latent edit batch (= 697 U-Net-forward equivalents, 346 TFLOP).
-Each rank edits its own images (weak scaling, no data-path collective).
+One step = one batch of --batch image/mask pairs edited together on each GPU (BASELINE config 2:
+64 pairs over 8 GPUs = 8 per GPU; --batch 1 = config 1).  Each rank edits its own images (weak
+scaling, no data-path collective).
 
   python bench.py --gpus 1 --steps 3 --warmup 3          # our CUDA path
   python bench.py --impl reference ...                    # reference algorithm on the host cores
@@ -168,6 +170,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -181,9 +185,21 @@ def run_ours(args):
     gen = torch.Generator(device=dev)
     R = 256
 
+    BATCH = args.batch
+
     def host_inputs(i):
-        x0, m = synthetic_inputs(R, i)
-        return x0.pin_memory(), m.pin_memory()
+        xs, ms = zip(*[synthetic_inputs(R, i * BATCH + j) for j in range(BATCH)])
+        return torch.cat(xs, 0).pin_memory(), torch.stack(ms, 0).pin_memory()
+
+    def run_dev(x0, m):
+        if BATCH == 1:
+            return pipe.edit_device(x0, m[0], gen=gen)["images"]
+        return pipe.edit_batch_device(x0, m, gen=gen)["images"]
+
+    def run_host(x0, m):
+        if BATCH == 1:
+            return pipe.edit(x0, m[0], gen=gen)
+        return pipe.edit_batch(x0, m, gen=gen)
 
     def barrier():
         if world > 1:
@@ -201,13 +217,13 @@ def run_ours(args):
     for w in range(args.warmup):
         gen.manual_seed(1000 + w)
         x0, m = host_inputs(rank * 1000 + w)
-        pipe.edit(x0, m, gen=gen)
+        run_host(x0, m)
     barrier()
 
     # ---- device-resident timed region: `value` ----
     dev_inputs = []
     for s in range(args.steps):
-        x0, m = synthetic_inputs(R, rank * 1000 + 100 + s)
+        x0, m = host_inputs(rank * 1000 + 100 + s)
         dev_inputs.append((x0.to(dev), m.to(dev)))
     sampler = ClockSampler(local)
     if rank == 0:
@@ -218,7 +234,7 @@ def run_ours(args):
     e0.record()
     for s in range(args.steps):
         gen.manual_seed(2000 + s)
-        pipe.edit_device(dev_inputs[s][0], dev_inputs[s][1], gen=gen)
+        run_dev(dev_inputs[s][0], dev_inputs[s][1])
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
@@ -231,7 +247,7 @@ def run_ours(args):
     d2h = 0
     for s in range(args.steps):
         gen.manual_seed(3000 + s)
-        imgs = pipe.edit(host[s][0], host[s][1], gen=gen)
+        imgs = run_host(host[s][0], host[s][1])
         d2h = imgs.numel() * 4
     e1.record()
     barrier()
@@ -246,7 +262,7 @@ def run_ours(args):
     if rank == 0:
         lib.loco_profile_enable(1)
         gen.manual_seed(4000)
-        pipe.edit_device(dev_inputs[0][0], dev_inputs[0][1], gen=gen)
+        run_dev(dev_inputs[0][0], dev_inputs[0][1])
         import ctypes as C
         ms = (C.c_double * 3)(); work = (C.c_double * 3)(); nl = (C.c_longlong * 3)()
         lib.loco_profile_collect(ms, work, nl, 3)
@@ -258,7 +274,7 @@ def run_ours(args):
                 "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
-                "conv_ms_per_edit": ms[0], "groupnorm_ms_per_edit": ms[1],
+                "conv_ms_per_step": ms[0], "groupnorm_ms_per_step": ms[1],
                 "groupnorm_gbs": work[1] / (ms[1] * 1e-3) / 1e9 if ms[1] > 0 else 0.0,
                 "hbm_peak_gbs": pk["hbm_gbs"]}
         # JVP / VJP probe throughput (fused rank-5 passes)
@@ -281,6 +297,17 @@ def run_ours(args):
         probes = {"jvp_probes_per_s": K_RANK * reps / (a.elapsed_time(b) * 1e-3),
                   "vjp_probes_per_s": K_RANK * reps / (b.elapsed_time(c) * 1e-3),
                   "jvp_pass_ms": a.elapsed_time(b) / reps, "vjp_pass_ms": b.elapsed_time(c) / reps}
+        for bsz in sorted({1, BATCH, 5 * BATCH}):
+            pl = unet.plan(bsz)
+            xb = torch.randn(bsz, 3, R, R, device=dev)
+            pl.forward(xb, 595.3636)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                pl.forward(xb, 595.3636)
+            b.record()
+            torch.cuda.synchronize()
+            probes["fwd_b%d_ms" % bsz] = a.elapsed_time(b) / reps
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -293,16 +320,18 @@ def run_ours(args):
                "jvp_probes_per_s": smp["jvp_probes_per_s"]}
 
     if rank == 0:
-        n_edits = args.steps * world
+        n_edits = args.steps * world * BATCH
         value = n_edits / (ms_dev * 1e-3)
         line = {
             "metric": "edits/sec (rank-5 @256^2, t=0.6T)", "value": value, "unit": "edits/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "config-1 edit: DDPM-256 (ddpm-ema-celebahq-256 arch, random init), one "
-                                   "256x256 image per step per GPU, rank 5 + null rank 5, N=12 power iterations, "
-                                   "t=0.6T, 98+40+59 DDIM steps, edit batch 5",
+            "config": {"workload": "batch edit (BASELINE config 2 shape): DDPM-256 (ddpm-ema-celebahq-256 arch, "
+                                   "random init), %d image/mask pairs of 256x256 per step per GPU, each a full "
+                                   "config-1 edit: rank 5 + null rank 5, N=12 power iterations, t=0.6T, "
+                                   "98+40+59 DDIM steps, 5 edited latents per image" % BATCH,
+                       "images_per_step_per_gpu": BATCH,
                        "fwd_equivalents_per_edit": EDIT_FWD_EQUIV,
                        "tflop_per_edit": EDIT_FWD_EQUIV * F_DDPM256 / 1e12,
                        "l2": "per-edit working set (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
@@ -326,6 +355,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="image/mask pairs edited together per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,14 +19,19 @@ namespace loco {
 
 namespace {
 
-constexpr int kStages = 6;
-constexpr int kABytes = kConvBlockM * 128;       // 16 KB
-constexpr int kBBytes = kConvMaxBlockN * 128;    // 16 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kTmemCols = 256;                   // 2 accumulator stages x 128 fp32 columns
+constexpr int kABytes = kConvBlockM * 128;       // 16 KB: 128 pixels x 32 fp32 channels
+constexpr int kBBytes = kConvMaxBlockN * 128;    // 16 KB: 128 output channels x 32 fp32 channels
 constexpr int kThreads = 256;
-constexpr int kEpiBytes = 4 * 32 * 33 * 4;         // per-epilogue-warp transpose buffers
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+constexpr int kEpiBytes = 4 * 32 * 33 * 4;       // per-epilogue-warp transpose buffers
+// NT = M tiles (of 128 pixels) per work item.  NT = 2 shares every weight tile between two pixel
+// tiles: 48 KB of operands per two MMA groups instead of 64 KB, which matters because the kernel
+// is bound by the ~70 B/clk an SM can ingest from L2, not by the tensor pipe.
+template <int NT> struct Cfg {
+  static constexpr int kStages = NT == 1 ? 6 : 4;
+  static constexpr int kStageBytes = NT * kABytes + kBBytes;
+  static constexpr int kTmemCols = NT * 256;     // 2 accumulator stages x NT x 128 fp32 columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+};
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row
 // groups 1024 bytes apart (cute::UMMA::SmemDescriptor layout; version = 1 for sm_100).
@@ -51,8 +56,13 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return d;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
+  constexpr int kStages = Cfg<NT>::kStages;
+  constexpr int kStageBytes = Cfg<NT>::kStageBytes;
+  constexpr int kTmemCols = Cfg<NT>::kTmemCols;
+  constexpr int kBOff = NT * kABytes;            // weight tile offset inside a stage
   if (p.debug == 1) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -62,7 +72,6 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
   float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -93,38 +102,51 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int total_tiles = tiles_m * p.tiles_co;
+  const int units_m = tiles_m / NT;              // NT == 2 requires an even tile count
+  const int total_units = units_m * p.tiles_co;
   const int kiters = p.ntaps * p.c_chunks;
-  // Work item = (tile, K split).  Layers with fewer tiles than SMs split their K loop over several
-  // CTAs; the last CTA to finish a tile sums the partial tiles in fixed order and runs the epilogue.
-  const int ksplit = p.ksplit;
-  const int total_items = p.debug == 2 ? 0 : total_tiles * ksplit;
+  // Work item = (unit of NT pixel tiles x one output-channel tile, K split).  Layers with fewer
+  // tiles than SMs split their K loop over several CTAs (NT == 1 only); the partial tiles meet in
+  // L2 and every split CTA reduces + finishes its share of the tile.
+  const int ksplit = NT == 1 ? p.ksplit : 1;
+  const int total_items = p.debug == 2 ? 0 : total_units * ksplit;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * 128u;
+      const uint32_t tx_bytes = NT * kABytes + (uint32_t)p.block_n * 128u;
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const int tile = w % total_tiles;
-        const int split = w / total_tiles;
+        const int unit = w % total_units;
+        const int split = w / total_units;
         const int k0 = (int)((long long)kiters * split / ksplit);
         const int k1 = (int)((long long)kiters * (split + 1) / ksplit);
-        const int tm = tile % tiles_m;
-        const int tco = tile / tiles_m;
-        const int tx = tm % p.tiles_x;
-        const int ty = (tm / p.tiles_x) % p.tiles_y;
-        const int tn = tm / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, co0 = tco * p.block_n;
+        const int um = unit % units_m;
+        const int co0 = (unit / units_m) * p.block_n;
+        int x0[NT], y0[NT], n0[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int tm = um * NT + j;
+          x0[j] = (tm % p.tiles_x) * p.TW;
+          y0[j] = ((tm / p.tiles_x) % p.tiles_y) * p.TH;
+          n0[j] = (tm / (p.tiles_x * p.tiles_y)) * p.TN;
+        }
         int tap = k0 / p.c_chunks, cc = k0 % p.c_chunks;
         for (int it = k0; it < k1; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
+          if (p.debug == 3) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(sa, &p.amap[p.tap_map[tap]], &full_bar[stage], cc * kConvBlockK,
-                      x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n0);
-          tma_load_2d(sa + kABytes, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+          const CUtensorMap* am = &p.amap[p.tap_map[tap]];
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            tma_load_4d(sa + j * kABytes, am, &full_bar[stage], cc * kConvBlockK, x0[j] + p.tap_dx[tap],
+                        y0[j] + p.tap_dy[tap], n0[j]);
+          tma_load_2d(sa + kBOff, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++cc == p.c_chunks) { cc = 0; ++tap; }
         }
@@ -140,27 +162,35 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc_tf32(p.block_n);
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const int split = w / total_tiles;
+        const int split = w / total_units;
         const int nk = (int)((long long)kiters * (split + 1) / ksplit) - (int)((long long)kiters * split / ksplit);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kConvMaxBlockN;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT) * kConvMaxBlockN;
         for (int it = 0; it < nk; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+          const uint64_t bdesc = make_smem_desc(sa + kBOff);
+          if (p.debug == 4) {
+            mbar_arrive(&empty_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
-          for (int k = 0; k < kConvBlockK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
-            umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (uint32_t)((it | k) != 0));
+          for (int j = 0; j < NT; ++j) {
+            const uint64_t adesc = make_smem_desc(sa + j * kABytes);
+#pragma unroll
+            for (int k = 0; k < kConvBlockK / 8; ++k) {
+              // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
+              umma_tf32(d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+                        idesc, (uint32_t)((it | k) != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (p.debug == 4) mbar_arrive(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -179,72 +209,73 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-      const int tile = w % total_tiles;
-      const int split = w / total_tiles;
-      const int tm = tile % tiles_m;
-      const int tco = tile / tiles_m;
-      const int tx = tm % p.tiles_x;
-      const int ty = (tm / p.tiles_x) % p.tiles_y;
-      const int tn = tm / (p.tiles_x * p.tiles_y);
-      const int co0 = tco * p.block_n;
-      long long ooff[8], aoff[8];
-      uint32_t vmask = 0, bmask = 0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int R = q * 32 + it * 4 + pr;
-        const int x = tx * p.TW + (R & (p.TW - 1));
-        const int y = ty * p.TH + ((R >> lTW) & (p.TH - 1));
-        const int n = tn * p.TN + (R >> (lTW + lTH));
-        if (n < p.N && y < p.Ho && x < p.Wo) vmask |= 1u << it;
-        if (n < p.bias_rows) bmask |= 1u << it;
-        ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
-        aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
-      }
-      // partial tile of this (tile, split): [128 rows][block_n] fp32, row-major
-      float* pbase = p.partial + ((long long)tile * ksplit) * (kConvBlockM * p.block_n);
-      float* pmine = pbase + (long long)split * (kConvBlockM * p.block_n) +
-                     (long long)(q * 32 + pr) * p.block_n + cq * 4;
+      const int unit = w % total_units;
+      const int split = w / total_units;
+      const int um = unit % units_m;
+      const int co0 = (unit / units_m) * p.block_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kConvMaxBlockN;
-      const bool finalize = true;
-      if (ksplit > 1) {
-        // ---- phase 1: publish the raw accumulators of this K slice ----
-        for (int ch = 0; ch < p.block_n; ch += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch, r);
-          tmem_ld_wait();
+#pragma unroll 1
+      for (int jt = 0; jt < (p.debug == 5 ? 0 : NT); ++jt) {
+        const int tm = um * NT + jt;
+        const int tx = tm % p.tiles_x;
+        const int ty = (tm / p.tiles_x) % p.tiles_y;
+        const int tn = tm / (p.tiles_x * p.tiles_y);
+        long long ooff[8], aoff[8];
+        uint32_t vmask = 0, bmask = 0;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
-          __syncwarp();
+        for (int it = 0; it < 8; ++it) {
+          const int R = q * 32 + it * 4 + pr;
+          const int x = tx * p.TW + (R & (p.TW - 1));
+          const int y = ty * p.TH + ((R >> lTW) & (p.TH - 1));
+          const int n = tn * p.TN + (R >> (lTW + lTH));
+          if (n < p.N && y < p.Ho && x < p.Wo) vmask |= 1u << it;
+          if (n < p.bias_rows) bmask |= 1u << it;
+          ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
+          aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)(acc * NT + jt) * kConvMaxBlockN;
+        // partial tile of this (unit, split): [128 rows][block_n] fp32, row-major (split-K only)
+        float* pbase = p.partial + ((long long)unit * ksplit) * (kConvBlockM * p.block_n);
+        if (ksplit > 1) {
+          // ---- phase 1: publish the raw accumulators of this K slice ----
+          float* pmine = pbase + (long long)split * (kConvBlockM * p.block_n) +
+                         (long long)(q * 32 + pr) * p.block_n + cq * 4;
+          for (int ch = 0; ch < p.block_n; ch += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + ch, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
-            __stcg(reinterpret_cast<float4*>(pmine + (long long)(it * 4) * p.block_n + ch),
-                   make_float4(tp[0], tp[1], tp[2], tp[3]));
+            for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
+              __stcg(reinterpret_cast<float4*>(pmine + (long long)(it * 4) * p.block_n + ch),
+                     make_float4(tp[0], tp[1], tp[2], tp[3]));
+            }
+            __syncwarp();
           }
+          tc_fence_before();
           __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator stage is free again
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 128) {
-          // publish, then wait until every K slice of this tile is in L2.  All items of a split
-          // layer are co-resident (items <= #SMs, one per CTA), so this cannot deadlock; the
-          // bound turns a protocol bug into a launch error instead of a hang.
-          atomicAdd(&p.counters[tile], 1);
-          uint32_t spins = 0;
-          while (*reinterpret_cast<volatile int*>(&p.counters[tile]) < ksplit) {
-            __nanosleep(64);
-            if (++spins > (1u << 22)) { printf("loco: split-K wait timeout tile %d\n", tile); __trap(); }
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator stage is free again
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 128) {
+            // publish, then wait until every K slice of this tile is in L2.  All items of a split
+            // layer are co-resident (items <= #SMs, one per CTA), so this cannot deadlock; the
+            // bound turns a protocol bug into a launch error instead of a hang.
+            atomicAdd(&p.counters[unit], 1);
+            uint32_t spins = 0;
+            while (*reinterpret_cast<volatile int*>(&p.counters[unit]) < ksplit) {
+              __nanosleep(64);
+              if (++spins > (1u << 22)) { printf("loco: split-K wait timeout unit %d\n", unit); __trap(); }
+            }
           }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          __threadfence();
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        __threadfence();
-      }
-      if (finalize) {
         for (int ch = 0; ch < p.block_n; ch += 32) {
           // split-K: the (column chunk, lane quarter) units of the tile are dealt round-robin to
           // the ksplit CTAs, so the final reduction + epilogue is spread over all of them
@@ -324,10 +355,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         // last CTA out resets the counters for the next launch
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 128) {
-          const int old = atomicAdd(&p.counters[p.counter_stride + tile], 1);
+          const int old = atomicAdd(&p.counters[p.counter_stride + unit], 1);
           if (old == ksplit - 1) {
-            p.counters[tile] = 0;
-            p.counters[p.counter_stride + tile] = 0;
+            p.counters[unit] = 0;
+            p.counters[p.counter_stride + unit] = 0;
           }
         }
       }
@@ -538,6 +569,12 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
       if (ks < 1) ks = 1;
       while (ks > 1 && (long long)tiles * ks * kConvBlockM * p.block_n > prob.splitk_partial_floats) --ks;
     }
+    // two pixel tiles per item (shared weight tile) when that still fills >= 2 waves of the GPU
+    p.nt = (ks == 1 && (p.tiles_x * p.tiles_y * p.tiles_n) % 2 == 0 && tiles >= 4 * sms) ? 2 : 1;
+    {
+      const char* e = getenv("LOCO_CONV_NT");
+      if (e && atoi(e) == 1) p.nt = 1;
+    }
     p.ksplit = ks;
     {
       const char* e = getenv("LOCO_CONV_DEBUG");
@@ -546,7 +583,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     p.partial = prob.splitk_partial;
     p.counters = prob.splitk_counters;
     p.counter_stride = prob.splitk_max_tiles;
-    const int items = tiles * ks;
+    const int items = tiles * ks / p.nt;
     L->grid[i] = items < sms ? items : sms;
     L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
   }
@@ -556,8 +593,10 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
 int conv_init() {
   static bool attr_set = false;
   if (!attr_set) {
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
     attr_set = true;
   }
   return 0;
@@ -568,7 +607,10 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {
-      conv_gemm_tf32_kernel<<<L.grid[i], kThreads, kSmemBytes, stream>>>(L.p[i]);
+      if (L.p[i].nt == 2)
+        conv_gemm_tf32_kernel<2><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
+      else
+        conv_gemm_tf32_kernel<1><<<L.grid[i], kThreads, Cfg<1>::kSmemBytes, stream>>>(L.p[i]);
     }
     count_launch(L.nlaunch);
   }

@@ -77,6 +77,51 @@ class EditPipeline(object):
                     xt=xt)
 
     @torch.no_grad()
+    def edit_batch_device(self, x0s, masks, pc=0, gen=None):
+        """Batch editing (BASELINE config 2: many image/mask pairs per GPU).  x0s [B,3,R,R], masks
+        bool [B,3,R,R] on the device.  The DDIM inversion, the forward pass to t and the final
+        denoising of all 5*B edited latents run as single batched U-Net programs; the two local
+        bases are per image (their tangents belong to one primal point).  Returns [B,5,3,R,R]."""
+        drv = self.driver
+        sched = drv.scheduler
+        B = x0s.shape[0]
+        sched.set_timesteps(drv.inv_steps, device=self.device, is_inversion=True)
+        xt = x0s.contiguous()
+        n = len(sched._ts_host)
+        for i in range(n - 1):
+            t = sched._ts_host[i]
+            xt = sched.step(self.unet(xt, t), t, xt, eta=0, t_idx=i).prev_sample
+        xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
+        t_host = sched._ts_host[t_idx]
+        kw = dict(min_iter=10 ** 9, max_iter=self.n_iter, convergence_threshold=1e-4, verbose=False,
+                  align_sign=True)
+        batches, vTs = [], []
+        for b in range(B):
+            xb = xt[b:b + 1].contiguous()
+            _, _, vT_mod = local_basis(self.unet, sched, xb, t_host, self.k, mask=masks[b],
+                                       v0=self._v0(self.k, gen), **kw)
+            _, _, vT_null = local_basis(self.unet, sched, xb, t_host, self.k_null, mask=~masks[b],
+                                        v0=self._v0(self.k_null, gen), **kw)
+            vT = ops.nullspace_project(vT_mod, vT_null, project=True)
+            vTs.append(vT)
+            batches.append(drv.build_edit_batch(xb, vT[pc], self.vis_num))
+        per = batches[0].shape[0]
+        allx = torch.cat(batches, 0).contiguous()
+        drv.noise_fn = (lambda i, x: torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=gen)) \
+            if gen is not None else None
+        imgs = drv.DDIMforwardsteps(allx, t_start_idx=drv.edit_t_idx, t_end_idx=-1, save_image=False,
+                                    performance_boosting=True)
+        return dict(images=imgs.reshape(B, per, *imgs.shape[1:]), vT=torch.stack(vTs, 0), xt=xt)
+
+    @torch.no_grad()
+    def edit_batch(self, x0s_host, masks_host, pc=0, gen=None):
+        """Host (pinned) tensors in, edited images [B,5,3,R,R] back on the host."""
+        x0s = x0s_host.to(self.device, non_blocking=True)
+        masks = masks_host.to(self.device, non_blocking=True)
+        out = self.edit_batch_device(x0s, masks, pc=pc, gen=gen)
+        return out["images"].to("cpu", non_blocking=False)
+
+    @torch.no_grad()
     def edit(self, x0_host, mask_host, pc=0, gen=None, **kw):
         """Host tensors in (pinned for async copies), edited images [2*vis_num-1,3,R,R] back on the host."""
         x0 = x0_host.to(self.device, non_blocking=True)
