@@ -326,7 +326,9 @@ class EditUncondDiffusion(object):
             pca_rank=50, chunk_size=25, min_iter=10, max_iter=100, convergence_threshold=1e-3,
             mask=None, noise=False, v0=None):
         """src/modules/edit.py:2406-2504; `op`/`block_idx` are accepted and ignored like there."""
-        return local_basis(self.unet, self.scheduler, x, t, pca_rank, v0=v0 if v0 is not None else self.v0,
+        if v0 is None and self.v0 is not None:      # injected initial basis (dict keyed by rank, or tensor)
+            v0 = self.v0.get(pca_rank) if isinstance(self.v0, dict) else self.v0
+        return local_basis(self.unet, self.scheduler, x, t, pca_rank, v0=v0,
                            min_iter=min_iter, max_iter=max_iter, convergence_threshold=convergence_threshold,
                            mask=mask, noise=noise, align_sign=self.align_sign, verbose=self.verbose,
                            chunk_size=chunk_size)
