@@ -100,6 +100,16 @@ int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, cons
                         int noise, const float* V, int k, long long d, float* u_full, float* w_out,
                         void* scratch, void* stream);
 
+/* One iteration of BOTH local bases of run_edit_null_space_projection (src/modules/edit.py:2294 and
+ * :2307) in a single fused pass: rows [0,k1) of V are probes of the masked Jacobian (edit basis),
+ * rows [k1,k1+k2) probes of the complement-mask Jacobian (null basis).  They share x_t, t and the
+ * primal activations, so one (1, k1+k2, k1+k2) plan serves both; each group is orthonormalised on
+ * its own.  Results equal two loco_pullback_iteration calls. */
+int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float at,
+                                 const unsigned char* mask, int noise, const float* V, int k1, int k2,
+                                 long long d, int align_sign, float* u_full, float* w_out, float* V_out,
+                                 float* s_out, void* scratch, void* stream);
+
 /* ---------------- bandwidth-bound pieces ---------------- */
 /* P = (x - eps*sqrt(1-at))/sqrt(at): get_x0 without the mask (src/modules/edit.py:2386) */
 int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream);

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "loco_pullback_scratch_bytes": (_LL, [_I, _LL]),
     "loco_pullback_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),
     "loco_pullback_probe": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _P, _P, _P, _P]),
+    "loco_pullback_pair_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),
     "loco_pmp_forward": (_I, [_P, _P, _F, _LL, _P, _P]),
     "loco_orthonormalise_scratch_bytes": (_LL, [_I]),
     "loco_orthonormalise": (_I, [_P, _I, _LL, _P, _P, _P, _P, _P]),

@@ -159,9 +159,38 @@ long long loco_pullback_scratch_bytes(int k, long long d) {
   return (long long)(2 * k1d + 4 * kd + align_up((size_t)loco_orthonormalise_scratch_bytes(k), 256));
 }
 
+static int pullback_probe_impl(loco_plan_t* p, const float* xt, float t, float at,
+                               const unsigned char* mask, int noise, const float* V, int k, int k_invert,
+                               long long d, float* u_full, float* w_out, void* scratch, void* stream);
+
 int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, const unsigned char* mask,
                         int noise, const float* V, int k, long long d, float* u_full, float* w_out,
                         void* scratch, void* stream) {
+  return pullback_probe_impl(p, xt, t, at, mask, noise, V, k, k, d, u_full, w_out, scratch, stream);
+}
+
+int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float at,
+                                 const unsigned char* mask, int noise, const float* V, int k1, int k2,
+                                 long long d, int align_sign, float* u_full, float* w_out, float* V_out,
+                                 float* s_out, void* scratch, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(V_out && s_out && scratch && w_out && mask, "loco_pullback_pair_iteration: null argument");
+  const int k = k1 + k2;
+  LOCO_TRY(pullback_probe_impl(p, xt, t, at, mask, noise, V, k, k1, d, u_full, w_out, scratch, stream));
+  const size_t kd = align_up((size_t)k * d * 4, 256);
+  const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);
+  double* oscr = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 2 * k1d + 4 * kd);
+  // the two bases are orthonormalised independently (rows [0,k1) and [k1,k1+k2))
+  LOCO_TRY(orthonormalise(w_out, k1, d, align_sign ? V : nullptr, V_out, s_out, oscr, ST(stream)));
+  LOCO_TRY(orthonormalise(w_out + (size_t)k1 * d, k2, d, align_sign ? V + (size_t)k1 * d : nullptr,
+                          V_out + (size_t)k1 * d, s_out + k1, oscr, ST(stream)));
+  return 0;
+  GUARD_END
+}
+
+static int pullback_probe_impl(loco_plan_t* p, const float* xt, float t, float at,
+                               const unsigned char* mask, int noise, const float* V, int k, int k_invert,
+                               long long d, float* u_full, float* w_out, void* scratch, void* stream) {
   GUARD_BEGIN
   LOCO_REQUIRE(p && xt && V && u_full && w_out && scratch, "loco_pullback_probe: null argument");
   Plan& P = *p->p;
@@ -182,7 +211,7 @@ int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, cons
   LOCO_CHECK_CUDA(cudaMemcpyAsync(xin, xt, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(xin + d, V, sizeof(float) * k * d, cudaMemcpyDeviceToDevice, s));
   LOCO_TRY(P.forward(xin, t, eps, s));
-  LOCO_TRY(pmp_jvp_epilogue(V, eps + d, mask, at, noise, k, d, u_full, g_eps, gx_direct, s));
+  LOCO_TRY(pmp_jvp_epilogue(V, eps + d, mask, at, noise, k, k_invert, d, u_full, g_eps, gx_direct, s));
   LOCO_TRY(P.vjp(g_eps, gx_unet, s));
   LOCO_TRY(axpy(gx_direct, gx_unet, 1.0f, (long long)k * d, w_out, s));
   return 0;

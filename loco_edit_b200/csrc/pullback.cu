@@ -18,15 +18,16 @@ inline int grid_for(long long total, int block, int cap = 148 * 8) {
 // ------------------------------------------------------------------------------------------------
 __global__ void pmp_jvp_kernel(const float* __restrict__ v, const float* __restrict__ ed,
                                const unsigned char* __restrict__ mask, float at, int noise, int k,
-                               long long d, float* __restrict__ u, float* __restrict__ g_eps,
-                               float* __restrict__ gx) {
+                               int k_invert, long long d, float* __restrict__ u,
+                               float* __restrict__ g_eps, float* __restrict__ gx) {
   const float s1 = __fsqrt_rn(__fsub_rn(1.0f, at));
   const float sa = __fsqrt_rn(at);
   const long long total = (long long)k * d;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long j = i % d;
-    const bool m = mask ? (mask[j] != 0) : true;
+    // rows >= k_invert use the complement mask (edit basis and null basis probed in one batch)
+    const bool m = mask ? ((mask[j] != 0) != (i / d >= k_invert)) : true;
     float uu, ge, gd;
     if (noise) {
       uu = m ? ed[i] : 0.f;
@@ -377,10 +378,10 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, int rows, lon
 }  // namespace
 
 int pmp_jvp_epilogue(const float* v, const float* eps_dot, const unsigned char* mask, float at,
-                     int noise, int k, long long d, float* u, float* g_eps, float* gx_direct,
-                     cudaStream_t s) {
-  pmp_jvp_kernel<<<grid_for((long long)k * d, 256), 256, 0, s>>>(v, eps_dot, mask, at, noise, k, d, u,
-                                                                g_eps, gx_direct);
+                     int noise, int k, int k_invert, long long d, float* u, float* g_eps,
+                     float* gx_direct, cudaStream_t s) {
+  pmp_jvp_kernel<<<grid_for((long long)k * d, 256), 256, 0, s>>>(v, eps_dot, mask, at, noise, k,
+                                                                k_invert, d, u, g_eps, gx_direct);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

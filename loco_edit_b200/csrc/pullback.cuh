@@ -11,9 +11,10 @@ namespace loco {
 //   noise == 0:  u = mask * (v - eps_dot*sqrt(1-at)) / sqrt(at)
 //   noise != 0:  u = mask * eps_dot
 // Also emits the seeds of the transposed pass: g_eps = d<u, out>/d eps, gx_direct = d<u, out>/d x.
+// Rows >= k_invert use the complement of the mask (pass k_invert = k for a single mask).
 int pmp_jvp_epilogue(const float* v, const float* eps_dot, const unsigned char* mask, float at,
-                     int noise, int k, long long d, float* u, float* g_eps, float* gx_direct,
-                     cudaStream_t s);
+                     int noise, int k, int k_invert, long long d, float* u, float* g_eps,
+                     float* gx_direct, cudaStream_t s);
 // PMP value for primal rows: P = (x - eps*sqrt(1-at))/sqrt(at)   (bit-compatible op order)
 int pmp_forward(const float* x, const float* eps, float at, long long n, float* out, cudaStream_t s);
 

@@ -39,8 +39,15 @@ def local_basis(unet, scheduler, x, t, pca_rank, v0=None, min_iter=10, max_iter=
 
     Restates `local_encoder_decoder_pullback_xt` (src/modules/edit.py:2406-2504): returns
     (u [l_o,k] = J V^T of the last iterate, s [k] = sqrt(svdvals(U^T J)), vT [k,d]).
-    `chunk_size` is accepted for signature compatibility; all k tangents run in one fused pass."""
+    Up to `chunk_size` tangents (default 25, the reference's value) run in one fused pass; larger
+    ranks are probed chunk by chunk exactly like the reference's `v.chunk(num_chunk)` (:2419, :2448)
+    -- the 1+k rows of activations of a k = 64 plan would not fit 180 GB -- and orthonormalised
+    together."""
     k = int(pca_rank)
+    chunk_size = 25 if chunk_size is None else int(chunk_size)
+    if k > chunk_size:
+        return _local_basis_chunked(unet, scheduler, x, t, k, v0, min_iter, max_iter,
+                                    convergence_threshold, mask, noise, align_sign, verbose, chunk_size)
     ws = _pb_workspace(unet, k)
     d = ws.d
     dev = unet.device
@@ -80,6 +87,76 @@ def local_basis(unet, scheduler, x, t, pca_rank, v0=None, min_iter=10, max_iter=
         idx = ops.mask_indices(mask_u8)
         u = ops.gather_rows(ws.u_full, idx)
     return u.T, s, vT
+
+
+def _local_basis_chunked(unet, scheduler, x, t, k, v0, min_iter, max_iter, convergence_threshold, mask,
+                         noise, align_sign, verbose, chunk_size):
+    """Rank k > chunk_size: probe in chunks (torch.chunk sizes, src/modules/edit.py:2419, 2448)."""
+    dev = unet.device
+    R = unet.arch["resolution"]
+    d = 3 * R * R
+    x = x.to(device=dev, dtype=torch.float32).contiguous().reshape(1, -1)
+    t_host = float(t)
+    at = scheduler.alpha_at(t_host)
+    mask_u8 = None if mask is None else mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
+    if v0 is None:
+        q, _ = torch.linalg.qr(torch.randn(d, k, device=dev, dtype=torch.float))
+        v0 = q.T
+    V = v0.reshape(k, d).contiguous().clone()
+    num_chunk = k // chunk_size if k % chunk_size == 0 else k // chunk_size + 1
+    sizes = [c.shape[0] for c in torch.empty(k, 1).chunk(num_chunk)]
+    W = torch.empty(k, d, dtype=torch.float32, device=dev)
+    U = torch.empty(k, d, dtype=torch.float32, device=dev)
+    s = None
+    for i in range(max_iter):
+        lo = 0
+        for kc in sizes:
+            ws = _pb_workspace(unet, kc)
+            u_c, w_c = ws.probe(x, t_host, at, mask_u8, noise, V[lo:lo + kc].contiguous())
+            U[lo:lo + kc].copy_(u_c)
+            W[lo:lo + kc].copy_(w_c)
+            lo += kc
+        V_new, s = ops.orthonormalise(W, v_prev=V if align_sign else None)
+        need_check = i > min_iter
+        if verbose or need_check:
+            convergence = torch.dist(V, V_new).item()
+            if verbose:
+                print(f'power method : {i}-th step convergence : ', convergence)
+        done = need_check and torch.allclose(V, V_new, atol=convergence_threshold)
+        V = V_new
+        if done:
+            break
+    u = U if mask_u8 is None else ops.gather_rows(U, ops.mask_indices(mask_u8))
+    return u.T, s, V
+
+
+def local_basis_pair(unet, scheduler, x, t, k, k_null, mask, v0=None, v0_null=None, n_iter=12,
+                     noise=False, align_sign=True):
+    """Edit basis (mask) and null basis (~mask) of run_edit_null_space_projection
+    (src/modules/edit.py:2294-2310) computed together: both probe the Jacobian at the same x_t, so
+    their k + k_null tangents share one fused JVP pass, one VJP pass and one set of primal
+    activations per iteration.  Fixed iteration count (the reference's loop with min_iter >=
+    max_iter).  Returns (vT_modify [k,d], s_modify, vT_null [k_null,d], s_null)."""
+    kt = k + k_null
+    ws = _pb_workspace(unet, kt)
+    d = ws.d
+    dev = unet.device
+    x = x.to(device=dev, dtype=torch.float32).contiguous().reshape(1, -1)
+    t_host = float(t)
+    at = scheduler.alpha_at(t_host)
+    mask_u8 = mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
+    cur, nxt = ws.V
+    for v, lo, kk in ((v0, 0, k), (v0_null, k, k_null)):
+        if v is None:
+            q, _ = torch.linalg.qr(torch.randn(d, kk, device=dev, dtype=torch.float))
+            v = q.T
+        cur[lo:lo + kk].copy_(v.reshape(kk, d))
+    for _ in range(n_iter):
+        ws.iterate_pair(x, t_host, at, mask_u8, noise, cur, nxt, k, k_null, align_sign=align_sign)
+        cur, nxt = nxt, cur
+    ws.V = [cur, nxt]
+    s = ws.s.clone()
+    return cur[:k].clone(), s[:k], cur[k:].clone(), s[k:]
 
 
 class SyntheticDataset(object):

@@ -140,6 +140,14 @@ class PullbackWorkspace:
             "loco_pullback_iteration")
 
 
+    def iterate_pair(self, xt, t, at, mask_u8, noise, V_in, V_out, k1, k2, align_sign=False):
+        """Edit basis (rows [0,k1), mask) and null basis (rows [k1,k1+k2), ~mask) in one fused pass."""
+        assert k1 + k2 == self.k and mask_u8 is not None
+        check(self.lib.loco_pullback_pair_iteration(
+            self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8), 1 if noise else 0, ptr(V_in),
+            k1, k2, self.d, 1 if align_sign else 0, ptr(self.u_full), ptr(self.w), ptr(V_out),
+            ptr(self.s), _aligned(self.scratch), stream_ptr()), "loco_pullback_pair_iteration")
+
     def probe(self, xt, t, at, mask_u8, noise, V_in):
         """Rows of U (masked J V^T) and W (J^T U) for the k rows of V_in, no orthonormalisation."""
         check(self.lib.loco_pullback_probe(

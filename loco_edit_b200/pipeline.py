@@ -16,7 +16,7 @@ import types
 import torch
 
 from . import ops
-from .edit import EditUncondDiffusion, local_basis
+from .edit import EditUncondDiffusion, local_basis, local_basis_pair
 
 
 class EditPipeline(object):
@@ -57,12 +57,10 @@ class EditPipeline(object):
             xt = sched.step(self.unet(xt, t), t, xt, eta=0, t_idx=i).prev_sample
         xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
         t_host = sched._ts_host[t_idx]
-        kw = dict(min_iter=10 ** 9, max_iter=self.n_iter, convergence_threshold=1e-4, verbose=False,
-                  align_sign=True)
-        _, s_mod, vT_mod = local_basis(self.unet, sched, xt, t_host, self.k, mask=mask,
-                                       v0=v0_mod if v0_mod is not None else self._v0(self.k, gen), **kw)
-        _, s_null, vT_null = local_basis(self.unet, sched, xt, t_host, self.k_null, mask=~mask,
-                                         v0=v0_null if v0_null is not None else self._v0(self.k_null, gen), **kw)
+        vT_mod, s_mod, vT_null, s_null = local_basis_pair(
+            self.unet, sched, xt, t_host, self.k, self.k_null, mask,
+            v0=v0_mod if v0_mod is not None else self._v0(self.k, gen),
+            v0_null=v0_null if v0_null is not None else self._v0(self.k_null, gen), n_iter=self.n_iter)
         vT = ops.nullspace_project(vT_mod, vT_null, project=True)
         batch = drv.build_edit_batch(xt, vT[pc], self.vis_num)
         if noises is not None:
@@ -93,15 +91,12 @@ class EditPipeline(object):
             xt = sched.step(self.unet(xt, t), t, xt, eta=0, t_idx=i).prev_sample
         xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
         t_host = sched._ts_host[t_idx]
-        kw = dict(min_iter=10 ** 9, max_iter=self.n_iter, convergence_threshold=1e-4, verbose=False,
-                  align_sign=True)
         batches, vTs = [], []
         for b in range(B):
             xb = xt[b:b + 1].contiguous()
-            _, _, vT_mod = local_basis(self.unet, sched, xb, t_host, self.k, mask=masks[b],
-                                       v0=self._v0(self.k, gen), **kw)
-            _, _, vT_null = local_basis(self.unet, sched, xb, t_host, self.k_null, mask=~masks[b],
-                                        v0=self._v0(self.k_null, gen), **kw)
+            vT_mod, _, vT_null, _ = local_basis_pair(
+                self.unet, sched, xb, t_host, self.k, self.k_null, masks[b], v0=self._v0(self.k, gen),
+                v0_null=self._v0(self.k_null, gen), n_iter=self.n_iter)
             vT = ops.nullspace_project(vT_mod, vT_null, project=True)
             vTs.append(vT)
             batches.append(drv.build_edit_batch(xb, vT[pc], self.vis_num))
