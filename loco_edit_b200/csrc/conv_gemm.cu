@@ -336,6 +336,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
           }
+          float gs1 = 0.f, gs2 = 0.f;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (!((vmask >> it) & 1u)) continue;
@@ -344,6 +345,25 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
             }
             *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
+            gs1 += (o.x + o.y) + (o.z + o.w);
+            gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          }
+          if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
+            // fused GroupNorm statistics of what was just stored: the 4 lanes that share a channel
+            // quad (different pixels) combine, then one fp64 atomic pair per consumer
+            gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
+            gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
+            const int nrow = tn * p.TN + ((q * 32) >> (lTW + lTH));   // uniform per warp (TW*TH >= 32)
+            if (pr == 0 && nrow < p.N) {
+#pragma unroll
+              for (int tg = 0; tg < 2; ++tg) {
+                if (p.st_ptr[tg] == nullptr) continue;
+                const int g = (p.st_choff[tg] + co0 + ch + cq * 4) / p.st_cg[tg];
+                double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
+                atomicAdd(dst, (double)gs1);
+                atomicAdd(dst + 1, (double)gs2);
+              }
+            }
           }
         }
       }
@@ -459,6 +479,10 @@ int fill_common(ConvGemmParams& p, const ConvProblem& prob, int N, int Ho, int W
   p.addend = add; p.add_sN = asN; p.add_sH = asH; p.add_sW = asW;
   p.bias = prob.bias; p.bias2 = prob.bias2; p.bias_rows = prob.bias_rows;
   p.accumulate = prob.accumulate; p.round_out = prob.round_out;
+  for (int i = 0; i < 2; ++i) {
+    p.st_ptr[i] = prob.st_ptr[i]; p.st_cg[i] = prob.st_cg[i]; p.st_choff[i] = prob.st_choff[i];
+    if (p.st_ptr[i]) LOCO_REQUIRE(p.TW * p.TH >= 32 && p.st_cg[i] % 4 == 0, "conv: fused statistics need >= 32-pixel image tiles");
+  }
   LOCO_REQUIRE((osW % 4) == 0 && (osH % 4) == 0 && (osN % 4) == 0 && (((uintptr_t)out) & 15) == 0,
                "conv: output view not float4-aligned");
   if (add)

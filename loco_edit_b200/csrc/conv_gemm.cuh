@@ -39,6 +39,11 @@ struct ConvGemmParams {
   float* partial;             // split-K partial tiles [tile][split][128][block_n]
   int* counters;              // split-K arrival [tile] and done [counter_stride + tile] counters
   int counter_stride;
+  // optional fused GroupNorm statistics of the stored output (forward-only programs): per batch
+  // row and group (sum, sum of squares) accumulated with fp64 atomics into up to two consumers
+  double* st_ptr[2];
+  int st_cg[2];               // channels per group of the consumer GroupNorm
+  int st_choff[2];            // channel offset of this output inside the consumer's tensor
   int accumulate;             // out += result (VJP fan-in)
   int round_out;              // round stored values to tf32
 };
@@ -64,6 +69,9 @@ struct ConvProblem {
   const View* addend = nullptr;
   int accumulate = 0;
   int round_out = 0;
+  double* st_ptr[2] = {nullptr, nullptr};
+  int st_cg[2] = {0, 0};
+  int st_choff[2] = {0, 0};
   // optional split-K scratch shared by all launches of a stream (partials + zeroed counters)
   float* splitk_partial = nullptr;
   long long splitk_partial_floats = 0;

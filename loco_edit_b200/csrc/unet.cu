@@ -289,10 +289,18 @@ int Model::check_loaded() const {
 // ------------------------------------------------------------------------------------------------
 typedef std::function<int(cudaStream_t)> Fn;
 
+struct StatTarget {         // where a producer may accumulate GroupNorm statistics of its output
+  double* st = nullptr;     // [rows][32][2] doubles of the consumer GroupNorm
+  int cg = 0;               // consumer's channels per group
+  int choff = 0;            // channel offset of the producer's tensor inside the consumer's input
+};
 struct TH {                 // a forward tensor and the cotangent buffer that mirrors it
   View v;                   // [NP+NT, H, W, C]
   View g;                   // [NC, H, W, C]
   std::vector<int> ids;     // cotangent region ids (two for a full concat buffer)
+  StatTarget st_self;       // GroupNorm over this tensor's own channels
+  StatTarget st_cb;         // GroupNorm over the decoder concat buffer this tensor is a slice of
+  int partner = -1;         // id of the other slice of that concat buffer
 };
 
 struct Plan::Impl {
@@ -350,7 +358,8 @@ int Plan::build(float* workspace) {
 
   // ---- bump allocators over three regions: activations | forward stats | backward stats ----
   size_t act_off = 0, fs_off = 0, bs_off = 0;
-  uintptr_t act_base = (uintptr_t)workspace;
+  // the size query uses a fake non-null base so that "pointer == nullptr" keeps meaning "absent"
+  uintptr_t act_base = dry ? (uintptr_t)4096 : (uintptr_t)workspace;
   uintptr_t fs_base = act_base + I.act_floats * 4;
   uintptr_t bs_base = fs_base + I.fstat_floats * 4;
   auto alloc_act = [&](size_t n) -> float* {
@@ -373,8 +382,14 @@ int Plan::build(float* workspace) {
     if (NC == 0) return make_view(nullptr, 0, H, W, C);
     return make_view(alloc_act((size_t)NC * H * W * C), NC, H, W, C);
   };
+  // GroupNorm statistics are fused into the producing conv epilogue in forward-only programs
+  // (tangent rows need sum(x0*dx), which a tile of one batch row cannot form)
+  const bool fuse_stats = (NT == 0);
+  std::vector<char> fused_self, fused_cb;
+  auto new_id = [&]() { fused_self.push_back(0); fused_cb.push_back(0); return I.n_ids++; };
   auto new_tensor = [&](int H, int W, int C) {
-    TH t; t.v = Tf(H, W, C); t.g = Tg(H, W, C); t.ids = {I.n_ids++};
+    TH t; t.v = Tf(H, W, C); t.g = Tg(H, W, C); t.ids = {new_id()};
+    t.st_self.st = alloc_fstat(NB); t.st_self.cg = C / 32; t.st_self.choff = 0;
     return t;
   };
   auto row0 = [](const View& v) { return slice_n(v, 0, 1); };
@@ -419,12 +434,27 @@ int Plan::build(float* workspace) {
     return L_;
   };
   auto conv_fwd = [&](int kind, View in, View out, const ConvRef& c, const float* bias2,
-                      const View* addend) {
+                      const View* addend, const TH* out_th = nullptr, StatTarget extra = StatTarget()) {
     ConvProblem p;
     p.kind = kind; p.in = in; p.out = out; p.wpack = dry ? nullptr : M.w(c.wf);
     p.Kc = c.cin; p.Ngemm = c.cout;
     p.bias = dry ? nullptr : M.w(c.bias); p.bias2 = bias2; p.bias_rows = NP;
     p.addend = addend; p.accumulate = 0; p.round_out = 1;
+    if (fuse_stats) {
+      int nt = 0;
+      auto add_target = [&](const StatTarget& t) {
+        p.st_ptr[nt] = t.st; p.st_cg[nt] = t.cg; p.st_choff[nt] = t.choff; ++nt;
+      };
+      if (extra.st) add_target(extra);
+      if (out_th) {
+        const int id = out_th->ids[0];
+        if (out_th->st_self.st) { add_target(out_th->st_self); fused_self[id] = 1; }
+        // a concat buffer's statistics are fused only if both of its slices are produced by convs
+        if (out_th->st_cb.st && (out_th->partner < 0 || fused_cb[out_th->partner])) {
+          add_target(out_th->st_cb); fused_cb[id] = 1;
+        }
+      }
+    }
     ConvLaunch* l = mk_conv(p, false);
     I.fwd.push_back([l](cudaStream_t s) { return conv_run(*l, s); });
   };
@@ -440,16 +470,22 @@ int Plan::build(float* workspace) {
     push_b([l](cudaStream_t s) { return conv_run(*l, s); });
   };
   const float eps = A.gn_eps;
-  auto gn_fwd = [&](View x, const NormRef& n, int silu, int round_out, View y) -> double* {
-    double* st = alloc_fstat(NB);
+  auto gn_fwd = [&](View x, const NormRef& n, int silu, int round_out, View y, double* st = nullptr,
+                    bool fused = false) -> double* {
+    if (!st) st = alloc_fstat(NB);
     const float* ga = dry ? nullptr : M.w(n.gamma);
     const float* be = dry ? nullptr : M.w(n.beta);
     const int np = NP;
     I.fwd.push_back([=](cudaStream_t s) {
-      LOCO_TRY(gn_stats_fwd(x, np, st, s));
+      if (!fused) LOCO_TRY(gn_stats_fwd(x, np, st, s));   // else: accumulated by the producer's epilogue
       return gn_apply_fwd(x, np, st, ga, be, eps, silu, round_out, y, s);
     });
     return st;
+  };
+  auto th_fused = [&](const TH& t) -> bool {
+    if (!fuse_stats) return false;
+    if (t.ids.size() == 2) return fused_cb[t.ids[0]] && fused_cb[t.ids[1]];
+    return fused_self[t.ids[0]] != 0;
   };
   auto gn_bwd = [&](View xp, const double* pstats, View gy, const NormRef& n, int silu,
                     const View* addend, int accumulate, int round_out, View gx) {
@@ -497,18 +533,19 @@ int Plan::build(float* workspace) {
   auto resblock = [&](const ResRef& R, const TH& x, const TH& out) {
     const int H = x.v.H, W = x.v.W;
     View a1 = Tf(H, W, R.cin);
-    double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1);
+    double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1, x.st_self.st, th_fused(x));
     View h1 = Tf(H, W, R.cout);
-    conv_fwd(CONV_3x3, a1, h1, R.c1, tproj + R.temb_off, nullptr);
+    StatTarget t2; t2.st = alloc_fstat(NB); t2.cg = R.cout / 32; t2.choff = 0;
+    conv_fwd(CONV_3x3, a1, h1, R.c1, tproj + R.temb_off, nullptr, nullptr, t2);
     View a2 = Tf(H, W, R.cout);
-    double* st2 = gn_fwd(h1, R.n2, 1, 1, a2);
+    double* st2 = gn_fwd(h1, R.n2, 1, 1, a2, t2.st, fuse_stats);
     View sc;
     if (R.has_nin) {
       sc = Tf(H, W, R.cout);
       conv_fwd(CONV_1x1, x.v, sc, R.nin, nullptr, nullptr);
-      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &sc);
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &sc, &out);
     } else {
-      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &x.v);
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &x.v, &out);
     }
     if (NC > 0) {
       begin_group();
@@ -529,14 +566,14 @@ int Plan::build(float* workspace) {
   auto attnblock = [&](const AttnRef& R, const TH& x, const TH& out) {
     const int H = x.v.H, W = x.v.W, C = R.C, T = H * W;
     View hn = Tf(H, W, C);
-    double* st = gn_fwd(x.v, R.n, 0, 1, hn);
+    double* st = gn_fwd(x.v, R.n, 0, 1, hn, x.st_self.st, th_fused(x));
     View qkv = Tf(H, W, 3 * C);
     conv_fwd(CONV_1x1, hn, qkv, R.qkv, nullptr, nullptr);
     float* S = alloc_act((size_t)NB * T * T);
     View o = Tf(H, W, C);
     const int np = NP;
     I.fwd.push_back([=](cudaStream_t s) { return attention_forward(qkv, np, S, o, s); });
-    conv_fwd(CONV_1x1, o, out.v, R.proj, nullptr, &x.v);
+    conv_fwd(CONV_1x1, o, out.v, R.proj, nullptr, &x.v, &out);
     if (NC > 0) {
       begin_group();
       View go = Tg(H, W, C);
@@ -580,10 +617,16 @@ int Plan::build(float* workspace) {
         CB& cb = cbs[u];
         cb.full.v = Tf(h.res, h.res, C0 + C1);
         cb.full.g = Tg(h.res, h.res, C0 + C1);
-        const int id_d = I.n_ids++, id_s = I.n_ids++;
+        const int id_d = new_id(), id_s = new_id();
         cb.full.ids = {id_d, id_s};
+        cb.full.st_self.st = alloc_fstat(NB); cb.full.st_self.cg = (C0 + C1) / 32; cb.full.st_self.choff = 0;
         cb.dec.v = slice_c(cb.full.v, 0, C0); cb.dec.g = slice_c(cb.full.g, 0, C0); cb.dec.ids = {id_d};
         cb.skip.v = slice_c(cb.full.v, C0, C1); cb.skip.g = slice_c(cb.full.g, C0, C1); cb.skip.ids = {id_s};
+        // the skip slice feeds the next encoder GroupNorm on its own and the decoder GroupNorm as a
+        // part of the concat buffer; the decoder slice only the latter
+        cb.skip.st_self.st = alloc_fstat(NB); cb.skip.st_self.cg = C1 / 32; cb.skip.st_self.choff = 0;
+        cb.skip.st_cb = cb.full.st_self; cb.skip.st_cb.choff = C0;
+        cb.dec.st_cb = cb.full.st_self; cb.dec.st_cb.choff = 0; cb.dec.partner = id_s;
         block_in = bo;
       }
     }
@@ -626,7 +669,7 @@ int Plan::build(float* workspace) {
         TH& x = hs_slot(hs_top);
         TH& out = hs_slot(hs_top + 1);
         const ConvRef& c = M.down_sample[l];
-        conv_fwd(CONV_3x3_S2, x.v, out.v, c, nullptr, nullptr);
+        conv_fwd(CONV_3x3_S2, x.v, out.v, c, nullptr, nullptr, &out);
         if (NC > 0) {
           begin_group();
           const int f = writer_flag(x.ids);
@@ -675,7 +718,7 @@ int Plan::build(float* workspace) {
           const View tv = target.v;
           I.fwd.push_back([=](cudaStream_t s) { return upsample2x(tv, hu, s); });
           TH& nxt = cbs[u + 1].dec;
-          conv_fwd(CONV_3x3, hu, nxt.v, c, nullptr, nullptr);
+          conv_fwd(CONV_3x3, hu, nxt.v, c, nullptr, nullptr, &nxt);
           if (NC > 0) {
             begin_group();
             View ghu = Tg(2 * res, 2 * res, R.cout);
@@ -693,7 +736,7 @@ int Plan::build(float* workspace) {
   {
     const int res = hfin.v.H, C = hfin.v.C;
     View a = Tf(res, res, C);
-    double* st = gn_fwd(hfin.v, M.norm_out, 1, 0, a);
+    double* st = gn_fwd(hfin.v, M.norm_out, 1, 0, a, hfin.st_self.st, th_fused(hfin));
     Impl* Ip = impl.get();
     const float* wo = dry ? nullptr : M.w(M.conv_out_w);
     const float* bo = dry ? nullptr : M.w(M.conv_out_b);
