@@ -136,7 +136,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int it = k0; it < k1; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
-          if (p.debug == 3) {
+          if (p.debug == 3 || p.debug == 6) {
             mbar_arrive(&full_bar[stage]);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -161,34 +161,43 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc_tf32(p.block_n);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem));            // stage 0, pixel tile 0
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + kBOff);    // stage 0, weight tile
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         const int split = w / total_units;
         const int nk = (int)((long long)kiters * (split + 1) / ksplit) - (int)((long long)kiters * split / ksplit);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT) * kConvMaxBlockN;
+        // The barrier wait of stage s+1 is issued before the last MMA of stage s, so its latency
+        // (and the descriptor arithmetic) overlaps with MMAs that are still executing.
+        if (nk > 0) mbar_wait(&full_bar[stage], phase);
         for (int it = 0; it < nk; ++it) {
-          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t bdesc = make_smem_desc(sa + kBOff);
           if (p.debug == 4) {
             mbar_arrive(&empty_bar[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (it + 1 < nk) mbar_wait(&full_bar[stage], phase);
             continue;
           }
+          const uint64_t so = (uint64_t)stage * (uint64_t)(kStageBytes >> 4);   // stage offset, 16 B units
+          const uint64_t bdesc = bdesc0 + so;
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == kStages) { nstage = 0; nphase ^= 1; }
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            const uint64_t adesc = make_smem_desc(sa + j * kABytes);
+            const uint64_t adesc = adesc0 + so + (uint64_t)(j * (kABytes >> 4));
 #pragma unroll
             for (int k = 0; k < kConvBlockK / 8; ++k) {
+              if (j == NT - 1 && k == kConvBlockK / 8 - 1 && it + 1 < nk) mbar_wait(&full_bar[nstage], nphase);
               // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
               umma_tf32(d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                         idesc, (uint32_t)((it | k) != 0));
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          stage = nstage; phase = nphase;
         }
         if (p.debug == 4) mbar_arrive(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
@@ -216,7 +225,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int jt = 0; jt < (p.debug == 5 ? 0 : NT); ++jt) {
+      for (int jt = 0; jt < ((p.debug == 5 || p.debug == 6) ? 0 : NT); ++jt) {
         const int tm = um * NT + jt;
         const int tx = tm % p.tiles_x;
         const int ty = (tm / p.tiles_x) % p.tiles_y;
