@@ -405,6 +405,253 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// "Wide" variant for the large layers: operand roles swapped.  The weight tile (128 output channels
+// x 32 input channels) is the M operand, 256 pixels (two pixel tiles) are the N operand of one
+// tcgen05.mma 128x256x8.  Per 32-channel stage the tensor core then reads 4 x (4 KB + 8 KB) = 48 KB
+// of shared memory instead of 8 x (4 KB + 4 KB) = 64 KB, which is what bounds this kernel (shared
+// memory serves both the TMA fills and the MMA operand reads).  The accumulator is [cout][pixel]
+// (TMEM lane = output channel); the epilogue's shared-memory transpose turns it back into
+// channels-last 128-byte segments.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
+  constexpr int NT = 2;
+  constexpr int kStages = Cfg<2>::kStages;          // 4
+  constexpr int kStageBytes = Cfg<2>::kStageBytes;  // 48 KB: [weights 16 KB | pixels 0 | pixels 1]
+  constexpr int kTmemCols = 512;                    // 2 accumulator stages x 256 pixel columns
+  constexpr int kPOff = kBBytes;                    // pixel tiles start after the weight tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.amap[0]);
+    prefetch_tmap(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int units_m = tiles_m / NT;
+  const int total_items = units_m * p.tiles_co;
+  const int kiters = p.ntaps * p.c_chunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = NT * kABytes + kBBytes;     // block_n == 128 on this path
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int um = w % units_m;
+        const int co0 = (w / units_m) * 128;
+        int x0[NT], y0[NT], n0[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int tm = um * NT + j;
+          x0[j] = (tm % p.tiles_x) * p.TW;
+          y0[j] = ((tm / p.tiles_x) % p.tiles_y) * p.TH;
+          n0[j] = (tm / (p.tiles_x * p.tiles_y)) * p.TN;
+        }
+        int tap = 0, cc = 0;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          const CUtensorMap* am = &p.amap[p.tap_map[tap]];
+          tma_load_2d(sa, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            tma_load_4d(sa + kPOff + j * kABytes, am, &full_bar[stage], cc * kConvBlockK,
+                        x0[j] + p.tap_dx[tap], y0[j] + p.tap_dy[tap], n0[j]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++cc == p.c_chunks) { cc = 0; ++tap; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      // M = 128 (output channels), N = 256 (pixels)
+      uint32_t idesc = 0;
+      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
+      idesc |= (uint32_t)(256 >> 3) << 17;
+      idesc |= (uint32_t)(128 >> 4) << 24;
+      const uint64_t wdesc0 = make_smem_desc(smem_u32(smem));            // weights  (M operand)
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(smem) + kPOff);    // pixels   (N operand)
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        mbar_wait(&full_bar[stage], phase);
+        for (int it = 0; it < kiters; ++it) {
+          tc_fence_after();
+          const uint64_t so = (uint64_t)stage * (uint64_t)(kStageBytes >> 4);
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 8; ++k) {
+            if (k == kConvBlockK / 8 - 1 && it + 1 < kiters) mbar_wait(&full_bar[nstage], nphase);
+            umma_tf32(d_tmem, wdesc0 + so + (uint64_t)(k * 2), pdesc0 + so + (uint64_t)(k * 2), idesc,
+                      (uint32_t)((it | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          stage = nstage; phase = nphase;
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // epilogue: this warp owns output channels [32 q, 32 q + 32) of the tile (TMEM lanes) and walks
+    // the 256 pixel columns in chunks of 32
+    const int q = warp & 3;
+    float* tbuf = epi_smem + q * (32 * 33);
+    const int pr = lane >> 3;            // pixel sub-row (0..3)
+    const int cq = lane & 7;             // channel quad inside this warp's 32 channels
+    const int lTW = p.log_tw, lTH = p.log_th;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int um = w % units_m;
+      const int co = (w / units_m) * 128 + q * 32 + cq * 4;    // first of this lane's 4 channels
+      float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+      if (p.bias2) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co));
+        bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+#pragma unroll 1
+      for (int chn = 0; chn < 8; ++chn) {               // 8 chunks of 32 pixels
+        const int tm = um * NT + (chn >> 2);
+        const int tx = tm % p.tiles_x;
+        const int ty = (tm / p.tiles_x) % p.tiles_y;
+        const int tn = tm / (p.tiles_x * p.tiles_y);
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + chn * 32, r);
+        tmem_ld_wait();
+        // tbuf[channel = lane][pixel]
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+        __syncwarp();
+        float4 v[8];
+        long long ooff[8], aoff[8];
+        uint32_t vmask = 0, bmask = 0;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int pix = it * 4 + pr;                  // pixel inside the chunk
+          const float* tp = tbuf + (cq * 4) * 33 + pix;
+          v[it] = make_float4(tp[0], tp[33], tp[66], tp[99]);
+          const int R = (chn & 3) * 32 + pix;           // pixel inside its 128-pixel tile
+          const int x = tx * p.TW + (R & (p.TW - 1));
+          const int y = ty * p.TH + ((R >> lTW) & (p.TH - 1));
+          const int n = tn * p.TN + (R >> (lTW + lTH));
+          if (n < p.N && y < p.Ho && x < p.Wo) vmask |= 1u << it;
+          if (n < p.bias_rows) bmask |= 1u << it;
+          ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co;
+          aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+        if (p.addend) {
+          float4 a[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it]))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+        }
+        if (p.accumulate) {
+          float4 a[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it])
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+        }
+        float gs1 = 0.f, gs2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (!((vmask >> it) & 1u)) continue;
+          float4 o = v[it];
+          if (p.round_out) {
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+          }
+          *reinterpret_cast<float4*>(p.out + ooff[it]) = o;
+          gs1 += (o.x + o.y) + (o.z + o.w);
+          gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+        }
+        if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
+          gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
+          gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
+          const int nrow = tn * p.TN + (((chn & 3) * 32) >> (lTW + lTH));   // uniform per chunk
+          if (pr == 0 && nrow < p.N) {
+#pragma unroll
+            for (int tg = 0; tg < 2; ++tg) {
+              if (p.st_ptr[tg] == nullptr) continue;
+              const int g = (p.st_choff[tg] + co) / p.st_cg[tg];
+              double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
+              atomicAdd(dst, (double)gs1);
+              atomicAdd(dst + 1, (double)gs2);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -607,6 +854,8 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     {
       const char* e = getenv("LOCO_CONV_NT");
       if (e && atoi(e) == 1) p.nt = 1;
+      // nt == 3 selects the "wide" (operand-swapped, N = 256 pixels) kernel
+      if (p.nt == 2 && p.block_n == 128 && !(e && atoi(e) == 2)) p.nt = 3;
     }
     p.ksplit = ks;
     {
@@ -616,7 +865,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     p.partial = prob.splitk_partial;
     p.counters = prob.splitk_counters;
     p.counter_stride = prob.splitk_max_tiles;
-    const int items = tiles * ks / p.nt;
+    const int items = tiles * ks / (p.nt == 3 ? 2 : p.nt);
     L->grid[i] = items < sms ? items : sms;
     L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
   }
@@ -630,6 +879,8 @@ int conv_init() {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
     attr_set = true;
   }
   return 0;
@@ -640,7 +891,9 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {
-      if (L.p[i].nt == 2)
+      if (L.p[i].nt == 3)
+        conv_gemm_tf32_wide_kernel<<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
+      else if (L.p[i].nt == 2)
         conv_gemm_tf32_kernel<2><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
       else
         conv_gemm_tf32_kernel<1><<<L.grid[i], kThreads, Cfg<1>::kSmemBytes, stream>>>(L.p[i]);

@@ -56,6 +56,11 @@ CONV_CASES = [
     (3, 2, 8, 8, 256, 128),
     (4, 3, 16, 16, 128, 128),    # dy [3,16,16,128] -> dx [3,32,32,128]
     (4, 5, 8, 8, 256, 256),
+    # >= 4 waves of tiles: the operand-swapped "wide" kernel (two pixel tiles per 128x256x8 MMA)
+    (0, 6, 128, 128, 128, 128),
+    (3, 5, 128, 128, 128, 128),
+    (1, 6, 128, 128, 256, 128),
+    (0, 5, 128, 128, 256, 256),
 ]
 
 
@@ -75,10 +80,10 @@ def test_conv_tcgen05_exact_inputs(dev, kind, N, H, W, Cin, Cout):
     assert e < 1e-5
 
 
-def test_conv_epilogue_bias_addend_accumulate(dev):
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(4, 16, 16, 128, 256), (5, 128, 128, 128, 128)])
+def test_conv_epilogue_bias_addend_accumulate(dev, N, H, W, Cin, Cout):
     from loco_edit_b200 import ops
     g = torch.Generator().manual_seed(5)
-    N, H, W, Cin, Cout = 4, 16, 16, 128, 256
     w = tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / 34.0).to(dev)
     x = tf32_round(torch.randn(N, Cin, H, W, generator=g)).to(dev)
     bias = torch.randn(Cout, generator=g).to(dev)
