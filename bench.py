@@ -25,7 +25,9 @@ sys.path.insert(0, ROOT)
 
 F_DDPM256 = 0.4970e12          # algorithmic FLOPs of one U-Net forward, B=1, 256^2
 K_RANK, K_NULL, N_ITER = 5, 5, 12
-EDIT_FWD_EQUIV = 138 + 2 * N_ITER * (1 + 2 * K_RANK) + 59 * 5    # 697
+EDIT_FWD_EQUIV = 138 + 2 * N_ITER * (1 + 2 * K_RANK) + 59 * 5    # 697: BASELINE.md's definition of an edit
+# executed here: both bases share one primal row per iteration -> 138 + 12*(1 + 2*10) + 295 = 685
+EDIT_FWD_EXECUTED = 138 + N_ITER * (1 + 2 * (K_RANK + K_NULL)) + 59 * 5
 
 
 def peaks():
@@ -270,7 +272,10 @@ def run_ours(args):
         conv_tflops = work[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         roof = {"bound": "tensor", "kernel": "conv_gemm_tf32_kernel", "achieved": conv_tflops,
-                "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
+                # dram__bytes_read+write of the dominant launch (3x3 128->128 at 256^2, 6 rows; algorithmic
+                # 403 MB) from the committed ncu --set full capture, profiles/r1_conv_gemm_ncu_full_raw.csv
+                "traffic": 360.6e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
                 "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
@@ -334,9 +339,10 @@ def run_ours(args):
                        "images_per_step_per_gpu": BATCH,
                        "fwd_equivalents_per_edit": EDIT_FWD_EQUIV,
                        "tflop_per_edit": EDIT_FWD_EQUIV * F_DDPM256 / 1e12,
+                       "fwd_equivalents_executed": EDIT_FWD_EXECUTED,
                        "l2": "per-edit working set (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": "dp%d (independent images per rank, no collective)" % world},
-            "achieved_tflops": value * EDIT_FWD_EQUIV * F_DDPM256 / 1e12,
+            "achieved_tflops": value * EDIT_FWD_EXECUTED * F_DDPM256 / 1e12,
             "e2e": {"value": n_edits / (ms_e2e * 1e-3), "unit": "edits/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
