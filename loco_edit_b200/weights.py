@@ -92,15 +92,148 @@ def ddpm_param_shapes(arch):
     return out
 
 
+# src/models/guided_diffusion/script_util.py:166-190 (P2_DICT: FFHQ_P2 / AFHQ_P2 / Flower_P2 / ...)
+P2_256 = dict(kind="p2", ch=128, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=1,
+              attn_resolutions=(16,), head_ch=64, resolution=256, in_ch=3, out_ch=3, gn_eps=1e-5)
+
+
+def tiny_p2_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1, ch=128,
+                 head_ch=64):
+    """Reduced-depth variant of the P2 / guided-diffusion architecture for fast parity tests."""
+    return dict(kind="p2", ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
+                attn_resolutions=tuple(attn_resolutions), head_ch=head_ch, resolution=resolution,
+                in_ch=3, out_ch=3, gn_eps=1e-5)
+
+
+def p2_layout(arch):
+    """Module layout of UNetModel.__init__ (guided_diffusion/unet.py:470-618) for
+    resblock_updown = True: (input blocks, middle, output blocks), each block a list of
+    ('conv_in'|'res'|'attn'|'down'|'up', cin, cout)."""
+    ch0, mult, nrb = arch["ch"], tuple(arch["ch_mult"]), arch["num_res_blocks"]
+    attn_ds = tuple(arch["resolution"] // r for r in arch["attn_resolutions"])
+    ch = int(mult[0] * ch0)
+    inputs = [[("conv_in", 3, ch)]]
+    chans = [ch]
+    ds = 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            layers = [("res", ch, int(m * ch0))]
+            ch = int(m * ch0)
+            if ds in attn_ds:
+                layers.append(("attn", ch, ch))
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(mult) - 1:
+            inputs.append([("down", ch, ch)])
+            chans.append(ch)
+            ds *= 2
+    middle = [("res", ch, ch), ("attn", ch, ch), ("res", ch, ch)]
+    outputs = []
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            ich = chans.pop()
+            layers = [("res", ch + ich, int(ch0 * m))]
+            ch = int(ch0 * m)
+            if ds in attn_ds:
+                layers.append(("attn", ch, ch))
+            if level and i == nrb:
+                layers.append(("up", ch, ch))
+                ds //= 2
+            outputs.append(layers)
+    return inputs, middle, outputs
+
+
+def p2_param_shapes(arch):
+    """Ordered {name: shape} of the reference's guided-diffusion UNetModel.state_dict() built by
+    create_model(**P2_DICT) (script_util.py:379-435; learn_sigma => 6 output channels)."""
+    ch0 = arch["ch"]
+    temb = 4 * ch0
+    out = {}
+
+    def res(p, cin, cout):
+        out[p + ".in_layers.0.weight"] = (cin,)
+        out[p + ".in_layers.0.bias"] = (cin,)
+        out[p + ".in_layers.2.weight"] = (cout, cin, 3, 3)
+        out[p + ".in_layers.2.bias"] = (cout,)
+        out[p + ".emb_layers.1.weight"] = (2 * cout, temb)
+        out[p + ".emb_layers.1.bias"] = (2 * cout,)
+        out[p + ".out_layers.0.weight"] = (cout,)
+        out[p + ".out_layers.0.bias"] = (cout,)
+        out[p + ".out_layers.3.weight"] = (cout, cout, 3, 3)
+        out[p + ".out_layers.3.bias"] = (cout,)
+        if cin != cout:
+            out[p + ".skip_connection.weight"] = (cout, cin, 1, 1)
+            out[p + ".skip_connection.bias"] = (cout,)
+
+    def attn(p, c):
+        out[p + ".norm.weight"] = (c,)
+        out[p + ".norm.bias"] = (c,)
+        out[p + ".qkv.weight"] = (3 * c, c, 1)
+        out[p + ".qkv.bias"] = (3 * c,)
+        out[p + ".proj_out.weight"] = (c, c, 1)
+        out[p + ".proj_out.bias"] = (c,)
+
+    def block(prefix, layers):
+        for j, (kind, cin, cout) in enumerate(layers):
+            p = f"{prefix}.{j}"
+            if kind == "conv_in":
+                out[p + ".weight"] = (cout, cin, 3, 3)
+                out[p + ".bias"] = (cout,)
+            elif kind == "attn":
+                attn(p, cin)
+            else:
+                res(p, cin, cout)
+
+    out["time_embed.0.weight"] = (temb, ch0)
+    out["time_embed.0.bias"] = (temb,)
+    out["time_embed.2.weight"] = (temb, temb)
+    out["time_embed.2.bias"] = (temb,)
+    inputs, middle, outputs = p2_layout(arch)
+    for i, layers in enumerate(inputs):
+        block(f"input_blocks.{i}", layers)
+    block("middle_block", middle)
+    for i, layers in enumerate(outputs):
+        block(f"output_blocks.{i}", layers)
+    c_last = outputs[-1][0][2]
+    out["out.0.weight"] = (c_last,)
+    out["out.0.bias"] = (c_last,)
+    out["out.2.weight"] = (6, c_last, 3, 3)
+    out["out.2.bias"] = (6,)
+    return out
+
+
+def param_shapes(arch):
+    """{name: shape} of the reference state_dict for either architecture family."""
+    return p2_param_shapes(arch) if arch.get("kind") == "p2" else ddpm_param_shapes(arch)
+
+
+def _is_norm_name(arch, name):
+    if arch.get("kind") == "p2":
+        return (".in_layers.0." in name or ".out_layers.0." in name or ".norm." in name
+                or name.startswith("out.0."))
+    return ".norm" in name or name.startswith("norm_out")
+
+
+def _is_zero_init(arch, name):
+    """Tensors the reference zero-initialises (zero_module, guided_diffusion/nn.py:68-74;
+    unet.py:212-214, 296, 617).  With random weights they would make eps == 0, so the synthetic
+    factory re-randomises them with N(0, 0.02)."""
+    return arch.get("kind") == "p2" and (".out_layers.3." in name or ".proj_out." in name
+                                         or name.startswith("out.2."))
+
+
 def random_state_dict(arch, seed=1234, perturb_norm=0.0):
     """Seeded random-init weights with torch's default init distributions
     (Conv2d/Linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)); GroupNorm: weight 1, bias 0).
     Each tensor has its own generator keyed by (seed, name), so the values do not depend on
     enumeration order.  perturb_norm > 0 randomises the GroupNorm affine (tests only)."""
     sd = {}
-    for name, shape in ddpm_param_shapes(arch).items():
+    for name, shape in param_shapes(arch).items():
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
-        is_norm = ".norm" in name or name.startswith("norm_out")
+        is_norm = _is_norm_name(arch, name)
+        if _is_zero_init(arch, name):
+            sd[name] = 0.02 * torch.randn(shape, generator=g)
+            continue
         if is_norm:
             base = torch.ones(shape) if name.endswith(".weight") else torch.zeros(shape)
             if perturb_norm > 0:
@@ -127,5 +260,5 @@ _shape_cache = {}
 def ddpm_param_shapes_cache(arch):
     key = repr(sorted(arch.items()))
     if key not in _shape_cache:
-        _shape_cache[key] = ddpm_param_shapes(arch)
+        _shape_cache[key] = param_shapes(arch)
     return _shape_cache[key]

@@ -128,3 +128,49 @@ def test_driver_pipeline_matches_reference_driver(golden_dir):
         img = pullback_ref.ddim_forward(unet, sched, batch, 40, -1, boost_idx=g["boost_idx"], noises=nz)
         mse = float(((img - g["finals"][pc]) ** 2).mean())
         assert mse < 1e-8, mse      # identical arithmetic on the same CPU
+
+
+# ---- P2 / guided-diffusion U-Net family (BASELINE config 2; tests/golden/make_golden_p2.py) ----
+def test_p2_param_shapes_match_reference(golden_dir):
+    from loco_edit_b200.weights import P2_256, p2_param_shapes
+    ref = json.load(open(os.path.join(golden_dir, "p2_param_shapes.json")))
+    mine = p2_param_shapes(P2_256)
+    assert list(mine.keys()) == list(ref.keys())
+    n = 0
+    for k in ref:
+        assert list(mine[k]) == ref[k], k
+        c = 1
+        for d in ref[k]:
+            c *= d
+        n += c
+    assert n == 93563910
+
+
+def test_p2_unet_forward_matches_reference(golden_dir):
+    from oracle import p2_ref
+    g = _load(golden_dir, "p2_tiny.pt")
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    with torch.no_grad():
+        eps = p2_ref.unet_forward(sd, g["arch"], g["x"], g["t"])
+    assert torch.allclose(eps, g["eps"], atol=2e-5, rtol=1e-5), float((eps - g["eps"]).abs().max())
+
+
+@pytest.mark.parametrize("case", ["mask_k3", "notmask_k2"])
+def test_p2_local_basis_matches_reference(golden_dir, case):
+    from oracle import p2_ref
+    g = _load(golden_dir, "p2_pullback_tiny.pt")
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    unet = p2_ref.RefP2UNet(g["arch"], sd)
+    sched = pullback_ref.RefScheduler()
+    sched.set_timesteps(100)
+    mask, k = {"mask_k3": (g["mask"], 3), "notmask_k2": (~g["mask"], 2)}[case]
+    d = g["xt"].numel()
+    torch.manual_seed(g["v0_seed"])
+    v0, _ = torch.linalg.qr(torch.randn(d, k))
+    for n_iter in (1, 2):
+        u, s, vT = pullback_ref.local_basis(unet, sched, g["xt"], g["t"], v0.T, n_iter, mask=mask)
+        ref = g["cases"][case][n_iter]
+        assert torch.allclose(s, ref["s"], rtol=1e-4), (s, ref["s"])
+        assert _principal_angle_deg(vT, ref["vT"]) < 0.05
+        dots = (vT * ref["vT"]).sum(1).abs()
+        assert float((1 - dots).abs().max()) < 1e-3, dots
