@@ -26,8 +26,13 @@ extern "C" {
 typedef struct loco_unet loco_unet_t;
 typedef struct loco_plan loco_plan_t;
 
-/* Architecture of the DDPM U-Net (reference: DDPM.__init__, src/models/ddpm/diffusion.py:24-126;
- * hyper-parameters of src/configs/custom_celeba_ddpm.yml:21-30). */
+/* Architecture of the U-Net.
+ * kind 0: DDPM.__init__, src/models/ddpm/diffusion.py:24-126 (hyper-parameters of
+ *         src/configs/custom_celeba_ddpm.yml:21-30; == google/ddpm-ema-celebahq-256);
+ * kind 1: guided-diffusion UNetModel as built by create_model(**P2_DICT),
+ *         src/models/guided_diffusion/script_util.py:166-190,379-435 and unet.py:398-684
+ *         (scale-shift norm, ResBlock up/down-sampling, learn_sigma: eps = first 3 of 6 output
+ *         channels, multi-head "legacy" attention with head_ch channels per head). */
 typedef struct loco_arch {
   int ch;                  /* base channels (multiple of 128) */
   int n_levels;            /* len(ch_mult) <= 8 */
@@ -37,7 +42,9 @@ typedef struct loco_arch {
   int attn_resolutions[4];
   int resolution;          /* input H = W */
   int in_ch, out_ch;       /* 3, 3 */
-  float gn_eps;            /* 1e-6 */
+  float gn_eps;            /* 1e-6 (DDPM) / 1e-5 (guided diffusion) */
+  int kind;                /* 0 = DDPM, 1 = P2 / guided diffusion */
+  int head_ch;             /* kind 1: channels per attention head (num_head_channels); else 0 */
 } loco_arch_t;
 
 int loco_abi_version(void);
@@ -159,11 +166,13 @@ int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_pr
 int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* gy, int K,
                             const float* gamma, const float* beta, float eps, int silu, float* gx,
                             void* stats, void* stream);
-/* attention core on qkv [N,T,3C]; S scratch [N,T,T]; o [N,T,C] */
-int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, float* S, float* o,
-                       void* stream);
-int loco_attention_vjp(const float* go, int K, int T, int C, const float* qkv0, const float* P0,
-                       float* gP, float* gqkv, void* stream);
+/* attention core on qkv [N,T,3C]; S scratch [N,heads,T,T]; o [N,T,C].  head_ch = 0: one head,
+ * channels q|k|v (ddpm/diffusion.py:941-966); head_ch > 0: C/head_ch heads, per head q|k|v
+ * (QKVAttentionLegacy, guided_diffusion/unet.py:339-356). */
+int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int head_ch, float* S,
+                       float* o, void* stream);
+int loco_attention_vjp(const float* go, int K, int T, int C, int head_ch, const float* qkv0,
+                       const float* P0, float* gP, float* gqkv, void* stream);
 
 #ifdef __cplusplus
 }

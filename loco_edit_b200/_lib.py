@@ -20,6 +20,7 @@ class Arch(C.Structure):
         ("ch", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8),
         ("num_res_blocks", C.c_int), ("n_attn", C.c_int), ("attn_resolutions", C.c_int * 4),
         ("resolution", C.c_int), ("in_ch", C.c_int), ("out_ch", C.c_int), ("gn_eps", C.c_float),
+        ("kind", C.c_int), ("head_ch", C.c_int),
     ]
 
 
@@ -68,8 +69,8 @@ PROTOTYPES = {
                              C.POINTER(_I), C.POINTER(_I), _P]),
     "loco_groupnorm_silu_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_groupnorm_silu_vjp": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P]),
-    "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
-    "loco_attention_vjp": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "loco_attention_vjp": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -38,7 +38,7 @@ static int require_device() {
 
 extern "C" {
 
-int loco_abi_version(void) { return 1; }
+int loco_abi_version(void) { return 2; }
 long long loco_launch_count(void) { return launch_count(); }
 int loco_profile_enable(int on) { profile_enable(on != 0); return 0; }
 int loco_profile_collect(double* ms, double* work, long long* launches, int nfam) {
@@ -63,6 +63,10 @@ int loco_unet_create(const loco_arch_t* a, loco_unet_t** out) {
   A.num_res_blocks = a->num_res_blocks; A.n_attn = a->n_attn;
   for (int i = 0; i < 4; ++i) A.attn_resolutions[i] = a->attn_resolutions[i];
   A.resolution = a->resolution; A.in_ch = a->in_ch; A.out_ch = a->out_ch; A.gn_eps = a->gn_eps;
+  LOCO_REQUIRE(a->kind == 0 || a->kind == 1, "loco_unet_create: unknown architecture kind %d", a->kind);
+  LOCO_REQUIRE(a->kind == 0 || (a->head_ch > 0 && a->head_ch % 4 == 0),
+               "loco_unet_create: guided-diffusion U-Net needs head_ch > 0");
+  A.kind = a->kind; A.head_ch = a->kind == 1 ? a->head_ch : 0;
   *out = new loco_unet{new Model(A)};
   return 0;
   GUARD_END
@@ -402,20 +406,20 @@ int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* g
   LOCO_TRY(gn_stats_vjp(xv, ps, gyv, gamma, beta, eps, silu, bs, s));
   return gn_apply_vjp(xv, ps, gyv, bs, gamma, beta, eps, silu, nullptr, 0, 0, gxv, s);
 }
-int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, float* S, float* o,
-                       void* stream) {
+int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int head_ch, float* S,
+                       float* o, void* stream) {
   LOCO_TRY(require_device());
   View q = make_view(const_cast<float*>(qkv), N, 1, T, 3 * C);
   View ov = make_view(o, N, 1, T, C);
-  return attention_forward(q, n_primal, S, ov, ST(stream));
+  return attention_forward(q, n_primal, head_ch, S, ov, ST(stream));
 }
-int loco_attention_vjp(const float* go, int K, int T, int C, const float* qkv0, const float* P0,
-                       float* gP, float* gqkv, void* stream) {
+int loco_attention_vjp(const float* go, int K, int T, int C, int head_ch, const float* qkv0,
+                       const float* P0, float* gP, float* gqkv, void* stream) {
   LOCO_TRY(require_device());
   View g = make_view(const_cast<float*>(go), K, 1, T, C);
   View q0 = make_view(const_cast<float*>(qkv0), 1, 1, T, 3 * C);
   View gq = make_view(gqkv, K, 1, T, 3 * C);
-  return attention_vjp(g, q0, P0, gP, gq, ST(stream));
+  return attention_vjp(g, q0, head_ch, P0, gP, gq, ST(stream));
 }
 
 }  // extern "C"

@@ -12,22 +12,27 @@ int attention_init();   // one-time kernel attribute setup
 struct GemmOperand {
   const float* ptr;
   long long s0, s1, sb;   // strides of (first index, second index, batch)
+  long long sh = 0;       // stride of the attention head (second batch dimension)
 };
 int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
-                 int M, int N, int K, int batch, float alpha, float beta, int round_out,
-                 cudaStream_t s);
+                 long long sCh, int M, int N, int K, int batch, int heads, float alpha, float beta,
+                 int round_out, cudaStream_t s);
 
 // P[b][i][:] = softmax(scale * S[b][i][:]) in place.
 int softmax_rows(float* S, int T, int batch, float scale, cudaStream_t s);
 // X[b][i][:] = scale * P0[i][:] * (X[b][i][:] - sum_j P0[i][j] X[b][i][j])   (softmax JVP and VJP)
-int softmax_lin_rows(const float* P0, float* X, int T, int batch, float scale, cudaStream_t s);
+int softmax_lin_rows(const float* P0, float* X, int T, int batch, int heads, float scale,
+                     cudaStream_t s);
 
-// qkv: [N, T, 3C] (q | k | v along channels), S: [N, T, T] scratch that keeps P afterwards,
-// o: [N, T, C].  Rows < n_primal are ordinary forward passes; the remaining rows are tangents of
-// primal row 0.
-int attention_forward(View qkv, int n_primal, float* S, View o, cudaStream_t s);
-// go: [k, T, C] cotangent of o; qkv0/P0: saved primal row; gP: [k, T, T] scratch;
+// qkv: [N, T, 3C]; S: [N, heads, T, T] scratch that keeps P afterwards; o: [N, T, C].
+// head_ch == 0: one head, channels q | k | v (DDPM AttnBlock); head_ch > 0: C / head_ch heads in
+// the guided-diffusion "legacy" order (per head q | k | v of head_ch channels each,
+// guided_diffusion/unet.py:339-356).  Rows < n_primal are ordinary forward passes; the remaining
+// rows are tangents of primal row 0.
+int attention_forward(View qkv, int n_primal, int head_ch, float* S, View o, cudaStream_t s);
+// go: [k, T, C] cotangent of o; qkv0/P0: saved primal row; gP: [k, heads, T, T] scratch;
 // gqkv: [k, T, 3C] result.
-int attention_vjp(View go, View qkv0, const float* P0, float* gP, View gqkv, cudaStream_t s);
+int attention_vjp(View go, View qkv0, int head_ch, const float* P0, float* gP, View gqkv,
+                  cudaStream_t s);
 
 }  // namespace loco

@@ -400,7 +400,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
 // ------------------------------------------------------------------------------------------------
 // Resampling / add
 // ------------------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(View in, View out) {
+__global__ void upsample2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -410,12 +410,19 @@ __global__ void upsample2x_kernel(View in, View out) {
     const int x = (int)(r % out.W); r /= out.W;
     const int y = (int)(r % out.H);
     const int n = (int)(r / out.H);
-    const float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + (y >> 1) * in.sH +
-                                                      (x >> 1) * in.sW + cv * 4);
-    *reinterpret_cast<float4*>(out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4) = v;
+    float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + (y >> 1) * in.sH +
+                                                (x >> 1) * in.sW + cv * 4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    if (accumulate) {
+      const float4 p = *reinterpret_cast<const float4*>(o);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    *reinterpret_cast<float4*>(o) = v;
   }
 }
-__global__ void sumpool2x_kernel(View in, View out, int accumulate) {
+__global__ void sumpool2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -430,13 +437,14 @@ __global__ void sumpool2x_kernel(View in, View out, int accumulate) {
     const float4 c = *reinterpret_cast<const float4*>(b + in.sW);
     const float4 d = *reinterpret_cast<const float4*>(b + in.sH);
     const float4 e = *reinterpret_cast<const float4*>(b + in.sH + in.sW);
-    float4 v = make_float4((a.x + c.x) + (d.x + e.x), (a.y + c.y) + (d.y + e.y),
-                           (a.z + c.z) + (d.z + e.z), (a.w + c.w) + (d.w + e.w));
+    float4 v = make_float4(scale * ((a.x + c.x) + (d.x + e.x)), scale * ((a.y + c.y) + (d.y + e.y)),
+                           scale * ((a.z + c.z) + (d.z + e.z)), scale * ((a.w + c.w) + (d.w + e.w)));
     float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
     if (accumulate) {
       const float4 p = *reinterpret_cast<const float4*>(o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     *reinterpret_cast<float4*>(o) = v;
   }
 }
@@ -467,19 +475,21 @@ __global__ void add_views_kernel(View in, View out, int accumulate) {
 __global__ void set_scalar_kernel(float* dst, float v) { *dst = v; }
 __global__ void temb_kernel(const float* __restrict__ t_dev, int ch, const float* __restrict__ w0,
                             const float* __restrict__ b0, const float* __restrict__ w1,
-                            const float* __restrict__ b1, float* __restrict__ scratch) {
+                            const float* __restrict__ b1, float* __restrict__ scratch, int style) {
   extern __shared__ float sm[];   // emb[ch] + h[4ch]
   float* emb = sm;
   float* h = sm + ch;
   const float t = *t_dev;
   const int half = ch / 2;
   const int tch = 4 * ch;
-  const float coef = -(float)(log(10000.0) / (double)(half - 1));
+  // style 0: DDPM [sin, cos], w_i = exp(-ln(1e4) i / (half-1))      (ddpm/diffusion.py:783-804)
+  // style 1: guided-diffusion [cos, sin], w_i = exp(-ln(1e4) i / half)  (guided_diffusion/nn.py:103-121)
+  const float coef = -(float)(log(10000.0) / (double)(style == 0 ? half - 1 : half));
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float w = expf((float)i * coef);
     const float a = t * w;
-    emb[i] = sinf(a);
-    emb[half + i] = cosf(a);
+    emb[style == 0 ? i : half + i] = sinf(a);
+    emb[style == 0 ? half + i : i] = cosf(a);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -499,6 +509,20 @@ __global__ void temb_kernel(const float* __restrict__ t_dev, int ch, const float
     for (int i = lane; i < tch; i += 32) acc += w1[(long long)o * tch + i] * h[i];
     acc = warp_sum(acc);
     if (lane == 0) scratch[tch + o] = silu_f(acc + b1[o]);
+  }
+}
+// P2 scale-shift normalisation (guided_diffusion/unet.py:247-252): GN(x) * (1 + scale) + shift with
+// (scale | shift) = emb_layers(emb) folds into an effective affine of the GroupNorm:
+//   gamma' = gamma (1 + scale),  beta' = beta (1 + scale) + shift.   One block per site.
+__global__ void scale_shift_affine_kernel(const AffineSite* __restrict__ sites,
+                                          const float* __restrict__ weights,
+                                          const float* __restrict__ tproj, float* __restrict__ out) {
+  const AffineSite st = sites[blockIdx.x];
+  for (int c = threadIdx.x; c < st.C; c += blockDim.x) {
+    const float sc = 1.0f + tproj[st.tproj_off + c];
+    const float sh = tproj[st.tproj_off + st.C + c];
+    out[st.out_off + c] = weights[st.gamma_off + c] * sc;
+    out[st.out_off + st.C + c] = weights[st.beta_off + c] * sc + sh;
   }
 }
 // out[c] = b[c] + W[c,:] . temb_act   (one warp per output)
@@ -592,6 +616,7 @@ int layers_init() {
   LOCO_CARVE(edge_expand_kernel); LOCO_CARVE(edge_reduce_kernel);
   LOCO_CARVE(upsample2x_kernel); LOCO_CARVE(sumpool2x_kernel); LOCO_CARVE(add_views_kernel);
   LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
+  LOCO_CARVE(scale_shift_affine_kernel);
 #undef LOCO_CARVE
   done = true;
   return 0;
@@ -659,19 +684,19 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   return 0;
 }
 
-int upsample2x(View in, View out, cudaStream_t s) {
+int upsample2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s) {
   LOCO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && out.N == in.N,
                "upsample2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int sumpool2x(View in, View out, int accumulate, cudaStream_t s) {
+int sumpool2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s) {
   LOCO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W && out.C == in.C && out.N == in.N,
                "sumpool2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
-  sumpool2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
+  sumpool2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -690,9 +715,16 @@ int set_scalar(float* dst, float v, cudaStream_t s) {
   return 0;
 }
 int temb_forward(const float* t_dev, int ch, const float* w0, const float* b0, const float* w1,
-                 const float* b1, float* scratch, cudaStream_t s) {
+                 const float* b1, float* scratch, int style, cudaStream_t s) {
   const size_t smem = (size_t)(ch + 4 * ch) * sizeof(float);
-  temb_kernel<<<1, 512, smem, s>>>(t_dev, ch, w0, b0, w1, b1, scratch);
+  temb_kernel<<<1, 512, smem, s>>>(t_dev, ch, w0, b0, w1, b1, scratch, style);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int scale_shift_affine(const AffineSite* sites_dev, int n_sites, const float* weights,
+                       const float* tproj, float* out, cudaStream_t s) {
+  if (n_sites <= 0) return 0;
+  scale_shift_affine_kernel<<<n_sites, 256, 0, s>>>(sites_dev, weights, tproj, out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -46,8 +46,12 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
                  int round_out, View gx, cudaStream_t s);
 
 // ---- resampling ----
-int upsample2x(View in, View out, cudaStream_t s);                 // nearest, out = 2H x 2W
-int sumpool2x(View in, View out, int accumulate, cudaStream_t s);  // VJP of upsample2x
+// out (+)= scale * nearest_upsample(in), out = 2H x 2W.  scale 1: the DDPM Upsample / P2 up ResBlock
+// (ddpm/diffusion.py:816-832, guided_diffusion/unet.py:95-124); scale 1/4: VJP of the 2x2 avg-pool.
+int upsample2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s);
+// out (+)= scale * 2x2 sum-pool(in).  scale 1: VJP of upsample2x; scale 1/4: the avg-pool of the P2
+// down ResBlock (guided_diffusion/unet.py:127-158 with use_conv = False).
+int sumpool2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s);
 // out (+)= in   (cotangent fan-in where no producing kernel can fuse it)
 int add_views(View in, View out, int accumulate, cudaStream_t s);
 
@@ -55,8 +59,15 @@ int add_views(View in, View out, int accumulate, cudaStream_t s);
 // 154-157, 783-804): temb_act = silu(dense1(silu(dense0([sin(t w), cos(t w)])))), then every
 // ResnetBlock's temb_proj Linear(temb_ch -> Cout) evaluated into one packed vector.
 // t is read from device memory so a captured CUDA graph can be replayed for any timestep.
+// style 0 = DDPM sinusoid ([sin, cos], divisor half-1), 1 = guided-diffusion ([cos, sin], half).
 int temb_forward(const float* t_dev, int ch, const float* w0, const float* b0, const float* w1,
-                 const float* b1, float* scratch /*2*4ch*/, cudaStream_t s);
+                 const float* b1, float* scratch /*2*4ch*/, int style, cudaStream_t s);
+// P2 scale-shift norm folded into the GroupNorm affine, all sites of a program in one launch:
+// out[out_off + c] = gamma[c] (1 + scale[c]), out[out_off + C + c] = beta[c] (1 + scale[c]) + shift[c]
+// with (scale | shift) = tproj[tproj_off .. tproj_off + 2C).
+struct AffineSite { long long gamma_off, beta_off; int tproj_off, C; long long out_off; };
+int scale_shift_affine(const AffineSite* sites_dev, int n_sites, const float* weights,
+                       const float* tproj, float* out, cudaStream_t s);
 int set_scalar(float* dst, float v, cudaStream_t s);
 int temb_project(const float* temb_act, int temb_ch, const float* w, const float* b, int cout,
                  float* out, cudaStream_t s);

@@ -90,14 +90,15 @@ int Model::add_slot(ParamSlot s) {
   slots.push_back(s);
   return (int)slots.size() - 1;
 }
-ConvRef Model::add_conv(const std::string& prefix, int cin, int cout, int ksz) {
+ConvRef Model::add_conv(const std::string& prefix, int cin, int cout, int ksz, bool conv1d) {
   ConvRef c;
   c.cin = cin; c.cout = cout; c.ksz = ksz;
   c.wf = alloc((size_t)cout * cin * ksz * ksz);
   c.wd = alloc((size_t)cout * cin * ksz * ksz);
   c.bias = alloc(cout);
   ParamSlot w;
-  w.name = prefix + ".weight"; w.shape = {cout, cin, ksz, ksz}; w.kind = ParamSlot::CONV_GEMM;
+  w.name = prefix + ".weight"; w.kind = ParamSlot::CONV_GEMM;
+  if (conv1d) w.shape = {cout, cin, ksz}; else w.shape = {cout, cin, ksz, ksz};
   w.off_a = c.wf; w.off_b = c.wd; w.cout = cout; w.cin = cin; w.ksz = ksz;
   w.row_off = 0; w.rows_total = cout;
   add_slot(w);
@@ -167,7 +168,138 @@ static bool in_list(const int* lst, int n, int v) {
   return false;
 }
 
+// guided-diffusion ResBlock (unet.py:161-236): in_layers = GN, SiLU, conv3x3; emb_layers = SiLU,
+// Linear(4ch -> 2 Cout); out_layers = GN, SiLU, Dropout, conv3x3; skip_connection = 1x1 iff Cin != Cout
+ResRef Model::add_res_p2(const std::string& prefix, int cin, int cout, int resample) {
+  ResRef r;
+  r.cin = cin; r.cout = cout; r.scale_shift = true; r.resample = resample;
+  r.n1 = add_norm(prefix + ".in_layers.0", cin);
+  r.c1 = add_conv(prefix + ".in_layers.2", cin, cout, 3);
+  r.temb_off = tproj_rows;
+  tproj_rows += 2 * cout;
+  {
+    ParamSlot w; w.name = prefix + ".emb_layers.1.weight"; w.shape = {2 * cout, arch.ch * 4};
+    w.kind = ParamSlot::RAW; w.off_a = (size_t)r.temb_off; w.cout = -1;
+    add_slot(w);
+    ParamSlot b; b.name = prefix + ".emb_layers.1.bias"; b.shape = {2 * cout}; b.kind = ParamSlot::RAW;
+    b.off_a = (size_t)r.temb_off; b.cout = -2;
+    add_slot(b);
+  }
+  r.n2 = add_norm(prefix + ".out_layers.0", cout);
+  r.c2 = add_conv(prefix + ".out_layers.3", cout, cout, 3);
+  r.has_nin = cin != cout;
+  if (r.has_nin) r.nin = add_conv(prefix + ".skip_connection", cin, cout, 1);
+  return r;
+}
+// guided-diffusion AttentionBlock (unet.py:261-308): norm, qkv = conv1d(C, 3C, 1) in the per-head
+// q|k|v ("legacy") channel order, proj_out = conv1d(C, C, 1)
+AttnRef Model::add_attn_p2(const std::string& prefix, int C) {
+  AttnRef a;
+  a.C = C;
+  a.n = add_norm(prefix + ".norm", C);
+  a.qkv = add_conv(prefix + ".qkv", C, 3 * C, 1, true);
+  a.proj = add_conv(prefix + ".proj_out", C, C, 1, true);
+  return a;
+}
+
+void Model::finish_temb() {
+  // stacked timestep projections
+  const int temb_ch = 4 * arch.ch;
+  tproj_w = alloc((size_t)tproj_rows * temb_ch);
+  tproj_b = alloc(tproj_rows);
+  for (auto& s : slots) {
+    if (s.kind == ParamSlot::RAW && s.cout == -1) s.off_a = tproj_w + s.off_a * (size_t)temb_ch;
+    if (s.kind == ParamSlot::RAW && s.cout == -2) s.off_a = tproj_b + s.off_a;
+  }
+}
+
 Model::Model(const Arch& a) : arch(a) {
+  if (a.kind == 1) build_p2(); else build_ddpm();
+  finish_temb();
+}
+
+// Module tree of UNetModel.__init__ (guided_diffusion/unet.py:470-618) with resblock_updown = True,
+// use_scale_shift_norm = True, learn_sigma = True.  Same skeleton as the DDPM U-Net (one skip tensor
+// per block, nrb+1 decoder blocks per level), so the two families share the plan builder.
+void Model::build_p2() {
+  const Arch& a = arch;
+  const int ch = a.ch, temb_ch = 4 * a.ch, L = a.n_levels;
+  temb_w0 = alloc((size_t)temb_ch * ch); temb_b0 = alloc(temb_ch);
+  temb_w1 = alloc((size_t)temb_ch * temb_ch); temb_b1 = alloc(temb_ch);
+  {
+    ParamSlot s;
+    s.kind = ParamSlot::RAW;
+    s.name = "time_embed.0.weight"; s.shape = {temb_ch, ch}; s.off_a = temb_w0; add_slot(s);
+    s.name = "time_embed.0.bias"; s.shape = {temb_ch}; s.off_a = temb_b0; add_slot(s);
+    s.name = "time_embed.2.weight"; s.shape = {temb_ch, temb_ch}; s.off_a = temb_w1; add_slot(s);
+    s.name = "time_embed.2.bias"; s.shape = {temb_ch}; s.off_a = temb_b1; add_slot(s);
+  }
+  conv_in_w = alloc(27 * ch); conv_in_b = alloc(ch);
+  {
+    ParamSlot s;
+    s.name = "input_blocks.0.0.weight"; s.shape = {ch, a.in_ch, 3, 3}; s.kind = ParamSlot::CONV_EDGE_IN;
+    s.off_a = conv_in_w; s.cout = ch; add_slot(s);
+    ParamSlot b; b.name = "input_blocks.0.0.bias"; b.shape = {ch}; b.kind = ParamSlot::RAW;
+    b.off_a = conv_in_b; add_slot(b);
+  }
+  down_res.resize(L); down_attn.resize(L); down_rb.resize(L);
+  up_res.resize(L); up_attn.resize(L); up_rb.resize(L);
+  down_sample.resize(L); up_sample.resize(L);
+  int curr_res = a.resolution;
+  int block_in = ch * a.ch_mult[0];
+  int ib = 1;
+  for (int l = 0; l < L; ++l) {
+    const int block_out = ch * a.ch_mult[l];
+    for (int b = 0; b < a.num_res_blocks; ++b, ++ib) {
+      const std::string p = "input_blocks." + std::to_string(ib);
+      down_res[l].push_back(add_res_p2(p + ".0", block_in, block_out, 0));
+      block_in = block_out;
+      if (in_list(a.attn_resolutions, a.n_attn, curr_res))
+        down_attn[l].push_back(add_attn_p2(p + ".1", block_in));
+    }
+    if (l != L - 1) {
+      down_rb[l] = add_res_p2("input_blocks." + std::to_string(ib) + ".0", block_in, block_in, 1);
+      ++ib;
+      curr_res /= 2;
+    }
+  }
+  mid1 = add_res_p2("middle_block.0", block_in, block_in, 0);
+  mid_attn = add_attn_p2("middle_block.1", block_in);
+  mid2 = add_res_p2("middle_block.2", block_in, block_in, 0);
+  int ob = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const int block_out = ch * a.ch_mult[l];
+    int skip_in = ch * a.ch_mult[l];
+    for (int b = 0; b < a.num_res_blocks + 1; ++b, ++ob) {
+      if (b == a.num_res_blocks) skip_in = ch * (l == 0 ? a.ch_mult[0] : a.ch_mult[l - 1]);
+      const std::string p = "output_blocks." + std::to_string(ob);
+      up_res[l].push_back(add_res_p2(p + ".0", block_in + skip_in, block_out, 0));
+      block_in = block_out;
+      int j = 1;
+      if (in_list(a.attn_resolutions, a.n_attn, curr_res)) {
+        up_attn[l].push_back(add_attn_p2(p + "." + std::to_string(j), block_in));
+        ++j;
+      }
+      if (l != 0 && b == a.num_res_blocks) {
+        up_rb[l] = add_res_p2(p + "." + std::to_string(j), block_in, block_in, 2);
+        curr_res *= 2;
+      }
+    }
+  }
+  norm_out = add_norm("out.0", block_in);
+  conv_out_w = alloc(27 * block_in); conv_out_b = alloc(64);
+  {
+    // learn_sigma: 6 output channels, eps = the first 3 (unet.py:680-684); only those are packed
+    ParamSlot s;
+    s.name = "out.2.weight"; s.shape = {2 * a.out_ch, block_in, 3, 3}; s.kind = ParamSlot::CONV_EDGE_OUT;
+    s.off_a = conv_out_w; s.cin = block_in; add_slot(s);
+    ParamSlot b; b.name = "out.2.bias"; b.shape = {2 * a.out_ch}; b.kind = ParamSlot::RAW;
+    b.off_a = conv_out_b; add_slot(b);
+  }
+}
+
+void Model::build_ddpm() {
+  const Arch& a = arch;
   const int ch = a.ch, temb_ch = 4 * a.ch, L = a.n_levels;
   temb_w0 = alloc((size_t)temb_ch * ch); temb_b0 = alloc(temb_ch);
   temb_w1 = alloc((size_t)temb_ch * temb_ch); temb_b1 = alloc(temb_ch);
@@ -235,13 +367,6 @@ Model::Model(const Arch& a) : arch(a) {
     s.off_a = conv_out_w; s.cin = block_in; add_slot(s);
     ParamSlot b; b.name = "conv_out.bias"; b.shape = {a.out_ch}; b.kind = ParamSlot::RAW;
     b.off_a = conv_out_b; add_slot(b);
-  }
-  // stacked timestep projections
-  tproj_w = alloc((size_t)tproj_rows * temb_ch);
-  tproj_b = alloc(tproj_rows);
-  for (auto& s : slots) {
-    if (s.kind == ParamSlot::RAW && s.cout == -1) s.off_a = tproj_w + s.off_a * (size_t)temb_ch;
-    if (s.kind == ParamSlot::RAW && s.cout == -2) s.off_a = tproj_b + s.off_a;
   }
 }
 
@@ -470,11 +595,12 @@ int Plan::build(float* workspace) {
     push_b([l](cudaStream_t s) { return conv_run(*l, s); });
   };
   const float eps = A.gn_eps;
+  // `aff` (optional): effective affine [gamma' | beta'] of a scale-shift norm site (kind 1)
   auto gn_fwd = [&](View x, const NormRef& n, int silu, int round_out, View y, double* st = nullptr,
-                    bool fused = false) -> double* {
+                    bool fused = false, const float* aff = nullptr) -> double* {
     if (!st) st = alloc_fstat(NB);
-    const float* ga = dry ? nullptr : M.w(n.gamma);
-    const float* be = dry ? nullptr : M.w(n.beta);
+    const float* ga = aff ? aff : (dry ? nullptr : M.w(n.gamma));
+    const float* be = aff ? aff + n.C : (dry ? nullptr : M.w(n.beta));
     const int np = NP;
     I.fwd.push_back([=](cudaStream_t s) {
       if (!fused) LOCO_TRY(gn_stats_fwd(x, np, st, s));   // else: accumulated by the producer's epilogue
@@ -488,10 +614,11 @@ int Plan::build(float* workspace) {
     return fused_self[t.ids[0]] != 0;
   };
   auto gn_bwd = [&](View xp, const double* pstats, View gy, const NormRef& n, int silu,
-                    const View* addend, int accumulate, int round_out, View gx) {
+                    const View* addend, int accumulate, int round_out, View gx,
+                    const float* aff = nullptr) {
     double* st = alloc_bstat(NC);
-    const float* ga = dry ? nullptr : M.w(n.gamma);
-    const float* be = dry ? nullptr : M.w(n.beta);
+    const float* ga = aff ? aff : (dry ? nullptr : M.w(n.gamma));
+    const float* be = aff ? aff + n.C : (dry ? nullptr : M.w(n.beta));
     const bool has_add = addend != nullptr;
     const View add = has_add ? *addend : View();
     push_b([=](cudaStream_t s) {
@@ -516,50 +643,95 @@ int Plan::build(float* workspace) {
   const int temb_ch = 4 * A.ch;
   float* temb_scratch = alloc_act(2 * temb_ch);
   float* tproj = alloc_act(M.tproj_rows);
-  if (!dry) {
-    const Model* Mp = model;
-    Impl* Ip = impl.get();
-    I.fwd.push_back([=](cudaStream_t s) {
-      LOCO_TRY(temb_forward(Ip->t_dev, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
-                            Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, s));
-      return temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
-                          Mp->tproj_rows, tproj, s);
-    });
-  } else {
-    I.fwd.push_back([](cudaStream_t) { return 0; });
-  }
+  // kind 1: every ResBlock's second GroupNorm takes its affine from (scale | shift) = tproj slice;
+  // the effective [gamma' | beta'] vectors live in `aff_buf`, filled by one launch per forward
+  std::vector<AffineSite> aff_sites;
+  float* aff_buf = alloc_act(A.kind == 1 ? (size_t)M.tproj_rows : 0);
+  AffineSite* aff_dev = reinterpret_cast<AffineSite*>(alloc_act(A.kind == 1 ? 4096 : 0));
+  const int aff_cap = (int)(4096 * sizeof(float) / sizeof(AffineSite));
+  size_t aff_off = 0;
+  auto affine_site = [&](const ResRef& R) -> const float* {
+    if (!R.scale_shift) return nullptr;
+    AffineSite st;
+    st.gamma_off = (long long)R.n2.gamma; st.beta_off = (long long)R.n2.beta;
+    st.tproj_off = R.temb_off; st.C = R.cout; st.out_off = (long long)aff_off;
+    aff_sites.push_back(st);
+    const float* p = aff_buf + aff_off;
+    aff_off += 2 * (size_t)R.cout;
+    return p;
+  };
+  const size_t temb_op_index = I.fwd.size();
+  I.fwd.push_back([](cudaStream_t) { return 0; });   // replaced below once the sites are known
 
   // ---- blocks ----
   auto resblock = [&](const ResRef& R, const TH& x, const TH& out) {
     const int H = x.v.H, W = x.v.W;
+    const int Ho = R.resample == 1 ? H / 2 : (R.resample == 2 ? 2 * H : H);
+    const int Wo = R.resample == 1 ? W / 2 : (R.resample == 2 ? 2 * W : W);
+    const float* aff = affine_site(R);
     View a1 = Tf(H, W, R.cin);
     double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1, x.st_self.st, th_fused(x));
-    View h1 = Tf(H, W, R.cout);
+    // guided-diffusion up/down ResBlock: both branches are resampled after GN+SiLU
+    // (unet.py:238-244): avg-pool 2x2 (Downsample, use_conv = False) or nearest x2 (Upsample)
+    View a1r = a1, xr = x.v;
+    if (R.resample != 0) {
+      a1r = Tf(Ho, Wo, R.cin);
+      xr = Tf(Ho, Wo, R.cin);
+      const View xv = x.v;
+      if (R.resample == 1)
+        I.fwd.push_back([=](cudaStream_t s) {
+          LOCO_TRY(sumpool2x(a1, a1r, 0.25f, 0, 1, s));
+          return sumpool2x(xv, xr, 0.25f, 0, 0, s);
+        });
+      else
+        I.fwd.push_back([=](cudaStream_t s) {
+          LOCO_TRY(upsample2x(a1, a1r, 1.f, 0, 0, s));
+          return upsample2x(xv, xr, 1.f, 0, 0, s);
+        });
+    }
+    View h1 = Tf(Ho, Wo, R.cout);
     StatTarget t2; t2.st = alloc_fstat(NB); t2.cg = R.cout / 32; t2.choff = 0;
-    conv_fwd(CONV_3x3, a1, h1, R.c1, tproj + R.temb_off, nullptr, nullptr, t2);
-    View a2 = Tf(H, W, R.cout);
-    double* st2 = gn_fwd(h1, R.n2, 1, 1, a2, t2.st, fuse_stats);
+    conv_fwd(CONV_3x3, a1r, h1, R.c1, R.scale_shift ? nullptr : tproj + R.temb_off, nullptr, nullptr, t2);
+    View a2 = Tf(Ho, Wo, R.cout);
+    double* st2 = gn_fwd(h1, R.n2, 1, 1, a2, t2.st, fuse_stats, aff);
     View sc;
     if (R.has_nin) {
-      sc = Tf(H, W, R.cout);
-      conv_fwd(CONV_1x1, x.v, sc, R.nin, nullptr, nullptr);
+      sc = Tf(Ho, Wo, R.cout);
+      conv_fwd(CONV_1x1, xr, sc, R.nin, nullptr, nullptr);
       conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &sc, &out);
     } else {
-      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &x.v, &out);
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &xr, &out);
     }
     if (NC > 0) {
       begin_group();
-      View ga2 = Tg(H, W, R.cout);
+      View ga2 = Tg(Ho, Wo, R.cout);
       conv_bwd(CONV_3x3, out.g, ga2, R.c2, 0);
-      View gh1 = Tg(H, W, R.cout);
-      gn_bwd(row0(h1), st2, ga2, R.n2, 1, nullptr, 0, 1, gh1);
-      View ga1 = Tg(H, W, R.cin);
-      conv_bwd(CONV_3x3, gh1, ga1, R.c1, 0);
+      View gh1 = Tg(Ho, Wo, R.cout);
+      gn_bwd(row0(h1), st2, ga2, R.n2, 1, nullptr, 0, 1, gh1, aff);
+      View ga1r = Tg(Ho, Wo, R.cin);
+      conv_bwd(CONV_3x3, gh1, ga1r, R.c1, 0);
+      View ga1 = ga1r;
+      if (R.resample != 0) {
+        ga1 = Tg(H, W, R.cin);
+        if (R.resample == 1) push_b([=](cudaStream_t s) { return upsample2x(ga1r, ga1, 0.25f, 0, 0, s); });
+        else push_b([=](cudaStream_t s) { return sumpool2x(ga1r, ga1, 1.f, 0, 0, s); });
+      }
       const int f1 = writer_flag(x.ids);
-      gn_bwd(row0(x.v), st1, ga1, R.n1, 1, R.has_nin ? nullptr : &out.g, f1, 1, x.g);
+      const bool fuse_identity = !R.has_nin && R.resample == 0;
+      gn_bwd(row0(x.v), st1, ga1, R.n1, 1, fuse_identity ? &out.g : nullptr, f1, 1, x.g);
       if (R.has_nin) {
+        if (R.resample != 0 && err == 0) {   // (a void lambda: report through `err`)
+          set_error("plan: resampling ResBlock with a 1x1 shortcut is not supported");
+          err = 3;
+        }
         const int f2 = writer_flag(x.ids);
         conv_bwd(CONV_1x1, out.g, x.g, R.nin, f2);
+      } else if (R.resample != 0) {
+        // identity shortcut through the resampling: x.g += resample^T(out.g)
+        const int f2 = writer_flag(x.ids);
+        const View og = out.g, xg = x.g;
+        if (R.resample == 1) push_b([=](cudaStream_t s) { return upsample2x(og, xg, 0.25f, f2, 1, s); });
+        else push_b([=](cudaStream_t s) { return sumpool2x(og, xg, 1.f, f2, 1, s); });
       }
     }
   };
@@ -569,19 +741,21 @@ int Plan::build(float* workspace) {
     double* st = gn_fwd(x.v, R.n, 0, 1, hn, x.st_self.st, th_fused(x));
     View qkv = Tf(H, W, 3 * C);
     conv_fwd(CONV_1x1, hn, qkv, R.qkv, nullptr, nullptr);
-    float* S = alloc_act((size_t)NB * T * T);
+    const int hc = A.kind == 1 ? A.head_ch : 0;
+    const int heads = hc > 0 ? C / hc : 1;
+    float* S = alloc_act((size_t)NB * heads * T * T);
     View o = Tf(H, W, C);
     const int np = NP;
-    I.fwd.push_back([=](cudaStream_t s) { return attention_forward(qkv, np, S, o, s); });
+    I.fwd.push_back([=](cudaStream_t s) { return attention_forward(qkv, np, hc, S, o, s); });
     conv_fwd(CONV_1x1, o, out.v, R.proj, nullptr, &x.v, &out);
     if (NC > 0) {
       begin_group();
       View go = Tg(H, W, C);
       conv_bwd(CONV_1x1, out.g, go, R.proj, 0);
       View gqkv = Tg(H, W, 3 * C);
-      float* gP = alloc_act((size_t)NC * T * T);
+      float* gP = alloc_act((size_t)NC * heads * T * T);
       View qkv0 = row0(qkv);
-      push_b([=](cudaStream_t s) { return attention_vjp(go, qkv0, S, gP, gqkv, s); });
+      push_b([=](cudaStream_t s) { return attention_vjp(go, qkv0, hc, S, gP, gqkv, s); });
       View ghn = Tg(H, W, C);
       conv_bwd(CONV_1x1, gqkv, ghn, R.qkv, 0);
       const int f = writer_flag(x.ids);
@@ -632,7 +806,6 @@ int Plan::build(float* workspace) {
     }
   }
   auto hs_slot = [&](int i) -> TH& { return cbs[n_hs - 1 - i].skip; };
-
   // conv_in
   {
     TH& h0 = hs_slot(0);
@@ -668,12 +841,16 @@ int Plan::build(float* workspace) {
       if (l != L - 1) {
         TH& x = hs_slot(hs_top);
         TH& out = hs_slot(hs_top + 1);
-        const ConvRef& c = M.down_sample[l];
-        conv_fwd(CONV_3x3_S2, x.v, out.v, c, nullptr, nullptr, &out);
-        if (NC > 0) {
-          begin_group();
-          const int f = writer_flag(x.ids);
-          conv_bwd(CONV_3x3_S2, out.g, x.g, c, f);
+        if (A.kind == 1) {
+          resblock(M.down_rb[l], x, out);
+        } else {
+          const ConvRef& c = M.down_sample[l];
+          conv_fwd(CONV_3x3_S2, x.v, out.v, c, nullptr, nullptr, &out);
+          if (NC > 0) {
+            begin_group();
+            const int f = writer_flag(x.ids);
+            conv_bwd(CONV_3x3_S2, out.g, x.g, c, f);
+          }
         }
         ++hs_top;
         res /= 2;
@@ -712,11 +889,13 @@ int Plan::build(float* workspace) {
         } else {
           resblock(R, cbs[u].full, target);
         }
-        if (needs_up) {
+        if (needs_up && A.kind == 1) {
+          resblock(M.up_rb[l], target, cbs[u + 1].dec);
+        } else if (needs_up) {
           const ConvRef& c = M.up_sample[l];
           View hu = Tf(2 * res, 2 * res, R.cout);
           const View tv = target.v;
-          I.fwd.push_back([=](cudaStream_t s) { return upsample2x(tv, hu, s); });
+          I.fwd.push_back([=](cudaStream_t s) { return upsample2x(tv, hu, 1.f, 0, 0, s); });
           TH& nxt = cbs[u + 1].dec;
           conv_fwd(CONV_3x3, hu, nxt.v, c, nullptr, nullptr, &nxt);
           if (NC > 0) {
@@ -725,7 +904,7 @@ int Plan::build(float* workspace) {
             conv_bwd(CONV_3x3, nxt.g, ghu, c, 0);
             const int f = writer_flag(target.ids);
             const View tg = target.g;
-            push_b([=](cudaStream_t s) { return sumpool2x(ghu, tg, f, s); });
+            push_b([=](cudaStream_t s) { return sumpool2x(ghu, tg, 1.f, f, 0, s); });
           }
         }
         if (very_last) hfin = target;
@@ -751,6 +930,26 @@ int Plan::build(float* workspace) {
     }
   }
   if (err != 0) return err;
+
+  // ---- timestep embedding op (first op of the forward program) ----
+  LOCO_REQUIRE((int)aff_sites.size() <= aff_cap, "plan: %d scale-shift sites exceed the table", (int)aff_sites.size());
+  if (!dry) {
+    const Model* Mp = model;
+    Impl* Ip = impl.get();
+    const int n_aff = (int)aff_sites.size();
+    if (n_aff > 0) {
+      const cudaError_t ce = cudaMemcpy(aff_dev, aff_sites.data(), sizeof(AffineSite) * n_aff,
+                                        cudaMemcpyHostToDevice);
+      LOCO_REQUIRE(ce == cudaSuccess, "plan: cudaMemcpy(affine sites) failed: %s", cudaGetErrorString(ce));
+    }
+    I.fwd[temb_op_index] = [=](cudaStream_t s) {
+      LOCO_TRY(temb_forward(Ip->t_dev, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
+                            Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, Mp->arch.kind, s));
+      LOCO_TRY(temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
+                            Mp->tproj_rows, tproj, s));
+      return scale_shift_affine(aff_dev, n_aff, Mp->arena, tproj, aff_buf, s);
+    };
+  }
 
   if (dry) {
     I.act_floats = act_off; I.fstat_floats = fs_off; I.bstat_floats = bs_off;

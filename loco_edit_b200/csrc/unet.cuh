@@ -1,6 +1,8 @@
-// DDPM U-Net executor (architecture of the reference's models/ddpm/diffusion.py:22-200, i.e.
-// google/ddpm-ema-celebahq-256): forward, fused primal+k-tangent forward (JVP) and k-cotangent
-// backward (VJP) as static launch programs over a caller-provided workspace.
+// U-Net executor for the two unconditional model families of the reference: the DDPM U-Net
+// (models/ddpm/diffusion.py:22-200, i.e. google/ddpm-ema-celebahq-256) and the P2 / guided-diffusion
+// U-Net (models/guided_diffusion/unet.py:398-684 with P2_DICT).  Forward, fused primal+k-tangent
+// forward (JVP) and k-cotangent backward (VJP) as static launch programs over a caller-provided
+// workspace.
 #pragma once
 #include <map>
 #include <memory>
@@ -24,6 +26,8 @@ struct Arch {
   int in_ch = 3;
   int out_ch = 3;
   float gn_eps = 1e-6f;
+  int kind = 0;       // 0 = DDPM (ddpm/diffusion.py), 1 = P2 / guided diffusion (guided_diffusion/unet.py)
+  int head_ch = 0;    // kind 1: channels per attention head
 };
 
 // One named parameter of the reference state_dict and where its packed forms live in the arena.
@@ -47,6 +51,10 @@ struct ResRef {
   ConvRef c1, c2, nin;
   bool has_nin = false;
   int temb_off = 0;    // offset into the packed timestep-projection vector
+  // guided-diffusion ResBlock (unet.py:161-258): timestep projection is (scale | shift) of the
+  // second GroupNorm instead of a bias; resample 1 = avg-pool /2, 2 = nearest x2 on both branches
+  bool scale_shift = false;
+  int resample = 0;
 };
 struct AttnRef { int C = 0; NormRef n; ConvRef qkv, proj; };
 
@@ -67,7 +75,8 @@ class Model {
   NormRef norm_out;
   std::vector<std::vector<ResRef>> down_res, up_res;
   std::vector<std::vector<AttnRef>> down_attn, up_attn;
-  std::vector<ConvRef> down_sample, up_sample;   // per level (cin == 0 when absent)
+  std::vector<ConvRef> down_sample, up_sample;   // per level (cin == 0 when absent), kind 0
+  std::vector<ResRef> down_rb, up_rb;            // per level: resampling ResBlocks, kind 1
   ResRef mid1, mid2;
   AttnRef mid_attn;
 
@@ -78,7 +87,12 @@ class Model {
  private:
   size_t alloc(size_t n);
   int add_slot(ParamSlot s);
-  ConvRef add_conv(const std::string& prefix, int cin, int cout, int ksz);
+  void build_ddpm();
+  void build_p2();
+  void finish_temb();
+  ConvRef add_conv(const std::string& prefix, int cin, int cout, int ksz, bool conv1d = false);
+  ResRef add_res_p2(const std::string& prefix, int cin, int cout, int resample);
+  AttnRef add_attn_p2(const std::string& prefix, int C);
   NormRef add_norm(const std::string& prefix, int C);
   ResRef add_res(const std::string& prefix, int cin, int cout);
   AttnRef add_attn(const std::string& prefix, int C);

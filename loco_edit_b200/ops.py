@@ -201,22 +201,25 @@ def groupnorm_silu_vjp(xp, gy, gamma, beta, eps, silu):
     return gx
 
 
-def attention_fwd(qkv, n_primal):
+def attention_fwd(qkv, n_primal, head_ch=0):
+    """head_ch = 0: one head, channels q|k|v (DDPM); > 0: per-head q|k|v (guided-diffusion legacy)."""
     qkv = _f32(qkv)
     N, T, C3 = qkv.shape
     Cc = C3 // 3
-    S = torch.empty(N, T, T, dtype=torch.float32, device=qkv.device)
+    heads = 1 if head_ch <= 0 else Cc // head_ch
+    S = torch.empty(N, heads, T, T, dtype=torch.float32, device=qkv.device)
     o = torch.empty(N, T, Cc, dtype=torch.float32, device=qkv.device)
-    check(_lib.load().loco_attention_fwd(ptr(qkv), N, T, Cc, n_primal, ptr(S), ptr(o), stream_ptr()),
-          "loco_attention_fwd")
-    return o, S
+    check(_lib.load().loco_attention_fwd(ptr(qkv), N, T, Cc, n_primal, head_ch, ptr(S), ptr(o),
+                                         stream_ptr()), "loco_attention_fwd")
+    return o, (S if head_ch > 0 else S[:, 0])
 
 
-def attention_vjp(go, qkv0, P0):
+def attention_vjp(go, qkv0, P0, head_ch=0):
     go = _f32(go)
     K, T, Cc = go.shape
-    gP = torch.empty(K, T, T, dtype=torch.float32, device=go.device)
+    heads = 1 if head_ch <= 0 else Cc // head_ch
+    gP = torch.empty(K, heads, T, T, dtype=torch.float32, device=go.device)
     gqkv = torch.empty(K, T, 3 * Cc, dtype=torch.float32, device=go.device)
-    check(_lib.load().loco_attention_vjp(ptr(go), K, T, Cc, ptr(_f32(qkv0)), ptr(_f32(P0)), ptr(gP),
-                                         ptr(gqkv), stream_ptr()), "loco_attention_vjp")
+    check(_lib.load().loco_attention_vjp(ptr(go), K, T, Cc, head_ch, ptr(_f32(qkv0)), ptr(_f32(P0)),
+                                         ptr(gP), ptr(gqkv), stream_ptr()), "loco_attention_vjp")
     return gqkv

@@ -29,6 +29,8 @@ def _make_arch(a):
     s.in_ch = a.get("in_ch", 3)
     s.out_ch = a.get("out_ch", 3)
     s.gn_eps = a.get("gn_eps", 1e-6)
+    s.kind = 1 if a.get("kind") == "p2" else 0
+    s.head_ch = a.get("head_ch", 0) if s.kind == 1 else 0
     return s
 
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libloco_b200.so does not export %s" % n
         assert n in _lib.PROTOTYPES, "python binding lacks a prototype for %s" % n
-    assert lib.loco_abi_version() == 1
+    assert lib.loco_abi_version() == 2
 
 
 def test_model_registry_matches_reference_state_dict(golden_dir):
@@ -87,3 +87,37 @@ def test_compute_fails_loudly_without_gpu():
     from loco_edit_b200.unet import B200UNet
     with pytest.raises(_lib.LocoError):
         B200UNet(DDPM256, {}, device="cpu")
+
+
+def test_p2_model_registry_matches_reference_state_dict(golden_dir):
+    """kind 1 (P2 / guided diffusion): the parameter registry equals create_model(**P2_DICT)'s
+    state_dict (names, order-independent, shapes) and the plan sizing runs without a device."""
+    from loco_edit_b200.unet import _make_arch
+    from loco_edit_b200.weights import P2_256
+    lib = _lib.load()
+    h = C.c_void_p()
+    arch = _make_arch(P2_256)
+    assert arch.kind == 1 and arch.head_ch == 64
+    _lib.check(lib.loco_unet_create(C.byref(arch), C.byref(h)))
+    try:
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        nd = C.c_int()
+        got = {}
+        for i in range(lib.loco_unet_num_params(h)):
+            _lib.check(lib.loco_unet_param_info(h, i, buf, 256, shape, C.byref(nd)))
+            got[buf.value.decode()] = [shape[j] for j in range(nd.value)]
+        ref = json.load(open(os.path.join(golden_dir, "p2_param_shapes.json")))
+        assert got == ref
+        p = C.c_void_p()
+        _lib.check(lib.loco_plan_create(h, 1, 3, 3, C.byref(p)))
+        ff, vf = C.c_double(), C.c_double()
+        fo, vo = C.c_int(), C.c_int()
+        _lib.check(lib.loco_plan_info(p, C.byref(ff), C.byref(vf), C.byref(fo), C.byref(vo)))
+        # SURVEY appendix C.2: 387.5 GFLOP of convolutions per sample-forward, minus the two
+        # 3-channel edge convolutions (0.45 + 0.45 GFLOP at 3 output channels) run on CUDA cores
+        assert abs(ff.value / 4 - 0.3866e12) / 0.3866e12 < 0.01, ff.value / 4
+        assert abs(vf.value / 3 - 0.3866e12) / 0.3866e12 < 0.01
+        lib.loco_plan_destroy(p)
+    finally:
+        lib.loco_unet_destroy(h)
