@@ -413,6 +413,22 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 // (TMEM lane = output channel); the epilogue's shared-memory transpose turns it back into
 // channels-last 128-byte segments.
 // ------------------------------------------------------------------------------------------------
+//
+// HALO = true ("halo" variant, 3x3 stride-1 fprop/dgrad): the work item is a 16 x 16 pixel block.
+// Instead of one 128-pixel box per filter tap (9 x 32 KB of activations per 32-channel slab), the
+// producer loads, per slab, three x-shifted copies of the (16 + 2)-row halo window (3 x 36 KB); the
+// three taps of a filter column then address the same copy at row offsets 0 / 16 / 32 (2 KB steps,
+// which keeps the 1024-byte swizzle atoms aligned).  L2 -> SM traffic per MMA clock drops from 96
+// to 55 bytes (activations 2.67x less), below what the L2 can sustain per SM, so the kernel turns
+// from L2-ingest-bound into tensor-pipe-bound.  Weights (16 KB per tap) ride a second, finer ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloRows = 18 * 16;                  // (16 + 2) image rows x 16 pixels
+constexpr int kHaloABytes = kHaloRows * 128;        // 36 KB per x-shifted copy and channel slab
+constexpr int kHaloStagesA = 3;
+constexpr int kHaloStagesB = 6;
+constexpr int kHaloSmemBytes = kHaloStagesA * kHaloABytes + kHaloStagesB * kBBytes + 1024 + 256 + kEpiBytes;
+
+template <bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int NT = 2;
@@ -420,24 +436,29 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kStageBytes = Cfg<2>::kStageBytes;  // 48 KB: [weights 16 KB | pixels 0 | pixels 1]
   constexpr int kTmemCols = 512;                    // 2 accumulator stages x 256 pixel columns
   constexpr int kPOff = kBBytes;                    // pixel tiles start after the weight tile
+  constexpr int kRingBytes = HALO ? kHaloStagesA * kHaloABytes + kHaloStagesB * kBBytes
+                                  : kStages * kStageBytes;
+  constexpr int kNFull = HALO ? kHaloStagesA + kHaloStagesB : kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  // HALO: full_bar[0..3) / empty_bar[0..3) = activation ring, [3..9) = weight ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* empty_bar = full_bar + kNFull;
+  uint64_t* tfull_bar = empty_bar + kNFull;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+  float* epi_smem = reinterpret_cast<float*>(smem + kRingBytes + 256);
+  uint8_t* smem_w = smem + kHaloStagesA * kHaloABytes;      // HALO: weight ring base
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.amap[0]);
+    prefetch_tmap(HALO ? &p.hmap : &p.amap[0]);
     prefetch_tmap(&p.bmap);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kNFull; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -460,8 +481,102 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   const int units_m = tiles_m / NT;
   const int total_items = units_m * p.tiles_co;
   const int kiters = p.ntaps * p.c_chunks;
+  const int half_y = p.tiles_y >> 1;     // HALO: 16-row blocks per image (TW = 16, TH = 8, TN = 1)
 
-  if (warp == 0) {
+  if (warp == 0 && HALO) {
+    if (elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int um = w % units_m;
+        const int co0 = (w / units_m) * 128;
+        const int x0 = (um % p.tiles_x) * 16;
+        const int y0 = ((um / p.tiles_x) % half_y) * 16;
+        const int n0 = um / (p.tiles_x * half_y);
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+#pragma unroll 1
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&empty_bar[as], aph ^ 1);
+            if (p.debug == 3 || p.debug == 7 || p.debug == 9) {   // profiling aid: no activation traffic
+              mbar_arrive(&full_bar[as]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[as], kHaloABytes);
+              tma_load_4d(smem + as * kHaloABytes, &p.hmap, &full_bar[as], cc * kConvBlockK,
+                          x0 + dxi - 1, y0 - 1, n0);
+            }
+            if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
+#pragma unroll 1
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              uint64_t* fb = &full_bar[kHaloStagesA + bs];
+              mbar_wait(&empty_bar[kHaloStagesA + bs], bph ^ 1);
+              if (p.debug == 3 || p.debug == 8 || p.debug == 9) {   // profiling aid: no weight traffic
+                mbar_arrive(fb);
+              } else {
+                mbar_arrive_expect_tx(fb, kBBytes);
+                tma_load_2d(smem_w + bs * kBBytes, &p.bmap, fb, p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0);
+              }
+              if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && HALO) {
+    if (elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      uint32_t idesc = 0;                      // M = 128 (output channels), N = 256 (pixels)
+      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
+      idesc |= (uint32_t)(256 >> 3) << 17;
+      idesc |= (uint32_t)(128 >> 4) << 24;
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(smem));      // halo copies (N operand)
+      const uint64_t wdesc0 = make_smem_desc(smem_u32(smem_w));    // weights     (M operand)
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        uint32_t first = 0;
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+#pragma unroll 1
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&full_bar[as], aph);
+            const uint64_t pdesc = pdesc0 + (uint64_t)as * (uint64_t)(kHaloABytes >> 4);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&full_bar[kHaloStagesA + bs], bph);
+              tc_fence_after();
+              const uint64_t wdesc = wdesc0 + (uint64_t)bs * (uint64_t)(kBBytes >> 4);
+              // the 256 pixels of tap row dyi are the 256 consecutive 128-byte rows that start
+              // dyi image rows (16 pixels = 2 KB) into the halo copy
+              const uint64_t pd = pdesc + (uint64_t)(dyi * ((16 * 128) >> 4));
+              if (p.debug == 4) {                      // profiling aid: no tensor-core work
+                mbar_arrive(&empty_bar[kHaloStagesA + bs]);
+                if (dyi == 2) mbar_arrive(&empty_bar[as]);
+                if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
+                continue;
+              }
+#pragma unroll
+              for (int k = 0; k < kConvBlockK / 8; ++k) {
+                umma_tf32(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+                first = 1;
+              }
+              umma_commit(&empty_bar[kHaloStagesA + bs]);
+              if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
+            }
+            if (p.debug != 4) umma_commit(&empty_bar[as]);
+            if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
+          }
+        }
+        if (p.debug == 4) mbar_arrive(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -556,11 +671,18 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
 #pragma unroll 1
-      for (int chn = 0; chn < 8; ++chn) {               // 8 chunks of 32 pixels
-        const int tm = um * NT + (chn >> 2);
-        const int tx = tm % p.tiles_x;
-        const int ty = (tm / p.tiles_x) % p.tiles_y;
-        const int tn = tm / (p.tiles_x * p.tiles_y);
+      for (int chn = ((p.debug == 5 || p.debug == 9) ? 8 : 0); chn < 8; ++chn) {   // 8 chunks of 32 pixels
+        int tx, ty, tn;
+        if (HALO) {       // the unit is a 16 x 16 block: two 16 x 8 tiles stacked vertically
+          tx = um % p.tiles_x;
+          ty = ((um / p.tiles_x) % half_y) * 2 + (chn >> 2);
+          tn = um / (p.tiles_x * half_y);
+        } else {
+          const int tm = um * NT + (chn >> 2);
+          tx = tm % p.tiles_x;
+          ty = (tm / p.tiles_x) % p.tiles_y;
+          tn = tm / (p.tiles_x * p.tiles_y);
+        }
         uint32_t r[32];
         tmem_ld_32x32(taddr + chn * 32, r);
         tmem_ld_wait();
@@ -852,10 +974,34 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     // two pixel tiles per item (shared weight tile) when that still fills >= 2 waves of the GPU
     p.nt = (ks == 1 && (p.tiles_x * p.tiles_y * p.tiles_n) % 2 == 0 && tiles >= 4 * sms) ? 2 : 1;
     {
+      // LOCO_CONV_NT caps the variant (profiling aid): 1 = one tile per item, 2 = two tiles sharing
+      // the weight tile, 3 = "wide" (operand-swapped, N = 256 pixels), default 4 = halo where eligible
       const char* e = getenv("LOCO_CONV_NT");
-      if (e && atoi(e) == 1) p.nt = 1;
-      // nt == 3 selects the "wide" (operand-swapped, N = 256 pixels) kernel
-      if (p.nt == 2 && p.block_n == 128 && !(e && atoi(e) == 2)) p.nt = 3;
+      const int cap = e ? atoi(e) : 4;
+      if (cap == 1) p.nt = 1;
+      if (p.nt == 2 && p.block_n == 128 && cap >= 3) {
+        p.nt = 3;
+        const bool s1 = prob.kind == CONV_3x3 || prob.kind == CONV_3x3_DGRAD;
+        if (cap >= 4 && s1 && p.TW == 16 && p.TH == 8 && p.TN == 1 && p.tiles_y % 2 == 0) {
+          // halo variant: (16+2)-row windows, one x-shifted copy per filter column
+          const View& in = prob.in;
+          EncodeTiledFn fn = get_encode_fn();
+          if (!fn) return 3;
+          cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
+          cuuint64_t strides[3] = {(cuuint64_t)in.sW * 4, (cuuint64_t)in.sH * 4, (cuuint64_t)in.sN * 4};
+          cuuint32_t box[4] = {(cuuint32_t)kConvBlockK, 16, 18, 1};
+          cuuint32_t estr[4] = {1, 1, 1, 1};
+          CUresult r = fn(&p.hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.ptr, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo) failed: %d", (int)r);
+          for (int dxi = 0; dxi < 3; ++dxi)
+            for (int dyi = 0; dyi < 3; ++dyi)
+              for (int t = 0; t < 9; ++t)
+                if (p.tap_dx[t] == dxi - 1 && p.tap_dy[t] == dyi - 1) p.halo_wk[dxi * 3 + dyi] = p.tap_wk[t];
+          p.nt = 4;
+        }
+      }
     }
     p.ksplit = ks;
     {
@@ -865,7 +1011,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     p.partial = prob.splitk_partial;
     p.counters = prob.splitk_counters;
     p.counter_stride = prob.splitk_max_tiles;
-    const int items = tiles * ks / (p.nt == 3 ? 2 : p.nt);
+    const int items = tiles * ks / (p.nt >= 3 ? 2 : p.nt);
     L->grid[i] = items < sms ? items : sms;
     L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
   }
@@ -879,8 +1025,10 @@ int conv_init() {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel,
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
     attr_set = true;
   }
   return 0;
@@ -891,8 +1039,10 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {
-      if (L.p[i].nt == 3)
-        conv_gemm_tf32_wide_kernel<<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
+      if (L.p[i].nt == 4)
+        conv_gemm_tf32_wide_kernel<true><<<L.grid[i], kThreads, kHaloSmemBytes, stream>>>(L.p[i]);
+      else if (L.p[i].nt == 3)
+        conv_gemm_tf32_wide_kernel<false><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
       else if (L.p[i].nt == 2)
         conv_gemm_tf32_kernel<2><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
       else

@@ -15,6 +15,8 @@ constexpr int kConvMaxBlockN = 128;
 struct ConvGemmParams {
   CUtensorMap amap[4];   // activation maps: dims (C, W, H, N); [1..3] only for stride-2 phase views
   CUtensorMap bmap;      // packed weights: dims (Ktot, Cout), box (32, block_n)
+  CUtensorMap hmap;      // halo variant: activation map with box (32, 16, 18, 1)
+  int halo_wk[9];        // halo variant: weight column offset of tap (dx, dy) at [3 (dx+1) + (dy+1)]
   int ntaps;
   int tap_map[kConvMaxTaps];
   int tap_dy[kConvMaxTaps];
@@ -34,7 +36,7 @@ struct ConvGemmParams {
   const float* bias2;         // second per-channel bias (timestep projection), same rule
   int bias_rows;
   int debug;                  // profiling aid: 1 = exit at entry, 2 = setup/teardown only
-  int nt;                     // pixel tiles per work item (1 or 2)
+  int nt;                     // kernel variant: 1 / 2 pixel tiles per item, 3 = wide, 4 = halo
   int ksplit;                 // K-loop split factor (1 = none)
   float* partial;             // split-K partial tiles [tile][split][128][block_n]
   int* counters;              // split-K arrival [tile] and done [counter_stride + tile] counters

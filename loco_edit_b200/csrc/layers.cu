@@ -164,12 +164,15 @@ struct GnGeom {
 // A thread owns one channel quad of `pv` pixels and walks ALL batch rows of those pixels: the
 // primal value is loaded (and its sigmoid evaluated) once and shared by the k tangent / cotangent
 // rows, and the loads of a row chunk are issued together.
-inline GnGeom gn_geom(int C, long long HW, int pv) {
+// `resident` = blocks of the kernel that fit the GPU at once (occupancy x SMs): the grid is one
+// full wave of persistent blocks that stride over the pixel chunks.
+inline GnGeom gn_geom(int C, long long HW, int resident) {
   GnGeom g;
   g.block = gn_block_dim(C);
   g.pstep = g.block / (C / 4);
-  g.ppb = g.pstep * pv;
-  g.nblk = (int)((HW + g.ppb - 1) / g.ppb);
+  g.ppb = g.pstep;
+  const long long nchunks = (HW + g.pstep - 1) / g.pstep;
+  g.nblk = (int)(nchunks < resident ? nchunks : resident);
   return g;
 }
 
@@ -200,7 +203,10 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   const int pstep = blockDim.x / cvn;
   const int g = (cv * 4) / cg;
   const long long HW = (long long)x.H * x.W;
-  const long long pbase = (long long)blockIdx.x * (pstep * pv) + prow;
+  // persistent blocks: chunk c covers pixels [c * pstep, (c + 1) * pstep); a block walks the chunks
+  // c = blockIdx.x, blockIdx.x + gridDim.x, ... so the grid is one full wave and has no tail
+  const long long nchunks = (HW + pstep - 1) / pstep;
+  (void)pv;
   const View& rows = (MODE == 0) ? x : gy;
   const int N = rows.N;
   const bool jvp = (MODE == 0) && (n_primal < N);   // row 0 primal, rows 1.. tangents
@@ -221,8 +227,8 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     float s1[kRC], s2[kRC];
 #pragma unroll
     for (int r = 0; r < kRC; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
-    for (int j = 0; j < pv; ++j) {
-      const long long p = pbase + (long long)j * pstep;
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const long long p = ch * pstep + prow;
       if (p >= HW) break;
       const int y = (int)(p / x.W), xx = (int)(p % x.W);
       const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
@@ -328,9 +334,10 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   float2 mr0 = make_float2(0.f, 1.f);
   if (jvp || MODE == 1) mr0 = (MODE == 0) ? tab[0][g] : mean_rstd(pstats + g * 2, cnt, eps);
 
-  const long long pbase = (long long)blockIdx.x * (pstep * pv) + prow;
-  for (int j = 0; j < pv; ++j) {
-    const long long p = pbase + (long long)j * pstep;
+  const long long nchunks = (HW + pstep - 1) / pstep;
+  (void)pv;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long p = ch * pstep + prow;
     if (p >= HW) break;
     const int y = (int)(p / x.W), xx = (int)(p % x.W);
     const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
@@ -604,6 +611,19 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   return 0;
 }
 
+// resident blocks of each GroupNorm kernel at its block size (queried once)
+template <typename K>
+static int gn_resident(K kernel, int block, int* cache) {
+  if (*cache == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    *cache = per_sm * num_sms();
+  }
+  return *cache;
+}
+static int g_res_stats0[2], g_res_stats1[2], g_res_apply0[2], g_res_apply1[2];   // [block == 192]
+
 // All kernels of the U-Net programs ask for the same (maximum shared memory) L1/smem split as the
 // tcgen05 conv kernel, so the SMs never have to re-partition between consecutive launches.
 int layers_init() {
@@ -618,27 +638,28 @@ int layers_init() {
   LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
   LOCO_CARVE(scale_shift_affine_kernel);
 #undef LOCO_CARVE
+  // occupancy queries up front (never inside a stream capture)
+  for (int b = 0; b < 2; ++b) {
+    const int bd = b ? 192 : 256;
+    gn_resident(gn_stats_kernel<0>, bd, &g_res_stats0[b]);
+    gn_resident(gn_stats_kernel<1>, bd, &g_res_stats1[b]);
+    gn_resident(gn_apply_kernel<0>, bd, &g_res_apply0[b]);
+    gn_resident(gn_apply_kernel<1>, bd, &g_res_apply1[b]);
+  }
   done = true;
   return 0;
 }
 
-static int gn_pv(int C, long long HW) {
-  // pixels per thread: enough blocks for >= 2 waves on large tensors, short chains on small ones
-  const int pstep = gn_block_dim(C) / (C / 4);
-  const long long blocks1 = (HW + pstep - 1) / pstep;
-  int pv = (int)(blocks1 / (148 * 4));
-  if (pv < 1) pv = 1;
-  if (pv > 8) pv = 8;
-  return pv;
-}
+
 
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
-  const int pv = gn_pv(x.C, (long long)x.H * x.W);
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, pv);
+  const int bd = gn_block_dim(x.C);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W,
+                           gn_resident(gn_stats_kernel<0>, bd, &g_res_stats0[bd == 192]));
   ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C, s);
   gn_stats_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
-                                               stats, pv);
+                                               stats, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -647,11 +668,12 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
   LOCO_TRY(check_gn_view(x, "gn_apply_fwd"));
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
   LOCO_REQUIRE(x.N <= kGnMaxRows, "gn_apply_fwd: batch %d > %d rows", x.N, kGnMaxRows);
-  const int pv = gn_pv(x.C, (long long)x.H * x.W);
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, pv);
+  const int bd = gn_block_dim(x.C);
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W,
+                           gn_resident(gn_apply_kernel<0>, bd, &g_res_apply0[bd == 192]));
   ProfScope prof(1, 8.0 * x.N * x.H * x.W * x.C, s);
   gn_apply_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
-                                               silu, round_out, nullptr, 0, 0, 0, 0, y, pv);
+                                               silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -659,10 +681,11 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
                  float eps, int silu, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
-  const int pv = gn_pv(xp.C, (long long)xp.H * xp.W);
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, pv);
+  const int bd = gn_block_dim(xp.C);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W,
+                           gn_resident(gn_stats_kernel<1>, bd, &g_res_stats1[bd == 192]));
   ProfScope prof(1, 4.0 * (gy.N + 1) * gy.H * gy.W * gy.C, s);
-  gn_stats_kernel<1><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, pv);
+  gn_stats_kernel<1><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -674,12 +697,13 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   LOCO_TRY(check_gn_view(gx, "gn_apply_vjp(gx)"));
   if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
   LOCO_REQUIRE(gy.N <= kGnMaxRows, "gn_apply_vjp: batch %d > %d rows", gy.N, kGnMaxRows);
-  const int pv = gn_pv(xp.C, (long long)xp.H * xp.W);
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, pv);
+  const int bd = gn_block_dim(xp.C);
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W,
+                           gn_resident(gn_apply_kernel<1>, bd, &g_res_apply1[bd == 192]));
   ProfScope prof(1, 4.0 * gy.H * gy.W * gy.C * (1 + gy.N * (2 + (addend ? 1 : 0) + (accumulate ? 1 : 0))), s);
   gn_apply_kernel<1><<<g.nblk, g.block, 0, s>>>(
       xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, pv);
+      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

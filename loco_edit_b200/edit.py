@@ -199,8 +199,11 @@ class EditUncondDiffusion(object):
             raise NotImplementedError("the uncond hot path runs in fp32/TF32 (all reference scripts use --dtype fp32)")
         if unet is None:
             from .unet import B200UNet
-            from .weights import DDPM256, random_state_dict
-            arch = dict(DDPM256, resolution=self.image_size)
+            from .weights import DDPM256, P2_256, random_state_dict
+            # the reference picks the network family by model name (utils/utils.py:95-131):
+            # "*_P2" -> guided-diffusion UNetModel(P2_DICT); "*_HF" -> the DDPM U-Net architecture
+            base = P2_256 if self.model_name.endswith("_P2") else DDPM256
+            arch = dict(base, resolution=self.image_size)
             wp = getattr(args, "weights_path", "")
             sd = torch.load(wp, map_location="cpu") if wp else random_state_dict(arch, seed=1234)
             unet = B200UNet(arch, sd, device=self.device)

@@ -18,6 +18,12 @@ CASES = [
     (0, 1, 8, 8, 512, 512), (0, 6, 32, 32, 256, 256), (0, 1, 32, 32, 256, 256), (0, 6, 64, 64, 256, 256),
     (0, 1, 64, 64, 256, 256), (0, 1, 128, 128, 128, 128), (0, 6, 128, 128, 128, 128), (0, 1, 256, 256, 128, 128),
     (0, 5, 256, 256, 128, 128), (0, 6, 256, 256, 128, 128), (0, 6, 256, 256, 256, 128), (1, 6, 256, 256, 256, 128),
+    # batch-edit DDIM passes (B = 8 inversion / forward, B = 40 edited latents)
+    (0, 8, 256, 256, 128, 128), (0, 40, 256, 256, 128, 128), (0, 8, 256, 256, 256, 128), (0, 8, 128, 128, 128, 128),
+    (0, 40, 128, 128, 128, 128), (0, 8, 128, 128, 256, 256), (0, 8, 64, 64, 256, 256), (0, 40, 64, 64, 256, 256),
+    (0, 8, 64, 64, 512, 256), (0, 8, 32, 32, 256, 256), (0, 40, 32, 32, 256, 256), (0, 8, 32, 32, 512, 512),
+    (0, 8, 16, 16, 512, 512), (0, 40, 16, 16, 512, 512), (0, 8, 16, 16, 1024, 512), (0, 8, 8, 8, 512, 512),
+    (0, 40, 8, 8, 512, 512), (0, 8, 8, 8, 1024, 512), (1, 8, 16, 16, 512, 1536), (1, 40, 16, 16, 512, 512),
 ]
 print("kind N HxW Cin->Cout | ksplit grid ms TFLOP/s | (no split) ms")
 for kind, N, H, W, Cin, Cout in CASES:
