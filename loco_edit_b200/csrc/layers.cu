@@ -149,6 +149,150 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
   }
 }
 
+// ---- fast paths for C == 128 (every shipped architecture: conv_in / conv_out have `ch` = 128
+// channels on the wide side).  A warp owns a strip of 4 output pixels of one image row; lane l owns
+// channels [4l, 4l+4).  The 3 x 6 input window of the strip is loaded once and the 27 weight vectors
+// are read from shared memory once per strip (not once per pixel), which turns the old
+// shared-memory-bound kernels into HBM-streaming ones.
+constexpr int kStrip = 4;
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// sum 16 per-lane values over the 32 lanes with a halving butterfly (31 shuffles instead of 80):
+// afterwards lane l holds the total of value (l >> 1).
+template <int OFF, int HALF>
+__device__ __forceinline__ void butterfly_step(float (&v)[16], int lane) {
+  const bool hi = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const float send = hi ? v[i] : v[i + HALF];
+    const float keep = hi ? v[i + HALF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+  butterfly_step<16, 8>(v, lane);
+  butterfly_step<8, 4>(v, lane);
+  butterfly_step<4, 2>(v, lane);
+  butterfly_step<2, 1>(v, lane);
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(256, 2)
+edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __restrict__ bias,
+                      int bias_rows, float* __restrict__ out3, int flip) {
+  __shared__ float4 sw[27 * 32];   // [tap][j][channel quad]
+  const int H = in.H, W = in.W;
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(Wr)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int sx = W / kStrip;
+  const long long nstrips = (long long)in.N * H * sx;
+  for (long long st = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); st < nstrips;
+       st += (long long)gridDim.x * wpb) {
+    const int x0 = (int)(st % sx) * kStrip;
+    const int y = (int)((st / sx) % H);
+    const int n = (int)(st / ((long long)sx * H));
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    // input window rows y-1..y+1, columns x0-1..x0+4 (zero outside the image), one row at a time
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      float4 win[kStrip + 2];
+#pragma unroll
+      for (int c = 0; c < kStrip + 2; ++c) {
+        const int xx = x0 + c - 1;
+        win[c] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                     ? ld4(in.ptr + (long long)n * in.sN + (long long)yy * in.sH + (long long)xx * in.sW + lane * 4)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // window offset (r, c) <-> filter tap: forward (dy,dx) = (r-1,c-1) is tap (r,c); the flipped
+        // (data-gradient) form reads in(y - (r'-1), x - (c'-1)), i.e. tap (2-r, 2-c)
+        const int t = flip ? (2 - r) * 3 + (2 - c) : r * 3 + c;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 w = sw[(t * 3 + j) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < kStrip; ++q) {
+            const float4 v = win[q + c];
+            acc[q * 3 + j] += (v.x * w.x + v.y * w.y) + (v.z * w.z + v.w * w.w);
+          }
+        }
+      }
+    }
+    const float tot = butterfly16(acc, lane);
+    const int idx = lane >> 1;           // value index q * 3 + j
+    if ((lane & 1) == 0 && idx < kStrip * 3) {
+      const int q = idx / 3, j = idx % 3;
+      const bool ub = bias && n < bias_rows;
+      out3[((long long)n * 3 + j) * H * W + (long long)y * W + x0 + q] = tot + (ub ? bias[j] : 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ We,
+                      const float* __restrict__ bias, int bias_rows, View out, int flip,
+                      int round_out) {
+  __shared__ float4 sw[27 * 32];   // [tap][j][channel quad]
+  const int H = out.H, W = out.W;
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(We)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int sx = W / kStrip;
+  const long long nstrips = (long long)out.N * H * sx;
+  const float4 b4 = bias ? ld4(bias + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long st = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); st < nstrips;
+       st += (long long)gridDim.x * wpb) {
+    const int x0 = (int)(st % sx) * kStrip;
+    const int y = (int)((st / sx) % H);
+    const int n = (int)(st / ((long long)sx * H));
+    const float* src = in3 + (long long)n * 3 * H * W;
+    // lanes 0..17 each fetch one (row, column) of the 3 x 6 window of the three image planes
+    float wv[3] = {0.f, 0.f, 0.f};
+    if (lane < 3 * (kStrip + 2)) {
+      const int r = lane / (kStrip + 2), c = lane % (kStrip + 2);
+      const int yy = y + r - 1, xx = x0 + c - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) wv[j] = __ldg(src + ((long long)j * H + yy) * W + xx);
+      }
+    }
+    float4 acc[kStrip];
+    const bool ub = bias && n < bias_rows;
+#pragma unroll
+    for (int q = 0; q < kStrip; ++q) acc[q] = ub ? b4 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int t = flip ? (2 - r) * 3 + (2 - c) : r * 3 + c;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 w = sw[(t * 3 + j) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < kStrip; ++q) {
+            const float v = __shfl_sync(0xffffffffu, wv[j], r * (kStrip + 2) + q + c);
+            acc[q].x = fmaf(v, w.x, acc[q].x); acc[q].y = fmaf(v, w.y, acc[q].y);
+            acc[q].z = fmaf(v, w.z, acc[q].z); acc[q].w = fmaf(v, w.w, acc[q].w);
+          }
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < kStrip; ++q) {
+      float4 o = acc[q];
+      if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      *reinterpret_cast<float4*>(out.ptr + (long long)n * out.sN + (long long)y * out.sH +
+                                 (long long)(x0 + q) * out.sW + lane * 4) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm
 // ------------------------------------------------------------------------------------------------
@@ -176,7 +320,6 @@ inline GnGeom gn_geom(int C, long long HW, int resident) {
   return g;
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float fast_sigmoid(float u) { return __fdividef(1.0f, 1.0f + __expf(-u)); }
 
 // (mean, rstd) of a primal row's group from its (sum x, sum x^2)
@@ -588,6 +731,14 @@ int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t 
 
 int edge_conv_expand(const float* in3, const float* We, const float* bias, int bias_rows, View out,
                      int flip, int round_out, cudaStream_t s) {
+  if (out.C == 128 && out.W % kStrip == 0) {
+    const long long nstrips = (long long)out.N * out.H * (out.W / kStrip);
+    ProfScope prof(2, 0, s);
+    edge_expand128_kernel<<<grid_for((nstrips + 7) / 8, 1, num_sms() * 4), 256, 0, s>>>(
+        in3, We, bias, bias_rows, out, flip, round_out);
+    count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   LOCO_REQUIRE(out.C % 4 == 0 && 256 % (out.C / 4) == 0, "edge_conv_expand: C=%d unsupported", out.C);
   const int ppb = 256 / (out.C / 4);
   const long long HW = (long long)out.H * out.W;
@@ -601,6 +752,14 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
 }
 int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3,
                      int flip, cudaStream_t s) {
+  if (in.C == 128 && in.W % kStrip == 0) {
+    const long long nstrips = (long long)in.N * in.H * (in.W / kStrip);
+    ProfScope prof(2, 0, s);
+    edge_reduce128_kernel<<<grid_for((nstrips + 7) / 8, 1, num_sms() * 4), 256, 0, s>>>(
+        in, Wr, bias, bias_rows, out3, flip);
+    count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   LOCO_REQUIRE(in.C % 4 == 0, "edge_conv_reduce: C=%d unsupported", in.C);
   const long long HW = (long long)in.H * in.W;
   dim3 grid((unsigned)((HW + 8 * kEdgeIters - 1) / (8 * kEdgeIters)), in.N);
@@ -634,6 +793,7 @@ int layers_init() {
   LOCO_CARVE(gn_stats_kernel<0>); LOCO_CARVE(gn_stats_kernel<1>);
   LOCO_CARVE(gn_apply_kernel<0>); LOCO_CARVE(gn_apply_kernel<1>);
   LOCO_CARVE(edge_expand_kernel); LOCO_CARVE(edge_reduce_kernel);
+  LOCO_CARVE(edge_expand128_kernel); LOCO_CARVE(edge_reduce128_kernel);
   LOCO_CARVE(upsample2x_kernel); LOCO_CARVE(sumpool2x_kernel); LOCO_CARVE(add_views_kernel);
   LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
   LOCO_CARVE(scale_shift_affine_kernel);

@@ -1,5 +1,5 @@
 """Short profiling workload for ncu: one fused rank-5 JVP pass, one rank-5 VJP pass and one plain
-B=1 forward of the DDPM-256 U-Net (the three launch programs every edit is made of).
+B=1 forward and one B=8 forward of the DDPM-256 U-Net (the launch programs every edit is made of).
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
         python profiles/profile_step.py
 """
@@ -19,10 +19,13 @@ x = torch.randn(1 + k, 3, 256, 256, device=dev)
 g = torch.randn(k, 3, 256, 256, device=dev)
 p = net.plan(1, k, k)
 p1 = net.plan(1)
+p8 = net.plan(8)
+x8 = torch.randn(8, 3, 256, 256, device=dev)
 reps = int(os.environ.get("REPS", "1"))
 for _ in range(reps):
     p.forward(x, 595.3636)
     p.vjp(g)
     p1.forward(x[:1].contiguous(), 595.3636)
+    p8.forward(x8, 595.3636)
 torch.cuda.synchronize()
 print("done")
