@@ -56,6 +56,31 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return d;
 }
 
+// L2 prefetch of the epilogue's read-side tile (residual addend and/or the accumulate target) of a
+// 128-pixel tile: issued by the epilogue warps before they wait for the accumulator, so the DRAM
+// latency of those reads is hidden behind the MMAs of the same tile.  512-byte pixel rows of
+// block_n fp32 channels = block_n / 32 lines; thread `t` (0..127) takes pixel row t.
+__device__ __forceinline__ void prefetch_l2(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_epilogue_tile(const ConvGemmParams& p, int tx, int ty, int tn,
+                                                       int co0, int t) {
+  if (p.addend == nullptr && !p.accumulate) return;
+  const int R = t;
+  const int x = tx * p.TW + (R & (p.TW - 1));
+  const int y = ty * p.TH + ((R >> p.log_tw) & (p.TH - 1));
+  const int n = tn * p.TN + (R >> (p.log_tw + p.log_th));
+  if (n >= p.N || y >= p.Ho || x >= p.Wo) return;
+  if (p.addend) {
+    const float* a = p.addend + (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0;
+    for (int c = 0; c < p.block_n; c += 32) prefetch_l2(a + c);
+  }
+  if (p.accumulate) {
+    const float* o = p.out + (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
+    for (int c = 0; c < p.block_n; c += 32) prefetch_l2(o + c);
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -222,6 +247,14 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int split = w / total_units;
       const int um = unit % units_m;
       const int co0 = (unit / units_m) * p.block_n;
+      if (ksplit == 1) {
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt) {
+          const int tm = um * NT + jt;
+          prefetch_epilogue_tile(p, tm % p.tiles_x, (tm / p.tiles_x) % p.tiles_y,
+                                 tm / (p.tiles_x * p.tiles_y), co0, (int)threadIdx.x - 128);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -456,6 +489,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(HALO ? &p.hmap : &p.amap[0]);
     prefetch_tmap(&p.bmap);
+    if (HALO && p.c2_chunks > 0) { prefetch_tmap(&p.hmap2); prefetch_tmap(&p.bmap2); }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kNFull; ++i) {
@@ -519,6 +553,18 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
         }
+        // fused 1x1 shortcut: one 16 x 16 pixel box of the second input + one weight tile per slab
+        for (int cc = 0; cc < p.c2_chunks; ++cc) {
+          mbar_wait(&empty_bar[as], aph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[as], 2 * kABytes);
+          tma_load_4d(smem + as * kHaloABytes, &p.hmap2, &full_bar[as], cc * kConvBlockK, x0, y0, n0);
+          if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
+          uint64_t* fb = &full_bar[kHaloStagesA + bs];
+          mbar_wait(&empty_bar[kHaloStagesA + bs], bph ^ 1);
+          mbar_arrive_expect_tx(fb, kBBytes);
+          tma_load_2d(smem_w + bs * kBBytes, &p.bmap2, fb, cc * kConvBlockK, co0);
+          if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -569,6 +615,22 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
             if (p.debug != 4) umma_commit(&empty_bar[as]);
             if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
           }
+        }
+        for (int cc = 0; cc < p.c2_chunks; ++cc) {        // fused 1x1 shortcut slabs
+          mbar_wait(&full_bar[as], aph);
+          mbar_wait(&full_bar[kHaloStagesA + bs], bph);
+          tc_fence_after();
+          const uint64_t pd = pdesc0 + (uint64_t)as * (uint64_t)(kHaloABytes >> 4);
+          const uint64_t wdesc = wdesc0 + (uint64_t)bs * (uint64_t)(kBBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 8; ++k) {
+            umma_tf32(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+            first = 1;
+          }
+          umma_commit(&empty_bar[kHaloStagesA + bs]);
+          umma_commit(&empty_bar[as]);
+          if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
+          if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
         }
         if (p.debug == 4) mbar_arrive(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
@@ -666,6 +728,21 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       if (p.bias2) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co));
         bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+      }
+#pragma unroll
+      for (int jt = 0; jt < NT; ++jt) {
+        int tx, ty, tn;
+        if (HALO) {
+          tx = um % p.tiles_x;
+          ty = ((um / p.tiles_x) % half_y) * 2 + jt;
+          tn = um / (p.tiles_x * half_y);
+        } else {
+          const int tm = um * NT + jt;
+          tx = tm % p.tiles_x;
+          ty = (tm / p.tiles_x) % p.tiles_y;
+          tn = tm / (p.tiles_x * p.tiles_y);
+        }
+        prefetch_epilogue_tile(p, tx, ty, tn, (w / units_m) * 128, (int)threadIdx.x - 128);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -871,6 +948,20 @@ int fill_common(ConvGemmParams& p, const ConvProblem& prob, int N, int Ho, int W
 
 }  // namespace
 
+static int conv_variant_cap() {
+  // LOCO_CONV_NT caps the variant (profiling aid): 1 = one tile per item, 2 = two tiles sharing
+  // the weight tile, 3 = "wide" (operand-swapped, N = 256 pixels), default 4 = halo where eligible
+  const char* e = getenv("LOCO_CONV_NT");
+  return e ? atoi(e) : 4;
+}
+
+bool conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
+  if (kind != CONV_3x3 && kind != CONV_3x3_DGRAD) return false;
+  if (Cout % 128 != 0 || W % 16 != 0 || H % 16 != 0 || conv_variant_cap() < 4) return false;
+  const long long tiles = (long long)N * (H / 8) * (W / 16) * (Cout / 128);
+  return tiles >= 4LL * num_sms();
+}
+
 int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
   memset(L, 0, sizeof(*L));
   const View& in = prob.in;
@@ -974,10 +1065,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     // two pixel tiles per item (shared weight tile) when that still fills >= 2 waves of the GPU
     p.nt = (ks == 1 && (p.tiles_x * p.tiles_y * p.tiles_n) % 2 == 0 && tiles >= 4 * sms) ? 2 : 1;
     {
-      // LOCO_CONV_NT caps the variant (profiling aid): 1 = one tile per item, 2 = two tiles sharing
-      // the weight tile, 3 = "wide" (operand-swapped, N = 256 pixels), default 4 = halo where eligible
-      const char* e = getenv("LOCO_CONV_NT");
-      const int cap = e ? atoi(e) : 4;
+      const int cap = conv_variant_cap();
       if (cap == 1) p.nt = 1;
       if (p.nt == 2 && p.block_n == 128 && cap >= 3) {
         p.nt = 3;
@@ -1000,6 +1088,24 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
               for (int t = 0; t < 9; ++t)
                 if (p.tap_dx[t] == dxi - 1 && p.tap_dy[t] == dyi - 1) p.halo_wk[dxi * 3 + dyi] = p.tap_wk[t];
           p.nt = 4;
+          LOCO_REQUIRE(conv_halo_eligible(prob.kind, p.N, p.Ho, p.Wo, p.Cout), "conv: halo eligibility mismatch");
+          if (prob.in2 != nullptr) {
+            const View& i2 = *prob.in2;
+            LOCO_REQUIRE(i2.N == in.N && i2.H == in.H && i2.W == in.W && i2.C == prob.Kc2 &&
+                             prob.Kc2 % kConvBlockK == 0 && prob.wpack2 != nullptr,
+                         "conv: fused shortcut input mismatch");
+            cuuint64_t d2[4] = {(cuuint64_t)i2.C, (cuuint64_t)i2.W, (cuuint64_t)i2.H, (cuuint64_t)i2.N};
+            cuuint64_t s2[3] = {(cuuint64_t)i2.sW * 4, (cuuint64_t)i2.sH * 4, (cuuint64_t)i2.sN * 4};
+            cuuint32_t b2[4] = {(cuuint32_t)kConvBlockK, 16, 16, 1};
+            LOCO_REQUIRE(((uintptr_t)i2.ptr & 15) == 0 && s2[0] % 16 == 0 && s2[1] % 16 == 0 && s2[2] % 16 == 0,
+                         "conv: fused shortcut input not 16B aligned");
+            r = fn(&p.hmap2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, i2.ptr, d2, s2, b2, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(shortcut) failed: %d", (int)r);
+            LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 128));
+            p.c2_chunks = prob.Kc2 / kConvBlockK;
+          }
         }
       }
     }
@@ -1013,7 +1119,9 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     p.counter_stride = prob.splitk_max_tiles;
     const int items = tiles * ks / (p.nt >= 3 ? 2 : p.nt);
     L->grid[i] = items < sms ? items : sms;
-    L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * p.ntaps * p.c_chunks * kConvBlockK;
+    L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * (p.ntaps * p.c_chunks + p.c2_chunks) * kConvBlockK;
+    LOCO_REQUIRE(prob.in2 == nullptr || p.c2_chunks > 0,
+                 "conv: a fused 1x1 shortcut needs the halo variant (check conv_halo_eligible)");
   }
   return 0;
 }

@@ -17,6 +17,12 @@ struct ConvGemmParams {
   CUtensorMap bmap;      // packed weights: dims (Ktot, Cout), box (32, block_n)
   CUtensorMap hmap;      // halo variant: activation map with box (32, 16, 18, 1)
   int halo_wk[9];        // halo variant: weight column offset of tap (dx, dy) at [3 (dx+1) + (dy+1)]
+  // halo variant, fused 1x1 shortcut (ResnetBlock nin_shortcut / skip_connection): the K loop is
+  // extended by the channels of a second input through a second weight matrix, so that
+  // out = conv3x3(in) + conv1x1(in2) is one accumulation and the shortcut tensor never exists
+  CUtensorMap hmap2;     // second input, box (32, 16, 16, 1)
+  CUtensorMap bmap2;     // its weights: dims (C2, Cout), box (32, 128)
+  int c2_chunks;         // channels of the second input / 32 (0 = no fused shortcut)
   int ntaps;
   int tap_map[kConvMaxTaps];
   int tap_dy[kConvMaxTaps];
@@ -69,6 +75,10 @@ struct ConvProblem {
   const float* bias2 = nullptr;
   int bias_rows = 0;
   const View* addend = nullptr;
+  // optional fused 1x1 shortcut (only honoured by the halo variant: check conv_halo_eligible first)
+  const View* in2 = nullptr;
+  const float* wpack2 = nullptr;   // [Ngemm][Kc2] K-major, tf32-rounded
+  int Kc2 = 0;
   int accumulate = 0;
   int round_out = 0;
   double* st_ptr[2] = {nullptr, nullptr};
@@ -90,6 +100,9 @@ struct ConvLaunch {
 };
 
 int conv_init();   // one-time kernel attribute setup (must not happen inside a stream capture)
+// true iff conv_prepare will pick the halo variant for a stride-1 3x3 (fprop or dgrad) of this
+// shape: a pure function of the shape, so plan builders can decide fusions during the size query
+bool conv_halo_eligible(int kind, int N, int H, int W, int Cout);
 int conv_prepare(const ConvProblem& prob, ConvLaunch* out);
 int conv_run(const ConvLaunch& l, cudaStream_t stream);
 

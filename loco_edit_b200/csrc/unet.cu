@@ -547,8 +547,9 @@ int Plan::build(float* workspace) {
   auto mk_conv = [&](ConvProblem prob, bool is_bwd) -> ConvLaunch* {
     I.launches.emplace_back();
     ConvLaunch* L_ = &I.launches.back();
-    const double fl = 2.0 * prob.out.N * prob.out.H * prob.out.W * (double)prob.Ngemm * prob.Kc *
-                      (prob.kind == CONV_1x1 ? 1 : 9) / (prob.kind == CONV_3x3_S2_DGRAD ? 4 : 1);
+    const double fl = 2.0 * prob.out.N * prob.out.H * prob.out.W * (double)prob.Ngemm *
+                      ((double)prob.Kc * (prob.kind == CONV_1x1 ? 1 : 9) / (prob.kind == CONV_3x3_S2_DGRAD ? 4 : 1) +
+                       prob.Kc2);
     (is_bwd ? vjp_flops : fwd_flops) += fl;
     prob.splitk_partial = splitk_partial; prob.splitk_partial_floats = splitk_floats;
     prob.splitk_counters = splitk_counters; prob.splitk_max_tiles = splitk_tiles;
@@ -558,11 +559,14 @@ int Plan::build(float* workspace) {
     }
     return L_;
   };
+  // in2 / c2: optional fused 1x1 shortcut (out = conv(in) + conv1x1_{c2}(in2)), halo variant only
   auto conv_fwd = [&](int kind, View in, View out, const ConvRef& c, const float* bias2,
-                      const View* addend, const TH* out_th = nullptr, StatTarget extra = StatTarget()) {
+                      const View* addend, const TH* out_th = nullptr, StatTarget extra = StatTarget(),
+                      const View* in2 = nullptr, const ConvRef* c2 = nullptr) {
     ConvProblem p;
     p.kind = kind; p.in = in; p.out = out; p.wpack = dry ? nullptr : M.w(c.wf);
     p.Kc = c.cin; p.Ngemm = c.cout;
+    if (in2 != nullptr) { p.in2 = in2; p.wpack2 = dry ? nullptr : M.w(c2->wf); p.Kc2 = c2->cin; }
     p.bias = dry ? nullptr : M.w(c.bias); p.bias2 = bias2; p.bias_rows = NP;
     p.addend = addend; p.accumulate = 0; p.round_out = 1;
     if (fuse_stats) {
@@ -695,7 +699,11 @@ int Plan::build(float* workspace) {
     View a2 = Tf(Ho, Wo, R.cout);
     double* st2 = gn_fwd(h1, R.n2, 1, 1, a2, t2.st, fuse_stats, aff);
     View sc;
-    if (R.has_nin) {
+    if (R.has_nin && conv_halo_eligible(CONV_3x3, NB, Ho, Wo, R.cout)) {
+      // the 1x1 shortcut rides the K loop of conv2 (its bias goes in the second bias slot)
+      conv_fwd(CONV_3x3, a2, out.v, R.c2, dry ? nullptr : M.w(R.nin.bias), nullptr, &out, StatTarget(),
+               &xr, &R.nin);
+    } else if (R.has_nin) {
       sc = Tf(Ho, Wo, R.cout);
       conv_fwd(CONV_1x1, xr, sc, R.nin, nullptr, nullptr);
       conv_fwd(CONV_3x3, a2, out.v, R.c2, nullptr, &sc, &out);
