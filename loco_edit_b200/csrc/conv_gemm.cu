@@ -955,11 +955,31 @@ static int conv_variant_cap() {
   return e ? atoi(e) : 4;
 }
 
+// two-pixel-tile variants (NT = 2, wide, halo) are used from this many 128-pixel tiles per SM on
+static int conv_two_tile_min() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("LOCO_CONV_MIN_TILES_PER_SM");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 bool conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
   if (kind != CONV_3x3 && kind != CONV_3x3_DGRAD) return false;
   if (Cout % 128 != 0 || W % 16 != 0 || H % 16 != 0 || conv_variant_cap() < 4) return false;
   const long long tiles = (long long)N * (H / 8) * (W / 16) * (Cout / 128);
-  return tiles >= 4LL * num_sms();
+  const long long sms = num_sms();
+  if (tiles >= (long long)conv_two_tile_min() * sms) return true;
+  // Below that, weigh the wave quantisation of the two granularities: a halo item (256 pixels)
+  // costs 1 unit, a one-tile item (128 pixels, twice the operand traffic per FLOP) 0.62 units
+  // (measured on 64x64 and 256x256 layers, profiles/README.md); split-K territory stays one-tile.
+  const long long items = tiles / 2;
+  if (tiles * 2 <= sms || items * 2 < sms) return false;
+  const double t_halo = (double)((items + sms - 1) / sms);
+  const double t_one = 0.62 * (double)((tiles + sms - 1) / sms);
+  return t_halo <= t_one;
 }
 
 int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
@@ -1063,7 +1083,10 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
       while (ks > 1 && (long long)tiles * ks * kConvBlockM * p.block_n > prob.splitk_partial_floats) --ks;
     }
     // two pixel tiles per item (shared weight tile) when that still fills >= 2 waves of the GPU
-    p.nt = (ks == 1 && (p.tiles_x * p.tiles_y * p.tiles_n) % 2 == 0 && tiles >= 4 * sms) ? 2 : 1;
+    const bool halo_shape = (prob.kind == CONV_3x3 || prob.kind == CONV_3x3_DGRAD) && ks == 1 &&
+                            conv_halo_eligible(prob.kind, p.N, p.Ho, p.Wo, p.Cout);
+    p.nt = (ks == 1 && (p.tiles_x * p.tiles_y * p.tiles_n) % 2 == 0 &&
+            (tiles >= conv_two_tile_min() * sms || halo_shape)) ? 2 : 1;
     {
       const int cap = conv_variant_cap();
       if (cap == 1) p.nt = 1;
