@@ -271,11 +271,15 @@ def run_ours(args):
         lib.loco_profile_enable(0)
         conv_tflops = work[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        roof = {"bound": "tensor", "kernel": "conv_gemm_tf32_kernel", "achieved": conv_tflops,
+        roof = {"bound": "tensor",
+                "kernel": "tcgen05 implicit-GEMM conv family (conv_gemm_tf32_wide_kernel<halo> on the "
+                          ">=64^2 layers, conv_gemm_tf32_kernel on the small ones)",
+                "achieved": conv_tflops,
                 "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                # dram__bytes_read+write of the dominant launch (3x3 128->128 at 256^2, 6 rows; algorithmic
-                # 403 MB) from the committed ncu --set full capture, profiles/r1_conv_gemm_ncu_full_raw.csv
-                "traffic": 360.6e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
+                # dram__bytes_read+write of the dominant launch (halo variant, 3x3 128->128 at 256^2,
+                # 6 rows; algorithmic 403 MB) from the committed ncu --set full capture,
+                # profiles/r1_conv_halo_ncu_full_raw.csv
+                "traffic": 352.2e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
                 "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
@@ -314,6 +318,37 @@ def run_ours(args):
             torch.cuda.synchronize()
             probes["fwd_b%d_ms" % bsz] = a.elapsed_time(b) / reps
 
+    # ---- BASELINE config 2 proper: the P2 / guided-diffusion U-Net with the FFHQ_P2 script settings
+    # (edit_t 0.2, rank 3 + null 5, scale 12, 1 step; scripts/main_hf_null_space_projection_FFHQ_P2.sh),
+    # one warm-up and one timed batch of BATCH image/mask pairs on rank 0 (reported as an extra key) ----
+    p2 = None
+    if rank == 0 and not args.no_p2:
+        from loco_edit_b200.weights import P2_256
+        del pipe
+        unet._plans.clear()
+        torch.cuda.empty_cache()
+        net2 = B200UNet(P2_256, random_state_dict(P2_256, seed=1234), device=dev)
+        pipe2 = EditPipeline(net2, k=3, k_null=5, edit_t=0.2, n_iter=N_ITER, scale=12.0, num_step=1, vis_num=2)
+        xs, ms_ = host_inputs(rank * 1000 + 300)
+        xs, ms_ = xs.to(dev), ms_.to(dev)
+        gen.manual_seed(5000)
+        pipe2.edit_batch_device(xs, ms_, gen=gen)
+        torch.cuda.synchronize()
+        e0.record()
+        out2 = pipe2.edit_batch_device(xs, ms_, gen=gen)["images"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1)
+        f_p2 = 0.3879e12
+        fwd_eq = 98 + 79 + N_ITER * (1 + 2 * (3 + 5)) + 20 * 3
+        p2 = {"value": BATCH / (ms2 * 1e-3), "unit": "edits/s", "ms_per_step": ms2,
+              "workload": "P2 U-Net (P2_DICT, 93.6 M params, random init), %d pairs per step, FFHQ_P2 script "
+                          "settings: t=0.2T, rank 3 + null 5, N=12, 98+79+20 DDIM steps, 3 edited latents" % BATCH,
+              "fwd_equivalents_executed": fwd_eq,
+              "achieved_tflops": BATCH * fwd_eq * f_p2 / (ms2 * 1e-3) / 1e12,
+              "finite": bool(torch.isfinite(out2).all())}
+        del pipe2, net2
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -346,7 +381,7 @@ def run_ours(args):
             "e2e": {"value": n_edits / (ms_e2e * 1e-3), "unit": "edits/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "p2_ffhq": p2,
         }
         if probes:
             line.update(probes)
@@ -363,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="image/mask pairs edited together per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2", action="store_true", help="skip the extra P2 / FFHQ_P2 batch-edit measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -173,3 +173,75 @@ def test_full_size_p2_256_properties(dev):
     scale = deps.double().flatten(1).norm(dim=1) * G.double().flatten(1).norm(dim=1)
     print("P2-256 adjoint gap:", ((lhs - rhs).abs() / scale).tolist())
     assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
+
+
+def test_p2_driver_ffhq_script_settings(dev, tmp_path):
+    """Drop-in driver on the P2 family with the FFHQ_P2 launch-script settings
+    (src/scripts/main_hf_null_space_projection_FFHQ_P2.sh: edit_t 0.2, pca_rank 3, pca_rank_null 5, scale 12, 1 step): basis
+    files with the reference's names / shapes, orthonormal rows, the edit basis equal to the
+    oracle's power method from the same x_t (< 1 degree), finite edited images."""
+    import types
+    from loco_edit_b200.edit import EditUncondDiffusion
+    from loco_edit_b200.scheduler import YHCustomScheduler
+    from oracle import pullback_ref
+    arch, sd, net, ref = _setup("two_level_attn16", dev)
+    R = arch["resolution"]
+    g = torch.Generator().manual_seed(0)
+    x0 = (0.5 * torch.randn(1, 3, R, R, generator=g)).clamp(-1, 1)
+    mask = torch.zeros(3, R, R, dtype=torch.bool)
+    mask[:, 12:20, 8:24] = True
+
+    class _DS:
+        def __getitem__(self, idx):
+            return x0
+
+        def getmask(self, idx, choose_sem):
+            return mask
+
+    args = types.SimpleNamespace(
+        device=dev, dtype=torch.float32, seed=3, model_name="FFHQ_P2", dataset_name="FFHQ",
+        image_size=R, for_steps=100, inv_steps=100, edit_t=0.2, performance_boosting_t=0.2,
+        x_space_guidance_edit_step=1.0, x_space_guidance_scale=12.0, x_space_guidance_num_step=1,
+        result_folder=str(tmp_path), sample_idx=4, choose_sem="hair", mask_index=0, sampling_mode=False,
+        vT_path="", vT1_path="", verbose=False, save_images=False, noise_schedule=None)
+    e = EditUncondDiffusion(args, unet=net, dataset=_DS())
+    d = x0.numel()
+    v0a, _ = torch.linalg.qr(torch.randn(d, 3, generator=g))
+    v0b, _ = torch.linalg.qr(torch.randn(d, 5, generator=g))
+    e.v0 = {3: v0a.T.contiguous().to(dev), 5: v0b.T.contiguous().to(dev)}
+    orig = e.local_encoder_decoder_pullback_xt
+    xts = []
+
+    def capped(**kw):
+        kw["max_iter"] = 2
+        xts.append(kw["x"].detach().clone())
+        return orig(**kw)
+
+    e.local_encoder_decoder_pullback_xt = capped
+    e.run_edit_null_space_projection(idx=4, vis_num=1, vis_num_pc=1, pca_rank=3, pca_rank_null=5,
+                                     null_space_projection=True, use_mask=True)
+    torch.cuda.synchronize()
+    files = {}
+    for root, _, fs in os.walk(e.result_folder):
+        for f in fs:
+            if f.endswith(".pt"):
+                files[f] = torch.load(os.path.join(root, f)).cpu()
+    assert files["vT-modify-pca-rank-3.pt"].shape == (3, d) and files["vT-null-5.pt"].shape == (5, d)
+    pcs = [k for k in files if k.endswith("pc_000-vT.pt")]
+    assert len(pcs) == 1 and "edit_0.2T_null_proj_True_rank5_scale_12.0" in pcs[0] and files[pcs[0]].shape == (1, d)
+    for k in ("vT-modify-pca-rank-3.pt", "vT-null-5.pt"):
+        v = files[k].double()
+        assert float((v @ v.T - torch.eye(v.shape[0], dtype=torch.float64)).abs().max()) < 1e-4
+    # projected direction is orthogonal to the null basis and has unit norm
+    vp = files[pcs[0]].double()
+    assert abs(float(vp.norm()) - 1) < 1e-5 and float((files["vT-null-5.pt"].double() @ vp.T).abs().max()) < 1e-4
+    # the edit basis against the oracle's power method from the driver's own x_t
+    sched = pullback_ref.RefScheduler()
+    sched.set_timesteps(100)
+    assert e.edit_t_idx == 79          # |t - 0.2 * 1000| is smallest at timesteps[79] = 201.8
+    _, _, vref = pullback_ref.local_basis(ref, sched, xts[0].cpu(), sched.timesteps[79], v0a.T, 2, mask=mask)
+    ang = float(principal_angles_deg(files["vT-modify-pca-rank-3.pt"], vref).max())
+    print(f"P2 driver edit basis vs oracle from the same x_t: {ang:.3f} deg")
+    assert ang < 1.0
+    assert len(e.last_images) == 1 and e.last_images[0].shape == (3, 3, R, R)
+    assert torch.isfinite(e.last_images[0]).all()
