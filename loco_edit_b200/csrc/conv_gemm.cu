@@ -851,6 +851,321 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair halo variant (tcgen05 cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) work on
+// neighbouring 16 x 16 pixel blocks of the same output-channel tile.  Pixels are the M operand again
+// (128 per CTA and MMA, M = 256 over the pair), the 128 output channels the N operand, and each CTA
+// holds only HALF of every weight tile (64 channels): the tensor cores of both SMs read both halves.
+// Per SM the operand bytes per MMA clock drop from 55 to 40, below the ~43 B/clk an SM can ingest
+// (profiles/README.md), which neither the halo layout alone nor a cluster multicast achieves.
+//   * both CTAs run a TMA producer for their own activation windows and weight half; the bytes are
+//     completed on the LEADER's full barriers (cta_group::2 TMA), whose single arrival is the
+//     leader producer's expect_tx for both CTAs' bytes;
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and releases stages / publishes
+//     accumulators with multicast commits to the barriers of both CTAs;
+//   * every CTA's epilogue drains its own TMEM (lane = pixel) and arrives on the leader's
+//     accumulator-empty barrier (count = 8 warps).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairStagesA = 3;
+constexpr int kPairStagesB = 8;
+constexpr int kPairBBytes = 64 * 128;     // this CTA's half of a weight tile
+constexpr int kPairSmemBytes = kPairStagesA * kHaloABytes + kPairStagesB * kPairBBytes + 1024 + 256 + kEpiBytes;
+
+// Epilogue of one 128-pixel x block_n tile whose accumulator has TMEM lane = pixel (shared by the
+// pair kernel; same arithmetic and store order as the one-tile kernel's epilogue).
+__device__ __forceinline__ void epilogue_pixel_tile(const ConvGemmParams& p, uint32_t taddr, float* tbuf,
+                                                    int q, int lane, int tx, int ty, int tn, int co0) {
+  const int pr = lane >> 3, cq = lane & 7;
+  const int lTW = p.log_tw, lTH = p.log_th;
+  long long ooff[8], aoff[8];
+  uint32_t vmask = 0, bmask = 0;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int R = q * 32 + it * 4 + pr;
+    const int x = tx * p.TW + (R & (p.TW - 1));
+    const int y = ty * p.TH + ((R >> lTW) & (p.TH - 1));
+    const int n = tn * p.TN + (R >> (lTW + lTH));
+    if (n < p.N && y < p.Ho && x < p.Wo) vmask |= 1u << it;
+    if (n < p.bias_rows) bmask |= 1u << it;
+    ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
+    aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
+  }
+  for (int ch = 0; ch < p.block_n; ch += 32) {
+    float4 v[8];
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
+      v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+    }
+    __syncwarp();
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
+    if (p.bias2) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
+      bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+    if (p.addend) {
+      float4 a[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+    }
+    if (p.accumulate) {
+      float4 a[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+    }
+    float gs1 = 0.f, gs2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if (!((vmask >> it) & 1u)) continue;
+      float4 o = v[it];
+      if (p.round_out) {
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+      }
+      *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
+      gs1 += (o.x + o.y) + (o.z + o.w);
+      gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    }
+    if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
+      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
+      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
+      const int nrow = tn * p.TN + ((q * 32) >> (lTW + lTH));   // uniform per warp (TW*TH >= 32)
+      if (pr == 0 && nrow < p.N) {
+#pragma unroll
+        for (int tg = 0; tg < 2; ++tg) {
+          if (p.st_ptr[tg] == nullptr) continue;
+          const int g = (p.st_choff[tg] + co0 + ch + cq * 4) / p.st_cg[tg];
+          double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
+          atomicAdd(dst, (double)gs1);
+          atomicAdd(dst + 1, (double)gs2);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* smem_w = smem + kPairStagesA * kHaloABytes;
+  constexpr int kRing = kPairStagesA * kHaloABytes + kPairStagesB * kPairBBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kRing);
+  uint64_t* b_full = a_full + kPairStagesA;
+  uint64_t* a_empty = b_full + kPairStagesB;
+  uint64_t* b_empty = a_empty + kPairStagesA;
+  uint64_t* tfull_bar = b_empty + kPairStagesB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + kRing + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.hmap);
+    prefetch_tmap(&p.bmap);
+    if (p.c2_chunks > 0) { prefetch_tmap(&p.hmap2); prefetch_tmap(&p.bmap2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kPairStagesA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kPairStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);      // the four epilogue warps of each CTA of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // the peer's barriers and TMEM exist from here on
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int half_y = p.tiles_y >> 1;
+  const int units_m = p.tiles_x * half_y * p.tiles_n;        // 16 x 16 blocks per output-channel tile
+  const int total_items = units_m * p.tiles_co;              // even; units_m even (host checks)
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int um = w % units_m;
+        const int co0 = (w / units_m) * 128;
+        const int x0 = (um % p.tiles_x) * 16;
+        const int y0 = ((um / p.tiles_x) % half_y) * 16;
+        const int n0 = um / (p.tiles_x * half_y);
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+#pragma unroll 1
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
+            tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
+                             x0 + dxi - 1, y0 - 1, n0);
+            if (++as == kPairStagesA) { as = 0; aph ^= 1; }
+#pragma unroll 1
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
+              tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap, map_to_cta(&b_full[bs], 0),
+                               p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0 + (int)rank * 64);
+              if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+        for (int cc = 0; cc < p.c2_chunks; ++cc) {          // fused 1x1 shortcut slabs
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * 2 * kABytes);
+          tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap2, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
+                           x0, y0, n0);
+          if (++as == kPairStagesA) { as = 0; aph ^= 1; }
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
+          tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap2, map_to_cta(&b_full[bs], 0), cc * kConvBlockK,
+                           co0 + (int)rank * 64);
+          if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && leader) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      uint32_t idesc = 0;                      // M = 256 (pixels of both CTAs), N = 128 (output channels)
+      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
+      idesc |= (uint32_t)(128 >> 3) << 17;
+      idesc |= (uint32_t)(256 >> 4) << 24;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem));
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_w));
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        uint32_t first = 0;
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+#pragma unroll 1
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&a_full[as], aph);
+            const uint64_t ad_s = adesc0 + (uint64_t)as * (uint64_t)(kHaloABytes >> 4);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint64_t bd = bdesc0 + (uint64_t)bs * (uint64_t)(kPairBBytes >> 4);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                // pixel tile j of this CTA's block = the 128 window rows that start (dyi + 8 j) image rows in
+                const uint64_t ad = ad_s + (uint64_t)((dyi * 16 * 128 + j * kABytes) >> 4);
+#pragma unroll
+                for (int k = 0; k < kConvBlockK / 8; ++k)
+                  umma_tf32_pair(d_tmem + j * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                                 first | (uint32_t)(k != 0));
+              }
+              first = 1;
+              umma_commit_pair(&b_empty[bs], 3);
+              if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
+            }
+            umma_commit_pair(&a_empty[as], 3);
+            if (++as == kPairStagesA) { as = 0; aph ^= 1; }
+          }
+        }
+        for (int cc = 0; cc < p.c2_chunks; ++cc) {
+          mbar_wait(&a_full[as], aph);
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint64_t ad_s = adesc0 + (uint64_t)as * (uint64_t)(kHaloABytes >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)bs * (uint64_t)(kPairBBytes >> 4);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < kConvBlockK / 8; ++k)
+              umma_tf32_pair(d_tmem + j * 128, ad_s + (uint64_t)((j * kABytes) >> 4) + (uint64_t)(k * 2),
+                             bd + (uint64_t)(k * 2), idesc, first | (uint32_t)(k != 0));
+          first = 1;
+          umma_commit_pair(&b_empty[bs], 3);
+          umma_commit_pair(&a_empty[as], 3);
+          if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
+          if (++as == kPairStagesA) { as = 0; aph ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own TMEM) ------------------------------
+    const int q = warp & 3;
+    float* tbuf = epi_smem + q * (32 * 33);
+    const uint32_t tempty_leader0 = map_to_cta(&tempty_bar[0], 0);
+    const uint32_t tempty_leader1 = map_to_cta(&tempty_bar[1], 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int um = w % units_m;
+      const int co0 = (w / units_m) * 128;
+      const int tx = um % p.tiles_x;
+      const int ty0 = ((um / p.tiles_x) % half_y) * 2;
+      const int tn = um / (p.tiles_x * half_y);
+#pragma unroll
+      for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int jt = 0; jt < 2; ++jt) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
+        epilogue_pixel_tile(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // neither CTA frees TMEM / exits while the pair's MMAs or arrivals are in flight
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1142,6 +1457,18 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     p.counter_stride = prob.splitk_max_tiles;
     const int items = tiles * ks / (p.nt >= 3 ? 2 : p.nt);
     L->grid[i] = items < sms ? items : sms;
+    {
+      // CTA-pair variant (nt == 5): consecutive items must share their weight tile (even number of
+      // 16 x 16 blocks per output-channel tile) and the grid must be whole pairs
+      const char* e = getenv("LOCO_CONV_PAIR");
+      const int units = p.tiles_x * p.tiles_y * p.tiles_n / 2;
+      if (p.nt == 4 && !(e && atoi(e) == 0) && units % 2 == 0 && items >= 2) {
+        p.nt = 5;
+        L->grid[i] &= ~1;
+        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, 64));
+        if (p.c2_chunks > 0) LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 64));
+      }
+    }
     L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * (p.ntaps * p.c_chunks + p.c2_chunks) * kConvBlockK;
     LOCO_REQUIRE(prob.in2 == nullptr || p.c2_chunks > 0,
                  "conv: a fused 1x1 shortcut needs the halo variant (check conv_halo_eligible)");
@@ -1160,6 +1487,8 @@ int conv_init() {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
+    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_pair_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
   return 0;
@@ -1170,7 +1499,9 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {
-      if (L.p[i].nt == 4)
+      if (L.p[i].nt == 5)
+        conv_gemm_tf32_pair_kernel<<<L.grid[i], kThreads, kPairSmemBytes, stream>>>(L.p[i]);
+      else if (L.p[i].nt == 4)
         conv_gemm_tf32_wide_kernel<true><<<L.grid[i], kThreads, kHaloSmemBytes, stream>>>(L.p[i]);
       else if (L.p[i].nt == 3)
         conv_gemm_tf32_wide_kernel<false><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);

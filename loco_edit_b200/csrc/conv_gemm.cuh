@@ -42,7 +42,7 @@ struct ConvGemmParams {
   const float* bias2;         // second per-channel bias (timestep projection), same rule
   int bias_rows;
   int debug;                  // profiling aid: 1 = exit at entry, 2 = setup/teardown only
-  int nt;                     // kernel variant: 1 / 2 pixel tiles per item, 3 = wide, 4 = halo
+  int nt;                     // kernel variant: 1 / 2 pixel tiles per item, 3 = wide, 4 = halo, 5 = CTA-pair halo (cta_group::2)
   int ksplit;                 // K-loop split factor (1 = none)
   float* partial;             // split-K partial tiles [tile][split][128][block_n]
   int* counters;              // split-K arrival [tile] and done [counter_stride + tile] counters
