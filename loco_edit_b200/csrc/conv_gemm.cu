@@ -865,7 +865,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 //   * every CTA's epilogue drains its own TMEM (lane = pixel) and arrives on the leader's
 //     accumulator-empty barrier (count = 8 warps).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairStagesA = 3;
+constexpr int kPairStagesA = 4;
 constexpr int kPairStagesB = 8;
 constexpr int kPairBBytes = 64 * 128;     // this CTA's half of a weight tile
 constexpr int kPairSmemBytes = kPairStagesA * kHaloABytes + kPairStagesB * kPairBBytes + 1024 + 256 + kEpiBytes;
@@ -1024,16 +1024,24 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll 1
           for (int dxi = 0; dxi < 3; ++dxi) {
             mbar_wait(&a_empty[as], aph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
-            tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
-                             x0 + dxi - 1, y0 - 1, n0);
+            if (p.debug == 3 || p.debug == 9) {            // profiling aid: no operand traffic
+              if (leader) mbar_arrive(&a_full[as]);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
+              tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
+                               x0 + dxi - 1, y0 - 1, n0);
+            }
             if (++as == kPairStagesA) { as = 0; aph ^= 1; }
 #pragma unroll 1
             for (int dyi = 0; dyi < 3; ++dyi) {
               mbar_wait(&b_empty[bs], bph ^ 1);
-              if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
-              tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap, map_to_cta(&b_full[bs], 0),
-                               p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0 + (int)rank * 64);
+              if (p.debug == 3 || p.debug == 9) {
+                if (leader) mbar_arrive(&b_full[bs]);
+              } else {
+                if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
+                tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap, map_to_cta(&b_full[bs], 0),
+                                 p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0 + (int)rank * 64);
+              }
               if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
             }
           }
@@ -1141,7 +1149,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int jt = 0; jt < 2; ++jt) {
+      for (int jt = ((p.debug == 5 || p.debug == 9) ? 2 : 0); jt < 2; ++jt) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
         epilogue_pixel_tile(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
       }
