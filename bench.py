@@ -272,14 +272,14 @@ def run_ours(args):
         conv_tflops = work[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         roof = {"bound": "tensor",
-                "kernel": "tcgen05 implicit-GEMM conv family (conv_gemm_tf32_wide_kernel<halo> on the "
-                          ">=64^2 layers, conv_gemm_tf32_kernel on the small ones)",
+                "kernel": "tcgen05 implicit-GEMM conv family (conv_gemm_tf32_pair_kernel = cta_group::2 halo "
+                          "variant on the >=64^2 layers, conv_gemm_tf32_kernel on the small ones)",
                 "achieved": conv_tflops,
                 "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                # dram__bytes_read+write of the dominant launch (halo variant, 3x3 128->128 at 256^2,
-                # 6 rows; algorithmic 403 MB) from the committed ncu --set full capture,
-                # profiles/r1_conv_halo_ncu_full_raw.csv
-                "traffic": 352.2e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
+                # dram__bytes_read+write of the dominant launch (CTA-pair halo variant, 3x3 128->128 at
+                # 256^2, 6 rows; algorithmic 403 MB) from the committed ncu --set full capture,
+                # profiles/r1_conv_pair_ncu_full_raw.csv
+                "traffic": 352.8e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
                 "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
