@@ -174,3 +174,21 @@ def test_p2_local_basis_matches_reference(golden_dir, case):
         assert _principal_angle_deg(vT, ref["vT"]) < 0.05
         dots = (vT * ref["vT"]).sum(1).abs()
         assert float((1 - dots).abs().max()) < 1e-3, dots
+
+
+def test_full_size_forward_oracles_match_reference(golden_dir):
+    """256 x 256, full-depth configurations (tests/golden/make_golden_full.py): one forward each."""
+    from loco_edit_b200.weights import P2_256
+    from oracle import p2_ref
+    gen = torch.Generator().manual_seed(0)
+    (0.5 * torch.randn(1, 3, 256, 256, generator=gen)).clamp(-1, 1)
+    xt = torch.randn(1, 3, 256, 256, generator=gen)
+    for name, arch, fwd in (("full256_ddpm.pt", DDPM256, ddpm_ref.unet_forward),
+                            ("full256_p2.pt", P2_256, p2_ref.unet_forward)):
+        g = _load(golden_dir, name)
+        sd = random_state_dict(arch, seed=g["weights_seed"])
+        with torch.no_grad():
+            eps = fwd(sd, arch, xt, g["t"])
+        ref = g["eps"].float()          # stored in fp16
+        err = float((eps - ref).norm() / ref.norm())
+        assert err < 1e-3, (name, err)
