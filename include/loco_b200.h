@@ -152,6 +152,16 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
                      int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
                      void* stream);
+/* y = conv3x3(x; w) + conv1x1(x2; w2) + bias in one launch: `ResnetBlock.conv2` + `nin_shortcut`
+ * (src/models/ddpm/diffusion.py:905-912) / `out_layers` conv + `skip_connection`
+ * (src/models/guided_diffusion/unet.py:252-258) as the U-Net programs run them, with the optional
+ * fused GroupNorm statistics of the result (stats: 64*N doubles = [row][group](sum, sum sq), groups of
+ * stat_cg channels).  x2 may be null.  Only shapes served by the halo conv variants (H, W multiples of
+ * 16, Cout multiple of 128, >= ~1 tile per SM). wpack/wpack2: scratch of w/w2's size. */
+int loco_conv2d_fused_nhwc(const float* x, int N, int H, int W, int Cin, const float* w, int Cout,
+                           const float* x2, int C2, const float* w2, float* wpack, float* wpack2,
+                           const float* bias, int bias_rows, float* y, double* stats, int stat_cg,
+                           void* stream);
 /* micro-benchmark of one prepared conv launch (wpack must already hold packed weights):
  * average device ms over `reps` back-to-back launches; reports the split-K factor / grid used. */
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,

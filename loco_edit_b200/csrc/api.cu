@@ -327,6 +327,47 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
   GUARD_END
 }
 
+// y = conv3x3(x; w) + conv1x1(x2; w2) + bias (first bias_rows rows) in ONE launch (the ResnetBlock's
+// conv2 + nin_shortcut, halo variants only), optionally accumulating the GroupNorm statistics
+// (sum, sum of squares per row and group of `stat_cg` channels) of the stored result.
+int loco_conv2d_fused_nhwc(const float* x, int N, int H, int W, int Cin, const float* w, int Cout,
+                           const float* x2, int C2, const float* w2, float* wpack, float* wpack2,
+                           const float* bias, int bias_rows, float* y, double* stats, int stat_cg,
+                           void* stream) {
+  GUARD_BEGIN
+  LOCO_TRY(require_device());
+  LOCO_REQUIRE(x && w && y && wpack, "loco_conv2d_fused_nhwc: null argument");
+  cudaStream_t s = ST(stream);
+  LOCO_TRY(conv_init());
+  LOCO_REQUIRE(conv_halo_eligible(CONV_3x3, N, H, W, Cout),
+               "loco_conv2d_fused_nhwc: shape %d x %dx%d x %d is not served by the halo conv variants", N, H,
+               W, Cout);
+  ConvProblem p;
+  p.kind = CONV_3x3;
+  LOCO_TRY(pack_conv_fprop(w, wpack, Cout, Cin, 3, 3, s));
+  p.Kc = Cin; p.Ngemm = Cout;
+  p.in = make_view(const_cast<float*>(x), N, H, W, Cin);
+  p.out = make_view(y, N, H, W, Cout);
+  p.wpack = wpack;
+  p.bias = bias; p.bias_rows = bias_rows;
+  View v2;
+  if (x2) {
+    LOCO_REQUIRE(w2 && wpack2, "loco_conv2d_fused_nhwc: shortcut weights missing");
+    LOCO_TRY(pack_conv_fprop(w2, wpack2, Cout, C2, 1, 1, s));
+    v2 = make_view(const_cast<float*>(x2), N, H, W, C2);
+    p.in2 = &v2; p.wpack2 = wpack2; p.Kc2 = C2;
+  }
+  if (stats) {
+    LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
+    p.st_ptr[0] = stats; p.st_cg[0] = stat_cg; p.st_choff[0] = 0;
+  }
+  p.round_out = 0;
+  ConvLaunch L;
+  LOCO_TRY(conv_prepare(p, &L));
+  return conv_run(L, s);
+  GUARD_END
+}
+
 // Micro-benchmark of one prepared conv launch: `reps` back-to-back launches between two events.
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
                     float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,

@@ -179,6 +179,30 @@ def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=Fals
     return out
 
 
+def conv2d_fused_nhwc(x, w, x2=None, w2=None, bias=None, bias_rows=0, stat_groups=0):
+    """conv3x3(x; w) + conv1x1(x2; w2) + bias in one launch (conv2 + shortcut of a ResnetBlock);
+    stat_groups > 0 also returns the fused GroupNorm statistics [N, stat_groups, 2] of the result."""
+    x, w = _f32(x), _f32(w)
+    N, H, W_, Cin = x.shape
+    Cout = w.shape[0]
+    out = torch.empty(N, H, W_, Cout, dtype=torch.float32, device=x.device)
+    wpack = torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+    C2, wpack2 = 0, None
+    if x2 is not None:
+        x2, w2 = _f32(x2), _f32(w2)
+        C2 = x2.shape[-1]
+        wpack2 = torch.empty(w2.numel(), dtype=torch.float32, device=x.device)
+    stats = None
+    if stat_groups:
+        assert stat_groups == 32
+        stats = torch.zeros(N, 32, 2, dtype=torch.float64, device=x.device)
+    check(_lib.load().loco_conv2d_fused_nhwc(ptr(x), N, H, W_, Cin, ptr(w), Cout, ptr(x2), C2, ptr(w2),
+                                             ptr(wpack), ptr(wpack2), ptr(bias), bias_rows, ptr(out),
+                                             ptr(stats), Cout // 32 if stat_groups else 0, stream_ptr()),
+          "loco_conv2d_fused_nhwc")
+    return (out, stats) if stat_groups else out
+
+
 def groupnorm_silu_fwd(x, n_primal, gamma, beta, eps, silu):
     x = _f32(x)
     N, H, W_, Cc = x.shape

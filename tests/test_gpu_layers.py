@@ -285,3 +285,29 @@ def test_gram(dev):
         G = ops.gram(A.to(dev), B.to(dev))
         ref = A.double() @ B.double().T
         assert float((G.cpu() - ref).abs().max()) < 1e-3 * (d ** 0.5) * 1e-2
+
+
+@pytest.mark.parametrize("N,H,Cin,C2,Cout", [(6, 128, 128, 256, 128), (3, 256, 128, 256, 128), (8, 64, 256, 384, 256)])
+def test_conv_fused_shortcut_and_statistics(dev, N, H, Cin, C2, Cout):
+    """conv2 + 1x1 shortcut in one accumulation (halo / CTA-pair variants) and the GroupNorm
+    statistics fused into its epilogue, against fp64 PyTorch on tf32-representable inputs."""
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(N * 1000 + H)
+    w = tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+    w2 = tf32_round(torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).to(dev)
+    x = tf32_round(torch.randn(N, Cin, H, H, generator=g)).to(dev)
+    x2 = tf32_round(torch.randn(N, C2, H, H, generator=g)).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.double(), padding=1) + F.conv2d(x2.double(), w2.double())
+    ref[:2] += bias.double()[None, :, None, None]
+    y, st = ops.conv2d_fused_nhwc(nhwc(x), w, nhwc(x2), w2, bias=bias, bias_rows=2, stat_groups=32)
+    torch.cuda.synchronize()
+    e = rel_err(nchw(y), ref)
+    print(f"fused conv+shortcut N={N} {H}x{H} {Cin}+{C2}->{Cout}: rel_err={e:.3e}")
+    assert e < 1e-5
+    grp = ref.reshape(N, 32, -1)
+    sref = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], -1)
+    assert rel_err(st, sref) < 2e-5      # fp32 partial sums per 32-pixel chunk, fp64 across chunks
+    # without the shortcut
+    y1 = ops.conv2d_fused_nhwc(nhwc(x), w)
+    assert rel_err(nchw(y1), F.conv2d(x.double(), w.double(), padding=1)) < 1e-5
