@@ -320,9 +320,9 @@ def run_ours(args):
 
     # ---- BASELINE config 2 proper: the P2 / guided-diffusion U-Net with the FFHQ_P2 script settings
     # (edit_t 0.2, rank 3 + null 5, scale 12, 1 step; scripts/main_hf_null_space_projection_FFHQ_P2.sh),
-    # one warm-up and one timed batch of BATCH image/mask pairs on rank 0 (reported as an extra key) ----
+    # one warm-up and one timed batch of BATCH image/mask pairs (single-GPU runs only; extra key) ----
     p2 = None
-    if rank == 0 and not args.no_p2:
+    if rank == 0 and world == 1 and not args.no_p2:
         from loco_edit_b200.weights import P2_256
         del pipe
         unet._plans.clear()
