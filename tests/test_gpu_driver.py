@@ -151,3 +151,43 @@ def test_driver_matches_reference_driver(golden_dir, tmp_path):
     print(f"edited images vs reference driver: PSNR {p:.1f} dB, max abs diff {float((img - ref).abs().max()):.2e}, "
           f"rel {float((img - ref).norm() / ref.norm()):.2e}")
     assert p >= 40.0
+
+
+def test_group_edit_composes_directions_like_the_reference(golden_dir, tmp_path):
+    """group_edit_null_space_projection (src/modules/edit.py:2171-2212): two saved directions are
+    applied cumulatively with step scale * num_step; the 3-latent batch (bit-exact) and the
+    eta = 1 DDIM stage from the driver's own x_t against the oracle with the same injected noise."""
+    from oracle import ddpm_ref, pullback_ref
+    from loco_edit_b200.weights import random_state_dict, tiny_arch
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(golden_dir, "driver_tiny.pt"), weights_only=False)
+    d = g["x0"].numel()
+    gen = torch.Generator().manual_seed(21)
+    v = torch.randn(2, 1, d, generator=gen)
+    v = v / v.norm(dim=2, keepdim=True)
+    paths = []
+    for i in range(2):
+        p = str(tmp_path / f"dir{i}-vT.pt")
+        torch.save(v[i], p)
+        paths.append(p)
+    e = _make(dev, tmp_path / "g", g, vT_path=paths[0])
+    e.vT1_path = paths[1]
+    noises = [torch.randn(3, 3, 32, 32, generator=gen) for _ in range(20)]
+    it = iter(noises)
+    e.noise_fn = lambda i, x: next(it).to(dev)
+    xt = e.group_edit_null_space_projection(idx=7)
+    torch.cuda.synchronize()
+    assert len(e.last_images) == 1 and e.last_images[0].shape == (3, 3, 32, 32)
+    # the composed latents: xt, xt + s*n*v0, xt + s*n*(v0 + v1)   (s = 0.5, n = 4 in _make)
+    xt_c = xt.cpu()
+    step = 0.5 * 4
+    b1 = xt_c + step * v[0].reshape(1, 3, 32, 32)
+    batch = torch.cat([xt_c, b1, b1 + step * v[1].reshape(1, 3, 32, 32)], 0)
+    arch = tiny_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1)
+    ref_unet = ddpm_ref.RefUNet(arch, random_state_dict(arch, seed=1234, perturb_norm=0.1))
+    rs = pullback_ref.RefScheduler()
+    nz = {g["boost_idx"] + i: noises[i] for i in range(20)}
+    ref = pullback_ref.ddim_forward(ref_unet, rs, batch, 40, -1, boost_idx=g["boost_idx"], noises=nz)
+    p = _psnr(e.last_images[0].cpu(), ref)
+    print(f"group edit (2 directions) vs oracle from the same x_t: PSNR {p:.1f} dB")
+    assert p >= 40.0
