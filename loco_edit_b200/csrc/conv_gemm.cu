@@ -22,7 +22,8 @@ namespace {
 constexpr int kABytes = kConvBlockM * 128;       // 16 KB: 128 pixels x 32 fp32 channels
 constexpr int kBBytes = kConvMaxBlockN * 128;    // 16 KB: 128 output channels x 32 fp32 channels
 constexpr int kThreads = 256;
-constexpr int kEpiBytes = 4 * 32 * 33 * 4;       // per-epilogue-warp transpose buffers
+constexpr int kEpiPitch = 36;                    // floats per pixel row of a transpose buffer (16 B aligned, conflict-free)
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;   // per-epilogue-warp transpose buffers
 // NT = M tiles (of 128 pixels) per work item.  NT = 2 shares every weight tile between two pixel
 // tiles: 48 KB of operands per two MMA groups instead of 64 KB, which matters because the kernel
 // is bound by the ~70 B/clk an SM can ingest from L2, not by the tensor pipe.
@@ -78,6 +79,100 @@ __device__ __forceinline__ void prefetch_epilogue_tile(const ConvGemmParams& p, 
   if (p.accumulate) {
     const float* o = p.out + (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
     for (int c = 0; c < p.block_n; c += 32) prefetch_l2(o + c);
+  }
+}
+
+
+// TMEM gives each thread one pixel row (32 consecutive channels); the padded shared-memory transpose
+// turns that into "8 lanes x float4 = 128 contiguous bytes of one pixel" per load/store instruction.
+// 8 STS.128 + 8 LDS.128 per thread, both bank-conflict-free at a pitch of 36 floats.
+__device__ __forceinline__ void epilogue_transpose(const uint32_t (&r)[32], float* tbuf, int lane, int pr, int cq,
+                                                   float4 (&v)[8]) {
+  float4* trow = reinterpret_cast<float4*>(tbuf + lane * kEpiPitch);
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    trow[c] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                          __uint_as_float(r[4 * c + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    v[it] = *reinterpret_cast<const float4*>(tbuf + (it * 4 + pr) * kEpiPitch + cq * 4);
+  __syncwarp();
+}
+
+// Everything after the accumulator values of one 32-channel chunk are in registers (v[it] = channels
+// [ch + 4 cq, +4) of pixel row it*4 + pr of this warp's 32 rows): bias on the primal rows, residual,
+// VJP accumulation, tf32 rounding, 128-byte-coalesced stores, fused GroupNorm statistics.  The common
+// cases (whole tile valid, bias on all or none of the rows, no statistics) take branch-free paths:
+// the epilogue runs one warp per SM sub-partition, so its time is its instruction count.
+__device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, float4 (&v)[8],
+                                                    const long long (&ooff)[8], const long long (&aoff)[8],
+                                                    uint32_t vmask, uint32_t bmask, float4 bsum, int ch,
+                                                    int co0, int cq, int pr, int nrow) {
+  if (bmask == 0xFFu) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+  } else if (bmask != 0u) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+  }
+  if (p.addend) {
+    float4 a[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+  }
+  if (p.accumulate) {
+    float4 a[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
+  }
+  if (p.round_out) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      v[it].x = round_tf32(v[it].x); v[it].y = round_tf32(v[it].y);
+      v[it].z = round_tf32(v[it].z); v[it].w = round_tf32(v[it].w);
+    }
+  }
+  if (vmask == 0xFFu) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = v[it];
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if ((vmask >> it) & 1u) *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = v[it];
+  }
+  if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
+    // fused GroupNorm statistics of what was just stored: the 4 lanes that share a channel quad
+    // (different pixels) combine, then one fp64 atomic pair per consumer
+    float gs1 = 0.f, gs2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if (!((vmask >> it) & 1u)) continue;
+      const float4 o = v[it];
+      gs1 += (o.x + o.y) + (o.z + o.w);
+      gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    }
+    gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
+    gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
+    if (pr == 0 && nrow < p.N) {
+#pragma unroll
+      for (int tg = 0; tg < 2; ++tg) {
+        if (p.st_ptr[tg] == nullptr) continue;
+        const int g = (p.st_choff[tg] + co0 + ch + cq * 4) / p.st_cg[tg];
+        double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
+        atomicAdd(dst, (double)gs1);
+        atomicAdd(dst + 1, (double)gs2);
+      }
+    }
   }
 }
 
@@ -236,7 +331,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     // "8 lanes x float4 = 128 contiguous bytes of one pixel" so every global load/store of the
     // residual / accumulate / output / split-K partial streams is a fully used 128-byte segment.
     const int q = warp & 3;              // TMEM lane quarter owned by this warp
-    float* tbuf = epi_smem + q * (32 * 33);
+    float* tbuf = epi_smem + q * (32 * kEpiPitch);
     const int pr = lane >> 3;            // pixel sub-row handled by this lane (0..3)
     const int cq = lane & 7;             // channel quad within the 32-column chunk
     const int lTW = p.log_tw, lTH = p.log_th;
@@ -286,18 +381,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                          (long long)(q * 32 + pr) * p.block_n + cq * 4;
           for (int ch = 0; ch < p.block_n; ch += 32) {
             uint32_t r[32];
+            float4 t4[8];
             tmem_ld_32x32(taddr + ch, r);
             tmem_ld_wait();
+            epilogue_transpose(r, tbuf, lane, pr, cq, t4);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
-              __stcg(reinterpret_cast<float4*>(pmine + (long long)(it * 4) * p.block_n + ch),
-                     make_float4(tp[0], tp[1], tp[2], tp[3]));
-            }
-            __syncwarp();
+            for (int it = 0; it < 8; ++it)
+              __stcg(reinterpret_cast<float4*>(pmine + (long long)(it * 4) * p.block_n + ch), t4[it]);
           }
           tc_fence_before();
           __syncwarp();
@@ -341,72 +431,18 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             uint32_t r[32];
             tmem_ld_32x32(taddr + ch, r);
             tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
-              v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
-            }
-            __syncwarp();
+            epilogue_transpose(r, tbuf, lane, pr, cq, v);
           }
           float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
-          if (p.bias2) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
-            bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
-          if (p.addend) {
-            float4 a[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-          }
-          if (p.accumulate) {
-            float4 a[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-          }
-          float gs1 = 0.f, gs2 = 0.f;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            if (!((vmask >> it) & 1u)) continue;
-            float4 o = v[it];
-            if (p.round_out) {
-              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            }
-            *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
-            gs1 += (o.x + o.y) + (o.z + o.w);
-            gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-          }
-          if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
-            // fused GroupNorm statistics of what was just stored: the 4 lanes that share a channel
-            // quad (different pixels) combine, then one fp64 atomic pair per consumer
-            gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
-            gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
-            const int nrow = tn * p.TN + ((q * 32) >> (lTW + lTH));   // uniform per warp (TW*TH >= 32)
-            if (pr == 0 && nrow < p.N) {
-#pragma unroll
-              for (int tg = 0; tg < 2; ++tg) {
-                if (p.st_ptr[tg] == nullptr) continue;
-                const int g = (p.st_choff[tg] + co0 + ch + cq * 4) / p.st_cg[tg];
-                double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
-                atomicAdd(dst, (double)gs1);
-                atomicAdd(dst + 1, (double)gs2);
-              }
+          if (bmask != 0u) {
+            if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
+            if (p.bias2) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
+              bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
             }
           }
+          epilogue_chunk_tail(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr,
+                              tn * p.TN + ((q * 32) >> (lTW + lTH)));
         }
       }
       if (ksplit == 1) {
@@ -866,9 +902,10 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 //     accumulator-empty barrier (count = 8 warps).
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairStagesA = 4;
-constexpr int kPairStagesB = 8;
+constexpr int kPairStagesB = 7;
 constexpr int kPairBBytes = 64 * 128;     // this CTA's half of a weight tile
 constexpr int kPairSmemBytes = kPairStagesA * kHaloABytes + kPairStagesB * kPairBBytes + 1024 + 256 + kEpiBytes;
+static_assert(kPairSmemBytes <= 232448 && kHaloSmemBytes <= 232448, "dynamic shared memory above the 227 KB limit");
 
 // Epilogue of one 128-pixel x block_n tile whose accumulator has TMEM lane = pixel (shared by the
 // pair kernel; same arithmetic and store order as the one-tile kernel's epilogue).
@@ -889,74 +926,22 @@ __device__ __forceinline__ void epilogue_pixel_tile(const ConvGemmParams& p, uin
     ooff[it] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0 + cq * 4;
     aoff[it] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0 + cq * 4;
   }
+  const int nrow = tn * p.TN + ((q * 32) >> (lTW + lTH));   // uniform per warp (TW*TH >= 32)
   for (int ch = 0; ch < p.block_n; ch += 32) {
     float4 v[8];
     uint32_t r[32];
     tmem_ld_32x32(taddr + ch, r);
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);      // overlaps the TMEM load
+    if (bmask != 0u) {
+      if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
+      if (p.bias2) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
+        bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+      }
+    }
     tmem_ld_wait();
-#pragma unroll
-    for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = __uint_as_float(r[c]);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const float* tp = tbuf + (it * 4 + pr) * 33 + cq * 4;
-      v[it] = make_float4(tp[0], tp[1], tp[2], tp[3]);
-    }
-    __syncwarp();
-    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + ch + cq * 4));
-    if (p.bias2) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + co0 + ch + cq * 4));
-      bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it)
-      if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
-    if (p.addend) {
-      float4 a[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-    }
-    if (p.accumulate) {
-      float4 a[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
-    }
-    float gs1 = 0.f, gs2 = 0.f;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      if (!((vmask >> it) & 1u)) continue;
-      float4 o = v[it];
-      if (p.round_out) {
-        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-      }
-      *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = o;
-      gs1 += (o.x + o.y) + (o.z + o.w);
-      gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-    }
-    if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
-      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 8);  gs2 += __shfl_xor_sync(0xffffffffu, gs2, 8);
-      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gs2 += __shfl_xor_sync(0xffffffffu, gs2, 16);
-      const int nrow = tn * p.TN + ((q * 32) >> (lTW + lTH));   // uniform per warp (TW*TH >= 32)
-      if (pr == 0 && nrow < p.N) {
-#pragma unroll
-        for (int tg = 0; tg < 2; ++tg) {
-          if (p.st_ptr[tg] == nullptr) continue;
-          const int g = (p.st_choff[tg] + co0 + ch + cq * 4) / p.st_cg[tg];
-          double* dst = p.st_ptr[tg] + ((long long)nrow * 32 + g) * 2;
-          atomicAdd(dst, (double)gs1);
-          atomicAdd(dst + 1, (double)gs2);
-        }
-      }
-    }
+    epilogue_transpose(r, tbuf, lane, pr, cq, v);
+    epilogue_chunk_tail(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr, nrow);
   }
 }
 
@@ -1133,7 +1118,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   } else if (warp >= 4) {
     // ------------------------------ epilogue (both CTAs, own TMEM) ------------------------------
     const int q = warp & 3;
-    float* tbuf = epi_smem + q * (32 * 33);
+    float* tbuf = epi_smem + q * (32 * kEpiPitch);
     const uint32_t tempty_leader0 = map_to_cta(&tempty_bar[0], 0);
     const uint32_t tempty_leader1 = map_to_cta(&tempty_bar[1], 0);
     int acc = 0;
