@@ -1398,8 +1398,14 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     {
       const int cap = conv_variant_cap();
       if (cap == 1) p.nt = 1;
+      // 1x1 convolutions are HBM-bound (4-8 K iterations per tile): the one-tile kernel streams them
+      // at 6.1 TB/s; two tiles per item only pay off when the weight tile is re-used a lot
+      if (prob.kind == CONV_1x1 && p.nt == 2 && prob.Ngemm < 2 * prob.Kc) p.nt = 1;
       if (p.nt == 2 && p.block_n == 128 && cap >= 3) {
-        p.nt = 3;
+        // the operand-swapped "wide" kernel without the halo layout lost to the two-tile kernel once
+        // the latter got the vectorised epilogue (1x1 N=10 256^2 128->256: 370 vs 233 us); it is
+        // kept selectable (LOCO_CONV_NT=3) as the single-CTA base of the halo variant
+        if (cap == 3) p.nt = 3;
         const bool s1 = prob.kind == CONV_3x3 || prob.kind == CONV_3x3_DGRAD;
         if (cap >= 4 && s1 && p.TW == 16 && p.TH == 8 && p.TN == 1 && p.tiles_y % 2 == 0) {
           // halo variant: (16+2)-row windows, one x-shifted copy per filter column
