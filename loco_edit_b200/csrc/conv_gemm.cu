@@ -1281,12 +1281,12 @@ bool conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
   const long long sms = num_sms();
   if (tiles >= (long long)conv_two_tile_min() * sms) return true;
   // Below that, weigh the wave quantisation of the two granularities: a halo item (256 pixels)
-  // costs 1 unit, a one-tile item (128 pixels, twice the operand traffic per FLOP) 0.62 units
+  // costs 1 unit, a one-tile item (128 pixels, twice the operand traffic per FLOP) 0.68 units
   // (measured on 64x64 and 256x256 layers, profiles/README.md); split-K territory stays one-tile.
   const long long items = tiles / 2;
   if (tiles * 2 <= sms || items * 2 < sms) return false;
   const double t_halo = (double)((items + sms - 1) / sms);
-  const double t_one = 0.62 * (double)((tiles + sms - 1) / sms);
+  const double t_one = 0.68 * (double)((tiles + sms - 1) / sms);
   return t_halo <= t_one;
 }
 
