@@ -280,6 +280,8 @@ def run_ours(args):
                 # 256^2, 6 rows; algorithmic 403 MB) from the committed ncu --set full capture,
                 # profiles/r1_conv_pair_ncu_full_raw.csv
                 "traffic": 352.8e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
+                # same capture: sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active / _elapsed
+                "ncu_tensor_pipe_active_pct": 80.9, "ncu_tensor_pipe_elapsed_pct": 74.0,
                 "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
