@@ -152,6 +152,9 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
                      int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
                      void* stream);
+/* Pure host logic: 1 if a stride-1 3x3 convolution (kind 0) or its data gradient (kind 3) of this
+ * shape is served by the halo / CTA-pair tcgen05 kernels (wave-quantisation cost model). */
+int loco_conv_halo_eligible(int kind, int N, int H, int W, int Cout);
 /* y = conv3x3(x; w) + conv1x1(x2; w2) + bias in one launch: `ResnetBlock.conv2` + `nin_shortcut`
  * (src/models/ddpm/diffusion.py:905-912) / `out_layers` conv + `skip_connection`
  * (src/models/guided_diffusion/unet.py:252-258) as the U-Net programs run them, with the optional

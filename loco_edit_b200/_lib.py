@@ -64,6 +64,7 @@ PROTOTYPES = {
     "loco_gather_rows": (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     "loco_scatter_rows": (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     "loco_gram": (_I, [_P, _I, _P, _I, _LL, _P, _P]),
+    "loco_conv_halo_eligible": (_I, [_I, _I, _I, _I, _I]),
     "loco_conv2d_fused_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _P]),
     "loco_conv2d_nhwc": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _LL, _P]),
     "loco_conv_bench": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, C.POINTER(_F),

@@ -368,6 +368,12 @@ int loco_conv2d_fused_nhwc(const float* x, int N, int H, int W, int Cin, const f
   GUARD_END
 }
 
+// Host-side variant decision for a stride-1 3x3 (fprop or dgrad) of this shape: 1 = served by the
+// halo / CTA-pair kernels (and eligible for the fused 1x1 shortcut), 0 = one-/two-tile kernel.
+int loco_conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
+  return conv_halo_eligible(kind, N, H, W, Cout) ? 1 : 0;
+}
+
 // Micro-benchmark of one prepared conv launch: `reps` back-to-back launches between two events.
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
                     float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,

@@ -121,3 +121,22 @@ def test_p2_model_registry_matches_reference_state_dict(golden_dir):
         lib.loco_plan_destroy(p)
     finally:
         lib.loco_unet_destroy(h)
+
+
+def test_conv_variant_selection_is_stable():
+    """The host-side cost model that routes 3x3 layers to the halo / CTA-pair kernels (pure host
+    logic, 148 SMs assumed without a device): the layer shapes of the bench must keep their variant."""
+    lib = _lib.load()
+    el = lambda kind, N, H, W, C: lib.loco_conv_halo_eligible(kind, N, H, W, C)
+    # >= 64^2 layers of the fused (1+k)-row passes and of the batched forwards
+    for N in (6, 8, 11, 40):
+        assert el(0, N, 256, 256, 128) == 1 and el(3, N, 256, 256, 128) == 1
+        assert el(0, N, 128, 128, 128) == 1
+    assert el(0, 8, 64, 64, 256) == 1 and el(0, 40, 64, 64, 256) == 1 and el(0, 40, 32, 32, 256) == 1
+    assert el(0, 1, 256, 256, 128) == 1                  # B = 1: 256 blocks, 2 waves beat 4 x 0.68
+    # split-K / one-tile territory
+    assert el(0, 6, 16, 16, 512) == 0 and el(0, 6, 8, 8, 512) == 0 and el(0, 1, 64, 64, 256) == 0
+    assert el(0, 6, 32, 32, 256) == 0
+    # only stride-1 3x3, 128-multiple output channels, 16-multiple images
+    assert el(1, 40, 256, 256, 128) == 0 and el(2, 40, 256, 256, 128) == 0
+    assert el(0, 40, 256, 256, 64) == 0 and el(0, 40, 24, 24, 128) == 0
