@@ -67,3 +67,33 @@ def test_edit_batch_layout_matches_reference_lines():
         mid = n_out // 2
         assert torch.equal(b[mid], xt[0])
         assert float((b[-1] - xt[0]).mean()) > 0 and float((b[0] - xt[0]).mean()) < 0
+
+
+def test_preset_derives_the_reference_fields(tmp_path, monkeypatch):
+    """preset() (src/utils/define_argparser.py:138-249): experiment folder names, derived fields and
+    the asserts of the unconditional models; model-name dispatch of the two U-Net families."""
+    from loco_edit_b200.define_argparser import parse_args, preset
+    monkeypatch.chdir(tmp_path)
+    base = ["--dtype", "fp32", "--device", "cpu", "--result_folder", str(tmp_path / "runs"), "--seed", "3",
+            "--use_yh_custom_scheduler", "True", "--performance_boosting_t", "0.2", "--for_steps", "100"]
+    a = preset(parse_args(base + ["--model_name", "FFHQ_P2", "--dataset_name", "FFHQ"]))
+    assert a.exp == "FFHQ_P2-FFHQ" and a.result_folder.endswith(os.path.join("FFHQ_P2-FFHQ", "results"))
+    assert os.path.isdir(a.result_folder) and os.path.isdir(a.obs_folder)
+    assert (a.c_in, a.image_size, a.memory_bound) == (3, 256, 50) and a.dtype == torch.float32
+    assert not (a.is_stable_diffusion or a.is_DeepFloyd_IF_diffusion or a.is_LCM)
+    b = preset(parse_args(base + ["--model_name", "LSUN_church_HF", "--dataset_name", "LSUN_church"]))
+    assert b.exp == "LSUN_church_HF-LSUN_church"
+    # seed 0 means "draw a seed" (:140-141)
+    c = preset(parse_args([x if x != "3" else "0" for x in base] + ["--model_name", "CelebA_HQ_HF",
+                                                                    "--dataset_name", "CelebA_HQ_mask"]))
+    assert c.seed != 0
+    # unconditional models assert for_steps == 100 and performance_boosting_t == 0.2 (:244-247)
+    bad = [x for x in base]
+    bad[bad.index("--for_steps") + 1] = "50"
+    with pytest.raises(AssertionError):
+        preset(parse_args(bad + ["--model_name", "FFHQ_P2", "--dataset_name", "FFHQ"]))
+    with pytest.raises(ValueError):
+        preset(parse_args(base + ["--model_name", "NotAModel", "--dataset_name", "x"]))
+    # the Edit class picks the network family by model name (reference: utils/utils.py:101-131)
+    from loco_edit_b200.weights import P2_256, DDPM256, param_shapes
+    assert "input_blocks.0.0.weight" in param_shapes(P2_256) and "conv_in.weight" in param_shapes(DDPM256)
