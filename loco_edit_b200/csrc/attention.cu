@@ -7,24 +7,30 @@ namespace loco {
 namespace {
 
 constexpr int BM = 32, BN = 64, BK = 16;
-constexpr int kGemmThreads = 128;
+constexpr int kGemmGroup = 128;                 // threads that own one K slab at a time
+constexpr int kGemmThreads = 2 * kGemmGroup;
 
-// 32x64 output tile per 128-thread block (8x16 threads, 4x4 outputs each); the next K slab is
-// prefetched into registers while the current one is multiplied out of shared memory, so the
-// global/L2 latency of the tiny attention operands overlaps the FMAs, and the small tile keeps
-// >= 160 blocks in flight for a 256x256 product.
+// 32x64 output tile per block.  The attention operands are tiny (256 or 64 tokens), so a launch has
+// only about one block per SM and is bound by the latency of its K loop, not by FMA throughput:
+// the block therefore runs TWO 128-thread groups (8x16 threads, 4x4 outputs each) that walk
+// alternate K slabs with their own shared-memory tiles and named barriers, which halves the
+// length of the dependent chain; the next slab of a group is prefetched into registers while the
+// current one is multiplied, and group 1 hands its partial sums to group 0 through shared memory
+// (fixed order: bit-reproducible).
 __global__ void __launch_bounds__(kGemmThreads)
 batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long long sCm,
                     long long sCn, long long sCb, long long sCh, int heads, int M, int N, int K,
                     float alpha, float beta, int round_out, int a_kcontig, int b_ncontig) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  __shared__ float red[kGemmGroup][17];
   const int b = blockIdx.z / heads;       // batch row
   const int hd = blockIdx.z % heads;      // attention head
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const float* Ab = A.ptr + b * A.sb + hd * A.sh;
   const float* Bb = B.ptr + b * B.sb + hd * B.sh;
-  const int tid = threadIdx.x;
+  const int grp = threadIdx.x / kGemmGroup;
+  const int tid = threadIdx.x % kGemmGroup;
   const int tx = tid % 16, ty = tid / 16;   // 8x16 threads, 4x4 outputs each
   float acc[4][4];
 #pragma unroll
@@ -36,14 +42,14 @@ batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long lo
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int e = tid + kGemmThreads * r;
+      const int e = tid + kGemmGroup * r;
       int m, k;
       if (a_kcontig) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
       ra[r] = (m0 + m < M && k0 + k < K) ? Ab[(long long)(m0 + m) * A.s0 + (long long)(k0 + k) * A.s1] : 0.f;
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int e = tid + kGemmThreads * r;
+      const int e = tid + kGemmGroup * r;
       int n, k;
       if (b_ncontig) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
       rb[r] = (n0 + n < N && k0 + k < K) ? Bb[(long long)(k0 + k) * B.s0 + (long long)(n0 + n) * B.s1] : 0.f;
@@ -52,38 +58,48 @@ batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long lo
   auto stash = [&]() {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int e = tid + kGemmThreads * r;
+      const int e = tid + kGemmGroup * r;
       int m, k;
       if (a_kcontig) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
-      As[k][m] = ra[r];
+      As[grp][k][m] = ra[r];
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int e = tid + kGemmThreads * r;
+      const int e = tid + kGemmGroup * r;
       int n, k;
       if (b_ncontig) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
-      Bs[k][n] = rb[r];
+      Bs[grp][k][n] = rb[r];
     }
   };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGemmGroup) : "memory"); };
+  const int kstep = 2 * BK;
+  if (grp * BK < K) fetch(grp * BK);
+  for (int k0 = grp * BK; k0 < K; k0 += kstep) {
     stash();
-    __syncthreads();
-    if (k0 + BK < K) fetch(k0 + BK);
+    group_sync();
+    if (k0 + kstep < K) fetch(k0 + kstep);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[4], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = As[grp][k][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[grp][k][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
-    __syncthreads();
+    group_sync();
   }
+  if (grp == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[tid][i * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (grp == 1) return;
   float* Cb = C + b * sCb + hd * sCh;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -94,7 +110,7 @@ batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long lo
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float* cp = Cb + (long long)m * sCm + (long long)n * sCn;
-      float v = alpha * acc[i][j];
+      float v = alpha * (acc[i][j] + red[tid][i * 4 + j]);
       if (beta != 0.f) v += beta * (*cp);
       if (round_out) v = round_tf32(v);
       *cp = v;
