@@ -327,7 +327,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_p2:
         from loco_edit_b200.weights import P2_256
         del pipe
-        unet._plans.clear()
+        unet.release_plans()
         torch.cuda.empty_cache()
         net2 = B200UNet(P2_256, random_state_dict(P2_256, seed=1234), device=dev)
         pipe2 = EditPipeline(net2, k=3, k_null=5, edit_t=0.2, n_iter=N_ITER, scale=12.0, num_step=1, vis_num=2)

@@ -107,6 +107,11 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """torch's current stream ON `device` (a tensor, a torch.device or None = current device).
+    Kernels are enqueued on the device that owns the tensors, not on the thread's current device, so
+    `--device cuda:1` needs no prior torch.cuda.set_device (the library switches devices itself)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

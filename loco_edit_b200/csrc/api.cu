@@ -13,6 +13,8 @@ struct loco_unet { Model* m; };
 struct loco_plan { Plan* p; };
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+// run on the device that owns the caller's buffers (see DeviceGuard in common.cuh)
+#define ON_DEVICE_OF(ptr) DeviceGuard _dev_guard(static_cast<const void*>(ptr))
 #define GUARD_BEGIN try {
 #define GUARD_END                                            \
   }                                                          \
@@ -96,6 +98,7 @@ int loco_unet_param_info(const loco_unet_t* m, int i, char* name, int name_cap, 
 }
 int loco_unet_load_param(loco_unet_t* m, const char* name, const float* src, long long numel,
                          void* stream) {
+  ON_DEVICE_OF(src);
   GUARD_BEGIN
   LOCO_REQUIRE(m && name && src, "loco_unet_load_param: null argument");
   LOCO_TRY(require_device());
@@ -177,6 +180,7 @@ int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float
                                  const unsigned char* mask, int noise, const float* V, int k1, int k2,
                                  long long d, int align_sign, float* u_full, float* w_out, float* V_out,
                                  float* s_out, void* scratch, void* stream) {
+  ON_DEVICE_OF(xt);
   GUARD_BEGIN
   LOCO_REQUIRE(V_out && s_out && scratch && w_out && mask, "loco_pullback_pair_iteration: null argument");
   const int k = k1 + k2;
@@ -195,6 +199,7 @@ int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float
 static int pullback_probe_impl(loco_plan_t* p, const float* xt, float t, float at,
                                const unsigned char* mask, int noise, const float* V, int k, int k_invert,
                                long long d, float* u_full, float* w_out, void* scratch, void* stream) {
+  ON_DEVICE_OF(xt);
   GUARD_BEGIN
   LOCO_REQUIRE(p && xt && V && u_full && w_out && scratch, "loco_pullback_probe: null argument");
   Plan& P = *p->p;
@@ -226,6 +231,7 @@ int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
                             const unsigned char* mask, int noise, const float* V, int k, long long d,
                             int align_sign, float* u_full, float* w_out, float* V_out, float* s_out,
                             void* scratch, void* stream) {
+  ON_DEVICE_OF(xt);
   GUARD_BEGIN
   LOCO_REQUIRE(V_out && s_out && scratch, "loco_pullback_iteration: null argument");
   const size_t kd = align_up((size_t)k * d * 4, 256);
@@ -242,44 +248,53 @@ int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
 
 // ------------------------------------------------------------------------------------------------
 int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream) {
+  ON_DEVICE_OF(x);
   LOCO_TRY(require_device());
   return pmp_forward(x, eps, at, n, out, ST(stream));
 }
 int loco_orthonormalise(const float* W, int k, long long d, const float* v_prev, float* V,
                         float* s_out, void* scratch, void* stream) {
+  ON_DEVICE_OF(W);
   LOCO_TRY(require_device());
   return orthonormalise(W, k, d, v_prev, V, s_out, reinterpret_cast<double*>(scratch), ST(stream));
 }
 int loco_nullspace_project(const float* vT_mod, int k, const float* Vn, int k_null, long long d,
                            int project, float* out, void* scratch, void* stream) {
+  ON_DEVICE_OF(vT_mod);
   LOCO_TRY(require_device());
   return nullspace_project(vT_mod, k, Vn, k_null, d, project, out, reinterpret_cast<double*>(scratch),
                            ST(stream));
 }
 int loco_ddim_step(const float* xt, const float* et, const float* noise, float at, float at_next,
                    float eta, long long n, float* xt_next, float* x0_pred, void* stream) {
+  ON_DEVICE_OF(xt);
   LOCO_TRY(require_device());
   return ddim_step(xt, et, noise, at, at_next, eta, n, xt_next, x0_pred, ST(stream));
 }
 int loco_axpy(const float* x, const float* v, float scale, long long n, float* out, void* stream) {
+  ON_DEVICE_OF(x);
   LOCO_TRY(require_device());
   return axpy(x, v, scale, n, out, ST(stream));
 }
 int loco_mask_indices(const unsigned char* mask, long long d, int* idx, int* count, void* stream) {
+  ON_DEVICE_OF(mask);
   LOCO_TRY(require_device());
   return mask_indices(mask, d, idx, count, ST(stream));
 }
 int loco_gather_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
                      void* stream) {
+  ON_DEVICE_OF(src);
   LOCO_TRY(require_device());
   return gather_rows(src, rows, d, idx, count, out, ST(stream));
 }
 int loco_scatter_rows(const float* src, int rows, long long d, const int* idx, int count, float* out,
                       void* stream) {
+  ON_DEVICE_OF(src);
   LOCO_TRY(require_device());
   return scatter_rows(src, rows, d, idx, count, out, ST(stream));
 }
 int loco_gram(const float* A, int ka, const float* B, int kb, long long d, double* G, void* stream) {
+  ON_DEVICE_OF(A);
   LOCO_TRY(require_device());
   return gram(A, ka, B, kb, d, G, ST(stream));
 }
@@ -289,6 +304,7 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
                      int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
                      void* stream) {
+  ON_DEVICE_OF(x);
   GUARD_BEGIN
   LOCO_TRY(require_device());
   cudaStream_t s = ST(stream);
@@ -334,6 +350,7 @@ int loco_conv2d_fused_nhwc(const float* x, int N, int H, int W, int Cin, const f
                            const float* x2, int C2, const float* w2, float* wpack, float* wpack2,
                            const float* bias, int bias_rows, float* y, double* stats, int stat_cg,
                            void* stream) {
+  ON_DEVICE_OF(x);
   GUARD_BEGIN
   LOCO_TRY(require_device());
   LOCO_REQUIRE(x && w && y && wpack, "loco_conv2d_fused_nhwc: null argument");
@@ -378,6 +395,7 @@ int loco_conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
                     float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
                     float* ms_out, int* ksplit_out, int* grid_out, void* stream) {
+  ON_DEVICE_OF(x);
   GUARD_BEGIN
   LOCO_TRY(require_device());
   cudaStream_t s = ST(stream);
@@ -430,6 +448,7 @@ int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpac
 int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_primal,
                             const float* gamma, const float* beta, float eps, int silu, float* y,
                             void* stats, void* stream) {
+  ON_DEVICE_OF(x);
   LOCO_TRY(require_device());
   cudaStream_t s = ST(stream);
   View xv = make_view(const_cast<float*>(x), N, H, W, C);
@@ -441,6 +460,7 @@ int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_pr
 int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* gy, int K,
                             const float* gamma, const float* beta, float eps, int silu, float* gx,
                             void* stats, void* stream) {
+  ON_DEVICE_OF(gy);
   LOCO_TRY(require_device());
   cudaStream_t s = ST(stream);
   View xv = make_view(const_cast<float*>(xp), 1, H, W, C);
@@ -455,6 +475,7 @@ int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* g
 }
 int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int head_ch, float* S,
                        float* o, void* stream) {
+  ON_DEVICE_OF(qkv);
   LOCO_TRY(require_device());
   View q = make_view(const_cast<float*>(qkv), N, 1, T, 3 * C);
   View ov = make_view(o, N, 1, T, C);
@@ -462,6 +483,7 @@ int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int 
 }
 int loco_attention_vjp(const float* go, int K, int T, int C, int head_ch, const float* qkv0,
                        const float* P0, float* gP, float* gqkv, void* stream) {
+  ON_DEVICE_OF(go);
   LOCO_TRY(require_device());
   View g = make_view(const_cast<float*>(go), K, 1, T, C);
   View q0 = make_view(const_cast<float*>(qkv0), 1, 1, T, 3 * C);

@@ -161,13 +161,12 @@ int check_tokens(const View& v, const char* what) {
 }  // namespace
 
 int attention_init() {
-  static bool done = false;
-  if (done) return 0;
+  static bool done[kMaxDevices] = {false};
+  if (!first_time_on_device(done)) return 0;
   const int co = cudaSharedmemCarveoutMaxShared;
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_lin_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-  done = true;
   return 0;
 }
 

@@ -64,6 +64,29 @@ inline View slice_n(const View& v, int n0, int N) {
 
 int num_sms();
 
+// ---- multi-device support -----------------------------------------------------------------
+// Every C-ABI entry point runs on the device that OWNS the caller's pointers (not on whatever the
+// host thread's current device happens to be), so `--device cuda:1` works without a prior
+// cudaSetDevice by the caller.  One-time kernel attribute setup, the graph-capture stream and the
+// SM count are kept per device.
+constexpr int kMaxDevices = 64;
+int current_device();                       // cudaGetDevice, 0 on failure
+int pointer_device(const void* dev_ptr);    // device owning a device pointer, -1 if unknown
+struct DeviceGuard {                        // switch to `dev` (>= 0), restore on destruction
+  explicit DeviceGuard(int dev);
+  explicit DeviceGuard(const void* dev_ptr) : DeviceGuard(pointer_device(dev_ptr)) {}
+  ~DeviceGuard();
+  int prev = -1;
+  bool switched = false;
+};
+// true exactly once per device for a given flag array (callers run their per-device setup then)
+inline bool first_time_on_device(bool (&flags)[kMaxDevices]) {
+  const int d = current_device();
+  if (d < 0 || d >= kMaxDevices || flags[d]) return false;
+  flags[d] = true;
+  return true;
+}
+
 // Launch accounting (bench.py's `gpu_launches`) and optional per-kernel-family event timing
 // (bench.py's roofline leg).  Families: 0 = tcgen05 conv GEMM, 1 = GroupNorm, 2 = other.
 void count_launch(int n = 1);

@@ -1476,8 +1476,8 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
 }
 
 int conv_init() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};
+  if (first_time_on_device(attr_set)) {
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<2>,
@@ -1488,7 +1488,6 @@ int conv_init() {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_pair_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
-    attr_set = true;
   }
   return 0;
 }

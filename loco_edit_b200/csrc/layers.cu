@@ -786,8 +786,8 @@ static int g_res_stats0[2], g_res_stats1[2], g_res_apply0[2], g_res_apply1[2];  
 // All kernels of the U-Net programs ask for the same (maximum shared memory) L1/smem split as the
 // tcgen05 conv kernel, so the SMs never have to re-partition between consecutive launches.
 int layers_init() {
-  static bool done = false;
-  if (done) return 0;
+  static bool done[kMaxDevices] = {false};
+  if (!first_time_on_device(done)) return 0;
   const int co = cudaSharedmemCarveoutMaxShared;
 #define LOCO_CARVE(k) LOCO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co))
   LOCO_CARVE(gn_stats_kernel<0>); LOCO_CARVE(gn_stats_kernel<1>);
@@ -806,7 +806,6 @@ int layers_init() {
     gn_resident(gn_apply_kernel<0>, bd, &g_res_apply0[b]);
     gn_resident(gn_apply_kernel<1>, bd, &g_res_apply1[b]);
   }
-  done = true;
   return 0;
 }
 

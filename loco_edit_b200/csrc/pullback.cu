@@ -59,28 +59,31 @@ __global__ void pmp_fwd_kernel(const float* __restrict__ x, const float* __restr
 // ------------------------------------------------------------------------------------------------
 // Small ranks (<= 8 rows each side): every thread keeps the whole ka x kb accumulator in registers
 // and streams d with coalesced loads; one double atomic per entry per block.
+// Products and sums are fp64 throughout (the product of two floats is exact in a double), so the
+// Gram matrix carries the full fp32 precision of W: eigenvalues down to ~1e-14 of the largest are
+// resolved, where fp32 partial sums would square the condition number into the 1e-7 rounding floor.
 __global__ void __launch_bounds__(256)
 gram_small_kernel(const float* __restrict__ A, int ka, const float* __restrict__ B, int kb,
                   long long d, double* __restrict__ G) {
-  float acc[8][8];
+  double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  // each block owns a contiguous slab so partial sums stay short (fp32 partials, fp64 totals)
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  // each block owns a contiguous slab
   const long long per_block = (d + gridDim.x - 1) / gridDim.x;
   const long long c0 = blockIdx.x * per_block;
   const long long c1 = min(d, c0 + per_block);
   for (long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-    float a[8], b[8];
+    double a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = i < ka ? A[i * d + c] : 0.f;
+    for (int i = 0; i < 8; ++i) a[i] = i < ka ? (double)A[i * d + c] : 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = j < kb ? B[j * d + c] : 0.f;
+    for (int j = 0; j < 8; ++j) b[j] = j < kb ? (double)B[j * d + c] : 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
   }
   __shared__ double red[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,7 +91,7 @@ gram_small_kernel(const float* __restrict__ A, int ka, const float* __restrict__
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const double v = warp_sum((double)acc[i][j]);
+      const double v = warp_sum(acc[i][j]);
       if (lane == 0) red[warp][i * 8 + j] = v;
     }
   __syncthreads();
@@ -110,11 +113,11 @@ gram_big_kernel(const float* __restrict__ A, int ka, const float* __restrict__ B
   __shared__ float As[64][kGramSlab + 1];
   __shared__ float Bs[64][kGramSlab + 1];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  float acc[4][4];
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int sl = 0; sl < slabs_per_block; ++sl) {
     const long long c0 = ((long long)blockIdx.x * slabs_per_block + sl) * kGramSlab;
     if (c0 >= d) break;
@@ -127,15 +130,15 @@ gram_big_kernel(const float* __restrict__ A, int ka, const float* __restrict__ B
     __syncthreads();
 #pragma unroll 8
     for (int c = 0; c < kGramSlab; ++c) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][c];
+      for (int i = 0; i < 4; ++i) a[i] = (double)As[ty * 4 + i][c];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[tx * 4 + j][c];
+      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[tx * 4 + j][c];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -144,16 +147,22 @@ gram_big_kernel(const float* __restrict__ A, int ka, const float* __restrict__ B
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = ty * 4 + i, c = tx * 4 + j;
-      if (r < ka && c < kb) atomicAdd(&G[r * kb + c], (double)acc[i][j]);
+      if (r < ka && c < kb) atomicAdd(&G[r * kb + c], acc[i][j]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // k x k symmetric eigen-decomposition (cyclic Jacobi, fp64) -> transform T = L^-1/2 Q^T
 // scratch layout: G[k*k] | C2[k*k] | T[k*k] | lambda[k] | (unused k)
+// mode 0 / 1: T = diag(sign) L^-1/2 Q^T of G = W W^T, rows by descending eigenvalue (1: signs from
+// C2 = W V_prev^T), s_out = L^(1/4).
+// mode 2 (re-orthonormalisation pass, "CholeskyQR2" in its symmetric / Loewdin form): G = V1 V1^T
+// of the first-pass result V1 = T W; T <- G^-1/2 T, which keeps row order and signs (G ~ I) and
+// brings ||V V^T - I|| from cond(W)^2 * 1e-7 down to fp32 round-off.  s_out is not touched.
 // ------------------------------------------------------------------------------------------------
-__global__ void eig_transform_kernel(double* __restrict__ scratch, int k, int has_prev,
+__global__ void eig_transform_kernel(double* __restrict__ scratch, int k, int mode,
                                      float* __restrict__ s_out) {
+  const int has_prev = mode == 1;
   extern __shared__ double sm[];
   double* A = sm;                 // k*k
   double* Q = sm + k * k;         // k*k
@@ -207,6 +216,27 @@ __global__ void eig_transform_kernel(double* __restrict__ scratch, int k, int ha
       }
   }
   __syncthreads();
+  if (mode == 2) {
+    // A (k*k) is free once the eigenvalues are read: build S = Q L^-1/2 Q^T there, then T <- S T
+    if (t < k) { double l = A[t * k + t]; lam[t] = 1.0 / sqrt(l < 1e-300 ? 1e-300 : l); }
+    __syncthreads();
+    for (int e = t; e < k * k; e += blockDim.x) {
+      const int i = e / k, j = e % k;
+      double acc = 0.0;
+      for (int m = 0; m < k; ++m) acc += Q[i * k + m] * lam[m] * Q[j * k + m];
+      A[e] = acc;
+    }
+    __syncthreads();
+    for (int e = t; e < k * k; e += blockDim.x) {     // Q <- S T (Q is free now)
+      const int i = e / k, j = e % k;
+      double acc = 0.0;
+      for (int m = 0; m < k; ++m) acc += A[i * k + m] * T[m * k + j];
+      Q[e] = acc;
+    }
+    __syncthreads();
+    for (int e = t; e < k * k; e += blockDim.x) T[e] = Q[e];
+    return;
+  }
   if (t == 0) {
     for (int i = 0; i < k; ++i) { lam[i] = A[i * k + i]; order[i] = i; }
     for (int i = 0; i < k; ++i) {          // selection sort, descending
@@ -234,27 +264,29 @@ __global__ void eig_transform_kernel(double* __restrict__ scratch, int k, int ha
   }
 }
 
-// V[i][c] = sum_j T[i][j] W[j][c]
+// V[i][c] = sum_j T[i][j] W[j][c], accumulated in fp64: rows of T that belong to small singular
+// values have entries ~ 1/sigma and cancel against nearly dependent rows of W, so fp32 products
+// would lose cond(W) * 6e-8 of the result.
 __global__ void apply_transform_kernel(const float* __restrict__ W, const double* __restrict__ T,
                                        int k, long long d, float* __restrict__ V) {
-  extern __shared__ float Ts[];   // k*k
-  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Ts[e] = (float)T[e];
+  extern __shared__ double Ts[];   // k*k
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Ts[e] = T[e];
   __syncthreads();
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < d;
        c += (long long)gridDim.x * blockDim.x) {
     for (int i0 = 0; i0 < k; i0 += 8) {
-      float acc[8];
+      double acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0;
       for (int j = 0; j < k; ++j) {
-        const float w = W[j * d + c];
+        const double w = (double)W[j * d + c];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (i0 + i < k) acc[i] = fmaf(Ts[(i0 + i) * k + j], w, acc[i]);
+          if (i0 + i < k) acc[i] = fma(Ts[(i0 + i) * k + j], w, acc[i]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (i0 + i < k) V[(i0 + i) * d + c] = acc[i];
+        if (i0 + i < k) V[(i0 + i) * d + c] = (float)acc[i];
     }
   }
 }
@@ -416,15 +448,23 @@ int orthonormalise(const float* W, int k, long long d, const float* v_prev, floa
   LOCO_TRY(gram(W, k, W, k, d, scratch, s));
   if (v_prev) LOCO_TRY(gram(W, k, v_prev, k, d, scratch + k * k, s));
   const size_t smem = sizeof(double) * (size_t)(2 * k * k + k) + sizeof(int) * (size_t)k;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};
+  if (first_time_on_device(attr_set)) {
     LOCO_CHECK_CUDA(cudaFuncSetAttribute(eig_transform_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    attr_set = true;
   }
   eig_transform_kernel<<<1, 64, smem, s>>>(scratch, k, v_prev ? 1 : 0, s_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
-  apply_transform_kernel<<<grid_for(d, 256), 256, sizeof(float) * (size_t)(k * k), s>>>(
+  apply_transform_kernel<<<grid_for(d, 256), 256, sizeof(double) * (size_t)(k * k), s>>>(
+      W, scratch + 2 * k * k, k, d, V);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  // second pass: V1 V1^T = I + E with |E| ~ cond(W)^2 * 1e-7 (the Gram route squares the condition
+  // number); fold G2^-1/2 into the transform and re-apply it to W (no [k,d] temporary needed)
+  LOCO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)(k * k), s));
+  LOCO_TRY(gram(V, k, V, k, d, scratch, s));
+  eig_transform_kernel<<<1, 64, smem, s>>>(scratch, k, 2, s_out);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  apply_transform_kernel<<<grid_for(d, 256), 256, sizeof(double) * (size_t)(k * k), s>>>(
       W, scratch + 2 * k * k, k, d, V);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -64,15 +64,35 @@ int profile_collect(double* ms, double* work, long long* launches, int nfam) {
   return 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev;
+}
+int pointer_device(const void* p) {
+  if (p == nullptr) return -1;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return -1;
+  return a.device;
+}
+DeviceGuard::DeviceGuard(int dev) {
+  if (dev < 0) return;
+  if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; return; }
+  if (prev != dev && cudaSetDevice(dev) == cudaSuccess) switched = true;
+}
+DeviceGuard::~DeviceGuard() {
+  if (switched) cudaSetDevice(prev);
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  int& v = n[dev < kMaxDevices ? dev : 0];
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
   }
-  return n;
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +486,13 @@ int Plan::build(float* workspace) {
   Impl& I = *impl;
   const bool dry = workspace == nullptr;
   LOCO_REQUIRE(dry || I.sized, "plan: size query must precede binding");
+  if (!dry) device = pointer_device(workspace);
+  DeviceGuard guard(device);
+  if (!dry && model->arena != nullptr) {
+    const int wdev = pointer_device(model->arena);
+    LOCO_REQUIRE(wdev < 0 || device < 0 || wdev == device,
+                 "plan: workspace lives on device %d but the model weights on device %d", device, wdev);
+  }
   LOCO_REQUIRE(NP >= 1 && NT >= 0 && NC >= 0, "plan: bad batch configuration");
   LOCO_REQUIRE((NT == 0 && NC == 0) || NP == 1, "plan: tangents/cotangents need exactly one primal row");
   const Model& M = *model;
@@ -1017,7 +1044,9 @@ static int run_program(std::vector<Fn>& ops, double* stats, size_t stat_bytes, c
   if (*exec == nullptr) {
     // capture on a private stream (the caller's may be the legacy default stream, which cannot
     // be captured); nothing executes during capture, the graph is then launched on `s`
-    static cudaStream_t cap = nullptr;
+    static cudaStream_t caps[kMaxDevices] = {nullptr};
+    const int cdev = current_device();
+    cudaStream_t& cap = caps[cdev < kMaxDevices ? cdev : 0];
     if (!cap) LOCO_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     const long long l0 = launch_count();
@@ -1039,6 +1068,7 @@ static int run_program(std::vector<Fn>& ops, double* stats, size_t stat_bytes, c
 
 int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
+  DeviceGuard guard(device);
   Impl& I = *impl;
   const size_t bytes = sizeof(float) * (size_t)(NP + NT) * 3 * model->arch.resolution * model->arch.resolution;
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.in_buf, x, bytes, cudaMemcpyDeviceToDevice, s));
@@ -1052,6 +1082,7 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
 int Plan::vjp(const float* g_eps, float* gx, cudaStream_t s) {
   LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
   LOCO_REQUIRE(NC > 0, "plan: built without cotangent rows");
+  DeviceGuard guard(device);
   Impl& I = *impl;
   const size_t bytes = sizeof(float) * (size_t)NC * 3 * model->arch.resolution * model->arch.resolution;
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.gin_buf, g_eps, bytes, cudaMemcpyDeviceToDevice, s));

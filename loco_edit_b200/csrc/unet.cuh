@@ -106,6 +106,7 @@ class Plan {
   int NP, NT, NC;
   size_t workspace_floats = 0;
   float* base = nullptr;
+  int device = -1;    // device owning the bound workspace (every launch of the plan runs there)
   double fwd_flops = 0, vjp_flops = 0;
   int fwd_launches = 0, vjp_launches = 0;
 

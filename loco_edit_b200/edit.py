@@ -17,6 +17,7 @@ Deliberate deviations (documented in DESIGN.md): no CPU staging of latents (`buf
 the reference's convergence test (:2489-2494) is not defeated by SVD sign flips (`align_sign`);
 `v0=` lets a caller inject the initial basis for deterministic parity runs.
 """
+import collections
 import os
 
 import torch
@@ -26,10 +27,27 @@ from .scheduler import YHCustomScheduler
 
 
 def _pb_workspace(unet, k):
-    cache = unet.__dict__.setdefault("_pb_cache", {})
+    """Power-method buffers for rank k, LRU-bounded (each entry pins the [k,d] iteration buffers; the
+    (1,k,k) plan behind it lives in the U-Net's own bounded plan cache)."""
+    cache = unet.__dict__.setdefault("_pb_cache", collections.OrderedDict())
+    if k in cache:
+        cache.move_to_end(k)
+        if cache[k].plan.released:          # its plan was evicted meanwhile: rebuild
+            del cache[k]
     if k not in cache:
+        while len(cache) >= unet.max_cached_plans:
+            cache.popitem(last=False)
         cache[k] = ops.PullbackWorkspace(unet, k)
     return cache[k]
+
+
+def random_basis(d, k, device, generator=None):
+    """Algorithm-1 init (src/modules/edit.py:2435-2438: Q of qr(randn(d, k))): an orthonormalised
+    Gaussian block, through the library's own orthonormalisation kernel (no cuSOLVER on the path).
+    Same distribution (Haar) as the reference's; parity runs inject the reference's draw via v0=."""
+    g = torch.randn(k, d, device=device, dtype=torch.float32, generator=generator)
+    V, _ = ops.orthonormalise(g)
+    return V
 
 
 def local_basis(unet, scheduler, x, t, pca_rank, v0=None, min_iter=10, max_iter=100,
@@ -60,10 +78,7 @@ def local_basis(unet, scheduler, x, t, pca_rank, v0=None, min_iter=10, max_iter=
         mask_u8 = mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
         assert mask_u8.numel() == d, "mask must cover (c, h, w) of x"
     if v0 is None:
-        # Algorithm 1 init (src/modules/edit.py:2435-2438)
-        vT = torch.randn(d, k, device=dev, dtype=torch.float)
-        vT, _ = torch.linalg.qr(vT)
-        v0 = vT.T.contiguous()
+        v0 = random_basis(d, k, dev)
     cur, nxt = ws.V
     cur.copy_(v0.reshape(k, d))
     for i in range(max_iter):
@@ -100,8 +115,7 @@ def _local_basis_chunked(unet, scheduler, x, t, k, v0, min_iter, max_iter, conve
     at = scheduler.alpha_at(t_host)
     mask_u8 = None if mask is None else mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
     if v0 is None:
-        q, _ = torch.linalg.qr(torch.randn(d, k, device=dev, dtype=torch.float))
-        v0 = q.T
+        v0 = random_basis(d, k, dev)
     V = v0.reshape(k, d).contiguous().clone()
     num_chunk = k // chunk_size if k % chunk_size == 0 else k // chunk_size + 1
     sizes = [c.shape[0] for c in torch.empty(k, 1).chunk(num_chunk)]
@@ -148,8 +162,7 @@ def local_basis_pair(unet, scheduler, x, t, k, k_null, mask, v0=None, v0_null=No
     cur, nxt = ws.V
     for v, lo, kk in ((v0, 0, k), (v0_null, k, k_null)):
         if v is None:
-            q, _ = torch.linalg.qr(torch.randn(d, kk, device=dev, dtype=torch.float))
-            v = q.T
+            v = random_basis(d, kk, dev)
         cur[lo:lo + kk].copy_(v.reshape(kk, d))
     for _ in range(n_iter):
         ws.iterate_pair(x, t_host, at, mask_u8, noise, cur, nxt, k, k_null, align_sign=align_sign)
@@ -199,13 +212,20 @@ class EditUncondDiffusion(object):
             raise NotImplementedError("the uncond hot path runs in fp32/TF32 (all reference scripts use --dtype fp32)")
         if unet is None:
             from .unet import B200UNet
-            from .weights import DDPM256, P2_256, random_state_dict
+            from .weights import (DDPM256, P2_256, hf_unet2d_to_ddpm, is_hf_unet2d_state_dict,
+                                  random_state_dict)
             # the reference picks the network family by model name (utils/utils.py:95-131):
             # "*_P2" -> guided-diffusion UNetModel(P2_DICT); "*_HF" -> the DDPM U-Net architecture
+            if self.model_name == "FFHQ_HF":
+                # google/ncsnpp-ffhq-256 (utils/utils.py:99-100) is an NCSN++ score network, not this U-Net
+                raise NotImplementedError("FFHQ_HF (google/ncsnpp-ffhq-256, NCSN++) is not an architecture of "
+                                          "this hot path; the DDPM (*_HF, CelebA_HQ) and P2 (*_P2) U-Nets are")
             base = P2_256 if self.model_name.endswith("_P2") else DDPM256
             arch = dict(base, resolution=self.image_size)
             wp = getattr(args, "weights_path", "")
             sd = torch.load(wp, map_location="cpu") if wp else random_state_dict(arch, seed=1234)
+            if base is DDPM256 and is_hf_unet2d_state_dict(sd):
+                sd = hf_unet2d_to_ddpm(sd, arch)     # a diffusers UNet2DModel checkpoint (*_HF models)
             unet = B200UNet(arch, sd, device=self.device)
         self.unet = unet
         self.scheduler = YHCustomScheduler(args, device=self.device)
@@ -292,15 +312,29 @@ class EditUncondDiffusion(object):
         return xt
 
     def _get_masks(self, idx, use_mask):
-        """Mask sources of src/modules/edit.py:2234-2267 without the SAM network: the dataset's
-        ground-truth mask, or a cached `mask/mask.pt` (bool [n,res,res], mask_segmentation.py:23-25)."""
-        mpath = os.path.join(self.result_folder, "mask/mask.pt")
-        if self.dataset_name == "CelebA_HQ_mask" or not os.path.exists(mpath):
+        """Mask sources of src/modules/edit.py:2234-2267.
+          CelebA_HQ_mask : the dataset's ground-truth semantic mask (:2248-2251), always used;
+          Random / FFHQ / AFHQ / ... : `mask/mask.pt` (bool [n,1,res,res] written by
+            MaskSegmentation.mask_segmentation, mask_segmentation.py:18-26), row `--mask_index`,
+            repeated over the 3 channels (:2247, :2262-2265); `use_mask=False` -> None (unmasked
+            pull-back, :2266-2267).
+        The SAM network that writes mask.pt in the reference is out of scope: a
+        missing file is an error here, never a silent substitute."""
+        if self.dataset_name == "CelebA_HQ_mask":
             return self.dataset.getmask(idx=getattr(self.args, "sample_idx", idx),
                                         choose_sem=getattr(self.args, "choose_sem", None))
-        if not use_mask:
+        if not use_mask and self.dataset_name != "Random":
             return None
-        masks = torch.load(mpath)
+        mpath = os.path.join(self.result_folder, "mask/mask.pt")
+        if not os.path.exists(mpath):
+            if hasattr(self.dataset, "getmask") and getattr(self.args, "allow_dataset_mask", False):
+                return self.dataset.getmask(idx=idx, choose_sem=None)
+            raise FileNotFoundError(
+                f"{mpath} not found: dataset '{self.dataset_name}' takes its masks from a cached mask.pt "
+                "(the reference generates it with SAM, which this path does not ship). Write a bool "
+                "[n,1,res,res] tensor there (loco_edit_b200.masks.save_masks), or pass "
+                "--allow_dataset_mask True to use the synthetic dataset's rectangle on purpose.")
+        masks = torch.load(mpath, map_location="cpu")
         return masks[getattr(self.args, "mask_index", 0)].squeeze(dim=0).repeat(3, 1, 1)
 
     @torch.no_grad()
@@ -416,7 +450,7 @@ class EditUncondDiffusion(object):
     @torch.no_grad()
     def DDIMforwardsteps(self, xt, t_start_idx, t_end_idx, vis_psd=False, save_image=True,
                          return_xt=True, performance_boosting=False):
-        """src/modules/edit.py:2508-2614 (batch chunking by memory_bound and CPU staging dropped)."""
+        """src/modules/edit.py:2508-2614 (CPU staging of the latents dropped; `memory_bound` chunking kept)."""
         assert (t_start_idx < self.for_steps) & (t_end_idx <= self.for_steps)
         self.scheduler.set_timesteps(self.for_steps, device=self.device)
         ts = self.scheduler._ts_host
@@ -430,7 +464,10 @@ class EditUncondDiffusion(object):
             boost = performance_boosting and (self.performance_boosting_t_idx <= i) and \
                 (self.performance_boosting_t_idx != n - 1)
             eta = 1 if boost else 0
-            et = self.unet(xt, ts[i])
+            if xt.size(0) <= self.memory_bound:
+                et = self.unet(xt, ts[i])
+            else:   # src/modules/edit.py:2564-2576: the batch goes through the U-Net in chunks
+                et = torch.cat([self.unet(c.contiguous(), ts[i]) for c in xt.split(self.memory_bound)], 0)
             noise = self.noise_fn(i, xt) if (eta and self.noise_fn is not None) else None
             xt = self.scheduler.step(et, ts[i], xt, eta=eta, t_idx=i, noise=noise).prev_sample
         if performance_boosting:

@@ -25,7 +25,7 @@ def _aligned(buf):
 def pmp_forward(x, eps, at):
     """(x - eps*sqrt(1-at))/sqrt(at) -- get_x0 without mask (reference modules/edit.py:2386)."""
     out = torch.empty_like(_f32(x))
-    check(_lib.load().loco_pmp_forward(ptr(x), ptr(_f32(eps)), float(at), x.numel(), ptr(out), stream_ptr()),
+    check(_lib.load().loco_pmp_forward(ptr(x), ptr(_f32(eps)), float(at), x.numel(), ptr(out), stream_ptr(x)),
           "loco_pmp_forward")
     return out
 
@@ -40,7 +40,7 @@ def orthonormalise(W, v_prev=None):
     s = torch.empty(k, dtype=torch.float32, device=W.device)
     scr = _scratch(lib.loco_orthonormalise_scratch_bytes(k), W.device)
     check(lib.loco_orthonormalise(ptr(W), k, d, ptr(_f32(v_prev)) if v_prev is not None else None,
-                                  ptr(V), ptr(s), _aligned(scr), stream_ptr()), "loco_orthonormalise")
+                                  ptr(V), ptr(s), _aligned(scr), stream_ptr(W)), "loco_orthonormalise")
     return V, s
 
 
@@ -53,7 +53,7 @@ def nullspace_project(vT_mod, vT_null, project=True):
     out = torch.empty_like(vT_mod)
     scr = _scratch(8 * (kn * k + k), vT_mod.device)
     check(lib.loco_nullspace_project(ptr(vT_mod), k, ptr(_f32(vT_null)) if kn else None, kn, d,
-                                     1 if (project and kn) else 0, ptr(out), _aligned(scr), stream_ptr()),
+                                     1 if (project and kn) else 0, ptr(out), _aligned(scr), stream_ptr(vT_mod)),
           "loco_nullspace_project")
     return out
 
@@ -65,7 +65,7 @@ def ddim_step(xt, et, at, at_next, eta=0.0, noise=None, want_x0=False):
     x0 = torch.empty_like(xt) if want_x0 else None
     check(_lib.load().loco_ddim_step(ptr(xt), ptr(_f32(et)), ptr(_f32(noise)) if noise is not None else None,
                                      float(at), float(at_next), float(eta), xt.numel(), ptr(out),
-                                     ptr(x0), stream_ptr()), "loco_ddim_step")
+                                     ptr(x0), stream_ptr(xt)), "loco_ddim_step")
     return (out, x0) if want_x0 else out
 
 
@@ -73,7 +73,7 @@ def axpy(x, v, scale):
     """x + scale * v (reference modules/edit.py:2623)."""
     x = _f32(x)
     out = torch.empty_like(x)
-    check(_lib.load().loco_axpy(ptr(x), ptr(_f32(v)), float(scale), x.numel(), ptr(out), stream_ptr()),
+    check(_lib.load().loco_axpy(ptr(x), ptr(_f32(v)), float(scale), x.numel(), ptr(out), stream_ptr(x)),
           "loco_axpy")
     return out
 
@@ -85,7 +85,7 @@ def mask_indices(mask):
     assert m.is_cuda
     idx = torch.empty(m.numel(), dtype=torch.int32, device=m.device)
     cnt = torch.zeros(1, dtype=torch.int32, device=m.device)
-    check(_lib.load().loco_mask_indices(ptr(m), m.numel(), ptr(idx), ptr(cnt), stream_ptr()),
+    check(_lib.load().loco_mask_indices(ptr(m), m.numel(), ptr(idx), ptr(cnt), stream_ptr(m)),
           "loco_mask_indices")
     return idx[: int(cnt.item())]
 
@@ -94,7 +94,7 @@ def gather_rows(src, idx):
     src = _f32(src)
     rows, d = src.shape
     out = torch.empty(rows, idx.numel(), dtype=torch.float32, device=src.device)
-    check(_lib.load().loco_gather_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr()),
+    check(_lib.load().loco_gather_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr(src)),
           "loco_gather_rows")
     return out
 
@@ -103,7 +103,7 @@ def scatter_rows(src, idx, d):
     src = _f32(src)
     rows = src.shape[0]
     out = torch.empty(rows, d, dtype=torch.float32, device=src.device)
-    check(_lib.load().loco_scatter_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr()),
+    check(_lib.load().loco_scatter_rows(ptr(src), rows, d, ptr(idx), idx.numel(), ptr(out), stream_ptr(src)),
           "loco_scatter_rows")
     return out
 
@@ -111,7 +111,7 @@ def scatter_rows(src, idx, d):
 def gram(A, B):
     A, B = _f32(A), _f32(B)
     G = torch.zeros(A.shape[0], B.shape[0], dtype=torch.float64, device=A.device)
-    check(_lib.load().loco_gram(ptr(A), A.shape[0], ptr(B), B.shape[0], A.shape[1], ptr(G), stream_ptr()),
+    check(_lib.load().loco_gram(ptr(A), A.shape[0], ptr(B), B.shape[0], A.shape[1], ptr(G), stream_ptr(A)),
           "loco_gram")
     return G
 
@@ -136,7 +136,7 @@ class PullbackWorkspace:
         check(self.lib.loco_pullback_iteration(
             self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8) if mask_u8 is not None else None,
             1 if noise else 0, ptr(V_in), self.k, self.d, 1 if align_sign else 0, ptr(self.u_full),
-            ptr(self.w), ptr(V_out), ptr(self.s), _aligned(self.scratch), stream_ptr()),
+            ptr(self.w), ptr(V_out), ptr(self.s), _aligned(self.scratch), stream_ptr(xt)),
             "loco_pullback_iteration")
 
 
@@ -146,14 +146,14 @@ class PullbackWorkspace:
         check(self.lib.loco_pullback_pair_iteration(
             self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8), 1 if noise else 0, ptr(V_in),
             k1, k2, self.d, 1 if align_sign else 0, ptr(self.u_full), ptr(self.w), ptr(V_out),
-            ptr(self.s), _aligned(self.scratch), stream_ptr()), "loco_pullback_pair_iteration")
+            ptr(self.s), _aligned(self.scratch), stream_ptr(xt)), "loco_pullback_pair_iteration")
 
     def probe(self, xt, t, at, mask_u8, noise, V_in):
         """Rows of U (masked J V^T) and W (J^T U) for the k rows of V_in, no orthonormalisation."""
         check(self.lib.loco_pullback_probe(
             self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8) if mask_u8 is not None else None,
             1 if noise else 0, ptr(V_in), self.k, self.d, ptr(self.u_full), ptr(self.w),
-            _aligned(self.scratch), stream_ptr()), "loco_pullback_probe")
+            _aligned(self.scratch), stream_ptr(xt)), "loco_pullback_probe")
         return self.u_full, self.w
 
 
@@ -174,7 +174,7 @@ def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=Fals
     scr = torch.zeros(16 << 20, dtype=torch.uint8, device=x.device) if splitk else None
     check(_lib.load().loco_conv2d_nhwc(kind, ptr(x), N, H, W_, Cx, ptr(w), Cout, Cin, ptr(wpack),
                                        ptr(bias), bias_rows, ptr(addend), 1 if accumulate else 0,
-                                       ptr(out), ptr(scr), scr.numel() if splitk else 0, stream_ptr()),
+                                       ptr(out), ptr(scr), scr.numel() if splitk else 0, stream_ptr(x)),
           "loco_conv2d_nhwc")
     return out
 
@@ -198,7 +198,7 @@ def conv2d_fused_nhwc(x, w, x2=None, w2=None, bias=None, bias_rows=0, stat_group
         stats = torch.zeros(N, 32, 2, dtype=torch.float64, device=x.device)
     check(_lib.load().loco_conv2d_fused_nhwc(ptr(x), N, H, W_, Cin, ptr(w), Cout, ptr(x2), C2, ptr(w2),
                                              ptr(wpack), ptr(wpack2), ptr(bias), bias_rows, ptr(out),
-                                             ptr(stats), Cout // 32 if stat_groups else 0, stream_ptr()),
+                                             ptr(stats), Cout // 32 if stat_groups else 0, stream_ptr(x)),
           "loco_conv2d_fused_nhwc")
     return (out, stats) if stat_groups else out
 
@@ -210,7 +210,7 @@ def groupnorm_silu_fwd(x, n_primal, gamma, beta, eps, silu):
     stats = torch.empty(64 * N, dtype=torch.float64, device=x.device)
     check(_lib.load().loco_groupnorm_silu_fwd(ptr(x), N, H, W_, Cc, n_primal, ptr(_f32(gamma)),
                                               ptr(_f32(beta)), float(eps), 1 if silu else 0, ptr(y),
-                                              ptr(stats), stream_ptr()), "loco_groupnorm_silu_fwd")
+                                              ptr(stats), stream_ptr(x)), "loco_groupnorm_silu_fwd")
     return y
 
 
@@ -221,7 +221,7 @@ def groupnorm_silu_vjp(xp, gy, gamma, beta, eps, silu):
     stats = torch.empty(64 * (K + 1), dtype=torch.float64, device=gy.device)
     check(_lib.load().loco_groupnorm_silu_vjp(ptr(xp), H, W_, Cc, ptr(gy), K, ptr(_f32(gamma)),
                                               ptr(_f32(beta)), float(eps), 1 if silu else 0, ptr(gx),
-                                              ptr(stats), stream_ptr()), "loco_groupnorm_silu_vjp")
+                                              ptr(stats), stream_ptr(gy)), "loco_groupnorm_silu_vjp")
     return gx
 
 
@@ -234,7 +234,7 @@ def attention_fwd(qkv, n_primal, head_ch=0):
     S = torch.empty(N, heads, T, T, dtype=torch.float32, device=qkv.device)
     o = torch.empty(N, T, Cc, dtype=torch.float32, device=qkv.device)
     check(_lib.load().loco_attention_fwd(ptr(qkv), N, T, Cc, n_primal, head_ch, ptr(S), ptr(o),
-                                         stream_ptr()), "loco_attention_fwd")
+                                         stream_ptr(qkv)), "loco_attention_fwd")
     return o, (S if head_ch > 0 else S[:, 0])
 
 
@@ -245,5 +245,5 @@ def attention_vjp(go, qkv0, P0, head_ch=0):
     gP = torch.empty(K, heads, T, T, dtype=torch.float32, device=go.device)
     gqkv = torch.empty(K, T, 3 * Cc, dtype=torch.float32, device=go.device)
     check(_lib.load().loco_attention_vjp(ptr(go), K, T, Cc, head_ch, ptr(_f32(qkv0)), ptr(_f32(P0)),
-                                         ptr(gP), ptr(gqkv), stream_ptr()), "loco_attention_vjp")
+                                         ptr(gP), ptr(gqkv), stream_ptr(go)), "loco_attention_vjp")
     return gqkv

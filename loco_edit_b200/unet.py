@@ -5,6 +5,7 @@ the reference's `self.unet(xt, t)` (src/modules/edit.py:2151, 2375, 2572); `jvp`
 fused primal+tangent and transposed passes the power method is built from.  All arithmetic runs in
 libloco_b200.so; torch only owns the device memory and the stream.
 """
+import collections
 import ctypes as C
 
 import torch
@@ -55,6 +56,15 @@ class Plan:
         check(self.lib.loco_plan_info(h, C.byref(ff), C.byref(vf), C.byref(fo), C.byref(vo)))
         self.fwd_flops, self.vjp_flops = ff.value, vf.value
         self.fwd_ops, self.vjp_ops = fo.value, vo.value
+        self.released = False
+
+    def release(self):
+        """Free the plan's workspace and launch programs now (evicted from the U-Net's plan cache)."""
+        if not self.released:
+            self.released = True
+            self.lib.loco_plan_destroy(self.handle)
+            self.handle = None
+            self.workspace = None
 
     def forward(self, x, t, out=None):
         n = self.shape[0] + self.shape[1]
@@ -63,7 +73,7 @@ class Plan:
         assert tuple(x.shape) == (n, 3, R, R), (tuple(x.shape), n, R)
         if out is None:
             out = torch.empty_like(x)
-        check(self.lib.loco_unet_forward(self.handle, ptr(x), float(t), ptr(out), stream_ptr()),
+        check(self.lib.loco_unet_forward(self.handle, ptr(x), float(t), ptr(out), stream_ptr(x)),
               "loco_unet_forward")
         return out
 
@@ -74,17 +84,22 @@ class Plan:
         assert tuple(g_eps.shape) == (k, 3, R, R)
         if out is None:
             out = torch.empty_like(g_eps)
-        check(self.lib.loco_unet_vjp(self.handle, ptr(g_eps), ptr(out), stream_ptr()), "loco_unet_vjp")
+        check(self.lib.loco_unet_vjp(self.handle, ptr(g_eps), ptr(out), stream_ptr(g_eps)), "loco_unet_vjp")
         return out
 
     def __del__(self):
         try:
-            self.lib.loco_plan_destroy(self.handle)
+            self.release()
         except Exception:
             pass
 
 
 class B200UNet:
+    # every plan pins a full activation workspace (1.5 GB for (1,0,0), 16 GB for (1,5,5) at 256^2):
+    # keep the most recently used few, release the rest (a run that mixes many ranks / batch sizes
+    # must not grow without bound)
+    max_cached_plans = 8
+
     def __init__(self, arch, state_dict, device="cuda:0"):
         self.lib = _lib.load()
         self.arch = dict(arch)
@@ -99,7 +114,7 @@ class B200UNet:
         self.arena = torch.zeros(n + 64, dtype=torch.float32, device=self.device)
         off = ((-self.arena.data_ptr()) % 256) // 4
         check(self.lib.loco_unet_bind_weights(h, C.c_void_p(self.arena.data_ptr() + 4 * off)))
-        self._plans = {}
+        self._plans = collections.OrderedDict()
         self.load_state_dict(state_dict)
 
     def param_shapes(self):
@@ -124,15 +139,26 @@ class B200UNet:
                     raise _lib.LocoError("parameter %s has shape %s, expected %s" % (name, tuple(w.shape), shape))
                 wd = w.detach().to(device=self.device, dtype=torch.float32).contiguous()
                 check(self.lib.loco_unet_load_param(self.handle, name.encode(), ptr(wd), wd.numel(),
-                                                    stream_ptr()), "loco_unet_load_param(%s)" % name)
-            torch.cuda.current_stream().synchronize()
+                                                    stream_ptr(self.device)), "loco_unet_load_param(%s)" % name)
+            torch.cuda.current_stream(self.device).synchronize()
 
     def plan(self, n_primal, n_tangent=0, n_cot=0):
         key = (n_primal, n_tangent, n_cot)
-        if key not in self._plans:
-            with torch.cuda.device(self.device):
-                self._plans[key] = Plan(self, *key)
+        if key in self._plans:
+            self._plans.move_to_end(key)
+            return self._plans[key]
+        while len(self._plans) >= self.max_cached_plans:
+            _, old = self._plans.popitem(last=False)
+            old.release()
+        with torch.cuda.device(self.device):
+            self._plans[key] = Plan(self, *key)
         return self._plans[key]
+
+    def release_plans(self):
+        """Drop every cached plan and its workspace (e.g. before switching to another model)."""
+        while self._plans:
+            self._plans.popitem()[1].release()
+        self.__dict__.pop("_pb_cache", None)
 
     def __call__(self, x, t):
         """eps = unet(x, t); x [B,3,R,R] fp32 on the device, t scalar (tensor or float)."""
@@ -153,7 +179,7 @@ class B200UNet:
 
     def __del__(self):
         try:
-            self._plans.clear()
+            self.release_plans()
             self.lib.loco_unet_destroy(self.handle)
         except Exception:
             pass

@@ -262,3 +262,76 @@ def ddpm_param_shapes_cache(arch):
     if key not in _shape_cache:
         _shape_cache[key] = param_shapes(arch)
     return _shape_cache[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# Hugging Face `UNet2DModel` checkpoints (google/ddpm-ema-{celebahq,church,bedroom}-256)
+# ------------------------------------------------------------------------------------------------
+_HF_RES = {"norm1": "norm1", "conv1": "conv1", "time_emb_proj": "temb_proj", "norm2": "norm2",
+           "conv2": "conv2", "conv_shortcut": "nin_shortcut"}
+# diffusers 0.11 (the reference's pin, requirements.txt:4) names the attention projections
+# query/key/value/proj_attn; later releases to_q/to_k/to_v/to_out.0.  Both are Linear [C, C].
+_HF_ATTN = {"group_norm": "norm", "query": "q", "key": "k", "value": "v", "proj_attn": "proj_out",
+            "to_q": "q", "to_k": "k", "to_v": "v", "to_out.0": "proj_out"}
+
+
+def hf_unet2d_to_ddpm(sd, arch=DDPM256):
+    """Rename a diffusers `UNet2DModel.state_dict()` of the `*_HF` models the reference loads with
+    `DDIMPipeline.from_pretrained` (src/utils/utils.py:93-98, 122-125) to the `DDPM.state_dict()` names
+    this package packs (src/models/ddpm/diffusion.py:24-126; SURVEY 8c: same architecture).  The
+    attention projections are Linear [C, C] there and 1x1 Conv [C, C, 1, 1] here.
+
+    diffusers is not installed in this image, so the name table follows the published module tree of
+    `UNet2DModel` (down_blocks / mid_block / up_blocks, resnets / attentions / downsamplers /
+    upsamplers) and is checked for completeness against `ddpm_param_shapes(arch)`: every expected
+    parameter must be produced exactly once with the right shape, anything else raises."""
+    L = len(tuple(arch["ch_mult"]))
+    out = {}
+    for name, w in sd.items():
+        parts = name.split(".")
+        leaf = parts[-1]                      # weight | bias
+        new = None
+        if parts[0] == "time_embedding":
+            new = "temb.dense.%d.%s" % ({"linear_1": 0, "linear_2": 1}[parts[1]], leaf)
+        elif parts[0] in ("conv_in", "conv_out"):
+            new = name
+        elif parts[0] == "conv_norm_out":
+            new = "norm_out." + leaf
+        elif parts[0] in ("down_blocks", "up_blocks", "mid_block"):
+            if parts[0] == "mid_block":
+                kind, idx, rest = parts[1], int(parts[2]), parts[3:-1]
+                prefix = None
+            else:
+                lvl, kind, idx, rest = int(parts[1]), parts[2], int(parts[3]), parts[4:-1]
+                prefix = "down.%d" % lvl if parts[0] == "down_blocks" else "up.%d" % (L - 1 - lvl)
+            sub = ".".join(rest)
+            if kind == "resnets":
+                tgt = ("mid.block_%d" % (idx + 1)) if prefix is None else "%s.block.%d" % (prefix, idx)
+                new = "%s.%s.%s" % (tgt, _HF_RES[sub], leaf)
+            elif kind == "attentions":
+                tgt = "mid.attn_1" if prefix is None else "%s.attn.%d" % (prefix, idx)
+                new = "%s.%s.%s" % (tgt, _HF_ATTN[sub], leaf)
+                if sub != "group_norm" and leaf == "weight" and w.dim() == 2:
+                    w = w[:, :, None, None]
+            elif kind == "downsamplers":
+                new = "%s.downsample.conv.%s" % (prefix, leaf)
+            elif kind == "upsamplers":
+                new = "%s.upsample.conv.%s" % (prefix, leaf)
+        if new is None:
+            raise KeyError("hf_unet2d_to_ddpm: unexpected parameter '%s'" % name)
+        if new in out:
+            raise KeyError("hf_unet2d_to_ddpm: '%s' maps to '%s' twice" % (name, new))
+        out[new] = w
+    want = ddpm_param_shapes(arch)
+    missing = [k for k in want if k not in out]
+    extra = [k for k in out if k not in want]
+    if missing or extra:
+        raise KeyError("hf_unet2d_to_ddpm: missing %s, unexpected %s" % (missing[:3], extra[:3]))
+    for k, shp in want.items():
+        if tuple(out[k].shape) != tuple(shp):
+            raise ValueError("hf_unet2d_to_ddpm: %s has shape %s, expected %s" % (k, tuple(out[k].shape), shp))
+    return out
+
+
+def is_hf_unet2d_state_dict(sd):
+    return any(k.startswith(("down_blocks.", "time_embedding.")) for k in sd)

@@ -216,6 +216,39 @@ def test_orthonormalise_matches_svd(dev, k, d):
     assert float(((V2 * Vp).sum(1)).min()) > 0.99
 
 
+@pytest.mark.parametrize("k,d,decay", [(50, 196608, 1e-4), (64, 49152, 1e-5), (25, 196608, 1e-3)])
+def test_orthonormalise_decaying_spectrum_matches_svd(dev, k, d, decay):
+    """The reference default is pca_rank = 50 on a fast-decaying PMP-Jacobian spectrum
+    (src/modules/edit.py:2482 runs torch.linalg.svd on the k x d matrix).  The Gram route squares the
+    condition number, so the Gram matrix is accumulated in fp64, the transform is applied in fp64 and
+    a second (Loewdin) pass re-orthonormalises: V V^T - I and the principal angles of the leading /
+    trailing halves must stay at fp32 round-off for singular values spread over `decay`."""
+    from gpu_util import principal_angles_deg
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(100 + k)
+    Q, _ = torch.linalg.qr(torch.randn(d, k, generator=g, dtype=torch.float64))
+    R, _ = torch.linalg.qr(torch.randn(k, k, generator=g, dtype=torch.float64))
+    sv = torch.logspace(0, torch.log10(torch.tensor(decay)).item(), k, dtype=torch.float64) * 37.0
+    W64 = (R * sv[None, :]) @ Q.T                        # k x d with singular values sv
+    W = W64.float().to(dev)
+    V, s = ops.orthonormalise(W)
+    torch.cuda.synchronize()
+    _, sref, vh = torch.linalg.svd(W.double().cpu(), full_matrices=False)     # svd of the fp32 input
+    srel = float(((s.cpu().double() ** 2 - sref).abs() / sref).max())
+    gram = (V.double() @ V.double().T).cpu()
+    orth = float((gram - torch.eye(k, dtype=torch.float64)).abs().max())
+    h = k // 2
+    a_top = float(principal_angles_deg(V[:h], vh[:h]).max())
+    a_all = float(principal_angles_deg(V, vh).max())
+    dots = (V.double().cpu() * vh).sum(1).abs()
+    print(f"k={k} decay={decay:g}: s rel {srel:.2e}, |VV^T-I| {orth:.2e}, top-half angle {a_top:.4f} deg, "
+          f"row space {a_all:.4f} deg, min |<v_i, vh_i>| {float(dots.min()):.6f}")
+    assert srel < 1e-3            # north_star: singular values to 1e-3 relative
+    assert orth < 2e-5
+    assert a_top < 0.1 and a_all < 0.1
+    assert float(dots.min()) > 0.999
+
+
 @pytest.mark.parametrize("k,kn,d,project", [(5, 5, 196608, True), (2, 3, 3072, True), (3, 10, 12288, True), (4, 5, 3072, False)])
 def test_nullspace_project(dev, k, kn, d, project):
     from loco_edit_b200 import ops

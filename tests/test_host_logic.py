@@ -97,3 +97,68 @@ def test_preset_derives_the_reference_fields(tmp_path, monkeypatch):
     # the Edit class picks the network family by model name (reference: utils/utils.py:101-131)
     from loco_edit_b200.weights import P2_256, DDPM256, param_shapes
     assert "input_blocks.0.0.weight" in param_shapes(P2_256) and "conv_in.weight" in param_shapes(DDPM256)
+
+
+def _ddpm_to_hf_names(arch, legacy_attn):
+    """Inverse name table (test-side): DDPM.state_dict() name -> diffusers UNet2DModel name."""
+    from loco_edit_b200.weights import ddpm_param_shapes
+    L = len(arch["ch_mult"])
+    res = {"norm1": "norm1", "conv1": "conv1", "temb_proj": "time_emb_proj", "norm2": "norm2", "conv2": "conv2",
+           "nin_shortcut": "conv_shortcut"}
+    att = ({"norm": "group_norm", "q": "query", "k": "key", "v": "value", "proj_out": "proj_attn"} if legacy_attn
+           else {"norm": "group_norm", "q": "to_q", "k": "to_k", "v": "to_v", "proj_out": "to_out.0"})
+    out = {}
+    for name, shp in ddpm_param_shapes(arch).items():
+        p = name.split(".")
+        leaf = p[-1]
+        if p[0] == "temb":
+            hf = "time_embedding.linear_%d.%s" % (int(p[2]) + 1, leaf)
+        elif p[0] in ("conv_in", "conv_out"):
+            hf = name
+        elif p[0] == "norm_out":
+            hf = "conv_norm_out." + leaf
+        elif p[0] == "mid":
+            hf = ("mid_block.resnets.%d.%s.%s" % (int(p[1][-1]) - 1, res[p[2]], leaf) if p[1].startswith("block")
+                  else "mid_block.attentions.0.%s.%s" % (att[p[2]], leaf))
+        else:
+            blk = "down_blocks.%s" % p[1] if p[0] == "down" else "up_blocks.%d" % (L - 1 - int(p[1]))
+            if p[2] == "block":
+                hf = "%s.resnets.%s.%s.%s" % (blk, p[3], res[p[4]], leaf)
+            elif p[2] == "attn":
+                hf = "%s.attentions.%s.%s.%s" % (blk, p[3], att[p[4]], leaf)
+            else:
+                hf = "%s.%ssamplers.0.conv.%s" % (blk, "down" if p[2] == "downsample" else "up", leaf)
+        is_attn_proj = ".attentions." in hf and "group_norm" not in hf and leaf == "weight"
+        out[name] = (hf, tuple(shp[:2]) if is_attn_proj else tuple(shp))
+    return out
+
+
+@pytest.mark.parametrize("legacy_attn", [True, False])
+def test_hf_unet2d_checkpoint_names_map_onto_the_ddpm_state_dict(legacy_attn):
+    """`*_HF` models are diffusers UNet2DModel checkpoints (src/utils/utils.py:93-98, 122-125); the
+    remapper must produce exactly DDPM.state_dict() (names, shapes; Linear q/k/v -> 1x1 conv) for
+    both the diffusers-0.11 and the current attention naming, and refuse anything else."""
+    from loco_edit_b200.weights import DDPM256, hf_unet2d_to_ddpm, is_hf_unet2d_state_dict, random_state_dict, tiny_arch
+    for arch in (tiny_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1), DDPM256):
+        names = _ddpm_to_hf_names(arch, legacy_attn)
+        if arch is DDPM256:      # names/shapes only for the 113 M-parameter model
+            with torch.device("meta"):
+                hf = {h: torch.empty(shp) for h, shp in names.values()}
+            got = hf_unet2d_to_ddpm(hf, arch)
+            assert len(got) == len(names)
+            continue
+        sd = random_state_dict(arch, seed=5)
+        hf = {h: sd[n].reshape(shp).clone() for n, (h, shp) in names.items()}
+        assert is_hf_unet2d_state_dict(hf) and not is_hf_unet2d_state_dict(sd)
+        got = hf_unet2d_to_ddpm(hf, arch)
+        assert list(sorted(got)) == list(sorted(sd))
+        for n in sd:
+            assert torch.equal(got[n], sd[n]), n
+        bad = dict(hf)
+        bad["down_blocks.0.resnets.0.mystery.weight"] = torch.zeros(1)
+        with pytest.raises(KeyError):
+            hf_unet2d_to_ddpm(bad, arch)
+        short = dict(hf)
+        short.pop("conv_out.bias")
+        with pytest.raises(KeyError):
+            hf_unet2d_to_ddpm(short, arch)
