@@ -95,10 +95,12 @@ def synthetic_inputs(R, idx):
 # reference arm: the reference algorithm (CPU oracle port of its PyTorch path) on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(threads):
-    """Bounded sample of the config-1 edit on the host: one U-Net forward (B=1) and one rank-1
-    power iteration (jacfwd-style JVP + autograd VJP) at 256x256.  The edit is extrapolated with the
-    reference's own op counts: 138 F + 24 iterations of (1+3k)/(1+3) x the
-    rank-1 iteration + 59*5 F."""
+    """Bounded sample of the config-1 edit on the host cores (CPU oracle port of the reference's
+    PyTorch path, fp32): ONE full rank-5 power iteration at 256x256 (5 forward-mode products + a fresh
+    forward + 5 reverse passes = the reference's (1+3k) F, src/modules/edit.py:2443-2494), one U-Net
+    forward at B = 1 and one at B = 5 (the batch of the final DDIM stage).  The edit is assembled from
+    those measured pieces with the reference's own counts: 138 forwards (B=1) + 2 bases x 12
+    iterations + 59 steps at B=5."""
     import torch
     from loco_edit_b200.weights import DDPM256, random_state_dict
     from oracle import ddpm_ref, pullback_ref
@@ -110,19 +112,27 @@ def cpu_sample(threads):
     x0, mask = synthetic_inputs(256, 0)
     t = sched.timesteps[40]
     g = torch.Generator().manual_seed(7)
-    v0, _ = torch.linalg.qr(torch.randn(x0.numel(), 1, generator=g))
+    v0, _ = torch.linalg.qr(torch.randn(x0.numel(), K_RANK, generator=g))
     with torch.no_grad():
         unet(x0, t)                                   # warm-up (thread pool, allocator)
         t0 = time.perf_counter()
         unet(x0, t)
         f1 = time.perf_counter() - t0
+        x5 = x0.repeat(5, 1, 1, 1)
+        t0 = time.perf_counter()
+        unet(x5, t)
+        f5 = time.perf_counter() - t0
     t0 = time.perf_counter()
-    pullback_ref.power_iteration(unet, sched, x0, t, v0.T, mask=mask)
-    it1 = time.perf_counter() - t0
-    it5 = it1 * (1 + 3 * K_RANK) / 4.0
-    edit_s = 138 * f1 + 2 * N_ITER * it5 + 59 * 5 * f1
-    return {"forward_s": f1, "rank1_iter_s": it1, "edit_s_extrapolated": edit_s,
+    pullback_ref.power_iteration(unet, sched, x0, t, v0.T.contiguous(), mask=mask)
+    it5 = time.perf_counter() - t0
+    edit_s = 138 * f1 + 2 * N_ITER * it5 + 59 * f5
+    return {"forward_b1_s": f1, "forward_b5_s": f5, "rank5_iter_s": it5, "edit_s_assembled": edit_s,
             "jvp_probes_per_s": K_RANK / it5}
+
+
+CPU_SAMPLE_TEXT = ("measured on the host cores, fp32 torch CPU, 256^2: one FULL rank-5 power iteration (5 JVP + "
+                   "forward + 5 VJP), one U-Net forward at B=1, one at B=5; edit = 138 x fwd(B=1) + 24 x "
+                   "iteration + 59 x fwd(B=5)")
 
 
 def run_reference(args):
@@ -138,24 +148,210 @@ def run_reference(args):
     for _ in range(steps):
         vals.append(cpu_sample(threads))
     wall = time.perf_counter() - t_all
-    edit_s = statistics.mean(v["edit_s_extrapolated"] for v in vals)
+    edit_s = statistics.mean(v["edit_s_assembled"] for v in vals)
     value = 1.0 / edit_s
-    sample = ("per step: 1 U-Net forward (B=1) + 1 rank-1 power iteration (JVP+VJP) at 256^2, fp32, "
-              "torch CPU; edit extrapolated as 138 F + 24 x (16/4) x iter + 295 F (BASELINE.md s2)")
+    sample = "per step: " + CPU_SAMPLE_TEXT
     line = {
         "impl": "reference", "metric": "edits/sec (rank-5 @256^2, t=0.6T)", "value": value,
         "unit": "edits/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
         "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config-1 edit: DDPM-256 random-init, 1 image, rank 5 + null 5, N=12, t=0.6T",
-                   "timing": "host wall clock, extrapolated from a bounded sample"},
+                   "timing": "host wall clock; the edit is assembled from the measured pieces of a bounded sample"},
         "cpu_baseline": {"value": value, "unit": "edits/s", "cores": threads, "kind": "port",
                          "sample": sample,
+                         "forward_b1_s": statistics.mean(v["forward_b1_s"] for v in vals),
+                         "forward_b5_s": statistics.mean(v["forward_b5_s"] for v in vals),
+                         "rank5_iter_s": statistics.mean(v["rank5_iter_s"] for v in vals),
                          "jvp_probes_per_s": statistics.mean(v["jvp_probes_per_s"] for v in vals)},
         "e2e": {"value": value, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm: extra measurements (all CUDA events on torch's current stream = the launching stream)
+# ------------------------------------------------------------------------------------------------
+def _timed(fn, reps, sync):
+    import torch
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for _ in range(reps):
+        sync()
+        a.record()
+        fn()
+        b.record()
+        sync()
+        out.append(a.elapsed_time(b))
+    return out
+
+
+def measure_latency_b1(pipe, gen, R):
+    """north_star target: ONE config-1 edit (rank 5 + null 5, N = 12, 98+40+59 DDIM steps, 5 edited
+    latents) through the public call `EditPipeline.edit` with pinned host buffers in and images back
+    on the host: median of 3 after one warm-up call."""
+    import torch
+    x0, m = synthetic_inputs(R, 777)
+    x0, m = x0.pin_memory(), m.pin_memory()
+    gen.manual_seed(6000)
+    pipe.edit(x0, m, gen=gen)
+    ts = _timed(lambda: pipe.edit(x0, m, gen=gen), 3, torch.cuda.synchronize)
+    return statistics.median(ts)
+
+
+def measure_dropin(unet, dev, R):
+    """The reference-facing driver itself: `EditUncondDiffusion.run_edit_null_space_projection` with the
+    reference's own settings (two separate power methods with min_iter=10 / max_iter=50: with
+    random-init weights neither converges, so 50 iterations each; basis files written with
+    torch.save), vis_num 2, one direction.  Second call of two, fresh result folder each."""
+    import shutil
+    import tempfile
+    import types
+    import torch
+    from loco_edit_b200.edit import EditUncondDiffusion
+    ms = []
+    for rep in range(2):
+        tmp = tempfile.mkdtemp(prefix="loco_dropin_")
+        a = types.SimpleNamespace(
+            device=dev, dtype=torch.float32, seed=1, model_name="CelebA_HQ_HF", dataset_name="CelebA_HQ_mask",
+            image_size=R, for_steps=100, inv_steps=100, edit_t=0.6, performance_boosting_t=0.2,
+            x_space_guidance_edit_step=1.0, x_space_guidance_scale=0.5, x_space_guidance_num_step=16,
+            result_folder=tmp, sample_idx=0, choose_sem="hair", mask_index=0, sampling_mode=False,
+            vT_path="", vT1_path="", verbose=False, save_images=False, noise_schedule=None)
+        e = EditUncondDiffusion(a, unet=unet)
+        ms.append(_timed(lambda: e.run_edit_null_space_projection(idx=0, vis_num=2, vis_num_pc=1, pca_rank=5,
+                                                                  pca_rank_null=5), 1, torch.cuda.synchronize)[0])
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"ms": ms[-1], "power_iterations": "2 x 50 (min_iter=10, max_iter=50, never converges on random weights)",
+            "fwd_equivalents_executed": 138 + 2 * 50 * (1 + 2 * K_RANK) + 59 * 5,
+            "entry_point": "EditUncondDiffusion.run_edit_null_space_projection (files written)"}
+
+
+def measure_bandwidth_kernels(dev, hbm_peak):
+    """north_star (2): achieved HBM GB/s of the bandwidth-bound pieces around the U-Net, each on its
+    config-1 shapes (k = k_null = 5, d = 196608, l_o = 24576) and on the batch-edit shape of the DDIM
+    update.  Working sets rotate through > 256 MB of distinct buffers so that no call is served by the
+    126 MB L2; bytes are the algorithmic ones."""
+    import torch
+    from loco_edit_b200 import ops
+    d, k = 3 * 256 * 256, 5
+    nset = 48                                      # 48 x [5, d] fp32 = 189 MB per operand family
+    g = torch.Generator(device=dev).manual_seed(9)
+    W = [torch.randn(k, d, device=dev, generator=g) for _ in range(nset)]
+    Vn = [ops.orthonormalise(torch.randn(k, d, device=dev, generator=g))[0] for _ in range(nset)]
+    mask = torch.zeros(3, 256, 256, dtype=torch.bool, device=dev)
+    mask[:, 96:160, 64:192] = True
+    idx = ops.mask_indices(mask)
+    xb = [torch.randn(40, 3, 256, 256, device=dev, generator=g) for _ in range(4)]      # 4 x 31 MB x 3 operands
+    eb = [torch.randn(40, 3, 256, 256, device=dev, generator=g) for _ in range(4)]
+    nb = [torch.randn(40, 3, 256, 256, device=dev, generator=g) for _ in range(4)]
+    out = {}
+
+    def run(name, fn, nbytes, reps):
+        for i in range(3):
+            fn(i)
+        t = _timed(lambda: [fn(i) for i in range(reps)], 3, torch.cuda.synchronize)
+        us = 1e3 * min(t) / reps
+        out[name] = {"us": us, "bytes": nbytes, "gbs": nbytes / (us * 1e-6) / 1e9,
+                     "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / hbm_peak}
+
+    # algorithmic bytes as in SURVEY 8(d): orthonormalise 3*k*d*4 (read W for the Gram matrix, read W and
+    # write V for the transform; the implementation's second re-orthonormalisation pass moves twice
+    # that), projection (2k + k_null)*d*4, mask gather (d + l_o)*4 per row
+    run("orthonormalise_k5", lambda i: ops.orthonormalise(W[i % nset]), 3 * k * d * 4, nset)
+    run("nullspace_project_k5", lambda i: ops.nullspace_project(W[i % nset], Vn[i % nset]), (2 * k + k) * d * 4, nset)
+    run("gather_rows_mask", lambda i: ops.gather_rows(W[i % nset], idx), k * (d + idx.numel()) * 4, nset)
+    run("ddim_step_b40_eta0", lambda i: ops.ddim_step(xb[i % 4], eb[i % 4], 0.5, 0.6), 3 * xb[0].numel() * 4, 8)
+    run("ddim_step_b40_eta1", lambda i: ops.ddim_step(xb[i % 4], eb[i % 4], 0.5, 0.6, eta=1.0, noise=nb[i % 4]),
+        4 * xb[0].numel() * 4, 8)
+    run("axpy_b40", lambda i: ops.axpy(xb[i % 4], eb[i % 4], 0.5), 3 * xb[0].numel() * 4, 8)
+    return out
+
+
+def measure_probe_shard(unet, sched, dev, world, rank, R, barrier, max_over_ranks, n_it=3, k=64):
+    """BASELINE config 3 under torchrun: rank-64 subspace iteration (mask = None, t idx 40), probe
+    tangents sharded over the ranks (64 / world rows each, probed in chunks of <= 25), one all-gather
+    of the [64, d] W rows per iteration, replicated orthonormalisation.  Rank 0 then repeats the same
+    iterations alone (3 chunks of 22/22/20) for the strong-scaling reference and the parity figures."""
+    import torch
+    import torch.distributed as dist
+    from loco_edit_b200 import dist as ld
+    from loco_edit_b200.edit import local_basis, random_basis
+    d = 3 * R * R
+    sched.set_timesteps(100, device=dev)
+    t = sched._ts_host[40]
+    g = torch.Generator(device=dev).manual_seed(11)
+    xt = torch.randn(1, 3, R, R, device=dev, generator=g)
+    v0 = random_basis(d, k, dev, generator=g)
+    dist.broadcast(xt, src=0)
+    dist.broadcast(v0, src=0)
+    unet.release_plans()
+    torch.cuda.empty_cache()
+    ld.sharded_local_basis_cuda(unet, sched, xt, t, k, v0, 1, mask=None)          # warm-up: plans, graphs, NCCL
+    barrier()
+    timer = ld.CommTimer()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _, s, V = ld.sharded_local_basis_cuda(unet, sched, xt, t, k, v0, n_it, mask=None, timer=timer)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    ag = max_over_ranks(timer.total_ms())
+    res = None
+    unet.release_plans()
+    torch.cuda.empty_cache()
+    if rank == 0:
+        local_basis(unet, sched, xt, t, k, v0=v0, min_iter=10 ** 6, max_iter=1, mask=None, verbose=False)
+        torch.cuda.synchronize()
+        a.record()
+        _, s1, V1 = local_basis(unet, sched, xt, t, k, v0=v0, min_iter=10 ** 6, max_iter=n_it, mask=None,
+                                verbose=False)
+        b.record()
+        torch.cuda.synchronize()
+        ms1 = a.elapsed_time(b)
+        qa, _ = torch.linalg.qr(V.double().T.cpu())
+        qb, _ = torch.linalg.qr(V1.double().T.cpu())
+        ang = torch.rad2deg(torch.acos(torch.linalg.svdvals(qa.T @ qb).clamp(max=1.0)))
+        res = {"rank": k, "iterations": n_it, "probes_per_rank": [hi - lo for lo, hi in
+                                                                  (ld.shard_range(k, world, r) for r in range(world))],
+               "ms_per_iter": ms / n_it, "probes_per_s": k * n_it / (ms * 1e-3),
+               "allgather_ms_per_iter": ag / n_it, "allgather_share": ag / ms,
+               "allgather_bytes_per_iter": k * d * 4,
+               "single_gpu_ms_per_iter": ms1 / n_it, "single_gpu_probes_per_s": k * n_it / (ms1 * 1e-3),
+               "speedup_vs_1gpu": ms1 / ms,
+               "parity_s_rel": float(((s - s1).abs() / s1).max()), "parity_deg": float(ang.max()),
+               "s_top3": [float(x) for x in s[:3]],
+               "timing": "CUDA events, max over ranks; parity = sharded vs rank 0 alone, same V0, same iterations"}
+        unet.release_plans()
+        torch.cuda.empty_cache()
+    barrier()
+    return res
+
+
+def measure_sharded_latency(pipe, gen, dev, R, world, barrier, max_over_ranks):
+    """ONE config-1 edit by all ranks together (`EditPipeline.edit_sharded`): replicated serial chain,
+    the 10 probes of {edit, null} bases sharded jointly, the 5 final latents sharded; host buffers."""
+    import torch
+    from loco_edit_b200 import dist as ld
+    x0, m = synthetic_inputs(R, 777)
+    x0, m = x0.pin_memory(), m.pin_memory()
+    gen.manual_seed(6000)
+    pipe.edit_sharded(x0, m, gen=gen)
+    ts, ags = [], []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        timer = ld.CommTimer()
+        barrier()
+        a.record()
+        pipe.edit_sharded(x0, m, gen=gen, timer=timer)
+        b.record()
+        barrier()
+        ts.append(max_over_ranks(a.elapsed_time(b)))
+        ags.append(max_over_ranks(timer.total_ms()))
+    i = ts.index(statistics.median(ts))
+    return {"ms": ts[i], "allgather_ms": ags[i], "n_gpus": world,
+            "what": "one config-1 edit, 138-step chain replicated, 10 probes and 5 final latents sharded"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,6 +516,21 @@ def run_ours(args):
             torch.cuda.synchronize()
             probes["fwd_b%d_ms" % bsz] = a.elapsed_time(b) / reps
 
+    # ---- single-edit latency (north_star: < 1 s), the drop-in driver, the small HBM-bound kernels ----
+    latency_b1 = dropin = bw = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        latency_b1 = measure_latency_b1(pipe, gen, R)
+        dropin = measure_dropin(unet, dev, R)
+        bw = measure_bandwidth_kernels(dev, pk["hbm_gbs"])
+    # ---- multi-GPU data path with a collective: one edit by all ranks, and BASELINE config 3 ----
+    sharded_latency = probe_shard = None
+    if world > 1 and not args.no_extras:
+        unet.release_plans()
+        torch.cuda.empty_cache()
+        sharded_latency = measure_sharded_latency(pipe, gen, dev, R, world, barrier, max_over_ranks)
+        probe_shard = measure_probe_shard(unet, pipe.driver.scheduler, dev, world, rank, R, barrier,
+                                          max_over_ranks)
+
     # ---- BASELINE config 2 proper: the P2 / guided-diffusion U-Net with the FFHQ_P2 script settings
     # (edit_t 0.2, rank 3 + null 5, scale 12, 1 step; scripts/main_hf_null_space_projection_FFHQ_P2.sh),
     # one warm-up and one timed batch of BATCH image/mask pairs (single-GPU runs only; extra key) ----
@@ -355,11 +566,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         smp = cpu_sample(threads)
-        cpu = {"value": 1.0 / smp["edit_s_extrapolated"], "unit": "edits/s", "cores": threads, "kind": "port",
-               "sample": "1 U-Net forward (B=1) + 1 rank-1 power iteration at 256^2 on the host cores; edit "
-                         "extrapolated with the reference's op counts (138 F + 24 x 4 x iter + 295 F)",
-               "forward_s": smp["forward_s"], "rank1_iter_s": smp["rank1_iter_s"],
-               "jvp_probes_per_s": smp["jvp_probes_per_s"]}
+        cpu = {"value": 1.0 / smp["edit_s_assembled"], "unit": "edits/s", "cores": threads, "kind": "port",
+               "sample": CPU_SAMPLE_TEXT,
+               "forward_b1_s": smp["forward_b1_s"], "forward_b5_s": smp["forward_b5_s"],
+               "rank5_iter_s": smp["rank5_iter_s"], "jvp_probes_per_s": smp["jvp_probes_per_s"]}
 
     if rank == 0:
         n_edits = args.steps * world * BATCH
@@ -384,6 +594,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "p2_ffhq": p2,
+            "latency_b1_ms": latency_b1, "latency_b1_target_ms": 1000.0,
+            "latency_b1_sharded": sharded_latency, "probe_shard": probe_shard,
+            "dropin_driver": dropin, "bandwidth_kernels": bw,
         }
         if probes:
             line.update(probes)
@@ -401,6 +614,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="image/mask pairs edited together per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2", action="store_true", help="skip the extra P2 / FFHQ_P2 batch-edit measurement")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the single-edit latency / drop-in driver / small-kernel / probe-sharding legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

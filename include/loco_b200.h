@@ -74,6 +74,15 @@ int loco_unet_load_param(loco_unet_t* m, const char* name, const float* src, lon
  * the transposed pass.  (B,0,0) = plain eps_theta(x,t) for the DDIM loops; (1,k,k) = pull-back. */
 int loco_plan_create(const loco_unet_t* m, int n_primal, int n_tangent, int n_cotangent,
                      loco_plan_t** out);
+/* Same with storage / arithmetic flags.  LOCO_PLAN_FP16: every activation of the program is stored
+ * in fp16 and the GEMM-shaped layers run on tcgen05.mma kind::f16 (fp32 accumulation) instead of
+ * fp32 storage + kind::tf32: same 10-bit operand mantissa as the TF32 path (the reference's own GPU
+ * numerics, torch's cudnn.allow_tf32 default), half the HBM bytes, twice the tensor rate.  Meant for
+ * the Jacobian-free programs (n_tangent = n_cotangent = 0): the DDIM inversion / denoising loops
+ * `self.unet(xt, t)` of src/modules/edit.py:2151 and :2572. */
+#define LOCO_PLAN_FP16 1
+int loco_plan_create_ex(const loco_unet_t* m, int n_primal, int n_tangent, int n_cotangent, int flags,
+                        loco_plan_t** out);
 void loco_plan_destroy(loco_plan_t* p);
 long long loco_plan_workspace_bytes(const loco_plan_t* p);
 int loco_plan_bind(loco_plan_t* p, void* workspace);
@@ -106,6 +115,13 @@ int loco_pullback_iteration(loco_plan_t* p, const float* xt, float t, float at,
 int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, const unsigned char* mask,
                         int noise, const float* V, int k, long long d, float* u_full, float* w_out,
                         void* scratch, void* stream);
+
+/* Same for a mixed shard of the joint {edit basis, null basis} probe set: rows [0,k_invert) of V are
+ * probed through the masked Jacobian, rows [k_invert,k) through the complement-mask Jacobian
+ * (src/modules/edit.py:2294 and :2307 share x_t, t and the primal activations). */
+int loco_pullback_probe_pair(loco_plan_t* p, const float* xt, float t, float at,
+                             const unsigned char* mask, int noise, const float* V, int k, int k_invert,
+                             long long d, float* u_full, float* w_out, void* scratch, void* stream);
 
 /* One iteration of BOTH local bases of run_edit_null_space_projection (src/modules/edit.py:2294 and
  * :2307) in a single fused pass: rows [0,k1) of V are probes of the masked Jacobian (edit basis),
@@ -152,6 +168,12 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
                      int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
                      void* stream);
+/* Same with typed tensors: in16 != 0: x (and the packed weights in wpack) are fp16 -> tcgen05.mma
+ * kind::f16; out16 != 0: y and addend are fp16.  Accumulation is fp32 either way. */
+int loco_conv2d_nhwc_ex(int kind, const void* x, int N, int H, int W, int Cx, const float* w, int Cout,
+                        int Cin, void* wpack, const float* bias, int bias_rows, const void* addend,
+                        int accumulate, void* y, void* splitk_scratch, long long splitk_bytes,
+                        int in16, int out16, void* stream);
 /* Pure host logic: 1 if a stride-1 3x3 convolution (kind 0) or its data gradient (kind 3) of this
  * shape is served by the halo / CTA-pair tcgen05 kernels (wave-quantisation cost model). */
 int loco_conv_halo_eligible(int kind, int N, int H, int W, int Cout);

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "loco_unet_param_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I)]),
     "loco_unet_load_param": (_I, [_P, C.c_char_p, _P, _LL, _P]),
     "loco_plan_create": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
+    "loco_plan_create_ex": (_I, [_P, _I, _I, _I, _I, C.POINTER(_P)]),
     "loco_plan_destroy": (None, [_P]),
     "loco_plan_workspace_bytes": (_LL, [_P]),
     "loco_plan_bind": (_I, [_P, _P]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "loco_pullback_scratch_bytes": (_LL, [_I, _LL]),
     "loco_pullback_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),
     "loco_pullback_probe": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _P, _P, _P, _P]),
+    "loco_pullback_probe_pair": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P]),
     "loco_pullback_pair_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),
     "loco_pmp_forward": (_I, [_P, _P, _F, _LL, _P, _P]),
     "loco_orthonormalise_scratch_bytes": (_LL, [_I]),
@@ -67,6 +69,7 @@ PROTOTYPES = {
     "loco_conv_halo_eligible": (_I, [_I, _I, _I, _I, _I]),
     "loco_conv2d_fused_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _P]),
     "loco_conv2d_nhwc": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _LL, _P]),
+    "loco_conv2d_nhwc_ex": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _P]),
     "loco_conv_bench": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, C.POINTER(_F),
                              C.POINTER(_I), C.POINTER(_I), _P]),
     "loco_groupnorm_silu_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),

@@ -118,6 +118,18 @@ int loco_plan_create(const loco_unet_t* m, int n_primal, int n_tangent, int n_co
   return 0;
   GUARD_END
 }
+int loco_plan_create_ex(const loco_unet_t* m, int n_primal, int n_tangent, int n_cotangent, int flags,
+                        loco_plan_t** out) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(m && out, "loco_plan_create_ex: null argument");
+  LOCO_REQUIRE((flags & ~LOCO_PLAN_FP16) == 0, "loco_plan_create_ex: unknown flags 0x%x", flags);
+  Plan* p = new Plan(m->m, n_primal, n_tangent, n_cotangent, flags);
+  const int r = p->build(nullptr);
+  if (r != 0) { delete p; return r; }
+  *out = new loco_plan{p};
+  return 0;
+  GUARD_END
+}
 void loco_plan_destroy(loco_plan_t* p) {
   if (p) { delete p->p; delete p; }
 }
@@ -174,6 +186,16 @@ int loco_pullback_probe(loco_plan_t* p, const float* xt, float t, float at, cons
                         int noise, const float* V, int k, long long d, float* u_full, float* w_out,
                         void* scratch, void* stream) {
   return pullback_probe_impl(p, xt, t, at, mask, noise, V, k, k, d, u_full, w_out, scratch, stream);
+}
+
+// Probe rows of a mixed batch: rows [0, k_invert) see the mask, rows [k_invert, k) its complement.
+// A rank's shard of the joint {edit, null} probe set of run_edit_null_space_projection may straddle
+// the boundary between the two bases ("shard the 10 probes of {edit, null} jointly").
+int loco_pullback_probe_pair(loco_plan_t* p, const float* xt, float t, float at, const unsigned char* mask,
+                             int noise, const float* V, int k, int k_invert, long long d, float* u_full,
+                             float* w_out, void* scratch, void* stream) {
+  LOCO_REQUIRE(mask != nullptr && k_invert >= 0 && k_invert <= k, "loco_pullback_probe_pair: bad mask / split");
+  return pullback_probe_impl(p, xt, t, at, mask, noise, V, k, k_invert, d, u_full, w_out, scratch, stream);
 }
 
 int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float at,
@@ -304,6 +326,18 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
                      int Cin, float* wpack, const float* bias, int bias_rows, const float* addend,
                      int accumulate, float* y, void* splitk_scratch, long long splitk_bytes,
                      void* stream) {
+  return loco_conv2d_nhwc_ex(kind, x, N, H, W, Cx, w, Cout, Cin, wpack, bias, bias_rows, addend, accumulate, y,
+                             splitk_scratch, splitk_bytes, 0, 0, stream);
+}
+
+int loco_conv2d_nhwc_ex(int kind, const void* x_, int N, int H, int W, int Cx, const float* w, int Cout,
+                        int Cin, void* wpack_, const float* bias, int bias_rows, const void* addend_,
+                        int accumulate, void* y_, void* splitk_scratch, long long splitk_bytes,
+                        int in16, int out16, void* stream) {
+  const float* x = reinterpret_cast<const float*>(x_);
+  float* wpack = reinterpret_cast<float*>(wpack_);
+  const float* addend = reinterpret_cast<const float*>(addend_);
+  float* y = reinterpret_cast<float*>(y_);
   ON_DEVICE_OF(x);
   GUARD_BEGIN
   LOCO_TRY(require_device());
@@ -313,22 +347,24 @@ int loco_conv2d_nhwc(int kind, const float* x, int N, int H, int W, int Cx, cons
   int Ho = H, Wo = W, Cy = Cout;
   if (kind == CONV_3x3 || kind == CONV_1x1 || kind == CONV_3x3_S2) {
     LOCO_REQUIRE(Cx == Cin, "loco_conv2d_nhwc: x has %d channels, weight expects %d", Cx, Cin);
-    LOCO_TRY(pack_conv_fprop(w, wpack, Cout, Cin, ksz, ksz, s));
+    if (in16) LOCO_TRY(pack_conv_fprop16(w, wpack, Cout, Cin, ksz, ksz, s));
+    else LOCO_TRY(pack_conv_fprop(w, wpack, Cout, Cin, ksz, ksz, s));
     if (kind == CONV_3x3_S2) { Ho = H / 2; Wo = W / 2; }
     p.Kc = Cin; p.Ngemm = Cout;
   } else {
     LOCO_REQUIRE(Cx == Cout, "loco_conv2d_nhwc: dy has %d channels, weight has Cout=%d", Cx, Cout);
-    LOCO_TRY(pack_conv_dgrad(w, wpack, Cout, Cin, ksz, ksz, Cout, 0, s));
+    if (in16) LOCO_TRY(pack_conv_dgrad16(w, wpack, Cout, Cin, ksz, ksz, Cout, 0, s));
+    else LOCO_TRY(pack_conv_dgrad(w, wpack, Cout, Cin, ksz, ksz, Cout, 0, s));
     if (kind == CONV_3x3_S2_DGRAD) { Ho = 2 * H; Wo = 2 * W; }
     p.Kc = Cout; p.Ngemm = Cin; Cy = Cin;
   }
   p.kind = kind;
-  p.in = make_view(const_cast<float*>(x), N, H, W, Cx);
-  p.out = make_view(y, N, Ho, Wo, Cy);
+  p.in = make_view(const_cast<float*>(x), N, H, W, Cx, in16 ? 1 : 0);
+  p.out = make_view(y, N, Ho, Wo, Cy, out16 ? 1 : 0);
   p.wpack = wpack;
   p.bias = bias; p.bias_rows = bias_rows;
   View add;
-  if (addend) { add = make_view(const_cast<float*>(addend), N, Ho, Wo, Cy); p.addend = &add; }
+  if (addend) { add = make_view(const_cast<float*>(addend), N, Ho, Wo, Cy, out16 ? 1 : 0); p.addend = &add; }
   p.accumulate = accumulate; p.round_out = 0;
   if (splitk_scratch && splitk_bytes >= (1 << 20)) {
     // layout: [4096 int counters (zeroed by the caller)] [partial tiles]

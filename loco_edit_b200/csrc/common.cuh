@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -42,24 +43,34 @@ const char* get_error();
   } while (0)
 
 // A 4-D activation view in HBM. Layout is channels-last: element (n,y,x,c) lives at
-// ptr[n*sN + y*sH + x*sW + c]. Channel slices of a wider buffer (skip-connection concat buffers)
-// are expressed by offsetting ptr and keeping sW = the full buffer width.
+// ptr[n*sN + y*sH + x*sW + c] (strides in ELEMENTS). Channel slices of a wider buffer
+// (skip-connection concat buffers) are expressed by offsetting ptr and keeping sW = the full buffer
+// width.  Elements are fp32 (half == 0) or fp16 (half == 1: `ptr` is then only a typed handle to
+// the first element, all address arithmetic goes through elem_ptr / the ld4t / st4t helpers).
+// fp16 storage carries the same 10-bit mantissa as the tf32-rounded fp32 storage (every producer
+// rounds to tf32 before the tensor core would truncate), at half the HBM bytes and twice the
+// tcgen05 rate (kind::f16); its 5-bit exponent is why it is used for primal rows only.
 struct View {
   float* ptr;
   int N, H, W, C;
   long long sN, sH, sW;
+  int half;
 };
 
-inline View make_view(float* p, int N, int H, int W, int C) {
-  View v; v.ptr = p; v.N = N; v.H = H; v.W = W; v.C = C;
+inline float* elem_ptr(const View& v, long long elem_off) {
+  return v.half ? reinterpret_cast<float*>(reinterpret_cast<char*>(v.ptr) + elem_off * 2)
+                : v.ptr + elem_off;
+}
+inline View make_view(float* p, int N, int H, int W, int C, int half = 0) {
+  View v; v.ptr = p; v.N = N; v.H = H; v.W = W; v.C = C; v.half = half;
   v.sW = C; v.sH = (long long)W * C; v.sN = (long long)H * W * C;
   return v;
 }
 inline View slice_c(const View& v, int c0, int C) {
-  View r = v; r.ptr = v.ptr + c0; r.C = C; return r;
+  View r = v; r.ptr = elem_ptr(v, c0); r.C = C; return r;
 }
 inline View slice_n(const View& v, int n0, int N) {
-  View r = v; r.ptr = v.ptr + (long long)n0 * v.sN; r.N = N; return r;
+  View r = v; r.ptr = elem_ptr(v, (long long)n0 * v.sN); r.N = N; return r;
 }
 
 int num_sms();
@@ -279,6 +290,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with fp16 operands (kind::f16: 16 elements = 32 bytes of K per instruction, twice the rate).
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -310,6 +340,32 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+
+// ---- typed 4-element vector access of an activation tensor (H16: fp16 storage, else fp32) ----
+template <bool H16>
+__device__ __forceinline__ float4 ld4t(const float* base, long long elem_off) {
+  if (H16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + elem_off);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(base + elem_off);
+}
+template <bool H16>
+__device__ __forceinline__ void st4t(float* base, long long elem_off, float4 v) {
+  if (H16) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + elem_off) = u;
+  } else {
+    *reinterpret_cast<float4*>(base + elem_off) = v;
+  }
+}
+// value as it will be read back from fp16 storage
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

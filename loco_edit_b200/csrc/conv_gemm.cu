@@ -46,15 +46,34 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128.
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+// Instruction descriptor, fp32 accumulate, both operands K-major: kind::tf32 (operand format 2) or
+// kind::f16 with fp16 operands (format 0).
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int in16) {
   uint32_t d = 0;
   d |= 1u << 4;                 // C format = F32
-  d |= 2u << 7;                 // A format = TF32
-  d |= 2u << 10;                // B format = TF32
+  if (!in16) {
+    d |= 2u << 7;               // A format = TF32
+    d |= 2u << 10;              // B format = TF32
+  }                             // (F16 = 0 for kind::f16)
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(kConvBlockM >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
+}
+// one K step of 32 bytes per operand row: 8 tf32 or 16 fp16 elements
+__device__ __forceinline__ void umma_any(int in16, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
+                                         uint32_t acc) {
+  if (in16) umma_f16(d_tmem, a, b, idesc, acc); else umma_tf32(d_tmem, a, b, idesc, acc);
+}
+__device__ __forceinline__ void umma_any_pair(int in16, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
+                                              uint32_t acc) {
+  if (in16) umma_f16_pair(d_tmem, a, b, idesc, acc); else umma_tf32_pair(d_tmem, a, b, idesc, acc);
+}
+// runtime-typed 4-channel access of the output-side tensors (h = fp16 storage)
+__device__ __forceinline__ float4 ld4r(const float* base, long long off, int h) {
+  return h ? ld4t<true>(base, off) : ld4t<false>(base, off);
+}
+__device__ __forceinline__ void st4r(float* base, long long off, float4 v, int h) {
+  if (h) st4t<true>(base, off, v); else st4t<false>(base, off, v);
 }
 
 // L2 prefetch of the epilogue's read-side tile (residual addend and/or the accumulate target) of a
@@ -72,13 +91,17 @@ __device__ __forceinline__ void prefetch_epilogue_tile(const ConvGemmParams& p, 
   const int y = ty * p.TH + ((R >> p.log_tw) & (p.TH - 1));
   const int n = tn * p.TN + (R >> (p.log_tw + p.log_th));
   if (n >= p.N || y >= p.Ho || x >= p.Wo) return;
+  const int esz = p.out16 ? 2 : 4;
+  const int line = 128 / esz;             // channels per 128-byte line
   if (p.addend) {
-    const float* a = p.addend + (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0;
-    for (int c = 0; c < p.block_n; c += 32) prefetch_l2(a + c);
+    const char* a = reinterpret_cast<const char*>(p.addend) +
+                    ((long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0) * esz;
+    for (int c = 0; c < p.block_n; c += line) prefetch_l2(reinterpret_cast<const float*>(a + c * esz));
   }
   if (p.accumulate) {
-    const float* o = p.out + (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
-    for (int c = 0; c < p.block_n; c += 32) prefetch_l2(o + c);
+    const char* o = reinterpret_cast<const char*>(p.out) +
+                    ((long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0) * esz;
+    for (int c = 0; c < p.block_n; c += line) prefetch_l2(reinterpret_cast<const float*>(o + c * esz));
   }
 }
 
@@ -117,12 +140,12 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
     for (int it = 0; it < 8; ++it)
       if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
   }
+  const int h = p.out16;
   if (p.addend) {
     float4 a[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it] + ch))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[it] = ((vmask >> it) & 1u) ? ld4r(p.addend, aoff[it] + ch, h) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
   }
@@ -130,12 +153,18 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
     float4 a[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it] + ch)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[it] = ((vmask >> it) & 1u) ? ld4r(p.out, ooff[it] + ch, h) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
   }
-  if (p.round_out) {
+  if (h) {
+    // fp16 storage: what is stored (and what the fused statistics must see) is the fp16 rounding
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      v[it].x = round_f16(v[it].x); v[it].y = round_f16(v[it].y);
+      v[it].z = round_f16(v[it].z); v[it].w = round_f16(v[it].w);
+    }
+  } else if (p.round_out) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       v[it].x = round_tf32(v[it].x); v[it].y = round_tf32(v[it].y);
@@ -144,11 +173,11 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
   }
   if (vmask == 0xFFu) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = v[it];
+    for (int it = 0; it < 8; ++it) st4r(p.out, ooff[it] + ch, v[it], h);
   } else {
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      if ((vmask >> it) & 1u) *reinterpret_cast<float4*>(p.out + ooff[it] + ch) = v[it];
+      if ((vmask >> it) & 1u) st4r(p.out, ooff[it] + ch, v[it], h);
   }
   if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
     // fused GroupNorm statistics of what was just stored: the 4 lanes that share a channel quad
@@ -263,9 +292,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const CUtensorMap* am = &p.amap[p.tap_map[tap]];
 #pragma unroll
           for (int j = 0; j < NT; ++j)
-            tma_load_4d(sa + j * kABytes, am, &full_bar[stage], cc * kConvBlockK, x0[j] + p.tap_dx[tap],
+            tma_load_4d(sa + j * kABytes, am, &full_bar[stage], cc * p.kblock, x0[j] + p.tap_dx[tap],
                         y0[j] + p.tap_dy[tap], n0[j]);
-          tma_load_2d(sa + kBOff, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+          tma_load_2d(sa + kBOff, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * p.kblock, co0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++cc == p.c_chunks) { cc = 0; ++tap; }
@@ -280,7 +309,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_tf32(p.block_n);
+      const uint32_t idesc = make_idesc(kConvBlockM, p.block_n, p.in16);
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem));            // stage 0, pixel tile 0
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + kBOff);    // stage 0, weight tile
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -312,7 +341,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int k = 0; k < kConvBlockK / 8; ++k) {
               if (j == NT - 1 && k == kConvBlockK / 8 - 1 && it + 1 < nk) mbar_wait(&full_bar[nstage], nphase);
               // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
-              umma_tf32(d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+              umma_any(p.in16, d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                         idesc, (uint32_t)((it | k) != 0));
             }
           }
@@ -571,7 +600,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_arrive(&full_bar[as]);
             } else {
               mbar_arrive_expect_tx(&full_bar[as], kHaloABytes);
-              tma_load_4d(smem + as * kHaloABytes, &p.hmap, &full_bar[as], cc * kConvBlockK,
+              tma_load_4d(smem + as * kHaloABytes, &p.hmap, &full_bar[as], cc * p.kblock,
                           x0 + dxi - 1, y0 - 1, n0);
             }
             if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
@@ -583,7 +612,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
                 mbar_arrive(fb);
               } else {
                 mbar_arrive_expect_tx(fb, kBBytes);
-                tma_load_2d(smem_w + bs * kBBytes, &p.bmap, fb, p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0);
+                tma_load_2d(smem_w + bs * kBBytes, &p.bmap, fb, p.halo_wk[dxi * 3 + dyi] + cc * p.kblock, co0);
               }
               if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
             }
@@ -593,12 +622,12 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int cc = 0; cc < p.c2_chunks; ++cc) {
           mbar_wait(&empty_bar[as], aph ^ 1);
           mbar_arrive_expect_tx(&full_bar[as], 2 * kABytes);
-          tma_load_4d(smem + as * kHaloABytes, &p.hmap2, &full_bar[as], cc * kConvBlockK, x0, y0, n0);
+          tma_load_4d(smem + as * kHaloABytes, &p.hmap2, &full_bar[as], cc * p.kblock, x0, y0, n0);
           if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
           uint64_t* fb = &full_bar[kHaloStagesA + bs];
           mbar_wait(&empty_bar[kHaloStagesA + bs], bph ^ 1);
           mbar_arrive_expect_tx(fb, kBBytes);
-          tma_load_2d(smem_w + bs * kBBytes, &p.bmap2, fb, cc * kConvBlockK, co0);
+          tma_load_2d(smem_w + bs * kBBytes, &p.bmap2, fb, cc * p.kblock, co0);
           if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
         }
       }
@@ -610,10 +639,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      uint32_t idesc = 0;                      // M = 128 (output channels), N = 256 (pixels)
-      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
-      idesc |= (uint32_t)(256 >> 3) << 17;
-      idesc |= (uint32_t)(128 >> 4) << 24;
+      const uint32_t idesc = make_idesc(128, 256, p.in16);   // M = 128 (output channels), N = 256 (pixels)
       const uint64_t pdesc0 = make_smem_desc(smem_u32(smem));      // halo copies (N operand)
       const uint64_t wdesc0 = make_smem_desc(smem_u32(smem_w));    // weights     (M operand)
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -642,7 +668,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
               }
 #pragma unroll
               for (int k = 0; k < kConvBlockK / 8; ++k) {
-                umma_tf32(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+                umma_any(p.in16, d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
                 first = 1;
               }
               umma_commit(&empty_bar[kHaloStagesA + bs]);
@@ -660,7 +686,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint64_t wdesc = wdesc0 + (uint64_t)bs * (uint64_t)(kBBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 8; ++k) {
-            umma_tf32(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+            umma_any(p.in16, d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
             first = 1;
           }
           umma_commit(&empty_bar[kHaloStagesA + bs]);
@@ -696,10 +722,10 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           uint8_t* sa = smem + stage * kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const CUtensorMap* am = &p.amap[p.tap_map[tap]];
-          tma_load_2d(sa, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * kConvBlockK, co0);
+          tma_load_2d(sa, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * p.kblock, co0);
 #pragma unroll
           for (int j = 0; j < NT; ++j)
-            tma_load_4d(sa + kPOff + j * kABytes, am, &full_bar[stage], cc * kConvBlockK,
+            tma_load_4d(sa + kPOff + j * kABytes, am, &full_bar[stage], cc * p.kblock,
                         x0[j] + p.tap_dx[tap], y0[j] + p.tap_dy[tap], n0[j]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++cc == p.c_chunks) { cc = 0; ++tap; }
@@ -713,11 +739,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      // M = 128 (output channels), N = 256 (pixels)
-      uint32_t idesc = 0;
-      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
-      idesc |= (uint32_t)(256 >> 3) << 17;
-      idesc |= (uint32_t)(128 >> 4) << 24;
+      const uint32_t idesc = make_idesc(128, 256, p.in16);   // M = 128 (output channels), N = 256 (pixels)
       const uint64_t wdesc0 = make_smem_desc(smem_u32(smem));            // weights  (M operand)
       const uint64_t pdesc0 = make_smem_desc(smem_u32(smem) + kPOff);    // pixels   (N operand)
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -734,7 +756,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 8; ++k) {
             if (k == kConvBlockK / 8 - 1 && it + 1 < kiters) mbar_wait(&full_bar[nstage], nphase);
-            umma_tf32(d_tmem, wdesc0 + so + (uint64_t)(k * 2), pdesc0 + so + (uint64_t)(k * 2), idesc,
+            umma_any(p.in16, d_tmem, wdesc0 + so + (uint64_t)(k * 2), pdesc0 + so + (uint64_t)(k * 2), idesc,
                       (uint32_t)((it | k) != 0));
           }
           umma_commit(&empty_bar[stage]);
@@ -824,12 +846,12 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
+        const int h = p.out16;
         if (p.addend) {
           float4 a[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? __ldg(reinterpret_cast<const float4*>(p.addend + aoff[it]))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[it] = ((vmask >> it) & 1u) ? ld4r(p.addend, aoff[it], h) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
         }
@@ -837,8 +859,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           float4 a[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? *reinterpret_cast<const float4*>(p.out + ooff[it])
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[it] = ((vmask >> it) & 1u) ? ld4r(p.out, ooff[it], h) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
         }
@@ -847,10 +868,12 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int it = 0; it < 8; ++it) {
           if (!((vmask >> it) & 1u)) continue;
           float4 o = v[it];
-          if (p.round_out) {
+          if (h) {
+            o.x = round_f16(o.x); o.y = round_f16(o.y); o.z = round_f16(o.z); o.w = round_f16(o.w);
+          } else if (p.round_out) {
             o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
           }
-          *reinterpret_cast<float4*>(p.out + ooff[it]) = o;
+          st4r(p.out, ooff[it], o, h);
           gs1 += (o.x + o.y) + (o.z + o.w);
           gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
         }
@@ -1013,7 +1036,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
               if (leader) mbar_arrive(&a_full[as]);
             } else {
               if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
-              tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
+              tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * p.kblock,
                                x0 + dxi - 1, y0 - 1, n0);
             }
             if (++as == kPairStagesA) { as = 0; aph ^= 1; }
@@ -1025,7 +1048,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
               } else {
                 if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
                 tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap, map_to_cta(&b_full[bs], 0),
-                                 p.halo_wk[dxi * 3 + dyi] + cc * kConvBlockK, co0 + (int)rank * 64);
+                                 p.halo_wk[dxi * 3 + dyi] + cc * p.kblock, co0 + (int)rank * 64);
               }
               if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
             }
@@ -1034,12 +1057,12 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int cc = 0; cc < p.c2_chunks; ++cc) {          // fused 1x1 shortcut slabs
           mbar_wait(&a_empty[as], aph ^ 1);
           if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * 2 * kABytes);
-          tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap2, map_to_cta(&a_full[as], 0), cc * kConvBlockK,
+          tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap2, map_to_cta(&a_full[as], 0), cc * p.kblock,
                            x0, y0, n0);
           if (++as == kPairStagesA) { as = 0; aph ^= 1; }
           mbar_wait(&b_empty[bs], bph ^ 1);
           if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
-          tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap2, map_to_cta(&b_full[bs], 0), cc * kConvBlockK,
+          tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap2, map_to_cta(&b_full[bs], 0), cc * p.kblock,
                            co0 + (int)rank * 64);
           if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
         }
@@ -1053,10 +1076,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      uint32_t idesc = 0;                      // M = 256 (pixels of both CTAs), N = 128 (output channels)
-      idesc |= 1u << 4; idesc |= 2u << 7; idesc |= 2u << 10;
-      idesc |= (uint32_t)(128 >> 3) << 17;
-      idesc |= (uint32_t)(256 >> 4) << 24;
+      const uint32_t idesc = make_idesc(256, 128, p.in16);   // M = 256 (pixels of both CTAs), N = 128 (output channels)
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem));
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_w));
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -1080,7 +1100,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
                 const uint64_t ad = ad_s + (uint64_t)((dyi * 16 * 128 + j * kABytes) >> 4);
 #pragma unroll
                 for (int k = 0; k < kConvBlockK / 8; ++k)
-                  umma_tf32_pair(d_tmem + j * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                  umma_any_pair(p.in16, d_tmem + j * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
                                  first | (uint32_t)(k != 0));
               }
               first = 1;
@@ -1101,7 +1121,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int k = 0; k < kConvBlockK / 8; ++k)
-              umma_tf32_pair(d_tmem + j * 128, ad_s + (uint64_t)((j * kABytes) >> 4) + (uint64_t)(k * 2),
+              umma_any_pair(p.in16, d_tmem + j * 128, ad_s + (uint64_t)((j * kABytes) >> 4) + (uint64_t)(k * 2),
                              bd + (uint64_t)(k * 2), idesc, first | (uint32_t)(k != 0));
           first = 1;
           umma_commit_pair(&b_empty[bs], 3);
@@ -1181,38 +1201,43 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// `half`: fp16 elements (64 channels per 128-byte swizzle row), else fp32 (32 channels)
 int encode_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, long long sW,
-                   long long sH, long long sN, int TW, int TH, int TN) {
+                   long long sH, long long sN, int TW, int TH, int TN, int half) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 3;
+  const cuuint64_t esz = half ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)sW * 4, (cuuint64_t)sH * 4, (cuuint64_t)sN * 4};
-  cuuint32_t box[4] = {(cuuint32_t)kConvBlockK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * esz, (cuuint64_t)sH * esz, (cuuint64_t)sN * esz};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   LOCO_REQUIRE(((uintptr_t)base & 15) == 0, "activation base not 16B aligned");
   LOCO_REQUIRE(strides[0] % 16 == 0 && strides[1] % 16 == 0 && strides[2] % 16 == 0,
                "activation strides must be multiples of 16 bytes");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides,
+  CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                  const_cast<float*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d N=%d)",
-               (int)r, C, W, H, N);
+  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d N=%d half=%d)",
+               (int)r, C, W, H, N, half);
   return 0;
 }
 
-int encode_w_map(CUtensorMap* m, const float* base, int Ktot, int Cout, int block_n) {
+int encode_w_map(CUtensorMap* m, const float* base, int Ktot, int Cout, int block_n, int half) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 3;
+  const cuuint64_t esz = half ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kConvBlockK, (cuuint32_t)block_n};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
   LOCO_REQUIRE(((uintptr_t)base & 15) == 0, "weight base not 16B aligned");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+  CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<float*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d Cout=%d)", (int)r,
-               Ktot, Cout);
+  LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d Cout=%d half=%d)", (int)r,
+               Ktot, Cout, half);
   return 0;
 }
 
@@ -1226,9 +1251,15 @@ void pick_box(int W, int H, int* TW, int* TH, int* TN) {
 int fill_common(ConvGemmParams& p, const ConvProblem& prob, int N, int Ho, int Wo, float* out,
                 long long osN, long long osH, long long osW, const float* add, long long asN,
                 long long asH, long long asW) {
-  LOCO_REQUIRE(prob.Kc % kConvBlockK == 0, "conv: input channels %d not a multiple of 32", prob.Kc);
+  p.in16 = prob.in.half; p.out16 = prob.out.half;
+  p.kblock = p.in16 ? 2 * kConvBlockK : kConvBlockK;
+  LOCO_REQUIRE(prob.Kc % p.kblock == 0, "conv: input channels %d not a multiple of %d", prob.Kc, p.kblock);
   LOCO_REQUIRE(prob.Ngemm % 32 == 0, "conv: output channels %d not a multiple of 32", prob.Ngemm);
-  p.c_chunks = prob.Kc / kConvBlockK;
+  LOCO_REQUIRE(prob.addend == nullptr || prob.addend->half == prob.out.half,
+               "conv: addend and output must have the same element type");
+  LOCO_REQUIRE(prob.in2 == nullptr || prob.in2->half == prob.in.half,
+               "conv: both inputs of a fused shortcut must have the same element type");
+  p.c_chunks = prob.Kc / p.kblock;
   p.block_n = prob.Ngemm % 128 == 0 ? 128 : (prob.Ngemm % 64 == 0 ? 64 : 32);
   pick_box(Wo, Ho, &p.TW, &p.TH, &p.TN);
   LOCO_REQUIRE((p.TW & (p.TW - 1)) == 0 && (p.TH & (p.TH - 1)) == 0, "conv: tile dims must be powers of two");
@@ -1305,7 +1336,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     LOCO_TRY(fill_common(p, prob, out.N, out.H, out.W, out.ptr, out.sN, out.sH, out.sW,
                          ad ? ad->ptr : nullptr, ad ? ad->sN : 0, ad ? ad->sH : 0, ad ? ad->sW : 0));
     LOCO_TRY(encode_act_map(&p.amap[0], in.ptr, in.C, in.W, in.H, in.N, in.sW, in.sH, in.sN, p.TW,
-                            p.TH, p.TN));
+                            p.TH, p.TN, in.half));
     if (prob.kind == CONV_1x1) {
       p.ntaps = 1; p.tap_map[0] = 0; p.tap_dy[0] = 0; p.tap_dx[0] = 0; p.tap_wk[0] = 0;
     } else {
@@ -1320,7 +1351,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
           p.tap_wk[t] = t * prob.Kc;
         }
     }
-    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, p.block_n));
+    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, p.block_n, prob.in.half));
     L->nlaunch = 1;
   } else if (prob.kind == CONV_3x3_S2) {
     LOCO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W, "conv: stride-2 spatial mismatch");
@@ -1330,9 +1361,9 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     // Four phase views of the input: x[:, pr::2, pc::2, :]
     for (int pr = 0; pr < 2; ++pr)
       for (int pc = 0; pc < 2; ++pc)
-        LOCO_TRY(encode_act_map(&p.amap[pr * 2 + pc], in.ptr + pr * in.sH + pc * in.sW, in.C,
+        LOCO_TRY(encode_act_map(&p.amap[pr * 2 + pc], elem_ptr(in, pr * in.sH + pc * in.sW), in.C,
                                 in.W / 2, in.H / 2, in.N, 2 * in.sW, 2 * in.sH, in.sN, p.TW, p.TH,
-                                p.TN));
+                                p.TN, in.half));
     p.ntaps = 9;
     for (int r = 0; r < 3; ++r)
       for (int s = 0; s < 3; ++s) {
@@ -1343,7 +1374,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
         p.tap_dx[t] = s >> 1;
         p.tap_wk[t] = t * prob.Kc;
       }
-    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n));
+    LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n, prob.in.half));
     L->nlaunch = 1;
   } else if (prob.kind == CONV_3x3_S2_DGRAD) {
     // in = dy [N,h,w,Cout_fwd], out = dx [N,2h,2w,Cin_fwd]; one launch per output phase.
@@ -1353,11 +1384,11 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
     for (int pr = 0; pr < 2; ++pr)
       for (int pc = 0; pc < 2; ++pc) {
         ConvGemmParams& p = L->p[li];
-        float* obase = out.ptr + pr * out.sH + pc * out.sW;
+        float* obase = elem_ptr(out, pr * out.sH + pc * out.sW);
         LOCO_TRY(fill_common(p, prob, out.N, in.H, in.W, obase, out.sN, 2 * out.sH, 2 * out.sW,
                              nullptr, 0, 0, 0));
         LOCO_TRY(encode_act_map(&p.amap[0], in.ptr, in.C, in.W, in.H, in.N, in.sW, in.sH, in.sN,
-                                p.TW, p.TH, p.TN));
+                                p.TW, p.TH, p.TN, in.half));
         int nt = 0;
         for (int r = 0; r < 3; ++r)
           for (int s = 0; s < 3; ++s) {
@@ -1370,7 +1401,7 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
             ++nt;
           }
         p.ntaps = nt;
-        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n));
+        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, 9 * prob.Kc, prob.Ngemm, p.block_n, prob.in.half));
         ++li;
       }
     L->nlaunch = 4;
@@ -1413,10 +1444,12 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
           EncodeTiledFn fn = get_encode_fn();
           if (!fn) return 3;
           cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
-          cuuint64_t strides[3] = {(cuuint64_t)in.sW * 4, (cuuint64_t)in.sH * 4, (cuuint64_t)in.sN * 4};
-          cuuint32_t box[4] = {(cuuint32_t)kConvBlockK, 16, 18, 1};
+          const cuuint64_t esz = in.half ? 2 : 4;
+          const CUtensorMapDataType dt = in.half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+          cuuint64_t strides[3] = {(cuuint64_t)in.sW * esz, (cuuint64_t)in.sH * esz, (cuuint64_t)in.sN * esz};
+          cuuint32_t box[4] = {(cuuint32_t)p.kblock, 16, 18, 1};
           cuuint32_t estr[4] = {1, 1, 1, 1};
-          CUresult r = fn(&p.hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.ptr, dims, strides, box, estr,
+          CUresult r = fn(&p.hmap, dt, 4, in.ptr, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo) failed: %d", (int)r);
@@ -1429,19 +1462,19 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
           if (prob.in2 != nullptr) {
             const View& i2 = *prob.in2;
             LOCO_REQUIRE(i2.N == in.N && i2.H == in.H && i2.W == in.W && i2.C == prob.Kc2 &&
-                             prob.Kc2 % kConvBlockK == 0 && prob.wpack2 != nullptr,
+                             prob.Kc2 % p.kblock == 0 && prob.wpack2 != nullptr,
                          "conv: fused shortcut input mismatch");
             cuuint64_t d2[4] = {(cuuint64_t)i2.C, (cuuint64_t)i2.W, (cuuint64_t)i2.H, (cuuint64_t)i2.N};
-            cuuint64_t s2[3] = {(cuuint64_t)i2.sW * 4, (cuuint64_t)i2.sH * 4, (cuuint64_t)i2.sN * 4};
-            cuuint32_t b2[4] = {(cuuint32_t)kConvBlockK, 16, 16, 1};
+            cuuint64_t s2[3] = {(cuuint64_t)i2.sW * esz, (cuuint64_t)i2.sH * esz, (cuuint64_t)i2.sN * esz};
+            cuuint32_t b2[4] = {(cuuint32_t)p.kblock, 16, 16, 1};
             LOCO_REQUIRE(((uintptr_t)i2.ptr & 15) == 0 && s2[0] % 16 == 0 && s2[1] % 16 == 0 && s2[2] % 16 == 0,
                          "conv: fused shortcut input not 16B aligned");
-            r = fn(&p.hmap2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, i2.ptr, d2, s2, b2, estr,
+            r = fn(&p.hmap2, dt, 4, i2.ptr, d2, s2, b2, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             LOCO_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(shortcut) failed: %d", (int)r);
-            LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 128));
-            p.c2_chunks = prob.Kc2 / kConvBlockK;
+            LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 128, prob.in.half));
+            p.c2_chunks = prob.Kc2 / p.kblock;
           }
         }
       }
@@ -1464,11 +1497,11 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
       if (p.nt == 4 && !(e && atoi(e) == 0) && units % 2 == 0 && items >= 2) {
         p.nt = 5;
         L->grid[i] &= ~1;
-        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, 64));
-        if (p.c2_chunks > 0) LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 64));
+        LOCO_TRY(encode_w_map(&p.bmap, prob.wpack, p.ntaps * prob.Kc, prob.Ngemm, 64, prob.in.half));
+        if (p.c2_chunks > 0) LOCO_TRY(encode_w_map(&p.bmap2, prob.wpack2, prob.Kc2, prob.Ngemm, 64, prob.in.half));
       }
     }
-    L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * (p.ntaps * p.c_chunks + p.c2_chunks) * kConvBlockK;
+    L->flops += 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * (p.ntaps * p.c_chunks + p.c2_chunks) * p.kblock;
     LOCO_REQUIRE(prob.in2 == nullptr || p.c2_chunks > 0,
                  "conv: a fused 1x1 shortcut needs the halo variant (check conv_halo_eligible)");
   }

@@ -54,6 +54,11 @@ struct ConvGemmParams {
   int st_choff[2];            // channel offset of this output inside the consumer's tensor
   int accumulate;             // out += result (VJP fan-in)
   int round_out;              // round stored values to tf32
+  // element types: in16 = activations and packed weights are fp16 (tcgen05.mma kind::f16, 64
+  // channels per 128-byte swizzle row), else fp32 consumed as tf32 (32 channels per row);
+  // out16 = the output / addend / accumulate tensors are fp16, else fp32.  Accumulation is fp32.
+  int in16, out16;
+  int kblock;                 // channels per K stage: 64 (fp16) or 32 (fp32)
 };
 
 enum ConvKind {
@@ -68,7 +73,7 @@ struct ConvProblem {
   int kind;
   View in;              // activations feeding the GEMM (x for fprop, dy for dgrad)
   View out;             // result (y for fprop, dx for dgrad)
-  const float* wpack;   // [Ngemm][ntaps_total * Kc] K-major, tf32-rounded
+  const float* wpack;   // [Ngemm][ntaps_total * Kc] K-major, tf32-rounded fp32 -- or fp16 data when in.half
   int Kc;               // channels of `in`
   int Ngemm;            // channels of `out`
   const float* bias = nullptr;
@@ -77,7 +82,7 @@ struct ConvProblem {
   const View* addend = nullptr;
   // optional fused 1x1 shortcut (only honoured by the halo variant: check conv_halo_eligible first)
   const View* in2 = nullptr;
-  const float* wpack2 = nullptr;   // [Ngemm][Kc2] K-major, tf32-rounded
+  const float* wpack2 = nullptr;   // [Ngemm][Kc2] K-major, tf32-rounded (fp16 data when in.half)
   int Kc2 = 0;
   int accumulate = 0;
   int round_out = 0;

@@ -20,7 +20,12 @@ __device__ __forceinline__ float silu_grad(float u) {
 // ------------------------------------------------------------------------------------------------
 // Weight packing
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_fprop_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout,
+// destination element: tf32-rounded fp32 (tensor core kind::tf32) or fp16 (kind::f16)
+__device__ __forceinline__ void put_w(float* dst, long long i, float v) { dst[i] = round_tf32(v); }
+__device__ __forceinline__ void put_w(__half* dst, long long i, float v) { dst[i] = __float2half_rn(v); }
+
+template <typename T>
+__global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout,
                                   int Cin, int taps) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -28,10 +33,11 @@ __global__ void pack_fprop_kernel(const float* __restrict__ w, float* __restrict
     const int ci = (int)(i % Cin);
     const int t = (int)((i / Cin) % taps);
     const int co = (int)(i / ((long long)Cin * taps));
-    dst[i] = round_tf32(w[((long long)co * Cin + ci) * taps + t]);
+    put_w(dst, i, w[((long long)co * Cin + ci) * taps + t]);
   }
 }
-__global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout,
+template <typename T>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout,
                                   int Cin, int taps, int cout_total, int co_off) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -39,8 +45,7 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
     const int co = (int)(i % Cout);
     const int t = (int)((i / Cout) % taps);
     const int ci = (int)(i / ((long long)Cout * taps));
-    dst[((long long)ci * taps + t) * cout_total + co_off + co] =
-        round_tf32(w[((long long)co * Cin + ci) * taps + t]);
+    put_w(dst, ((long long)ci * taps + t) * cout_total + co_off + co, w[((long long)co * Cin + ci) * taps + t]);
   }
 }
 __global__ void pack_edge_kernel(const float* __restrict__ w, float* __restrict__ dst, int C,
@@ -59,6 +64,7 @@ __global__ void pack_edge_kernel(const float* __restrict__ w, float* __restrict_
 // Edge convolutions
 // ------------------------------------------------------------------------------------------------
 constexpr int kEdgeIters = 16;
+template <bool F16>
 __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* __restrict__ We,
                                    const float* __restrict__ bias, int bias_rows, View out,
                                    int flip, int round_out) {
@@ -99,11 +105,12 @@ __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* _
     acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y);
     acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
   }
-  *reinterpret_cast<float4*>(out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4) = acc;
+  st4t<F16>(out.ptr, n * out.sN + y * out.sH + x * out.sW + cv * 4, acc);
   }
 }
 
 // One warp per output pixel; lanes stride over channels, three warp reductions per pixel.
+template <bool F16>
 __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
                                    const float* __restrict__ bias, int bias_rows,
                                    float* __restrict__ out3, int flip) {
@@ -125,10 +132,10 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
     for (int s = 0; s < 3; ++s) {
       const int xx = x + (flip ? 1 - s : s - 1);
       if (xx < 0 || xx >= W) continue;
-      const float* src = in.ptr + n * in.sN + yy * in.sH + xx * in.sW;
+      const long long soff = n * in.sN + yy * in.sH + xx * in.sW;
       const float* w = &sw[(r * 3 + s) * 3 * C];
       for (int c = lane * 4; c < C; c += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(src + c);
+        const float4 v = ld4t<F16>(in.ptr, soff + c);
         const float4 w0 = *reinterpret_cast<const float4*>(w + c);
         const float4 w1 = *reinterpret_cast<const float4*>(w + C + c);
         const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * C + c);
@@ -177,6 +184,7 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256, 2)
 edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __restrict__ bias,
                       int bias_rows, float* __restrict__ out3, int flip) {
@@ -205,7 +213,7 @@ edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __rest
       for (int c = 0; c < kStrip + 2; ++c) {
         const int xx = x0 + c - 1;
         win[c] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                     ? ld4(in.ptr + (long long)n * in.sN + (long long)yy * in.sH + (long long)xx * in.sW + lane * 4)
+                     ? ld4t<F16>(in.ptr, (long long)n * in.sN + (long long)yy * in.sH + (long long)xx * in.sW + lane * 4)
                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -234,6 +242,7 @@ edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __rest
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ We,
                       const float* __restrict__ bias, int bias_rows, View out, int flip,
@@ -287,8 +296,7 @@ edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ W
     for (int q = 0; q < kStrip; ++q) {
       float4 o = acc[q];
       if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      *reinterpret_cast<float4*>(out.ptr + (long long)n * out.sN + (long long)y * out.sH +
-                                 (long long)(x0 + q) * out.sW + lane * 4) = o;
+      st4t<F16>(out.ptr, (long long)n * out.sN + (long long)y * out.sH + (long long)(x0 + q) * out.sW + lane * 4, o);
     }
   }
 }
@@ -332,7 +340,7 @@ __device__ __forceinline__ float2 mean_rstd(const double* st, double cnt, float 
 // ---- statistics ---------------------------------------------------------------------------------
 // mode 0 (forward/JVP): rows < n_primal: (sum x, sum x^2); tangent rows: (sum dx, sum x0 dx).
 // mode 1 (VJP): a = gamma * act'(u) * gy;  rows: (sum a, sum x a), x = primal input (x has 1 row).
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
@@ -379,11 +387,11 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
       float4 v[kRC];
 #pragma unroll
       for (int r = 0; r < kRC; ++r)
-        v[r] = (n0 + r < N) ? ld4(rows.ptr + (long long)(n0 + r) * rows.sN + roff)
+        v[r] = (n0 + r < N) ? ld4t<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
       float xs[4] = {0.f, 0.f, 0.f, 0.f};
       if (jvp || MODE == 1) {
-        const float4 x0 = (MODE == 0 && n0 == 0) ? v[0] : ld4(x.ptr + xoff);
+        const float4 x0 = (MODE == 0 && n0 == 0) ? v[0] : ld4t<F16>(x.ptr, xoff);
         xs[0] = x0.x; xs[1] = x0.y; xs[2] = x0.z; xs[3] = x0.w;
       }
       if (MODE == 1) {
@@ -435,7 +443,7 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
 
 // ---- apply ----------------------------------------------------------------------------------------
 // mode 0: y = act(gn(x)) for primal rows, JVP rule for tangent rows.  mode 1: VJP rule.
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -490,7 +498,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     // primal-point quantities shared by every tangent / cotangent row of this pixel
     float xh[4] = {0.f, 0.f, 0.f, 0.f}, coef[4] = {1.f, 1.f, 1.f, 1.f};
     if (jvp || MODE == 1) {
-      const float4 x0 = ld4(x.ptr + xoff);
+      const float4 x0 = ld4t<F16>(x.ptr, xoff);
       const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -508,10 +516,10 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
         v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         e[r] = v[r];
         if (n0 + r < N) {
-          v[r] = ld4(rows.ptr + (long long)(n0 + r) * rows.sN + roff);
-          if (MODE == 1 && addend) e[r] = ld4(addend + (long long)(n0 + r) * add_sN + aoff);
+          v[r] = ld4t<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff);
+          if (MODE == 1 && addend) e[r] = ld4t<F16>(addend, (long long)(n0 + r) * add_sN + aoff);
           if (MODE == 1 && accumulate) {
-            const float4 c = ld4(out.ptr + (long long)(n0 + r) * out.sN + ooff);
+            const float4 c = ld4t<F16>(out.ptr, (long long)(n0 + r) * out.sN + ooff);
             e[r].x += c.x; e[r].y += c.y; e[r].z += c.z; e[r].w += c.w;
           }
         }
@@ -537,11 +545,11 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
             else o[i] = mr0.y * (coef[i] * vs[i] - t2.x - xh[i] * t2.y) + es[i];
           }
         }
-        if (round_out) {
+        if (round_out && !F16) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = round_tf32(o[i]);
         }
-        *reinterpret_cast<float4*>(out.ptr + (long long)n * out.sN + ooff) = make_float4(o[0], o[1], o[2], o[3]);
+        st4t<F16>(out.ptr, (long long)n * out.sN + ooff, make_float4(o[0], o[1], o[2], o[3]));
       }
     }
   }
@@ -550,6 +558,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
 // ------------------------------------------------------------------------------------------------
 // Resampling / add
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void upsample2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
@@ -560,18 +569,18 @@ __global__ void upsample2x_kernel(View in, View out, float scale, int accumulate
     const int x = (int)(r % out.W); r /= out.W;
     const int y = (int)(r % out.H);
     const int n = (int)(r / out.H);
-    float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + (y >> 1) * in.sH +
-                                                (x >> 1) * in.sW + cv * 4);
+    float4 v = ld4t<F16>(in.ptr, n * in.sN + (y >> 1) * in.sH + (x >> 1) * in.sW + cv * 4);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    const long long o = n * out.sN + y * out.sH + x * out.sW + cv * 4;
     if (accumulate) {
-      const float4 p = *reinterpret_cast<const float4*>(o);
+      const float4 p = ld4t<F16>(out.ptr, o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
-    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-    *reinterpret_cast<float4*>(o) = v;
+    if (round_out && !F16) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    st4t<F16>(out.ptr, o, v);
   }
 }
+template <bool F16>
 __global__ void sumpool2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
@@ -582,22 +591,23 @@ __global__ void sumpool2x_kernel(View in, View out, float scale, int accumulate,
     const int x = (int)(r % out.W); r /= out.W;
     const int y = (int)(r % out.H);
     const int n = (int)(r / out.H);
-    const float* b = in.ptr + n * in.sN + (2 * y) * in.sH + (2 * x) * in.sW + cv * 4;
-    const float4 a = *reinterpret_cast<const float4*>(b);
-    const float4 c = *reinterpret_cast<const float4*>(b + in.sW);
-    const float4 d = *reinterpret_cast<const float4*>(b + in.sH);
-    const float4 e = *reinterpret_cast<const float4*>(b + in.sH + in.sW);
+    const long long b = n * in.sN + (2 * y) * in.sH + (2 * x) * in.sW + cv * 4;
+    const float4 a = ld4t<F16>(in.ptr, b);
+    const float4 c = ld4t<F16>(in.ptr, b + in.sW);
+    const float4 d = ld4t<F16>(in.ptr, b + in.sH);
+    const float4 e = ld4t<F16>(in.ptr, b + in.sH + in.sW);
     float4 v = make_float4(scale * ((a.x + c.x) + (d.x + e.x)), scale * ((a.y + c.y) + (d.y + e.y)),
                            scale * ((a.z + c.z) + (d.z + e.z)), scale * ((a.w + c.w) + (d.w + e.w)));
-    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    const long long o = n * out.sN + y * out.sH + x * out.sW + cv * 4;
     if (accumulate) {
-      const float4 p = *reinterpret_cast<const float4*>(o);
+      const float4 p = ld4t<F16>(out.ptr, o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
-    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-    *reinterpret_cast<float4*>(o) = v;
+    if (round_out && !F16) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    st4t<F16>(out.ptr, o, v);
   }
 }
+template <bool F16>
 __global__ void add_views_kernel(View in, View out, int accumulate) {
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
@@ -608,13 +618,13 @@ __global__ void add_views_kernel(View in, View out, int accumulate) {
     const int x = (int)(r % out.W); r /= out.W;
     const int y = (int)(r % out.H);
     const int n = (int)(r / out.H);
-    float4 v = *reinterpret_cast<const float4*>(in.ptr + n * in.sN + y * in.sH + x * in.sW + cv * 4);
-    float* o = out.ptr + n * out.sN + y * out.sH + x * out.sW + cv * 4;
+    float4 v = ld4t<F16>(in.ptr, n * in.sN + y * in.sH + x * in.sW + cv * 4);
+    const long long o = n * out.sN + y * out.sH + x * out.sW + cv * 4;
     if (accumulate) {
-      const float4 p = *reinterpret_cast<const float4*>(o);
+      const float4 p = ld4t<F16>(out.ptr, o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
-    *reinterpret_cast<float4*>(o) = v;
+    st4t<F16>(out.ptr, o, v);
   }
 }
 
@@ -711,15 +721,30 @@ int check_gn_view(const View& v, const char* what) {
 // ------------------------------------------------------------------------------------------------
 int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * kh * kw;
-  pack_fprop_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw);
+  pack_fprop_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int kw, int cout_total,
                     int co_off, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * kh * kw;
-  pack_dgrad_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw, cout_total,
-                                                        co_off);
+  pack_dgrad_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(w, dst, Cout, Cin, kh * kw, cout_total,
+                                                               co_off);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv_fprop16(const float* w, void* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * kh * kw;
+  pack_fprop_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__half*>(dst), Cout, Cin,
+                                                                kh * kw);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv_dgrad16(const float* w, void* dst, int Cout, int Cin, int kh, int kw, int cout_total,
+                      int co_off, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * kh * kw;
+  pack_dgrad_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__half*>(dst), Cout, Cin,
+                                                                kh * kw, cout_total, co_off);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -734,8 +759,9 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
   if (out.C == 128 && out.W % kStrip == 0) {
     const long long nstrips = (long long)out.N * out.H * (out.W / kStrip);
     ProfScope prof(2, 0, s);
-    edge_expand128_kernel<<<grid_for((nstrips + 7) / 8, 1, num_sms() * 4), 256, 0, s>>>(
-        in3, We, bias, bias_rows, out, flip, round_out);
+    const int grid = grid_for((nstrips + 7) / 8, 1, num_sms() * 4);
+    if (out.half) edge_expand128_kernel<true><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+    else edge_expand128_kernel<false><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -746,7 +772,8 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
   dim3 grid((unsigned)((HW + ppb_all - 1) / ppb_all), out.N);
   const size_t smem = 27 * out.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_expand: C=%d too large", out.C);
-  edge_expand_kernel<<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+  if (out.half) edge_expand_kernel<true><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+  else edge_expand_kernel<false><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -755,8 +782,9 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   if (in.C == 128 && in.W % kStrip == 0) {
     const long long nstrips = (long long)in.N * in.H * (in.W / kStrip);
     ProfScope prof(2, 0, s);
-    edge_reduce128_kernel<<<grid_for((nstrips + 7) / 8, 1, num_sms() * 4), 256, 0, s>>>(
-        in, Wr, bias, bias_rows, out3, flip);
+    const int grid = grid_for((nstrips + 7) / 8, 1, num_sms() * 4);
+    if (in.half) edge_reduce128_kernel<true><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip);
+    else edge_reduce128_kernel<false><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip);
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -765,7 +793,8 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   dim3 grid((unsigned)((HW + 8 * kEdgeIters - 1) / (8 * kEdgeIters)), in.N);
   const size_t smem = 27 * in.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_reduce: C=%d too large", in.C);
-  edge_reduce_kernel<<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
+  if (in.half) edge_reduce_kernel<true><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
+  else edge_reduce_kernel<false><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -781,7 +810,12 @@ static int gn_resident(K kernel, int block, int* cache) {
   }
   return *cache;
 }
-static int g_res_stats0[2], g_res_stats1[2], g_res_apply0[2], g_res_apply1[2];   // [block == 192]
+// per device: [storage type][kernel: stats fwd, stats vjp, apply fwd, apply vjp][block == 192]
+static int g_res[kMaxDevices][2][4][2];
+static int* res_slot(int h, int kernel, int bd192) {
+  const int d = current_device();
+  return &g_res[d < kMaxDevices ? d : 0][h][kernel][bd192];
+}
 
 // All kernels of the U-Net programs ask for the same (maximum shared memory) L1/smem split as the
 // tcgen05 conv kernel, so the SMs never have to re-partition between consecutive launches.
@@ -790,35 +824,48 @@ int layers_init() {
   if (!first_time_on_device(done)) return 0;
   const int co = cudaSharedmemCarveoutMaxShared;
 #define LOCO_CARVE(k) LOCO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co))
-  LOCO_CARVE(gn_stats_kernel<0>); LOCO_CARVE(gn_stats_kernel<1>);
-  LOCO_CARVE(gn_apply_kernel<0>); LOCO_CARVE(gn_apply_kernel<1>);
-  LOCO_CARVE(edge_expand_kernel); LOCO_CARVE(edge_reduce_kernel);
-  LOCO_CARVE(edge_expand128_kernel); LOCO_CARVE(edge_reduce128_kernel);
-  LOCO_CARVE(upsample2x_kernel); LOCO_CARVE(sumpool2x_kernel); LOCO_CARVE(add_views_kernel);
+#define LOCO_CARVE2(k) LOCO_CARVE(k<false>); LOCO_CARVE(k<true>)
+  LOCO_CARVE((gn_stats_kernel<0, false>)); LOCO_CARVE((gn_stats_kernel<1, false>));
+  LOCO_CARVE((gn_apply_kernel<0, false>)); LOCO_CARVE((gn_apply_kernel<1, false>));
+  LOCO_CARVE((gn_stats_kernel<0, true>)); LOCO_CARVE((gn_stats_kernel<1, true>));
+  LOCO_CARVE((gn_apply_kernel<0, true>)); LOCO_CARVE((gn_apply_kernel<1, true>));
+  LOCO_CARVE2(edge_expand_kernel); LOCO_CARVE2(edge_reduce_kernel);
+  LOCO_CARVE2(edge_expand128_kernel); LOCO_CARVE2(edge_reduce128_kernel);
+  LOCO_CARVE2(upsample2x_kernel); LOCO_CARVE2(sumpool2x_kernel); LOCO_CARVE2(add_views_kernel);
   LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
   LOCO_CARVE(scale_shift_affine_kernel);
+#undef LOCO_CARVE2
 #undef LOCO_CARVE
   // occupancy queries up front (never inside a stream capture)
   for (int b = 0; b < 2; ++b) {
     const int bd = b ? 192 : 256;
-    gn_resident(gn_stats_kernel<0>, bd, &g_res_stats0[b]);
-    gn_resident(gn_stats_kernel<1>, bd, &g_res_stats1[b]);
-    gn_resident(gn_apply_kernel<0>, bd, &g_res_apply0[b]);
-    gn_resident(gn_apply_kernel<1>, bd, &g_res_apply1[b]);
+    gn_resident(gn_stats_kernel<0, false>, bd, res_slot(0, 0, b));
+    gn_resident(gn_stats_kernel<1, false>, bd, res_slot(0, 1, b));
+    gn_resident(gn_apply_kernel<0, false>, bd, res_slot(0, 2, b));
+    gn_resident(gn_apply_kernel<1, false>, bd, res_slot(0, 3, b));
+    gn_resident(gn_stats_kernel<0, true>, bd, res_slot(1, 0, b));
+    gn_resident(gn_stats_kernel<1, true>, bd, res_slot(1, 1, b));
+    gn_resident(gn_apply_kernel<0, true>, bd, res_slot(1, 2, b));
+    gn_resident(gn_apply_kernel<1, true>, bd, res_slot(1, 3, b));
   }
   return 0;
 }
 
-
+static int same_type(const View& a, const View& b, const char* what) {
+  LOCO_REQUIRE(a.half == b.half, "%s: mixed fp16 / fp32 tensors", what);
+  return 0;
+}
 
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
   const int bd = gn_block_dim(x.C);
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W,
-                           gn_resident(gn_stats_kernel<0>, bd, &g_res_stats0[bd == 192]));
-  ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C, s);
-  gn_stats_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0,
-                                               stats, 1);
+  const int h = x.half;
+  const int res = h ? gn_resident(gn_stats_kernel<0, true>, bd, res_slot(1, 0, bd == 192))
+                    : gn_resident(gn_stats_kernel<0, false>, bd, res_slot(0, 0, bd == 192));
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, res);
+  ProfScope prof(1, (h ? 2.0 : 4.0) * x.N * x.H * x.W * x.C, s);
+  if (h) gn_stats_kernel<0, true><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, 1);
+  else gn_stats_kernel<0, false><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -826,13 +873,18 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
                  float eps, int silu, int round_out, View y, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_apply_fwd"));
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
+  LOCO_TRY(same_type(x, y, "gn_apply_fwd"));
   LOCO_REQUIRE(x.N <= kGnMaxRows, "gn_apply_fwd: batch %d > %d rows", x.N, kGnMaxRows);
   const int bd = gn_block_dim(x.C);
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W,
-                           gn_resident(gn_apply_kernel<0>, bd, &g_res_apply0[bd == 192]));
-  ProfScope prof(1, 8.0 * x.N * x.H * x.W * x.C, s);
-  gn_apply_kernel<0><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
-                                               silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
+  const int h = x.half;
+  const int res = h ? gn_resident(gn_apply_kernel<0, true>, bd, res_slot(1, 2, bd == 192))
+                    : gn_resident(gn_apply_kernel<0, false>, bd, res_slot(0, 2, bd == 192));
+  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, res);
+  ProfScope prof(1, (h ? 4.0 : 8.0) * x.N * x.H * x.W * x.C, s);
+  if (h) gn_apply_kernel<0, true><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                                            silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
+  else gn_apply_kernel<0, false><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                                           silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -840,11 +892,15 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
                  float eps, int silu, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
+  LOCO_TRY(same_type(xp, gy, "gn_stats_vjp"));
   const int bd = gn_block_dim(xp.C);
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W,
-                           gn_resident(gn_stats_kernel<1>, bd, &g_res_stats1[bd == 192]));
-  ProfScope prof(1, 4.0 * (gy.N + 1) * gy.H * gy.W * gy.C, s);
-  gn_stats_kernel<1><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
+  const int h = xp.half;
+  const int res = h ? gn_resident(gn_stats_kernel<1, true>, bd, res_slot(1, 1, bd == 192))
+                    : gn_resident(gn_stats_kernel<1, false>, bd, res_slot(0, 1, bd == 192));
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, res);
+  ProfScope prof(1, (h ? 2.0 : 4.0) * (gy.N + 1) * gy.H * gy.W * gy.C, s);
+  if (h) gn_stats_kernel<1, true><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
+  else gn_stats_kernel<1, false><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -854,15 +910,23 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   LOCO_TRY(check_gn_view(xp, "gn_apply_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_apply_vjp(gy)"));
   LOCO_TRY(check_gn_view(gx, "gn_apply_vjp(gx)"));
-  if (addend) LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)"));
+  LOCO_TRY(same_type(xp, gy, "gn_apply_vjp")); LOCO_TRY(same_type(gy, gx, "gn_apply_vjp(gx)"));
+  if (addend) { LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)")); LOCO_TRY(same_type(*addend, gx, "gn_apply_vjp(addend)")); }
   LOCO_REQUIRE(gy.N <= kGnMaxRows, "gn_apply_vjp: batch %d > %d rows", gy.N, kGnMaxRows);
   const int bd = gn_block_dim(xp.C);
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W,
-                           gn_resident(gn_apply_kernel<1>, bd, &g_res_apply1[bd == 192]));
-  ProfScope prof(1, 4.0 * gy.H * gy.W * gy.C * (1 + gy.N * (2 + (addend ? 1 : 0) + (accumulate ? 1 : 0))), s);
-  gn_apply_kernel<1><<<g.nblk, g.block, 0, s>>>(
-      xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
+  const int h = xp.half;
+  const int res = h ? gn_resident(gn_apply_kernel<1, true>, bd, res_slot(1, 3, bd == 192))
+                    : gn_resident(gn_apply_kernel<1, false>, bd, res_slot(0, 3, bd == 192));
+  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, res);
+  ProfScope prof(1, (h ? 2.0 : 4.0) * gy.H * gy.W * gy.C * (1 + gy.N * (2 + (addend ? 1 : 0) + (accumulate ? 1 : 0))), s);
+  if (h)
+    gn_apply_kernel<1, true><<<g.nblk, g.block, 0, s>>>(
+        xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
+        addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
+  else
+    gn_apply_kernel<1, false><<<g.nblk, g.block, 0, s>>>(
+        xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
+        addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -871,7 +935,9 @@ int upsample2x(View in, View out, float scale, int accumulate, int round_out, cu
   LOCO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && out.N == in.N,
                "upsample2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
+  LOCO_TRY(same_type(in, out, "upsample2x"));
+  if (in.half) upsample2x_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
+  else upsample2x_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -879,7 +945,9 @@ int sumpool2x(View in, View out, float scale, int accumulate, int round_out, cud
   LOCO_REQUIRE(in.H == 2 * out.H && in.W == 2 * out.W && out.C == in.C && out.N == in.N,
                "sumpool2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
-  sumpool2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
+  LOCO_TRY(same_type(in, out, "sumpool2x"));
+  if (in.half) sumpool2x_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
+  else sumpool2x_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -887,7 +955,9 @@ int add_views(View in, View out, int accumulate, cudaStream_t s) {
   LOCO_REQUIRE(in.H == out.H && in.W == out.W && out.C == in.C && out.N == in.N,
                "add_views: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
-  add_views_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
+  LOCO_TRY(same_type(in, out, "add_views"));
+  if (in.half) add_views_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
+  else add_views_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, out, accumulate);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,10 @@ int pack_conv_fprop(const float* w, float* dst, int Cout, int Cin, int kh, int k
 // kh*kw*cout_total and this weight fills columns [co_off, co_off+Cout) of every tap.
 int pack_conv_dgrad(const float* w, float* dst, int Cout, int Cin, int kh, int kw, int cout_total,
                     int co_off, cudaStream_t s);
+// fp16 variants of the two GEMM packs (operands of tcgen05.mma kind::f16; dst holds __half)
+int pack_conv_fprop16(const float* w, void* dst, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+int pack_conv_dgrad16(const float* w, void* dst, int Cout, int Cin, int kh, int kw, int cout_total,
+                      int co_off, cudaStream_t s);
 // 3-channel edge convolutions: -> [9][3][C].  in_is_3: weight is [C][3][3][3] (conv_in), else
 // [3][C][3][3] (conv_out).  Kept in full fp32 (these run on CUDA cores).
 int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t s);

@@ -115,11 +115,14 @@ ConvRef Model::add_conv(const std::string& prefix, int cin, int cout, int ksz, b
   c.cin = cin; c.cout = cout; c.ksz = ksz;
   c.wf = alloc((size_t)cout * cin * ksz * ksz);
   c.wd = alloc((size_t)cout * cin * ksz * ksz);
+  c.wf16 = alloc(((size_t)cout * cin * ksz * ksz + 1) / 2);
+  c.wd16 = alloc(((size_t)cout * cin * ksz * ksz + 1) / 2);
   c.bias = alloc(cout);
   ParamSlot w;
   w.name = prefix + ".weight"; w.kind = ParamSlot::CONV_GEMM;
   if (conv1d) w.shape = {cout, cin, ksz}; else w.shape = {cout, cin, ksz, ksz};
-  w.off_a = c.wf; w.off_b = c.wd; w.cout = cout; w.cin = cin; w.ksz = ksz;
+  w.off_a = c.wf; w.off_b = c.wd; w.off_a16 = c.wf16; w.off_b16 = c.wd16;
+  w.cout = cout; w.cin = cin; w.ksz = ksz;
   w.row_off = 0; w.rows_total = cout;
   add_slot(w);
   ParamSlot b;
@@ -165,12 +168,15 @@ AttnRef Model::add_attn(const std::string& prefix, int C) {
   a.qkv.cin = C; a.qkv.cout = 3 * C; a.qkv.ksz = 1;
   a.qkv.wf = alloc((size_t)3 * C * C);
   a.qkv.wd = alloc((size_t)3 * C * C);
+  a.qkv.wf16 = alloc(((size_t)3 * C * C + 1) / 2);
+  a.qkv.wd16 = alloc(((size_t)3 * C * C + 1) / 2);
   a.qkv.bias = alloc(3 * C);
   const char* names[3] = {"q", "k", "v"};
   for (int i = 0; i < 3; ++i) {
     ParamSlot w;
     w.name = prefix + "." + names[i] + ".weight"; w.shape = {C, C, 1, 1}; w.kind = ParamSlot::CONV_QKV;
-    w.off_a = a.qkv.wf; w.off_b = a.qkv.wd; w.cout = C; w.cin = C; w.ksz = 1;
+    w.off_a = a.qkv.wf; w.off_b = a.qkv.wd; w.off_a16 = a.qkv.wf16; w.off_b16 = a.qkv.wd16;
+    w.cout = C; w.cin = C; w.ksz = 1;
     w.row_off = i * C; w.rows_total = 3 * C;
     add_slot(w);
     ParamSlot b;
@@ -412,6 +418,12 @@ int Model::load_param(const char* name, const float* src, long long numel, cudaS
                                sl.cout, sl.cin, sl.ksz, sl.ksz, s));
       LOCO_TRY(pack_conv_dgrad(src, w(sl.off_b), sl.cout, sl.cin, sl.ksz, sl.ksz, sl.rows_total,
                                sl.row_off, s));
+      // fp16 copies (half-sized: the row offset of a fused q|k|v block counts fp16 elements)
+      LOCO_TRY(pack_conv_fprop16(src, reinterpret_cast<char*>(w(sl.off_a16)) +
+                                          2 * (size_t)sl.row_off * sl.cin * sl.ksz * sl.ksz,
+                                 sl.cout, sl.cin, sl.ksz, sl.ksz, s));
+      LOCO_TRY(pack_conv_dgrad16(src, w(sl.off_b16), sl.cout, sl.cin, sl.ksz, sl.ksz, sl.rows_total,
+                                 sl.row_off, s));
       break;
     case ParamSlot::CONV_EDGE_IN:
       LOCO_TRY(pack_conv_edge(src, w(sl.off_a), sl.cout, 1, s));
@@ -529,11 +541,21 @@ int Plan::build(float* workspace) {
     bs_off += (size_t)rows * 32 * 2 * 2;
     return p;
   };
-  auto Tf = [&](int H, int W, int C) { return make_view(alloc_act((size_t)NB * H * W * C), NB, H, W, C); };
-  auto Tg = [&](int H, int W, int C) {
-    if (NC == 0) return make_view(nullptr, 0, H, W, C);
-    return make_view(alloc_act((size_t)NC * H * W * C), NC, H, W, C);
+  // activations of a plan share one storage type (act16), except the attention core's q|k|v, o and
+  // score tensors, which stay fp32 (Tf32 / Tg32): the conv kernels convert at those boundaries
+  const int A16 = act16;
+  auto act_floats_of = [&](size_t elems, int half) { return half ? (elems + 1) / 2 : elems; };
+  auto Tfx = [&](int H, int W, int C, int half) {
+    return make_view(alloc_act(act_floats_of((size_t)NB * H * W * C, half)), NB, H, W, C, half);
   };
+  auto Tgx = [&](int H, int W, int C, int half) {
+    if (NC == 0) return make_view(nullptr, 0, H, W, C, half);
+    return make_view(alloc_act(act_floats_of((size_t)NC * H * W * C, half)), NC, H, W, C, half);
+  };
+  auto Tf = [&](int H, int W, int C) { return Tfx(H, W, C, A16); };
+  auto Tg = [&](int H, int W, int C) { return Tgx(H, W, C, A16); };
+  auto Tf32 = [&](int H, int W, int C) { return Tfx(H, W, C, 0); };
+  auto Tg32 = [&](int H, int W, int C) { return Tgx(H, W, C, 0); };
   // GroupNorm statistics are fused into the producing conv epilogue in forward-only programs
   // (tangent rows need sum(x0*dx), which a tile of one batch row cannot form)
   const bool fuse_stats = (NT == 0);
@@ -591,9 +613,9 @@ int Plan::build(float* workspace) {
                       const View* addend, const TH* out_th = nullptr, StatTarget extra = StatTarget(),
                       const View* in2 = nullptr, const ConvRef* c2 = nullptr) {
     ConvProblem p;
-    p.kind = kind; p.in = in; p.out = out; p.wpack = dry ? nullptr : M.w(c.wf);
+    p.kind = kind; p.in = in; p.out = out; p.wpack = dry ? nullptr : M.w(in.half ? c.wf16 : c.wf);
     p.Kc = c.cin; p.Ngemm = c.cout;
-    if (in2 != nullptr) { p.in2 = in2; p.wpack2 = dry ? nullptr : M.w(c2->wf); p.Kc2 = c2->cin; }
+    if (in2 != nullptr) { p.in2 = in2; p.wpack2 = dry ? nullptr : M.w(in.half ? c2->wf16 : c2->wf); p.Kc2 = c2->cin; }
     p.bias = dry ? nullptr : M.w(c.bias); p.bias2 = bias2; p.bias_rows = NP;
     p.addend = addend; p.accumulate = 0; p.round_out = 1;
     if (fuse_stats) {
@@ -619,7 +641,7 @@ int Plan::build(float* workspace) {
     ConvProblem p;
     p.kind = fwd_kind == CONV_3x3 ? CONV_3x3_DGRAD
                                   : (fwd_kind == CONV_3x3_S2 ? CONV_3x3_S2_DGRAD : CONV_1x1);
-    p.in = gy; p.out = gx; p.wpack = dry ? nullptr : M.w(c.wd);
+    p.in = gy; p.out = gx; p.wpack = dry ? nullptr : M.w(gy.half ? c.wd16 : c.wd);
     p.Kc = c.cout; p.Ngemm = c.cin;
     p.accumulate = accumulate; p.round_out = 1;
     ConvLaunch* l = mk_conv(p, true);
@@ -774,20 +796,20 @@ int Plan::build(float* workspace) {
     const int H = x.v.H, W = x.v.W, C = R.C, T = H * W;
     View hn = Tf(H, W, C);
     double* st = gn_fwd(x.v, R.n, 0, 1, hn, x.st_self.st, th_fused(x));
-    View qkv = Tf(H, W, 3 * C);
+    View qkv = Tf32(H, W, 3 * C);
     conv_fwd(CONV_1x1, hn, qkv, R.qkv, nullptr, nullptr);
     const int hc = A.kind == 1 ? A.head_ch : 0;
     const int heads = hc > 0 ? C / hc : 1;
     float* S = alloc_act((size_t)NB * heads * T * T);
-    View o = Tf(H, W, C);
+    View o = Tf32(H, W, C);
     const int np = NP;
     I.fwd.push_back([=](cudaStream_t s) { return attention_forward(qkv, np, hc, S, o, s); });
     conv_fwd(CONV_1x1, o, out.v, R.proj, nullptr, &x.v, &out);
     if (NC > 0) {
       begin_group();
-      View go = Tg(H, W, C);
+      View go = Tg32(H, W, C);
       conv_bwd(CONV_1x1, out.g, go, R.proj, 0);
-      View gqkv = Tg(H, W, 3 * C);
+      View gqkv = Tg32(H, W, 3 * C);
       float* gP = alloc_act((size_t)NC * heads * T * T);
       View qkv0 = row0(qkv);
       push_b([=](cudaStream_t s) { return attention_vjp(go, qkv0, hc, S, gP, gqkv, s); });

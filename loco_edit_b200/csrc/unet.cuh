@@ -38,12 +38,15 @@ struct ParamSlot {
   enum Kind { RAW, CONV_GEMM, CONV_QKV, CONV_EDGE_IN, CONV_EDGE_OUT, BIAS_QKV } kind;
   size_t off_a = 0;   // RAW: copy; CONV_GEMM/QKV: fprop pack; EDGE: [9][3][C] pack
   size_t off_b = 0;   // CONV_GEMM/QKV: dgrad pack
+  size_t off_a16 = 0, off_b16 = 0;   // CONV_GEMM/QKV: fp16 copies of the two packs
   int cout = 0, cin = 0, ksz = 0;
   int row_off = 0, rows_total = 0;   // QKV fusion: rows [row_off, row_off+cout) of rows_total
   bool loaded = false;
 };
 
-struct ConvRef { int cin = 0, cout = 0, ksz = 0; size_t wf = 0, wd = 0, bias = 0; };
+// wf / wd: fprop / dgrad GEMM operands (tf32-rounded fp32); wf16 / wd16: the same in fp16 (offsets
+// in floats, half the length) for plans that keep their activations in fp16
+struct ConvRef { int cin = 0, cout = 0, ksz = 0; size_t wf = 0, wd = 0, bias = 0, wf16 = 0, wd16 = 0; };
 struct NormRef { int C = 0; size_t gamma = 0, beta = 0; };
 struct ResRef {
   int cin = 0, cout = 0;
@@ -100,10 +103,13 @@ class Model {
 
 class Plan {
  public:
-  Plan(const Model* m, int n_primal, int n_tangent, int n_cot)
-      : model(m), NP(n_primal), NT(n_tangent), NC(n_cot) {}
+  // flags bit 0: activations stored in fp16 and GEMM layers on tcgen05 kind::f16 (primal-only
+  // programs: the DDIM inversion / denoising loops); 0: fp32 storage, kind::tf32
+  Plan(const Model* m, int n_primal, int n_tangent, int n_cot, int flags = 0)
+      : model(m), NP(n_primal), NT(n_tangent), NC(n_cot), act16(flags & 1) {}
   const Model* model;
   int NP, NT, NC;
+  int act16;
   size_t workspace_floats = 0;
   float* base = nullptr;
   int device = -1;    // device owning the bound workspace (every launch of the plan runs there)

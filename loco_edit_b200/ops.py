@@ -157,6 +157,15 @@ class PullbackWorkspace:
         return self.u_full, self.w
 
 
+    def probe_pair(self, xt, t, at, mask_u8, noise, V_in, k_invert):
+        """Like probe(), rows [0,k_invert) through the mask, rows [k_invert,k) through its complement."""
+        check(self.lib.loco_pullback_probe_pair(
+            self.plan.handle, ptr(xt), float(t), float(at), ptr(mask_u8), 1 if noise else 0, ptr(V_in),
+            self.k, int(k_invert), self.d, ptr(self.u_full), ptr(self.w), _aligned(self.scratch),
+            stream_ptr(xt)), "loco_pullback_probe_pair")
+        return self.u_full, self.w
+
+
 # ---------------------------------------------------------------------------------------------
 # single layers (parity tests)
 # ---------------------------------------------------------------------------------------------
@@ -176,6 +185,29 @@ def conv2d_nhwc(kind, x, w, bias=None, bias_rows=0, addend=None, accumulate=Fals
                                        ptr(bias), bias_rows, ptr(addend), 1 if accumulate else 0,
                                        ptr(out), ptr(scr), scr.numel() if splitk else 0, stream_ptr(x)),
           "loco_conv2d_nhwc")
+    return out
+
+
+def conv2d_nhwc_typed(kind, x, w, bias=None, bias_rows=0, addend=None, out_dtype=None, splitk=True):
+    """Like conv2d_nhwc with fp16 or fp32 tensors: x.dtype selects the tensor-core kind (fp16 ->
+    kind::f16, fp32 -> kind::tf32), out_dtype (default x.dtype) the storage of the result / addend."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float16, torch.float32)
+    out_dtype = out_dtype or x.dtype
+    w = _f32(w)
+    N, H, W_, Cx = x.shape
+    Cout, Cin = w.shape[0], w.shape[1]
+    Ho, Wo = (H // 2, W_ // 2) if kind == 2 else ((2 * H, 2 * W_) if kind == 4 else (H, W_))
+    Cy = Cout if kind in (0, 1, 2) else Cin
+    out = torch.zeros(N, Ho, Wo, Cy, dtype=out_dtype, device=x.device)
+    if addend is not None:
+        assert addend.dtype == out_dtype and addend.is_contiguous()
+    wpack = torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+    scr = torch.zeros(16 << 20, dtype=torch.uint8, device=x.device) if splitk else None
+    check(_lib.load().loco_conv2d_nhwc_ex(kind, ptr(x), N, H, W_, Cx, ptr(w), Cout, Cin, ptr(wpack),
+                                          ptr(bias), bias_rows, ptr(addend), 0, ptr(out), ptr(scr),
+                                          scr.numel() if splitk else 0, 1 if x.dtype == torch.float16 else 0,
+                                          1 if out_dtype == torch.float16 else 0, stream_ptr(x)),
+          "loco_conv2d_nhwc_ex")
     return out
 
 

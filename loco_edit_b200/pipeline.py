@@ -75,6 +75,60 @@ class EditPipeline(object):
                     xt=xt)
 
     @torch.no_grad()
+    def edit_sharded_device(self, x0, mask, pc=0, gen=None, v0_mod=None, v0_null=None, group=None, timer=None):
+        """ONE image edited by all ranks of `group` together (single-edit latency lever):
+        the inversion / forward-to-t chain is serial and runs replicated on every rank (same kernels,
+        same inputs); the k + k_null probes of the two local bases are sharded jointly over the ranks
+        with one all-gather of the W rows per power iteration; the 2*vis_num-1 edited latents of the
+        final DDIM stage are sharded over the ranks and gathered once at the end.
+        Every rank returns the full image batch."""
+        import torch.distributed as dist
+        from . import dist as ld
+        drv = self.driver
+        sched = drv.scheduler
+        sched.set_timesteps(drv.inv_steps, device=self.device, is_inversion=True)
+        xt = x0.contiguous()
+        n = len(sched._ts_host)
+        for i in range(n - 1):
+            t = sched._ts_host[i]
+            xt = sched.step(self.unet(xt, t), t, xt, eta=0, t_idx=i).prev_sample
+        xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            # replicated chains agree to the TF32 noise level only (GroupNorm statistics use atomics);
+            # rank 0's x_t is THE x_t, so that all ranks probe the same Jacobian
+            dist.broadcast(xt, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        t_host = sched._ts_host[t_idx]
+        v0_mod = v0_mod if v0_mod is not None else self._v0(self.k, gen)
+        v0_null = v0_null if v0_null is not None else self._v0(self.k_null, gen)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast(v0_mod, src=src, group=group)
+            dist.broadcast(v0_null, src=src, group=group)
+        vT_mod, s_mod, vT_null, s_null = ld.sharded_local_basis_pair_cuda(
+            self.unet, sched, xt, t_host, self.k, self.k_null, mask, v0_mod, v0_null, self.n_iter,
+            group=group, timer=timer)
+        vT = ops.nullspace_project(vT_mod, vT_null, project=True)
+        batch = drv.build_edit_batch(xt, vT[pc], self.vis_num)
+        mine = ld.shard_images(list(range(batch.shape[0])), group)
+        drv.noise_fn = (lambda i, x: torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=gen)) \
+            if gen is not None else None
+        if mine:
+            local = drv.DDIMforwardsteps(batch[mine[0]:mine[-1] + 1].contiguous(), t_start_idx=drv.edit_t_idx,
+                                         t_end_idx=-1, save_image=False, performance_boosting=True)
+        else:
+            local = batch[:0]
+        imgs = ld.gather_images(local, batch.shape[0], group)
+        return dict(images=imgs, vT=vT, vT_modify=vT_mod, vT_null=vT_null, s_modify=s_mod, s_null=s_null, xt=xt)
+
+    @torch.no_grad()
+    def edit_sharded(self, x0_host, mask_host, pc=0, gen=None, group=None, timer=None):
+        """Host tensors in, edited images back on the host; all ranks of `group` call this together."""
+        x0 = x0_host.to(self.device, non_blocking=True)
+        mask = mask_host.to(self.device, non_blocking=True)
+        out = self.edit_sharded_device(x0, mask, pc=pc, gen=gen, group=group, timer=timer)
+        return out["images"].to("cpu", non_blocking=False)
+
+    @torch.no_grad()
     def edit_batch_device(self, x0s, masks, pc=0, gen=None):
         """Batch editing (BASELINE config 2: many image/mask pairs per GPU).  x0s [B,3,R,R], masks
         bool [B,3,R,R] on the device.  The DDIM inversion, the forward pass to t and the final

@@ -7,6 +7,7 @@ libloco_b200.so; torch only owns the device memory and the stream.
 """
 import collections
 import ctypes as C
+import os
 
 import torch
 
@@ -38,13 +39,14 @@ def _make_arch(a):
 class Plan:
     """A static launch program for a fixed (n_primal, n_tangent, n_cotangent) batch."""
 
-    def __init__(self, unet, n_primal, n_tangent, n_cot):
+    def __init__(self, unet, n_primal, n_tangent, n_cot, half=False):
         self.lib = _lib.load()
         self.unet = unet
         self.shape = (n_primal, n_tangent, n_cot)
+        self.half = bool(half)
         h = C.c_void_p()
-        check(self.lib.loco_plan_create(unet.handle, n_primal, n_tangent, n_cot, C.byref(h)),
-              "loco_plan_create")
+        check(self.lib.loco_plan_create_ex(unet.handle, n_primal, n_tangent, n_cot, 1 if half else 0,
+                                           C.byref(h)), "loco_plan_create_ex")
         self.handle = h
         nbytes = self.lib.loco_plan_workspace_bytes(h)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=unet.device)
@@ -115,6 +117,9 @@ class B200UNet:
         off = ((-self.arena.data_ptr()) % 256) // 4
         check(self.lib.loco_unet_bind_weights(h, C.c_void_p(self.arena.data_ptr() + 4 * off)))
         self._plans = collections.OrderedDict()
+        # arithmetic of the Jacobian-free programs (DDIM loops): fp16 storage + kind::f16 tensor cores,
+        # or fp32 storage + kind::tf32 (LOCO_FWD_FP16=0); the JVP / VJP programs always run tf32
+        self.fwd_half = os.environ.get("LOCO_FWD_FP16", "0") != "0"
         self.load_state_dict(state_dict)
 
     def param_shapes(self):
@@ -142,8 +147,12 @@ class B200UNet:
                                                     stream_ptr(self.device)), "loco_unet_load_param(%s)" % name)
             torch.cuda.current_stream(self.device).synchronize()
 
-    def plan(self, n_primal, n_tangent=0, n_cot=0):
-        key = (n_primal, n_tangent, n_cot)
+    def plan(self, n_primal, n_tangent=0, n_cot=0, half=None):
+        """`half` (fp16 activations + tcgen05 kind::f16) defaults to `self.fwd_half` for the
+        Jacobian-free programs and to False for the JVP / VJP programs."""
+        if half is None:
+            half = self.fwd_half and n_tangent == 0 and n_cot == 0
+        key = (n_primal, n_tangent, n_cot, bool(half))
         if key in self._plans:
             self._plans.move_to_end(key)
             return self._plans[key]
@@ -151,7 +160,7 @@ class B200UNet:
             _, old = self._plans.popitem(last=False)
             old.release()
         with torch.cuda.device(self.device):
-            self._plans[key] = Plan(self, *key)
+            self._plans[key] = Plan(self, n_primal, n_tangent, n_cot, half=half)
         return self._plans[key]
 
     def release_plans(self):
