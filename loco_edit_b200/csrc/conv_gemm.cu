@@ -60,20 +60,16 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int in16) {
   return d;
 }
 // one K step of 32 bytes per operand row: 8 tf32 or 16 fp16 elements
-__device__ __forceinline__ void umma_any(int in16, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
-                                         uint32_t acc) {
-  if (in16) umma_f16(d_tmem, a, b, idesc, acc); else umma_tf32(d_tmem, a, b, idesc, acc);
+// (the element types are template parameters of the kernels: the fp32 / tf32 instantiations are
+// instruction-for-instruction the kernels of round 1, the epilogue runs one warp per SM
+// sub-partition and its time is its instruction count)
+template <bool IN16>
+__device__ __forceinline__ void umma_any(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (IN16) umma_f16(d_tmem, a, b, idesc, acc); else umma_tf32(d_tmem, a, b, idesc, acc);
 }
-__device__ __forceinline__ void umma_any_pair(int in16, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
-                                              uint32_t acc) {
-  if (in16) umma_f16_pair(d_tmem, a, b, idesc, acc); else umma_tf32_pair(d_tmem, a, b, idesc, acc);
-}
-// runtime-typed 4-channel access of the output-side tensors (h = fp16 storage)
-__device__ __forceinline__ float4 ld4r(const float* base, long long off, int h) {
-  return h ? ld4t<true>(base, off) : ld4t<false>(base, off);
-}
-__device__ __forceinline__ void st4r(float* base, long long off, float4 v, int h) {
-  if (h) st4t<true>(base, off, v); else st4t<false>(base, off, v);
+template <bool IN16>
+__device__ __forceinline__ void umma_any_pair(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (IN16) umma_f16_pair(d_tmem, a, b, idesc, acc); else umma_tf32_pair(d_tmem, a, b, idesc, acc);
 }
 
 // L2 prefetch of the epilogue's read-side tile (residual addend and/or the accumulate target) of a
@@ -83,6 +79,7 @@ __device__ __forceinline__ void st4r(float* base, long long off, float4 v, int h
 __device__ __forceinline__ void prefetch_l2(const float* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+template <bool OUT16>
 __device__ __forceinline__ void prefetch_epilogue_tile(const ConvGemmParams& p, int tx, int ty, int tn,
                                                        int co0, int t) {
   if (p.addend == nullptr && !p.accumulate) return;
@@ -91,8 +88,8 @@ __device__ __forceinline__ void prefetch_epilogue_tile(const ConvGemmParams& p, 
   const int y = ty * p.TH + ((R >> p.log_tw) & (p.TH - 1));
   const int n = tn * p.TN + (R >> (p.log_tw + p.log_th));
   if (n >= p.N || y >= p.Ho || x >= p.Wo) return;
-  const int esz = p.out16 ? 2 : 4;
-  const int line = 128 / esz;             // channels per 128-byte line
+  constexpr int esz = OUT16 ? 2 : 4;
+  constexpr int line = 128 / esz;         // channels per 128-byte line
   if (p.addend) {
     const char* a = reinterpret_cast<const char*>(p.addend) +
                     ((long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0) * esz;
@@ -128,6 +125,7 @@ __device__ __forceinline__ void epilogue_transpose(const uint32_t (&r)[32], floa
 // VJP accumulation, tf32 rounding, 128-byte-coalesced stores, fused GroupNorm statistics.  The common
 // cases (whole tile valid, bias on all or none of the rows, no statistics) take branch-free paths:
 // the epilogue runs one warp per SM sub-partition, so its time is its instruction count.
+template <bool OUT16>
 __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, float4 (&v)[8],
                                                     const long long (&ooff)[8], const long long (&aoff)[8],
                                                     uint32_t vmask, uint32_t bmask, float4 bsum, int ch,
@@ -140,12 +138,12 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
     for (int it = 0; it < 8; ++it)
       if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
   }
-  const int h = p.out16;
+  constexpr bool h = OUT16;
   if (p.addend) {
     float4 a[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      a[it] = ((vmask >> it) & 1u) ? ld4r(p.addend, aoff[it] + ch, h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[it] = ((vmask >> it) & 1u) ? ld4t<OUT16>(p.addend, aoff[it] + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
   }
@@ -153,7 +151,7 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
     float4 a[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      a[it] = ((vmask >> it) & 1u) ? ld4r(p.out, ooff[it] + ch, h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[it] = ((vmask >> it) & 1u) ? ld4t<OUT16>(p.out, ooff[it] + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
   }
@@ -173,11 +171,11 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
   }
   if (vmask == 0xFFu) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) st4r(p.out, ooff[it] + ch, v[it], h);
+    for (int it = 0; it < 8; ++it) st4t<OUT16>(p.out, ooff[it] + ch, v[it]);
   } else {
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      if ((vmask >> it) & 1u) st4r(p.out, ooff[it] + ch, v[it], h);
+      if ((vmask >> it) & 1u) st4t<OUT16>(p.out, ooff[it] + ch, v[it]);
   }
   if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) {
     // fused GroupNorm statistics of what was just stored: the 4 lanes that share a channel quad
@@ -205,7 +203,7 @@ __device__ __forceinline__ void epilogue_chunk_tail(const ConvGemmParams& p, flo
   }
 }
 
-template <int NT>
+template <int NT, bool IN16, bool OUT16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kStages = Cfg<NT>::kStages;
@@ -292,9 +290,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const CUtensorMap* am = &p.amap[p.tap_map[tap]];
 #pragma unroll
           for (int j = 0; j < NT; ++j)
-            tma_load_4d(sa + j * kABytes, am, &full_bar[stage], cc * p.kblock, x0[j] + p.tap_dx[tap],
+            tma_load_4d(sa + j * kABytes, am, &full_bar[stage], cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), x0[j] + p.tap_dx[tap],
                         y0[j] + p.tap_dy[tap], n0[j]);
-          tma_load_2d(sa + kBOff, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * p.kblock, co0);
+          tma_load_2d(sa + kBOff, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), co0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++cc == p.c_chunks) { cc = 0; ++tap; }
@@ -309,7 +307,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc(kConvBlockM, p.block_n, p.in16);
+      const uint32_t idesc = make_idesc(kConvBlockM, p.block_n, IN16);
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem));            // stage 0, pixel tile 0
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + kBOff);    // stage 0, weight tile
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -341,7 +339,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int k = 0; k < kConvBlockK / 8; ++k) {
               if (j == NT - 1 && k == kConvBlockK / 8 - 1 && it + 1 < nk) mbar_wait(&full_bar[nstage], nphase);
               // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in 16-byte units)
-              umma_any(p.in16, d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+              umma_any<IN16>(d_tmem + j * kConvMaxBlockN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                         idesc, (uint32_t)((it | k) != 0));
             }
           }
@@ -375,7 +373,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
           const int tm = um * NT + jt;
-          prefetch_epilogue_tile(p, tm % p.tiles_x, (tm / p.tiles_x) % p.tiles_y,
+          prefetch_epilogue_tile<OUT16>(p, tm % p.tiles_x, (tm / p.tiles_x) % p.tiles_y,
                                  tm / (p.tiles_x * p.tiles_y), co0, (int)threadIdx.x - 128);
         }
       }
@@ -470,7 +468,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
             }
           }
-          epilogue_chunk_tail(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr,
+          epilogue_chunk_tail<OUT16>(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr,
                               tn * p.TN + ((q * 32) >> (lTW + lTH)));
         }
       }
@@ -526,7 +524,7 @@ constexpr int kHaloStagesA = 3;
 constexpr int kHaloStagesB = 6;
 constexpr int kHaloSmemBytes = kHaloStagesA * kHaloABytes + kHaloStagesB * kBBytes + 1024 + 256 + kEpiBytes;
 
-template <bool HALO>
+template <bool HALO, bool IN16, bool OUT16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int NT = 2;
@@ -600,7 +598,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_arrive(&full_bar[as]);
             } else {
               mbar_arrive_expect_tx(&full_bar[as], kHaloABytes);
-              tma_load_4d(smem + as * kHaloABytes, &p.hmap, &full_bar[as], cc * p.kblock,
+              tma_load_4d(smem + as * kHaloABytes, &p.hmap, &full_bar[as], cc * (IN16 ? 2 * kConvBlockK : kConvBlockK),
                           x0 + dxi - 1, y0 - 1, n0);
             }
             if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
@@ -612,7 +610,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
                 mbar_arrive(fb);
               } else {
                 mbar_arrive_expect_tx(fb, kBBytes);
-                tma_load_2d(smem_w + bs * kBBytes, &p.bmap, fb, p.halo_wk[dxi * 3 + dyi] + cc * p.kblock, co0);
+                tma_load_2d(smem_w + bs * kBBytes, &p.bmap, fb, p.halo_wk[dxi * 3 + dyi] + cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), co0);
               }
               if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
             }
@@ -622,12 +620,12 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int cc = 0; cc < p.c2_chunks; ++cc) {
           mbar_wait(&empty_bar[as], aph ^ 1);
           mbar_arrive_expect_tx(&full_bar[as], 2 * kABytes);
-          tma_load_4d(smem + as * kHaloABytes, &p.hmap2, &full_bar[as], cc * p.kblock, x0, y0, n0);
+          tma_load_4d(smem + as * kHaloABytes, &p.hmap2, &full_bar[as], cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), x0, y0, n0);
           if (++as == kHaloStagesA) { as = 0; aph ^= 1; }
           uint64_t* fb = &full_bar[kHaloStagesA + bs];
           mbar_wait(&empty_bar[kHaloStagesA + bs], bph ^ 1);
           mbar_arrive_expect_tx(fb, kBBytes);
-          tma_load_2d(smem_w + bs * kBBytes, &p.bmap2, fb, cc * p.kblock, co0);
+          tma_load_2d(smem_w + bs * kBBytes, &p.bmap2, fb, cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), co0);
           if (++bs == kHaloStagesB) { bs = 0; bph ^= 1; }
         }
       }
@@ -639,7 +637,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc(128, 256, p.in16);   // M = 128 (output channels), N = 256 (pixels)
+      const uint32_t idesc = make_idesc(128, 256, IN16);   // M = 128 (output channels), N = 256 (pixels)
       const uint64_t pdesc0 = make_smem_desc(smem_u32(smem));      // halo copies (N operand)
       const uint64_t wdesc0 = make_smem_desc(smem_u32(smem_w));    // weights     (M operand)
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -668,7 +666,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
               }
 #pragma unroll
               for (int k = 0; k < kConvBlockK / 8; ++k) {
-                umma_any(p.in16, d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+                umma_any<IN16>(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
                 first = 1;
               }
               umma_commit(&empty_bar[kHaloStagesA + bs]);
@@ -686,7 +684,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint64_t wdesc = wdesc0 + (uint64_t)bs * (uint64_t)(kBBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 8; ++k) {
-            umma_any(p.in16, d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
+            umma_any<IN16>(d_tmem, wdesc + (uint64_t)(k * 2), pd + (uint64_t)(k * 2), idesc, first);
             first = 1;
           }
           umma_commit(&empty_bar[kHaloStagesA + bs]);
@@ -722,10 +720,10 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           uint8_t* sa = smem + stage * kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const CUtensorMap* am = &p.amap[p.tap_map[tap]];
-          tma_load_2d(sa, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * p.kblock, co0);
+          tma_load_2d(sa, &p.bmap, &full_bar[stage], p.tap_wk[tap] + cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), co0);
 #pragma unroll
           for (int j = 0; j < NT; ++j)
-            tma_load_4d(sa + kPOff + j * kABytes, am, &full_bar[stage], cc * p.kblock,
+            tma_load_4d(sa + kPOff + j * kABytes, am, &full_bar[stage], cc * (IN16 ? 2 * kConvBlockK : kConvBlockK),
                         x0[j] + p.tap_dx[tap], y0[j] + p.tap_dy[tap], n0[j]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++cc == p.c_chunks) { cc = 0; ++tap; }
@@ -739,7 +737,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc(128, 256, p.in16);   // M = 128 (output channels), N = 256 (pixels)
+      const uint32_t idesc = make_idesc(128, 256, IN16);   // M = 128 (output channels), N = 256 (pixels)
       const uint64_t wdesc0 = make_smem_desc(smem_u32(smem));            // weights  (M operand)
       const uint64_t pdesc0 = make_smem_desc(smem_u32(smem) + kPOff);    // pixels   (N operand)
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -756,7 +754,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 8; ++k) {
             if (k == kConvBlockK / 8 - 1 && it + 1 < kiters) mbar_wait(&full_bar[nstage], nphase);
-            umma_any(p.in16, d_tmem, wdesc0 + so + (uint64_t)(k * 2), pdesc0 + so + (uint64_t)(k * 2), idesc,
+            umma_any<IN16>(d_tmem, wdesc0 + so + (uint64_t)(k * 2), pdesc0 + so + (uint64_t)(k * 2), idesc,
                       (uint32_t)((it | k) != 0));
           }
           umma_commit(&empty_bar[stage]);
@@ -800,7 +798,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           ty = (tm / p.tiles_x) % p.tiles_y;
           tn = tm / (p.tiles_x * p.tiles_y);
         }
-        prefetch_epilogue_tile(p, tx, ty, tn, (w / units_m) * 128, (int)threadIdx.x - 128);
+        prefetch_epilogue_tile<OUT16>(p, tx, ty, tn, (w / units_m) * 128, (int)threadIdx.x - 128);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -846,12 +844,12 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           if ((bmask >> it) & 1u) { v[it].x += bsum.x; v[it].y += bsum.y; v[it].z += bsum.z; v[it].w += bsum.w; }
-        const int h = p.out16;
+        constexpr bool h = OUT16;
         if (p.addend) {
           float4 a[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? ld4r(p.addend, aoff[it], h) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[it] = ((vmask >> it) & 1u) ? ld4t<OUT16>(p.addend, aoff[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
         }
@@ -859,7 +857,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           float4 a[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            a[it] = ((vmask >> it) & 1u) ? ld4r(p.out, ooff[it], h) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[it] = ((vmask >> it) & 1u) ? ld4t<OUT16>(p.out, ooff[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 8; ++it) { v[it].x += a[it].x; v[it].y += a[it].y; v[it].z += a[it].z; v[it].w += a[it].w; }
         }
@@ -873,7 +871,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
           } else if (p.round_out) {
             o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
           }
-          st4r(p.out, ooff[it], o, h);
+          st4t<OUT16>(p.out, ooff[it], o);
           gs1 += (o.x + o.y) + (o.z + o.w);
           gs2 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
         }
@@ -932,6 +930,7 @@ static_assert(kPairSmemBytes <= 232448 && kHaloSmemBytes <= 232448, "dynamic sha
 
 // Epilogue of one 128-pixel x block_n tile whose accumulator has TMEM lane = pixel (shared by the
 // pair kernel; same arithmetic and store order as the one-tile kernel's epilogue).
+template <bool OUT16>
 __device__ __forceinline__ void epilogue_pixel_tile(const ConvGemmParams& p, uint32_t taddr, float* tbuf,
                                                     int q, int lane, int tx, int ty, int tn, int co0) {
   const int pr = lane >> 3, cq = lane & 7;
@@ -964,10 +963,11 @@ __device__ __forceinline__ void epilogue_pixel_tile(const ConvGemmParams& p, uin
     }
     tmem_ld_wait();
     epilogue_transpose(r, tbuf, lane, pr, cq, v);
-    epilogue_chunk_tail(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr, nrow);
+    epilogue_chunk_tail<OUT16>(p, v, ooff, aoff, vmask, bmask, bsum, ch, co0, cq, pr, nrow);
   }
 }
 
+template <bool IN16, bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1036,7 +1036,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
               if (leader) mbar_arrive(&a_full[as]);
             } else {
               if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
-              tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * p.kblock,
+              tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap, map_to_cta(&a_full[as], 0), cc * (IN16 ? 2 * kConvBlockK : kConvBlockK),
                                x0 + dxi - 1, y0 - 1, n0);
             }
             if (++as == kPairStagesA) { as = 0; aph ^= 1; }
@@ -1048,7 +1048,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
               } else {
                 if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
                 tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap, map_to_cta(&b_full[bs], 0),
-                                 p.halo_wk[dxi * 3 + dyi] + cc * p.kblock, co0 + (int)rank * 64);
+                                 p.halo_wk[dxi * 3 + dyi] + cc * (IN16 ? 2 * kConvBlockK : kConvBlockK), co0 + (int)rank * 64);
               }
               if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
             }
@@ -1057,12 +1057,12 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int cc = 0; cc < p.c2_chunks; ++cc) {          // fused 1x1 shortcut slabs
           mbar_wait(&a_empty[as], aph ^ 1);
           if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * 2 * kABytes);
-          tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap2, map_to_cta(&a_full[as], 0), cc * p.kblock,
+          tma_load_4d_pair(smem + as * kHaloABytes, &p.hmap2, map_to_cta(&a_full[as], 0), cc * (IN16 ? 2 * kConvBlockK : kConvBlockK),
                            x0, y0, n0);
           if (++as == kPairStagesA) { as = 0; aph ^= 1; }
           mbar_wait(&b_empty[bs], bph ^ 1);
           if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kPairBBytes);
-          tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap2, map_to_cta(&b_full[bs], 0), cc * p.kblock,
+          tma_load_2d_pair(smem_w + bs * kPairBBytes, &p.bmap2, map_to_cta(&b_full[bs], 0), cc * (IN16 ? 2 * kConvBlockK : kConvBlockK),
                            co0 + (int)rank * 64);
           if (++bs == kPairStagesB) { bs = 0; bph ^= 1; }
         }
@@ -1076,7 +1076,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc(256, 128, p.in16);   // M = 256 (pixels of both CTAs), N = 128 (output channels)
+      const uint32_t idesc = make_idesc(256, 128, IN16);   // M = 256 (pixels of both CTAs), N = 128 (output channels)
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem));
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_w));
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -1100,7 +1100,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
                 const uint64_t ad = ad_s + (uint64_t)((dyi * 16 * 128 + j * kABytes) >> 4);
 #pragma unroll
                 for (int k = 0; k < kConvBlockK / 8; ++k)
-                  umma_any_pair(p.in16, d_tmem + j * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                  umma_any_pair<IN16>(d_tmem + j * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
                                  first | (uint32_t)(k != 0));
               }
               first = 1;
@@ -1121,7 +1121,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int k = 0; k < kConvBlockK / 8; ++k)
-              umma_any_pair(p.in16, d_tmem + j * 128, ad_s + (uint64_t)((j * kABytes) >> 4) + (uint64_t)(k * 2),
+              umma_any_pair<IN16>(d_tmem + j * 128, ad_s + (uint64_t)((j * kABytes) >> 4) + (uint64_t)(k * 2),
                              bd + (uint64_t)(k * 2), idesc, first | (uint32_t)(k != 0));
           first = 1;
           umma_commit_pair(&b_empty[bs], 3);
@@ -1150,13 +1150,13 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       const int ty0 = ((um / p.tiles_x) % half_y) * 2;
       const int tn = um / (p.tiles_x * half_y);
 #pragma unroll
-      for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
+      for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile<OUT16>(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int jt = ((p.debug == 5 || p.debug == 9) ? 2 : 0); jt < 2; ++jt) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
-        epilogue_pixel_tile(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
+        epilogue_pixel_tile<OUT16>(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
       }
       tc_fence_before();
       __syncwarp();
@@ -1508,19 +1508,42 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
   return 0;
 }
 
+namespace {
+typedef void (*ConvKernel)(const ConvGemmParams);
+// kernel of variant nt (1, 2: pixel tiles per item; 3: wide; 4: halo; 5: CTA-pair halo) for the
+// element types (in16, out16); the wide non-halo variant exists for fp32 only (profiling aid)
+ConvKernel conv_kernel(int nt, int in16, int out16, int* smem) {
+#define LOCO_PICK(K) (in16 ? (out16 ? (ConvKernel)K(true, true) : (ConvKernel)K(true, false)) \
+                           : (out16 ? (ConvKernel)K(false, true) : (ConvKernel)K(false, false)))
+#define K_PAIR(a, b) conv_gemm_tf32_pair_kernel<a, b>
+#define K_HALO(a, b) conv_gemm_tf32_wide_kernel<true, a, b>
+#define K_TWO(a, b) conv_gemm_tf32_kernel<2, a, b>
+#define K_ONE(a, b) conv_gemm_tf32_kernel<1, a, b>
+  switch (nt) {
+    case 5: *smem = kPairSmemBytes; return LOCO_PICK(K_PAIR);
+    case 4: *smem = kHaloSmemBytes; return LOCO_PICK(K_HALO);
+    case 3: *smem = Cfg<2>::kSmemBytes; return (in16 || out16) ? nullptr : (ConvKernel)conv_gemm_tf32_wide_kernel<false, false, false>;
+    case 2: *smem = Cfg<2>::kSmemBytes; return LOCO_PICK(K_TWO);
+    default: *smem = Cfg<1>::kSmemBytes; return LOCO_PICK(K_ONE);
+  }
+#undef K_ONE
+#undef K_TWO
+#undef K_HALO
+#undef K_PAIR
+#undef LOCO_PICK
+}
+}  // namespace
+
 int conv_init() {
   static bool attr_set[kMaxDevices] = {false};
   if (first_time_on_device(attr_set)) {
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_wide_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
-    LOCO_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_pair_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    for (int nt = 1; nt <= 5; ++nt)
+      for (int i = 0; i < 2; ++i)
+        for (int o = 0; o < 2; ++o) {
+          int smem = 0;
+          ConvKernel k = conv_kernel(nt, i, o, &smem);
+          if (k) LOCO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        }
   }
   return 0;
 }
@@ -1530,16 +1553,15 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   {
     ProfScope prof(0, L.flops, stream);
     for (int i = 0; i < L.nlaunch; ++i) {
-      if (L.p[i].nt == 5)
-        conv_gemm_tf32_pair_kernel<<<L.grid[i], kThreads, kPairSmemBytes, stream>>>(L.p[i]);
-      else if (L.p[i].nt == 4)
-        conv_gemm_tf32_wide_kernel<true><<<L.grid[i], kThreads, kHaloSmemBytes, stream>>>(L.p[i]);
-      else if (L.p[i].nt == 3)
-        conv_gemm_tf32_wide_kernel<false><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
-      else if (L.p[i].nt == 2)
-        conv_gemm_tf32_kernel<2><<<L.grid[i], kThreads, Cfg<2>::kSmemBytes, stream>>>(L.p[i]);
-      else
-        conv_gemm_tf32_kernel<1><<<L.grid[i], kThreads, Cfg<1>::kSmemBytes, stream>>>(L.p[i]);
+      int smem = 0;
+      ConvKernel k = conv_kernel(L.p[i].nt, L.p[i].in16, L.p[i].out16, &smem);
+      LOCO_REQUIRE(k != nullptr, "conv: variant %d has no fp16 instantiation", L.p[i].nt);
+      if (L.p[i].nt == 5) {
+        // the CTA-pair kernel carries __cluster_dims__(2,1,1): plain launch, even grid
+        k<<<L.grid[i], kThreads, smem, stream>>>(L.p[i]);
+      } else {
+        k<<<L.grid[i], kThreads, smem, stream>>>(L.p[i]);
+      }
     }
     count_launch(L.nlaunch);
   }

@@ -334,8 +334,8 @@ class EditUncondDiffusion(object):
                 "(the reference generates it with SAM, which this path does not ship). Write a bool "
                 "[n,1,res,res] tensor there (loco_edit_b200.masks.save_masks), or pass "
                 "--allow_dataset_mask True to use the synthetic dataset's rectangle on purpose.")
-        masks = torch.load(mpath, map_location="cpu")
-        return masks[getattr(self.args, "mask_index", 0)].squeeze(dim=0).repeat(3, 1, 1)
+        from .masks import load_mask
+        return load_mask(self.result_folder, getattr(self.args, "mask_index", 0))
 
     @torch.no_grad()
     def run_edit_null_space_projection(

@@ -205,6 +205,11 @@ def test_p2_driver_ffhq_script_settings(dev, tmp_path):
         result_folder=str(tmp_path), sample_idx=4, choose_sem="hair", mask_index=0, sampling_mode=False,
         vT_path="", vT1_path="", verbose=False, save_images=False, noise_schedule=None)
     e = EditUncondDiffusion(args, unet=net, dataset=_DS())
+    # FFHQ-style datasets take their mask from the cached mask/mask.pt (src/modules/edit.py:2252-2265;
+    # the reference fills it with SAM): row 1 of a 2-mask file, selected with --mask_index
+    from loco_edit_b200.masks import save_masks
+    save_masks(e.result_folder, torch.stack([~mask[0], mask[0]], 0))
+    e.args.mask_index = 1
     d = x0.numel()
     v0a, _ = torch.linalg.qr(torch.randn(d, 3, generator=g))
     v0b, _ = torch.linalg.qr(torch.randn(d, 5, generator=g))

@@ -162,3 +162,41 @@ def test_hf_unet2d_checkpoint_names_map_onto_the_ddpm_state_dict(legacy_attn):
         short.pop("conv_out.bias")
         with pytest.raises(KeyError):
             hf_unet2d_to_ddpm(short, arch)
+
+
+def test_mask_files_and_postprocessing(tmp_path):
+    """mask/mask.pt format of the SAM wrapper (src/modules/mask_segmentation.py:18-26), the row
+    selection of the drivers (src/modules/edit.py:2247) and the DiffEdit formula (:1401-1402)."""
+    import torch.nn.functional as F
+    from loco_edit_b200 import masks as M
+    g = torch.Generator().manual_seed(2)
+    raw = torch.rand(3, 37, 53, generator=g) > 0.5
+    want = torch.round(F.interpolate(raw.unsqueeze(dim=1).to(torch.float32), [16, 16]).squeeze(dim=1)).to(torch.bool)
+    got = M.resize_masks(raw, 16)
+    assert got.dtype == torch.bool and torch.equal(got, want)
+    path = M.save_masks(str(tmp_path), got)
+    assert path.endswith(os.path.join("mask", "mask.pt")) and torch.load(path).shape == (3, 16, 16)
+    m1 = M.load_mask(str(tmp_path), 1)
+    assert m1.shape == (3, 16, 16) and torch.equal(m1[0], got[1]) and torch.equal(m1[2], got[1])
+    e1, e2 = torch.randn(10, 3, 8, 8, generator=g), torch.randn(10, 3, 8, 8, generator=g)
+    mask = (e1 - e2).mean(dim=0, keepdim=True).mean(dim=1)
+    ref = torch.round((mask - mask.min() / (mask.max() - mask.min()))).to(torch.bool)      # reference line, verbatim
+    assert torch.equal(M.diffedit_mask(e1, e2), ref)
+    assert int(M.rectangle_mask(256).sum()) == 3 * 64 * 128
+
+
+def test_driver_refuses_to_invent_a_mask(tmp_path):
+    """A non-CelebA dataset without mask/mask.pt is an error, `use_mask=False` means no
+    mask (src/modules/edit.py:2266-2267) -- checked on the host logic only (no GPU needed)."""
+    import types
+    from loco_edit_b200.edit import EditUncondDiffusion
+    e = object.__new__(EditUncondDiffusion)
+    e.dataset_name, e.result_folder = "FFHQ", str(tmp_path)
+    e.args = types.SimpleNamespace(mask_index=0)
+    e.dataset = None
+    assert e._get_masks(0, use_mask=False) is None
+    with pytest.raises(FileNotFoundError):
+        e._get_masks(0, use_mask=True)
+    from loco_edit_b200.masks import save_masks
+    save_masks(str(tmp_path), torch.ones(2, 8, 8, dtype=torch.bool))
+    assert e._get_masks(0, use_mask=True).shape == (3, 8, 8)
