@@ -192,6 +192,13 @@ int loco_conv2d_fused_nhwc(const float* x, int N, int H, int W, int Cin, const f
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
                     float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
                     float* ms_out, int* ksplit_out, int* grid_out, void* stream);
+/* Same with typed tensors (in16 / out16 as in loco_conv2d_nhwc_ex; wpack must hold fp16 data when
+ * in16), an optional residual addend of the output's type and optional fused GroupNorm statistics
+ * (stats: 64*N doubles, zeroed by the caller; they keep accumulating over the repetitions). */
+int loco_conv_bench_ex(int kind, void* x, int N, int H, int W, int Cx, void* wpack, int Cout, int Cin,
+                       void* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
+                       int in16, int out16, const void* addend, double* stats, float* ms_out,
+                       int* ksplit_out, int* grid_out, void* stream);
 /* GroupNorm(32)+optional SiLU on [N,H,W,C]; rows >= n_primal are tangents of row 0.
  * stats: 8*N*64 bytes scratch. */
 int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_primal,

@@ -72,6 +72,8 @@ PROTOTYPES = {
     "loco_conv2d_nhwc_ex": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _P]),
     "loco_conv_bench": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, C.POINTER(_F),
                              C.POINTER(_I), C.POINTER(_I), _P]),
+    "loco_conv_bench_ex": (_I, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, _I, _I, _P, _P,
+                                C.POINTER(_F), C.POINTER(_I), C.POINTER(_I), _P]),
     "loco_groupnorm_silu_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_groupnorm_silu_vjp": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),

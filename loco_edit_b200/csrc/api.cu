@@ -431,6 +431,17 @@ int loco_conv_halo_eligible(int kind, int N, int H, int W, int Cout) {
 int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpack, int Cout, int Cin,
                     float* y, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
                     float* ms_out, int* ksplit_out, int* grid_out, void* stream) {
+  return loco_conv_bench_ex(kind, x, N, H, W, Cx, wpack, Cout, Cin, y, splitk_scratch, splitk_bytes, max_ksplit,
+                            reps, 0, 0, nullptr, nullptr, ms_out, ksplit_out, grid_out, stream);
+}
+
+int loco_conv_bench_ex(int kind, void* x_, int N, int H, int W, int Cx, void* wpack_, int Cout, int Cin,
+                       void* y_, void* splitk_scratch, long long splitk_bytes, int max_ksplit, int reps,
+                       int in16, int out16, const void* addend_, double* stats, float* ms_out,
+                       int* ksplit_out, int* grid_out, void* stream) {
+  float* x = reinterpret_cast<float*>(x_);
+  float* wpack = reinterpret_cast<float*>(wpack_);
+  float* y = reinterpret_cast<float*>(y_);
   ON_DEVICE_OF(x);
   GUARD_BEGIN
   LOCO_TRY(require_device());
@@ -445,10 +456,16 @@ int loco_conv_bench(int kind, float* x, int N, int H, int W, int Cx, float* wpac
     p.Kc = Cout; p.Ngemm = Cin; Cy = Cin;
   }
   p.kind = kind;
-  p.in = make_view(x, N, H, W, Cx);
-  p.out = make_view(y, N, Ho, Wo, Cy);
+  p.in = make_view(x, N, H, W, Cx, in16 ? 1 : 0);
+  p.out = make_view(y, N, Ho, Wo, Cy, out16 ? 1 : 0);
   p.wpack = wpack;
   p.round_out = 1;
+  View addv;
+  if (addend_) {
+    addv = make_view(reinterpret_cast<float*>(const_cast<void*>(addend_)), N, Ho, Wo, Cy, out16 ? 1 : 0);
+    p.addend = &addv;
+  }
+  if (stats) { p.st_ptr[0] = stats; p.st_cg[0] = Cy / 32; p.st_choff[0] = 0; }
   if (splitk_scratch && max_ksplit > 1) {
     p.splitk_counters = reinterpret_cast<int*>(splitk_scratch);
     p.splitk_max_tiles = 2048;   // arrive [0,2048) + done [2048,4096)

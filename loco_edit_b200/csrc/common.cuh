@@ -367,6 +367,51 @@ __device__ __forceinline__ void st4t(float* base, long long elem_off, float4 v) 
 // value as it will be read back from fp16 storage
 __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread
+struct __align__(32) U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ldg256(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ U32x8 ld256(const void* p) {       // coherent (read-modify-write targets)
+  U32x8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// sum 16 per-lane values over the 32 lanes with a halving butterfly (31 shuffles instead of 80):
+// afterwards lane l holds the total of value (l >> 1).
+template <int OFF, int HALF>
+__device__ __forceinline__ void butterfly_step(float (&v)[16], int lane) {
+  const bool hi = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const float send = hi ? v[i] : v[i + HALF];
+    const float keep = hi ? v[i + HALF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+  butterfly_step<16, 8>(v, lane);
+  butterfly_step<8, 4>(v, lane);
+  butterfly_step<4, 2>(v, lane);
+  butterfly_step<2, 1>(v, lane);
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

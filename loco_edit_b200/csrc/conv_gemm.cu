@@ -967,6 +967,167 @@ __device__ __forceinline__ void epilogue_pixel_tile(const ConvGemmParams& p, uin
   }
 }
 
+// ---- fp16 output: epilogue of one work item (two 128-pixel x 128-channel tiles) WITHOUT the
+// shared-memory transpose.  TMEM gives thread t of the warp pixel row 32 q + t with 32 consecutive
+// channels per load; in fp16 those are 64 contiguous bytes of the channels-last tensor, so the thread
+// stores them itself as four 16-byte vectors (24 shared/global memory instructions per chunk
+// become 4).  The residual tile is fetched into REGISTERS (2 tiles x 16 x 16 bytes per thread)
+// before the wait for the accumulator, so its L2 / HBM latency is paid once per item, under the MMAs,
+// instead of once per 32-channel chunk; the per-channel bias of the item is staged in shared memory.
+// Measured on 40 x 256 x 256 x 128 -> 128 with residual + statistics (profiles/r2_conv_decomp_*.txt).
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// Per-CTA GroupNorm-statistics accumulator of the direct epilogue: [target][group][sum, sum sq] in
+// shared memory, flushed with one fp64 atomic per entry when the CTA moves on to another image row
+// (and at kernel end).  All persistent CTAs work on the same image at the same time, so per-chunk
+// global atomics serialise on that image's 64 addresses (+216 us on the 40 x 256^2 layer).
+struct StatAcc {
+  float* acc;      // shared: [2][64]
+  int cur_n;       // image row the accumulator belongs to (-1: empty)
+};
+__device__ __forceinline__ void stat_flush(const ConvGemmParams& p, StatAcc& sa) {
+  // called by all 128 epilogue threads
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int t = (int)threadIdx.x - 128;
+  if (sa.cur_n >= 0) {
+    const int tg = t >> 6, e = t & 63;
+    const float v = sa.acc[t];
+    if (p.st_ptr[tg] != nullptr && v != 0.f) atomicAdd(p.st_ptr[tg] + (long long)sa.cur_n * 64 + e, (double)v);
+  }
+  sa.acc[t] = 0.f;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ void pair_epilogue_direct16(const ConvGemmParams& p, uint32_t tmem_q, float* bias_smem,
+                                                       StatAcc& sa, int q, int lane, int tx, int ty0, int tn,
+                                                       int co0, uint64_t* tfull, uint32_t tphase, bool skip) {
+  // geometry of the pair kernel: TW = 16, TH = 8, TN = 1, block_n = 128
+  const int R = q * 32 + lane;
+  const int x = tx * 16 + (R & 15);
+  const int n = tn;
+  const bool want_stats = p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr;
+  bool valid[2];
+  long long ooff[2], aoff[2];
+#pragma unroll
+  for (int jt = 0; jt < 2; ++jt) {
+    const int y = (ty0 + jt) * 8 + (R >> 4);
+    valid[jt] = n < p.N && y < p.Ho && x < p.Wo;
+    ooff[jt] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
+    aoff[jt] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0;
+  }
+  if (want_stats && n != sa.cur_n) {       // uniform over the CTA's epilogue threads
+    stat_flush(p, sa);
+    sa.cur_n = n;
+  }
+  const bool has_bias = (p.bias != nullptr || p.bias2 != nullptr) && n < p.bias_rows;
+  if (has_bias) {      // 128 epilogue threads stage the item's 128 bias values (uniform branch: n = tn)
+    const int c = (int)threadIdx.x - 128;
+    float b = p.bias ? __ldg(p.bias + co0 + c) : 0.f;
+    if (p.bias2) b += __ldg(p.bias2 + co0 + c);
+    bias_smem[c] = b;
+  }
+  U32x8 A[2][8];       // the residual rows of this thread's two pixels: 2 x 256 bytes, in flight under the MMAs
+  if (p.addend != nullptr) {
+#pragma unroll
+    for (int jt = 0; jt < 2; ++jt) {
+      const __half* ap = reinterpret_cast<const __half*>(p.addend) + aoff[jt];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (valid[jt]) A[jt][j] = ldg256(ap + 16 * j);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) A[jt][j].v[i] = 0u;
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");       // bias visible to the four epilogue warps
+  mbar_wait(tfull, tphase);
+  tc_fence_after();
+  if (!skip) {
+#pragma unroll
+    for (int jt = 0; jt < 2; ++jt) {
+      __half* op = reinterpret_cast<__half*>(p.out) + ooff[jt];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_q + (uint32_t)(jt * 128 + c * 32), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (has_bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_smem + c * 32 + i * 4);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        }
+        if (p.addend != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = unpack_h2(A[jt][c * 2 + j].v[i]);
+              v[16 * j + 2 * i] += a.x; v[16 * j + 2 * i + 1] += a.y;
+            }
+        }
+        if (p.accumulate) {       // VJP fan-in (not used by the forward-only fp16 programs): plain loads
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            U32x8 a;
+            if (valid[jt]) a = ld256(op + c * 32 + 16 * j);
+            else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a.v[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = unpack_h2(a.v[i]);
+              v[16 * j + 2 * i] += f.x; v[16 * j + 2 * i + 1] += f.y;
+            }
+          }
+        }
+        uint32_t h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+        if (valid[jt]) {
+          st256(op + c * 32, h);
+          st256(op + c * 32 + 16, h + 8);
+        }
+        if (want_stats) {
+          // fused GroupNorm statistics of the stored (fp16-rounded) values: per channel quad (sum, sum of
+          // squares) of this pixel, summed over the warp's 32 pixels by a halving butterfly, then added to
+          // the CTA's shared-memory accumulator
+          float sv[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 lo = unpack_h2(h[2 * i]), hi = unpack_h2(h[2 * i + 1]);
+            sv[2 * i] = valid[jt] ? (lo.x + lo.y) + (hi.x + hi.y) : 0.f;
+            sv[2 * i + 1] = valid[jt] ? (lo.x * lo.x + lo.y * lo.y) + (hi.x * hi.x + hi.y * hi.y) : 0.f;
+          }
+          const float tot = butterfly16(sv, lane);
+          if ((lane & 1) == 0) {
+            const int idx = lane >> 1;          // value index = quad * 2 + (0: sum, 1: sum of squares)
+#pragma unroll
+            for (int tg = 0; tg < 2; ++tg) {
+              if (p.st_ptr[tg] == nullptr) continue;
+              const int g = (p.st_choff[tg] + co0 + c * 32 + (idx >> 1) * 4) / p.st_cg[tg];
+              atomicAdd(&sa.acc[tg * 64 + g * 2 + (idx & 1)], tot);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");       // bias_smem may be overwritten by the next item
+}
+
 template <bool IN16, bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -1143,20 +1304,29 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t tempty_leader1 = map_to_cta(&tempty_bar[1], 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    StatAcc sacc;
+    sacc.acc = epi_smem + 128;       // after the 128 staged bias values
+    sacc.cur_n = -1;
+    if (OUT16) sacc.acc[(int)threadIdx.x - 128] = 0.f;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const int um = w % units_m;
       const int co0 = (w / units_m) * 128;
       const int tx = um % p.tiles_x;
       const int ty0 = ((um / p.tiles_x) % half_y) * 2;
       const int tn = um / (p.tiles_x * half_y);
+      if (OUT16) {
+        pair_epilogue_direct16(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2) * 128u, epi_smem, sacc,
+                               q, lane, tx, ty0, tn, co0, &tfull_bar[acc], acc_phase, p.debug == 5 || p.debug == 9);
+      } else {
 #pragma unroll
-      for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile<OUT16>(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+        for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile<OUT16>(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int jt = ((p.debug == 5 || p.debug == 9) ? 2 : 0); jt < 2; ++jt) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
-        epilogue_pixel_tile<OUT16>(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
+        for (int jt = ((p.debug == 5 || p.debug == 9) ? 2 : 0); jt < 2; ++jt) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
+          epilogue_pixel_tile<OUT16>(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1167,6 +1337,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (OUT16 && (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr)) stat_flush(p, sacc);
   }
 
   tc_fence_before();

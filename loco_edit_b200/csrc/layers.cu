@@ -164,26 +164,6 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
 constexpr int kStrip = 4;
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// sum 16 per-lane values over the 32 lanes with a halving butterfly (31 shuffles instead of 80):
-// afterwards lane l holds the total of value (l >> 1).
-template <int OFF, int HALF>
-__device__ __forceinline__ void butterfly_step(float (&v)[16], int lane) {
-  const bool hi = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < HALF; ++i) {
-    const float send = hi ? v[i] : v[i + HALF];
-    const float keep = hi ? v[i + HALF] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-  }
-}
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-  butterfly_step<16, 8>(v, lane);
-  butterfly_step<8, 4>(v, lane);
-  butterfly_step<4, 2>(v, lane);
-  butterfly_step<2, 1>(v, lane);
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 template <bool F16>
 __global__ void __launch_bounds__(256, 2)
 edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __restrict__ bias,
@@ -306,6 +286,9 @@ edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ W
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroups = 32;
 constexpr int kRC = 6;          // batch rows processed per register chunk (1 primal + 5 tangents)
+// fp16 rows are half as wide (8-byte vectors per thread): twice the rows per register chunk keeps
+// the same number of bytes in flight per thread on the forward / JVP kernels
+template <int MODE, bool F16> struct GnRows { static constexpr int value = (F16 && MODE == 0) ? 2 * kRC : kRC; };
 constexpr int kGnMaxRows = 96;  // rows whose per-group scalars fit the shared table
 
 __host__ __device__ inline int gn_block_dim(int C) { return (256 % (C / 4) == 0) ? 256 : 192; }
@@ -345,7 +328,8 @@ __global__ void __launch_bounds__(256)
 gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                 double* __restrict__ stats, int pv) {
-  __shared__ float part[2 * kRC][256];
+  constexpr int RC = GnRows<MODE, F16>::value;
+  __shared__ float part[2 * RC][256];
   const int C = x.C;
   const int cvn = C >> 2;
   const int cg = C / kGroups;
@@ -374,19 +358,19 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     bs[0] = be.x; bs[1] = be.y; bs[2] = be.z; bs[3] = be.w;
   }
 
-  for (int n0 = 0; n0 < N; n0 += kRC) {
-    float s1[kRC], s2[kRC];
+  for (int n0 = 0; n0 < N; n0 += RC) {
+    float s1[RC], s2[RC];
 #pragma unroll
-    for (int r = 0; r < kRC; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
+    for (int r = 0; r < RC; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
       const long long p = ch * pstep + prow;
       if (p >= HW) break;
       const int y = (int)(p / x.W), xx = (int)(p % x.W);
       const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
       const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * 4;
-      float4 v[kRC];
+      float4 v[RC];
 #pragma unroll
-      for (int r = 0; r < kRC; ++r)
+      for (int r = 0; r < RC; ++r)
         v[r] = (n0 + r < N) ? ld4t<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
       float xs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -404,7 +388,7 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
         }
       }
 #pragma unroll
-      for (int r = 0; r < kRC; ++r) {
+      for (int r = 0; r < RC; ++r) {
         const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
         const bool tangent = jvp && (n0 + r >= n_primal);
 #pragma unroll
@@ -422,12 +406,12 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     }
     // fixed-order block reduction (bit-reproducible per block); fp64 atomics across blocks
 #pragma unroll
-    for (int r = 0; r < kRC; ++r) {
+    for (int r = 0; r < RC; ++r) {
       part[2 * r][threadIdx.x] = s1[r];
       part[2 * r + 1][threadIdx.x] = s2[r];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < kRC * kGroups * 2; e += blockDim.x) {
+    for (int e = threadIdx.x; e < RC * kGroups * 2; e += blockDim.x) {
       const int r = e / (kGroups * 2), gw = e % (kGroups * 2);
       if (n0 + r >= N) continue;
       const int gg = gw >> 1, which = gw & 1;
@@ -451,6 +435,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
                 const float* __restrict__ addend, long long add_sN, long long add_sH,
                 long long add_sW, int accumulate, View out, int pv) {
   // per (row, group) scalars: primal rows (mean, rstd); tangent / cotangent rows (m1, m2)
+  constexpr int RC = GnRows<MODE, F16>::value;
   __shared__ float2 tab[kGnMaxRows][kGroups];
   const int C = x.C;
   const int cvn = C >> 2;
@@ -509,10 +494,10 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
         coef[i] = d * gs[i];          // act'(u) * gamma
       }
     }
-    for (int n0 = 0; n0 < N; n0 += kRC) {
-      float4 v[kRC], e[kRC];
+    for (int n0 = 0; n0 < N; n0 += RC) {
+      float4 v[RC], e[RC];
 #pragma unroll
-      for (int r = 0; r < kRC; ++r) {
+      for (int r = 0; r < RC; ++r) {
         v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         e[r] = v[r];
         if (n0 + r < N) {
@@ -525,7 +510,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
         }
       }
 #pragma unroll
-      for (int r = 0; r < kRC; ++r) {
+      for (int r = 0; r < RC; ++r) {
         const int n = n0 + r;
         if (n >= N) break;
         const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
@@ -578,6 +563,54 @@ __global__ void upsample2x_kernel(View in, View out, float scale, int accumulate
     }
     if (round_out && !F16) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     st4t<F16>(out.ptr, o, v);
+  }
+}
+// Non-accumulating fast path: one thread per INPUT vector of 16 bytes (4 fp32 / 8 fp16 channels),
+// one load and four 16-byte stores (the output-indexed kernel above issues one 8/16-byte load per
+// output vector and was latency-bound at 1.4 TB/s on the 128^2 -> 256^2 site).
+template <bool F16>
+__global__ void __launch_bounds__(256)
+upsample2x_fast_kernel(View in, View out, float scale, int round_out) {
+  constexpr int VEC = F16 ? 8 : 4;
+  const int cvn = in.C / VEC;
+  const long long total = (long long)in.N * in.H * in.W * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int x = (int)(r % in.W); r /= in.W;
+    const int y = (int)(r % in.H);
+    const int n = (int)(r / in.H);
+    const long long ioff = n * in.sN + y * in.sH + x * in.sW + cv * VEC;
+    const long long ooff = n * out.sN + (2 * y) * out.sH + (2 * x) * out.sW + cv * VEC;
+    uint4 o;
+    if (F16) {
+      uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(in.ptr) + ioff);
+      if (scale != 1.f) {
+        uint32_t* w = &u.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+          const __half2 h = __floats2half2_rn(f.x * scale, f.y * scale);
+          w[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
+      o = u;
+      __half* op = reinterpret_cast<__half*>(out.ptr) + ooff;
+      *reinterpret_cast<uint4*>(op) = o;
+      *reinterpret_cast<uint4*>(op + out.sW) = o;
+      *reinterpret_cast<uint4*>(op + out.sH) = o;
+      *reinterpret_cast<uint4*>(op + out.sH + out.sW) = o;
+    } else {
+      float4 v = *reinterpret_cast<const float4*>(in.ptr + ioff);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+      float* op = out.ptr + ooff;
+      *reinterpret_cast<float4*>(op) = v;
+      *reinterpret_cast<float4*>(op + out.sW) = v;
+      *reinterpret_cast<float4*>(op + out.sH) = v;
+      *reinterpret_cast<float4*>(op + out.sH + out.sW) = v;
+    }
   }
 }
 template <bool F16>
@@ -831,7 +864,7 @@ int layers_init() {
   LOCO_CARVE((gn_apply_kernel<0, true>)); LOCO_CARVE((gn_apply_kernel<1, true>));
   LOCO_CARVE2(edge_expand_kernel); LOCO_CARVE2(edge_reduce_kernel);
   LOCO_CARVE2(edge_expand128_kernel); LOCO_CARVE2(edge_reduce128_kernel);
-  LOCO_CARVE2(upsample2x_kernel); LOCO_CARVE2(sumpool2x_kernel); LOCO_CARVE2(add_views_kernel);
+  LOCO_CARVE2(upsample2x_kernel); LOCO_CARVE2(upsample2x_fast_kernel); LOCO_CARVE2(sumpool2x_kernel); LOCO_CARVE2(add_views_kernel);
   LOCO_CARVE(temb_kernel); LOCO_CARVE(temb_project_kernel); LOCO_CARVE(set_scalar_kernel);
   LOCO_CARVE(scale_shift_affine_kernel);
 #undef LOCO_CARVE2
@@ -936,6 +969,16 @@ int upsample2x(View in, View out, float scale, int accumulate, int round_out, cu
                "upsample2x: shape mismatch");
   const long long total = (long long)out.N * out.H * out.W * (out.C / 4);
   LOCO_TRY(same_type(in, out, "upsample2x"));
+  const int vec = in.half ? 8 : 4;
+  if (!accumulate && in.C % vec == 0 && in.sW % vec == 0 && in.sH % vec == 0 && in.sN % vec == 0 &&
+      out.sW % vec == 0 && out.sH % vec == 0 && out.sN % vec == 0 && (((uintptr_t)in.ptr | (uintptr_t)out.ptr) & 15) == 0) {
+    const long long tin = (long long)in.N * in.H * in.W * (in.C / vec);
+    const int grid = grid_for(tin, 256, num_sms() * 8);
+    if (in.half) upsample2x_fast_kernel<true><<<grid, 256, 0, s>>>(in, out, scale, round_out);
+    else upsample2x_fast_kernel<false><<<grid, 256, 0, s>>>(in, out, scale, round_out);
+    count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (in.half) upsample2x_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   else upsample2x_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, out, scale, accumulate, round_out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
