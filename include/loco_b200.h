@@ -93,6 +93,14 @@ int loco_plan_info(const loco_plan_t* p, double* fwd_flops, double* vjp_flops, i
  * x, eps: [n_primal + n_tangent, 3, R, R]; tangent rows hold dx on input and d eps on output,
  * i.e. the forward-mode product torch.func.jacfwd computes at src/modules/edit.py:2455. */
 int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void* stream);
+/* Conditional U-Net eps(x, t, c): `cond` [4*ch] (device; NULL = unconditional) is added to the
+ * timestep embedding of every following loco_unet_forward of this plan -- the class / pooled-text
+ * conditioning of guided-diffusion style U-Nets.  It is the stand-in for the text-conditioned U-Nets
+ * of the T-LOCO twins (`self.unet(x, t, encoder_hidden_states=...)`, src/modules/edit.py:655-658,
+ * 1319-1322): classifier-free guidance evaluates the same network under 2-3 conditionings and
+ * combines eps linearly, so its Jacobian products are the same linear combination of this plan's
+ * JVP / VJP passes. */
+int loco_plan_set_condition(loco_plan_t* p, const float* cond, void* stream);
 /* gx[j] = (d eps / d x)^T g_eps[j] at the primal point of the last loco_unet_forward: replaces
  * the k backward passes of torch.autograd.functional.jacobian (src/modules/edit.py:2479). */
 int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream);

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "loco_plan_bind": (_I, [_P, _P]),
     "loco_plan_info": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(_I)]),
     "loco_unet_forward": (_I, [_P, _P, _F, _P, _P]),
+    "loco_plan_set_condition": (_I, [_P, _P, _P]),
     "loco_unet_vjp": (_I, [_P, _P, _P, _P]),
     "loco_pullback_scratch_bytes": (_LL, [_I, _LL]),
     "loco_pullback_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),

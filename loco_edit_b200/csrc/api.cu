@@ -160,6 +160,12 @@ int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void*
   return p->p->forward(x, t, eps, ST(stream));
   GUARD_END
 }
+int loco_plan_set_condition(loco_plan_t* p, const float* cond, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p, "loco_plan_set_condition: null plan");
+  return p->p->set_condition(cond, ST(stream));
+  GUARD_END
+}
 int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream) {
   GUARD_BEGIN
   LOCO_REQUIRE(p && g_eps && gx, "loco_unet_vjp: null argument");

@@ -982,154 +982,206 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
-// Per-CTA GroupNorm-statistics accumulator of the direct epilogue: [target][group][sum, sum sq] in
-// shared memory, flushed with one fp64 atomic per entry when the CTA moves on to another image row
-// (and at kernel end).  All persistent CTAs work on the same image at the same time, so per-chunk
-// global atomics serialise on that image's 64 addresses (+216 us on the 40 x 256^2 layer).
+// Per-warpgroup GroupNorm-statistics accumulator of the direct epilogue: [target][group][sum, sum sq]
+// in shared memory, flushed with one fp64 atomic per entry when the warpgroup moves on to another
+// image row (and at kernel end).  All persistent CTAs work on the same image at the same time, so
+// per-chunk global atomics serialise on that image's 64 addresses (+216 us on the 40 x 256^2 layer).
+__device__ __forceinline__ void wg_bar(int bar) {       // named barrier 1 or 2, 128 threads
+  if (bar == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 struct StatAcc {
   float* acc;      // shared: [2][64]
   int cur_n;       // image row the accumulator belongs to (-1: empty)
 };
-__device__ __forceinline__ void stat_flush(const ConvGemmParams& p, StatAcc& sa) {
-  // called by all 128 epilogue threads
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  const int t = (int)threadIdx.x - 128;
+// called by the 128 threads of one epilogue warpgroup (named barrier `bar`, thread index t in it)
+__device__ __forceinline__ void stat_flush(const ConvGemmParams& p, StatAcc& sa, int bar, int t) {
+  wg_bar(bar);
   if (sa.cur_n >= 0) {
     const int tg = t >> 6, e = t & 63;
     const float v = sa.acc[t];
     if (p.st_ptr[tg] != nullptr && v != 0.f) atomicAdd(p.st_ptr[tg] + (long long)sa.cur_n * 64 + e, (double)v);
   }
   sa.acc[t] = 0.f;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  wg_bar(bar);
 }
 
-__device__ __forceinline__ void pair_epilogue_direct16(const ConvGemmParams& p, uint32_t tmem_q, float* bias_smem,
-                                                       StatAcc& sa, int q, int lane, int tx, int ty0, int tn,
-                                                       int co0, uint64_t* tfull, uint32_t tphase, bool skip) {
+// ---- "direct" epilogue of ONE 128-pixel x 128-channel tile of the pair kernel, run by one warpgroup.
+// TMEM gives thread t of warp q pixel row 32 q + t with 32 consecutive channels per load: 128 (fp32) or
+// 64 (fp16) contiguous bytes of the channels-last tensor, which the thread stores itself with 256-bit
+// stores -- no shared-memory transpose (24 shared/global memory instructions per chunk become 2-4).
+//   * the residual tile is fetched into registers BEFORE the wait for the accumulator (fp16: the
+//     whole 256-byte pixel row; fp32: the first chunk, then one chunk ahead), so its latency sits
+//     under the MMAs; the next item's residual rows are L2-prefetched an item ahead;
+//   * the per-channel bias of the item is staged in shared memory once per item;
+//   * statistics go to the warpgroup's shared-memory accumulator.
+template <bool OUT16>
+__device__ __forceinline__ void tile_epilogue_direct(const ConvGemmParams& p, uint32_t tmem_tile_q, float* bias_smem,
+                                                     StatAcc& sa, int bar, int q, int lane, int tx, int ty, int tn,
+                                                     int co0, uint64_t* tfull, uint32_t tphase, bool skip,
+                                                     long long next_aoff) {
   // geometry of the pair kernel: TW = 16, TH = 8, TN = 1, block_n = 128
-  const int R = q * 32 + lane;
-  const int x = tx * 16 + (R & 15);
+  constexpr int ESZ = OUT16 ? 2 : 4;
+  constexpr int CPV = 32 / ESZ;                  // channels per 256-bit vector: 16 (fp16) / 8 (fp32)
+  constexpr int VPC = 32 / CPV;                  // vectors per 32-channel chunk: 2 / 4
+  const int t = q * 32 + lane;                   // thread index inside the warpgroup = pixel row of the tile
+  const int x = tx * 16 + (t & 15);
+  const int y = ty * 8 + (t >> 4);
   const int n = tn;
   const bool want_stats = p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr;
-  bool valid[2];
-  long long ooff[2], aoff[2];
-#pragma unroll
-  for (int jt = 0; jt < 2; ++jt) {
-    const int y = (ty0 + jt) * 8 + (R >> 4);
-    valid[jt] = n < p.N && y < p.Ho && x < p.Wo;
-    ooff[jt] = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
-    aoff[jt] = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0;
-  }
-  if (want_stats && n != sa.cur_n) {       // uniform over the CTA's epilogue threads
-    stat_flush(p, sa);
+  const bool valid = n < p.N && y < p.Ho && x < p.Wo;
+  const long long ooff = (long long)n * p.out_sN + (long long)y * p.out_sH + (long long)x * p.out_sW + co0;
+  const long long aoff = (long long)n * p.add_sN + (long long)y * p.add_sH + (long long)x * p.add_sW + co0;
+  char* op = reinterpret_cast<char*>(p.out) + ooff * ESZ;
+  const char* ap = reinterpret_cast<const char*>(p.addend) + aoff * ESZ;
+  if (want_stats && n != sa.cur_n) {       // uniform over the warpgroup
+    stat_flush(p, sa, bar, t);
     sa.cur_n = n;
   }
   const bool has_bias = (p.bias != nullptr || p.bias2 != nullptr) && n < p.bias_rows;
-  if (has_bias) {      // 128 epilogue threads stage the item's 128 bias values (uniform branch: n = tn)
-    const int c = (int)threadIdx.x - 128;
-    float b = p.bias ? __ldg(p.bias + co0 + c) : 0.f;
-    if (p.bias2) b += __ldg(p.bias2 + co0 + c);
-    bias_smem[c] = b;
+  if (has_bias) {      // the warpgroup's 128 threads stage the item's 128 bias values (uniform branch)
+    float b = p.bias ? __ldg(p.bias + co0 + t) : 0.f;
+    if (p.bias2) b += __ldg(p.bias2 + co0 + t);
+    bias_smem[t] = b;
   }
-  U32x8 A[2][8];       // the residual rows of this thread's two pixels: 2 x 256 bytes, in flight under the MMAs
+  constexpr int NA = OUT16 ? 8 : 4;            // residual vectors kept in registers
+  U32x8 A[NA];
   if (p.addend != nullptr) {
 #pragma unroll
-    for (int jt = 0; jt < 2; ++jt) {
-      const __half* ap = reinterpret_cast<const __half*>(p.addend) + aoff[jt];
+    for (int j = 0; j < NA; ++j) {
+      if (valid) A[j] = ldg256(ap + 32 * j);
+      else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (valid[jt]) A[jt][j] = ldg256(ap + 16 * j);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) A[jt][j].v[i] = 0u;
-        }
+        for (int i = 0; i < 8; ++i) A[j].v[i] = 0u;
       }
     }
+    // residual row of the pixel this thread handles in the CTA's NEXT item: into L2 now
+    if (next_aoff >= 0) {
+      const char* np = reinterpret_cast<const char*>(p.addend) + next_aoff * ESZ;
+#pragma unroll
+      for (int j = 0; j < 128 * ESZ / 128; ++j) prefetch_l2(reinterpret_cast<const float*>(np + 128 * j));
+    }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");       // bias visible to the four epilogue warps
+  wg_bar(bar);       // bias visible to the warpgroup
   mbar_wait(tfull, tphase);
   tc_fence_after();
   if (!skip) {
 #pragma unroll
-    for (int jt = 0; jt < 2; ++jt) {
-      __half* op = reinterpret_cast<__half*>(p.out) + ooff[jt];
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_tile_q + (uint32_t)(c * 32), r);
+      U32x8 An[4];                       // fp32: the next chunk's residual, one chunk ahead
+      if (!OUT16 && p.addend != nullptr && c < 3) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_q + (uint32_t)(jt * 128 + c * 32), r);
-        tmem_ld_wait();
-        float v[32];
+        for (int j = 0; j < 4; ++j) {
+          if (valid) An[j] = ldg256(ap + 128 * (c + 1) + 32 * j);
+          else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (has_bias) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_smem + c * 32 + i * 4);
-            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int i = 0; i < 8; ++i) An[j].v[i] = 0u;
           }
         }
-        if (p.addend != nullptr) {
+      }
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (has_bias) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_smem + c * 32 + i * 4);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if (p.addend != nullptr) {
+        if (OUT16) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float2 a = unpack_h2(A[jt][c * 2 + j].v[i]);
-              v[16 * j + 2 * i] += a.x; v[16 * j + 2 * i + 1] += a.y;
-            }
-        }
-        if (p.accumulate) {       // VJP fan-in (not used by the forward-only fp16 programs): plain loads
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            U32x8 a;
-            if (valid[jt]) a = ld256(op + c * 32 + 16 * j);
-            else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a.v[i] = 0u;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 f = unpack_h2(a.v[i]);
+              const float2 f = unpack_h2(A[c * 2 + j].v[i]);
               v[16 * j + 2 * i] += f.x; v[16 * j + 2 * i + 1] += f.y;
             }
-          }
-        }
-        uint32_t h[16];
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = pack_h2(v[2 * i], v[2 * i + 1]);
-        if (valid[jt]) {
-          st256(op + c * 32, h);
-          st256(op + c * 32 + 16, h + 8);
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] += __uint_as_float(A[j].v[i]);
         }
-        if (want_stats) {
-          // fused GroupNorm statistics of the stored (fp16-rounded) values: per channel quad (sum, sum of
-          // squares) of this pixel, summed over the warp's 32 pixels by a halving butterfly, then added to
-          // the CTA's shared-memory accumulator
-          float sv[16];
+      }
+      if (p.accumulate) {       // VJP fan-in: out += result
+#pragma unroll
+        for (int j = 0; j < VPC; ++j) {
+          U32x8 a;
+          if (valid) a = ld256(op + (c * 32 + CPV * j) * ESZ);
+          else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a.v[i] = 0u;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float2 lo = unpack_h2(h[2 * i]), hi = unpack_h2(h[2 * i + 1]);
-            sv[2 * i] = valid[jt] ? (lo.x + lo.y) + (hi.x + hi.y) : 0.f;
-            sv[2 * i + 1] = valid[jt] ? (lo.x * lo.x + lo.y * lo.y) + (hi.x * hi.x + hi.y * hi.y) : 0.f;
-          }
-          const float tot = butterfly16(sv, lane);
-          if ((lane & 1) == 0) {
-            const int idx = lane >> 1;          // value index = quad * 2 + (0: sum, 1: sum of squares)
-#pragma unroll
-            for (int tg = 0; tg < 2; ++tg) {
-              if (p.st_ptr[tg] == nullptr) continue;
-              const int g = (p.st_choff[tg] + co0 + c * 32 + (idx >> 1) * 4) / p.st_cg[tg];
-              atomicAdd(&sa.acc[tg * 64 + g * 2 + (idx & 1)], tot);
+            if (OUT16) {
+              const float2 f = unpack_h2(a.v[i]);
+              v[16 * j + 2 * i] += f.x; v[16 * j + 2 * i + 1] += f.y;
+            } else {
+              v[8 * j + i] += __uint_as_float(a.v[i]);
             }
           }
         }
       }
+      if (OUT16) {
+        uint32_t h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+        if (valid) {
+          st256(op + c * 64, h);
+          st256(op + c * 64 + 32, h + 8);
+        }
+      } else {
+        if (p.round_out) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+        }
+        if (valid) {
+          uint32_t* w = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st256(op + c * 128 + 32 * j, w + 8 * j);
+        }
+      }
+      if (want_stats) {
+        // fused GroupNorm statistics: per channel quad (sum, sum of squares) of this pixel, summed over the
+        // warp's 32 pixels by a halving butterfly, then added to the warpgroup's shared accumulator.  fp16
+        // storage: taken from the fp32 values before the final rounding (the difference averages out over
+        // the >= 4096 elements of a group; the tf32 path rounds first, as before).
+        float sv[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = v[4 * i], a1 = v[4 * i + 1], a2 = v[4 * i + 2], a3 = v[4 * i + 3];
+          sv[2 * i] = valid ? (a0 + a1) + (a2 + a3) : 0.f;
+          sv[2 * i + 1] = valid ? (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3) : 0.f;
+        }
+        const float tot = butterfly16(sv, lane);
+        if ((lane & 1) == 0) {
+          const int idx = lane >> 1;          // value index = quad * 2 + (0: sum, 1: sum of squares)
+#pragma unroll
+          for (int tg = 0; tg < 2; ++tg) {
+            if (p.st_ptr[tg] == nullptr) continue;
+            const int g = (p.st_choff[tg] + co0 + c * 32 + (idx >> 1) * 4) / p.st_cg[tg];
+            atomicAdd(&sa.acc[tg * 64 + g * 2 + (idx & 1)], tot);
+          }
+        }
+      }
+      if (!OUT16 && c < 3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) A[j] = An[j];
+      }
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");       // bias_smem may be overwritten by the next item
+  wg_bar(bar);       // bias_smem may be overwritten by the next item
 }
 
+constexpr int kPairThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7 and 8-11: epilogue
 template <bool IN16, bool OUT16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -1160,7 +1212,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int i = 0; i < kPairStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);      // the four epilogue warps of each CTA of the pair
+      mbar_init(&tempty_bar[i], 16);     // the eight epilogue warps of each CTA of the pair
     }
     fence_mbar_init();
   }
@@ -1173,11 +1225,15 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   cluster_sync_all();                    // the peer's barriers and TMEM exist from here on
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // register re-allocation between the warpgroups (launch: 65536 / 384 = 168 per thread): the
+  // producer / MMA warpgroup needs few, the two epilogue warpgroups keep a residual tile in registers
 
   const int half_y = p.tiles_y >> 1;
   const int units_m = p.tiles_x * half_y * p.tiles_n;        // 16 x 16 blocks per output-channel tile
   const int total_items = units_m * p.tiles_co;              // even; units_m even (host checks)
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
     if (elect_one()) {
@@ -1296,38 +1352,43 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------ epilogue (both CTAs, own TMEM) ------------------------------
+    // two warpgroups: warps 4-7 drain tile 0 (rows 0-7 of the 16 x 16 block), warps 8-11 tile 1
     const int q = warp & 3;
-    float* tbuf = epi_smem + q * (32 * kEpiPitch);
+    const int jt = (warp - 4) >> 2;
+    const int bar = 1 + jt;                              // named barrier of this warpgroup
+    float* wg_smem = epi_smem + jt * 256;                // [0,128): bias, [128,256): statistics
     const uint32_t tempty_leader0 = map_to_cta(&tempty_bar[0], 0);
     const uint32_t tempty_leader1 = map_to_cta(&tempty_bar[1], 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     StatAcc sacc;
-    sacc.acc = epi_smem + 128;       // after the 128 staged bias values
+    sacc.acc = wg_smem + 128;
     sacc.cur_n = -1;
-    if (OUT16) sacc.acc[(int)threadIdx.x - 128] = 0.f;
+    sacc.acc[q * 32 + lane] = 0.f;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const int um = w % units_m;
       const int co0 = (w / units_m) * 128;
       const int tx = um % p.tiles_x;
       const int ty0 = ((um / p.tiles_x) % half_y) * 2;
       const int tn = um / (p.tiles_x * half_y);
-      if (OUT16) {
-        pair_epilogue_direct16(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2) * 128u, epi_smem, sacc,
-                               q, lane, tx, ty0, tn, co0, &tfull_bar[acc], acc_phase, p.debug == 5 || p.debug == 9);
-      } else {
-#pragma unroll
-        for (int jt = 0; jt < 2; ++jt) prefetch_epilogue_tile<OUT16>(p, tx, ty0 + jt, tn, co0, (int)threadIdx.x - 128);
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int jt = ((p.debug == 5 || p.debug == 9) ? 2 : 0); jt < 2; ++jt) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u;
-          epilogue_pixel_tile<OUT16>(p, taddr, tbuf, q, lane, tx, ty0 + jt, tn, co0);
-        }
+      long long next_aoff = -1;
+      if (p.addend != nullptr && w + (int)gridDim.x < total_items) {
+        const int w2 = w + (int)gridDim.x;
+        const int um2 = w2 % units_m;
+        const int t = q * 32 + lane;
+        const int x2 = (um2 % p.tiles_x) * 16 + (t & 15);
+        const int y2 = (((um2 / p.tiles_x) % half_y) * 2 + jt) * 8 + (t >> 4);
+        const int n2 = um2 / (p.tiles_x * half_y);
+        if (n2 < p.N && y2 < p.Ho && x2 < p.Wo)
+          next_aoff = (long long)n2 * p.add_sN + (long long)y2 * p.add_sH + (long long)x2 * p.add_sW + (w2 / units_m) * 128;
       }
+      tile_epilogue_direct<OUT16>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 + jt) * 128u, wg_smem,
+                                  sacc, bar, q, lane, tx, ty0 + jt, tn, co0, &tfull_bar[acc], acc_phase,
+                                  p.debug == 5 || p.debug == 9, next_aoff);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1337,7 +1398,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (OUT16 && (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr)) stat_flush(p, sacc);
+    if (p.st_ptr[0] != nullptr || p.st_ptr[1] != nullptr) stat_flush(p, sacc, bar, q * 32 + lane);
   }
 
   tc_fence_before();
@@ -1729,7 +1790,7 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
       LOCO_REQUIRE(k != nullptr, "conv: variant %d has no fp16 instantiation", L.p[i].nt);
       if (L.p[i].nt == 5) {
         // the CTA-pair kernel carries __cluster_dims__(2,1,1): plain launch, even grid
-        k<<<L.grid[i], kThreads, smem, stream>>>(L.p[i]);
+        k<<<L.grid[i], kPairThreads, smem, stream>>>(L.p[i]);
       } else {
         k<<<L.grid[i], kThreads, smem, stream>>>(L.p[i]);
       }

@@ -64,8 +64,9 @@ int add_views(View in, View out, int accumulate, cudaStream_t s);
 // ResnetBlock's temb_proj Linear(temb_ch -> Cout) evaluated into one packed vector.
 // t is read from device memory so a captured CUDA graph can be replayed for any timestep.
 // style 0 = DDPM sinusoid ([sin, cos], divisor half-1), 1 = guided-diffusion ([cos, sin], half).
+// cond: optional [4ch] conditioning embedding (device) added to the timestep embedding.
 int temb_forward(const float* t_dev, int ch, const float* w0, const float* b0, const float* w1,
-                 const float* b1, float* scratch /*2*4ch*/, int style, cudaStream_t s);
+                 const float* b1, float* scratch /*2*4ch*/, int style, const float* cond, cudaStream_t s);
 // P2 scale-shift norm folded into the GroupNorm affine, all sites of a program in one launch:
 // out[out_off + c] = gamma[c] (1 + scale[c]), out[out_off + C + c] = beta[c] (1 + scale[c]) + shift[c]
 // with (scale | shift) = tproj[tproj_off .. tproj_off + 2C).

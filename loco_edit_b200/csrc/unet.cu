@@ -465,6 +465,7 @@ struct Plan::Impl {
   // programs can be captured once into CUDA graphs and replayed for any caller pointers / t)
   const float* cur_x = nullptr;
   float* t_dev = nullptr;
+  float* cond_dev = nullptr;      // [4 ch] conditioning embedding added to the timestep embedding (zeros: none)
   float* cur_eps = nullptr;
   const float* cur_geps = nullptr;
   float* cur_gx = nullptr;
@@ -689,6 +690,11 @@ int Plan::build(float* workspace) {
     I.gin_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
     I.gout_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
     I.t_dev = alloc_act(64);
+    I.cond_dev = alloc_act(4 * (size_t)A.ch);
+    if (!dry) {
+      const cudaError_t ce = cudaMemset(I.cond_dev, 0, sizeof(float) * 4 * (size_t)A.ch);
+      LOCO_REQUIRE(ce == cudaSuccess, "plan: cudaMemset(condition) failed: %s", cudaGetErrorString(ce));
+    }
     if (I.fwd_graph) { cudaGraphExecDestroy(I.fwd_graph); I.fwd_graph = nullptr; }
     if (I.bwd_graph) { cudaGraphExecDestroy(I.bwd_graph); I.bwd_graph = nullptr; }
   }
@@ -1001,7 +1007,7 @@ int Plan::build(float* workspace) {
     }
     I.fwd[temb_op_index] = [=](cudaStream_t s) {
       LOCO_TRY(temb_forward(Ip->t_dev, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
-                            Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, Mp->arch.kind, s));
+                            Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, Mp->arch.kind, Ip->cond_dev, s));
       LOCO_TRY(temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
                             Mp->tproj_rows, tproj, s));
       return scale_shift_affine(aff_dev, n_aff, Mp->arena, tproj, aff_buf, s);
@@ -1098,6 +1104,15 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   I.cur_x = I.in_buf; I.cur_eps = I.out_buf;
   LOCO_TRY(run_program(I.fwd, I.fstats, I.fstat_bytes, &I.fwd_graph, &I.fwd_graph_launches, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, bytes, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int Plan::set_condition(const float* cond, cudaStream_t s) {
+  LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
+  DeviceGuard guard(device);
+  const size_t bytes = sizeof(float) * 4 * (size_t)model->arch.ch;
+  if (cond) LOCO_CHECK_CUDA(cudaMemcpyAsync(impl->cond_dev, cond, bytes, cudaMemcpyDeviceToDevice, s));
+  else LOCO_CHECK_CUDA(cudaMemsetAsync(impl->cond_dev, 0, bytes, s));
   return 0;
 }
 

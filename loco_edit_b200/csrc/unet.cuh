@@ -119,6 +119,9 @@ class Plan {
   int build(float* workspace);   // workspace == nullptr: size query only
   // x: [NP+NT, 3, R, R] (row 0.. primal samples, then tangents); eps: same shape.
   int forward(const float* x_nchw, float t, float* eps_nchw, cudaStream_t s);
+  // conditioning embedding [4 ch] (device, or null = none) added to the timestep embedding of every
+  // following forward(); x -> eps(x, t, c) stays a function of x only, so JVP / VJP are unchanged
+  int set_condition(const float* cond, cudaStream_t s);
   // g_eps: [NC, 3, R, R] cotangents of eps; gx: [NC, 3, R, R] = J_eps^T g_eps.
   int vjp(const float* g_eps_nchw, float* gx_nchw, cudaStream_t s);
 

@@ -79,6 +79,15 @@ class Plan:
               "loco_unet_forward")
         return out
 
+    def set_condition(self, cond):
+        """Conditioning embedding [4*ch] (device tensor, or None) added to the timestep embedding of the
+        following forward() calls of this plan."""
+        if cond is not None:
+            assert cond.is_cuda and cond.dtype == torch.float32 and cond.is_contiguous()
+            assert cond.numel() == 4 * self.unet.arch["ch"], (cond.numel(), self.unet.arch["ch"])
+        check(self.lib.loco_plan_set_condition(self.handle, ptr(cond), stream_ptr(self.unet.device)),
+              "loco_plan_set_condition")
+
     def vjp(self, g_eps, out=None):
         k = self.shape[2]
         R = self.unet.arch["resolution"]
@@ -147,12 +156,14 @@ class B200UNet:
                                                     stream_ptr(self.device)), "loco_unet_load_param(%s)" % name)
             torch.cuda.current_stream(self.device).synchronize()
 
-    def plan(self, n_primal, n_tangent=0, n_cot=0, half=None):
+    def plan(self, n_primal, n_tangent=0, n_cot=0, half=None, slot=0):
         """`half` (fp16 activations + tcgen05 kind::f16) defaults to `self.fwd_half` for the
         Jacobian-free programs and to False for the JVP / VJP programs."""
         if half is None:
             half = self.fwd_half and n_tangent == 0 and n_cot == 0
-        key = (n_primal, n_tangent, n_cot, bool(half))
+        # `slot` separates otherwise identical plans that must keep their own saved activations (one per
+        # conditioning of a classifier-free-guidance Jacobian product)
+        key = (n_primal, n_tangent, n_cot, bool(half), int(slot))
         if key in self._plans:
             self._plans.move_to_end(key)
             return self._plans[key]
