@@ -67,7 +67,7 @@ constexpr int kEdgeIters = 16;
 template <bool F16>
 __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* __restrict__ We,
                                    const float* __restrict__ bias, int bias_rows, View out,
-                                   int flip, int round_out) {
+                                   int flip, int round_out, const float* __restrict__ scale_dev, int scale_from) {
   extern __shared__ float sw[];   // [27][C]
   const int C = out.C, H = out.H, W = out.W;
   for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = We[i];
@@ -101,6 +101,10 @@ __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* _
       }
     }
   }
+  if (scale_dev != nullptr && n >= scale_from) {
+    const float sc = scale_dev[0];
+    acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+  }
   if (round_out) {
     acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y);
     acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
@@ -113,7 +117,8 @@ __global__ void edge_expand_kernel(const float* __restrict__ in3, const float* _
 template <bool F16>
 __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
                                    const float* __restrict__ bias, int bias_rows,
-                                   float* __restrict__ out3, int flip) {
+                                   float* __restrict__ out3, int flip, const float* __restrict__ scale_dev,
+                                   int scale_from) {
   extern __shared__ float sw[];   // [27][C]
   const int C = in.C, H = in.H, W = in.W;
   for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = Wr[i];
@@ -148,10 +153,11 @@ __global__ void edge_reduce_kernel(View in, const float* __restrict__ Wr,
   a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
   if (lane == 0) {
     const bool ub = bias && n < bias_rows;
+    const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[1] : 1.f;
     float* dst = out3 + (long long)n * 3 * H * W + (long long)y * W + x;
-    dst[0] = a0 + (ub ? bias[0] : 0.f);
-    dst[(long long)H * W] = a1 + (ub ? bias[1] : 0.f);
-    dst[2LL * H * W] = a2 + (ub ? bias[2] : 0.f);
+    dst[0] = a0 * sc + (ub ? bias[0] : 0.f);
+    dst[(long long)H * W] = a1 * sc + (ub ? bias[1] : 0.f);
+    dst[2LL * H * W] = a2 * sc + (ub ? bias[2] : 0.f);
   }
   }
 }
@@ -167,7 +173,8 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 template <bool F16>
 __global__ void __launch_bounds__(256, 2)
 edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __restrict__ bias,
-                      int bias_rows, float* __restrict__ out3, int flip) {
+                      int bias_rows, float* __restrict__ out3, int flip, const float* __restrict__ scale_dev,
+                      int scale_from) {
   __shared__ float4 sw[27 * 32];   // [tap][j][channel quad]
   const int H = in.H, W = in.W;
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(Wr)[i];
@@ -217,7 +224,8 @@ edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __rest
     if ((lane & 1) == 0 && idx < kStrip * 3) {
       const int q = idx / 3, j = idx % 3;
       const bool ub = bias && n < bias_rows;
-      out3[((long long)n * 3 + j) * H * W + (long long)y * W + x0 + q] = tot + (ub ? bias[j] : 0.f);
+      const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[1] : 1.f;
+      out3[((long long)n * 3 + j) * H * W + (long long)y * W + x0 + q] = tot * sc + (ub ? bias[j] : 0.f);
     }
   }
 }
@@ -226,7 +234,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ We,
                       const float* __restrict__ bias, int bias_rows, View out, int flip,
-                      int round_out) {
+                      int round_out, const float* __restrict__ scale_dev, int scale_from) {
   __shared__ float4 sw[27 * 32];   // [tap][j][channel quad]
   const int H = out.H, W = out.W;
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(We)[i];
@@ -273,8 +281,11 @@ edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ W
         }
       }
 #pragma unroll
+    const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[0] : 1.f;
+#pragma unroll
     for (int q = 0; q < kStrip; ++q) {
       float4 o = acc[q];
+      o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
       if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       st4t<F16>(out.ptr, (long long)n * out.sN + (long long)y * out.sH + (long long)(x0 + q) * out.sW + lane * 4, o);
     }
@@ -805,6 +816,27 @@ __global__ void temb_project_kernel(const float* __restrict__ temb_act, int temb
   if (lane == 0) out[o] = acc + b[o];
 }
 
+// Power-of-two scale that brings max |v| to about `target`: the fp16 JVP / VJP programs carry their
+// tangent / cotangent rows scaled by it (both passes are linear in those rows, a power of two is exact)
+// so that the rows sit in the middle of fp16's exponent range whatever their natural magnitude
+// (tangents of an orthonormal basis of R^196608 are ~2e-3, with activations down to 1e-6).
+__global__ void amax_kernel(const float* __restrict__ v, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));     // non-negative floats order like uints
+}
+__global__ void pow2_scale_kernel(const unsigned* __restrict__ amax_bits, float target, float* __restrict__ scale2) {
+  const float a = __uint_as_float(*amax_bits);
+  float sc = 1.f;
+  if (a > 0.f && isfinite(a)) sc = exp2f(floorf(log2f(target / a)));
+  sc = fminf(fmaxf(sc, 1.0f / 16777216.f), 16777216.f);
+  scale2[0] = sc;
+  scale2[1] = 1.0f / sc;
+}
+
 inline int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -861,14 +893,23 @@ int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t 
   return 0;
 }
 
+int pow2_scale(const float* v, long long n, float target, float* scale2, unsigned* tmp, cudaStream_t s) {
+  LOCO_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(unsigned), s));
+  amax_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(v, n, tmp);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  pow2_scale_kernel<<<1, 1, 0, s>>>(tmp, target, scale2);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int edge_conv_expand(const float* in3, const float* We, const float* bias, int bias_rows, View out,
-                     int flip, int round_out, cudaStream_t s) {
+                     int flip, int round_out, cudaStream_t s, const float* scale_dev, int scale_from) {
   if (out.C == 128 && out.W % kStrip == 0) {
     const long long nstrips = (long long)out.N * out.H * (out.W / kStrip);
     ProfScope prof(2, 0, s);
     const int grid = grid_for((nstrips + 7) / 8, 1, num_sms() * 4);
-    if (out.half) edge_expand128_kernel<true><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
-    else edge_expand128_kernel<false><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+    if (out.half) edge_expand128_kernel<true><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out, scale_dev, scale_from);
+    else edge_expand128_kernel<false><<<grid, 256, 0, s>>>(in3, We, bias, bias_rows, out, flip, round_out, scale_dev, scale_from);
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -879,19 +920,19 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
   dim3 grid((unsigned)((HW + ppb_all - 1) / ppb_all), out.N);
   const size_t smem = 27 * out.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_expand: C=%d too large", out.C);
-  if (out.half) edge_expand_kernel<true><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
-  else edge_expand_kernel<false><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out);
+  if (out.half) edge_expand_kernel<true><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out, scale_dev, scale_from);
+  else edge_expand_kernel<false><<<grid, 256, smem, s>>>(in3, We, bias, bias_rows, out, flip, round_out, scale_dev, scale_from);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3,
-                     int flip, cudaStream_t s) {
+                     int flip, cudaStream_t s, const float* scale_dev, int scale_from) {
   if (in.C == 128 && in.W % kStrip == 0) {
     const long long nstrips = (long long)in.N * in.H * (in.W / kStrip);
     ProfScope prof(2, 0, s);
     const int grid = grid_for((nstrips + 7) / 8, 1, num_sms() * 4);
-    if (in.half) edge_reduce128_kernel<true><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip);
-    else edge_reduce128_kernel<false><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip);
+    if (in.half) edge_reduce128_kernel<true><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip, scale_dev, scale_from);
+    else edge_reduce128_kernel<false><<<grid, 256, 0, s>>>(in, Wr, bias, bias_rows, out3, flip, scale_dev, scale_from);
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -900,8 +941,8 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
   dim3 grid((unsigned)((HW + 8 * kEdgeIters - 1) / (8 * kEdgeIters)), in.N);
   const size_t smem = 27 * in.C * sizeof(float);
   LOCO_REQUIRE(smem <= 48 * 1024, "edge_conv_reduce: C=%d too large", in.C);
-  if (in.half) edge_reduce_kernel<true><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
-  else edge_reduce_kernel<false><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip);
+  if (in.half) edge_reduce_kernel<true><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip, scale_dev, scale_from);
+  else edge_reduce_kernel<false><<<grid, 256, smem, s>>>(in, Wr, bias, bias_rows, out3, flip, scale_dev, scale_from);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

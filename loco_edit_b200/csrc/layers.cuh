@@ -26,12 +26,18 @@ int pack_conv_edge(const float* w, float* dst, int C, int in_is_3, cudaStream_t 
 // ---- 3-channel edge convolutions (NCHW <-> channels-last boundary of the network) ----
 // out[n,y,x,c] = bias[c]*(n<bias_rows) + sum_{tap,j} We[tap][j][c] * in3[n,j,y+dy,x+dx];
 // flip = 0: (dy,dx) = (r-1,s-1) (conv_in forward); flip = 1: (1-r,1-s) (conv_out data gradient).
+// scale_dev (optional, device float[2] = {s, 1/s}): rows n >= scale_from of the expand output are
+// multiplied by s, of the reduce output by 1/s (power-of-two range scaling of the fp16 tangent /
+// cotangent rows, see pow2_scale).
 int edge_conv_expand(const float* in3_nchw, const float* We, const float* bias, int bias_rows,
-                     View out, int flip, int round_out, cudaStream_t s);
+                     View out, int flip, int round_out, cudaStream_t s, const float* scale_dev = nullptr,
+                     int scale_from = 0);
 // out3[n,j,y,x] = bias[j]*(n<bias_rows) + sum_{tap,c} Wr[tap][j][c] * in[n,y+dy,x+dx,c];
 // flip = 0: conv_out forward; flip = 1: conv_in data gradient.
 int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3_nchw,
-                     int flip, cudaStream_t s);
+                     int flip, cudaStream_t s, const float* scale_dev = nullptr, int scale_from = 0);
+// scale2[0] = 2^floor(log2(target / max|v|)), scale2[1] = its inverse; tmp: one device word of scratch
+int pow2_scale(const float* v, long long n, float target, float* scale2, unsigned* tmp, cudaStream_t s);
 
 // ---- GroupNorm(32 groups) + optional SiLU: forward, JVP and VJP ----
 // stats layout: double [rows][32][2].

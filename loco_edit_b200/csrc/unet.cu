@@ -466,6 +466,11 @@ struct Plan::Impl {
   const float* cur_x = nullptr;
   float* t_dev = nullptr;
   float* cond_dev = nullptr;      // [4 ch] conditioning embedding added to the timestep embedding (zeros: none)
+  // fp16 JVP / VJP programs: power-of-two range scales {s, 1/s} of the tangent rows and of the
+  // cotangent rows (applied by the edge convolutions, removed again at the other end), + scratch
+  float* tscale_dev = nullptr;
+  float* cscale_dev = nullptr;
+  unsigned* scale_tmp = nullptr;
   float* cur_eps = nullptr;
   const float* cur_geps = nullptr;
   float* cur_gx = nullptr;
@@ -691,6 +696,9 @@ int Plan::build(float* workspace) {
     I.gout_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
     I.t_dev = alloc_act(64);
     I.cond_dev = alloc_act(4 * (size_t)A.ch);
+    I.tscale_dev = alloc_act(64);
+    I.cscale_dev = I.tscale_dev + 8;
+    I.scale_tmp = reinterpret_cast<unsigned*>(I.tscale_dev + 16);
     if (!dry) {
       const cudaError_t ce = cudaMemset(I.cond_dev, 0, sizeof(float) * 4 * (size_t)A.ch);
       LOCO_REQUIRE(ce == cudaSuccess, "plan: cudaMemset(condition) failed: %s", cudaGetErrorString(ce));
@@ -877,10 +885,15 @@ int Plan::build(float* workspace) {
     const float* bi = dry ? nullptr : M.w(M.conv_in_b);
     const View hv = h0.v, hg = h0.g;
     const int np = NP;
-    I.fwd.push_back([=](cudaStream_t s) { return edge_conv_expand(Ip->cur_x, wi, bi, np, hv, 0, 1, s); });
+    const bool sc16 = A16 != 0;     // range scaling of the tangent / cotangent rows (fp16 storage only)
+    I.fwd.push_back([=](cudaStream_t s) {
+      return edge_conv_expand(Ip->cur_x, wi, bi, np, hv, 0, 1, s, sc16 ? Ip->tscale_dev : nullptr, np);
+    });
     if (NC > 0) {
       begin_group();
-      push_b([=](cudaStream_t s) { return edge_conv_reduce(hg, wi, nullptr, 0, Ip->cur_gx, 1, s); });
+      push_b([=](cudaStream_t s) {
+        return edge_conv_reduce(hg, wi, nullptr, 0, Ip->cur_gx, 1, s, sc16 ? Ip->cscale_dev : nullptr, 0);
+      });
     }
   }
   // encoder
@@ -983,11 +996,16 @@ int Plan::build(float* workspace) {
     const float* wo = dry ? nullptr : M.w(M.conv_out_w);
     const float* bo = dry ? nullptr : M.w(M.conv_out_b);
     const int np = NP;
-    I.fwd.push_back([=](cudaStream_t s) { return edge_conv_reduce(a, wo, bo, np, Ip->cur_eps, 0, s); });
+    const bool sc16 = A16 != 0;
+    I.fwd.push_back([=](cudaStream_t s) {
+      return edge_conv_reduce(a, wo, bo, np, Ip->cur_eps, 0, s, sc16 ? Ip->tscale_dev : nullptr, np);
+    });
     if (NC > 0) {
       begin_group();
       View ga = Tg(res, res, C);
-      push_b([=](cudaStream_t s) { return edge_conv_expand(Ip->cur_geps, wo, nullptr, 0, ga, 1, 0, s); });
+      push_b([=](cudaStream_t s) {
+        return edge_conv_expand(Ip->cur_geps, wo, nullptr, 0, ga, 1, 0, s, sc16 ? Ip->cscale_dev : nullptr, 0);
+      });
       const int f = writer_flag(hfin.ids);
       gn_bwd(row0(hfin.v), st, ga, M.norm_out, 1, nullptr, f, 1, hfin.g);
     }
@@ -1101,6 +1119,10 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   const size_t bytes = sizeof(float) * (size_t)(NP + NT) * 3 * model->arch.resolution * model->arch.resolution;
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.in_buf, x, bytes, cudaMemcpyDeviceToDevice, s));
   LOCO_TRY(set_scalar(I.t_dev, t, s));
+  if (act16 && NT > 0) {
+    const long long img = 3LL * model->arch.resolution * model->arch.resolution;
+    LOCO_TRY(pow2_scale(I.in_buf + (size_t)NP * img, (long long)NT * img, 64.f, I.tscale_dev, I.scale_tmp, s));
+  }
   I.cur_x = I.in_buf; I.cur_eps = I.out_buf;
   LOCO_TRY(run_program(I.fwd, I.fstats, I.fstat_bytes, &I.fwd_graph, &I.fwd_graph_launches, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, bytes, cudaMemcpyDeviceToDevice, s));
@@ -1123,6 +1145,10 @@ int Plan::vjp(const float* g_eps, float* gx, cudaStream_t s) {
   Impl& I = *impl;
   const size_t bytes = sizeof(float) * (size_t)NC * 3 * model->arch.resolution * model->arch.resolution;
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.gin_buf, g_eps, bytes, cudaMemcpyDeviceToDevice, s));
+  if (act16) {
+    const long long img = 3LL * model->arch.resolution * model->arch.resolution;
+    LOCO_TRY(pow2_scale(I.gin_buf, (long long)NC * img, 64.f, I.cscale_dev, I.scale_tmp, s));
+  }
   I.cur_geps = I.gin_buf; I.cur_gx = I.gout_buf;
   LOCO_TRY(run_program(I.bwd, I.bstats, I.bstat_bytes, &I.bwd_graph, &I.bwd_graph_launches, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(gx, I.gout_buf, bytes, cudaMemcpyDeviceToDevice, s));

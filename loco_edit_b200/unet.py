@@ -129,6 +129,9 @@ class B200UNet:
         # arithmetic of the Jacobian-free programs (DDIM loops): fp16 storage + kind::f16 tensor cores,
         # or fp32 storage + kind::tf32 (LOCO_FWD_FP16=0); the JVP / VJP programs always run tf32
         self.fwd_half = os.environ.get("LOCO_FWD_FP16", "0") != "0"
+        # arithmetic of the Jacobian programs (fused primal + k-tangent JVP, k-cotangent VJP): same switch;
+        # their tangent / cotangent rows are range-scaled by a power of two inside the library
+        self.jac_half = os.environ.get("LOCO_JAC_FP16", "0") != "0"
         self.load_state_dict(state_dict)
 
     def param_shapes(self):
@@ -158,9 +161,9 @@ class B200UNet:
 
     def plan(self, n_primal, n_tangent=0, n_cot=0, half=None, slot=0):
         """`half` (fp16 activations + tcgen05 kind::f16) defaults to `self.fwd_half` for the
-        Jacobian-free programs and to False for the JVP / VJP programs."""
+        Jacobian-free programs and to `self.jac_half` for the JVP / VJP programs."""
         if half is None:
-            half = self.fwd_half and n_tangent == 0 and n_cot == 0
+            half = self.fwd_half if (n_tangent == 0 and n_cot == 0) else self.jac_half
         # `slot` separates otherwise identical plans that must keep their own saved activations (one per
         # conditioning of a classifier-free-guidance Jacobian product)
         key = (n_primal, n_tangent, n_cot, bool(half), int(slot))

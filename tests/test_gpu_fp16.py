@@ -102,6 +102,50 @@ def test_unet_forward_fp16_matches_oracle(dev, name):
     assert torch.isfinite(e16).all() and a < 5e-3
 
 
+@pytest.mark.parametrize("name", ["two_level_attn16", "three_level_attn8"])
+def test_unet_jvp_vjp_fp16_match_oracle(dev, name):
+    """Fused primal + k-tangent JVP and k-cotangent VJP on fp16 plans (rows range-scaled by a power of
+    two inside the library) against the fp32 oracle (torch.func.jvp / autograd), plus the adjoint
+    identity <J v, g> = <v, J^T g> between the two CUDA passes.  Tangents of very different magnitude
+    (1e-3 .. 1e+2) in one batch: the scale is per pass, so each row keeps ~11 bits only if the rows of a
+    pass are of similar size -- the power method's rows are (orthonormal V, U = J V)."""
+    from test_gpu_unet import ARCHS
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict, tiny_arch
+    from oracle import ddpm_ref
+    arch = tiny_arch(**ARCHS[name])
+    sd = random_state_dict(arch, seed=1234, perturb_norm=0.1)
+    net = B200UNet(arch, sd, device=dev)
+    net.jac_half = True
+    ref = ddpm_ref.RefUNet(arch, sd)
+    R = arch["resolution"]
+    g = torch.Generator().manual_seed(1)
+    k = 3
+    x = torch.randn(1, 3, R, R, generator=g)
+    t = torch.tensor(595.3636)
+    for scale in (1.0, 1e-3, 50.0):
+        V = torch.randn(k, 3, R, R, generator=g) * scale
+        G = torch.randn(k, 3, R, R, generator=g) * scale
+        eps, deps = net.jvp(x.to(dev), t, V.to(dev))
+        gx = net.vjp(k, G.to(dev))
+        torch.cuda.synchronize()
+        assert net.plan(1, k, k).half
+        ref_d, ref_g = [], []
+        for j in range(k):
+            _, d = torch.func.jvp(lambda xx: ref(xx, t), (x,), (V[j:j + 1],))
+            ref_d.append(d)
+            xg = x.clone().requires_grad_(True)
+            (ref(xg, t) * G[j:j + 1]).sum().backward()
+            ref_g.append(xg.grad)
+        ej = rel_err(deps.cpu(), torch.cat(ref_d))
+        ev = rel_err(gx.cpu(), torch.cat(ref_g))
+        lhs = (deps.double() * G.to(dev).double()).sum()
+        rhs = (V.to(dev).double() * gx.double()).sum()
+        adj = abs(float(lhs - rhs)) / abs(float(lhs))
+        print(f"{name} scale {scale:g}: JVP rel_err {ej:.3e}, VJP rel_err {ev:.3e}, adjoint gap {adj:.2e}")
+        assert ej < 5e-3 and ev < 5e-3 and adj < 5e-3
+
+
 def test_p2_forward_fp16_matches_oracle(dev):
     from loco_edit_b200.unet import B200UNet
     from loco_edit_b200.weights import random_state_dict, tiny_p2_arch

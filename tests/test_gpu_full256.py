@@ -77,7 +77,8 @@ def _psnr(a, b):
     return 10 * math.log10(4.0 / mse)      # images live in [-1, 1]
 
 
-def test_headline_config_rank5_n12_matches_reference_driver(dev, golden_dir, tmp_path):
+@pytest.mark.parametrize("arith", ["tf32", "fp16"])
+def test_headline_config_rank5_n12_matches_reference_driver(dev, golden_dir, tmp_path, arith):
     """BASELINE config 1 at its own size and depth against the UNMODIFIED reference driver
     (tests/golden/make_golden_n12.py -> driver_full256.pt: `run_edit_null_space_projection`,
     src/modules/edit.py:2216-2366, on the 113.7 M-parameter DDPM-256 U-Net at 256 x 256, rank 5 + null
@@ -106,6 +107,9 @@ def test_headline_config_rank5_n12_matches_reference_driver(dev, golden_dir, tmp
     noises = [torch.randn(5, 3, 256, 256) for _ in range(20)]
 
     net = B200UNet(DDPM256, random_state_dict(DDPM256, seed=g["weights_seed"]), device=dev)
+    # "tf32": fp32 storage + tcgen05 kind::tf32 everywhere; "fp16": fp16 storage + kind::f16 for the DDIM
+    # programs AND the Jacobian programs (tangent / cotangent rows range-scaled inside the library)
+    net.fwd_half = net.jac_half = (arith == "fp16")
     args = types.SimpleNamespace(
         device=dev, dtype=torch.float32, seed=11, model_name="CelebA_HQ_HF", dataset_name="CelebA_HQ_mask",
         image_size=256, for_steps=100, inv_steps=100, edit_t=0.6, performance_boosting_t=0.2,
@@ -114,6 +118,7 @@ def test_headline_config_rank5_n12_matches_reference_driver(dev, golden_dir, tmp
         vT_path="", vT1_path="", verbose=False, save_images=False, noise_schedule=None)
     e = EditUncondDiffusion(args, unet=net)
     assert e.edit_t_idx == 40 and e.performance_boosting_t_idx == 79
+    assert net.plan(1, 5, 5).half == (arith == "fp16")
     t40 = e.scheduler._ts_host[40]
     base = "basis/local_basis-0.6T-select-mask-hair/"
     files = g["files"]
@@ -137,9 +142,9 @@ def test_headline_config_rank5_n12_matches_reference_driver(dev, golden_dir, tmp
             assert srel < 1e-3, msg
         return s, V
 
-    s_m, vm = run(v0a, mask, trace[0], "edit basis")
+    s_m, vm = run(v0a, mask, trace[0], arith + " edit basis")
     ang_m = float(principal_angles_deg(vm, files[base + "vT-modify-pca-rank-5.pt"]).max())
-    s_n, vn = run(v0b, ~mask, trace[1], "null basis")
+    s_n, vn = run(v0b, ~mask, trace[1], arith + " null basis")
     ang_n = float(principal_angles_deg(vn, files[base + "vT-null-5.pt"]).max())
     print(f"after N=12: edit basis {ang_m:.3f} deg, null basis {ang_n:.3f} deg vs the reference's files")
     assert ang_m < 1.0 and ang_n < 1.0
