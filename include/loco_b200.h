@@ -144,6 +144,18 @@ int loco_pullback_pair_iteration(loco_plan_t* p, const float* xt, float t, float
 /* ---------------- bandwidth-bound pieces ---------------- */
 /* P = (x - eps*sqrt(1-at))/sqrt(at): get_x0 without the mask (src/modules/edit.py:2386) */
 int loco_pmp_forward(const float* x, const float* eps, float at, long long n, float* out, void* stream);
+/* out = wa*a + wb*b + wc*c (b, c may be NULL): the classifier-free-guidance combination
+ * `e_null + g (e_for - e_null) + g_edit (e_edit - e_null)` of src/modules/edit.py:660-673 / 1326-1373,
+ * also applied to the tangents / cotangent products of the conditionings (the combination is linear). */
+int loco_combine3(const float* a, float wa, const float* b, float wb, const float* c, float wc, long long n,
+                  float* out, void* stream);
+/* PMP differentiated along k directions (get_x0, src/modules/edit.py:1566-1587, 2369-2391):
+ *   u = mask o (V - eps_dot sqrt(1-at)) / sqrt(at)   (noise != 0: u = mask o eps_dot)
+ * and the seeds of the transposed pass g_eps = d<u,P>/d eps, gx_direct = d<u,P>/d x.  Rows >= k_invert
+ * use the complement mask.  All [k, d]. */
+int loco_pmp_jvp_epilogue(const float* V, const float* eps_dot, const unsigned char* mask, float at, int noise,
+                          int k, int k_invert, long long d, float* u, float* g_eps, float* gx_direct,
+                          void* stream);
 /* Vh and sqrt(singular values) of W [k,d]: torch.linalg.svd at src/modules/edit.py:2482.
  * scratch >= loco_orthonormalise_scratch_bytes(k). */
 long long loco_orthonormalise_scratch_bytes(int k);

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "loco_pullback_probe_pair": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P]),
     "loco_pullback_pair_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),
     "loco_pmp_forward": (_I, [_P, _P, _F, _LL, _P, _P]),
+    "loco_combine3": (_I, [_P, _F, _P, _F, _P, _F, _LL, _P, _P]),
+    "loco_pmp_jvp_epilogue": (_I, [_P, _P, _P, _F, _I, _I, _I, _LL, _P, _P, _P, _P]),
     "loco_orthonormalise_scratch_bytes": (_LL, [_I]),
     "loco_orthonormalise": (_I, [_P, _I, _LL, _P, _P, _P, _P, _P]),
     "loco_nullspace_project": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),

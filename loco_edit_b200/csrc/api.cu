@@ -280,6 +280,21 @@ int loco_pmp_forward(const float* x, const float* eps, float at, long long n, fl
   LOCO_TRY(require_device());
   return pmp_forward(x, eps, at, n, out, ST(stream));
 }
+int loco_combine3(const float* a, float wa, const float* b, float wb, const float* c, float wc, long long n,
+                  float* out, void* stream) {
+  ON_DEVICE_OF(a);
+  LOCO_TRY(require_device());
+  LOCO_REQUIRE(a && out, "loco_combine3: null argument");
+  return combine3(a, wa, b, wb, c, wc, n, out, ST(stream));
+}
+int loco_pmp_jvp_epilogue(const float* V, const float* eps_dot, const unsigned char* mask, float at, int noise,
+                          int k, int k_invert, long long d, float* u, float* g_eps, float* gx_direct,
+                          void* stream) {
+  ON_DEVICE_OF(V);
+  LOCO_TRY(require_device());
+  LOCO_REQUIRE(V && eps_dot && u && g_eps && gx_direct, "loco_pmp_jvp_epilogue: null argument");
+  return pmp_jvp_epilogue(V, eps_dot, mask, at, noise, k, k_invert, d, u, g_eps, gx_direct, ST(stream));
+}
 int loco_orthonormalise(const float* W, int k, long long d, const float* v_prev, float* V,
                         float* s_out, void* scratch, void* stream) {
   ON_DEVICE_OF(W);

@@ -365,6 +365,19 @@ __global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict
     out[i] = __fadd_rn(x[i], __fmul_rn(scale, v[i]));
 }
 
+// out = wa*a + wb*b + wc*c (b, c optional): classifier-free-guidance combination of noise
+// predictions (reference: modules/edit.py:660-673, 1326-1373) and of their Jacobian products
+__global__ void combine3_kernel(const float* __restrict__ a, float wa, const float* __restrict__ b, float wb,
+                                const float* __restrict__ c, float wc, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = wa * a[i];
+    if (b) v = fmaf(wb, b[i], v);
+    if (c) v = fmaf(wc, c[i], v);
+    out[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Mask compaction / gather / scatter
 // ------------------------------------------------------------------------------------------------
@@ -414,6 +427,12 @@ int pmp_jvp_epilogue(const float* v, const float* eps_dot, const unsigned char* 
                      float* gx_direct, cudaStream_t s) {
   pmp_jvp_kernel<<<grid_for((long long)k * d, 256), 256, 0, s>>>(v, eps_dot, mask, at, noise, k,
                                                                 k_invert, d, u, g_eps, gx_direct);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int combine3(const float* a, float wa, const float* b, float wb, const float* c, float wc, long long n,
+             float* out, cudaStream_t s) {
+  combine3_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, wa, b, wb, c, wc, n, out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,9 @@ namespace loco {
 int pmp_jvp_epilogue(const float* v, const float* eps_dot, const unsigned char* mask, float at,
                      int noise, int k, int k_invert, long long d, float* u, float* g_eps,
                      float* gx_direct, cudaStream_t s);
+// out = wa*a + wb*b + wc*c; b and c may be null
+int combine3(const float* a, float wa, const float* b, float wb, const float* c, float wc, long long n,
+             float* out, cudaStream_t s);
 // PMP value for primal rows: P = (x - eps*sqrt(1-at))/sqrt(at)   (bit-compatible op order)
 int pmp_forward(const float* x, const float* eps, float at, long long n, float* out, cudaStream_t s);
 

@@ -30,6 +30,28 @@ def pmp_forward(x, eps, at):
     return out
 
 
+def combine3(a, wa, b=None, wb=0.0, c=None, wc=0.0):
+    """wa*a + wb*b + wc*c (classifier-free-guidance combination, reference modules/edit.py:660-673)."""
+    a = _f32(a)
+    out = torch.empty_like(a)
+    check(_lib.load().loco_combine3(ptr(a), float(wa), ptr(_f32(b)) if b is not None else None, float(wb),
+                                    ptr(_f32(c)) if c is not None else None, float(wc), a.numel(), ptr(out),
+                                    stream_ptr(a)), "loco_combine3")
+    return out
+
+
+def pmp_jvp_epilogue(V, eps_dot, mask_u8, at, noise=False, k_invert=None):
+    """(u, g_eps, gx_direct), all [k, d]: the PMP differentiated along the rows of V given the tangents
+    eps_dot of the noise prediction, and the seeds of the transposed pass (pullback.cuh)."""
+    V, eps_dot = _f32(V), _f32(eps_dot)
+    k, d = V.shape
+    u, ge, gd = torch.empty_like(V), torch.empty_like(V), torch.empty_like(V)
+    check(_lib.load().loco_pmp_jvp_epilogue(ptr(V), ptr(eps_dot), ptr(mask_u8) if mask_u8 is not None else None,
+                                            float(at), 1 if noise else 0, k, k if k_invert is None else int(k_invert),
+                                            d, ptr(u), ptr(ge), ptr(gd), stream_ptr(V)), "loco_pmp_jvp_epilogue")
+    return u, ge, gd
+
+
 def orthonormalise(W, v_prev=None):
     """(V, s): V = Vh of svd(W) (rows, up to sign), s = sqrt(singular values)
     (reference modules/edit.py:2482, 2499-2502)."""

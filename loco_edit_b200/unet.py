@@ -126,12 +126,13 @@ class B200UNet:
         off = ((-self.arena.data_ptr()) % 256) // 4
         check(self.lib.loco_unet_bind_weights(h, C.c_void_p(self.arena.data_ptr() + 4 * off)))
         self._plans = collections.OrderedDict()
-        # arithmetic of the Jacobian-free programs (DDIM loops): fp16 storage + kind::f16 tensor cores,
-        # or fp32 storage + kind::tf32 (LOCO_FWD_FP16=0); the JVP / VJP programs always run tf32
-        self.fwd_half = os.environ.get("LOCO_FWD_FP16", "0") != "0"
+        # arithmetic of the Jacobian-free programs (DDIM loops): fp16 storage + kind::f16 tensor cores
+        # (default), or fp32 storage + kind::tf32 (LOCO_FWD_FP16=0).  Same 10-bit operand mantissa either
+        # way; parity of both against the unmodified reference: tests/test_gpu_full256.py
+        self.fwd_half = os.environ.get("LOCO_FWD_FP16", "1") != "0"
         # arithmetic of the Jacobian programs (fused primal + k-tangent JVP, k-cotangent VJP): same switch;
         # their tangent / cotangent rows are range-scaled by a power of two inside the library
-        self.jac_half = os.environ.get("LOCO_JAC_FP16", "0") != "0"
+        self.jac_half = os.environ.get("LOCO_JAC_FP16", "1") != "0"
         self.load_state_dict(state_dict)
 
     def param_shapes(self):

@@ -61,11 +61,15 @@ def attn_block(sd, p, x, eps):
     return x + conv(sd, p + ".proj_out", h_)
 
 
-def unet_forward(sd, arch, x, t):
+def unet_forward(sd, arch, x, t, cond=None):
     """models/ddpm/diffusion.py:145-200 (PullBackDDPM.forward with op=None).
 
     x: [B,3,R,R]; t: 0-dim or [1] tensor / float (shared by the batch, as in the reference where
-    temb has batch 1 and broadcasts)."""
+    temb has batch 1 and broadcasts).
+    cond (optional, [4*ch]): conditioning embedding added to the timestep embedding before the
+    blocks' SiLU + projection -- the stand-in conditional U-Net eps(x, t, c) used to pin the
+    Edit-class logic of the T-LOCO twins (the SD / IF networks themselves are diffusers
+    code that is not in /root/reference)."""
     ch, mult, nrb = arch["ch"], tuple(arch["ch_mult"]), arch["num_res_blocks"]
     attn_res, eps = tuple(arch["attn_resolutions"]), arch.get("gn_eps", 1e-6)
     L = len(mult)
@@ -74,6 +78,8 @@ def unet_forward(sd, arch, x, t):
     temb = F.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
     temb = swish(temb)
     temb = F.linear(temb, sd["temb.dense.1.weight"], sd["temb.dense.1.bias"])
+    if cond is not None:
+        temb = temb + cond.reshape(1, -1).to(temb.dtype)
 
     cur = arch["resolution"]
     hs = [conv(sd, "conv_in", x, padding=1)]
@@ -111,5 +117,5 @@ class RefUNet:
         self.arch = dict(arch)
         self.sd = {k: v.to(dtype) for k, v in sd.items()}
 
-    def __call__(self, x, t):
-        return unet_forward(self.sd, self.arch, x, t)
+    def __call__(self, x, t, cond=None):
+        return unet_forward(self.sd, self.arch, x, t, cond=cond)
