@@ -22,20 +22,34 @@ class SchedulerOutput(object):
         self.x0 = P_xt
 
 
+def cosine_betas(n=1000, max_beta=0.999):
+    """"squaredcos_cap_v2" (Nichol & Dhariwal cosine schedule, the beta schedule of the DeepFloyd-IF
+    stage-I DDPM scheduler whose `alphas_cumprod` the reference keeps, utils.py:163):
+    beta_i = min(1 - ab((i+1)/n) / ab(i/n), max_beta), ab(s) = cos((s + 0.008) / 1.008 * pi / 2)^2."""
+    import math
+    ab = lambda s: math.cos((s + 0.008) / 1.008 * math.pi / 2) ** 2
+    return torch.tensor([min(1 - ab((i + 1) / n) / ab(i / n), max_beta) for i in range(n)], dtype=torch.float64)
+
+
 class YHCustomScheduler(object):
     def __init__(self, args=None, device=None, dtype=torch.float32):
-        self.t_max = 999
+        # t_max: 999 for the custom scheduler (utils.py:309); the DeepFloyd-IF monkey patch uses 990
+        # (get_deepfloyd_if_scheduler, utils.py:159-170)
+        self.t_max = getattr(args, "t_max", 999) if args is not None else 999
         ns = getattr(args, "noise_schedule", None) if args is not None else None
         self.noise_schedule = "linear" if ns is None else ns
-        if self.noise_schedule != "linear":
-            raise NotImplementedError("only the linear schedule is used by the uncond hot path")
+        if self.noise_schedule not in ("linear", "squaredcos_cap_v2"):
+            raise NotImplementedError("noise schedule '%s'" % self.noise_schedule)
         self.device = torch.device(device if device is not None else getattr(args, "device", "cuda:0"))
         self.dtype = getattr(args, "dtype", dtype) if args is not None else dtype
         self.timesteps = None
         self.timesteps_next = None
         self.learn_sigma = False
         # utils.py:385-406: fp64 linspace betas -> cumprod -> cast to args.dtype
-        betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+        if self.noise_schedule == "linear":
+            betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+        else:
+            betas = cosine_betas(1000)
         self.betas = betas.to(device=self.device, dtype=self.dtype)
         acp = torch.cumprod(1.0 - betas, dim=0).to(self.dtype)
         self._acp_host = acp.float().tolist()
