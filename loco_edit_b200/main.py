@@ -1,7 +1,9 @@
 """Entry point mirroring the reference's src/main.py (:12-103): same flags, same dispatch on the
-`--run_*` booleans.  Only the unconditional-diffusion path (EditUncondDiffusion) is implemented in
-this round; the text-to-image classes (SD / DeepFloyd-IF / LCM) need U-Nets whose arithmetic lives
-in un-vendored third-party code and raise NotImplementedError.
+`--run_*` booleans.  The unconditional path runs `EditUncondDiffusion`; DeepFloyd-IF model names run the
+T-LOCO class `EditDeepFloydIF` of loco_edit_b200/t2i.py on its stand-in conditional U-Net with seeded
+prompt embeddings (the IF network and its T5 encoder are diffusers / transformers models that cannot
+be obtained here); the latent-space classes (Stable Diffusion, LCM) need a VAE
+decoder inside every Jacobian product and raise NotImplementedError.
 
     python -m loco_edit_b200.main --model_name LSUN_church_HF --dataset_name LSUN_church --dtype fp32 \
         --edit_t 0.6 --performance_boosting_t 0.2 --pca_rank 5 --pca_rank_null 5 \
@@ -12,10 +14,34 @@ from .define_argparser import parse_args, preset
 from .edit import EditUncondDiffusion
 
 
+def main_deepfloyd(args):
+    """src/main.py:28-32, 72-85 for `--model_name DeepFloyd/IF-I-*`: pixel-space T-LOCO on 64 x 64."""
+    import torch
+    from .t2i import CondB200UNet, EditDeepFloydIF, synthetic_prompt_embedding
+    from .unet import B200UNet
+    from .weights import DDPM256, random_state_dict
+    print("DeepFloyd-IF: running the stand-in conditional U-Net with seeded prompt embeddings "
+          "(the IF checkpoint / T5 encoder are not available offline)")
+    arch = dict(DDPM256, resolution=args.image_size, ch_mult=(1, 2, 2, 4))       # 64 -> 8, attention at 16
+    net = CondB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=torch.device(args.device)), 64)
+    embs = [synthetic_prompt_embedding(p or "", 77, 64) for p in (args.for_prompt, args.edit_prompt, "")]
+    edit = EditDeepFloydIF(args, net, *embs)
+    common = dict(op='mid', block_idx=0, mask_index=args.mask_index, vis_num=args.vis_num, vis_num_pc=args.pca_rank,
+                  pca_rank=args.pca_rank, edit_prompt=args.edit_prompt, null_space_projection=args.null_space_projection,
+                  pca_rank_null=args.pca_rank_null)
+    if args.run_edit_null_space_projection_xt:
+        edit.run_edit_null_space_projection_xt(**common)
+    if args.run_edit_null_space_projection_xt_semantic:
+        edit.run_edit_null_space_projection_xt_semantic(jacobian=args.jacobian, **common)
+    return edit
+
+
 def main(argv=None):
     args = preset(parse_args(argv))
-    if args.is_stable_diffusion or args.is_DeepFloyd_IF_diffusion or args.is_LCM:
-        raise NotImplementedError("T2I editing classes are listed under 'next' in DESIGN.md (SURVEY 8f)")
+    if args.is_stable_diffusion or args.is_LCM:
+        raise NotImplementedError("latent-space T2I classes need the VAE-decoder Jacobian (DESIGN.md, out of scope)")
+    if args.is_DeepFloyd_IF_diffusion:
+        return main_deepfloyd(args)
     print('is custmized diffusion model')
     edit = EditUncondDiffusion(args)
     if args.run_edit_null_space_projection:
