@@ -228,6 +228,17 @@ int loco_groupnorm_silu_fwd(const float* x, int N, int H, int W, int C, int n_pr
 int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* gy, int K,
                             const float* gamma, const float* beta, float eps, int silu, float* gx,
                             void* stats, void* stream);
+/* Typed variants of the two entry points above: half = 1 takes fp16 tensors (the storage type of
+ * the default programs; x / y / gy / gx / addend are then __half*), and `stages` selects the passes
+ * (bit 0: statistics incl. clearing `stats`, bit 1: apply) so that each bandwidth-bound kernel can
+ * be verified and timed alone.  VJP: gx = J^T gy (+ addend) (+ gx if accumulate). */
+int loco_groupnorm_silu_fwd_ex(const void* x, int half, int N, int H, int W, int C, int n_primal,
+                               const float* gamma, const float* beta, float eps, int silu, void* y,
+                               void* stats, int stages, void* stream);
+int loco_groupnorm_silu_vjp_ex(const void* xp, int half, int H, int W, int C, const void* gy, int K,
+                               const float* gamma, const float* beta, float eps, int silu,
+                               const void* addend, int accumulate, void* gx, void* stats, int stages,
+                               void* stream);
 /* attention core on qkv [N,T,3C]; S scratch [N,heads,T,T]; o [N,T,C].  head_ch = 0: one head,
  * channels q|k|v (ddpm/diffusion.py:941-966); head_ch > 0: C/head_ch heads, per head q|k|v
  * (QKVAttentionLegacy, guided_diffusion/unet.py:339-356). */

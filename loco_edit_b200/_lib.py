@@ -79,6 +79,8 @@ PROTOTYPES = {
                                 C.POINTER(_F), C.POINTER(_I), C.POINTER(_I), _P]),
     "loco_groupnorm_silu_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
     "loco_groupnorm_silu_vjp": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P]),
+    "loco_groupnorm_silu_fwd_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
+    "loco_groupnorm_silu_vjp_ex": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _I, _P, _P, _I, _P]),
     "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "loco_attention_vjp": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }

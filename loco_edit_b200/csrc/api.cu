@@ -547,6 +547,48 @@ int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* g
   LOCO_TRY(gn_stats_vjp(xv, ps, gyv, gamma, beta, eps, silu, bs, s));
   return gn_apply_vjp(xv, ps, gyv, bs, gamma, beta, eps, silu, nullptr, 0, 0, gxv, s);
 }
+// Typed variants (half = 1: fp16 tensors, the storage type of the default programs) with the two
+// passes selectable (stages bit 0: statistics (+ their memset), bit 1: apply), so that each
+// bandwidth-bound kernel can be checked and timed on its own.
+int loco_groupnorm_silu_fwd_ex(const void* x, int half, int N, int H, int W, int C, int n_primal,
+                               const float* gamma, const float* beta, float eps, int silu, void* y,
+                               void* stats, int stages, void* stream) {
+  ON_DEVICE_OF(x);
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  View xv = make_view(reinterpret_cast<float*>(const_cast<void*>(x)), N, H, W, C, half);
+  View yv = make_view(reinterpret_cast<float*>(y), N, H, W, C, half);
+  if (stages & 1) {
+    LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
+    LOCO_TRY(gn_stats_fwd(xv, n_primal, reinterpret_cast<double*>(stats), s));
+  }
+  if (stages & 2)
+    LOCO_TRY(gn_apply_fwd(xv, n_primal, reinterpret_cast<double*>(stats), gamma, beta, eps, silu, 0, yv, s));
+  return 0;
+}
+int loco_groupnorm_silu_vjp_ex(const void* xp, int half, int H, int W, int C, const void* gy, int K,
+                               const float* gamma, const float* beta, float eps, int silu,
+                               const void* addend, int accumulate, void* gx, void* stats, int stages,
+                               void* stream) {
+  ON_DEVICE_OF(gy);
+  LOCO_TRY(require_device());
+  cudaStream_t s = ST(stream);
+  View xv = make_view(reinterpret_cast<float*>(const_cast<void*>(xp)), 1, H, W, C, half);
+  View gyv = make_view(reinterpret_cast<float*>(const_cast<void*>(gy)), K, H, W, C, half);
+  View gxv = make_view(reinterpret_cast<float*>(gx), K, H, W, C, half);
+  View addv = make_view(reinterpret_cast<float*>(const_cast<void*>(addend)), K, H, W, C, half);
+  double* ps = reinterpret_cast<double*>(stats);
+  double* bs = ps + 64;
+  if (stages & 1) {
+    LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * (K + 1), s));
+    LOCO_TRY(gn_stats_fwd(xv, 1, ps, s));
+    LOCO_TRY(gn_stats_vjp(xv, ps, gyv, gamma, beta, eps, silu, bs, s));
+  }
+  if (stages & 2)
+    LOCO_TRY(gn_apply_vjp(xv, ps, gyv, bs, gamma, beta, eps, silu, addend ? &addv : nullptr, accumulate, 0,
+                          gxv, s));
+  return 0;
+}
 int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int head_ch, float* S,
                        float* o, void* stream) {
   ON_DEVICE_OF(qkv);

@@ -4,6 +4,8 @@
 // its grid from the tensor so large layers launch many waves over the 148 SMs.
 #include "layers.cuh"
 #include <math.h>
+#include <algorithm>
+#include <type_traits>
 
 namespace loco {
 
@@ -297,26 +299,27 @@ edge_expand128_kernel(const float* __restrict__ in3, const float* __restrict__ W
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroups = 32;
 constexpr int kRC = 6;          // batch rows processed per register chunk (1 primal + 5 tangents)
-// fp16 rows are half as wide (8-byte vectors per thread): twice the rows per register chunk keeps
-// the same number of bytes in flight per thread on the forward / JVP kernels
-// (doubling the rows per chunk for fp16 was measured: more registers, fewer resident blocks, slower)
 template <int MODE, bool F16> struct GnRows { static constexpr int value = kRC; };
 constexpr int kGnMaxRows = 96;  // rows whose per-group scalars fit the shared table
 
-__host__ __device__ inline int gn_block_dim(int C) { return (256 % (C / 4) == 0) ? 256 : 192; }
+// A thread owns VEC consecutive channels = one 16-byte vector (4 fp32 / 8 fp16 channels) of a pixel.
+// With 8-byte vectors the fp16 kernels were latency-bound at the speed of the fp32 ones (2.9 / 3.6
+// TB/s on the 6 x 256^2 x 128 JVP site); 16 bytes per load keep the bytes in flight per thread equal.
+template <bool F16> struct GnVec { static constexpr int value = F16 ? 8 : 4; };
+__host__ __device__ inline int gn_block_dim(int C, int vec) { return (256 % (C / vec) == 0) ? 256 : 192; }
 
 struct GnGeom {
   int block, pstep, ppb, nblk;
 };
-// A thread owns one channel quad of `pv` pixels and walks ALL batch rows of those pixels: the
-// primal value is loaded (and its sigmoid evaluated) once and shared by the k tangent / cotangent
-// rows, and the loads of a row chunk are issued together.
+// A thread owns one channel vector of a pixel and walks ALL batch rows of that pixel: the primal
+// value is loaded (and its sigmoid evaluated) once and shared by the k tangent / cotangent rows, and
+// the loads of a row chunk are issued together.
 // `resident` = blocks of the kernel that fit the GPU at once (occupancy x SMs): the grid is one
 // full wave of persistent blocks that stride over the pixel chunks.
-inline GnGeom gn_geom(int C, long long HW, int resident) {
+inline GnGeom gn_geom(int C, int vec, long long HW, int resident) {
   GnGeom g;
-  g.block = gn_block_dim(C);
-  g.pstep = g.block / (C / 4);
+  g.block = gn_block_dim(C, vec);
+  g.pstep = g.block / (C / vec);
   g.ppb = g.pstep;
   const long long nchunks = (HW + g.pstep - 1) / g.pstep;
   g.nblk = (int)(nchunks < resident ? nchunks : resident);
@@ -332,68 +335,149 @@ __device__ __forceinline__ float2 mean_rstd(const double* st, double cnt, float 
   return make_float2((float)mu, (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps)));
 }
 
+// VEC consecutive channels of an activation tensor <-> registers
+template <bool F16>
+__device__ __forceinline__ void ldvec(const float* base, long long off, float (&v)[GnVec<F16>::value]) {
+  if (F16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + off);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  } else {
+    const float4 f = *reinterpret_cast<const float4*>(base + off);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void stvec(float* base, long long off, const float (&v)[GnVec<F16>::value]) {
+  if (F16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(base) + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    *reinterpret_cast<float4*>(base + off) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// the same 16 bytes kept packed (4 registers) until they are used: the kernels below issue the loads
+// of a whole row chunk first and unpack row by row, so that the bytes in flight per thread are not
+// bounded by the register cost of the unpacked fp32 values
+template <bool F16>
+__device__ __forceinline__ uint4 ldraw(const float* base, long long off) {
+  return F16 ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + off)
+             : *reinterpret_cast<const uint4*>(base + off);
+}
+template <bool F16>
+__device__ __forceinline__ void unpack(const uint4& u, float (&v)[GnVec<F16>::value]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if (F16) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __uint_as_float(w[k]);
+  }
+}
+
 // ---- statistics ---------------------------------------------------------------------------------
 // mode 0 (forward/JVP): rows < n_primal: (sum x, sum x^2); tangent rows: (sum dx, sum x0 dx).
 // mode 1 (VJP): a = gamma * act'(u) * gy;  rows: (sum a, sum x a), x = primal input (x has 1 row).
+// A thread's VEC channels are VEC / 4 quads; a quad never straddles a group (cg is a multiple of 4).
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                double* __restrict__ stats, int pv) {
+                double* __restrict__ stats, int lin) {
   constexpr int RC = GnRows<MODE, F16>::value;
-  __shared__ float part[2 * RC][256];
+  constexpr int VEC = GnVec<F16>::value;
+  constexpr int NQ = VEC / 4;                      // quads per thread
+  __shared__ float part[2 * RC][256 * NQ];         // [row, which][pixel row of the block][quad of the pixel]
   const int C = x.C;
-  const int cvn = C >> 2;
+  const int cvn = C / VEC;
+  const int qn = C >> 2;                           // quads per pixel
   const int cg = C / kGroups;
   const int cv = threadIdx.x % cvn;
   const int prow = threadIdx.x / cvn;
   const int pstep = blockDim.x / cvn;
-  const int g = (cv * 4) / cg;
-  const long long HW = (long long)x.H * x.W;
+  const int HW = x.H * x.W;
   // persistent blocks: chunk c covers pixels [c * pstep, (c + 1) * pstep); a block walks the chunks
   // c = blockIdx.x, blockIdx.x + gridDim.x, ... so the grid is one full wave and has no tail
-  const long long nchunks = (HW + pstep - 1) / pstep;
-  (void)pv;
+  // lin: every view has sH == W * sW, so a pixel's offset is p * sW (no division in the loop)
   const View& rows = (MODE == 0) ? x : gy;
   const int N = rows.N;
   const bool jvp = (MODE == 0) && (n_primal < N);   // row 0 primal, rows 1.. tangents
 
   // per-element factors of the primal point (VJP: a = fac * gy)
-  float fac[4] = {1.f, 1.f, 1.f, 1.f};
-  float mu = 0.f, rstd = 1.f;
-  float gs[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+  float fac[VEC];
+  float mu[NQ], rstd[NQ];
+  float gs[VEC], bs[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { fac[i] = 1.f; gs[i] = 1.f; bs[i] = 0.f; }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) { mu[q] = 0.f; rstd[q] = 1.f; }
   if (MODE == 1) {
-    const float2 mr = mean_rstd(pstats + g * 2, (double)HW * cg, eps);
-    mu = mr.x; rstd = mr.y;
-    const float4 ga = ld4(gamma + cv * 4), be = ld4(beta + cv * 4);
-    gs[0] = ga.x; gs[1] = ga.y; gs[2] = ga.z; gs[3] = ga.w;
-    bs[0] = be.x; bs[1] = be.y; bs[2] = be.z; bs[3] = be.w;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int g = (cv * VEC + 4 * q) / cg;
+      const float2 mr = mean_rstd(pstats + g * 2, (double)HW * cg, eps);
+      mu[q] = mr.x; rstd[q] = mr.y;
+      const float4 ga = ld4(gamma + cv * VEC + 4 * q), be = ld4(beta + cv * VEC + 4 * q);
+      gs[4 * q] = ga.x; gs[4 * q + 1] = ga.y; gs[4 * q + 2] = ga.z; gs[4 * q + 3] = ga.w;
+      bs[4 * q] = be.x; bs[4 * q + 1] = be.y; bs[4 * q + 2] = be.z; bs[4 * q + 3] = be.w;
+    }
   }
 
+  using Elem = typename std::conditional<F16, __half, float>::type;
+  const Elem* xbase = reinterpret_cast<const Elem*>(x.ptr) + cv * VEC;
   for (int n0 = 0; n0 < N; n0 += RC) {
-    float s1[RC], s2[RC];
+    float s1[RC][NQ], s2[RC][NQ];
 #pragma unroll
-    for (int r = 0; r < RC; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
-    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-      const long long p = ch * pstep + prow;
-      if (p >= HW) break;
-      const int y = (int)(p / x.W), xx = (int)(p % x.W);
-      const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
-      const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * 4;
-      float4 v[RC];
+    for (int r = 0; r < RC; ++r)
 #pragma unroll
-      for (int r = 0; r < RC; ++r)
-        v[r] = (n0 + r < N) ? ld4t<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      float xs[4] = {0.f, 0.f, 0.f, 0.f};
-      if (jvp || MODE == 1) {
-        const float4 x0 = (MODE == 0 && n0 == 0) ? v[0] : ld4t<F16>(x.ptr, xoff);
-        xs[0] = x0.x; xs[1] = x0.y; xs[2] = x0.z; xs[3] = x0.w;
+      for (int q = 0; q < NQ; ++q) { s1[r][q] = 0.f; s2[r][q] = 0.f; }
+    // row pointers; a chunk's rows past N re-read row N - 1 (an L1 hit) and their sums are never
+    // published, so the loop body carries no per-row predicates
+    const Elem* rbase[RC];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      const int nr = (n0 + r < N) ? n0 + r : N - 1;
+      rbase[r] = reinterpret_cast<const Elem*>(rows.ptr) + (long long)nr * rows.sN + cv * VEC;
+    }
+    const bool x_is_row0 = (MODE == 0 && n0 == 0);
+    const bool need_x = (jvp || MODE == 1) && !x_is_row0;
+    for (int p = blockIdx.x * pstep + prow; p < HW; p += gridDim.x * pstep) {
+      long long xoff, roff;
+      if (lin) {
+        xoff = (long long)p * x.sW; roff = (long long)p * rows.sW;
+      } else {
+        const int y = p / x.W, xx = p - y * x.W;
+        xoff = (long long)y * x.sH + (long long)xx * x.sW;
+        roff = (long long)y * rows.sH + (long long)xx * rows.sW;
       }
+      // all loads of the chunk are issued before the first use
+      uint4 rawx = make_uint4(0, 0, 0, 0);
+      if (need_x) rawx = *reinterpret_cast<const uint4*>(xbase + xoff);
+      uint4 raw[RC];
+#pragma unroll
+      for (int r = 0; r < RC; ++r) raw[r] = *reinterpret_cast<const uint4*>(rbase[r] + roff);
+      float xs[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) xs[i] = 0.f;
+      if (jvp || MODE == 1) unpack<F16>(x_is_row0 ? raw[0] : rawx, xs);
       if (MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float u = gs[i] * ((xs[i] - mu) * rstd) + bs[i];
+        for (int i = 0; i < VEC; ++i) {
+          const float u = gs[i] * ((xs[i] - mu[i >> 2]) * rstd[i >> 2]) + bs[i];
           float d = 1.0f;
           if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
           fac[i] = gs[i] * d;
@@ -401,36 +485,39 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
       }
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
-        const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
         const bool tangent = jvp && (n0 + r >= n_primal);
+        float v[VEC];
+        unpack<F16>(raw[r], v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < VEC; ++i) {
           if (MODE == 0) {
-            s1[r] += vs[i];
-            s2[r] += vs[i] * (tangent ? xs[i] : vs[i]);
+            s1[r][i >> 2] += v[i];
+            s2[r][i >> 2] += v[i] * (tangent ? xs[i] : v[i]);
           } else {
-            const float av = fac[i] * vs[i];
-            s1[r] += av;
-            s2[r] += av * xs[i];
+            const float av = fac[i] * v[i];
+            s1[r][i >> 2] += av;
+            s2[r][i >> 2] += av * xs[i];
           }
         }
       }
     }
     // fixed-order block reduction (bit-reproducible per block); fp64 atomics across blocks
 #pragma unroll
-    for (int r = 0; r < RC; ++r) {
-      part[2 * r][threadIdx.x] = s1[r];
-      part[2 * r + 1][threadIdx.x] = s2[r];
-    }
+    for (int r = 0; r < RC; ++r)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        part[2 * r][prow * qn + cv * NQ + q] = s1[r][q];
+        part[2 * r + 1][prow * qn + cv * NQ + q] = s2[r][q];
+      }
     __syncthreads();
     for (int e = threadIdx.x; e < RC * kGroups * 2; e += blockDim.x) {
       const int r = e / (kGroups * 2), gw = e % (kGroups * 2);
       if (n0 + r >= N) continue;
       const int gg = gw >> 1, which = gw & 1;
-      const int cv0 = gg * (cg >> 2), cv1 = cv0 + (cg >> 2);
+      const int q0 = gg * (cg >> 2), q1 = q0 + (cg >> 2);
       float acc = 0.f;
       for (int pr2 = 0; pr2 < pstep; ++pr2)
-        for (int c = cv0; c < cv1; ++c) acc += part[2 * r + which][pr2 * cvn + c];
+        for (int c = q0; c < q1; ++c) acc += part[2 * r + which][pr2 * qn + c];
       atomicAdd(&stats[(long long)(n0 + r) * kGroups * 2 + gw], (double)acc);
     }
     __syncthreads();
@@ -439,24 +526,31 @@ gn_stats_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
 
 // ---- apply ----------------------------------------------------------------------------------------
 // mode 0: y = act(gn(x)) for primal rows, JVP rule for tangent rows.  mode 1: VJP rule.
-template <int MODE, bool F16>
-__global__ void __launch_bounds__(256)
+// RC rows of a pixel are loaded together (packed, 4 registers per 16-byte vector) and then unpacked,
+// transformed and stored one at a time.  The VJP kernel has two instantiations: RC = 8 for the plain
+// rule, RC = 4 when an addend and / or the previous gx ride along (up to three loads per row).
+template <int MODE, bool F16, int RC>
+__global__ void __launch_bounds__(256, 2)
 gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats,
                 const double* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int silu, int round_out,
                 const float* __restrict__ addend, long long add_sN, long long add_sH,
-                long long add_sW, int accumulate, View out, int pv) {
+                long long add_sW, int accumulate, View out, int lin) {
+  constexpr int VEC = GnVec<F16>::value;
+  constexpr int NQ = VEC / 4;
+  constexpr bool EXTRA = (MODE == 1 && RC == 4);
   // per (row, group) scalars: primal rows (mean, rstd); tangent / cotangent rows (m1, m2)
-  constexpr int RC = GnRows<MODE, F16>::value;
   __shared__ float2 tab[kGnMaxRows][kGroups];
   const int C = x.C;
-  const int cvn = C >> 2;
+  const int cvn = C / VEC;
   const int cg = C / kGroups;
   const int cv = threadIdx.x % cvn;
   const int prow = threadIdx.x / cvn;
   const int pstep = blockDim.x / cvn;
-  const int g = (cv * 4) / cg;
-  const long long HW = (long long)x.H * x.W;
+  int g[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) g[q] = (cv * VEC + 4 * q) / cg;
+  const int HW = x.H * x.W;
   const double cnt = (double)HW * cg;
   const View& rows = (MODE == 0) ? x : gy;
   const int N = rows.N;
@@ -476,143 +570,163 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     }
   }
   __syncthreads();
-  const float4 ga4 = ld4(gamma + cv * 4), be4 = ld4(beta + cv * 4);
-  const float gs[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
-  const float bs[4] = {be4.x, be4.y, be4.z, be4.w};
-  float2 mr0 = make_float2(0.f, 1.f);
-  if (jvp || MODE == 1) mr0 = (MODE == 0) ? tab[0][g] : mean_rstd(pstats + g * 2, cnt, eps);
-
-  const long long nchunks = (HW + pstep - 1) / pstep;
-  (void)pv;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const long long p = ch * pstep + prow;
-    if (p >= HW) break;
-    const int y = (int)(p / x.W), xx = (int)(p % x.W);
-    const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * 4;
-    const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * 4;
-    const long long ooff = (long long)y * out.sH + (long long)xx * out.sW + cv * 4;
-    const long long aoff = (long long)y * add_sH + (long long)xx * add_sW + cv * 4;
-    // primal-point quantities shared by every tangent / cotangent row of this pixel
-    float xh[4] = {0.f, 0.f, 0.f, 0.f}, coef[4] = {1.f, 1.f, 1.f, 1.f};
-    if (jvp || MODE == 1) {
-      const float4 x0 = ld4t<F16>(x.ptr, xoff);
-      const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+  float gs[VEC], bs[VEC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xh[i] = (xs[i] - mr0.x) * mr0.y;
-        const float u = gs[i] * xh[i] + bs[i];
-        float d = 1.0f;
-        if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
-        coef[i] = d * gs[i];          // act'(u) * gamma
-      }
-    }
+  for (int q = 0; q < NQ; ++q) {
+    const float4 ga4 = ld4(gamma + cv * VEC + 4 * q), be4 = ld4(beta + cv * VEC + 4 * q);
+    gs[4 * q] = ga4.x; gs[4 * q + 1] = ga4.y; gs[4 * q + 2] = ga4.z; gs[4 * q + 3] = ga4.w;
+    bs[4 * q] = be4.x; bs[4 * q + 1] = be4.y; bs[4 * q + 2] = be4.z; bs[4 * q + 3] = be4.w;
+  }
+  float2 mr0[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    mr0[q] = make_float2(0.f, 1.f);
+    if (jvp || MODE == 1) mr0[q] = (MODE == 0) ? tab[0][g[q]] : mean_rstd(pstats + g[q] * 2, cnt, eps);
+  }
+
+  const int nchunks = (HW + pstep - 1) / pstep;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int p = ch * pstep + prow;
+    if (p >= HW) break;
+    int y = 0, xx = p;
+    if (!lin) { y = p / x.W; xx = p - y * x.W; }
+    const long long xoff = (long long)y * x.sH + (long long)xx * x.sW + cv * VEC;
+    const long long roff = (long long)y * rows.sH + (long long)xx * rows.sW + cv * VEC;
+    const long long ooff = (long long)y * out.sH + (long long)xx * out.sW + cv * VEC;
+    const long long aoff = (long long)y * add_sH + (long long)xx * add_sW + cv * VEC;
+    // primal-point quantities shared by every tangent / cotangent row of this pixel
+    float xh[VEC], coef[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { xh[i] = 0.f; coef[i] = 1.f; }
+    uint4 rawx = make_uint4(0, 0, 0, 0);
+    if (jvp || MODE == 1) rawx = ldraw<F16>(x.ptr, xoff);
     for (int n0 = 0; n0 < N; n0 += RC) {
-      float4 v[RC], e[RC];
+      uint4 rv[RC], re[EXTRA ? RC : 1], rc[EXTRA ? RC : 1];
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
-        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        e[r] = v[r];
+        rv[r] = make_uint4(0, 0, 0, 0);
+        if (EXTRA) { re[r] = rv[r]; rc[r] = rv[r]; }
         if (n0 + r < N) {
-          v[r] = ld4t<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff);
-          if (MODE == 1 && addend) e[r] = ld4t<F16>(addend, (long long)(n0 + r) * add_sN + aoff);
-          if (MODE == 1 && accumulate) {
-            const float4 c = ld4t<F16>(out.ptr, (long long)(n0 + r) * out.sN + ooff);
-            e[r].x += c.x; e[r].y += c.y; e[r].z += c.z; e[r].w += c.w;
-          }
+          rv[r] = ldraw<F16>(rows.ptr, (long long)(n0 + r) * rows.sN + roff);
+          if (EXTRA && addend) re[r] = ldraw<F16>(addend, (long long)(n0 + r) * add_sN + aoff);
+          if (EXTRA && accumulate) rc[r] = ldraw<F16>(out.ptr, (long long)(n0 + r) * out.sN + ooff);
+        }
+      }
+      if (n0 == 0 && (jvp || MODE == 1)) {
+        float xs[VEC];
+        unpack<F16>(rawx, xs);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          xh[i] = (xs[i] - mr0[i >> 2].x) * mr0[i >> 2].y;
+          const float u = gs[i] * xh[i] + bs[i];
+          float d = 1.0f;
+          if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
+          coef[i] = d * gs[i];          // act'(u) * gamma
         }
       }
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
         const int n = n0 + r;
         if (n >= N) break;
-        const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-        const float es[4] = {e[r].x, e[r].y, e[r].z, e[r].w};
-        const float2 t2 = tab[n][g];
-        float o[4];
+        float2 t2[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) t2[q] = tab[n][g[q]];
+        float v[VEC], o[VEC];
+        unpack<F16>(rv[r], v);
         if (MODE == 0 && n < n_primal) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float u = gs[i] * ((vs[i] - t2.x) * t2.y) + bs[i];
+          for (int i = 0; i < VEC; ++i) {
+            const float u = gs[i] * ((v[i] - t2[i >> 2].x) * t2[i >> 2].y) + bs[i];
             o[i] = silu ? u * fast_sigmoid(u) : u;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (MODE == 0) o[i] = coef[i] * mr0.y * (vs[i] - t2.x - xh[i] * t2.y);
-            else o[i] = mr0.y * (coef[i] * vs[i] - t2.x - xh[i] * t2.y) + es[i];
+          for (int i = 0; i < VEC; ++i) {
+            const float2 tq = t2[i >> 2];
+            const float rs0 = mr0[i >> 2].y;
+            if (MODE == 0) o[i] = coef[i] * rs0 * (v[i] - tq.x - xh[i] * tq.y);
+            else o[i] = rs0 * (coef[i] * v[i] - tq.x - xh[i] * tq.y);
+          }
+          if (EXTRA) {
+            float e[VEC], c[VEC];
+            unpack<F16>(re[r], e);
+            unpack<F16>(rc[r], c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] += e[i] + c[i];
           }
         }
         if (round_out && !F16) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = round_tf32(o[i]);
+          for (int i = 0; i < VEC; ++i) o[i] = round_tf32(o[i]);
         }
-        st4t<F16>(out.ptr, (long long)n * out.sN + ooff, make_float4(o[0], o[1], o[2], o[3]));
+        stvec<F16>(out.ptr, (long long)n * out.sN + ooff, o);
       }
     }
   }
 }
 
 // ---- fp16 forward-only apply (the Jacobian-free programs): y = act(gn(x)), 8 channels = 16 bytes
-// per thread and four pixels in flight per thread.  The generic kernel above moves 8-byte vectors in
-// fp16 and reached 4.1 TB/s on the 40 x 256^2 x 128 site (fp32: 5.2 TB/s).
+// per thread and four pixels in flight per thread.  blockIdx.y is the batch row, so the per-channel
+// affine u = a * x + b (a = gamma * rstd, b = beta - mean * a) is loop-invariant, and the pixel
+// offset is p * sW when the views are pixel-contiguous (`lin`): the loop body has no division (the
+// first version of this kernel spent ~120 of its ~230 instructions per vector on 64-bit divisions
+// and was issue-bound at 3.5 TB/s on the 40 x 256^2 x 128 site).
 constexpr int kGn16Unroll = 4;
 __global__ void __launch_bounds__(256)
 gn_apply_fwd16_kernel(View x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, float eps, int silu, View y) {
-  __shared__ float2 tab[kGnMaxRows][kGroups];
+                      const float* __restrict__ beta, float eps, int silu, View y, int lin) {
   const int C = x.C;
   const int c8n = C >> 3;
   const int cg = C / kGroups;
-  const long long HW = (long long)x.H * x.W;
+  const int HW = x.H * x.W;
   const double cnt = (double)HW * cg;
-  for (int e = threadIdx.x; e < x.N * kGroups; e += blockDim.x)
-    tab[e / kGroups][e % kGroups] = mean_rstd(stats + (long long)e * 2, cnt, eps);
-  __syncthreads();
+  const int n = blockIdx.y;
   const int cv = threadIdx.x % c8n;
   const int prow = threadIdx.x / c8n;
   const int pstep = blockDim.x / c8n;
-  const int g0 = (cv * 8) / cg, g1 = (cv * 8 + 4) / cg;
-  float ga[8], be[8];
+  float a[8], b[8];
   {
-    const float4 a = ld4(gamma + cv * 8), b = ld4(gamma + cv * 8 + 4);
-    const float4 c = ld4(beta + cv * 8), d = ld4(beta + cv * 8 + 4);
-    ga[0] = a.x; ga[1] = a.y; ga[2] = a.z; ga[3] = a.w; ga[4] = b.x; ga[5] = b.y; ga[6] = b.z; ga[7] = b.w;
-    be[0] = c.x; be[1] = c.y; be[2] = c.z; be[3] = c.w; be[4] = d.x; be[5] = d.y; be[6] = d.z; be[7] = d.w;
+    const float2 m0 = mean_rstd(stats + ((long long)n * kGroups + (cv * 8) / cg) * 2, cnt, eps);
+    const float2 m1 = mean_rstd(stats + ((long long)n * kGroups + (cv * 8 + 4) / cg) * 2, cnt, eps);
+    const float4 g0 = ld4(gamma + cv * 8), g1 = ld4(gamma + cv * 8 + 4);
+    const float4 b0 = ld4(beta + cv * 8), b1 = ld4(beta + cv * 8 + 4);
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 mr = i < 4 ? m0 : m1;
+      a[i] = ga[i] * mr.y;
+      b[i] = be[i] - mr.x * a[i];
+    }
   }
-  const long long total = (long long)x.N * HW;                         // pixels over all rows
-  const long long stride = (long long)gridDim.x * pstep;
-  const __half* xp = reinterpret_cast<const __half*>(x.ptr);
-  __half* yp = reinterpret_cast<__half*>(y.ptr);
-  for (long long p0 = (long long)blockIdx.x * pstep + prow; p0 < total; p0 += stride * kGn16Unroll) {
+  const int stride = gridDim.x * pstep;
+  const __half* xp = reinterpret_cast<const __half*>(x.ptr) + (long long)n * x.sN + cv * 8;
+  __half* yp = reinterpret_cast<__half*>(y.ptr) + (long long)n * y.sN + cv * 8;
+  for (int p0 = blockIdx.x * pstep + prow; p0 < HW; p0 += stride * kGn16Unroll) {
     uint4 v[kGn16Unroll];
     long long yo[kGn16Unroll];
-    int nn[kGn16Unroll];
 #pragma unroll
     for (int u = 0; u < kGn16Unroll; ++u) {
-      const long long p = p0 + u * stride;
-      nn[u] = -1;
-      if (p < total) {
-        const int n = (int)(p / HW);
-        const long long q = p - (long long)n * HW;
-        const int yy = (int)(q / x.W), xx = (int)(q % x.W);
-        nn[u] = n;
-        v[u] = *reinterpret_cast<const uint4*>(xp + (long long)n * x.sN + (long long)yy * x.sH + (long long)xx * x.sW + cv * 8);
-        yo[u] = (long long)n * y.sN + (long long)yy * y.sH + (long long)xx * y.sW + cv * 8;
+      const int p = p0 + u * stride;
+      yo[u] = -1;
+      if (p < HW) {
+        int yy = 0, xx = p;
+        if (!lin) { yy = p / x.W; xx = p - yy * x.W; }
+        v[u] = *reinterpret_cast<const uint4*>(xp + (long long)yy * x.sH + (long long)xx * x.sW);
+        yo[u] = (long long)yy * y.sH + (long long)xx * y.sW;
       }
     }
 #pragma unroll
     for (int u = 0; u < kGn16Unroll; ++u) {
-      if (nn[u] < 0) continue;
-      const float2 m0 = tab[nn[u]][g0], m1 = tab[nn[u]][g1];
+      if (yo[u] < 0) continue;
       const uint32_t* w = &v[u].x;
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
-        const float2 mr = k < 2 ? m0 : m1;
-        float u0 = ga[2 * k] * ((f.x - mr.x) * mr.y) + be[2 * k];
-        float u1 = ga[2 * k + 1] * ((f.y - mr.x) * mr.y) + be[2 * k + 1];
-        if (silu) { u0 *= fast_sigmoid(u0); u1 *= fast_sigmoid(u1); }
+        float u0 = fmaf(a[2 * k], f.x, b[2 * k]);
+        float u1 = fmaf(a[2 * k + 1], f.y, b[2 * k + 1]);
+        if (silu) { u0 = __fdividef(u0, 1.0f + __expf(-u0)); u1 = __fdividef(u1, 1.0f + __expf(-u1)); }
         const __half2 h = __floats2half2_rn(u0, u1);
         o[k] = *reinterpret_cast<const uint32_t*>(&h);
       }
@@ -844,12 +958,16 @@ inline int grid_for(long long total, int block, int cap = 148 * 16) {
   return (int)g;
 }
 
+// pixel-contiguous view: the offset of pixel p = y * W + x is p * sW
+inline int gn_lin(const View& v) { return v.sH == (long long)v.W * v.sW; }
 int check_gn_view(const View& v, const char* what) {
   LOCO_REQUIRE(v.C % 128 == 0, "%s: channels %d must be a multiple of 128", what, v.C);
   LOCO_REQUIRE(v.C <= 1024, "%s: channels %d > 1024", what, v.C);
   LOCO_REQUIRE((v.sW % 4) == 0 && (v.sH % 4) == 0 && (v.sN % 4) == 0 &&
                    (((uintptr_t)v.ptr) & 15) == 0,
                "%s: view not float4-aligned", what);
+  LOCO_REQUIRE(!v.half || ((v.sW % 8) == 0 && (v.sH % 8) == 0 && (v.sN % 8) == 0),
+               "%s: fp16 view not aligned to 16-byte vectors", what);
   return 0;
 }
 
@@ -959,7 +1077,7 @@ static int gn_resident(K kernel, int block, int* cache) {
   return *cache;
 }
 // per device: [storage type][kernel: stats fwd, stats vjp, apply fwd, apply vjp][block == 192]
-static int g_res[kMaxDevices][2][4][2];
+static int g_res[kMaxDevices][2][5][2];   // kernel 4: the VJP apply with addend / accumulate
 static int g_res16[kMaxDevices][2];       // gn_apply_fwd16_kernel, [block == 192]
 static int* res_slot(int h, int kernel, int bd192) {
   const int d = current_device();
@@ -975,9 +1093,9 @@ int layers_init() {
 #define LOCO_CARVE(k) LOCO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co))
 #define LOCO_CARVE2(k) LOCO_CARVE(k<false>); LOCO_CARVE(k<true>)
   LOCO_CARVE((gn_stats_kernel<0, false>)); LOCO_CARVE((gn_stats_kernel<1, false>));
-  LOCO_CARVE((gn_apply_kernel<0, false>)); LOCO_CARVE((gn_apply_kernel<1, false>));
+  LOCO_CARVE((gn_apply_kernel<0, false, kRC>)); LOCO_CARVE((gn_apply_kernel<1, false, 8>)); LOCO_CARVE((gn_apply_kernel<1, false, 4>));
   LOCO_CARVE((gn_stats_kernel<0, true>)); LOCO_CARVE((gn_stats_kernel<1, true>));
-  LOCO_CARVE((gn_apply_kernel<0, true>)); LOCO_CARVE((gn_apply_kernel<1, true>));
+  LOCO_CARVE((gn_apply_kernel<0, true, kRC>)); LOCO_CARVE((gn_apply_kernel<1, true, 8>)); LOCO_CARVE((gn_apply_kernel<1, true, 4>));
   LOCO_CARVE2(edge_expand_kernel); LOCO_CARVE2(edge_reduce_kernel);
   LOCO_CARVE2(edge_expand128_kernel); LOCO_CARVE2(edge_reduce128_kernel);
   LOCO_CARVE2(upsample2x_kernel); LOCO_CARVE2(upsample2x_fast_kernel); LOCO_CARVE2(sumpool2x_kernel); LOCO_CARVE2(add_views_kernel);
@@ -991,12 +1109,14 @@ int layers_init() {
     const int bd = b ? 192 : 256;
     gn_resident(gn_stats_kernel<0, false>, bd, res_slot(0, 0, b));
     gn_resident(gn_stats_kernel<1, false>, bd, res_slot(0, 1, b));
-    gn_resident(gn_apply_kernel<0, false>, bd, res_slot(0, 2, b));
-    gn_resident(gn_apply_kernel<1, false>, bd, res_slot(0, 3, b));
+    gn_resident(gn_apply_kernel<0, false, kRC>, bd, res_slot(0, 2, b));
+    gn_resident(gn_apply_kernel<1, false, 8>, bd, res_slot(0, 3, b));
+    gn_resident(gn_apply_kernel<1, false, 4>, bd, res_slot(0, 4, b));
     gn_resident(gn_stats_kernel<0, true>, bd, res_slot(1, 0, b));
     gn_resident(gn_stats_kernel<1, true>, bd, res_slot(1, 1, b));
-    gn_resident(gn_apply_kernel<0, true>, bd, res_slot(1, 2, b));
-    gn_resident(gn_apply_kernel<1, true>, bd, res_slot(1, 3, b));
+    gn_resident(gn_apply_kernel<0, true, kRC>, bd, res_slot(1, 2, b));
+    gn_resident(gn_apply_kernel<1, true, 8>, bd, res_slot(1, 3, b));
+    gn_resident(gn_apply_kernel<1, true, 4>, bd, res_slot(1, 4, b));
     gn_resident(gn_apply_fwd16_kernel, bd, &g_res16[current_device() < kMaxDevices ? current_device() : 0][b]);
   }
   return 0;
@@ -1009,14 +1129,15 @@ static int same_type(const View& a, const View& b, const char* what) {
 
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
-  const int bd = gn_block_dim(x.C);
   const int h = x.half;
+  const int vec = h ? 8 : 4;
+  const int bd = gn_block_dim(x.C, vec);
   const int res = h ? gn_resident(gn_stats_kernel<0, true>, bd, res_slot(1, 0, bd == 192))
                     : gn_resident(gn_stats_kernel<0, false>, bd, res_slot(0, 0, bd == 192));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, res);
+  const GnGeom g = gn_geom(x.C, vec, (long long)x.H * x.W, res);
   ProfScope prof(1, (h ? 2.0 : 4.0) * x.N * x.H * x.W * x.C, s);
-  if (h) gn_stats_kernel<0, true><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, 1);
-  else gn_stats_kernel<0, false><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, 1);
+  if (h) gn_stats_kernel<0, true><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, gn_lin(x));
+  else gn_stats_kernel<0, false><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, nullptr, nullptr, 0.f, 0, stats, gn_lin(x));
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1026,8 +1147,9 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
   LOCO_TRY(check_gn_view(y, "gn_apply_fwd(out)"));
   LOCO_TRY(same_type(x, y, "gn_apply_fwd"));
   LOCO_REQUIRE(x.N <= kGnMaxRows, "gn_apply_fwd: batch %d > %d rows", x.N, kGnMaxRows);
-  const int bd = gn_block_dim(x.C);
   const int h = x.half;
+  const int vec = h ? 8 : 4;
+  const int bd = gn_block_dim(x.C, vec);
   if (h && n_primal == x.N && x.C % 8 == 0 && (x.C / kGroups) % 4 == 0 && x.sW % 8 == 0 && x.sH % 8 == 0 &&
       x.sN % 8 == 0 && y.sW % 8 == 0 && y.sH % 8 == 0 && y.sN % 8 == 0) {
     // forward-only fp16: the 16-byte-vector kernel
@@ -1036,23 +1158,26 @@ int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, 
     LOCO_REQUIRE(block % c8n == 0, "gn_apply_fwd: C=%d unsupported by the fp16 kernel", x.C);
     int* rs = &g_res16[current_device() < kMaxDevices ? current_device() : 0][block == 192];
     gn_resident(gn_apply_fwd16_kernel, block, rs);
-    const long long pix = (long long)x.N * x.H * x.W;
+    // grid: (blocks per batch row, batch rows); about one resident wave in total
+    const long long pix = (long long)x.H * x.W;
     const int pstep = block / c8n;
     long long nblk = (pix + (long long)pstep * kGn16Unroll - 1) / ((long long)pstep * kGn16Unroll);
-    if (nblk > *rs) nblk = *rs;
+    const long long per_row = std::max(1, *rs / x.N);
+    if (nblk > per_row) nblk = per_row;
     ProfScope prof(1, 4.0 * x.N * x.H * x.W * x.C, s);
-    gn_apply_fwd16_kernel<<<(int)nblk, block, 0, s>>>(x, stats, gamma, beta, eps, silu, y);
+    gn_apply_fwd16_kernel<<<dim3((unsigned)nblk, (unsigned)x.N), block, 0, s>>>(x, stats, gamma, beta, eps, silu, y,
+                                                                             gn_lin(x) && gn_lin(y));
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  const int res = h ? gn_resident(gn_apply_kernel<0, true>, bd, res_slot(1, 2, bd == 192))
-                    : gn_resident(gn_apply_kernel<0, false>, bd, res_slot(0, 2, bd == 192));
-  const GnGeom g = gn_geom(x.C, (long long)x.H * x.W, res);
+  const int res = h ? gn_resident(gn_apply_kernel<0, true, kRC>, bd, res_slot(1, 2, bd == 192))
+                    : gn_resident(gn_apply_kernel<0, false, kRC>, bd, res_slot(0, 2, bd == 192));
+  const GnGeom g = gn_geom(x.C, vec, (long long)x.H * x.W, res);
   ProfScope prof(1, (h ? 4.0 : 8.0) * x.N * x.H * x.W * x.C, s);
-  if (h) gn_apply_kernel<0, true><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
-                                                            silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
-  else gn_apply_kernel<0, false><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
-                                                           silu, round_out, nullptr, 0, 0, 0, 0, y, 1);
+  if (h) gn_apply_kernel<0, true, kRC><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                                            silu, round_out, nullptr, 0, 0, 0, 0, y, gn_lin(x) && gn_lin(y));
+  else gn_apply_kernel<0, false, kRC><<<g.nblk, g.block, 0, s>>>(x, n_primal, x, nullptr, stats, gamma, beta, eps,
+                                                           silu, round_out, nullptr, 0, 0, 0, 0, y, gn_lin(x) && gn_lin(y));
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1061,14 +1186,15 @@ int gn_stats_vjp(View xp, const double* pstats, View gy, const float* gamma, con
   LOCO_TRY(check_gn_view(xp, "gn_stats_vjp"));
   LOCO_TRY(check_gn_view(gy, "gn_stats_vjp(gy)"));
   LOCO_TRY(same_type(xp, gy, "gn_stats_vjp"));
-  const int bd = gn_block_dim(xp.C);
   const int h = xp.half;
+  const int vec = h ? 8 : 4;
+  const int bd = gn_block_dim(xp.C, vec);
   const int res = h ? gn_resident(gn_stats_kernel<1, true>, bd, res_slot(1, 1, bd == 192))
                     : gn_resident(gn_stats_kernel<1, false>, bd, res_slot(0, 1, bd == 192));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, res);
+  const GnGeom g = gn_geom(xp.C, vec, (long long)xp.H * xp.W, res);
   ProfScope prof(1, (h ? 2.0 : 4.0) * (gy.N + 1) * gy.H * gy.W * gy.C, s);
-  if (h) gn_stats_kernel<1, true><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
-  else gn_stats_kernel<1, false><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, 1);
+  if (h) gn_stats_kernel<1, true><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, gn_lin(xp) && gn_lin(gy));
+  else gn_stats_kernel<1, false><<<g.nblk, g.block, 0, s>>>(xp, 0, gy, pstats, gamma, beta, eps, silu, stats, gn_lin(xp) && gn_lin(gy));
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1081,20 +1207,25 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   LOCO_TRY(same_type(xp, gy, "gn_apply_vjp")); LOCO_TRY(same_type(gy, gx, "gn_apply_vjp(gx)"));
   if (addend) { LOCO_TRY(check_gn_view(*addend, "gn_apply_vjp(addend)")); LOCO_TRY(same_type(*addend, gx, "gn_apply_vjp(addend)")); }
   LOCO_REQUIRE(gy.N <= kGnMaxRows, "gn_apply_vjp: batch %d > %d rows", gy.N, kGnMaxRows);
-  const int bd = gn_block_dim(xp.C);
   const int h = xp.half;
-  const int res = h ? gn_resident(gn_apply_kernel<1, true>, bd, res_slot(1, 3, bd == 192))
-                    : gn_resident(gn_apply_kernel<1, false>, bd, res_slot(0, 3, bd == 192));
-  const GnGeom g = gn_geom(xp.C, (long long)xp.H * xp.W, res);
+  const int vec = h ? 8 : 4;
+  const int bd = gn_block_dim(xp.C, vec);
+  const bool extra = addend != nullptr || accumulate != 0;
+  int res;
+  if (extra) res = h ? gn_resident(gn_apply_kernel<1, true, 4>, bd, res_slot(1, 4, bd == 192))
+                     : gn_resident(gn_apply_kernel<1, false, 4>, bd, res_slot(0, 4, bd == 192));
+  else res = h ? gn_resident(gn_apply_kernel<1, true, 8>, bd, res_slot(1, 3, bd == 192))
+               : gn_resident(gn_apply_kernel<1, false, 8>, bd, res_slot(0, 3, bd == 192));
+  const GnGeom g = gn_geom(xp.C, vec, (long long)xp.H * xp.W, res);
+  const int lin = gn_lin(xp) && gn_lin(gy) && gn_lin(gx) && (!addend || gn_lin(*addend));
   ProfScope prof(1, (h ? 2.0 : 4.0) * gy.H * gy.W * gy.C * (1 + gy.N * (2 + (addend ? 1 : 0) + (accumulate ? 1 : 0))), s);
-  if (h)
-    gn_apply_kernel<1, true><<<g.nblk, g.block, 0, s>>>(
-        xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-        addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
-  else
-    gn_apply_kernel<1, false><<<g.nblk, g.block, 0, s>>>(
-        xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,
-        addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, 1);
+#define LOCO_GN_VJP(F16, RC)                                                                          \
+  gn_apply_kernel<1, F16, RC><<<g.nblk, g.block, 0, s>>>(                                             \
+      xp, 0, gy, pstats, stats, gamma, beta, eps, silu, round_out, addend ? addend->ptr : nullptr,    \
+      addend ? addend->sN : 0, addend ? addend->sH : 0, addend ? addend->sW : 0, accumulate, gx, lin)
+  if (h) { if (extra) LOCO_GN_VJP(true, 4); else LOCO_GN_VJP(true, 8); }
+  else { if (extra) LOCO_GN_VJP(false, 4); else LOCO_GN_VJP(false, 8); }
+#undef LOCO_GN_VJP
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

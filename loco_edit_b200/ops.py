@@ -279,6 +279,33 @@ def groupnorm_silu_vjp(xp, gy, gamma, beta, eps, silu):
     return gx
 
 
+def groupnorm_silu_fwd_ex(x, n_primal, gamma, beta, eps, silu, y=None, stats=None, stages=3):
+    """Typed GroupNorm(+SiLU) forward / JVP on an NHWC tensor of dtype float32 or float16."""
+    assert x.dtype in (torch.float32, torch.float16) and x.is_contiguous()
+    N, H, W_, Cc = x.shape
+    y = torch.empty_like(x) if y is None else y
+    stats = torch.empty(64 * N, dtype=torch.float64, device=x.device) if stats is None else stats
+    check(_lib.load().loco_groupnorm_silu_fwd_ex(ptr(x), int(x.dtype == torch.float16), N, H, W_, Cc, n_primal,
+                                                 ptr(_f32(gamma)), ptr(_f32(beta)), float(eps),
+                                                 1 if silu else 0, ptr(y), ptr(stats), stages, stream_ptr(x)),
+          "loco_groupnorm_silu_fwd_ex")
+    return y, stats
+
+
+def groupnorm_silu_vjp_ex(xp, gy, gamma, beta, eps, silu, addend=None, accumulate=False, gx=None, stats=None,
+                          stages=3):
+    assert gy.dtype in (torch.float32, torch.float16) and gy.is_contiguous() and xp.dtype == gy.dtype
+    K, H, W_, Cc = gy.shape
+    gx = torch.empty_like(gy) if gx is None else gx
+    stats = torch.empty(64 * (K + 1), dtype=torch.float64, device=gy.device) if stats is None else stats
+    check(_lib.load().loco_groupnorm_silu_vjp_ex(ptr(xp), int(gy.dtype == torch.float16), H, W_, Cc, ptr(gy), K,
+                                                 ptr(_f32(gamma)), ptr(_f32(beta)), float(eps),
+                                                 1 if silu else 0, ptr(addend), 1 if accumulate else 0, ptr(gx),
+                                                 ptr(stats), stages, stream_ptr(gy)),
+          "loco_groupnorm_silu_vjp_ex")
+    return gx, stats
+
+
 def attention_fwd(qkv, n_primal, head_ch=0):
     """head_ch = 0: one head, channels q|k|v (DDPM); > 0: per-head q|k|v (guided-diffusion legacy)."""
     qkv = _f32(qkv)

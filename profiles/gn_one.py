@@ -1,9 +1,9 @@
-"""One GroupNorm+SiLU site, back-to-back launches (for ncu captures): [N, H, W, C] with 1 primal row
-and N-1 tangent rows (N >= 2), or a plain forward batch (--fwd).
-usage: python profiles/gn_one.py N H C [--fwd]"""
+"""One GroupNorm+SiLU site, a few back-to-back launches of each pass (for ncu captures).
+usage: python profiles/gn_one.py N H C [fwd|jvp|vjp] [f32]
+  fwd: N primal rows (forward-only programs); jvp: 1 primal + N-1 tangent rows; vjp: N cotangent rows
+  (plain, then with addend + accumulate)."""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import torch
@@ -11,21 +11,18 @@ import torch
 from loco_edit_b200 import ops
 
 N, H, C = [int(a) for a in sys.argv[1:4]]
-fwd = "--fwd" in sys.argv
+mode = sys.argv[4] if len(sys.argv) > 4 else "jvp"
+dt = torch.float32 if "f32" in sys.argv else torch.float16
 dev = torch.device("cuda:0")
-x = torch.randn(N, H, H, C, device=dev)
 gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-for _ in range(3):
-    ops.groupnorm_silu_fwd(x, N if fwd else 1, gamma, beta, 1e-6, True)
+x = torch.randn(N, H, H, C, device=dev).to(dt)
+y = torch.empty_like(x)
+for _ in range(4):
+    if mode == "vjp":
+        xp = x[:1].contiguous()
+        _, st = ops.groupnorm_silu_vjp_ex(xp, x, gamma, beta, 1e-6, True, gx=y)
+        ops.groupnorm_silu_vjp_ex(xp, x, gamma, beta, 1e-6, True, addend=x, accumulate=True, gx=y, stats=st, stages=2)
+    else:
+        ops.groupnorm_silu_fwd_ex(x, N if mode == "fwd" else 1, gamma, beta, 1e-6, True, y=y)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 20
-e0.record()
-for _ in range(reps):
-    ops.groupnorm_silu_fwd(x, N if fwd else 1, gamma, beta, 1e-6, True)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-byts = x.numel() * 4 * 3          # statistics pass reads once, apply pass reads + writes
-print(f"GroupNorm+SiLU {'fwd' if fwd else 'jvp'} [{N},{H},{H},{C}]: {ms*1e3:.1f} us (stats memset + stats + apply), "
-      f"{byts/ms/1e6:.0f} GB/s algorithmic")
+print("done")

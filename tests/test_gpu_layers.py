@@ -161,6 +161,50 @@ def test_groupnorm_silu_vjp(dev, C, H, silu):
     assert e < 1e-5
 
 
+@pytest.mark.parametrize("C,H,silu", [(128, 32, True), (256, 16, True), (384, 16, True), (512, 8, False),
+                                      (768, 8, True), (1024, 8, True)])
+def test_groupnorm_silu_fp16_fwd_jvp_vjp(dev, C, H, silu):
+    """The fp16-storage GroupNorm kernels (16-byte vectors; forward-only, JVP and VJP variants,
+    incl. addend + accumulate) against fp64 on the same fp16-representable inputs: the only error
+    left is the fp16 rounding of the stored result (2^-11 relative per element)."""
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(C * 7 + H)
+    k = 7                                     # > one register chunk of rows
+    h16 = lambda t: t.half().to(dev)
+    x = h16(torch.randn(1, C, H, H, generator=g) * 1.5 + 0.3)
+    dx = h16(torch.randn(k, C, H, H, generator=g))
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev)
+    eps = 1e-6
+    f = lambda z: _gn_silu(z, gamma.double(), beta.double(), eps, silu)
+    yref = f(x.double())
+    dys = [torch.func.jvp(f, (x.double(),), (dx[j:j + 1].double(),))[1] for j in range(k)]
+    ref = torch.cat([yref] + dys, 0)
+    y, _ = ops.groupnorm_silu_fwd_ex(nhwc(torch.cat([x, dx], 0)), 1, gamma, beta, eps, silu)
+    assert y.dtype == torch.float16
+    e0, e1 = rel_err(nchw(y.float())[:1], ref[:1]), rel_err(nchw(y.float())[1:], ref[1:])
+    # forward-only batch (the 16-byte kernel with the folded affine)
+    xb = h16(torch.randn(5, C, H, H, generator=g) * 2.0 - 0.5)
+    yb, _ = ops.groupnorm_silu_fwd_ex(nhwc(xb), 5, gamma, beta, eps, silu)
+    e2 = rel_err(nchw(yb.float()), f(xb.double()))
+    # VJP, with and without addend / accumulate
+    gy = h16(torch.randn(k, C, H, H, generator=g))
+    add = h16(torch.randn(k, C, H, H, generator=g))
+    acc = h16(torch.randn(k, C, H, H, generator=g))
+    xd = x.double().requires_grad_(True)
+    yy = _gn_silu(xd, gamma.double(), beta.double(), eps, silu)
+    gref = torch.cat([torch.autograd.grad(yy, xd, gy[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
+    gx, _ = ops.groupnorm_silu_vjp_ex(nhwc(x), nhwc(gy), gamma, beta, eps, silu)
+    e3 = rel_err(nchw(gx.float()), gref)
+    gx2 = nhwc(acc).clone()
+    ops.groupnorm_silu_vjp_ex(nhwc(x), nhwc(gy), gamma, beta, eps, silu, addend=nhwc(add), accumulate=True, gx=gx2)
+    e4 = rel_err(nchw(gx2.float()), gref + add.double() + acc.double())
+    torch.cuda.synchronize()
+    print(f"gn fp16 C={C} H={H} silu={silu}: primal {e0:.2e} tangent {e1:.2e} fwd batch {e2:.2e} vjp {e3:.2e} "
+          f"vjp+addend+acc {e4:.2e}")
+    assert max(e0, e1, e2, e3, e4) < 6e-4
+
+
 def _attn_core(qkv):   # qkv [N, T, 3C] -> o [N, T, C]   (reference ddpm/diffusion.py:950-962)
     C = qkv.shape[-1] // 3
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
