@@ -167,7 +167,7 @@ int attention_init() {
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(batched_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
   LOCO_CHECK_CUDA(cudaFuncSetAttribute(softmax_lin_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-  return 0;
+  return attention_tc_init();
 }
 
 int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
@@ -225,6 +225,8 @@ int attention_forward(View qkv, int n_primal, int head_ch, float* S, View o, cud
   LOCO_REQUIRE(o.C == C && o.N == N, "attention_forward: shape mismatch");
   LOCO_REQUIRE(nt == 0 || n_primal == 1, "attention_forward: tangents need exactly one primal row");
   LOCO_REQUIRE(head_ch <= 0 || C % head_ch == 0, "attention_forward: %d channels, heads of %d", C, head_ch);
+  if (attention_tc_eligible(T, C, head_ch) && !qkv.half && !o.half)
+    return attention_forward_tc(qkv, n_primal, head_ch, S, o, s);
   const HeadGeom G = head_geom(C, head_ch);
   const int Hh = G.heads, D = G.dh;
   const float scale = G.scale;
@@ -271,6 +273,8 @@ int attention_vjp(View go, View qkv0, int head_ch, const float* P0, float* gP, V
   const int T = qkv0.H * qkv0.W;
   const int K = go.N;
   LOCO_REQUIRE(go.C == C && gqkv.C == 3 * C && gqkv.N == K, "attention_vjp: shape mismatch");
+  if (attention_tc_eligible(T, C, head_ch) && !go.half && !qkv0.half && !gqkv.half)
+    return attention_vjp_tc(go, qkv0, head_ch, P0, gP, gqkv, s);
   const HeadGeom G = head_geom(C, head_ch);
   const int Hh = G.heads, D = G.dh;
   const float scale = G.scale;

@@ -35,4 +35,13 @@ int attention_forward(View qkv, int n_primal, int head_ch, float* S, View o, cud
 int attention_vjp(View go, View qkv0, int head_ch, const float* P0, float* gP, View gqkv,
                   cudaStream_t s);
 
+// Fused tcgen05 path (attention_tc.cu): taken by attention_forward / attention_vjp whenever the
+// shape is eligible (T <= 256 tokens, T % 32 == 0, head width D % 32 == 0, D <= 512, fp32 tensors);
+// LOCO_ATTN_TC=0 keeps the CUDA-core path above (profiling aid).
+bool attention_tc_enabled();
+bool attention_tc_eligible(int T, int C, int head_ch);
+int attention_tc_init();
+int attention_forward_tc(View qkv, int n_primal, int head_ch, float* S, View o, cudaStream_t s);
+int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP, View gqkv, cudaStream_t s);
+
 }  // namespace loco

@@ -35,6 +35,8 @@ def report(name, shape, us, nbytes):
 
 
 sites = [(256, 128), (128, 128), (64, 256), (32, 256), (16, 512)]
+if os.environ.get("SITES"):      # e.g. SITES=248x128,256x128
+    sites = [tuple(int(v) for v in t.split("x")) for t in os.environ["SITES"].split(",")]
 dt = torch.float32 if os.environ.get("HALF", "1") == "0" else torch.float16
 es = 4 if dt == torch.float32 else 2
 for H, C in sites:

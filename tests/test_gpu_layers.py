@@ -212,30 +212,43 @@ def _attn_core(qkv):   # qkv [N, T, 3C] -> o [N, T, C]   (reference ddpm/diffusi
     return torch.bmm(w, v)
 
 
-@pytest.mark.parametrize("T,C", [(64, 128), (256, 512)])
+def _tf32(x):
+    """Round to the nearest tf32-representable fp32 value (what the conv epilogues store)."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("T,C", [(64, 128), (256, 512), (128, 256), (256, 128)])
 def test_attention_fwd_jvp_vjp(dev, T, C):
+    """Fused tcgen05 attention (kind::tf32) against fp64 on tf32-representable operands: the
+    products are then exact, what remains is the tf32 rounding of the probabilities / of gS that
+    feed the second product and of the stored results (2^-11 relative each)."""
     from loco_edit_b200 import ops
     g = torch.Generator().manual_seed(T + C)
     k = 2
-    qkv = torch.randn(1, T, 3 * C, generator=g).to(dev)
-    dq = torch.randn(k, T, 3 * C, generator=g).to(dev)
+    qkv = _tf32(torch.randn(1, T, 3 * C, generator=g)).to(dev)
+    dq = _tf32(torch.randn(k, T, 3 * C, generator=g)).to(dev)
     oref = _attn_core(qkv.double())
     dref = torch.cat([torch.func.jvp(_attn_core, (qkv.double(),), (dq[j:j + 1].double(),))[1] for j in range(k)], 0)
     o, S = ops.attention_fwd(torch.cat([qkv, dq], 0).contiguous(), 1)
     torch.cuda.synchronize()
     # the stored o is rounded to tf32 for the following tensor-core projection: 2^-11 relative
-    assert rel_err(o[:1], oref) < 5e-4 and rel_err(o[1:], dref) < 5e-4
-    go = torch.randn(k, T, C, generator=g).to(dev)
+    e0, e1 = rel_err(o[:1], oref), rel_err(o[1:], dref)
+    print(f"attention T={T} C={C}: primal rel_err {e0:.2e} tangent {e1:.2e}")
+    assert e0 < 5e-4 and e1 < 1e-3
+    Sref = torch.softmax(torch.bmm(qkv[..., :C].double(), qkv[..., C:2 * C].double().transpose(1, 2)) * C ** -0.5, 2)
+    assert rel_err(S[:1], Sref) < 5e-4
+    go = _tf32(torch.randn(k, T, C, generator=g)).to(dev)
     qd = qkv.double().requires_grad_(True)
     od = _attn_core(qd)
     gref = torch.cat([torch.autograd.grad(od, qd, go[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
     gq = ops.attention_vjp(go, qkv, S[0].contiguous())
     torch.cuda.synchronize()
     e = rel_err(gq, gref)
-    print(f"attention T={T} C={C}: vjp rel_err {e:.2e}")
-    assert e < 5e-4
+    print(f"attention T={T} C={C}: vjp rel_err {e:.2e} (q {rel_err(gq[..., :C], gref[..., :C]):.2e} "
+          f"k {rel_err(gq[..., C:2 * C], gref[..., C:2 * C]):.2e} v {rel_err(gq[..., 2 * C:], gref[..., 2 * C:]):.2e})")
+    assert e < 1e-3
     # batch of primal rows only
-    qb = torch.randn(3, T, 3 * C, generator=g).to(dev)
+    qb = _tf32(torch.randn(3, T, 3 * C, generator=g)).to(dev)
     ob, _ = ops.attention_fwd(qb, 3)
     assert rel_err(ob, _attn_core(qb.double())) < 5e-4
 
