@@ -27,6 +27,7 @@
 // owns one query / key row, so row reductions need no shuffles), 4 = TMA producer, 5 = MMA issuer.
 #include "attention.cuh"
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,16 +51,22 @@ struct AttnTcParams {
   CUtensorMap go_mn;     // VJP: cotangent of o, MN-major chunks
   CUtensorMap gs_map;    // VJP kernel 2: gS scratch read MN-major, dims (T, T, heads * K), box (32, 128, 1), 32B-atom swizzle
   CUtensorMap p_map_mn;  // VJP kernel 2: P0 read MN-major (32B-atom swizzle)
+  CUtensorMap o_st;      // store map of the output rows (o, or gqkv in the VJP): dims (C_out, T, rows), box (32, 32, 1)
+  CUtensorMap p_st;      // store map of the probabilities (forward: S; VJP kernel 1: gS scratch), box (32, 32, 1)
   int T, D, heads;
   int qo, ko, vo, hs;    // channel offsets of q / k / v inside a token row, channel stride of a head
   int n_primal;          // forward kernel: batch rows; tangent kernel: tangent row r is batch row n_primal + r
   float scale;
   int debug;
-  float* S;              // probabilities [rows][heads][T][T] (forward: written; tangent / VJP: P0 = row 0)
-  float* gS;             // VJP scratch [K][heads][T][T]
-  float* o;              // forward / tangent: o rows; VJP: gqkv rows
-  long long o_sN, o_sT;  // batch-row and token strides of `o` (floats)
+  unsigned long long* stamps;   // LOCO_ATTN_DEBUG=9: %globaltimer stamps of CTA 0 (profiling aid)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LOCO_STAMP(i) do { if (p.stamps && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.stamps[i] = gtime(); } while (0)
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2) {
@@ -67,6 +74,35 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// TMA stores (shared -> global, bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread: a row warp spends its time on
+// TMEM round trips, so it fetches two probability slabs per trip
+__device__ __forceinline__ void tmem_ld_32x32_x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
       : "memory");
 }
 
@@ -232,55 +268,92 @@ __device__ __forceinline__ void load_slabs(const Smem& sm, const CUtensorMap* m,
 // byte offset of the 16-byte group c4 (4 keys) of `row` inside a 128B-swizzled slab
 __device__ __forceinline__ int swz(int row, int c4) { return row * 128 + ((c4 ^ (row & 7)) << 4); }
 
-// out[row][0..D) = round_tf32(TMEM row), 32 columns at a time
-__device__ __forceinline__ void store_rows(uint32_t trow, int D, float* dst, bool valid) {
-  for (int ch = 0; ch < D / 32; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + ch * 32, r);
+// The 32 rows of this warp of a [128 x D] TMEM tile -> global through `map` (channel c0, row r0, matrix n):
+// 64 columns per TMEM round trip, tf32-rounded, written into the warp's 32-row window of staging slabs
+// [slab0, slab0 + nslab) of the probability buffer (128B-swizzled like any other box) and pushed out
+// by 32 x 32 TMA stores (per-thread scattered stores of 2 KB rows cost 11 of the kernel's 33 us).
+__device__ __forceinline__ void store_rows(const Smem& sm, uint32_t trow, int D, const CUtensorMap* map, int c0,
+                                           int r0, int n, int warp, int lane, int slab0, int nslab) {
+  const int row = warp * 32 + lane;
+  const int ngroups = nslab / 2;                 // bulk groups (of two slabs) that may be in flight
+  for (int c = 0; c < D / 64; ++c) {
+    uint32_t r[64];
+    tmem_ld_32x32_x64(trow + c * 64, r);
+    if (c >= ngroups) {                          // the slabs about to be overwritten have been read
+      if (lane == 0) { if (ngroups >= 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); }
+      __syncwarp();
+    }
     tmem_ld_wait();
-    if (valid) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint8_t* slab = sm.P + (slab0 + (2 * c + h) % nslab) * kTcSlab;
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4)
-        *reinterpret_cast<float4*>(dst + ch * 32 + c4 * 4) =
-            make_float4(round_tf32(__uint_as_float(r[4 * c4])), round_tf32(__uint_as_float(r[4 * c4 + 1])),
-                        round_tf32(__uint_as_float(r[4 * c4 + 2])), round_tf32(__uint_as_float(r[4 * c4 + 3])));
+        *reinterpret_cast<float4*>(slab + swz(row, c4)) =
+            make_float4(round_tf32(__uint_as_float(r[32 * h + 4 * c4])), round_tf32(__uint_as_float(r[32 * h + 4 * c4 + 1])),
+                        round_tf32(__uint_as_float(r[32 * h + 4 * c4 + 2])), round_tf32(__uint_as_float(r[32 * h + 4 * c4 + 3])));
     }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        tma_store_3d(map, sm.P + (slab0 + (2 * c + h) % nslab) * kTcSlab + warp * 4096, c0 + (2 * c + h) * 32, r0 + warp * 32, n);
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+// the warp's 32 rows of the first T / 32 probability slabs -> matrix `mat` of `map` (rows r0 + 32 warp ..)
+__device__ __forceinline__ void store_slabs(const Smem& sm, const CUtensorMap* map, int T, int r0, int mat, int warp,
+                                            int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    for (int sl = 0; sl < T / 32; ++sl)
+      tma_store_3d(map, sm.P + sl * kTcSlab + warp * 4096, sl * 32, r0 + warp * 32, mat);
+    tma_store_commit();
   }
 }
 
-// X (TMEM row, T columns) -> scale * P0 o (X - sum_j P0 X) written over P0 in the slabs (tf32-rounded),
-// optionally also to a global row
-__device__ __forceinline__ void linearise_row(const Smem& sm, uint32_t trow, int T, int row, float scale,
-                                              float* grow) {
+// X (TMEM row, T columns) -> scale * P0 o (X - sum_j P0 X) written over P0 in the slabs (tf32-rounded)
+__device__ __forceinline__ void linearise_row(const Smem& sm, uint32_t trow, int T, int row, float scale) {
   float dot = 0.f;
-  for (int ch = 0; ch < T / 32; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + ch * 32, r);
+  for (int c = 0; c < T / 64; ++c) {
+    uint32_t r[64];
+    tmem_ld_32x32_x64(trow + c * 64, r);
     tmem_ld_wait();
-    const uint8_t* slab = sm.P + ch * kTcSlab;
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 p = *reinterpret_cast<const float4*>(slab + swz(row, c4));
-      dot += p.x * __uint_as_float(r[4 * c4]) + p.y * __uint_as_float(r[4 * c4 + 1]) +
-             p.z * __uint_as_float(r[4 * c4 + 2]) + p.w * __uint_as_float(r[4 * c4 + 3]);
+    for (int h = 0; h < 2; ++h) {
+      const uint8_t* slab = sm.P + (2 * c + h) * kTcSlab;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 p = *reinterpret_cast<const float4*>(slab + swz(row, c4));
+        dot += p.x * __uint_as_float(r[32 * h + 4 * c4]) + p.y * __uint_as_float(r[32 * h + 4 * c4 + 1]) +
+               p.z * __uint_as_float(r[32 * h + 4 * c4 + 2]) + p.w * __uint_as_float(r[32 * h + 4 * c4 + 3]);
+      }
     }
   }
-  for (int ch = 0; ch < T / 32; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + ch * 32, r);
+  for (int c = 0; c < T / 64; ++c) {
+    uint32_t r[64];
+    tmem_ld_32x32_x64(trow + c * 64, r);
     tmem_ld_wait();
-    uint8_t* slab = sm.P + ch * kTcSlab;
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      float4* pp = reinterpret_cast<float4*>(slab + swz(row, c4));
-      const float4 p = *pp;
-      float4 v;
-      v.x = round_tf32(scale * p.x * (__uint_as_float(r[4 * c4]) - dot));
-      v.y = round_tf32(scale * p.y * (__uint_as_float(r[4 * c4 + 1]) - dot));
-      v.z = round_tf32(scale * p.z * (__uint_as_float(r[4 * c4 + 2]) - dot));
-      v.w = round_tf32(scale * p.w * (__uint_as_float(r[4 * c4 + 3]) - dot));
-      *pp = v;
-      if (grow) *reinterpret_cast<float4*>(grow + ch * 32 + c4 * 4) = v;
+    for (int h = 0; h < 2; ++h) {
+      uint8_t* slab = sm.P + (2 * c + h) * kTcSlab;
+      float4 pv[8];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) pv[c4] = *reinterpret_cast<const float4*>(slab + swz(row, c4));
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 p = pv[c4];
+        float4 v;
+        v.x = round_tf32(scale * p.x * (__uint_as_float(r[32 * h + 4 * c4]) - dot));
+        v.y = round_tf32(scale * p.y * (__uint_as_float(r[32 * h + 4 * c4 + 1]) - dot));
+        v.z = round_tf32(scale * p.z * (__uint_as_float(r[32 * h + 4 * c4 + 2]) - dot));
+        v.w = round_tf32(scale * p.w * (__uint_as_float(r[32 * h + 4 * c4 + 3]) - dot));
+        *reinterpret_cast<float4*>(slab + swz(row, c4)) = v;
+      }
     }
   }
 }
@@ -295,7 +368,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, hd = blockIdx.y, n = blockIdx.z;
   const int T = p.T, D = p.D;
+  LOCO_STAMP(0);
   const uint32_t tmem = setup(sm, warp);
+  LOCO_STAMP(1);
   const int cq = hd * p.hs + p.qo, ck = hd * p.hs + p.ko, cv = hd * p.hs + p.vo;
   if (warp == 4) {
     if (lane == 0) {
@@ -316,52 +391,71 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   } else {
     const int row = threadIdx.x;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool valid = q0 + row < T;
     mbar_wait(sm.s_ready, 0);
     tc_fence_after();
+    LOCO_STAMP(2);
     const float sc = p.scale * kLog2e;
     float mx = -INFINITY;
-    for (int ch = 0; ch < T / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld_32x32(trow + ch * 32, r);
+    for (int c = 0; c < T / 64; ++c) {
+      uint32_t r[64];
+      tmem_ld_32x32_x64(trow + c * 64, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
     }
+    LOCO_STAMP(7);
+    // unnormalised exponentials go to the slabs, the row is rescaled in place once its sum is known
     float sum = 0.f;
-    for (int ch = 0; ch < T / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld_32x32(trow + ch * 32, r);
+    const float off = mx * sc;
+    for (int c = 0; c < T / 64; ++c) {
+      uint32_t r[64];
+      tmem_ld_32x32_x64(trow + c * 64, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum += exp2f((__uint_as_float(r[i]) - mx) * sc);
-    }
-    const float inv = 1.0f / sum;
-    float* Srow = p.S + (((long long)n * p.heads + hd) * T + q0 + row) * T;
-    for (int ch = 0; ch < T / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld_32x32(trow + ch * 32, r);
-      tmem_ld_wait();
-      uint8_t* slab = sm.P + ch * kTcSlab;
+      for (int h = 0; h < 2; ++h) {
+        uint8_t* slab = sm.P + (2 * c + h) * kTcSlab;
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        float4 v;
-        v.x = round_tf32(exp2f((__uint_as_float(r[4 * c4]) - mx) * sc) * inv);
-        v.y = round_tf32(exp2f((__uint_as_float(r[4 * c4 + 1]) - mx) * sc) * inv);
-        v.z = round_tf32(exp2f((__uint_as_float(r[4 * c4 + 2]) - mx) * sc) * inv);
-        v.w = round_tf32(exp2f((__uint_as_float(r[4 * c4 + 3]) - mx) * sc) * inv);
-        *reinterpret_cast<float4*>(slab + swz(row, c4)) = v;
-        if (valid) *reinterpret_cast<float4*>(Srow + ch * 32 + c4 * 4) = v;
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 v;
+          v.x = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4]), sc, -off));
+          v.y = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 1]), sc, -off));
+          v.z = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 2]), sc, -off));
+          v.w = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 3]), sc, -off));
+          sum += (v.x + v.y) + (v.z + v.w);
+          *reinterpret_cast<float4*>(slab + swz(row, c4)) = v;
+        }
       }
     }
+    const float inv = 1.0f / sum;
+    LOCO_STAMP(8);
+    for (int sl = 0; sl < T / 32; ++sl) {
+      uint8_t* slab = sm.P + sl * kTcSlab;
+      float4 v[8];                 // the loads of a slab row first: their latencies overlap
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) v[c4] = *reinterpret_cast<const float4*>(slab + swz(row, c4));
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        v[c4].x = round_tf32(v[c4].x * inv); v[c4].y = round_tf32(v[c4].y * inv);
+        v[c4].z = round_tf32(v[c4].z * inv); v[c4].w = round_tf32(v[c4].w * inv);
+        *reinterpret_cast<float4*>(slab + swz(row, c4)) = v[c4];
+      }
+    }
+    LOCO_STAMP(9);
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(sm.p_ready);
+    store_slabs(sm, &p.p_st, T, q0, n * p.heads + hd, warp, lane);     // P0 for the tangent / cotangent kernels
+    LOCO_STAMP(3);
     mbar_wait(sm.o_ready, 0);
     tc_fence_after();
-    store_rows(trow, D, p.o + (long long)n * p.o_sN + (long long)(q0 + row) * p.o_sT + hd * D, valid);
+    LOCO_STAMP(4);
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    store_rows(sm, trow, D, &p.o_st, hd * D, q0, n, warp, lane, 0, 8);
+    LOCO_STAMP(5);
   }
   teardown(tmem, warp);
+  LOCO_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,17 +499,16 @@ attn_jvp_tc_kernel(const __grid_constant__ AttnTcParams p) {
   } else {
     const int row = threadIdx.x;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool valid = q0 + row < T;
     mbar_wait(sm.p0_full, 0);
     mbar_wait(sm.s_ready, 0);
     tc_fence_after();
-    linearise_row(sm, trow, T, row, p.scale, nullptr);
+    linearise_row(sm, trow, T, row, p.scale);
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(sm.p_ready);
     mbar_wait(sm.o_ready, 0);
     tc_fence_after();
-    store_rows(trow, D, p.o + (long long)n * p.o_sN + (long long)(q0 + row) * p.o_sT + hd * D, valid);
+    store_rows(sm, trow, D, &p.o_st, hd * D, q0, n, warp, lane, 0, 8);
   }
   teardown(tmem, warp);
 }
@@ -452,18 +545,19 @@ attn_vjp1_tc_kernel(const __grid_constant__ AttnTcParams p) {
   } else {
     const int row = threadIdx.x;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool valid = q0 + row < T;
     mbar_wait(sm.p0_full, 0);
     mbar_wait(sm.s_ready, 0);
     tc_fence_after();
-    float* grow = valid ? p.gS + (((long long)r * p.heads + hd) * T + q0 + row) * T : nullptr;
-    linearise_row(sm, trow, T, row, p.scale, grow);
+    linearise_row(sm, trow, T, row, p.scale);
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(sm.p_ready);
+    store_slabs(sm, &p.p_st, T, q0, r * p.heads + hd, warp, lane);     // gS for kernel 2
     mbar_wait(sm.o_ready, 0);
     tc_fence_after();
-    store_rows(trow, D, p.o + (long long)r * p.o_sN + (long long)(q0 + row) * p.o_sT + cq, valid);
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    store_rows(sm, trow, D, &p.o_st, cq, q0, r, warp, lane, 0, 8);
   }
   teardown(tmem, warp);
 }
@@ -515,18 +609,16 @@ attn_vjp2_tc_kernel(const __grid_constant__ AttnTcParams p) {
       }
     }
   } else {
-    const int row = threadIdx.x;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool valid = k0 + row < T;
-    float* base = p.o + (long long)r * p.o_sN + (long long)(k0 + row) * p.o_sT;
     mbar_wait(sm.o_ready, 0);
     tc_fence_after();
-    store_rows(trow, D, base + cv, valid);
+    // staging in slabs 4..7: slabs 0..3 are being refilled for the second pass
+    store_rows(sm, trow, D, &p.o_st, cv, k0, r, warp, lane, 4, 4);
     tc_fence_before();
     mbar_arrive(sm.t_free);
     mbar_wait(sm.o_ready, 1);
     tc_fence_after();
-    store_rows(trow, D, base + ck, valid);
+    store_rows(sm, trow, D, &p.o_st, ck, k0, r, warp, lane, 4, 4);
   }
   teardown(tmem, warp);
 }
@@ -550,12 +642,12 @@ EncodeTiledFn encode_fn() {
 }
 // K-major rows of a [N][T][C] fp32 tensor (token pitch sT, row pitch sN floats): dims (C, T, N), box (32, 128, 1)
 int encode_rows_k(CUtensorMap* m, const float* base, int C, int T, int N, long long sT, long long sN,
-                  bool mn_swizzle = false) {
+                  bool mn_swizzle = false, int box_rows = 128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return 3;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)N};
   cuuint64_t strides[2] = {(cuuint64_t)sT * 4, (cuuint64_t)sN * 4};
-  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -596,7 +688,7 @@ bool attention_tc_enabled() {
 
 bool attention_tc_eligible(int T, int C, int head_ch) {
   const int D = head_ch > 0 ? head_ch : C;
-  return attention_tc_enabled() && T % 32 == 0 && T >= 32 && T <= 256 && D % 32 == 0 && D >= 32 && D <= 512 &&
+  return attention_tc_enabled() && T % 64 == 0 && T >= 64 && T <= 256 && D % 64 == 0 && D >= 64 && D <= 512 &&
          C % 32 == 0;
 }
 
@@ -631,13 +723,26 @@ int attention_forward_tc(View qkv, int n_primal, int head_ch, float* S, View o, 
   fill_geom(P, T, C, head_ch);
   P.n_primal = n_primal;
   { const char* e = getenv("LOCO_ATTN_DEBUG"); P.debug = e ? atoi(e) : 0; }
-  P.S = S; P.o = o.ptr; P.o_sN = o.sN; P.o_sT = o.sW;
   LOCO_TRY(encode_rows_k(&P.qkv_k, qkv.ptr, qkv.C, T, N, qkv.sW, qkv.sN));
   LOCO_TRY(encode_rows_mn(&P.qkv_mn, qkv.ptr, qkv.C, T, N, qkv.sW, qkv.sN, P.D));
   LOCO_TRY(encode_rows_k(&P.p_map, S, T, T, P.heads * N, T, (long long)T * T));
+  LOCO_TRY(encode_rows_k(&P.p_st, S, T, T, P.heads * N, T, (long long)T * T, false, 32));
+  LOCO_TRY(encode_rows_k(&P.o_st, o.ptr, o.C, T, N, o.sW, o.sN, false, 32));
   const int qblocks = (T + 127) / 128;
+  static unsigned long long* stamps = nullptr;
+  if (P.debug == 9) {
+    if (!stamps) { LOCO_CHECK_CUDA(cudaMalloc(&stamps, 64 * sizeof(unsigned long long))); }
+    P.stamps = stamps;
+  }
   attn_fwd_tc_kernel<<<dim3(qblocks, P.heads, n_primal), kTcThreads, kTcSmem, s>>>(P);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  if (P.debug == 9) {
+    unsigned long long h[10];
+    LOCO_CHECK_CUDA(cudaStreamSynchronize(s));
+    LOCO_CHECK_CUDA(cudaMemcpy(h, stamps, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "attn_fwd stamps (ns from entry): setup %llu s_ready %llu [max %llu exp %llu norm %llu] softmax %llu o_ready %llu stored %llu end %llu\n",
+            h[1] - h[0], h[2] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0]);
+  }
   if (nt > 0) {
     attn_jvp_tc_kernel<<<dim3(qblocks, P.heads, nt), kTcThreads, kTcSmem, s>>>(P);
     count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
@@ -655,7 +760,6 @@ int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP
   AttnTcParams P;
   memset(&P, 0, sizeof(P));
   fill_geom(P, T, C, head_ch);
-  P.S = const_cast<float*>(P0); P.gS = gP; P.o = gqkv.ptr; P.o_sN = gqkv.sN; P.o_sT = gqkv.sW;
   LOCO_TRY(encode_rows_k(&P.qkv_k, qkv0.ptr, qkv0.C, T, 1, qkv0.sW, qkv0.sN));
   LOCO_TRY(encode_rows_mn(&P.qkv_mn, qkv0.ptr, qkv0.C, T, 1, qkv0.sW, qkv0.sN, P.D));
   LOCO_TRY(encode_rows_k(&P.p_map, P0, T, T, P.heads, T, (long long)T * T));
@@ -663,6 +767,8 @@ int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP
   LOCO_TRY(encode_rows_mn(&P.go_mn, go.ptr, go.C, T, K, go.sW, go.sN, P.D));
   LOCO_TRY(encode_rows_k(&P.gs_map, gP, T, T, P.heads * K, T, (long long)T * T, true));
   LOCO_TRY(encode_rows_k(&P.p_map_mn, P0, T, T, P.heads, T, (long long)T * T, true));
+  LOCO_TRY(encode_rows_k(&P.p_st, gP, T, T, P.heads * K, T, (long long)T * T, false, 32));
+  LOCO_TRY(encode_rows_k(&P.o_st, gqkv.ptr, gqkv.C, T, K, gqkv.sW, gqkv.sN, false, 32));
   const int qblocks = (T + 127) / 128;
   attn_vjp1_tc_kernel<<<dim3(qblocks, P.heads, K), kTcThreads, kTcSmem, s>>>(P);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
