@@ -468,17 +468,20 @@ def run_ours(args):
         conv_tflops = work[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         roof = {"bound": "tensor",
-                "kernel": "tcgen05 implicit-GEMM conv family (conv_gemm_tf32_pair_kernel = cta_group::2 halo "
-                          "variant on the >=64^2 layers, conv_gemm_tf32_kernel on the small ones)",
+                "kernel": "tcgen05 implicit-GEMM conv family, kind::f16 (fp16 operands, fp32 accumulation in TMEM): "
+                          "conv_gemm_tf32_pair_kernel<1,1> = cta_group::2 halo variant on the >=64^2 layers, "
+                          "conv_gemm_tf32_kernel<.,1,1> on the small ones (the kernel names keep their round-1 "
+                          "'tf32' stem; the template arguments select the fp16 instantiation)",
                 "achieved": conv_tflops,
                 "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                # dram__bytes_read+write of the dominant launch (CTA-pair halo variant, 3x3 128->128 at
-                # 256^2, 6 rows; algorithmic 403 MB) from the committed ncu --set full capture,
-                # profiles/r1_conv_pair_ncu_full_raw.csv
-                "traffic": 352.8e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 (116 GFLOP)",
+                # dram__bytes_read + dram__bytes_write of the dominant launch from the committed ncu --set full
+                # capture profiles/r2u_conv_pair_f16_jvp6_ncu_full_raw.csv (CTA-pair halo variant, 3x3 128->128
+                # at 256^2, 6 rows = primal + 5 tangents, fp16 in / out: algorithmic 100.7 MB in + 100.7 MB out;
+                # part of the output is still in L2 when the kernel ends)
+                "traffic": 161.6e6, "traffic_launch": "conv 3x3 128->128, 6 x 256x256 fp16 (116 GFLOP, 83.0 us under ncu)",
                 # same capture: sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active / _elapsed
-                "ncu_tensor_pipe_active_pct": 80.9, "ncu_tensor_pipe_elapsed_pct": 74.0,
-                "peak_source": pk_kind + " bf16 dense sustained (kernel runs kind::tf32: half the bf16 rate)",
+                "ncu_tensor_pipe_active_pct": 86.8, "ncu_tensor_pipe_elapsed_pct": 75.2,
+                "peak_source": pk_kind + " bf16 dense sustained (kind::f16 runs at the bf16 rate)",
                 "launches": int(nl[0]), "avg_launch_ms": ms[0] / max(1, nl[0]),
                 "flops_per_launch": work[0] / max(1, nl[0]),
                 "conv_ms_per_step": ms[0], "groupnorm_ms_per_step": ms[1],
@@ -578,7 +581,7 @@ def run_ours(args):
             "metric": "edits/sec (rank-5 @256^2, t=0.6T)", "value": value, "unit": "edits/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "batch edit (BASELINE config 2 shape): DDPM-256 (ddpm-ema-celebahq-256 arch, "
                                    "random init), %d image/mask pairs of 256x256 per step per GPU, each a full "
                                    "config-1 edit: rank 5 + null rank 5, N=12 power iterations, t=0.6T, "
@@ -587,6 +590,10 @@ def run_ours(args):
                        "fwd_equivalents_per_edit": EDIT_FWD_EQUIV,
                        "tflop_per_edit": EDIT_FWD_EQUIV * F_DDPM256 / 1e12,
                        "fwd_equivalents_executed": EDIT_FWD_EXECUTED,
+                       "arithmetic": "fp16 storage + tcgen05 kind::f16 products with fp32 accumulation for the convs "
+                                     "(tangent / cotangent rows range-scaled by powers of two), fp32 GroupNorm / "
+                                     "softmax / PMP / DDIM math, tf32 tcgen05 attention products; LOCO_FWD_FP16=0 "
+                                     "LOCO_JAC_FP16=0 select the round-1 tf32 programs",
                        "l2": "per-edit working set (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": "dp%d (independent images per rank, no collective)" % world},
             "achieved_tflops": value * EDIT_FWD_EXECUTED * F_DDPM256 / 1e12,

@@ -445,12 +445,27 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* pr0 = pbase + (long long)(q * 32 + pr) * p.block_n + cq * 4 + ch;
-            for (int sidx = 0; sidx < ksplit; ++sidx) {
+            // the loads of four slices are in flight together (one L2 round trip per four slices instead
+            // of one per slice: 16 slices took 7.5 of the kernel's 20 us), the sums keep their order
+            const long long sstride = (long long)kConvBlockM * p.block_n;
+            int sidx = 0;
+            for (; sidx + 4 <= ksplit; sidx += 4) {
+              float4 t[4][8];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  t[u][it] = __ldcg(reinterpret_cast<const float4*>(pr0 + (sidx + u) * sstride + (long long)(it * 4) * p.block_n));
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) { v[it].x += t[u][it].x; v[it].y += t[u][it].y; v[it].z += t[u][it].z; v[it].w += t[u][it].w; }
+            }
+            for (; sidx < ksplit; ++sidx) {
               float4 t[8];
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                t[it] = __ldcg(reinterpret_cast<const float4*>(
-                    pr0 + (long long)sidx * (kConvBlockM * p.block_n) + (long long)(it * 4) * p.block_n));
+                t[it] = __ldcg(reinterpret_cast<const float4*>(pr0 + sidx * sstride + (long long)(it * 4) * p.block_n));
 #pragma unroll
               for (int it = 0; it < 8; ++it) { v[it].x += t[it].x; v[it].y += t[it].y; v[it].z += t[it].z; v[it].w += t[it].w; }
             }
@@ -1650,6 +1665,9 @@ int conv_prepare(const ConvProblem& prob, ConvLaunch* L) {
       ks = sms / tiles;
       if (ks > 16) ks = 16;
       if (ks > kiters / 4) ks = kiters / 4;
+      // 1x1 convolutions have 4-16 K iterations: the partial-tile exchange costs more than the split
+      // saves (fp16 sweep, profiles/README.md: 512->512 at 16^2, 6 rows: 14.4 us split in two, 10.3 us whole)
+      if (p.ntaps == 1 && kiters < 32) ks = 1;
       if (ks < 1) ks = 1;
       while (ks > 1 && (long long)tiles * ks * kConvBlockM * p.block_n > prob.splitk_partial_floats) --ks;
     }
