@@ -247,6 +247,18 @@ int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int 
 int loco_attention_vjp(const float* go, int K, int T, int C, int head_ch, const float* qkv0,
                        const float* P0, float* gP, float* gqkv, void* stream);
 
+/* Cross-attention of image tokens to a fixed context (text-conditioned U-Nets; SD / IF twins of the
+ * path, src/modules/edit.py:636-674, 1286-1373 call diffusers' UNet2DConditionModel, whose attention
+ * processor computes softmax(q k^T / sqrt(d)) v with k, v = linear maps of encoder_hidden_states):
+ * q [N,Tq,C] in `heads` heads of C/heads channels; kv [Tk,2C] = K_c | V_c, Tk a multiple of 64 (<= 256)
+ * of which the first Tk_valid rows exist (the rest must be zero); S [N,heads,Tq,Tk] receives the
+ * probabilities; o [N,Tq,C].  Rows >= n_primal are tangents of row 0 (the context is a constant).
+ * VJP at the primal probabilities P0 [heads,Tq,Tk]: go [K,Tq,C] -> gq [K,Tq,C].  Fused tcgen05 kernels. */
+int loco_cross_attention_fwd(const float* q, int N, int Tq, int C, int n_primal, const float* kv, int Tk,
+                             int Tk_valid, int heads, float* S, float* o, void* stream);
+int loco_cross_attention_vjp(const float* go, int K, int Tq, int C, const float* kv, int Tk, int Tk_valid,
+                             int heads, const float* P0, float* gq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ PROTOTYPES = {
     "loco_groupnorm_silu_fwd_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
     "loco_groupnorm_silu_vjp_ex": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _F, _I, _P, _I, _P, _P, _I, _P]),
     "loco_attention_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "loco_cross_attention_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "loco_cross_attention_vjp": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
     "loco_attention_vjp": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

@@ -597,6 +597,24 @@ int loco_attention_fwd(const float* qkv, int N, int T, int C, int n_primal, int 
   View ov = make_view(o, N, 1, T, C);
   return attention_forward(q, n_primal, head_ch, S, ov, ST(stream));
 }
+int loco_cross_attention_fwd(const float* q, int N, int Tq, int C, int n_primal, const float* kv, int Tk,
+                             int Tk_valid, int heads, float* S, float* o, void* stream) {
+  ON_DEVICE_OF(q);
+  LOCO_TRY(require_device());
+  View qv = make_view(const_cast<float*>(q), N, 1, Tq, C);
+  View kvv = make_view(const_cast<float*>(kv), 1, 1, Tk, 2 * C);
+  View ov = make_view(o, N, 1, Tq, C);
+  return attention_cross_forward_tc(qv, kvv, n_primal, heads, Tk_valid, S, ov, ST(stream));
+}
+int loco_cross_attention_vjp(const float* go, int K, int Tq, int C, const float* kv, int Tk, int Tk_valid,
+                             int heads, const float* P0, float* gq, void* stream) {
+  ON_DEVICE_OF(go);
+  LOCO_TRY(require_device());
+  View g = make_view(const_cast<float*>(go), K, 1, Tq, C);
+  View kvv = make_view(const_cast<float*>(kv), 1, 1, Tk, 2 * C);
+  View gqv = make_view(gq, K, 1, Tq, C);
+  return attention_cross_vjp_tc(g, kvv, heads, Tk_valid, P0, gqv, ST(stream));
+}
 int loco_attention_vjp(const float* go, int K, int T, int C, int head_ch, const float* qkv0,
                        const float* P0, float* gP, float* gqkv, void* stream) {
   ON_DEVICE_OF(go);

@@ -43,5 +43,11 @@ bool attention_tc_eligible(int T, int C, int head_ch);
 int attention_tc_init();
 int attention_forward_tc(View qkv, int n_primal, int head_ch, float* S, View o, cudaStream_t s);
 int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP, View gqkv, cudaStream_t s);
+// Cross-attention to a fixed context (attention_tc.cu): q [N, Tq, C], kv [1, Tk, 2C] = K_c | V_c with
+// Tk a multiple of 64 (<= 256) of which Tk_valid rows exist, S [N, heads, Tq, Tk], o [N, Tq, C];
+// rows >= n_primal are tangents of row 0 (d/dq only).  VJP: go [K, Tq, C] -> gq [K, Tq, C].
+bool attention_cross_eligible(int Tk, int C, int heads);
+int attention_cross_forward_tc(View q, View kv, int n_primal, int heads, int Tk_valid, float* S, View o, cudaStream_t s);
+int attention_cross_vjp_tc(View go, View kv, int heads, int Tk_valid, const float* P0, View gq, cudaStream_t s);
 
 }  // namespace loco

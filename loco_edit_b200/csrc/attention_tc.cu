@@ -53,7 +53,11 @@ struct AttnTcParams {
   CUtensorMap p_map_mn;  // VJP kernel 2: P0 read MN-major (32B-atom swizzle)
   CUtensorMap o_st;      // store map of the output rows (o, or gqkv in the VJP): dims (C_out, T, rows), box (32, 32, 1)
   CUtensorMap p_st;      // store map of the probabilities (forward: S; VJP kernel 1: gS scratch), box (32, 32, 1)
-  int T, D, heads;
+  CUtensorMap kv_k;      // key / value source, K-major boxes (self-attention: = qkv_k; cross-attention: the context projections)
+  CUtensorMap kv_mn;     // key / value source, MN-major chunks
+  int T, D, heads;       // T = query tokens
+  int Tk, Tk_valid;      // key tokens (padded to a multiple of 64) and how many of them exist
+  int cross;             // cross-attention: keys / values are constants (no dk, dv terms; VJP returns gq only)
   int qo, ko, vo, hs;    // channel offsets of q / k / v inside a token row, channel stride of a head
   int n_primal;          // forward kernel: batch rows; tangent kernel: tangent row r is batch row n_primal + r
   float scale;
@@ -367,7 +371,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, hd = blockIdx.y, n = blockIdx.z;
-  const int T = p.T, D = p.D;
+  const int T = p.Tk, D = p.D;                 // everything below is indexed by keys
+  const int nkv = p.cross ? 0 : n;             // batch row of the key / value source
   LOCO_STAMP(0);
   const uint32_t tmem = setup(sm, warp);
   LOCO_STAMP(1);
@@ -375,8 +380,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   if (warp == 4) {
     if (lane == 0) {
       int it = 0;
-      produce_k(sm, it, &p.qkv_k, cq, q0, n, &p.qkv_k, ck, n, T, D / 32);
-      produce_mn(sm, it, &p.qkv_mn, cv / 32, 0, n, T / 16, D);
+      produce_k(sm, it, &p.qkv_k, cq, q0, n, &p.kv_k, ck, nkv, T, D / 32);
+      produce_mn(sm, it, &p.kv_mn, cv / 32, 0, nkv, T / 16, D);
     }
   } else if (warp == 5) {
     if (lane == 0) {
@@ -401,7 +406,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
       tmem_ld_32x32_x64(trow + c * 64, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 64; ++i)
+        if (c * 64 + i < p.Tk_valid) mx = fmaxf(mx, __uint_as_float(r[i]));     // padded keys do not exist
     }
     LOCO_STAMP(7);
     // unnormalised exponentials go to the slabs, the row is rescaled in place once its sum is known
@@ -421,6 +427,13 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
           v.y = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 1]), sc, -off));
           v.z = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 2]), sc, -off));
           v.w = ex2_approx(fmaf(__uint_as_float(r[32 * h + 4 * c4 + 3]), sc, -off));
+          const int col = c * 64 + 32 * h + 4 * c4;
+          if (col + 3 >= p.Tk_valid) {
+            if (col >= p.Tk_valid) v.x = 0.f;
+            if (col + 1 >= p.Tk_valid) v.y = 0.f;
+            if (col + 2 >= p.Tk_valid) v.z = 0.f;
+            v.w = 0.f;
+          }
           sum += (v.x + v.y) + (v.z + v.w);
           *reinterpret_cast<float4*>(slab + swz(row, c4)) = v;
         }
@@ -467,33 +480,37 @@ attn_jvp_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, hd = blockIdx.y, n = p.n_primal + blockIdx.z;
-  const int T = p.T, D = p.D;
+  const int T = p.Tk, D = p.D;
   const uint32_t tmem = setup(sm, warp);
   const int cq = hd * p.hs + p.qo, ck = hd * p.hs + p.ko, cv = hd * p.hs + p.vo;
   if (warp == 4) {
     if (lane == 0) {
       int it = 0;
       load_slabs(sm, &p.p_map, 0, T / 32, q0, hd);                               // P0 (primal row 0)
-      produce_k(sm, it, &p.qkv_k, cq, q0, n, &p.qkv_k, ck, 0, T, D / 32);        // dq k0^T
-      produce_k(sm, it, &p.qkv_k, cq, q0, 0, &p.qkv_k, ck, n, T, D / 32);        // q0 dk^T
-      produce_mn(sm, it, &p.qkv_mn, cv / 32, 0, 0, T / 16, D);                   // dP v0
-      mbar_wait(sm.aux, 0);                                                      // dP consumed
-      load_slabs(sm, &p.p_map, 0, T / 32, q0, hd);                               // P0 again
-      produce_mn(sm, it, &p.qkv_mn, cv / 32, 0, n, T / 16, D);                   // P0 dv
+      produce_k(sm, it, &p.qkv_k, cq, q0, n, &p.kv_k, ck, 0, T, D / 32);         // dq k0^T
+      if (!p.cross) produce_k(sm, it, &p.qkv_k, cq, q0, 0, &p.kv_k, ck, n, T, D / 32);   // q0 dk^T
+      produce_mn(sm, it, &p.kv_mn, cv / 32, 0, 0, T / 16, D);                    // dP v0
+      if (!p.cross) {
+        mbar_wait(sm.aux, 0);                                                    // dP consumed
+        load_slabs(sm, &p.p_map, 0, T / 32, q0, hd);                             // P0 again
+        produce_mn(sm, it, &p.kv_mn, cv / 32, 0, n, T / 16, D);                  // P0 dv
+      }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       int it = 0;
       mma_k(sm, it, tmem, T, D / 32, false);
-      mma_k(sm, it, tmem, T, D / 32, true);
+      if (!p.cross) mma_k(sm, it, tmem, T, D / 32, true);
       umma_commit(sm.s_ready);
       mbar_wait(sm.p_ready, 0);
       tc_fence_after();
       mma_mn(sm, it, tmem, T / 16, D, 0, 0, false);
-      umma_commit(sm.aux);
-      mbar_wait(sm.p0_full, 1);
-      tc_fence_after();
-      mma_mn(sm, it, tmem, T / 16, D, 0, 0, true);
+      if (!p.cross) {
+        umma_commit(sm.aux);
+        mbar_wait(sm.p0_full, 1);
+        tc_fence_after();
+        mma_mn(sm, it, tmem, T / 16, D, 0, 0, true);
+      }
       umma_commit(sm.o_ready);
     }
   } else {
@@ -522,15 +539,15 @@ attn_vjp1_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, hd = blockIdx.y, r = blockIdx.z;
-  const int T = p.T, D = p.D;
+  const int T = p.Tk, D = p.D;
   const uint32_t tmem = setup(sm, warp);
   const int cq = hd * p.hs + p.qo, ck = hd * p.hs + p.ko, cv = hd * p.hs + p.vo;
   if (warp == 4) {
     if (lane == 0) {
       int it = 0;
       load_slabs(sm, &p.p_map, 0, T / 32, q0, hd);
-      produce_k(sm, it, &p.go_k, hd * D, q0, r, &p.qkv_k, cv, 0, T, D / 32);     // gP = go v0^T
-      produce_mn(sm, it, &p.qkv_mn, ck / 32, 0, 0, T / 16, D);                   // gq = gS k0
+      produce_k(sm, it, &p.go_k, hd * D, q0, r, &p.kv_k, cv, 0, T, D / 32);      // gP = go v0^T
+      produce_mn(sm, it, &p.kv_mn, ck / 32, 0, 0, T / 16, D);                    // gq = gS k0
     }
   } else if (warp == 5) {
     if (lane == 0) {
@@ -552,7 +569,7 @@ attn_vjp1_tc_kernel(const __grid_constant__ AttnTcParams p) {
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(sm.p_ready);
-    store_slabs(sm, &p.p_st, T, q0, r * p.heads + hd, warp, lane);     // gS for kernel 2
+    if (!p.cross) store_slabs(sm, &p.p_st, T, q0, r * p.heads + hd, warp, lane);     // gS for kernel 2
     mbar_wait(sm.o_ready, 0);
     tc_fence_after();
     if (lane == 0) tma_store_wait_read<0>();
@@ -725,6 +742,7 @@ int attention_forward_tc(View qkv, int n_primal, int head_ch, float* S, View o, 
   { const char* e = getenv("LOCO_ATTN_DEBUG"); P.debug = e ? atoi(e) : 0; }
   LOCO_TRY(encode_rows_k(&P.qkv_k, qkv.ptr, qkv.C, T, N, qkv.sW, qkv.sN));
   LOCO_TRY(encode_rows_mn(&P.qkv_mn, qkv.ptr, qkv.C, T, N, qkv.sW, qkv.sN, P.D));
+  P.kv_k = P.qkv_k; P.kv_mn = P.qkv_mn; P.Tk = T; P.Tk_valid = T;
   LOCO_TRY(encode_rows_k(&P.p_map, S, T, T, P.heads * N, T, (long long)T * T));
   LOCO_TRY(encode_rows_k(&P.p_st, S, T, T, P.heads * N, T, (long long)T * T, false, 32));
   LOCO_TRY(encode_rows_k(&P.o_st, o.ptr, o.C, T, N, o.sW, o.sN, false, 32));
@@ -762,6 +780,7 @@ int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP
   fill_geom(P, T, C, head_ch);
   LOCO_TRY(encode_rows_k(&P.qkv_k, qkv0.ptr, qkv0.C, T, 1, qkv0.sW, qkv0.sN));
   LOCO_TRY(encode_rows_mn(&P.qkv_mn, qkv0.ptr, qkv0.C, T, 1, qkv0.sW, qkv0.sN, P.D));
+  P.kv_k = P.qkv_k; P.kv_mn = P.qkv_mn; P.Tk = T; P.Tk_valid = T;
   LOCO_TRY(encode_rows_k(&P.p_map, P0, T, T, P.heads, T, (long long)T * T));
   LOCO_TRY(encode_rows_k(&P.go_k, go.ptr, go.C, T, K, go.sW, go.sN));
   LOCO_TRY(encode_rows_mn(&P.go_mn, go.ptr, go.C, T, K, go.sW, go.sN, P.D));
@@ -773,6 +792,77 @@ int attention_vjp_tc(View go, View qkv0, int head_ch, const float* P0, float* gP
   attn_vjp1_tc_kernel<<<dim3(qblocks, P.heads, K), kTcThreads, kTcSmem, s>>>(P);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   attn_vjp2_tc_kernel<<<dim3(qblocks, P.heads, K), kTcThreads, kTcSmem, s>>>(P);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention of image tokens to a fixed context (text-conditioned U-Nets):
+//   o = softmax(q K_c^T / sqrt(D)) V_c,   K_c | V_c = projections of the prompt embedding, constants
+// of the Jacobian (d/dx only): the tangent rule is do = dP V_c with dS = dq K_c^T, the VJP is
+// gq = gS K_c.  Same kernels as above with the key / value source decoupled from the query tensor:
+// any number of query tokens, up to 256 (padded) keys of which Tk_valid exist.
+//   q: [N, Tq, C] (heads of D = C / heads channels), kv: [1, Tk, 2C] (K_c | V_c, rows >= Tk_valid zero),
+//   S: [N, heads, Tq, Tk] probabilities (P0 = row 0 for the tangent / cotangent rules), o: [N, Tq, C].
+// ------------------------------------------------------------------------------------------------
+bool attention_cross_eligible(int Tk, int C, int heads) {
+  if (heads < 1 || C % heads != 0) return false;
+  const int D = C / heads;
+  return Tk % 64 == 0 && Tk >= 64 && Tk <= 256 && D % 64 == 0 && D <= 512;
+}
+
+namespace {
+int fill_cross(AttnTcParams& P, View q, View kv, int heads, int Tk_valid) {
+  const int C = q.C, Tq = q.H * q.W, Tk = kv.H * kv.W;
+  LOCO_REQUIRE(attention_cross_eligible(Tk, C, heads), "cross-attention: unsupported shape (Tk=%d C=%d heads=%d)", Tk, C, heads);
+  LOCO_REQUIRE(kv.C == 2 * C && kv.N == 1 && Tk_valid >= 1 && Tk_valid <= Tk, "cross-attention: kv must be [1, Tk, 2C]");
+  LOCO_REQUIRE(!q.half && !kv.half && aligned16(q.ptr) && aligned16(kv.ptr) && q.sW % 4 == 0 && q.sN % 4 == 0 && kv.sW % 4 == 0,
+               "cross-attention: fp32, 16-byte aligned tensors expected");
+  memset(&P, 0, sizeof(P));
+  P.T = Tq; P.Tk = Tk; P.Tk_valid = Tk_valid; P.cross = 1;
+  P.heads = heads; P.D = C / heads; P.qo = 0; P.ko = 0; P.vo = C; P.hs = P.D;
+  P.scale = 1.0f / sqrtf((float)P.D);
+  LOCO_TRY(encode_rows_k(&P.kv_k, kv.ptr, kv.C, Tk, 1, kv.sW, kv.sN));
+  LOCO_TRY(encode_rows_mn(&P.kv_mn, kv.ptr, kv.C, Tk, 1, kv.sW, kv.sN, P.D));
+  return 0;
+}
+}  // namespace
+
+int attention_cross_forward_tc(View q, View kv, int n_primal, int heads, int Tk_valid, float* S, View o, cudaStream_t s) {
+  const int N = q.N, nt = N - n_primal, Tq = q.H * q.W, Tk = kv.H * kv.W;
+  LOCO_REQUIRE(nt == 0 || n_primal == 1, "cross-attention: tangents need exactly one primal row");
+  LOCO_REQUIRE(o.C == q.C && o.N == N && !o.half && aligned16(o.ptr) && aligned16(S) && o.sW % 4 == 0 && o.sN % 4 == 0,
+               "cross-attention: output shape / alignment");
+  LOCO_TRY(attention_tc_init());
+  AttnTcParams P;
+  LOCO_TRY(fill_cross(P, q, kv, heads, Tk_valid));
+  P.n_primal = n_primal;
+  LOCO_TRY(encode_rows_k(&P.qkv_k, q.ptr, q.C, Tq, N, q.sW, q.sN));
+  LOCO_TRY(encode_rows_k(&P.p_map, S, Tk, Tq, heads * N, Tk, (long long)Tq * Tk));
+  LOCO_TRY(encode_rows_k(&P.p_st, S, Tk, Tq, heads * N, Tk, (long long)Tq * Tk, false, 32));
+  LOCO_TRY(encode_rows_k(&P.o_st, o.ptr, o.C, Tq, N, o.sW, o.sN, false, 32));
+  const int qblocks = (Tq + 127) / 128;
+  attn_fwd_tc_kernel<<<dim3(qblocks, heads, n_primal), kTcThreads, kTcSmem, s>>>(P);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  if (nt > 0) {
+    attn_jvp_tc_kernel<<<dim3(qblocks, heads, nt), kTcThreads, kTcSmem, s>>>(P);
+    count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int attention_cross_vjp_tc(View go, View kv, int heads, int Tk_valid, const float* P0, View gq, cudaStream_t s) {
+  const int K = go.N, Tq = go.H * go.W, Tk = kv.H * kv.W;
+  LOCO_REQUIRE(gq.C == go.C && gq.N == K && !gq.half && !go.half && aligned16(go.ptr) && aligned16(gq.ptr) && aligned16(P0) &&
+                   go.sW % 4 == 0 && go.sN % 4 == 0 && gq.sW % 4 == 0 && gq.sN % 4 == 0,
+               "cross-attention VJP: shape / alignment");
+  LOCO_TRY(attention_tc_init());
+  AttnTcParams P;
+  LOCO_TRY(fill_cross(P, go, kv, heads, Tk_valid));
+  LOCO_TRY(encode_rows_k(&P.go_k, go.ptr, go.C, Tq, K, go.sW, go.sN));
+  LOCO_TRY(encode_rows_k(&P.p_map, P0, Tk, Tq, heads, Tk, (long long)Tq * Tk));
+  LOCO_TRY(encode_rows_k(&P.o_st, gq.ptr, gq.C, Tq, K, gq.sW, gq.sN, false, 32));
+  attn_vjp1_tc_kernel<<<dim3((Tq + 127) / 128, heads, K), kTcThreads, kTcSmem, s>>>(P);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -328,3 +328,24 @@ def attention_vjp(go, qkv0, P0, head_ch=0):
     check(_lib.load().loco_attention_vjp(ptr(go), K, T, Cc, head_ch, ptr(_f32(qkv0)), ptr(_f32(P0)),
                                          ptr(gP), ptr(gqkv), stream_ptr(go)), "loco_attention_vjp")
     return gqkv
+
+
+def cross_attention_fwd(q, kv, n_primal, heads, tk_valid):
+    """q [N, Tq, C] fp32, kv [Tk, 2C] = K_c | V_c (rows >= tk_valid zero).  Returns (o [N, Tq, C], P [N, heads, Tq, Tk])."""
+    q, kv = _f32(q), _f32(kv)
+    N, Tq, Cc = q.shape
+    Tk = kv.shape[0]
+    S = torch.empty(N, heads, Tq, Tk, dtype=torch.float32, device=q.device)
+    o = torch.empty(N, Tq, Cc, dtype=torch.float32, device=q.device)
+    check(_lib.load().loco_cross_attention_fwd(ptr(q), N, Tq, Cc, n_primal, ptr(kv), Tk, tk_valid, heads, ptr(S), ptr(o),
+                                               stream_ptr(q)), "loco_cross_attention_fwd")
+    return o, S
+
+
+def cross_attention_vjp(go, kv, P0, heads, tk_valid):
+    go, kv, P0 = _f32(go), _f32(kv), _f32(P0)
+    K, Tq, Cc = go.shape
+    gq = torch.empty_like(go)
+    check(_lib.load().loco_cross_attention_vjp(ptr(go), K, Tq, Cc, ptr(kv), kv.shape[0], tk_valid, heads, ptr(P0), ptr(gq),
+                                               stream_ptr(go)), "loco_cross_attention_vjp")
+    return gq

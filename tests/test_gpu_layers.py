@@ -253,6 +253,46 @@ def test_attention_fwd_jvp_vjp(dev, T, C):
     assert rel_err(ob, _attn_core(qb.double())) < 5e-4
 
 
+@pytest.mark.parametrize("Tq,C,heads,Tk,Tkv", [(256, 512, 8, 128, 77), (1024, 256, 4, 128, 77), (100, 128, 1, 64, 64),
+                                                (4096, 128, 2, 256, 200)])
+def test_cross_attention_fwd_jvp_vjp(dev, Tq, C, heads, Tk, Tkv):
+    """Fused tcgen05 cross-attention (image tokens -> fixed context of Tkv tokens padded to Tk) against
+    fp64: forward, tangent rows (d/dq, the context is a constant) and the VJP."""
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(Tq + C + Tkv)
+    k = 2
+    D = C // heads
+    q = _tf32(torch.randn(1, Tq, C, generator=g)).to(dev)
+    dq = _tf32(torch.randn(k, Tq, C, generator=g)).to(dev)
+    kv = torch.zeros(Tk, 2 * C)
+    kv[:Tkv] = _tf32(torch.randn(Tkv, 2 * C, generator=g))
+    kv = kv.to(dev)
+
+    def f(z):      # z [n, Tq, C] -> [n, Tq, C]
+        n = z.shape[0]
+        zh = z.reshape(n, Tq, heads, D).transpose(1, 2)                        # [n, h, Tq, D]
+        kc = kv[:Tkv, :C].double().reshape(Tkv, heads, D).transpose(0, 1)      # [h, Tkv, D]
+        vc = kv[:Tkv, C:].double().reshape(Tkv, heads, D).transpose(0, 1)
+        w = torch.softmax(torch.einsum("nhqd,hkd->nhqk", zh, kc) * D ** -0.5, dim=-1)
+        return torch.einsum("nhqk,hkd->nhqd", w, vc).transpose(1, 2).reshape(n, Tq, C)
+
+    oref = f(q.double())
+    dref = torch.cat([torch.func.jvp(f, (q.double(),), (dq[j:j + 1].double(),))[1] for j in range(k)], 0)
+    o, S = ops.cross_attention_fwd(torch.cat([q, dq], 0).contiguous(), kv, 1, heads, Tkv)
+    torch.cuda.synchronize()
+    e0, e1 = rel_err(o[:1], oref), rel_err(o[1:], dref)
+    assert float(S[0, :, :, Tkv:].abs().max()) == 0.0 if Tkv < Tk else True
+    go = _tf32(torch.randn(k, Tq, C, generator=g)).to(dev)
+    qd = q.double().requires_grad_(True)
+    od = f(qd)
+    gref = torch.cat([torch.autograd.grad(od, qd, go[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
+    gq = ops.cross_attention_vjp(go, kv, S[0].contiguous(), heads, Tkv)
+    torch.cuda.synchronize()
+    e2 = rel_err(gq, gref)
+    print(f"cross-attention Tq={Tq} C={C} heads={heads} Tk={Tkv}/{Tk}: primal {e0:.2e} tangent {e1:.2e} vjp {e2:.2e}")
+    assert e0 < 5e-4 and e1 < 1e-3 and e2 < 1e-3
+
+
 @pytest.mark.parametrize("k,d", [(1, 3072), (5, 196608), (22, 12288), (64, 49152)])
 def test_orthonormalise_matches_svd(dev, k, d):
     from loco_edit_b200 import ops
