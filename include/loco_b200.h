@@ -45,6 +45,9 @@ typedef struct loco_arch {
   float gn_eps;            /* 1e-6 (DDPM) / 1e-5 (guided diffusion) */
   int kind;                /* 0 = DDPM, 1 = P2 / guided diffusion */
   int head_ch;             /* kind 1: channels per attention head (num_head_channels); else 0 */
+  int ctx_dim;             /* kind 0: > 0 adds a cross-attention sub-block to every AttnBlock, keys / values =
+                              Linear(ctx_dim -> 2C) of a prompt embedding (text-conditioned twins); 0 = none */
+  int ctx_heads;           /* heads of those cross-attention layers (C / heads a multiple of 64, <= 512) */
 } loco_arch_t;
 
 int loco_abi_version(void);
@@ -101,6 +104,11 @@ int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void*
  * combines eps linearly, so its Jacobian products are the same linear combination of this plan's
  * JVP / VJP passes. */
 int loco_plan_set_condition(loco_plan_t* p, const float* cond, void* stream);
+/* Prompt embedding ctx [n_tokens <= 128, ctx_dim] (device memory) of a U-Net created with ctx_dim > 0:
+ * the `encoder_hidden_states` of `self.unet(x, t, encoder_hidden_states=...)` (src/modules/edit.py:655-658,
+ * 1319-1322).  Computes K_c | V_c of every cross-attention layer once; must precede loco_unet_forward.
+ * The context is a constant of x -> eps(x, t, ctx), so JVP / VJP differentiate the query side only. */
+int loco_plan_set_context(loco_plan_t* p, const float* ctx, int n_tokens, void* stream);
 /* gx[j] = (d eps / d x)^T g_eps[j] at the primal point of the last loco_unet_forward: replaces
  * the k backward passes of torch.autograd.functional.jacobian (src/modules/edit.py:2479). */
 int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream);

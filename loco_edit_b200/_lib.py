@@ -20,7 +20,7 @@ class Arch(C.Structure):
         ("ch", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8),
         ("num_res_blocks", C.c_int), ("n_attn", C.c_int), ("attn_resolutions", C.c_int * 4),
         ("resolution", C.c_int), ("in_ch", C.c_int), ("out_ch", C.c_int), ("gn_eps", C.c_float),
-        ("kind", C.c_int), ("head_ch", C.c_int),
+        ("kind", C.c_int), ("head_ch", C.c_int), ("ctx_dim", C.c_int), ("ctx_heads", C.c_int),
     ]
 
 
@@ -51,6 +51,7 @@ PROTOTYPES = {
     "loco_plan_info": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(_I)]),
     "loco_unet_forward": (_I, [_P, _P, _F, _P, _P]),
     "loco_plan_set_condition": (_I, [_P, _P, _P]),
+    "loco_plan_set_context": (_I, [_P, _P, _I, _P]),
     "loco_unet_vjp": (_I, [_P, _P, _P, _P]),
     "loco_pullback_scratch_bytes": (_LL, [_I, _LL]),
     "loco_pullback_iteration": (_I, [_P, _P, _F, _F, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _P, _P, _P]),

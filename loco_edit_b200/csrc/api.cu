@@ -40,7 +40,7 @@ static int require_device() {
 
 extern "C" {
 
-int loco_abi_version(void) { return 2; }
+int loco_abi_version(void) { return 3; }
 long long loco_launch_count(void) { return launch_count(); }
 int loco_profile_enable(int on) { profile_enable(on != 0); return 0; }
 int loco_profile_collect(double* ms, double* work, long long* launches, int nfam) {
@@ -69,6 +69,10 @@ int loco_unet_create(const loco_arch_t* a, loco_unet_t** out) {
   LOCO_REQUIRE(a->kind == 0 || (a->head_ch > 0 && a->head_ch % 4 == 0),
                "loco_unet_create: guided-diffusion U-Net needs head_ch > 0");
   A.kind = a->kind; A.head_ch = a->kind == 1 ? a->head_ch : 0;
+  LOCO_REQUIRE(a->ctx_dim >= 0 && (a->ctx_dim == 0 || (a->kind == 0 && a->ctx_dim % 4 == 0 && a->ctx_heads >= 1)),
+               "loco_unet_create: cross-attention (ctx_dim %d, heads %d) needs kind 0, ctx_dim %% 4 == 0", a->ctx_dim,
+               a->ctx_heads);
+  A.ctx_dim = a->ctx_dim; A.ctx_heads = a->ctx_dim > 0 ? a->ctx_heads : 1;
   *out = new loco_unet{new Model(A)};
   return 0;
   GUARD_END
@@ -164,6 +168,12 @@ int loco_plan_set_condition(loco_plan_t* p, const float* cond, void* stream) {
   GUARD_BEGIN
   LOCO_REQUIRE(p, "loco_plan_set_condition: null plan");
   return p->p->set_condition(cond, ST(stream));
+  GUARD_END
+}
+int loco_plan_set_context(loco_plan_t* p, const float* ctx, int n_tokens, void* stream) {
+  GUARD_BEGIN
+  LOCO_REQUIRE(p, "loco_plan_set_context: null plan");
+  return p->p->set_context(ctx, n_tokens, ST(stream));
   GUARD_END
 }
 int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream) {

@@ -930,6 +930,22 @@ __global__ void temb_project_kernel(const float* __restrict__ temb_act, int temb
   if (lane == 0) out[o] = acc + b[o];
 }
 
+// Key | value projection of a prompt embedding for the cross-attention layers:
+// out[t][j] = round_tf32(b[j] + W[j,:] . ctx[t,:]) for the n_tok tokens that exist, 0 for the padding
+// rows (one warp per output; the result is an operand of the tcgen05 cross-attention kernels).
+__global__ void context_kv_kernel(const float* __restrict__ ctx, int n_tok, int dim, const float* __restrict__ w,
+                                  const float* __restrict__ b, int cout, int rows, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (long long)rows * cout) return;
+  const int t = (int)(o / cout), j = (int)(o % cout);
+  float acc = 0.f;
+  if (t < n_tok)
+    for (int i = lane; i < dim; i += 32) acc += w[(long long)j * dim + i] * ctx[(long long)t * dim + i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[o] = t < n_tok ? round_tf32(acc + b[j]) : 0.f;
+}
+
 // Power-of-two scale that brings max |v| to about `target`: the fp16 JVP / VJP programs carry their
 // tangent / cotangent rows scaled by it (both passes are linear in those rows, a power of two is exact)
 // so that the rows sit in the middle of fp16's exponent range whatever their natural magnitude
@@ -1287,6 +1303,13 @@ int scale_shift_affine(const AffineSite* sites_dev, int n_sites, const float* we
                        const float* tproj, float* out, cudaStream_t s) {
   if (n_sites <= 0) return 0;
   scale_shift_affine_kernel<<<n_sites, 256, 0, s>>>(sites_dev, weights, tproj, out);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int context_kv(const float* ctx, int n_tok, int dim, const float* w, const float* b, int cout, int rows, float* out,
+               cudaStream_t s) {
+  const long long outs = (long long)rows * cout;
+  context_kv_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, s>>>(ctx, n_tok, dim, w, b, cout, rows, out);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

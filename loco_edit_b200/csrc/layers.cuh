@@ -59,6 +59,9 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
 // out (+)= scale * nearest_upsample(in), out = 2H x 2W.  scale 1: the DDPM Upsample / P2 up ResBlock
 // (ddpm/diffusion.py:816-832, guided_diffusion/unet.py:95-124); scale 1/4: VJP of the 2x2 avg-pool.
 int upsample2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s);
+// K_c | V_c = ctx W^T + b for the first n_tok of `rows` context rows (the rest zero), tf32-rounded
+int context_kv(const float* ctx, int n_tok, int dim, const float* w, const float* b, int cout, int rows, float* out,
+               cudaStream_t s);
 // out (+)= scale * 2x2 sum-pool(in).  scale 1: VJP of upsample2x; scale 1/4: the avg-pool of the P2
 // down ResBlock (guided_diffusion/unet.py:127-158 with use_conv = False).
 int sumpool2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s);

@@ -185,6 +185,18 @@ AttnRef Model::add_attn(const std::string& prefix, int C) {
     add_slot(b);
   }
   a.proj = add_conv(prefix + ".proj_out", C, C, 1);
+  if (arch.ctx_dim > 0) {
+    a.cross = true;
+    a.n2 = add_norm(prefix + ".norm2", C);
+    a.q2 = add_conv(prefix + ".q2", C, C, 1);
+    a.kv_w = alloc((size_t)2 * C * arch.ctx_dim);
+    a.kv_b = alloc(2 * C);
+    ParamSlot w; w.name = prefix + ".kv2.weight"; w.shape = {2 * C, arch.ctx_dim}; w.kind = ParamSlot::RAW; w.off_a = a.kv_w;
+    add_slot(w);
+    ParamSlot b; b.name = prefix + ".kv2.bias"; b.shape = {2 * C}; b.kind = ParamSlot::RAW; b.off_a = a.kv_b;
+    add_slot(b);
+    a.proj2 = add_conv(prefix + ".proj_out2", C, C, 1);
+  }
   return a;
 }
 
@@ -477,6 +489,10 @@ struct Plan::Impl {
   float *in_buf = nullptr, *out_buf = nullptr, *gin_buf = nullptr, *gout_buf = nullptr;
   cudaGraphExec_t fwd_graph = nullptr, bwd_graph = nullptr;
   long long fwd_graph_launches = 0, bwd_graph_launches = 0;
+  // cross-attention layers: projection weights and the K_c | V_c buffer [kCtxPad][2C] of each
+  struct CrossLayer { const float* w; const float* b; int C; float* kv; };
+  std::vector<CrossLayer> cross_layers;
+  int ctx_tokens = 0;             // tokens of the current context (0: none set yet)
   ~Impl() {
     if (fwd_graph) cudaGraphExecDestroy(fwd_graph);
     if (bwd_graph) cudaGraphExecDestroy(bwd_graph);
@@ -521,7 +537,7 @@ int Plan::build(float* workspace) {
   if (!dry) LOCO_REQUIRE(M.arena != nullptr, "plan: model weights not bound");
   if (!dry) { LOCO_TRY(conv_init()); LOCO_TRY(layers_init()); LOCO_TRY(attention_init()); }
 
-  I.fwd.clear(); I.bwd_groups.clear(); I.bwd.clear(); I.launches.clear(); I.writers.clear();
+  I.fwd.clear(); I.bwd_groups.clear(); I.bwd.clear(); I.launches.clear(); I.writers.clear(); I.cross_layers.clear();
   I.n_ids = 0;
   fwd_flops = vjp_flops = 0;
   base = workspace;
@@ -806,7 +822,7 @@ int Plan::build(float* workspace) {
       }
     }
   };
-  auto attnblock = [&](const AttnRef& R, const TH& x, const TH& out) {
+  auto self_attn = [&](const AttnRef& R, const TH& x, const TH& out) {
     const int H = x.v.H, W = x.v.W, C = R.C, T = H * W;
     View hn = Tf(H, W, C);
     double* st = gn_fwd(x.v, R.n, 0, 1, hn, x.st_self.st, th_fused(x));
@@ -832,6 +848,49 @@ int Plan::build(float* workspace) {
       const int f = writer_flag(x.ids);
       gn_bwd(row0(x.v), st, ghn, R.n, 0, &out.g, f, 1, x.g);
     }
+  };
+  // out = x + proj2(softmax(q2(GN(x)) K_c^T / sqrt(D)) V_c): cross-attention to the prompt embedding.
+  // K_c | V_c do not depend on x, so the tangent / cotangent rules only involve the query side.
+  auto cross_attn = [&](const AttnRef& R, const TH& x, const TH& out) {
+    const int H = x.v.H, W = x.v.W, C = R.C, T = H * W;
+    const int heads = A.ctx_heads;
+    if (err == 0 && !attention_cross_eligible(kCtxPad, C, heads)) {
+      set_error("plan: cross-attention with %d channels in %d heads is not supported", C, heads);
+      err = 3;
+    }
+    float* kvb = alloc_act((size_t)kCtxPad * 2 * C);
+    if (!dry) {
+      Impl::CrossLayer cl; cl.w = M.w(R.kv_w); cl.b = M.w(R.kv_b); cl.C = C; cl.kv = kvb;
+      I.cross_layers.push_back(cl);
+    }
+    const View kv = make_view(kvb, 1, 1, kCtxPad, 2 * C);
+    View hn = Tf(H, W, C);
+    double* st = gn_fwd(x.v, R.n2, 0, 1, hn, x.st_self.st, th_fused(x));
+    View q = Tf32(H, W, C);
+    conv_fwd(CONV_1x1, hn, q, R.q2, nullptr, nullptr);
+    float* S = alloc_act((size_t)NB * heads * T * kCtxPad);
+    View o = Tf32(H, W, C);
+    const int np = NP;
+    Impl* Ip = impl.get();
+    I.fwd.push_back([=](cudaStream_t s) { return attention_cross_forward_tc(q, kv, np, heads, Ip->ctx_tokens, S, o, s); });
+    conv_fwd(CONV_1x1, o, out.v, R.proj2, nullptr, &x.v, &out);
+    if (NC > 0) {
+      begin_group();
+      View go = Tg32(H, W, C);
+      conv_bwd(CONV_1x1, out.g, go, R.proj2, 0);
+      View gq = Tg32(H, W, C);
+      push_b([=](cudaStream_t s) { return attention_cross_vjp_tc(go, kv, heads, Ip->ctx_tokens, S, gq, s); });
+      View ghn = Tg(H, W, C);
+      conv_bwd(CONV_1x1, gq, ghn, R.q2, 0);
+      const int f = writer_flag(x.ids);
+      gn_bwd(row0(x.v), st, ghn, R.n2, 0, &out.g, f, 1, x.g);
+    }
+  };
+  auto attnblock = [&](const AttnRef& R, const TH& x, const TH& out) {
+    if (!R.cross) { self_attn(R, x, out); return; }
+    TH mid = new_tensor(x.v.H, x.v.W, R.C);
+    self_attn(R, x, mid);
+    cross_attn(R, mid, out);
   };
 
   // ---- topology (reference: PullBackDDPM.forward, ddpm/diffusion.py:145-200) ----
@@ -1116,6 +1175,8 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
   DeviceGuard guard(device);
   Impl& I = *impl;
+  LOCO_REQUIRE(model->arch.ctx_dim == 0 || I.ctx_tokens > 0,
+               "plan: this U-Net has cross-attention layers, call set_context() before forward()");
   const size_t bytes = sizeof(float) * (size_t)(NP + NT) * 3 * model->arch.resolution * model->arch.resolution;
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.in_buf, x, bytes, cudaMemcpyDeviceToDevice, s));
   LOCO_TRY(set_scalar(I.t_dev, t, s));
@@ -1126,6 +1187,24 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   I.cur_x = I.in_buf; I.cur_eps = I.out_buf;
   LOCO_TRY(run_program(I.fwd, I.fstats, I.fstat_bytes, &I.fwd_graph, &I.fwd_graph_launches, s));
   LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, bytes, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int Plan::set_context(const float* ctx, int n_tok, cudaStream_t s) {
+  LOCO_REQUIRE(impl && base, "plan: not bound to a workspace");
+  const Arch& A = model->arch;
+  LOCO_REQUIRE(A.ctx_dim > 0, "plan: this architecture has no cross-attention layers");
+  LOCO_REQUIRE(ctx != nullptr && n_tok >= 1 && n_tok <= kCtxPad, "plan: context must have 1..%d tokens (got %d)", kCtxPad, n_tok);
+  DeviceGuard guard(device);
+  Impl& I = *impl;
+  if (n_tok != I.ctx_tokens) {
+    // the token count is a launch parameter of the attention kernels: re-capture the programs
+    if (I.fwd_graph) { cudaGraphExecDestroy(I.fwd_graph); I.fwd_graph = nullptr; }
+    if (I.bwd_graph) { cudaGraphExecDestroy(I.bwd_graph); I.bwd_graph = nullptr; }
+    I.ctx_tokens = n_tok;
+  }
+  for (const Impl::CrossLayer& cl : I.cross_layers)
+    LOCO_TRY(context_kv(ctx, n_tok, A.ctx_dim, cl.w, cl.b, 2 * cl.C, kCtxPad, cl.kv, s));
   return 0;
 }
 

@@ -28,7 +28,13 @@ struct Arch {
   float gn_eps = 1e-6f;
   int kind = 0;       // 0 = DDPM (ddpm/diffusion.py), 1 = P2 / guided diffusion (guided_diffusion/unet.py)
   int head_ch = 0;    // kind 1: channels per attention head
+  // kind 0 only: > 0 adds a cross-attention sub-block (GroupNorm, q projection, softmax(q K_c^T) V_c,
+  // output projection, residual) to every AttnBlock; K_c | V_c are linear maps of a prompt embedding
+  // [n_tok <= 128, ctx_dim] (text-conditioned twins of the path)
+  int ctx_dim = 0;
+  int ctx_heads = 1;
 };
+constexpr int kCtxPad = 128;   // context rows of the key / value buffers (tokens are zero-padded)
 
 // One named parameter of the reference state_dict and where its packed forms live in the arena.
 struct ParamSlot {
@@ -59,7 +65,12 @@ struct ResRef {
   bool scale_shift = false;
   int resample = 0;
 };
-struct AttnRef { int C = 0; NormRef n; ConvRef qkv, proj; };
+struct AttnRef {
+  int C = 0; NormRef n; ConvRef qkv, proj;
+  bool cross = false;            // cross-attention sub-block after the self-attention one
+  NormRef n2; ConvRef q2, proj2;
+  size_t kv_w = 0, kv_b = 0;     // Linear(ctx_dim -> 2C): [2C][ctx_dim] fp32, [2C]
+};
 
 class Model {
  public:
@@ -122,6 +133,9 @@ class Plan {
   // conditioning embedding [4 ch] (device, or null = none) added to the timestep embedding of every
   // following forward(); x -> eps(x, t, c) stays a function of x only, so JVP / VJP are unchanged
   int set_condition(const float* cond, cudaStream_t s);
+  // prompt embedding [n_tok, ctx_dim] (device) of the cross-attention layers: computes every layer's
+  // K_c | V_c once; like the conditioning embedding it is a constant of the Jacobian passes
+  int set_context(const float* ctx, int n_tok, cudaStream_t s);
   // g_eps: [NC, 3, R, R] cotangents of eps; gx: [NC, 3, R, R] = J_eps^T g_eps.
   int vjp(const float* g_eps_nchw, float* gx_nchw, cudaStream_t s);
 

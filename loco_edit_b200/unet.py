@@ -33,6 +33,8 @@ def _make_arch(a):
     s.gn_eps = a.get("gn_eps", 1e-6)
     s.kind = 1 if a.get("kind") == "p2" else 0
     s.head_ch = a.get("head_ch", 0) if s.kind == 1 else 0
+    s.ctx_dim = a.get("ctx_dim", 0) if s.kind == 0 else 0
+    s.ctx_heads = a.get("ctx_heads", 1)
     return s
 
 
@@ -87,6 +89,14 @@ class Plan:
             assert cond.numel() == 4 * self.unet.arch["ch"], (cond.numel(), self.unet.arch["ch"])
         check(self.lib.loco_plan_set_condition(self.handle, ptr(cond), stream_ptr(self.unet.device)),
               "loco_plan_set_condition")
+
+    def set_context(self, ctx):
+        """Prompt embedding [n_tok <= 128, ctx_dim] (device tensor) for the cross-attention layers of a
+        U-Net built with ctx_dim > 0: the `encoder_hidden_states` of the following forward() calls."""
+        assert ctx.is_cuda and ctx.dtype == torch.float32 and ctx.is_contiguous() and ctx.dim() == 2
+        assert ctx.shape[1] == self.unet.arch.get("ctx_dim", 0), (tuple(ctx.shape), self.unet.arch.get("ctx_dim"))
+        check(self.lib.loco_plan_set_context(self.handle, ptr(ctx), int(ctx.shape[0]), stream_ptr(ctx)),
+              "loco_plan_set_context")
 
     def vjp(self, g_eps, out=None):
         k = self.shape[2]

@@ -14,11 +14,23 @@ DDPM256 = dict(ch=128, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolu
                resolution=256, in_ch=3, out_ch=3, gn_eps=1e-6)
 
 
-def tiny_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1, ch=128):
-    """Reduced-depth variant of the same architecture for fast parity tests."""
-    return dict(ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
-                attn_resolutions=tuple(attn_resolutions), resolution=resolution, in_ch=3, out_ch=3,
-                gn_eps=1e-6)
+def tiny_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1, ch=128, ctx_dim=0,
+              ctx_heads=1):
+    """Reduced-depth variant of the same architecture for fast parity tests (ctx_dim > 0: with a
+    cross-attention sub-block in every AttnBlock)."""
+    a = dict(ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
+             attn_resolutions=tuple(attn_resolutions), resolution=resolution, in_ch=3, out_ch=3,
+             gn_eps=1e-6)
+    if ctx_dim > 0:
+        a.update(ctx_dim=ctx_dim, ctx_heads=ctx_heads)
+    return a
+
+
+# The DDPM-256 U-Net with cross-attention to a 77 x 768 prompt embedding (CLIP ViT-L/14 text states, the
+# conditioning of Stable Diffusion 1.x) in each of its six AttnBlocks, 8 heads of 64 channels: the
+# text-conditioned stand-in of BASELINE configs 4-5 (the SD / IF networks are diffusers code that is not
+# under /root/reference, SURVEY 8c)
+DDPM256_TEXT = dict(DDPM256, ctx_dim=768, ctx_heads=8)
 
 
 def ddpm_param_shapes(arch):
@@ -50,6 +62,14 @@ def ddpm_param_shapes(arch):
         norm(p + ".norm", c)
         for n in ("q", "k", "v", "proj_out"):
             conv(p + "." + n, c, c, 1)
+        if arch.get("ctx_dim", 0) > 0:
+            # cross-attention sub-block to a prompt embedding [n_tok, ctx_dim] (text-conditioned twins):
+            # GroupNorm, q projection, one Linear for K_c | V_c, output projection
+            norm(p + ".norm2", c)
+            conv(p + ".q2", c, c, 1)
+            out[p + ".kv2.weight"] = (2 * c, arch["ctx_dim"])
+            out[p + ".kv2.bias"] = (2 * c,)
+            conv(p + ".proj_out2", c, c, 1)
 
     out["temb.dense.0.weight"] = (temb, ch)
     out["temb.dense.0.bias"] = (temb,)

@@ -61,7 +61,23 @@ def attn_block(sd, p, x, eps):
     return x + conv(sd, p + ".proj_out", h_)
 
 
-def unet_forward(sd, arch, x, t, cond=None):
+def cross_attn_block(sd, p, x, ctx, heads, eps):
+    """Cross-attention sub-block of the text-conditioned stand-in (no reference restatement exists:
+    diffusers' `Attention` processor computes softmax(q k^T / sqrt(d)) v with q = to_q(hidden),
+    k = to_k(encoder_hidden_states), v = to_v(encoder_hidden_states), then to_out; parity unpinned at
+    the network level).  x [B,C,H,W], ctx [n_tok, ctx_dim]."""
+    b, c, h, w = x.shape
+    d = c // heads
+    q = conv(sd, p + ".q2", norm(sd, p + ".norm2", x, eps)).reshape(b, heads, d, h * w).transpose(2, 3)   # [b,hd,T,d]
+    kv = F.linear(ctx, sd[p + ".kv2.weight"], sd[p + ".kv2.bias"])                                       # [n_tok, 2c]
+    k = kv[:, :c].reshape(-1, heads, d).transpose(0, 1)                                                   # [hd,n,d]
+    v = kv[:, c:].reshape(-1, heads, d).transpose(0, 1)
+    wgt = F.softmax(torch.einsum("bhtd,hnd->bhtn", q, k) * d ** -0.5, dim=-1)
+    o = torch.einsum("bhtn,hnd->bhtd", wgt, v).transpose(2, 3).reshape(b, c, h, w)
+    return x + conv(sd, p + ".proj_out2", o)
+
+
+def unet_forward(sd, arch, x, t, cond=None, ctx=None):
     """models/ddpm/diffusion.py:145-200 (PullBackDDPM.forward with op=None).
 
     x: [B,3,R,R]; t: 0-dim or [1] tensor / float (shared by the batch, as in the reference where
@@ -73,6 +89,16 @@ def unet_forward(sd, arch, x, t, cond=None):
     ch, mult, nrb = arch["ch"], tuple(arch["ch_mult"]), arch["num_res_blocks"]
     attn_res, eps = tuple(arch["attn_resolutions"]), arch.get("gn_eps", 1e-6)
     L = len(mult)
+    heads = arch.get("ctx_heads", 1)
+    cross = arch.get("ctx_dim", 0) > 0
+    if cross:
+        assert ctx is not None, "this architecture has cross-attention layers: pass ctx [n_tok, ctx_dim]"
+        _attn = attn_block
+
+        def attn_block_(sd_, p_, h_, eps_):
+            return cross_attn_block(sd_, p_, _attn(sd_, p_, h_, eps_), ctx, heads, eps_)
+    else:
+        attn_block_ = attn_block
     t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)[:1]
     temb = timestep_embedding(t, ch)
     temb = F.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
@@ -87,7 +113,7 @@ def unet_forward(sd, arch, x, t, cond=None):
         for b in range(nrb):
             h = resnet_block(sd, f"down.{l}.block.{b}", hs[-1], temb, eps)
             if cur in attn_res:
-                h = attn_block(sd, f"down.{l}.attn.{b}", h, eps)
+                h = attn_block_(sd, f"down.{l}.attn.{b}", h, eps)
             hs.append(h)
         if l != L - 1:
             # Downsample: models/ddpm/diffusion.py:846-850, pad (0,1,0,1) then stride-2 conv
@@ -95,13 +121,13 @@ def unet_forward(sd, arch, x, t, cond=None):
             cur //= 2
     h = hs[-1]
     h = resnet_block(sd, "mid.block_1", h, temb, eps)
-    h = attn_block(sd, "mid.attn_1", h, eps)
+    h = attn_block_(sd, "mid.attn_1", h, eps)
     h = resnet_block(sd, "mid.block_2", h, temb, eps)
     for l in reversed(range(L)):
         for b in range(nrb + 1):
             h = resnet_block(sd, f"up.{l}.block.{b}", torch.cat([h, hs.pop()], dim=1), temb, eps)
             if cur in attn_res:
-                h = attn_block(sd, f"up.{l}.attn.{b}", h, eps)
+                h = attn_block_(sd, f"up.{l}.attn.{b}", h, eps)
         if l != 0:
             # Upsample: models/ddpm/diffusion.py:826-832, nearest x2 then 3x3 conv
             h = conv(sd, f"up.{l}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"), padding=1)
@@ -117,5 +143,5 @@ class RefUNet:
         self.arch = dict(arch)
         self.sd = {k: v.to(dtype) for k, v in sd.items()}
 
-    def __call__(self, x, t, cond=None):
-        return unet_forward(self.sd, self.arch, x, t, cond=cond)
+    def __call__(self, x, t, cond=None, ctx=None):
+        return unet_forward(self.sd, self.arch, x, t, cond=cond, ctx=ctx)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libloco_b200.so does not export %s" % n
         assert n in _lib.PROTOTYPES, "python binding lacks a prototype for %s" % n
-    assert lib.loco_abi_version() == 2
+    assert lib.loco_abi_version() == 3
 
 
 def test_model_registry_matches_reference_state_dict(golden_dir):

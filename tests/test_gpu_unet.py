@@ -87,6 +87,63 @@ def test_unet_jvp_vjp_match_oracle(dev, name):
     assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
 
 
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("name,ctx_dim,heads,n_tok", [("two_level_attn16", 96, 2, 77), ("three_level_attn8", 64, 4, 20)])
+def test_cross_attention_unet_fwd_jvp_vjp_match_oracle(dev, name, ctx_dim, heads, n_tok, half):
+    """U-Net with a cross-attention sub-block in every AttnBlock (text-conditioned twins):
+    eps(x, t, ctx), its fused primal + k-tangent pass and the k-cotangent pass against the CPU oracle,
+    with the adjoint identity between the two CUDA passes, in both arithmetic modes of the programs."""
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict, tiny_arch
+    from oracle import ddpm_ref
+    arch = tiny_arch(ctx_dim=ctx_dim, ctx_heads=heads, **ARCHS[name])
+    sd = random_state_dict(arch, seed=77, perturb_norm=0.1)
+    net, ref = B200UNet(arch, sd, device=dev), ddpm_ref.RefUNet(arch, sd)
+    R = arch["resolution"]
+    g = torch.Generator().manual_seed(5)
+    k = 3
+    x = torch.randn(1, 3, R, R, generator=g)
+    xb = torch.randn(2, 3, R, R, generator=g)
+    V = torch.randn(k, 3, R, R, generator=g)
+    G = torch.randn(k, 3, R, R, generator=g)
+    ctx = torch.randn(n_tok, ctx_dim, generator=g)
+    ctx2 = torch.randn(n_tok + 3, ctx_dim, generator=g)
+    t = torch.tensor(595.3636)
+    f = lambda z: ref(z, t, ctx=ctx)
+    with torch.no_grad():
+        eb_ref = f(xb)
+        eb2_ref = ref(xb, t, ctx=ctx2)
+    dref = torch.cat([torch.func.jvp(f, (x,), (V[j:j + 1],))[1] for j in range(k)], 0)
+    e0 = f(x).detach()
+    xg = x.clone().requires_grad_(True)
+    out = f(xg)
+    gref = torch.cat([torch.autograd.grad(out, xg, G[j:j + 1], retain_graph=True)[0] for j in range(k)], 0)
+    # a plan refuses to run without a context
+    pb = net.plan(2, half=half)
+    with pytest.raises(Exception):
+        pb.forward(xb.to(dev), float(t))
+    pb.set_context(ctx.to(dev))
+    eb = pb.forward(xb.to(dev), float(t))
+    pb.set_context(ctx2.to(dev))             # another prompt, another token count: the program is re-captured
+    eb2 = pb.forward(xb.to(dev), float(t))
+    pj = net.plan(1, k, k, half=half)
+    pj.set_context(ctx.to(dev))
+    o = pj.forward(torch.cat([x, V], 0).to(dev), float(t))
+    gx = pj.vjp(G.to(dev))
+    torch.cuda.synchronize()
+    eps, deps = o[:1], o[1:]
+    errs = [rel_err(eb.cpu(), eb_ref), rel_err(eb2.cpu(), eb2_ref), rel_err(eps.cpu(), e0), rel_err(deps.cpu(), dref),
+            rel_err(gx.cpu(), gref)]
+    print(f"{name} ctx {n_tok}x{ctx_dim} heads {heads} half={half}: fwd {errs[0]:.3e} / {errs[1]:.3e} primal {errs[2]:.3e} "
+          f"jvp {errs[3]:.3e} vjp {errs[4]:.3e}; different prompts differ by {rel_err(eb2.cpu(), eb.cpu()):.2e}")
+    assert max(errs) < 5e-3
+    assert rel_err(eb2.cpu(), eb.cpu()) > 1e-3          # the context matters
+    lhs = (deps.double() * G.to(dev).double()).sum(dim=(1, 2, 3))
+    rhs = (V.to(dev).double() * gx.double()).sum(dim=(1, 2, 3))
+    scale = deps.double().flatten(1).norm(dim=1) * G.to(dev).double().flatten(1).norm(dim=1)
+    assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
+
+
 @pytest.mark.parametrize("case", ["mask_k2", "notmask_k3", "nomask_k2", "noise_k2"])
 def test_power_iteration_matches_reference_golden(dev, golden_dir, case):
     """Same weights, x_t, t, mask and V0 as the reference run in tests/golden/make_golden.py."""
