@@ -89,11 +89,15 @@ class CondB200UNet(object):
             self._cache[key] = (prompt_emb, c.contiguous().to(self.device))
         return self._cache[key][1]
 
+    def apply_condition(self, plan, prompt_emb):
+        """Make `plan` evaluate eps(., t, prompt_emb) from now on."""
+        plan.set_condition(self.cond_vector(prompt_emb))
+
     def eps(self, x, t, prompt_emb):
         """Noise prediction of all rows of x under ONE prompt."""
         x = x.contiguous()
         plan = self.base.plan(x.shape[0])
-        plan.set_condition(self.cond_vector(prompt_emb))
+        self.apply_condition(plan, prompt_emb)
         return plan.forward(x, float(t))
 
     def __call__(self, x, t, encoder_hidden_states):
@@ -112,6 +116,31 @@ class CondB200UNet(object):
         return types.SimpleNamespace(sample=out)
 
 
+class TextB200UNet(CondB200UNet):
+    """eps(x, t, prompt) with REAL cross-attention: `base` is a B200UNet built with ctx_dim > 0, every
+    AttnBlock of which attends to the prompt tokens (loco_plan_set_context; fused tcgen05
+    cross-attention with JVP / VJP, csrc/attention_tc.cu).  `encoder_hidden_states` [1, n_tok <= 128,
+    ctx_dim] is used as is, like diffusers' UNet2DConditionModel does (src/modules/edit.py:655-658,
+    1319-1322).  Same call protocol as CondB200UNet, so the Edit classes take either."""
+
+    def __init__(self, base):
+        assert base.arch.get("ctx_dim", 0) > 0, "TextB200UNet needs a U-Net with cross-attention layers (ctx_dim > 0)"
+        self.base = base
+        self.device = base.device
+        self.arch = base.arch
+        self._cache = {}
+
+    def context(self, prompt_emb):
+        key = (prompt_emb.data_ptr(), tuple(prompt_emb.shape))
+        if key not in self._cache:
+            c = prompt_emb.detach().reshape(-1, prompt_emb.shape[-1]).to(device=self.device, dtype=torch.float32)
+            self._cache[key] = (prompt_emb, c.contiguous())
+        return self._cache[key][1]
+
+    def apply_condition(self, plan, prompt_emb):
+        plan.set_context(self.context(prompt_emb))
+
+
 class EditDeepFloydIF(object):
     """Drop-in for the hot-path methods of the reference class of the same name."""
 
@@ -119,7 +148,7 @@ class EditDeepFloydIF(object):
         self.seed = getattr(args, "seed", 0)
         self.device = torch.device(args.device)
         self.dtype = getattr(args, "dtype", torch.float32)
-        self.unet = unet                                    # CondB200UNet
+        self.unet = unet                                    # CondB200UNet or TextB200UNet
         # get_deepfloyd_if_scheduler (src/utils/utils.py:159-170): the stage-I scheduler's own alpha_bar
         # table with the custom timestep grid on t_max = 990
         sargs = types.SimpleNamespace(device=self.device, dtype=torch.float32, t_max=getattr(args, "t_max", 990),
@@ -259,7 +288,7 @@ class EditDeepFloydIF(object):
         outs = []
         for slot, wi, emb in slots:
             plan = self.unet.base.plan(1, k, k, slot=slot)
-            plan.set_condition(self.unet.cond_vector(emb))
+            self.unet.apply_condition(plan, emb)
             outs.append((plan.forward(xin, float(t))[1:].reshape(k, -1), wi))
         return self._combine(outs)
 

@@ -3,6 +3,8 @@ class `EditDeepFloydIF` (src/modules/edit.py:1198-2031), run on CPU against a st
 U-Net (build container only; see make_golden.py for the import stubs):
 
     python tests/golden/make_golden_t2i.py        # -> tests/golden/t2i_tiny.pt
+    python tests/golden/make_golden_t2i.py cross  # -> tests/golden/t2i_cross_tiny.pt (stand-in with real
+                                                  #    cross-attention to the prompt embedding)
 
 The DeepFloyd-IF / Stable-Diffusion networks are diffusers models that are not under /root/reference, so
 the network is a stand-in: the oracle's DDPM U-Net with the conditioning embedding
@@ -28,14 +30,15 @@ DIM, NTOK, R = 64, 8, 32
 G, G_EDIT = 7.5, 4.0
 
 
-def main():
+def main(cross=False):
     torch.set_num_threads(os.cpu_count())
     ddpm, uu, edit = mg.import_reference()
     from loco_edit_b200.scheduler import cosine_betas
     from loco_edit_b200.t2i import cond_projection, synthetic_prompt_embedding
     from loco_edit_b200.weights import random_state_dict, tiny_arch
     from oracle import ddpm_ref
-    arch = tiny_arch(resolution=R, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1)
+    arch = tiny_arch(resolution=R, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blocks=1,
+                     ctx_dim=DIM if cross else 0, ctx_heads=2)
     sd = random_state_dict(arch, seed=1234, perturb_norm=0.1)
     P = cond_projection(DIM, 4 * arch["ch"])
 
@@ -43,6 +46,9 @@ def main():
         def forward(self, x, t, encoder_hidden_states=None):
             outs = []
             for b in range(x.shape[0]):
+                if cross:      # every AttnBlock attends to the prompt tokens themselves
+                    outs.append(ddpm_ref.unet_forward(sd, arch, x[b:b + 1], t, ctx=encoder_hidden_states[b]))
+                    continue
                 c = encoder_hidden_states[b].mean(0) @ P
                 outs.append(ddpm_ref.unet_forward(sd, arch, x[b:b + 1], t, cond=c))
             eps = torch.cat(outs, 0)
@@ -108,9 +114,11 @@ def main():
                                                   edit_prompt_emb=embs[1], null_prompt_emb=embs[2],
                                                   mode="null+(for-null)+(edit-null)")
         out["ddpm_mid"] = {"xt": xt_mid, "t": t_mid, "idx": i_mid}
-    torch.save(out, os.path.join(HERE, "t2i_tiny.pt"))
+    torch.save(out, os.path.join(HERE, "t2i_cross_tiny.pt" if cross else "t2i_tiny.pt"))
     print("written", {k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__) for k, v in out.items()})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "cross" in sys.argv[1:]:
+    main(cross=True)
+elif __name__ == "__main__":
     main()

@@ -23,14 +23,19 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module")
-def setup(dev, golden_dir, tmp_path_factory):
-    from loco_edit_b200.t2i import CondB200UNet, EditDeepFloydIF, synthetic_prompt_embedding
+# two stand-in networks, each pinned by the unmodified reference class run on the same network:
+#   "temb":  conditioning = pooled prompt embedding added to the timestep embedding (t2i_tiny.pt)
+#   "cross": every AttnBlock cross-attends to the prompt tokens (t2i_cross_tiny.pt)
+@pytest.fixture(scope="module", params=["temb", "cross"])
+def setup(request, dev, golden_dir, tmp_path_factory):
+    from loco_edit_b200.t2i import CondB200UNet, EditDeepFloydIF, TextB200UNet, synthetic_prompt_embedding
     from loco_edit_b200.unet import B200UNet
     from loco_edit_b200.weights import random_state_dict
-    g = torch.load(os.path.join(golden_dir, "t2i_tiny.pt"), weights_only=False)
+    cross = request.param == "cross"
+    g = torch.load(os.path.join(golden_dir, "t2i_cross_tiny.pt" if cross else "t2i_tiny.pt"), weights_only=False)
     sd = random_state_dict(g["arch"], seed=1234, perturb_norm=0.1)
-    net = CondB200UNet(B200UNet(g["arch"], sd, device=dev), g["dim"])
+    base = B200UNet(g["arch"], sd, device=dev)
+    net = TextB200UNet(base) if cross else CondB200UNet(base, g["dim"])
     embs = [synthetic_prompt_embedding(p, g["ntok"], g["dim"]) for p in g["prompts"]]
     args = types.SimpleNamespace(device=dev, dtype=torch.float32, seed=3, for_steps=100, edit_t=0.4,
                                  guidance_scale=g["g"], guidance_scale_edit=g["g_edit"], image_size=32,
