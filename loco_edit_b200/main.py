@@ -1,7 +1,7 @@
 """Entry point mirroring the reference's src/main.py (:12-103): same flags, same dispatch on the
 `--run_*` booleans.  The unconditional path runs `EditUncondDiffusion`; DeepFloyd-IF model names run the
-T-LOCO class `EditDeepFloydIF` of loco_edit_b200/t2i.py on its stand-in conditional U-Net with seeded
-prompt embeddings (the IF network and its T5 encoder are diffusers / transformers models that cannot
+T-LOCO class `EditDeepFloydIF` of loco_edit_b200/t2i.py on a stand-in text-conditioned U-Net (cross-attention
+to seeded prompt embeddings (the IF network and its T5 encoder are diffusers / transformers models that cannot
 be obtained here); the latent-space classes (Stable Diffusion, LCM) need a VAE
 decoder inside every Jacobian product and raise NotImplementedError.
 
@@ -17,14 +17,14 @@ from .edit import EditUncondDiffusion
 def main_deepfloyd(args):
     """src/main.py:28-32, 72-85 for `--model_name DeepFloyd/IF-I-*`: pixel-space T-LOCO on 64 x 64."""
     import torch
-    from .t2i import CondB200UNet, EditDeepFloydIF, synthetic_prompt_embedding
+    from .t2i import EditDeepFloydIF, TextB200UNet, synthetic_prompt_embedding
     from .unet import B200UNet
-    from .weights import DDPM256, random_state_dict
-    print("DeepFloyd-IF: running the stand-in conditional U-Net with seeded prompt embeddings "
-          "(the IF checkpoint / T5 encoder are not available offline)")
-    arch = dict(DDPM256, resolution=args.image_size, ch_mult=(1, 2, 2, 4))       # 64 -> 8, attention at 16
-    net = CondB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=torch.device(args.device)), 64)
-    embs = [synthetic_prompt_embedding(p or "", 77, 64) for p in (args.for_prompt, args.edit_prompt, "")]
+    from .weights import if_standin_arch, random_state_dict
+    print("DeepFloyd-IF: running the stand-in text-conditioned U-Net (cross-attention to seeded prompt "
+          "embeddings; the IF checkpoint / T5 encoder are not available offline)")
+    arch = if_standin_arch(args.image_size)
+    net = TextB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=torch.device(args.device)))
+    embs = [synthetic_prompt_embedding(p or "", 77, 768) for p in (args.for_prompt, args.edit_prompt, "")]
     edit = EditDeepFloydIF(args, net, *embs)
     common = dict(op='mid', block_idx=0, mask_index=args.mask_index, vis_num=args.vis_num, vis_num_pc=args.pca_rank,
                   pca_rank=args.pca_rank, edit_prompt=args.edit_prompt, null_space_projection=args.null_space_projection,

@@ -33,6 +33,13 @@ def tiny_arch(resolution=32, ch_mult=(1, 2), attn_resolutions=(16,), num_res_blo
 DDPM256_TEXT = dict(DDPM256, ctx_dim=768, ctx_heads=8)
 
 
+def if_standin_arch(resolution=64):
+    """Text-conditioned stand-in at the DeepFloyd-IF stage-I size (BASELINE config 5: 64 x 64 pixels): four
+    levels 64 -> 8, self- and cross-attention (4 heads) at 16^2 and 8^2, prompt embedding 77 x 768."""
+    return dict(DDPM256, resolution=resolution, ch_mult=(1, 2, 4, 4), attn_resolutions=(16, 8), ctx_dim=768,
+                ctx_heads=4)
+
+
 def ddpm_param_shapes(arch):
     """Ordered {name: shape} of DDPM(arch).state_dict() (reference: ddpm/diffusion.py:24-126)."""
     ch, mult, nrb = arch["ch"], tuple(arch["ch_mult"]), arch["num_res_blocks"]

@@ -144,6 +144,37 @@ def test_cross_attention_unet_fwd_jvp_vjp_match_oracle(dev, name, ctx_dim, heads
     assert float(((lhs - rhs).abs() / scale).max()) < 2e-3
 
 
+def test_if_sized_text_unet_matches_oracle(dev):
+    """The stand-in of BASELINE config 5 (64 x 64, 512-channel self- and cross-attention at 16^2 and 8^2,
+    77 x 768 prompt embedding, the network `main.py --model_name DeepFloyd/...` runs): forward, JVP, VJP
+    against the CPU oracle in the default (fp16) arithmetic."""
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import if_standin_arch, random_state_dict
+    from oracle import ddpm_ref
+    arch = if_standin_arch(64)
+    sd = random_state_dict(arch, seed=1234)
+    net, ref = B200UNet(arch, sd, device=dev), ddpm_ref.RefUNet(arch, sd)
+    g = torch.Generator().manual_seed(9)
+    k = 2
+    x = torch.randn(1, 3, 64, 64, generator=g)
+    V, G = torch.randn(k, 3, 64, 64, generator=g), torch.randn(k, 3, 64, 64, generator=g)
+    ctx = torch.randn(77, 768, generator=g)
+    t = torch.tensor(742.5)
+    f = lambda z: ref(z, t, ctx=ctx)
+    dref = torch.cat([torch.func.jvp(f, (x,), (V[j:j + 1],))[1] for j in range(k)], 0)
+    xg = x.clone().requires_grad_(True)
+    out = f(xg)
+    gref = torch.cat([torch.autograd.grad(out, xg, G[j:j + 1], retain_graph=True)[0] for j in range(k)], 0)
+    p = net.plan(1, k, k)
+    p.set_context(ctx.to(dev))
+    o = p.forward(torch.cat([x, V], 0).to(dev), float(t))
+    gx = p.vjp(G.to(dev))
+    torch.cuda.synchronize()
+    e = [rel_err(o[:1].cpu(), out.detach()), rel_err(o[1:].cpu(), dref), rel_err(gx.cpu(), gref)]
+    print(f"IF-sized text U-Net: primal {e[0]:.3e} jvp {e[1]:.3e} vjp {e[2]:.3e}")
+    assert max(e) < 5e-3
+
+
 @pytest.mark.parametrize("case", ["mask_k2", "notmask_k3", "nomask_k2", "noise_k2"])
 def test_power_iteration_matches_reference_golden(dev, golden_dir, case):
     """Same weights, x_t, t, mask and V0 as the reference run in tests/golden/make_golden.py."""
