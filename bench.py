@@ -269,6 +269,47 @@ def measure_bandwidth_kernels(dev, hbm_peak):
     return out
 
 
+def measure_text_unet(dev, R):
+    """SURVEY 8(f1), BASELINE configs 4-5 stand-in: the DDPM-256 U-Net with a cross-attention sub-block
+    (8 heads, 77 x 768 prompt embedding) in each of its six AttnBlocks.  Device time of the fused rank-5
+    primal + tangent pass, of the rank-5 cotangent pass and of a B = 1 forward, next to which the
+    unconditional numbers of the main line show what the cross-attention layers cost."""
+    import torch
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import DDPM256_TEXT, random_state_dict
+    net = B200UNet(DDPM256_TEXT, random_state_dict(DDPM256_TEXT, seed=1234), device=dev)
+    g = torch.Generator(device=dev).manual_seed(21)
+    ctx = torch.randn(77, 768, device=dev, generator=g)
+    pj, p1 = net.plan(1, K_RANK, K_RANK), net.plan(1)
+    pj.set_context(ctx); p1.set_context(ctx)
+    xin = torch.randn(1 + K_RANK, 3, R, R, device=dev, generator=g)
+    gin = torch.randn(K_RANK, 3, R, R, device=dev, generator=g)
+    for _ in range(2):
+        pj.forward(xin, 595.3636); pj.vjp(gin); p1.forward(xin[:1].contiguous(), 595.3636)
+    torch.cuda.synchronize()
+    a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        pj.forward(xin, 595.3636)
+    b.record()
+    for _ in range(reps):
+        pj.vjp(gin)
+    c.record()
+    for _ in range(reps):
+        p1.forward(xin[:1].contiguous(), 595.3636)
+    d.record()
+    torch.cuda.synchronize()
+    out = {"arch": "DDPM-256 + cross-attention to a 77 x 768 prompt embedding in 6 AttnBlocks (8 heads), random init",
+           "jvp_pass_ms": a.elapsed_time(b) / reps, "vjp_pass_ms": b.elapsed_time(c) / reps,
+           "fwd_b1_ms": c.elapsed_time(d) / reps,
+           "jvp_probes_per_s": K_RANK * reps / (a.elapsed_time(b) * 1e-3)}
+    net.release_plans()
+    del net
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_probe_shard(unet, sched, dev, world, rank, R, barrier, max_over_ranks, n_it=3, k=64):
     """BASELINE config 3 under torchrun: rank-64 subspace iteration (mask = None, t idx 40), probe
     tangents sharded over the ranks (64 / world rows each, probed in chunks of <= 25), one all-gather
@@ -520,11 +561,12 @@ def run_ours(args):
             probes["fwd_b%d_ms" % bsz] = a.elapsed_time(b) / reps
 
     # ---- single-edit latency (north_star: < 1 s), the drop-in driver, the small HBM-bound kernels ----
-    latency_b1 = dropin = bw = None
+    latency_b1 = dropin = bw = text = None
     if rank == 0 and world == 1 and not args.no_extras:
         latency_b1 = measure_latency_b1(pipe, gen, R)
         dropin = measure_dropin(unet, dev, R)
         bw = measure_bandwidth_kernels(dev, pk["hbm_gbs"])
+        text = measure_text_unet(dev, R)
     # ---- multi-GPU data path with a collective: one edit by all ranks, and BASELINE config 3 ----
     sharded_latency = probe_shard = None
     if world > 1 and not args.no_extras:
@@ -603,7 +645,7 @@ def run_ours(args):
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "p2_ffhq": p2,
             "latency_b1_ms": latency_b1, "latency_b1_target_ms": 1000.0,
             "latency_b1_sharded": sharded_latency, "probe_shard": probe_shard,
-            "dropin_driver": dropin, "bandwidth_kernels": bw,
+            "dropin_driver": dropin, "bandwidth_kernels": bw, "text_conditioned": text,
         }
         if probes:
             line.update(probes)

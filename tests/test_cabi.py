@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from loco_edit_b200 import _lib
-from loco_edit_b200.weights import DDPM256, ddpm_param_shapes
+from loco_edit_b200.weights import DDPM256, DDPM256_TEXT, ddpm_param_shapes, if_standin_arch
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -28,6 +28,48 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libloco_b200.so does not export %s" % n
         assert n in _lib.PROTOTYPES, "python binding lacks a prototype for %s" % n
     assert lib.loco_abi_version() == 3
+
+
+@pytest.mark.parametrize("arch_name", ["DDPM256_TEXT", "if_standin"])
+def test_text_conditioned_registry_and_plan_sizing(arch_name):
+    """U-Nets with cross-attention layers (ctx_dim > 0): the library's parameter registry == the Python
+    shape table (norm2 / q2 / kv2 / proj_out2 per AttnBlock), plan sizing is host logic, and a bad
+    head split is refused at plan creation."""
+    from loco_edit_b200.unet import _make_arch
+    a = DDPM256_TEXT if arch_name == "DDPM256_TEXT" else if_standin_arch(64)
+    lib = _lib.load()
+    h = C.c_void_p()
+    arch = _make_arch(a)
+    assert arch.ctx_dim == 768
+    _lib.check(lib.loco_unet_create(C.byref(arch), C.byref(h)))
+    try:
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        nd = C.c_int()
+        got = {}
+        for i in range(lib.loco_unet_num_params(h)):
+            _lib.check(lib.loco_unet_param_info(h, i, buf, 256, shape, C.byref(nd)))
+            got[buf.value.decode()] = [shape[j] for j in range(nd.value)]
+        want = {k: list(v) for k, v in ddpm_param_shapes(a).items()}
+        assert got == want
+        n_attn = sum(1 for k in want if k.endswith(".kv2.weight"))
+        assert n_attn == (6 if arch_name == "DDPM256_TEXT" else 11) and all(v == [2 * want[k[:-10] + "q2.bias"][0], 768]
+                                                                           for k, v in want.items() if k.endswith(".kv2.weight"))
+        p = C.c_void_p()
+        _lib.check(lib.loco_plan_create(h, 1, 5, 5, C.byref(p)))
+        assert lib.loco_plan_workspace_bytes(p) > 1e8
+        lib.loco_plan_destroy(p)
+    finally:
+        lib.loco_unet_destroy(h)
+    # 512 channels in 3 heads is not a multiple of 64 per head: refused when the plan is sized
+    bad = _make_arch(dict(a, ctx_heads=3))
+    _lib.check(lib.loco_unet_create(C.byref(bad), C.byref(h)))
+    try:
+        p = C.c_void_p()
+        assert lib.loco_plan_create(h, 1, 0, 0, C.byref(p)) != 0
+        assert b"cross-attention" in lib.loco_last_error()
+    finally:
+        lib.loco_unet_destroy(h)
 
 
 def test_model_registry_matches_reference_state_dict(golden_dir):
