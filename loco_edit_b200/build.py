@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libloco_b200.so")
-SOURCES = ["conv_gemm.cu", "layers.cu", "attention.cu", "attention_tc.cu", "pullback.cu", "unet.cu", "api.cu"]
+SOURCES = ["conv_gemm.cu", "layers.cu", "edge_mma.cu", "attention.cu", "attention_tc.cu", "pullback.cu", "unet.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -216,7 +216,7 @@ edge_reduce128_kernel(View in, const float* __restrict__ Wr, const float* __rest
 #pragma unroll
           for (int q = 0; q < kStrip; ++q) {
             const float4 v = win[q + c];
-            acc[q * 3 + j] += (v.x * w.x + v.y * w.y) + (v.z * w.z + v.w * w.w);
+            acc[q * 3 + j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[q * 3 + j]))));
           }
         }
       }
@@ -1038,6 +1038,7 @@ int pow2_scale(const float* v, long long n, float target, float* scale2, unsigne
 
 int edge_conv_expand(const float* in3, const float* We, const float* bias, int bias_rows, View out,
                      int flip, int round_out, cudaStream_t s, const float* scale_dev, int scale_from) {
+  if (edge_mma_eligible(out)) return edge_conv_expand_mma(in3, We, bias, bias_rows, out, flip, s, scale_dev, scale_from);
   if (out.C == 128 && out.W % kStrip == 0) {
     const long long nstrips = (long long)out.N * out.H * (out.W / kStrip);
     ProfScope prof(2, 0, s);
@@ -1061,6 +1062,7 @@ int edge_conv_expand(const float* in3, const float* We, const float* bias, int b
 }
 int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows, float* out3,
                      int flip, cudaStream_t s, const float* scale_dev, int scale_from) {
+  if (edge_mma_eligible(in)) return edge_conv_reduce_mma(in, Wr, bias, bias_rows, out3, flip, s, scale_dev, scale_from);
   if (in.C == 128 && in.W % kStrip == 0) {
     const long long nstrips = (long long)in.N * in.H * (in.W / kStrip);
     ProfScope prof(2, 0, s);
@@ -1120,6 +1122,7 @@ int layers_init() {
   LOCO_CARVE(scale_shift_affine_kernel);
 #undef LOCO_CARVE2
 #undef LOCO_CARVE
+  LOCO_TRY(edge_mma_init());
   // occupancy queries up front (never inside a stream capture)
   for (int b = 0; b < 2; ++b) {
     const int bd = b ? 192 : 256;

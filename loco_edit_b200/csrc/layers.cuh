@@ -59,6 +59,14 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
 // out (+)= scale * nearest_upsample(in), out = 2H x 2W.  scale 1: the DDPM Upsample / P2 up ResBlock
 // (ddpm/diffusion.py:816-832, guided_diffusion/unet.py:95-124); scale 1/4: VJP of the 2x2 avg-pool.
 int upsample2x(View in, View out, float scale, int accumulate, int round_out, cudaStream_t s);
+// tensor-core (mma.sync) versions of the two edge convolutions for fp16 tensors with 128 channels whose
+// image is a multiple of 8 x 32 pixels (edge_mma.cu); LOCO_EDGE_MMA=0 keeps the CUDA-core kernels
+int edge_mma_init();
+bool edge_mma_eligible(const View& v);
+int edge_conv_reduce_mma(View in, const float* Wr, const float* bias, int bias_rows, float* out3, int flip, cudaStream_t s,
+                         const float* scale_dev, int scale_from);
+int edge_conv_expand_mma(const float* in3, const float* We, const float* bias, int bias_rows, View out, int flip,
+                         cudaStream_t s, const float* scale_dev, int scale_from);
 // K_c | V_c = ctx W^T + b for the first n_tok of `rows` context rows (the rest zero), tf32-rounded
 int context_kv(const float* ctx, int n_tok, int dim, const float* w, const float* b, int cout, int rows, float* out,
                cudaStream_t s);

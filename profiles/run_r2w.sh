@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2w_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2w_tests.log
-tail -3 gpurun_out/r2w_tests.log
-NS=1,6 python profiles/conv_sweep16.py 2>&1 | grep "16x16\|8x8\|32x32 256" | head -30
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2w_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2w_tests.log
+tail -12 gpurun_out/r2w_tests.log | cut -c1-300
 timeout 900 python bench.py --steps 1 --warmup 1 --no-p2 --no-cpu-baseline > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err
 python - <<'PY'
 import json
