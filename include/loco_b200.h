@@ -32,7 +32,18 @@ typedef struct loco_plan loco_plan_t;
  * kind 1: guided-diffusion UNetModel as built by create_model(**P2_DICT),
  *         src/models/guided_diffusion/script_util.py:166-190,379-435 and unet.py:398-684
  *         (scale-shift norm, ResBlock up/down-sampling, learn_sigma: eps = first 3 of 6 output
- *         channels, multi-head "legacy" attention with head_ch channels per head). */
+ *         channels, multi-head "legacy" attention with head_ch channels per head);
+ * kind 2: decoder half of a latent-diffusion VAE -- the `self.vae.decode(z).sample` inside the Stable
+ *         Diffusion twin's get_x0, src/modules/edit.py:764-774 (diffusers AutoencoderKL.decode =
+ *         Decoder(post_quant_conv(z)); module tree conv_in, mid.{block_1, attn_1, block_2},
+ *         up.{l}.block.{0..num_res_blocks} [+ up.{l}.upsample.conv], norm_out, conv_out with the
+ *         ResnetBlock / AttnBlock / Upsample of src/models/ddpm/diffusion.py:816-966, no timestep input).
+ *         `resolution` is the LATENT resolution; rows of the input are [in_ch, R, R], rows of the output
+ *         [out_ch, R << (n_levels-1), R << (n_levels-1)]; `t` is ignored.  Same plan / forward / vjp
+ *         entry points as the U-Nets (fused primal + k-tangent pass, k-cotangent pass).
+ * in_ch / out_ch other than 3 (the 4-channel latents of the Stable-Diffusion-shaped U-Net, kind 0, and
+ * of the decoder): that end of the network runs on the tcgen05 conv kernels over a thin side zero-padded
+ * to 64 channels instead of the 3-channel edge kernels. */
 typedef struct loco_arch {
   int ch;                  /* base channels (multiple of 128) */
   int n_levels;            /* len(ch_mult) <= 8 */
@@ -41,9 +52,9 @@ typedef struct loco_arch {
   int n_attn;              /* len(attn_resolutions) <= 4 */
   int attn_resolutions[4];
   int resolution;          /* input H = W */
-  int in_ch, out_ch;       /* 3, 3 */
+  int in_ch, out_ch;       /* 3, 3 (image-space U-Nets); 4, 4 (latent U-Net, kind 0); 4, 3 (kind 2); each 1..4 */
   float gn_eps;            /* 1e-6 (DDPM) / 1e-5 (guided diffusion) */
-  int kind;                /* 0 = DDPM, 1 = P2 / guided diffusion */
+  int kind;                /* 0 = DDPM, 1 = P2 / guided diffusion, 2 = VAE decoder */
   int head_ch;             /* kind 1: channels per attention head (num_head_channels); else 0 */
   int ctx_dim;             /* kind 0: > 0 adds a cross-attention sub-block to every AttnBlock, keys / values =
                               Linear(ctx_dim -> 2C) of a prompt embedding (text-conditioned twins); 0 = none */
@@ -93,8 +104,10 @@ int loco_plan_info(const loco_plan_t* p, double* fwd_flops, double* vjp_flops, i
                    int* vjp_ops);
 
 /* eps = unet(x, t): replaces `self.unet(xt, t)` (src/modules/edit.py:2151, 2375, 2572).
- * x, eps: [n_primal + n_tangent, 3, R, R]; tangent rows hold dx on input and d eps on output,
- * i.e. the forward-mode product torch.func.jacfwd computes at src/modules/edit.py:2455. */
+ * x: [n_primal + n_tangent, in_ch, R, R], eps: the same rows of the network output ([.., out_ch, R, R];
+ * kind 2: the decoded images [.., out_ch, R << (n_levels-1), ...], replacing `self.vae.decode(z).sample`,
+ * src/modules/edit.py:770); tangent rows hold dx on input and d eps on output, i.e. the forward-mode
+ * product torch.func.jacfwd computes at src/modules/edit.py:2455 (:880 for the latent-space twin). */
 int loco_unet_forward(loco_plan_t* p, const float* x, float t, float* eps, void* stream);
 /* Conditional U-Net eps(x, t, c): `cond` [4*ch] (device; NULL = unconditional) is added to the
  * timestep embedding of every following loco_unet_forward of this plan -- the class / pooled-text
@@ -110,7 +123,8 @@ int loco_plan_set_condition(loco_plan_t* p, const float* cond, void* stream);
  * The context is a constant of x -> eps(x, t, ctx), so JVP / VJP differentiate the query side only. */
 int loco_plan_set_context(loco_plan_t* p, const float* ctx, int n_tokens, void* stream);
 /* gx[j] = (d eps / d x)^T g_eps[j] at the primal point of the last loco_unet_forward: replaces
- * the k backward passes of torch.autograd.functional.jacobian (src/modules/edit.py:2479). */
+ * the k backward passes of torch.autograd.functional.jacobian (src/modules/edit.py:2479; :893 for the
+ * latent-space twin, where g_eps rows have the shape of the network OUTPUT and gx rows of its input). */
 int loco_unet_vjp(loco_plan_t* p, const float* g_eps, float* gx, void* stream);
 
 /* ---------------- pull-back (power method) ---------------- */

@@ -54,9 +54,11 @@ int loco_unet_create(const loco_arch_t* a, loco_unet_t** out) {
   LOCO_REQUIRE(a && out, "loco_unet_create: null argument");
   LOCO_REQUIRE(a->n_levels >= 1 && a->n_levels <= 8 && a->n_attn >= 0 && a->n_attn <= 4,
                "loco_unet_create: bad level/attention counts");
-  LOCO_REQUIRE(a->in_ch == 3 && a->out_ch == 3, "loco_unet_create: only 3-channel images");
+  LOCO_REQUIRE(a->in_ch >= 1 && a->in_ch <= 4 && a->out_ch >= 1 && a->out_ch <= 4,
+               "loco_unet_create: 1..4 input / output channels (got %d / %d)", a->in_ch, a->out_ch);
+  LOCO_REQUIRE(a->kind != 1 || (a->in_ch == 3 && a->out_ch == 3), "loco_unet_create: the guided-diffusion U-Net takes 3-channel images");
   LOCO_REQUIRE(a->ch % 128 == 0 && a->ch >= 128, "loco_unet_create: ch must be a multiple of 128");
-  LOCO_REQUIRE((a->resolution >> (a->n_levels - 1)) >= 4 &&
+  LOCO_REQUIRE((a->kind == 2 ? a->resolution : (a->resolution >> (a->n_levels - 1))) >= 4 &&
                    (a->resolution & (a->resolution - 1)) == 0,
                "loco_unet_create: resolution must be a power of two, >= 4 at the coarsest level");
   Arch A;
@@ -65,8 +67,8 @@ int loco_unet_create(const loco_arch_t* a, loco_unet_t** out) {
   A.num_res_blocks = a->num_res_blocks; A.n_attn = a->n_attn;
   for (int i = 0; i < 4; ++i) A.attn_resolutions[i] = a->attn_resolutions[i];
   A.resolution = a->resolution; A.in_ch = a->in_ch; A.out_ch = a->out_ch; A.gn_eps = a->gn_eps;
-  LOCO_REQUIRE(a->kind == 0 || a->kind == 1, "loco_unet_create: unknown architecture kind %d", a->kind);
-  LOCO_REQUIRE(a->kind == 0 || (a->head_ch > 0 && a->head_ch % 4 == 0),
+  LOCO_REQUIRE(a->kind >= 0 && a->kind <= 2, "loco_unet_create: unknown architecture kind %d", a->kind);
+  LOCO_REQUIRE(a->kind != 1 || (a->head_ch > 0 && a->head_ch % 4 == 0),
                "loco_unet_create: guided-diffusion U-Net needs head_ch > 0");
   A.kind = a->kind; A.head_ch = a->kind == 1 ? a->head_ch : 0;
   LOCO_REQUIRE(a->ctx_dim >= 0 && (a->ctx_dim == 0 || (a->kind == 0 && a->ctx_dim % 4 == 0 && a->ctx_heads >= 1)),
@@ -243,8 +245,8 @@ static int pullback_probe_impl(loco_plan_t* p, const float* xt, float t, float a
   Plan& P = *p->p;
   LOCO_REQUIRE(P.NP == 1 && P.NT == k && P.NC == k, "loco_pullback_probe: plan is (%d,%d,%d), need (1,%d,%d)",
                P.NP, P.NT, P.NC, k, k);
-  const int R = P.model->arch.resolution;
-  LOCO_REQUIRE(d == 3LL * R * R, "loco_pullback_probe: d=%lld does not match the model", d);
+  LOCO_REQUIRE(P.in_elems() == P.out_elems(), "loco_pullback_probe: needs a network with equal input and output shapes");
+  LOCO_REQUIRE(d == P.in_elems(), "loco_pullback_probe: d=%lld does not match the model", d);
   cudaStream_t s = ST(stream);
   const size_t kd = align_up((size_t)k * d * 4, 256);
   const size_t k1d = align_up((size_t)(k + 1) * d * 4, 256);

@@ -735,6 +735,265 @@ gn_apply_fwd16_kernel(View x, const double* __restrict__ stats, const float* __r
   }
 }
 
+// ---- small sites: statistics + apply in ONE launch ------------------------------------------------
+// The <= 64^2 GroupNorm sites of the Jacobian programs are launch-latency bound (two ~6 us kernels
+// for a tensor that sits in L2).  Here a block owns one (batch row, group): it reads the group's
+// slice of the row (and of the primal row) twice from L2 -- once for the sums, once to apply -- so a
+// site is one launch, needs no cleared statistics buffer and no atomics (bit-reproducible).
+//   MODE 0: primal rows y = act(gn(x)), tangent rows the JVP rule; the sums are also stored in the
+//           statistics buffer (the VJP pass reads the primal row's).
+//   MODE 1: VJP rule for cotangent row blockIdx.y at the primal point (xp, pstats).
+// A thread moves VW = 8 (or 4 when a group has 4 channels) consecutive channels of a pixel.
+constexpr int kGnSmallMax = 32768;            // elements of one (row, group) slice
+
+__device__ __forceinline__ double block_sum2(double a, double b, double* sh, double& out_b) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { sh[2 * w] = a; sh[2 * w + 1] = b; }
+  __syncthreads();
+  double ra = 0.0, rb = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ra += sh[2 * i]; rb += sh[2 * i + 1]; }   // fixed order
+  out_b = rb;
+  return ra;
+}
+
+template <int MODE, bool F16, int VW>
+__global__ void __launch_bounds__(256)
+gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats, double* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, int round_out,
+                const float* __restrict__ addend, long long add_sN, long long add_sW, int accumulate, View out) {
+  __shared__ double sh[16];
+  using Elem = typename std::conditional<F16, __half, float>::type;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = x.C, cg = C / kGroups, vpp = cg / VW;
+  const int HW = x.H * x.W, nvec = HW * vpp;
+  const double cnt = (double)HW * cg;
+  const View& rows = (MODE == 0) ? x : gy;
+  const bool tangent = (MODE == 0) && n >= n_primal;
+  const Elem* xrow = reinterpret_cast<const Elem*>(x.ptr) + ((MODE == 0 && !tangent) ? (long long)n * x.sN : 0) + g * cg;
+  const Elem* rrow = reinterpret_cast<const Elem*>(rows.ptr) + (long long)n * rows.sN + g * cg;
+  auto ldv = [&](const Elem* base, long long off, float (&v)[VW]) {
+    if (F16) {
+      if (VW == 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(base + off);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k])); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(base + off);
+        const uint32_t w[2] = {u.x, u.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k])); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < VW / 4; ++q) {
+        const float4 f = *reinterpret_cast<const float4*>(base + off + 4 * q);
+        v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+      }
+    }
+  };
+  auto stv = [&](Elem* base, long long off, const float (&v)[VW]) {
+    if (F16) {
+      uint32_t w[VW / 2];
+#pragma unroll
+      for (int k = 0; k < VW / 2; ++k) { const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<const uint32_t*>(&h); }
+      if (VW == 8) *reinterpret_cast<uint4*>(base + off) = make_uint4(w[0], w[1], w[2], w[VW / 2 - 2], w[VW / 2 - 1]);
+      else *reinterpret_cast<uint2*>(base + off) = make_uint2(w[0], w[1]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < VW / 4; ++q)
+        *reinterpret_cast<float4*>(base + off + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  };
+  // ---- statistics of the primal slice (mean, rstd) ----
+  float mu, rstd;
+  if (MODE == 1) {
+    const float2 mr = mean_rstd(pstats + g * 2, cnt, eps);
+    mu = mr.x; rstd = mr.y;
+  } else {
+    double s1 = 0.0, s2 = 0.0;
+    for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+      float v[VW];
+      ldv(xrow, (long long)(e / vpp) * x.sW + (e % vpp) * VW, v);
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int i = 0; i < VW; ++i) { a += v[i]; b += v[i] * v[i]; }
+      s1 += a; s2 += b;
+    }
+    double t2;
+    const double t1 = block_sum2(s1, s2, sh, t2);
+    if (!tangent && threadIdx.x == 0) { stats[((long long)n * kGroups + g) * 2] = t1; stats[((long long)n * kGroups + g) * 2 + 1] = t2; }
+    const double m = t1 / cnt, var = t2 / cnt - m * m;
+    mu = (float)m; rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+  }
+  float gs[VW], bs[VW];
+  // channel-dependent affine: a thread may see any of the vpp vectors of a pixel, so it is loaded per vector below
+  // ---- primal rows of the forward program: apply and leave ----
+  Elem* orow = reinterpret_cast<Elem*>(out.ptr) + (long long)n * out.sN + g * cg;
+  if (MODE == 0 && !tangent) {
+    for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+      const int p = e / vpp, c0 = (e % vpp) * VW;
+      float v[VW], o[VW];
+      ldv(xrow, (long long)p * x.sW + c0, v);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) { gs[i] = gamma[g * cg + c0 + i]; bs[i] = beta[g * cg + c0 + i]; }
+#pragma unroll
+      for (int i = 0; i < VW; ++i) {
+        const float u = gs[i] * ((v[i] - mu) * rstd) + bs[i];
+        o[i] = silu ? u * fast_sigmoid(u) : u;
+        if (round_out && !F16) o[i] = round_tf32(o[i]);
+      }
+      stv(orow, (long long)p * out.sW + c0, o);
+    }
+    return;
+  }
+  // ---- tangent / cotangent rows: sums against the primal slice ----
+  double s1 = 0.0, s2 = 0.0;
+  for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+    const int p = e / vpp, c0 = (e % vpp) * VW;
+    float xv[VW], rv[VW];
+    ldv(xrow, (long long)p * x.sW + c0, xv);
+    ldv(rrow, (long long)p * rows.sW + c0, rv);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < VW; ++i) {
+      float w = rv[i];
+      if (MODE == 1) {
+        const float gm = gamma[g * cg + c0 + i];
+        const float u = gm * ((xv[i] - mu) * rstd) + beta[g * cg + c0 + i];
+        float d = 1.0f;
+        if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
+        w = gm * d * rv[i];
+      }
+      a += w; b += w * xv[i];
+    }
+    s1 += a; s2 += b;
+  }
+  double t2;
+  const double t1 = block_sum2(s1, s2, sh, t2);
+  if (MODE == 0 && threadIdx.x == 0) { stats[((long long)n * kGroups + g) * 2] = t1; stats[((long long)n * kGroups + g) * 2 + 1] = t2; }
+  const float m1 = (float)(t1 / cnt);
+  const float m2 = (float)((t2 - (double)mu * t1) * (double)rstd / cnt);
+  const Elem* arow = addend ? reinterpret_cast<const Elem*>(addend) + (long long)n * add_sN + g * cg : nullptr;
+  for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+    const int p = e / vpp, c0 = (e % vpp) * VW;
+    float xv[VW], rv[VW], o[VW];
+    ldv(xrow, (long long)p * x.sW + c0, xv);
+    ldv(rrow, (long long)p * rows.sW + c0, rv);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) {
+      const float gm = gamma[g * cg + c0 + i];
+      const float xh = (xv[i] - mu) * rstd;
+      const float u = gm * xh + beta[g * cg + c0 + i];
+      float d = 1.0f;
+      if (silu) { const float sg = fast_sigmoid(u); d = sg * (1.0f + u * (1.0f - sg)); }
+      const float coef = d * gm;
+      if (MODE == 0) o[i] = coef * rstd * (rv[i] - m1 - xh * m2);
+      else o[i] = rstd * (coef * rv[i] - m1 - xh * m2);
+    }
+    if (MODE == 1 && arow) {
+      float av[VW];
+      ldv(arow, (long long)p * add_sW + c0, av);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) o[i] += av[i];
+    }
+    if (MODE == 1 && accumulate) {
+      float cv[VW];
+      ldv(orow, (long long)p * out.sW + c0, cv);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) o[i] += cv[i];
+    }
+    if (round_out && !F16) {
+#pragma unroll
+      for (int i = 0; i < VW; ++i) o[i] = round_tf32(o[i]);
+    }
+    stv(orow, (long long)p * out.sW + c0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thin edges: <= 4-channel NCHW fp32 tensors <-> zero-padded 64-channel NHWC activations
+// ------------------------------------------------------------------------------------------------
+// The 4-channel ends of the latent-space networks (Stable-Diffusion-shaped U-Net: 4 -> C and C -> 4;
+// VAE decoder: 4 -> C) run on the ordinary tcgen05 conv kernels over a thin side padded with zero
+// channels to one K block (64): the padding costs < 3 % of the network's FLOPs and needs no new GEMM
+// kernel.  These two kernels are the NCHW <-> padded-NHWC boundary, with the power-of-two range scale
+// of the tangent / cotangent rows and the optional c x c channel mix of `post_quant_conv`
+// (diffusers AutoencoderKL.decode = decoder(post_quant_conv(z)), src/modules/edit.py:770).
+// mix: [c*c + c] = 1x1 weight [o][i] then bias; transposed = 1 applies the transpose (VJP), no bias.
+template <bool F16>
+__global__ void __launch_bounds__(256)
+thin_pad_kernel(const float* __restrict__ in, int c, View out, const float* __restrict__ mix, int bias_rows,
+                const float* __restrict__ scale_dev, int scale_from, int round_out) {
+  constexpr int VPP = F16 ? kThinPad / 8 : kThinPad / 4;      // 16-byte vectors per pixel
+  const long long HW = (long long)out.H * out.W;
+  const long long total = (long long)out.N * HW * VPP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % VPP);
+    const long long p = i / VPP;
+    const long long pix = p % HW;
+    const int n = (int)(p / HW);
+    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    if (v == 0) {
+      float raw[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < c; ++j) raw[j] = in[((long long)n * c + j) * HW + pix];
+      if (mix != nullptr) {
+        for (int o = 0; o < c; ++o) {
+          float a = n < bias_rows ? mix[c * c + o] : 0.f;
+          for (int j = 0; j < c; ++j) a += mix[o * c + j] * raw[j];
+          val[o] = a;
+        }
+      } else {
+        for (int j = 0; j < c; ++j) val[j] = raw[j];
+      }
+      const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[0] : 1.f;
+      for (int j = 0; j < 4; ++j) { val[j] *= sc; if (round_out && !F16) val[j] = round_tf32(val[j]); }
+    }
+    const long long y = pix / out.W, x = pix % out.W;
+    const long long o = n * out.sN + y * out.sH + x * out.sW;
+    if (F16) {
+      const __half2 a = __floats2half2_rn(val[0], val[1]), b = __floats2half2_rn(val[2], val[3]);
+      uint4 u = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b), 0u, 0u);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out.ptr) + o + v * 8) = u;
+    } else {
+      *reinterpret_cast<float4*>(out.ptr + o + v * 4) = make_float4(val[0], val[1], val[2], val[3]);
+    }
+  }
+}
+template <bool F16>
+__global__ void __launch_bounds__(256)
+thin_extract_kernel(View in, int c, float* __restrict__ out, const float* __restrict__ mix,
+                    const float* __restrict__ scale_dev, int scale_from) {
+  const long long HW = (long long)in.H * in.W;
+  const long long total = (long long)in.N * HW;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long pix = p % HW;
+    const int n = (int)(p / HW);
+    const long long y = pix / in.W, x = pix % in.W;
+    const long long o = n * in.sN + y * in.sH + x * in.sW;
+    float val[4];
+    if (F16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(in.ptr) + o);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      val[0] = a.x; val[1] = a.y; val[2] = b.x; val[3] = b.y;
+    } else {
+      const float4 f = *reinterpret_cast<const float4*>(in.ptr + o);
+      val[0] = f.x; val[1] = f.y; val[2] = f.z; val[3] = f.w;
+    }
+    const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[1] : 1.f;
+    for (int j = 0; j < c; ++j) {
+      float a = val[j];
+      if (mix != nullptr) {                       // transpose of the channel mix: g_in[j] = sum_o W[o][j] g[o]
+        a = 0.f;
+        for (int o2 = 0; o2 < c; ++o2) a += mix[o2 * c + j] * val[o2];
+      }
+      out[((long long)n * c + j) * HW + pix] = a * sc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Resampling / add
 // ------------------------------------------------------------------------------------------------
@@ -1245,6 +1504,28 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
   if (h) { if (extra) LOCO_GN_VJP(true, 4); else LOCO_GN_VJP(true, 8); }
   else { if (extra) LOCO_GN_VJP(false, 4); else LOCO_GN_VJP(false, 8); }
 #undef LOCO_GN_VJP
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int thin_pad(const float* in_nchw, int c, View out, const float* mix, int bias_rows, const float* scale_dev,
+             int scale_from, int round_out, cudaStream_t s) {
+  LOCO_REQUIRE(c >= 1 && c <= 4 && out.C == kThinPad, "thin_pad: %d channels into a %d-channel tensor", c, out.C);
+  LOCO_REQUIRE((((uintptr_t)out.ptr) & 15) == 0 && out.sW % 8 == 0 && out.sH % 8 == 0 && out.sN % 8 == 0, "thin_pad: view not aligned");
+  const long long total = (long long)out.N * out.H * out.W * (out.half ? kThinPad / 8 : kThinPad / 4);
+  const int grid = grid_for(total, 256, num_sms() * 8);
+  if (out.half) thin_pad_kernel<true><<<grid, 256, 0, s>>>(in_nchw, c, out, mix, bias_rows, scale_dev, scale_from, round_out);
+  else thin_pad_kernel<false><<<grid, 256, 0, s>>>(in_nchw, c, out, mix, bias_rows, scale_dev, scale_from, round_out);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int thin_extract(View in, int c, float* out_nchw, const float* mix, const float* scale_dev, int scale_from, cudaStream_t s) {
+  LOCO_REQUIRE(c >= 1 && c <= 4 && in.C == kThinPad, "thin_extract: %d channels out of a %d-channel tensor", c, in.C);
+  LOCO_REQUIRE((((uintptr_t)in.ptr) & 15) == 0 && in.sW % 8 == 0 && in.sH % 8 == 0 && in.sN % 8 == 0, "thin_extract: view not aligned");
+  const long long total = (long long)in.N * in.H * in.W;
+  const int grid = grid_for(total, 256, num_sms() * 8);
+  if (in.half) thin_extract_kernel<true><<<grid, 256, 0, s>>>(in, c, out_nchw, mix, scale_dev, scale_from);
+  else thin_extract_kernel<false><<<grid, 256, 0, s>>>(in, c, out_nchw, mix, scale_dev, scale_from);
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -39,6 +39,17 @@ int edge_conv_reduce(View in, const float* Wr, const float* bias, int bias_rows,
 // scale2[0] = 2^floor(log2(target / max|v|)), scale2[1] = its inverse; tmp: one device word of scratch
 int pow2_scale(const float* v, long long n, float target, float* scale2, unsigned* tmp, cudaStream_t s);
 
+// ---- thin edges (<= 4 channels) as zero-padded 64-channel tensors for the tcgen05 conv kernels ----
+// (4-channel latents of the Stable-Diffusion-shaped U-Net and the VAE decoder)
+constexpr int kThinPad = 64;
+// out[n,y,x,0:c] = scale(n) * (mix ? W in + b*(n<bias_rows) : in)[n,:,y,x], out[...,c:64] = 0; in is NCHW fp32.
+// mix = [c*c + c] device floats (1x1 conv weight [o][i], then bias) or null; scale(n) = scale_dev[0] for
+// rows n >= scale_from (1 if scale_dev is null).
+int thin_pad(const float* in_nchw, int c, View out, const float* mix, int bias_rows, const float* scale_dev,
+             int scale_from, int round_out, cudaStream_t s);
+// out[n,j,y,x] = scale'(n) * (mix ? W^T in : in)[n,y,x,j] for j < c; scale'(n) = scale_dev[1] for rows >= scale_from.
+int thin_extract(View in, int c, float* out_nchw, const float* mix, const float* scale_dev, int scale_from, cudaStream_t s);
+
 // ---- GroupNorm(32 groups) + optional SiLU: forward, JVP and VJP ----
 // stats layout: double [rows][32][2].
 // Forward/JVP: rows < n_primal accumulate (sum x, sum x^2); tangent rows (sum dx, sum x0*dx) with

@@ -139,14 +139,14 @@ NormRef Model::add_norm(const std::string& prefix, int C) {
   add_slot(b);
   return n;
 }
-ResRef Model::add_res(const std::string& prefix, int cin, int cout) {
+ResRef Model::add_res(const std::string& prefix, int cin, int cout, bool temb) {
   ResRef r;
   r.cin = cin; r.cout = cout;
   r.n1 = add_norm(prefix + ".norm1", cin);
   r.c1 = add_conv(prefix + ".conv1", cin, cout, 3);
-  r.temb_off = tproj_rows;
-  tproj_rows += cout;
-  {
+  r.temb_off = temb ? tproj_rows : -1;
+  if (temb) {
+    tproj_rows += cout;
     // rows of the stacked projection matrix; arena offsets are fixed up after construction
     ParamSlot w; w.name = prefix + ".temb_proj.weight"; w.shape = {cout, arch.ch * 4};
     w.kind = ParamSlot::RAW; w.off_a = (size_t)r.temb_off; w.cout = -1;   // marker: temb matrix row
@@ -198,6 +198,60 @@ AttnRef Model::add_attn(const std::string& prefix, int C) {
     a.proj2 = add_conv(prefix + ".proj_out2", C, C, 1);
   }
   return a;
+}
+
+// 3x3 conv with a thin (<= 4 channel) side: GEMM packs over that side zero-padded to kThinPad
+ConvRef Model::add_thin_conv(const std::string& prefix, int cin, int cout) {
+  const int pcin = cin <= 4 ? kThinPad : cin, pcout = cout <= 4 ? kThinPad : cout;
+  ConvRef c;
+  c.cin = pcin; c.cout = pcout; c.ksz = 3;
+  const size_t n = (size_t)pcout * pcin * 9;
+  c.wf = alloc(n); c.wd = alloc(n); c.wf16 = alloc((n + 1) / 2); c.wd16 = alloc((n + 1) / 2);
+  c.bias = alloc(pcout);
+  ParamSlot w;
+  w.name = prefix + ".weight"; w.kind = ParamSlot::CONV_THIN; w.shape = {cout, cin, 3, 3};
+  w.off_a = c.wf; w.off_b = c.wd; w.off_a16 = c.wf16; w.off_b16 = c.wd16;
+  w.cout = cout; w.cin = cin; w.ksz = 3; w.pad_cin = pcin; w.pad_cout = pcout;
+  add_slot(w);
+  ParamSlot b;
+  b.name = prefix + ".bias"; b.shape = {cout}; b.kind = ParamSlot::RAW; b.off_a = c.bias;
+  add_slot(b);
+  return c;
+}
+
+// VAE decoder of a latent-diffusion model: diffusers' AutoencoderKL.decode (the `self.vae.decode` of
+// src/modules/edit.py:770) = Decoder(post_quant_conv(z)).  Module tree and parameter names of the
+// CompVis `Decoder` that AutoencoderKL restates (same ResnetBlock / AttnBlock / Upsample code as
+// src/models/ddpm/diffusion.py:816-966, without timestep input): conv_in, mid.{block_1, attn_1, block_2},
+// up.{l}.block.{0..nrb} (+ up.{l}.upsample.conv for l > 0), norm_out, conv_out.
+void Model::build_decoder() {
+  const Arch& a = arch;
+  const int ch = a.ch, L = a.n_levels;
+  thin = true;
+  has_pq = true;
+  pq_mix = alloc((size_t)a.in_ch * a.in_ch + a.in_ch);
+  {
+    ParamSlot s; s.kind = ParamSlot::RAW;
+    s.name = "post_quant_conv.weight"; s.shape = {a.in_ch, a.in_ch, 1, 1}; s.off_a = pq_mix; add_slot(s);
+    s.name = "post_quant_conv.bias"; s.shape = {a.in_ch}; s.off_a = pq_mix + (size_t)a.in_ch * a.in_ch; add_slot(s);
+  }
+  int block_in = ch * a.ch_mult[L - 1];
+  thin_in = add_thin_conv("decoder.conv_in", a.in_ch, block_in);
+  mid1 = add_res("decoder.mid.block_1", block_in, block_in, false);
+  mid_attn = add_attn("decoder.mid.attn_1", block_in);
+  mid2 = add_res("decoder.mid.block_2", block_in, block_in, false);
+  up_res.resize(L); up_attn.resize(L); up_sample.resize(L);
+  down_res.resize(L); down_attn.resize(L); down_sample.resize(L);
+  for (int l = L - 1; l >= 0; --l) {
+    const int block_out = ch * a.ch_mult[l];
+    for (int b = 0; b < a.num_res_blocks + 1; ++b) {
+      up_res[l].push_back(add_res("decoder.up." + std::to_string(l) + ".block." + std::to_string(b), block_in, block_out, false));
+      block_in = block_out;
+    }
+    if (l != 0) up_sample[l] = add_conv("decoder.up." + std::to_string(l) + ".upsample.conv", block_in, block_in, 3);
+  }
+  norm_out = add_norm("decoder.norm_out", block_in);
+  thin_out = add_thin_conv("decoder.conv_out", block_in, a.out_ch);
 }
 
 static bool in_list(const int* lst, int n, int v) {
@@ -252,7 +306,7 @@ void Model::finish_temb() {
 }
 
 Model::Model(const Arch& a) : arch(a) {
-  if (a.kind == 1) build_p2(); else build_ddpm();
+  if (a.kind == 2) build_decoder(); else if (a.kind == 1) build_p2(); else build_ddpm();
   finish_temb();
 }
 
@@ -349,8 +403,11 @@ void Model::build_ddpm() {
     s.name = "temb.dense.1.weight"; s.shape = {temb_ch, temb_ch}; s.off_a = temb_w1; add_slot(s);
     s.name = "temb.dense.1.bias"; s.shape = {temb_ch}; s.off_a = temb_b1; add_slot(s);
   }
-  conv_in_w = alloc(27 * ch); conv_in_b = alloc(ch);
-  {
+  thin = a.in_ch != 3 || a.out_ch != 3;     // latent-space U-Net (4 channels): padded tensor-core edges
+  if (thin) {
+    thin_in = add_thin_conv("conv_in", a.in_ch, ch);
+  } else {
+    conv_in_w = alloc(27 * ch); conv_in_b = alloc(ch);
     ParamSlot s;
     s.name = "conv_in.weight"; s.shape = {ch, a.in_ch, 3, 3}; s.kind = ParamSlot::CONV_EDGE_IN;
     s.off_a = conv_in_w; s.cout = ch; add_slot(s);
@@ -398,8 +455,10 @@ void Model::build_ddpm() {
     }
   }
   norm_out = add_norm("norm_out", block_in);
-  conv_out_w = alloc(27 * block_in); conv_out_b = alloc(64);
-  {
+  if (thin) {
+    thin_out = add_thin_conv("conv_out", block_in, a.out_ch);
+  } else {
+    conv_out_w = alloc(27 * block_in); conv_out_b = alloc(64);
     ParamSlot s;
     s.name = "conv_out.weight"; s.shape = {a.out_ch, block_in, 3, 3}; s.kind = ParamSlot::CONV_EDGE_OUT;
     s.off_a = conv_out_w; s.cin = block_in; add_slot(s);
@@ -437,6 +496,29 @@ int Model::load_param(const char* name, const float* src, long long numel, cudaS
       LOCO_TRY(pack_conv_dgrad16(src, w(sl.off_b16), sl.cout, sl.cin, sl.ksz, sl.ksz, sl.rows_total,
                                  sl.row_off, s));
       break;
+    case ParamSlot::CONV_THIN: {
+      // zero-pad the thin side to kThinPad channels in a scratch copy, then pack like any conv
+      const size_t row_real = (size_t)sl.cin * 9, row_pad = (size_t)sl.pad_cin * 9;
+      const size_t n = (size_t)sl.pad_cout * row_pad;
+      float* tmp = nullptr;
+      LOCO_CHECK_CUDA(cudaMalloc(&tmp, sizeof(float) * n));
+      int r = 0;
+      cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float) * n, s);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(tmp, sizeof(float) * row_pad, src, sizeof(float) * row_real, sizeof(float) * row_real,
+                              (size_t)sl.cout, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) {
+        r = pack_conv_fprop(tmp, w(sl.off_a), sl.pad_cout, sl.pad_cin, 3, 3, s);
+        if (r == 0) r = pack_conv_dgrad(tmp, w(sl.off_b), sl.pad_cout, sl.pad_cin, 3, 3, sl.pad_cout, 0, s);
+        if (r == 0) r = pack_conv_fprop16(tmp, w(sl.off_a16), sl.pad_cout, sl.pad_cin, 3, 3, s);
+        if (r == 0) r = pack_conv_dgrad16(tmp, w(sl.off_b16), sl.pad_cout, sl.pad_cin, 3, 3, sl.pad_cout, 0, s);
+      }
+      cudaStreamSynchronize(s);
+      cudaFree(tmp);
+      LOCO_CHECK_CUDA(e);
+      if (r != 0) return r;
+      break;
+    }
     case ParamSlot::CONV_EDGE_IN:
       LOCO_TRY(pack_conv_edge(src, w(sl.off_a), sl.cout, 1, s));
       break;
@@ -514,6 +596,16 @@ struct Plan::Impl {
   double* fstats = nullptr; size_t fstat_bytes = 0;
   double* bstats = nullptr; size_t bstat_bytes = 0;
 };
+
+long long Plan::in_elems() const {
+  const Arch& A = model->arch;
+  return (long long)A.in_ch * A.resolution * A.resolution;
+}
+long long Plan::out_elems() const {
+  const Arch& A = model->arch;
+  const long long Ro = A.kind == 2 ? ((long long)A.resolution << (A.n_levels - 1)) : A.resolution;
+  return (long long)A.out_ch * Ro * Ro;
+}
 
 int Plan::build(float* workspace) {
   if (!impl) impl = std::make_shared<Impl>();
@@ -705,11 +797,11 @@ int Plan::build(float* workspace) {
 
   // ---- staging buffers (NCHW images at the ABI) ----
   {
-    const size_t img = (size_t)3 * A.resolution * A.resolution;
-    I.in_buf = alloc_act((size_t)NB * img);
-    I.out_buf = alloc_act((size_t)NB * img);
-    I.gin_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
-    I.gout_buf = NC ? alloc_act((size_t)NC * img) : nullptr;
+    const size_t img_in = (size_t)in_elems(), img_out = (size_t)out_elems();
+    I.in_buf = alloc_act((size_t)NB * img_in);
+    I.out_buf = alloc_act((size_t)NB * img_out);
+    I.gin_buf = NC ? alloc_act((size_t)NC * img_out) : nullptr;
+    I.gout_buf = NC ? alloc_act((size_t)NC * img_in) : nullptr;
     I.t_dev = alloc_act(64);
     I.cond_dev = alloc_act(4 * (size_t)A.ch);
     I.tscale_dev = alloc_act(64);
@@ -774,7 +866,7 @@ int Plan::build(float* workspace) {
     }
     View h1 = Tf(Ho, Wo, R.cout);
     StatTarget t2; t2.st = alloc_fstat(NB); t2.cg = R.cout / 32; t2.choff = 0;
-    conv_fwd(CONV_3x3, a1r, h1, R.c1, R.scale_shift ? nullptr : tproj + R.temb_off, nullptr, nullptr, t2);
+    conv_fwd(CONV_3x3, a1r, h1, R.c1, (R.scale_shift || R.temb_off < 0) ? nullptr : tproj + R.temb_off, nullptr, nullptr, t2);
     View a2 = Tf(Ho, Wo, R.cout);
     double* st2 = gn_fwd(h1, R.n2, 1, 1, a2, t2.st, fuse_stats, aff);
     View sc;
@@ -893,6 +985,86 @@ int Plan::build(float* workspace) {
     cross_attn(R, mid, out);
   };
 
+  // ---- network input / output ends ----
+  // 3-channel images: CUDA-core / mma.sync edge convolutions; thin (4-channel latent) ends: zero-padded
+  // 64-channel tensors through the tcgen05 conv kernels (layers.cuh: thin_pad / thin_extract)
+  const bool sc16 = A16 != 0;     // range scaling of the tangent / cotangent rows (fp16 storage only)
+  auto emit_input = [&](TH& h0) {
+    Impl* Ip = impl.get();
+    const int np = NP;
+    if (M.thin) {
+      const int cin = A.in_ch, R0 = A.resolution;
+      View zin = Tf(R0, R0, kThinPad);
+      const float* mix = (M.has_pq && !dry) ? M.w(M.pq_mix) : nullptr;
+      I.fwd.push_back([=](cudaStream_t s) {
+        return thin_pad(Ip->cur_x, cin, zin, mix, np, sc16 ? Ip->tscale_dev : nullptr, np, 1, s);
+      });
+      conv_fwd(CONV_3x3, zin, h0.v, M.thin_in, nullptr, nullptr, &h0);
+      if (NC > 0) {
+        begin_group();
+        View gzin = Tg(R0, R0, kThinPad);
+        conv_bwd(CONV_3x3, h0.g, gzin, M.thin_in, 0);
+        push_b([=](cudaStream_t s) { return thin_extract(gzin, cin, Ip->cur_gx, mix, sc16 ? Ip->cscale_dev : nullptr, 0, s); });
+      }
+      return;
+    }
+    const float* wi = dry ? nullptr : M.w(M.conv_in_w);
+    const float* bi = dry ? nullptr : M.w(M.conv_in_b);
+    const View hv = h0.v, hg = h0.g;
+    I.fwd.push_back([=](cudaStream_t s) {
+      return edge_conv_expand(Ip->cur_x, wi, bi, np, hv, 0, 1, s, sc16 ? Ip->tscale_dev : nullptr, np);
+    });
+    if (NC > 0) {
+      begin_group();
+      push_b([=](cudaStream_t s) {
+        return edge_conv_reduce(hg, wi, nullptr, 0, Ip->cur_gx, 1, s, sc16 ? Ip->cscale_dev : nullptr, 0);
+      });
+    }
+  };
+  TH hfin;
+  if (A.kind == 2) {
+    // ---- VAE decoder (build_decoder): conv_in, mid, up levels L-1 .. 0, head ----
+    int res = A.resolution;
+    TH cur = new_tensor(res, res, M.mid1.cin);
+    emit_input(cur);
+    {
+      TH m1 = new_tensor(res, res, M.mid1.cout);
+      resblock(M.mid1, cur, m1);
+      TH m2 = new_tensor(res, res, M.mid1.cout);
+      attnblock(M.mid_attn, m1, m2);
+      TH m3 = new_tensor(res, res, M.mid2.cout);
+      resblock(M.mid2, m2, m3);
+      cur = m3;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      for (int b = 0; b < A.num_res_blocks + 1; ++b) {
+        const ResRef& R = M.up_res[l][b];
+        TH nxt = new_tensor(res, res, R.cout);
+        resblock(R, cur, nxt);
+        cur = nxt;
+      }
+      if (l != 0) {
+        const ConvRef& c = M.up_sample[l];
+        const int C = cur.v.C;
+        View hu = Tf(2 * res, 2 * res, C);
+        const View tv = cur.v;
+        I.fwd.push_back([=](cudaStream_t s) { return upsample2x(tv, hu, 1.f, 0, 0, s); });
+        TH nxt = new_tensor(2 * res, 2 * res, C);
+        conv_fwd(CONV_3x3, hu, nxt.v, c, nullptr, nullptr, &nxt);
+        if (NC > 0) {
+          begin_group();
+          View ghu = Tg(2 * res, 2 * res, C);
+          conv_bwd(CONV_3x3, nxt.g, ghu, c, 0);
+          const int f = writer_flag(cur.ids);
+          const View tg = cur.g;
+          push_b([=](cudaStream_t s) { return sumpool2x(ghu, tg, 1.f, f, 0, s); });
+        }
+        cur = nxt;
+        res *= 2;
+      }
+    }
+    hfin = cur;
+  } else {
   // ---- topology (reference: PullBackDDPM.forward, ddpm/diffusion.py:145-200) ----
   // simulate the encoder to learn the skip stack, then size the decoder concat buffers
   struct HsInfo { int C, res; };
@@ -937,24 +1109,7 @@ int Plan::build(float* workspace) {
   }
   auto hs_slot = [&](int i) -> TH& { return cbs[n_hs - 1 - i].skip; };
   // conv_in
-  {
-    TH& h0 = hs_slot(0);
-    Impl* Ip = impl.get();
-    const float* wi = dry ? nullptr : M.w(M.conv_in_w);
-    const float* bi = dry ? nullptr : M.w(M.conv_in_b);
-    const View hv = h0.v, hg = h0.g;
-    const int np = NP;
-    const bool sc16 = A16 != 0;     // range scaling of the tangent / cotangent rows (fp16 storage only)
-    I.fwd.push_back([=](cudaStream_t s) {
-      return edge_conv_expand(Ip->cur_x, wi, bi, np, hv, 0, 1, s, sc16 ? Ip->tscale_dev : nullptr, np);
-    });
-    if (NC > 0) {
-      begin_group();
-      push_b([=](cudaStream_t s) {
-        return edge_conv_reduce(hg, wi, nullptr, 0, Ip->cur_gx, 1, s, sc16 ? Ip->cscale_dev : nullptr, 0);
-      });
-    }
-  }
+  emit_input(hs_slot(0));
   // encoder
   int hs_top = 0;   // index of the last pushed skip tensor
   {
@@ -1003,7 +1158,6 @@ int Plan::build(float* workspace) {
     resblock(M.mid2, m2, cbs[0].dec);
   }
   // decoder
-  TH hfin;
   {
     int u = 0;
     for (int l = L - 1; l >= 0; --l) {
@@ -1046,8 +1200,27 @@ int Plan::build(float* workspace) {
       }
     }
   }
+  }   // U-Net topology
   // head
-  {
+  if (M.thin) {
+    const int res = hfin.v.H, C = hfin.v.C, cout = A.out_ch;
+    View a = Tf(res, res, C);
+    double* st = gn_fwd(hfin.v, M.norm_out, 1, 1, a, hfin.st_self.st, th_fused(hfin));
+    Impl* Ip = impl.get();
+    const int np = NP;
+    View o64 = Tf(res, res, kThinPad);
+    conv_fwd(CONV_3x3, a, o64, M.thin_out, nullptr, nullptr);
+    I.fwd.push_back([=](cudaStream_t s) { return thin_extract(o64, cout, Ip->cur_eps, nullptr, sc16 ? Ip->tscale_dev : nullptr, np, s); });
+    if (NC > 0) {
+      begin_group();
+      View g64 = Tg(res, res, kThinPad);
+      push_b([=](cudaStream_t s) { return thin_pad(Ip->cur_geps, cout, g64, nullptr, 0, sc16 ? Ip->cscale_dev : nullptr, 0, 1, s); });
+      View ga = Tg(res, res, C);
+      conv_bwd(CONV_3x3, g64, ga, M.thin_out, 0);
+      const int f = writer_flag(hfin.ids);
+      gn_bwd(row0(hfin.v), st, ga, M.norm_out, 1, nullptr, f, 1, hfin.g);
+    }
+  } else {
     const int res = hfin.v.H, C = hfin.v.C;
     View a = Tf(res, res, C);
     double* st = gn_fwd(hfin.v, M.norm_out, 1, 0, a, hfin.st_self.st, th_fused(hfin));
@@ -1055,7 +1228,6 @@ int Plan::build(float* workspace) {
     const float* wo = dry ? nullptr : M.w(M.conv_out_w);
     const float* bo = dry ? nullptr : M.w(M.conv_out_b);
     const int np = NP;
-    const bool sc16 = A16 != 0;
     I.fwd.push_back([=](cudaStream_t s) {
       return edge_conv_reduce(a, wo, bo, np, Ip->cur_eps, 0, s, sc16 ? Ip->tscale_dev : nullptr, np);
     });
@@ -1082,7 +1254,7 @@ int Plan::build(float* workspace) {
                                         cudaMemcpyHostToDevice);
       LOCO_REQUIRE(ce == cudaSuccess, "plan: cudaMemcpy(affine sites) failed: %s", cudaGetErrorString(ce));
     }
-    I.fwd[temb_op_index] = [=](cudaStream_t s) {
+    if (A.kind != 2) I.fwd[temb_op_index] = [=](cudaStream_t s) {
       LOCO_TRY(temb_forward(Ip->t_dev, Mp->arch.ch, Mp->w(Mp->temb_w0), Mp->w(Mp->temb_b0),
                             Mp->w(Mp->temb_w1), Mp->w(Mp->temb_b1), temb_scratch, Mp->arch.kind, Ip->cond_dev, s));
       LOCO_TRY(temb_project(temb_scratch + temb_ch, temb_ch, Mp->w(Mp->tproj_w), Mp->w(Mp->tproj_b),
@@ -1177,16 +1349,16 @@ int Plan::forward(const float* x, float t, float* eps_out, cudaStream_t s) {
   Impl& I = *impl;
   LOCO_REQUIRE(model->arch.ctx_dim == 0 || I.ctx_tokens > 0,
                "plan: this U-Net has cross-attention layers, call set_context() before forward()");
-  const size_t bytes = sizeof(float) * (size_t)(NP + NT) * 3 * model->arch.resolution * model->arch.resolution;
+  const size_t bytes = sizeof(float) * (size_t)(NP + NT) * in_elems();
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.in_buf, x, bytes, cudaMemcpyDeviceToDevice, s));
   LOCO_TRY(set_scalar(I.t_dev, t, s));
   if (act16 && NT > 0) {
-    const long long img = 3LL * model->arch.resolution * model->arch.resolution;
+    const long long img = in_elems();
     LOCO_TRY(pow2_scale(I.in_buf + (size_t)NP * img, (long long)NT * img, 64.f, I.tscale_dev, I.scale_tmp, s));
   }
   I.cur_x = I.in_buf; I.cur_eps = I.out_buf;
   LOCO_TRY(run_program(I.fwd, I.fstats, I.fstat_bytes, &I.fwd_graph, &I.fwd_graph_launches, s));
-  LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, bytes, cudaMemcpyDeviceToDevice, s));
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(eps_out, I.out_buf, sizeof(float) * (size_t)(NP + NT) * out_elems(), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
@@ -1222,15 +1394,15 @@ int Plan::vjp(const float* g_eps, float* gx, cudaStream_t s) {
   LOCO_REQUIRE(NC > 0, "plan: built without cotangent rows");
   DeviceGuard guard(device);
   Impl& I = *impl;
-  const size_t bytes = sizeof(float) * (size_t)NC * 3 * model->arch.resolution * model->arch.resolution;
+  const size_t bytes = sizeof(float) * (size_t)NC * out_elems();
   LOCO_CHECK_CUDA(cudaMemcpyAsync(I.gin_buf, g_eps, bytes, cudaMemcpyDeviceToDevice, s));
   if (act16) {
-    const long long img = 3LL * model->arch.resolution * model->arch.resolution;
+    const long long img = out_elems();
     LOCO_TRY(pow2_scale(I.gin_buf, (long long)NC * img, 64.f, I.cscale_dev, I.scale_tmp, s));
   }
   I.cur_geps = I.gin_buf; I.cur_gx = I.gout_buf;
   LOCO_TRY(run_program(I.bwd, I.bstats, I.bstat_bytes, &I.bwd_graph, &I.bwd_graph_launches, s));
-  LOCO_CHECK_CUDA(cudaMemcpyAsync(gx, I.gout_buf, bytes, cudaMemcpyDeviceToDevice, s));
+  LOCO_CHECK_CUDA(cudaMemcpyAsync(gx, I.gout_buf, sizeof(float) * (size_t)NC * in_elems(), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

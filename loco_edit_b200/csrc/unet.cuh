@@ -26,7 +26,8 @@ struct Arch {
   int in_ch = 3;
   int out_ch = 3;
   float gn_eps = 1e-6f;
-  int kind = 0;       // 0 = DDPM (ddpm/diffusion.py), 1 = P2 / guided diffusion (guided_diffusion/unet.py)
+  int kind = 0;       // 0 = DDPM (ddpm/diffusion.py), 1 = P2 / guided diffusion (guided_diffusion/unet.py),
+                      // 2 = VAE decoder (latent [in_ch, R, R] -> image [out_ch, R << (n_levels-1), ...]; no timestep)
   int head_ch = 0;    // kind 1: channels per attention head
   // kind 0 only: > 0 adds a cross-attention sub-block (GroupNorm, q projection, softmax(q K_c^T) V_c,
   // output projection, residual) to every AttnBlock; K_c | V_c are linear maps of a prompt embedding
@@ -41,7 +42,10 @@ struct ParamSlot {
   std::string name;
   std::vector<int> shape;
   long long numel;
-  enum Kind { RAW, CONV_GEMM, CONV_QKV, CONV_EDGE_IN, CONV_EDGE_OUT, BIAS_QKV } kind;
+  // CONV_THIN: a 3x3 conv with <= 4 channels on one side, packed like CONV_GEMM with that side
+  // zero-padded to kThinPad channels (pad_cin / pad_cout are the padded extents)
+  enum Kind { RAW, CONV_GEMM, CONV_QKV, CONV_EDGE_IN, CONV_EDGE_OUT, BIAS_QKV, CONV_THIN } kind;
+  int pad_cin = 0, pad_cout = 0;
   size_t off_a = 0;   // RAW: copy; CONV_GEMM/QKV: fprop pack; EDGE: [9][3][C] pack
   size_t off_b = 0;   // CONV_GEMM/QKV: dgrad pack
   size_t off_a16 = 0, off_b16 = 0;   // CONV_GEMM/QKV: fp16 copies of the two packs
@@ -59,7 +63,7 @@ struct ResRef {
   NormRef n1, n2;
   ConvRef c1, c2, nin;
   bool has_nin = false;
-  int temb_off = 0;    // offset into the packed timestep-projection vector
+  int temb_off = 0;    // offset into the packed timestep-projection vector (-1: no timestep input, VAE decoder)
   // guided-diffusion ResBlock (unet.py:161-258): timestep projection is (scale | shift) of the
   // second GroupNorm instead of a bias; resample 1 = avg-pool /2, 2 = nearest x2 on both branches
   bool scale_shift = false;
@@ -86,6 +90,11 @@ class Model {
   size_t tproj_w = 0, tproj_b = 0;   // all temb_proj layers stacked: [tproj_rows][temb_ch]
   int tproj_rows = 0;
   size_t conv_in_w = 0, conv_in_b = 0, conv_out_w = 0, conv_out_b = 0;
+  // thin edges (arch.in_ch / out_ch != 3, and the VAE decoder): tensor-core convs over a padded side
+  bool thin = false;
+  ConvRef thin_in, thin_out;
+  size_t pq_mix = 0;                 // kind 2: post_quant_conv [c*c weight | c bias]
+  bool has_pq = false;
   NormRef norm_out;
   std::vector<std::vector<ResRef>> down_res, up_res;
   std::vector<std::vector<AttnRef>> down_attn, up_attn;
@@ -103,12 +112,14 @@ class Model {
   int add_slot(ParamSlot s);
   void build_ddpm();
   void build_p2();
+  void build_decoder();
+  ConvRef add_thin_conv(const std::string& prefix, int cin, int cout);
   void finish_temb();
   ConvRef add_conv(const std::string& prefix, int cin, int cout, int ksz, bool conv1d = false);
   ResRef add_res_p2(const std::string& prefix, int cin, int cout, int resample);
   AttnRef add_attn_p2(const std::string& prefix, int C);
   NormRef add_norm(const std::string& prefix, int C);
-  ResRef add_res(const std::string& prefix, int cin, int cout);
+  ResRef add_res(const std::string& prefix, int cin, int cout, bool temb = true);
   AttnRef add_attn(const std::string& prefix, int C);
 };
 
@@ -128,7 +139,10 @@ class Plan {
   int fwd_launches = 0, vjp_launches = 0;
 
   int build(float* workspace);   // workspace == nullptr: size query only
-  // x: [NP+NT, 3, R, R] (row 0.. primal samples, then tangents); eps: same shape.
+  // x: [NP+NT, in_ch, R, R] (row 0.. primal samples, then tangents); eps: [NP+NT, out_ch, Ro, Ro]
+  // (Ro = R for the U-Nets, R << (n_levels-1) for the VAE decoder).
+  long long in_elems() const;    // per row
+  long long out_elems() const;
   int forward(const float* x_nchw, float t, float* eps_nchw, cudaStream_t s);
   // conditioning embedding [4 ch] (device, or null = none) added to the timestep embedding of every
   // following forward(); x -> eps(x, t, c) stays a function of x only, so JVP / VJP are unchanged

@@ -31,6 +31,13 @@ def cosine_betas(n=1000, max_beta=0.999):
     return torch.tensor([min(1 - ab((i + 1) / n) / ab(i / n), max_beta) for i in range(n)], dtype=torch.float64)
 
 
+def scaled_linear_betas(n=1000, beta_start=0.00085, beta_end=0.012):
+    """"scaled_linear": the beta schedule of the Stable Diffusion 1.x scheduler config whose `alphas_cumprod`
+    the reference keeps (get_stable_diffusion_scheduler, utils.py:147-157); diffusers builds it in fp32:
+    linspace(sqrt(beta_start), sqrt(beta_end), n) ** 2, alphas_cumprod = cumprod(1 - betas)."""
+    return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32) ** 2
+
+
 class YHCustomScheduler(object):
     def __init__(self, args=None, device=None, dtype=torch.float32):
         # t_max: 999 for the custom scheduler (utils.py:309); the DeepFloyd-IF monkey patch uses 990
@@ -38,7 +45,7 @@ class YHCustomScheduler(object):
         self.t_max = getattr(args, "t_max", 999) if args is not None else 999
         ns = getattr(args, "noise_schedule", None) if args is not None else None
         self.noise_schedule = "linear" if ns is None else ns
-        if self.noise_schedule not in ("linear", "squaredcos_cap_v2"):
+        if self.noise_schedule not in ("linear", "squaredcos_cap_v2", "scaled_linear"):
             raise NotImplementedError("noise schedule '%s'" % self.noise_schedule)
         self.device = torch.device(device if device is not None else getattr(args, "device", "cuda:0"))
         self.dtype = getattr(args, "dtype", dtype) if args is not None else dtype
@@ -48,6 +55,8 @@ class YHCustomScheduler(object):
         # utils.py:385-406: fp64 linspace betas -> cumprod -> cast to args.dtype
         if self.noise_schedule == "linear":
             betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+        elif self.noise_schedule == "scaled_linear":
+            betas = scaled_linear_betas(1000)
         else:
             betas = cosine_betas(1000)
         self.betas = betas.to(device=self.device, dtype=self.dtype)

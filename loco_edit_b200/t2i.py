@@ -143,6 +143,8 @@ class TextB200UNet(CondB200UNet):
 
 class EditDeepFloydIF(object):
     """Drop-in for the hot-path methods of the reference class of the same name."""
+    default_t_max = 990                              # get_deepfloyd_if_scheduler, src/utils/utils.py:162
+    default_noise_schedule = "squaredcos_cap_v2"
 
     def __init__(self, args, unet, for_prompt_emb, edit_prompt_emb, null_prompt_emb, dataset=None):
         self.seed = getattr(args, "seed", 0)
@@ -151,8 +153,8 @@ class EditDeepFloydIF(object):
         self.unet = unet                                    # CondB200UNet or TextB200UNet
         # get_deepfloyd_if_scheduler (src/utils/utils.py:159-170): the stage-I scheduler's own alpha_bar
         # table with the custom timestep grid on t_max = 990
-        sargs = types.SimpleNamespace(device=self.device, dtype=torch.float32, t_max=getattr(args, "t_max", 990),
-                                      noise_schedule=getattr(args, "noise_schedule", "squaredcos_cap_v2"))
+        sargs = types.SimpleNamespace(device=self.device, dtype=torch.float32, t_max=getattr(args, "t_max", self.default_t_max),
+                                      noise_schedule=getattr(args, "noise_schedule", self.default_noise_schedule))
         self.scheduler = YHCustomScheduler(sargs, device=self.device)
         self.for_steps = args.for_steps
         self.use_yh_custom_scheduler = True
@@ -284,7 +286,7 @@ class EditDeepFloydIF(object):
         """Guided tangents sum_i w_i J_i V^T: one fused primal + k-tangent pass per conditioning; the
         primal activations of conditioning i stay in plan slot i for the transposed pass."""
         k = V.shape[0]
-        xin = torch.cat([x_row.reshape(1, -1), V], 0).reshape(1 + k, 3, self.image_size, self.image_size).contiguous()
+        xin = torch.cat([x_row.reshape(1, -1), V], 0).reshape(1 + k, *self.unet.base.in_shape).contiguous()
         outs = []
         for slot, wi, emb in slots:
             plan = self.unet.base.plan(1, k, k, slot=slot)
@@ -294,7 +296,7 @@ class EditDeepFloydIF(object):
 
     def _vjp_cfg(self, g_eps, slots):
         k = g_eps.shape[0]
-        g = g_eps.reshape(k, 3, self.image_size, self.image_size).contiguous()
+        g = g_eps.reshape(k, *self.unet.base.out_shape).contiguous()
         outs = [(self.unet.base.plan(1, k, k, slot=slot).vjp(g).reshape(k, -1), wi) for slot, wi, _ in slots]
         return self._combine(outs)
 

@@ -31,7 +31,7 @@ def _make_arch(a):
     s.in_ch = a.get("in_ch", 3)
     s.out_ch = a.get("out_ch", 3)
     s.gn_eps = a.get("gn_eps", 1e-6)
-    s.kind = 1 if a.get("kind") == "p2" else 0
+    s.kind = {"p2": 1, "vae_decoder": 2}.get(a.get("kind"), 0)
     s.head_ch = a.get("head_ch", 0) if s.kind == 1 else 0
     s.ctx_dim = a.get("ctx_dim", 0) if s.kind == 0 else 0
     s.ctx_heads = a.get("ctx_heads", 1)
@@ -72,11 +72,10 @@ class Plan:
 
     def forward(self, x, t, out=None):
         n = self.shape[0] + self.shape[1]
-        R = self.unet.arch["resolution"]
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-        assert tuple(x.shape) == (n, 3, R, R), (tuple(x.shape), n, R)
+        assert tuple(x.shape) == (n,) + self.unet.in_shape, (tuple(x.shape), n, self.unet.in_shape)
         if out is None:
-            out = torch.empty_like(x)
+            out = torch.empty((n,) + self.unet.out_shape, dtype=torch.float32, device=x.device)
         check(self.lib.loco_unet_forward(self.handle, ptr(x), float(t), ptr(out), stream_ptr(x)),
               "loco_unet_forward")
         return out
@@ -100,11 +99,10 @@ class Plan:
 
     def vjp(self, g_eps, out=None):
         k = self.shape[2]
-        R = self.unet.arch["resolution"]
         assert g_eps.is_cuda and g_eps.dtype == torch.float32 and g_eps.is_contiguous()
-        assert tuple(g_eps.shape) == (k, 3, R, R)
+        assert tuple(g_eps.shape) == (k,) + self.unet.out_shape, (tuple(g_eps.shape), k, self.unet.out_shape)
         if out is None:
-            out = torch.empty_like(g_eps)
+            out = torch.empty((k,) + self.unet.in_shape, dtype=torch.float32, device=g_eps.device)
         check(self.lib.loco_unet_vjp(self.handle, ptr(g_eps), ptr(out), stream_ptr(g_eps)), "loco_unet_vjp")
         return out
 
@@ -128,6 +126,11 @@ class B200UNet:
         if self.device.type != "cuda":
             raise _lib.LocoError("B200UNet needs a CUDA device; there is no CPU fallback")
         self._arch_struct = _make_arch(arch)
+        a = self._arch_struct
+        # rows of the network input / output ([C, H, W]); the VAE decoder upsamples once per level but the last
+        r_out = a.resolution << (a.n_levels - 1) if a.kind == 2 else a.resolution
+        self.in_shape = (a.in_ch, a.resolution, a.resolution)
+        self.out_shape = (a.out_ch, r_out, r_out)
         h = C.c_void_p()
         check(self.lib.loco_unet_create(C.byref(self._arch_struct), C.byref(h)), "loco_unet_create")
         self.handle = h
@@ -195,7 +198,7 @@ class B200UNet:
         self.__dict__.pop("_pb_cache", None)
 
     def __call__(self, x, t):
-        """eps = unet(x, t); x [B,3,R,R] fp32 on the device, t scalar (tensor or float)."""
+        """eps = unet(x, t); x [B,C,R,R] fp32 on the device, t scalar (tensor or float)."""
         x = x.contiguous()
         return self.plan(x.shape[0]).forward(x, float(t))
 
@@ -217,3 +220,34 @@ class B200UNet:
             self.lib.loco_unet_destroy(self.handle)
         except Exception:
             pass
+
+
+class B200VAEDecoder(B200UNet):
+    """The `self.vae` of the latent-space twins (src/modules/edit.py:770: `self.vae.decode(z).sample`):
+    AutoencoderKL's decode = Decoder(post_quant_conv(z)) on the same CUDA executor (arch kind
+    "vae_decoder": latent [in_ch, R, R] -> image [3, R << (levels-1), ...], no timestep input), with the
+    fused primal + k-tangent pass and the k-cotangent pass the latent-space power method needs."""
+
+    def __init__(self, arch, state_dict, device="cuda:0"):
+        arch = dict(arch)
+        arch["kind"] = "vae_decoder"
+        arch.setdefault("in_ch", 4)
+        arch.setdefault("attn_resolutions", ())
+        super().__init__(arch, state_dict, device=device)
+
+    def decode(self, z):
+        z = z.contiguous()
+        return self.plan(z.shape[0]).forward(z, 0.0)
+
+    def __call__(self, z, t=0.0):
+        return self.decode(z)
+
+    def jvp(self, z, dZ):
+        """(x, dX): decode(z) [1,3,H,W] and the k tangents J_dec dZ in one fused pass."""
+        k = dZ.shape[0]
+        out = self.plan(1, k, k).forward(torch.cat([z.reshape(1, *self.in_shape), dZ.reshape(k, *self.in_shape)], 0).contiguous(), 0.0)
+        return out[:1], out[1:]
+
+    def vjp(self, k, g_x):
+        """J_dec^T g for k image-space cotangents at the latent of the last jvp() call."""
+        return self.plan(1, k, k).vjp(g_x.reshape(k, *self.out_shape).contiguous())

@@ -229,8 +229,77 @@ def p2_param_shapes(arch):
     return out
 
 
+# Decoder half of the Stable Diffusion 1.x VAE (diffusers AutoencoderKL config of CompVis/stable-diffusion-v1-*:
+# block_out_channels (128, 256, 512, 512), layers_per_block 2, latent_channels 4, one mid-block attention):
+# latent [4, 64, 64] -> image [3, 512, 512].  `resolution` is the LATENT resolution.
+SD_VAE_DECODER = dict(kind="vae_decoder", ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=(),
+                      resolution=64, in_ch=4, out_ch=3, gn_eps=1e-6)
+
+
+def tiny_vae_decoder_arch(resolution=8, ch_mult=(1, 2), num_res_blocks=1, ch=128, in_ch=4):
+    """Reduced-depth VAE decoder for fast parity tests (image = resolution << (levels - 1))."""
+    return dict(kind="vae_decoder", ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
+                attn_resolutions=(), resolution=resolution, in_ch=in_ch, out_ch=3, gn_eps=1e-6)
+
+
+def latent_unet_arch(resolution=16, ch_mult=(1, 2), attn_resolutions=(8,), num_res_blocks=1, ch=128, ctx_dim=64,
+                     ctx_heads=2):
+    """Text-conditioned stand-in U-Net over 4-channel latents (the shape of the Stable Diffusion U-Net's
+    interface: src/modules/edit.py:655-658)."""
+    a = tiny_arch(resolution, ch_mult, attn_resolutions, num_res_blocks, ch, ctx_dim, ctx_heads)
+    a.update(in_ch=4, out_ch=4)
+    return a
+
+
+def vae_decoder_param_shapes(arch):
+    """Ordered {name: shape} of the decoder half of a latent-diffusion VAE: `post_quant_conv` + the CompVis
+    `Decoder` module tree that diffusers' AutoencoderKL restates (conv_in, mid.{block_1, attn_1, block_2},
+    up.{l}.block.{b} [+ up.{l}.upsample.conv], norm_out, conv_out; ResnetBlock / AttnBlock / Upsample are the
+    modules of src/models/ddpm/diffusion.py:816-966 without the timestep projection)."""
+    ch, mult, nrb, zc = arch["ch"], tuple(arch["ch_mult"]), arch["num_res_blocks"], arch.get("in_ch", 4)
+    out = {}
+
+    def conv(p, cin, cout, k):
+        out[p + ".weight"] = (cout, cin, k, k)
+        out[p + ".bias"] = (cout,)
+
+    def norm(p, c):
+        out[p + ".weight"] = (c,)
+        out[p + ".bias"] = (c,)
+
+    def resblock(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cin, cout, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cin, cout, 1)
+
+    conv("post_quant_conv", zc, zc, 1)
+    L = len(mult)
+    block_in = ch * mult[L - 1]
+    conv("decoder.conv_in", zc, block_in, 3)
+    resblock("decoder.mid.block_1", block_in, block_in)
+    norm("decoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv("decoder.mid.attn_1." + n, block_in, block_in, 1)
+    resblock("decoder.mid.block_2", block_in, block_in)
+    for l in reversed(range(L)):
+        block_out = ch * mult[l]
+        for b in range(nrb + 1):
+            resblock(f"decoder.up.{l}.block.{b}", block_in, block_out)
+            block_in = block_out
+        if l != 0:
+            conv(f"decoder.up.{l}.upsample.conv", block_in, block_in, 3)
+    norm("decoder.norm_out", block_in)
+    conv("decoder.conv_out", block_in, arch.get("out_ch", 3), 3)
+    return out
+
+
 def param_shapes(arch):
     """{name: shape} of the reference state_dict for either architecture family."""
+    if arch.get("kind") == "vae_decoder":
+        return vae_decoder_param_shapes(arch)
     return p2_param_shapes(arch) if arch.get("kind") == "p2" else ddpm_param_shapes(arch)
 
 

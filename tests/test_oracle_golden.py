@@ -192,3 +192,60 @@ def test_full_size_forward_oracles_match_reference(golden_dir):
         ref = g["eps"].float()          # stored in fp16
         err = float((eps - ref).norm() / ref.norm())
         assert err < 1e-3, (name, err)
+
+
+def test_latent_space_oracle_matches_reference_stable_diffusion_class(golden_dir):
+    """oracle/vae_ref.py (pixel-space x0_hat through the VAE decoder, one pass of the latent-space power
+    method) against the unmodified `EditStableDiffusion` run on the same stand-in networks
+    (tests/golden/make_golden_sd.py)."""
+    from loco_edit_b200.scheduler import YHCustomScheduler
+    from loco_edit_b200.t2i import synthetic_prompt_embedding
+    from oracle import vae_ref
+    g = _load(golden_dir, "sd_tiny.pt")
+    sd = random_state_dict(g["arch"], seed=1234, perturb_norm=0.1)
+    vsd = random_state_dict(g["vae_arch"], seed=4321, perturb_norm=0.1)
+    vae = vae_ref.RefVAE(g["vae_arch"], vsd)
+    with torch.no_grad():
+        assert torch.allclose(vae.decode(g["z2"]).sample, g["decode"], atol=1e-5)
+    # the scheduler mirror holds Stable Diffusion's table, bit for bit
+    import types
+    sched = YHCustomScheduler(types.SimpleNamespace(device="cpu", dtype=torch.float32, t_max=999, noise_schedule="scaled_linear"),
+                              device="cpu")
+    assert torch.equal(sched.alphas_cumprod, g["alphas_cumprod"])
+    sched.set_timesteps(100, device="cpu")
+    assert torch.equal(sched.timesteps, g["timesteps"])
+    embs = [synthetic_prompt_embedding(p, g["ntok"], g["dim"]) for p in g["prompts"]]
+    G = g["g"]
+    t = g["t"]
+    at = float(g["alphas_cumprod"][int(float(t))])
+
+    def eps_fn(z):      # "null+(for-null)": e_null + g (e_for - e_null), src/modules/edit.py:664-666
+        ef = ddpm_ref.unet_forward(sd, g["arch"], z, t, ctx=embs[0][0])
+        en = ddpm_ref.unet_forward(sd, g["arch"], z, t, ctx=embs[2][0])
+        return en + G * (ef - en)
+
+    with torch.no_grad():
+        x0m = vae_ref.x0_hat_pixels(eps_fn, vae, g["zt"], at, g["mask"])
+    assert torch.allclose(x0m, g["x0_masked"], atol=2e-4, rtol=1e-4), float((x0m - g["x0_masked"]).abs().max())
+    torch.manual_seed(7)
+    v0, _ = torch.linalg.qr(torch.randn(g["zt"].numel(), 2))
+    u, s, vT = vae_ref.power_iteration_zt(eps_fn, vae, g["zt"], at, v0.T.contiguous(), g["mask"])
+    ref = g["pullback"][("null+(for-null)", "mask", 1)]
+    assert torch.allclose(s.sqrt(), ref["s"], rtol=1e-4), (s.sqrt(), ref["s"])
+    assert _principal_angle_deg(vT, ref["vT"]) < 0.05
+
+
+def test_vae_decoder_param_shapes_are_the_sd_vae():
+    """The decoder half of the SD 1.x VAE has 49.49 M parameters (diffusers AutoencoderKL: 83.65 M in total,
+    34.16 M of them in the encoder + quant_conv)."""
+    from loco_edit_b200.weights import SD_VAE_DECODER, vae_decoder_param_shapes
+    shapes = vae_decoder_param_shapes(SD_VAE_DECODER)
+    n = 0
+    for v in shapes.values():
+        c = 1
+        for d in v:
+            c *= d
+        n += c
+    assert shapes["decoder.conv_in.weight"] == (512, 4, 3, 3) and shapes["decoder.conv_out.weight"] == (3, 128, 3, 3)
+    assert shapes["decoder.up.1.block.0.nin_shortcut.weight"] == (256, 512, 1, 1)
+    assert n == 49490199, n
