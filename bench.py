@@ -310,6 +310,78 @@ def measure_text_unet(dev, R):
     return out
 
 
+def measure_sd_latent(dev):
+    """SURVEY 8(f2), BASELINE config 4 shape: the latent-space twin.  The VAE decoder of the Stable Diffusion
+    1.x shape (latent [4, 64, 64] -> image [3, 512, 512], 49.5 M parameters, random init) inside every Jacobian
+    product: device time of its fused rank-5 primal + tangent pass, of the rank-5 cotangent pass and of a
+    B = 1 decode; then one power iteration of `EditStableDiffusion.local_encoder_decoder_pullback_zt`
+    (stand-in latent U-Net under two-term guidance + PMP + decoder) per probe."""
+    import types
+    import torch
+    from loco_edit_b200.masks import rectangle_mask
+    from loco_edit_b200.sd import EditStableDiffusion
+    from loco_edit_b200.t2i import TextB200UNet, synthetic_prompt_embedding
+    from loco_edit_b200.unet import B200UNet, B200VAEDecoder
+    from loco_edit_b200.weights import SD_VAE_DECODER, random_state_dict, sd_standin_unet_arch
+    vae = B200VAEDecoder(SD_VAE_DECODER, random_state_dict(SD_VAE_DECODER, seed=4321), device=dev)
+    g = torch.Generator(device=dev).manual_seed(22)
+    pj, p1 = vae.plan(1, K_RANK, K_RANK), vae.plan(1)
+    zin = torch.randn(1 + K_RANK, 4, 64, 64, device=dev, generator=g)
+    gin = torch.randn(K_RANK, 3, 512, 512, device=dev, generator=g)
+    for _ in range(2):
+        pj.forward(zin, 0.0); pj.vjp(gin); p1.forward(zin[:1].contiguous(), 0.0)
+    torch.cuda.synchronize()
+    a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        pj.forward(zin, 0.0)
+    b.record()
+    for _ in range(reps):
+        pj.vjp(gin)
+    c.record()
+    for _ in range(reps):
+        p1.forward(zin[:1].contiguous(), 0.0)
+    d.record()
+    torch.cuda.synchronize()
+    jvp_ms, vjp_ms = a.elapsed_time(b) / reps, b.elapsed_time(c) / reps
+    out = {"decoder": "SD 1.x VAE decoder shape (ch 128, mult 1-2-4-4, 3 ResnetBlocks per level, mid attention over "
+                      "4096 tokens), latent 4x64x64 -> image 3x512x512, random init",
+           "decoder_tflop_per_row": pj.fwd_flops / (1 + K_RANK) / 1e12,
+           "decoder_jvp_pass_ms": jvp_ms, "decoder_vjp_pass_ms": vjp_ms, "decode_b1_ms": c.elapsed_time(d) / reps,
+           "decoder_jvp_tflops": pj.fwd_flops / (jvp_ms * 1e-3) / 1e12,
+           "decoder_vjp_tflops": pj.vjp_flops / (vjp_ms * 1e-3) / 1e12}
+    # one latent-space power iteration through both networks (rank 5, mask over the decoded image)
+    arch = sd_standin_unet_arch(64)
+    net = TextB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=dev))
+    embs = [synthetic_prompt_embedding(p, 77, 768) for p in ("a photo of a dog", "a dog with glasses", "")]
+    import tempfile
+    args = types.SimpleNamespace(device=dev, dtype=torch.float32, seed=3, for_steps=100, edit_t=0.6, guidance_scale=7.5,
+                                 guidance_scale_edit=4.0, result_folder=tempfile.mkdtemp(), for_prompt="bench")
+    e = EditStableDiffusion(args, net, vae, *embs)
+    zt = torch.randn(1, 4, 64, 64, device=dev, generator=g)
+    mask = rectangle_mask(512).to(dev)
+    t = float(e.scheduler.timesteps[e.edit_t_idx])
+    run = lambda n: e.local_encoder_decoder_pullback_zt(zt, t, e.edit_t_idx, *embs, pca_rank=K_RANK, min_iter=10 ** 6,
+                                                        max_iter=n, mask=mask, mode="null+(for-null)")
+    run(2)
+    torch.cuda.synchronize()
+    a.record()
+    n_it = 4
+    _, s, _ = run(n_it)
+    b.record()
+    torch.cuda.synchronize()
+    it_ms = a.elapsed_time(b) / n_it
+    out.update({"unet": "stand-in latent U-Net (ch 128, mult 1-2-4-4, self + cross attention at 16^2 / 8^2, 77 x 768 prompt), "
+                        "guidance mode null+(for-null): 2 conditionings per Jacobian product",
+                "power_iteration_ms": it_ms, "probes_per_s": K_RANK / (it_ms * 1e-3),
+                "singular_values_finite": bool(torch.isfinite(s).all())})
+    net.base.release_plans(); vae.release_plans()
+    del net, vae, e
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_probe_shard(unet, sched, dev, world, rank, R, barrier, max_over_ranks, n_it=3, k=64):
     """BASELINE config 3 under torchrun: rank-64 subspace iteration (mask = None, t idx 40), probe
     tangents sharded over the ranks (64 / world rows each, probed in chunks of <= 25), one all-gather
@@ -561,12 +633,13 @@ def run_ours(args):
             probes["fwd_b%d_ms" % bsz] = a.elapsed_time(b) / reps
 
     # ---- single-edit latency (north_star: < 1 s), the drop-in driver, the small HBM-bound kernels ----
-    latency_b1 = dropin = bw = text = None
+    latency_b1 = dropin = bw = text = sd_latent = None
     if rank == 0 and world == 1 and not args.no_extras:
         latency_b1 = measure_latency_b1(pipe, gen, R)
         dropin = measure_dropin(unet, dev, R)
         bw = measure_bandwidth_kernels(dev, pk["hbm_gbs"])
         text = measure_text_unet(dev, R)
+        sd_latent = measure_sd_latent(dev)
     # ---- multi-GPU data path with a collective: one edit by all ranks, and BASELINE config 3 ----
     sharded_latency = probe_shard = None
     if world > 1 and not args.no_extras:
@@ -646,6 +719,7 @@ def run_ours(args):
             "latency_b1_ms": latency_b1, "latency_b1_target_ms": 1000.0,
             "latency_b1_sharded": sharded_latency, "probe_shard": probe_shard,
             "dropin_driver": dropin, "bandwidth_kernels": bw, "text_conditioned": text,
+            "sd_latent": sd_latent,
         }
         if probes:
             line.update(probes)

@@ -2,8 +2,9 @@
 `--run_*` booleans.  The unconditional path runs `EditUncondDiffusion`; DeepFloyd-IF model names run the
 T-LOCO class `EditDeepFloydIF` of loco_edit_b200/t2i.py on a stand-in text-conditioned U-Net (cross-attention
 to seeded prompt embeddings (the IF network and its T5 encoder are diffusers / transformers models that cannot
-be obtained here); the latent-space classes (Stable Diffusion, LCM) need a VAE
-decoder inside every Jacobian product and raise NotImplementedError.
+be obtained here); Stable Diffusion model names run the latent-space class
+`EditStableDiffusion` of loco_edit_b200/sd.py on a stand-in latent U-Net and the SD-shaped VAE decoder (the
+decoder Jacobian sits inside every Jacobian product).  The LCM class raises NotImplementedError.
 
     python -m loco_edit_b200.main --model_name LSUN_church_HF --dataset_name LSUN_church --dtype fp32 \
         --edit_t 0.6 --performance_boosting_t 0.2 --pca_rank 5 --pca_rank_null 5 \
@@ -36,10 +37,39 @@ def main_deepfloyd(args):
     return edit
 
 
+def main_stable_diffusion(args):
+    """src/main.py:22-27, 52-71 for `--model_name *stable-diffusion*`: latent-space T-LOCO, z_t [4, 64, 64],
+    x0_hat [3, 512, 512] through the VAE decoder."""
+    import torch
+    from .sd import EditStableDiffusion
+    from .t2i import TextB200UNet, synthetic_prompt_embedding
+    from .unet import B200UNet, B200VAEDecoder
+    from .weights import SD_VAE_DECODER, random_state_dict, sd_standin_unet_arch
+    print("Stable Diffusion: running the stand-in latent U-Net and a random-init VAE decoder of the SD 1.x shape "
+          "(the checkpoints / CLIP text encoder are not available offline)")
+    dev = torch.device(args.device)
+    arch = sd_standin_unet_arch(args.image_size // 8)
+    varch = dict(SD_VAE_DECODER, resolution=args.image_size // 8)
+    net = TextB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=dev))
+    vae = B200VAEDecoder(varch, random_state_dict(varch, seed=4321), device=dev)
+    embs = [synthetic_prompt_embedding(p or "", 77, 768) for p in (args.for_prompt, args.edit_prompt, "")]
+    edit = EditStableDiffusion(args, net, vae, *embs)
+    common = dict(op='mid', block_idx=0, mask_index=args.mask_index, vis_num=args.vis_num, vis_num_pc=args.pca_rank,
+                  pca_rank=args.pca_rank, edit_prompt=args.edit_prompt, null_space_projection=args.null_space_projection,
+                  pca_rank_null=args.pca_rank_null)
+    if args.run_edit_null_space_projection_zt:
+        edit.run_edit_null_space_projection_zt(non_semantic=getattr(args, "non_semantic", False), **common)
+    if args.run_edit_null_space_projection_zt_semantic:
+        edit.run_edit_null_space_projection_zt_semantic(**common)
+    return edit
+
+
 def main(argv=None):
     args = preset(parse_args(argv))
-    if args.is_stable_diffusion or args.is_LCM:
-        raise NotImplementedError("latent-space T2I classes need the VAE-decoder Jacobian (DESIGN.md, out of scope)")
+    if args.is_LCM:
+        raise NotImplementedError("the latent-consistency class is not part of this path (DESIGN.md, out of scope)")
+    if args.is_stable_diffusion:
+        return main_stable_diffusion(args)
     if args.is_DeepFloyd_IF_diffusion:
         return main_deepfloyd(args)
     print('is custmized diffusion model')

@@ -13,7 +13,8 @@ networks on the CUDA executor:
 
 Built: `_classifer_free_guidance` (:636-674, four modes), `get_x0` (:757-781), `DDIMforwardsteps`
 (:677-755), `local_encoder_decoder_pullback_zt` (:830-915), `get_delta_zt_via_grad` (:784-828),
-`run_edit_null_space_projection_zt` (:918-1043) with the reference's basis file names, and
+`run_edit_null_space_projection_zt` (:918-1043) and `run_edit_null_space_projection_zt_semantic` (:1045-1175)
+with the reference's basis file names, and
 `x_space_guidance_direct` (:1177-1185).
 
 What is NOT the reference's: the two networks.  Stable Diffusion's U-Net and VAE are diffusers models
@@ -205,15 +206,10 @@ class EditStableDiffusion(EditDeepFloydIF):
         """src/modules/edit.py:1177-1185."""
         return ops.axpy(zt.contiguous(), vk.expand_as(zt).contiguous(), self.x_space_guidance_scale * single_edit_step)
 
-    # ------------------------------------------------------------------ driver
-    @torch.no_grad()
-    def run_edit_null_space_projection_zt(self, op, block_idx, vis_num, mask_index=0, vis_num_pc=1, vis_vT=False,
-                                          pca_rank=50, edit_prompt=None, null_space_projection=False, pca_rank_null=50,
-                                          non_semantic=False):
-        """src/modules/edit.py:918-1043 (masks come from `mask/mask.pt` under the result folder: SAM is out
-        of scope; the mask is a bool [H, W] over the decoded image, repeated over the 3 channels, :959)."""
-        if self.sampling_mode:
-            return None
+    # ------------------------------------------------------------------ drivers
+    def _start_zt(self, mask_index):
+        """z_T, the mask and z_t at the edit timestep (:933-966 without SAM; masks come from `mask/mask.pt`
+        under the result folder, a bool [H, W] over the DECODED image repeated over its 3 channels, :959)."""
         self.scheduler.set_timesteps(self.for_steps, device=self.device)
         zT = self.zT if self.zT is not None else torch.randn(1, *self.latent_shape, dtype=torch.float32, device=self.device)
         zT = zT.to(self.device)
@@ -222,37 +218,90 @@ class EditStableDiffusion(EditDeepFloydIF):
                   null_prompt_emb=self.null_prompt_emb, mode="null+(for-null)")
         zt, t, t_idx = self.DDIMforwardsteps(zT, t_start_idx=0, t_end_idx=self.edit_t_idx, **kw)
         assert t_idx == self.edit_t_idx
-        save_dir = os.path.join(self.result_folder, "basis", f'local_basis-{self.edit_t}T-pca-rank-{pca_rank}-select-mask{mask_index}')
+        return mask, zt, t, t_idx, kw
+
+    def _basis_paths(self, save_dir, pca_rank_null):
         os.makedirs(save_dir, exist_ok=True)
-        paths = dict(u_m=os.path.join(save_dir, 'u-modify.pt'), v_m=os.path.join(save_dir, 'vT-modify.pt'),
-                     u_n=os.path.join(save_dir, f'u-null-null_space_rank_{pca_rank_null}.pt'),
-                     v_n=os.path.join(save_dir, f'vT-null-null_space_rank_{pca_rank_null}.pt'))
-        if all(os.path.exists(p) for p in paths.values()):
-            vT_modify = torch.load(paths["v_m"], map_location=self.device).type(torch.float32)
-            vT_null = torch.load(paths["v_n"], map_location=self.device).type(torch.float32)
-        else:
-            pb = dict(op=op, block_idx=block_idx, chunk_size=5, min_iter=10, max_iter=50, convergence_threshold=1e-3,
-                      mode="null+(for-null)")
-            u_modify, _, vT_modify = self.local_encoder_decoder_pullback_zt(
-                zt, t, t_idx, self.for_prompt_emb, self.edit_prompt_emb, self.null_prompt_emb, pca_rank=pca_rank, mask=mask, **pb)
-            torch.save(u_modify, paths["u_m"])
-            torch.save(vT_modify, paths["v_m"])
-            vT_null = None
-            if null_space_projection:
-                u_null, _, vT_null = self.local_encoder_decoder_pullback_zt(
-                    zt, t, t_idx, self.for_prompt_emb, self.edit_prompt_emb, self.null_prompt_emb, pca_rank=pca_rank_null,
-                    mask=~mask, **pb)
-                torch.save(u_null, paths["u_n"])
-                torch.save(vT_null, paths["v_n"])
+        return dict(u_m=os.path.join(save_dir, 'u-modify.pt'), v_m=os.path.join(save_dir, 'vT-modify.pt'),
+                    u_n=os.path.join(save_dir, f'u-null-null_space_rank_{pca_rank_null}.pt'),
+                    v_n=os.path.join(save_dir, f'vT-null-null_space_rank_{pca_rank_null}.pt'))
+
+    def _null_basis(self, zt, t, t_idx, mask, op, block_idx, pca_rank_null, paths):
+        """:996-1003 / :1120-1127: the basis of the complement region, `~mask`."""
+        u_null, _, vT_null = self.local_encoder_decoder_pullback_zt(
+            zt, t, t_idx, self.for_prompt_emb, self.edit_prompt_emb, self.null_prompt_emb, op=op, block_idx=block_idx,
+            pca_rank=pca_rank_null, chunk_size=5, min_iter=10, max_iter=50, convergence_threshold=1e-3, mask=~mask,
+            mode="null+(for-null)")
+        torch.save(u_null, paths["u_n"])
+        torch.save(vT_null, paths["v_n"])
+        return vT_null
+
+    def _project_and_edit(self, zt, vT_modify, vT_null, null_space_projection, pca_rank_null, vis_num, vis_num_pc, name, kw):
+        """:1005-1043: normalise / project the directions, build the edited latents, denoise and decode."""
         if not null_space_projection:
             vT = ops.nullspace_project(vT_modify.contiguous(), None, project=False)
         else:
             vT = ops.nullspace_project(vT_modify.contiguous(), vT_null[:pca_rank_null, :].contiguous(), project=True)
         self.last_images = []
         imgs = None
-        for pc_idx in range(vis_num_pc):
-            self.EXP_NAME = (f'Edit_zt-edit_{self.edit_t}T-pc_{pc_idx}_select_mask{mask_index}_null_space_projection_'
-                             f'{null_space_projection}_null_space_rank_{pca_rank_null}')
+        for pc_idx in range(min(vis_num_pc, vT.shape[0])):
+            self.EXP_NAME = name(pc_idx)
             batch = self._edit_batch(zt, vT[pc_idx, :], vis_num)
             _, imgs = self.DDIMforwardsteps(batch, t_start_idx=self.edit_t_idx, t_end_idx=-1, **kw)
         return dict(vT=vT, vT_modify=vT_modify, vT_null=vT_null, zt=zt, images=imgs)
+
+    @torch.no_grad()
+    def run_edit_null_space_projection_zt(self, op, block_idx, vis_num, mask_index=0, vis_num_pc=1, vis_vT=False,
+                                          pca_rank=50, edit_prompt=None, null_space_projection=False, pca_rank_null=50,
+                                          non_semantic=False):
+        """src/modules/edit.py:918-1043 (unsupervised latent-space edit)."""
+        if self.sampling_mode:
+            return None
+        mask, zt, t, t_idx, kw = self._start_zt(mask_index)
+        paths = self._basis_paths(os.path.join(self.result_folder, "basis",
+                                               f'local_basis-{self.edit_t}T-pca-rank-{pca_rank}-select-mask{mask_index}'), pca_rank_null)
+        if all(os.path.exists(p) for p in paths.values()):
+            vT_modify = torch.load(paths["v_m"], map_location=self.device).type(torch.float32)
+            vT_null = torch.load(paths["v_n"], map_location=self.device).type(torch.float32)
+        else:
+            u_modify, _, vT_modify = self.local_encoder_decoder_pullback_zt(
+                zt, t, t_idx, self.for_prompt_emb, self.edit_prompt_emb, self.null_prompt_emb, op=op, block_idx=block_idx,
+                pca_rank=pca_rank, chunk_size=5, min_iter=10, max_iter=50, convergence_threshold=1e-3, mask=mask,
+                mode="null+(for-null)")
+            torch.save(u_modify, paths["u_m"])
+            torch.save(vT_modify, paths["v_m"])
+            vT_null = self._null_basis(zt, t, t_idx, mask, op, block_idx, pca_rank_null, paths) if null_space_projection else None
+        name = lambda pc: (f'Edit_zt-edit_{self.edit_t}T-pc_{pc}_select_mask{mask_index}_null_space_projection_'
+                           f'{null_space_projection}_null_space_rank_{pca_rank_null}')
+        return self._project_and_edit(zt, vT_modify, vT_null, null_space_projection, pca_rank_null, vis_num, vis_num_pc, name, kw)
+
+    @torch.no_grad()
+    def run_edit_null_space_projection_zt_semantic(self, op, block_idx, vis_num, mask_index=0, vis_num_pc=1, vis_vT=False,
+                                                   pca_rank=50, edit_prompt=None, null_space_projection=False,
+                                                   pca_rank_null=50):
+        """src/modules/edit.py:1045-1175 (text-supervised latent-space edit: the direction is
+        `get_delta_zt_via_grad`, projected off the null basis of `~mask`; the SEGA branch, :1164-1175, is a
+        plain guided denoising with the three-term mode)."""
+        if self.sampling_mode:
+            return None
+        mask, zt, t, t_idx, kw = self._start_zt(mask_index)
+        if getattr(self, "use_sega", False):
+            self.EXP_NAME = f'sega-edit_prompt-{self.edit_prompt}'
+            _, imgs = self.DDIMforwardsteps(zt, t_start_idx=self.edit_t_idx, t_end_idx=-1,
+                                            **dict(kw, mode="null+(for-null)+(edit-null)"))
+            return dict(zt=zt, images=imgs)
+        paths = self._basis_paths(os.path.join(
+            self.result_folder, "basis", f'local_basis-{self.edit_t}T-"{self.edit_prompt}"-pca-rank-{pca_rank}-select-mask{mask_index}'),
+            pca_rank_null)
+        if all(os.path.exists(p) for p in paths.values()):
+            vT_modify = torch.load(paths["v_m"], map_location=self.device).type(torch.float32)
+            vT_null = torch.load(paths["v_n"], map_location=self.device).type(torch.float32)
+        else:
+            vT_modify = self.get_delta_zt_via_grad(zt, t, t_idx, self.for_prompt_emb, self.edit_prompt_emb, self.null_prompt_emb,
+                                                   mask=mask, mode=self.tilda_v_score_type)
+            torch.save(vT_modify, paths["v_m"])
+            vT_null = self._null_basis(zt, t, t_idx, mask, op, block_idx, pca_rank_null, paths) if null_space_projection else None
+        name = lambda pc: (f'Edit_zt-edit_{self.edit_t}T-{op}-block_{block_idx}-pc_{pc:0=3d}_pos-edit_prompt-{self.edit_prompt}'
+                           f'_select_mask{mask_index}_null_space_projection_{null_space_projection}_null_space_rank_{pca_rank_null}'
+                           f'_{self.tilda_v_score_type}')
+        return self._project_and_edit(zt, vT_modify, vT_null, null_space_projection, pca_rank_null, vis_num, vis_num_pc, name, kw)

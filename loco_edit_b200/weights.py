@@ -251,6 +251,14 @@ def latent_unet_arch(resolution=16, ch_mult=(1, 2), attn_resolutions=(8,), num_r
     return a
 
 
+def sd_standin_unet_arch(resolution=64):
+    """Text-conditioned stand-in at the Stable Diffusion 1.x interface (BASELINE config 4): latents [4, 64, 64],
+    four levels 64 -> 8, self- and cross-attention (8 heads) at 16^2 and 8^2 (<= 256 tokens: the fused tcgen05
+    attention kernels), prompt embedding 77 x 768."""
+    return dict(DDPM256, resolution=resolution, ch_mult=(1, 2, 4, 4), attn_resolutions=(resolution // 4, resolution // 8),
+                ctx_dim=768, ctx_heads=8, in_ch=4, out_ch=4)
+
+
 def vae_decoder_param_shapes(arch):
     """Ordered {name: shape} of the decoder half of a latent-diffusion VAE: `post_quant_conv` + the CompVis
     `Decoder` module tree that diffusers' AutoencoderKL restates (conv_in, mid.{block_1, attn_1, block_2},

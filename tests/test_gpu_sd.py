@@ -196,3 +196,60 @@ def test_sd_driver_writes_the_reference_files(setup, dev):
     vT, vn = r["vT"].double().cpu(), r["vT_null"].double().cpu()
     assert float((vT @ vn.T).abs().max()) < 1e-4 and float((vT.norm(dim=1) - 1).abs().max()) < 1e-5
     assert r["images"].shape == (5, 32, 32, 3) and r["images"].dtype == torch.uint8
+
+
+def test_sd_semantic_driver(setup, dev):
+    """run_edit_null_space_projection_zt_semantic (src/modules/edit.py:1045-1175): the text-supervised direction
+    projected off the null basis of ~mask; file names of the reference."""
+    from loco_edit_b200.masks import save_masks
+    g, e, embs = setup
+    save_masks(e.result_folder, g["mask"][:1])
+    e.zT = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(9))
+    e.edit_prompt = "a dog with glasses"
+    orig = e.local_encoder_decoder_pullback_zt
+    e.local_encoder_decoder_pullback_zt = lambda *a, **k: orig(*a, **dict(k, min_iter=0, max_iter=2))
+    try:
+        r = e.run_edit_null_space_projection_zt_semantic(op="mid", block_idx=0, vis_num=1, mask_index=0, vis_num_pc=1, pca_rank=1,
+                                                         null_space_projection=True, pca_rank_null=2)
+    finally:
+        e.local_encoder_decoder_pullback_zt = orig
+    d = os.path.join(e.result_folder, "basis", f'local_basis-{e.edit_t}T-"a dog with glasses"-pca-rank-1-select-mask0')
+    assert sorted(os.listdir(d)) == ["u-null-null_space_rank_2.pt", "vT-modify.pt", "vT-null-null_space_rank_2.pt"]
+    assert torch.load(os.path.join(d, "vT-modify.pt")).shape == (1, 1024)
+    vT, vn = r["vT"].double().cpu(), r["vT_null"].double().cpu()
+    assert vT.shape == (1, 1024) and float((vT @ vn.T).abs().max()) < 1e-4 and abs(float(vT.norm()) - 1) < 1e-5
+    assert r["images"].shape == (3, 32, 32, 3) and r["images"].dtype == torch.uint8
+
+
+def test_sd_shaped_vae_decoder_full_size(dev):
+    """The decoder at the Stable Diffusion 1.x size (latent 4 x 64 x 64 -> 3 x 512 x 512, mid-block attention over
+    4096 tokens on the CUDA-core path): decode against the CPU oracle; JVP linearity and the adjoint identity
+    <J dz, g> = <dz, J^T g> on the CUDA side (size-independent properties)."""
+    from loco_edit_b200.unet import B200VAEDecoder
+    from loco_edit_b200.weights import SD_VAE_DECODER, random_state_dict
+    from oracle import vae_ref
+    vsd = random_state_dict(SD_VAE_DECODER, seed=4321)
+    vae = B200VAEDecoder(SD_VAE_DECODER, vsd, device=dev)
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 4, 64, 64, generator=gen)
+    with torch.no_grad():
+        ref = vae_ref.decoder_forward(vsd, SD_VAE_DECODER, z)
+    out = vae.decode(z.to(dev)).cpu()
+    print(f"SD-shaped decoder 64^2 -> 512^2: decode rel err {rel_err(out, ref):.2e}")
+    assert out.shape == (1, 3, 512, 512) and rel_err(out, ref) < 5e-3
+    k = 2
+    dZ = torch.randn(k, 4, 64, 64, generator=gen).to(dev)
+    G = torch.randn(k, 3, 512, 512, generator=gen).to(dev)
+    x, dX = vae.jvp(z.to(dev), dZ)
+    gz = vae.vjp(k, G)
+    torch.cuda.synchronize()
+    assert rel_err(x.cpu(), ref) < 5e-3
+    lhs = (dX.double() * G.double()).sum(dim=(1, 2, 3))
+    rhs = (dZ.double() * gz.double()).sum(dim=(1, 2, 3))
+    adj = float(((lhs - rhs).abs() / (dX.double().flatten(1).norm(dim=1) * G.double().flatten(1).norm(dim=1))).max())
+    # linearity: the tangent of (dz_0 + 2 dz_1) is dX_0 + 2 dX_1
+    _, dX2 = vae.jvp(z.to(dev), torch.stack([dZ[0] + 2 * dZ[1], dZ[1]], 0))
+    lin = rel_err(dX2[0], dX[0] + 2 * dX[1])
+    print(f"adjoint identity (relative to |J dz||g|) {adj:.2e}, linearity {lin:.2e}")
+    assert adj < 1e-3 and lin < 5e-3
+    vae.release_plans()
