@@ -135,6 +135,17 @@ CPU_SAMPLE_TEXT = ("measured on the host cores, fp32 torch CPU, 256^2: one FULL 
                    "iteration + 59 x fwd(B=5)")
 
 
+def workload_config(batch):
+    """The `config` keys both arms share (the reference arm runs the same workload on the host cores)."""
+    return {"workload": "batch edit (BASELINE config 2 shape): DDPM-256 (ddpm-ema-celebahq-256 arch, "
+                        "random init), %d image/mask pairs of 256x256 per step per GPU, each a full "
+                        "config-1 edit: rank 5 + null rank 5, N=12 power iterations, t=0.6T, "
+                        "98+40+59 DDIM steps, 5 edited latents per image" % batch,
+            "images_per_step_per_gpu": batch,
+            "fwd_equivalents_per_edit": EDIT_FWD_EQUIV,
+            "tflop_per_edit": EDIT_FWD_EQUIV * F_DDPM256 / 1e12}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -156,8 +167,11 @@ def run_reference(args):
         "unit": "edits/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
         "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config-1 edit: DDPM-256 random-init, 1 image, rank 5 + null 5, N=12, t=0.6T",
-                   "timing": "host wall clock; the edit is assembled from the measured pieces of a bounded sample"},
+        "config": dict(workload_config(args.batch),
+                       arithmetic="fp32 torch CPU (the reference's --dtype fp32), all host threads",
+                       timing="host wall clock; edits are independent and the host runs them one after the other, so "
+                              "edits/s of the batch = 1 / (seconds per edit); the edit is assembled from the measured "
+                              "pieces of a bounded sample (cpu_baseline.sample)"),
         "cpu_baseline": {"value": value, "unit": "edits/s", "cores": threads, "kind": "port",
                          "sample": sample,
                          "forward_b1_s": statistics.mean(v["forward_b1_s"] for v in vals),
@@ -697,13 +711,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "batch edit (BASELINE config 2 shape): DDPM-256 (ddpm-ema-celebahq-256 arch, "
-                                   "random init), %d image/mask pairs of 256x256 per step per GPU, each a full "
-                                   "config-1 edit: rank 5 + null rank 5, N=12 power iterations, t=0.6T, "
-                                   "98+40+59 DDIM steps, 5 edited latents per image" % BATCH,
-                       "images_per_step_per_gpu": BATCH,
-                       "fwd_equivalents_per_edit": EDIT_FWD_EQUIV,
-                       "tflop_per_edit": EDIT_FWD_EQUIV * F_DDPM256 / 1e12,
+            "config": {**workload_config(BATCH),
                        "fwd_equivalents_executed": EDIT_FWD_EXECUTED,
                        "arithmetic": "fp16 storage + tcgen05 kind::f16 products with fp32 accumulation for the convs "
                                      "(tangent / cotangent rows range-scaled by powers of two), fp32 GroupNorm / "

@@ -253,7 +253,8 @@ int loco_groupnorm_silu_vjp(const float* xp, int H, int W, int C, const float* g
 /* Typed variants of the two entry points above: half = 1 takes fp16 tensors (the storage type of
  * the default programs; x / y / gy / gx / addend are then __half*), and `stages` selects the passes
  * (bit 0: statistics incl. clearing `stats`, bit 1: apply) so that each bandwidth-bound kernel can
- * be verified and timed alone.  VJP: gx = J^T gy (+ addend) (+ gx if accumulate). */
+ * be verified and timed alone; bit 2: the one-launch kernel the programs use on their small sites (a
+ * (row, group) slice of <= 8 K elements: statistics + apply by one block per slice, no atomics).  VJP: gx = J^T gy (+ addend) (+ gx if accumulate). */
 int loco_groupnorm_silu_fwd_ex(const void* x, int half, int N, int H, int W, int C, int n_primal,
                                const float* gamma, const float* beta, float eps, int silu, void* y,
                                void* stats, int stages, void* stream);

@@ -570,6 +570,8 @@ int loco_groupnorm_silu_fwd_ex(const void* x, int half, int N, int H, int W, int
   cudaStream_t s = ST(stream);
   View xv = make_view(reinterpret_cast<float*>(const_cast<void*>(x)), N, H, W, C, half);
   View yv = make_view(reinterpret_cast<float*>(y), N, H, W, C, half);
+  if (stages & 4)     // the one-launch kernel of the small sites (statistics + apply, a block per (row, group))
+    return gn_small_fwd(xv, n_primal, reinterpret_cast<double*>(stats), gamma, beta, eps, silu, 0, yv, s);
   if (stages & 1) {
     LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
     LOCO_TRY(gn_stats_fwd(xv, n_primal, reinterpret_cast<double*>(stats), s));
@@ -591,6 +593,11 @@ int loco_groupnorm_silu_vjp_ex(const void* xp, int half, int H, int W, int C, co
   View addv = make_view(reinterpret_cast<float*>(const_cast<void*>(addend)), K, H, W, C, half);
   double* ps = reinterpret_cast<double*>(stats);
   double* bs = ps + 64;
+  if (stages & 4) {   // one launch for the primal statistics, one for statistics + apply of the cotangent rows
+    LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64, s));
+    LOCO_TRY(gn_stats_fwd(xv, 1, ps, s));
+    return gn_small_vjp(xv, ps, gyv, gamma, beta, eps, silu, addend ? &addv : nullptr, accumulate, 0, gxv, s);
+  }
   if (stages & 1) {
     LOCO_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * (K + 1), s));
     LOCO_TRY(gn_stats_fwd(xv, 1, ps, s));

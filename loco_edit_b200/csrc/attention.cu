@@ -1,6 +1,8 @@
 // Attention core (scores, softmax, value mixing) with JVP and VJP: see attention.cuh.
 #include "attention.cuh"
 #include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
 
 namespace loco {
 
@@ -118,6 +120,126 @@ batched_gemm_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long lo
   }
 }
 
+
+// ---- tensor-core version for the long-sequence case -------------------------------------------------
+// The VAE decoder's mid-block attention runs over 64 x 64 = 4096 tokens (512 channels, one head): 17 GFLOP per
+// product and row, 40 products per Jacobian product of the latent-space twin -- half of a decoder pass on the
+// fp32 CUDA-core kernel above (25 TFLOP/s).  Same contract (strided operands, alpha / beta / rounding), products on
+// warp-level mma.sync.m16n8k8 with tf32 operands (the 10-bit mantissa every other GEMM of the path uses) and fp32
+// accumulation: 128 x BN output tile per block, 8 warps of 64 x BN/4, K slabs of 32 staged in shared memory in the
+// orientation of the operand's contiguous index (pitches 36 / 8 mod 32: conflict-free fragment loads), next slab
+// prefetched into registers with 16-byte loads.  (tcgen05 needs TMA-describable, K-major 16-bit or tf32 tiles; half
+// of these products have an M- or N-major operand in fp32 and would need a transposing copy of a 64 MB matrix first.)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int kTM = 128, kTK = 32;
+template <int BN_, bool AKC, bool BNC>
+__global__ void __launch_bounds__(256)
+batched_gemm_mma_kernel(GemmOperand A, GemmOperand B, float* __restrict__ C, long long sCm, long long sCn,
+                        long long sCb, long long sCh, int heads, int M, int N, int K, float alpha, float beta,
+                        int round_out) {
+  constexpr int WN = BN_ / 4, NT = WN / 8;
+  constexpr int AP = AKC ? kTK + 4 : kTM + 8;               // A tile: [m][k] (K contiguous) or [k][m]
+  constexpr int BP = BNC ? BN_ + 8 : kTK + 4;               // B tile: [k][n] (N contiguous) or [n][k]
+  constexpr int ASZ = AKC ? kTM * AP : kTK * AP;
+  constexpr int BSZ = BNC ? kTK * BP : BN_ * BP;
+  constexpr int AV = kTM * kTK / 4 / 256;                   // 16-byte vectors per thread and slab
+  constexpr int BV = BN_ * kTK / 4 / 256;
+  __shared__ __align__(16) float As[ASZ];
+  __shared__ __align__(16) float Bs[BSZ];
+  const int b = blockIdx.z / heads, hd = blockIdx.z % heads;
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * BN_;
+  const float* __restrict__ Ab = A.ptr + b * A.sb + hd * A.sh;
+  const float* __restrict__ Bb = B.ptr + b * B.sb + hd * B.sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * WN;
+  float acc[4][NT][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  float4 ra[AV], rb[BV];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < AV; ++r) {
+      const int e = tid + 256 * r;
+      if (AKC) { const int m = e >> 3, kq = e & 7; ra[r] = *reinterpret_cast<const float4*>(Ab + (long long)(m0 + m) * A.s0 + k0 + 4 * kq); }
+      else { const int k = e >> 5, mq = e & 31; ra[r] = *reinterpret_cast<const float4*>(Ab + (long long)(k0 + k) * A.s1 + m0 + 4 * mq); }
+    }
+#pragma unroll
+    for (int r = 0; r < BV; ++r) {
+      const int e = tid + 256 * r;
+      if (BNC) { const int k = e / (BN_ / 4), nq = e % (BN_ / 4); rb[r] = *reinterpret_cast<const float4*>(Bb + (long long)(k0 + k) * B.s0 + n0 + 4 * nq); }
+      else { const int n = e >> 3, kq = e & 7; rb[r] = *reinterpret_cast<const float4*>(Bb + (long long)(n0 + n) * B.s1 + k0 + 4 * kq); }
+    }
+  };
+  auto rnd4 = [](float4 v) { return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)); };
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < AV; ++r) {
+      const int e = tid + 256 * r;
+      if (AKC) { const int m = e >> 3, kq = e & 7; *reinterpret_cast<float4*>(&As[m * AP + 4 * kq]) = rnd4(ra[r]); }
+      else { const int k = e >> 5, mq = e & 31; *reinterpret_cast<float4*>(&As[k * AP + 4 * mq]) = rnd4(ra[r]); }
+    }
+#pragma unroll
+    for (int r = 0; r < BV; ++r) {
+      const int e = tid + 256 * r;
+      if (BNC) { const int k = e / (BN_ / 4), nq = e % (BN_ / 4); *reinterpret_cast<float4*>(&Bs[k * BP + 4 * nq]) = rnd4(rb[r]); }
+      else { const int n = e >> 3, kq = e & 7; *reinterpret_cast<float4*>(&Bs[n * BP + 4 * kq]) = rnd4(rb[r]); }
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+    __syncthreads();                      // previous slab consumed
+    stash();
+    __syncthreads();
+    if (k0 + kTK < K) fetch(k0 + kTK);
+#pragma unroll
+    for (int ks = 0; ks < kTK / 8; ++ks) {
+      const int c0 = ks * 8 + t, c1 = c0 + 4;
+      uint32_t bf[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = wn + j * 8 + g;
+        bf[j][0] = __float_as_uint(BNC ? Bs[c0 * BP + n] : Bs[n * BP + c0]);
+        bf[j][1] = __float_as_uint(BNC ? Bs[c1 * BP + n] : Bs[n * BP + c1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r0 = wm + i * 16 + g, r1 = r0 + 8;
+        uint32_t af[4];
+        af[0] = __float_as_uint(AKC ? As[r0 * AP + c0] : As[c0 * AP + r0]);
+        af[1] = __float_as_uint(AKC ? As[r1 * AP + c0] : As[c0 * AP + r1]);
+        af[2] = __float_as_uint(AKC ? As[r0 * AP + c1] : As[c1 * AP + r0]);
+        af[3] = __float_as_uint(AKC ? As[r1 * AP + c1] : As[c1 * AP + r1]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], af, bf[j][0], bf[j][1]);
+      }
+    }
+  }
+  float* Cb = C + b * sCb + hd * sCh;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = m0 + wm + i * 16 + g + 8 * h;
+        const int n = n0 + wn + j * 8 + 2 * t;
+        float* cp = Cb + (long long)m * sCm + (long long)n * sCn;
+        float v0 = alpha * acc[i][j][2 * h], v1 = alpha * acc[i][j][2 * h + 1];
+        if (beta != 0.f) { v0 += beta * cp[0]; v1 += beta * cp[sCn]; }
+        if (round_out) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
+        cp[0] = v0; cp[sCn] = v1;
+      }
+}
+
 // One warp per row.
 __global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long rows, float scale) {
   const int lane = threadIdx.x & 31;
@@ -170,10 +292,44 @@ int attention_init() {
   return attention_tc_init();
 }
 
+static bool gemm_mma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOCO_ATTN_MMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int batched_gemm(GemmOperand A, GemmOperand B, float* C, long long sCm, long long sCn, long long sCb,
                  long long sCh, int M, int N, int K, int batch, int heads, float alpha, float beta,
                  int round_out, cudaStream_t s) {
   if (batch <= 0) return 0;
+  // long sequences: the mma.sync kernel (whole tiles, one unit stride per operand, 16-byte aligned vectors)
+  {
+    const bool akc = A.s1 == 1, amc = A.s0 == 1, bnc = B.s1 == 1, bkc = B.s0 == 1;
+    const int bn = (N % 128 == 0) ? 128 : 64;
+    auto al4 = [](long long v) { return v % 4 == 0; };
+    const bool vec = (akc ? al4(A.s0) : al4(A.s1)) && (bnc ? al4(B.s0) : al4(B.s1)) && al4(A.sb) && al4(A.sh) &&
+                     al4(B.sb) && al4(B.sh) && (((uintptr_t)A.ptr | (uintptr_t)B.ptr) & 15) == 0;
+    if (gemm_mma_enabled() && (long long)M * N * K >= (1LL << 27) && M % kTM == 0 && N % 64 == 0 && K % kTK == 0 &&
+        (akc || amc) && (bnc || bkc) && vec) {
+      dim3 grid(N / bn, M / kTM, batch * heads);
+#define LOCO_GEMM_MMA(BN_, AKC, BNC)                                                                             \
+  batched_gemm_mma_kernel<BN_, AKC, BNC><<<grid, 256, 0, s>>>(A, B, C, sCm, sCn, sCb, sCh, heads, M, N, K, alpha, \
+                                                              beta, round_out)
+      if (bn == 128) {
+        if (akc) { if (bnc) LOCO_GEMM_MMA(128, true, true); else LOCO_GEMM_MMA(128, true, false); }
+        else { if (bnc) LOCO_GEMM_MMA(128, false, true); else LOCO_GEMM_MMA(128, false, false); }
+      } else {
+        if (akc) { if (bnc) LOCO_GEMM_MMA(64, true, true); else LOCO_GEMM_MMA(64, true, false); }
+        else { if (bnc) LOCO_GEMM_MMA(64, false, true); else LOCO_GEMM_MMA(64, false, false); }
+      }
+#undef LOCO_GEMM_MMA
+      count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * heads);
   batched_gemm_kernel<<<grid, kGemmThreads, 0, s>>>(A, B, C, sCm, sCn, sCb, sCh, heads, M, N, K, alpha,
                                                     beta, round_out, A.s1 == 1 ? 1 : 0, B.s1 == 1 ? 1 : 0);

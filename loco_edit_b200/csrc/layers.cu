@@ -744,7 +744,7 @@ gn_apply_fwd16_kernel(View x, const double* __restrict__ stats, const float* __r
 //           statistics buffer (the VJP pass reads the primal row's).
 //   MODE 1: VJP rule for cotangent row blockIdx.y at the primal point (xp, pstats).
 // A thread moves VW = 8 (or 4 when a group has 4 channels) consecutive channels of a pixel.
-constexpr int kGnSmallMax = 32768;            // elements of one (row, group) slice
+constexpr int kGnSmallMax = 8192;             // elements of one (row, group) slice (measured: larger slices lose to the two-launch path)
 
 __device__ __forceinline__ double block_sum2(double a, double b, double* sh, double& out_b) {
   a = warp_sum(a); b = warp_sum(b);
@@ -759,11 +759,11 @@ __device__ __forceinline__ double block_sum2(double a, double b, double* sh, dou
 }
 
 template <int MODE, bool F16, int VW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats, double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, int round_out,
                 const float* __restrict__ addend, long long add_sN, long long add_sW, int accumulate, View out) {
-  __shared__ double sh[16];
+  __shared__ double sh[32];
   using Elem = typename std::conditional<F16, __half, float>::type;
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = x.C, cg = C / kGroups, vpp = cg / VW;
@@ -771,8 +771,8 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   const double cnt = (double)HW * cg;
   const View& rows = (MODE == 0) ? x : gy;
   const bool tangent = (MODE == 0) && n >= n_primal;
-  const Elem* xrow = reinterpret_cast<const Elem*>(x.ptr) + ((MODE == 0 && !tangent) ? (long long)n * x.sN : 0) + g * cg;
-  const Elem* rrow = reinterpret_cast<const Elem*>(rows.ptr) + (long long)n * rows.sN + g * cg;
+  const Elem* __restrict__ xrow = reinterpret_cast<const Elem*>(x.ptr) + ((MODE == 0 && !tangent) ? (long long)n * x.sN : 0) + g * cg;
+  const Elem* __restrict__ rrow = reinterpret_cast<const Elem*>(rows.ptr) + (long long)n * rows.sN + g * cg;
   auto ldv = [&](const Elem* base, long long off, float (&v)[VW]) {
     if (F16) {
       if (VW == 8) {
@@ -799,7 +799,7 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
       uint32_t w[VW / 2];
 #pragma unroll
       for (int k = 0; k < VW / 2; ++k) { const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<const uint32_t*>(&h); }
-      if (VW == 8) *reinterpret_cast<uint4*>(base + off) = make_uint4(w[0], w[1], w[2], w[VW / 2 - 2], w[VW / 2 - 1]);
+      if (VW == 8) *reinterpret_cast<uint4*>(base + off) = make_uint4(w[0], w[1], w[VW / 2 - 2], w[VW / 2 - 1]);
       else *reinterpret_cast<uint2*>(base + off) = make_uint2(w[0], w[1]);
     } else {
 #pragma unroll
@@ -814,6 +814,7 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
     mu = mr.x; rstd = mr.y;
   } else {
     double s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
     for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
       float v[VW];
       ldv(xrow, (long long)(e / vpp) * x.sW + (e % vpp) * VW, v);
@@ -833,6 +834,7 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   // ---- primal rows of the forward program: apply and leave ----
   Elem* orow = reinterpret_cast<Elem*>(out.ptr) + (long long)n * out.sN + g * cg;
   if (MODE == 0 && !tangent) {
+#pragma unroll 4
     for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
       const int p = e / vpp, c0 = (e % vpp) * VW;
       float v[VW], o[VW];
@@ -851,6 +853,7 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   }
   // ---- tangent / cotangent rows: sums against the primal slice ----
   double s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
   for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
     const int p = e / vpp, c0 = (e % vpp) * VW;
     float xv[VW], rv[VW];
@@ -877,6 +880,7 @@ gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
   const float m1 = (float)(t1 / cnt);
   const float m2 = (float)((t2 - (double)mu * t1) * (double)rstd / cnt);
   const Elem* arow = addend ? reinterpret_cast<const Elem*>(addend) + (long long)n * add_sN + g * cg : nullptr;
+#pragma unroll 2
   for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
     const int p = e / vpp, c0 = (e % vpp) * VW;
     float xv[VW], rv[VW], o[VW];
@@ -1506,6 +1510,63 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
 #undef LOCO_GN_VJP
   count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---- small sites: one launch per GroupNorm site (gn_small_kernel) ----
+static long long gn_small_max() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOCO_GN_SMALL_MAX");
+    v = e ? atoll(e) : kGnSmallMax;
+  }
+  return v;
+}
+// layout the kernel can address (any slice size)
+static bool gn_small_supported(const View& x) {
+  if (x.C % kGroups != 0) return false;
+  const int cg = x.C / kGroups;
+  if (cg % 4 != 0) return false;
+  const int vw = (cg % 8 == 0) ? 8 : 4;
+  return x.sW % vw == 0 && x.sH == (long long)x.W * x.sW && x.sN % vw == 0;
+}
+// ... and small enough for one block per (row, group) to beat the two-launch path (what the plans ask)
+bool gn_small_eligible(const View& x) {
+  return gn_small_supported(x) && (long long)x.H * x.W * (x.C / kGroups) <= gn_small_max();
+}
+template <int MODE>
+static int gn_small_launch(View x, int n_primal, View gy, const double* pstats, double* stats, const float* gamma,
+                           const float* beta, float eps, int silu, int round_out, const View* addend, int accumulate,
+                           View out, cudaStream_t s) {
+  const View& rows = MODE == 0 ? x : gy;
+  const int cg = x.C / kGroups, vw = (cg % 8 == 0) ? 8 : 4;
+  const long long nvec = (long long)x.H * x.W * (cg / vw);
+  const int block = nvec >= 2048 ? 512 : (nvec >= 256 ? 256 : 128);
+  const dim3 grid(kGroups, rows.N);
+  const float* ap = addend ? addend->ptr : nullptr;
+  const long long asN = addend ? addend->sN : 0, asW = addend ? addend->sW : 0;
+  ProfScope prof(1, (x.half ? 2.0 : 4.0) * rows.N * x.H * x.W * x.C * (MODE == 0 ? 3 : 3 + (addend ? 1 : 0) + (accumulate ? 1 : 0)), s);
+#define LOCO_GN_SMALL(F16, VW) \
+  gn_small_kernel<MODE, F16, VW><<<grid, block, 0, s>>>(x, n_primal, gy, pstats, stats, gamma, beta, eps, silu, round_out, ap, asN, asW, accumulate, out)
+  if (x.half) { if (vw == 8) LOCO_GN_SMALL(true, 8); else LOCO_GN_SMALL(true, 4); }
+  else { if (vw == 8) LOCO_GN_SMALL(false, 8); else LOCO_GN_SMALL(false, 4); }
+#undef LOCO_GN_SMALL
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gn_small_fwd(View x, int n_primal, double* stats, const float* gamma, const float* beta, float eps, int silu,
+                 int round_out, View y, cudaStream_t s) {
+  LOCO_TRY(same_type(x, y, "gn_small_fwd"));
+  LOCO_REQUIRE(gn_small_supported(x) && y.sW % 4 == 0 && y.sH == (long long)y.W * y.sW, "gn_small_fwd: layout not supported");
+  LOCO_REQUIRE(n_primal == x.N || n_primal == 1, "gn_small_fwd: tangent rows need exactly one primal row");
+  return gn_small_launch<0>(x, n_primal, x, nullptr, stats, gamma, beta, eps, silu, round_out, nullptr, 0, y, s);
+}
+int gn_small_vjp(View xp, const double* pstats, View gy, const float* gamma, const float* beta, float eps, int silu,
+                 const View* addend, int accumulate, int round_out, View gx, cudaStream_t s) {
+  LOCO_TRY(same_type(xp, gy, "gn_small_vjp")); LOCO_TRY(same_type(gy, gx, "gn_small_vjp(gx)"));
+  LOCO_REQUIRE(gn_small_supported(xp) && gn_small_supported(gy) && gx.sH == (long long)gx.W * gx.sW &&
+                   (!addend || addend->sH == (long long)addend->W * addend->sW),
+               "gn_small_vjp: layout not supported");
+  return gn_small_launch<1>(xp, 1, gy, pstats, nullptr, gamma, beta, eps, silu, round_out, addend, accumulate, gx, s);
 }
 
 int thin_pad(const float* in_nchw, int c, View out, const float* mix, int bias_rows, const float* scale_dev,

@@ -66,6 +66,14 @@ int gn_apply_vjp(View xp, const double* pstats, View gy, const double* stats, co
                  const float* beta, float eps, int silu, const View* addend, int accumulate,
                  int round_out, View gx, cudaStream_t s);
 
+// Small sites (a (row, group) slice of <= 8 K elements, LOCO_GN_SMALL_MAX: the <= 32^2 layers): statistics + apply in ONE launch, a
+// block per (row, group), no atomics.  gn_small_fwd also stores the statistics (the VJP pass reads the primal row's).
+bool gn_small_eligible(const View& x);
+int gn_small_fwd(View x, int n_primal, double* stats, const float* gamma, const float* beta, float eps, int silu,
+                 int round_out, View y, cudaStream_t s);
+int gn_small_vjp(View xp, const double* pstats, View gy, const float* gamma, const float* beta, float eps, int silu,
+                 const View* addend, int accumulate, int round_out, View gx, cudaStream_t s);
+
 // ---- resampling ----
 // out (+)= scale * nearest_upsample(in), out = 2H x 2W.  scale 1: the DDPM Upsample / P2 up ResBlock
 // (ddpm/diffusion.py:816-832, guided_diffusion/unet.py:95-124); scale 1/4: VJP of the 2x2 avg-pool.

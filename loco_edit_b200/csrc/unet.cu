@@ -769,7 +769,10 @@ int Plan::build(float* workspace) {
     const float* ga = aff ? aff : (dry ? nullptr : M.w(n.gamma));
     const float* be = aff ? aff + n.C : (dry ? nullptr : M.w(n.beta));
     const int np = NP;
+    // small sites whose statistics no conv epilogue produced: statistics + apply in one launch
+    const bool small = !fused && gn_small_eligible(x) && y.sH == (long long)y.W * y.sW;
     I.fwd.push_back([=](cudaStream_t s) {
+      if (small) return gn_small_fwd(x, np, st, ga, be, eps, silu, round_out, y, s);
       if (!fused) LOCO_TRY(gn_stats_fwd(x, np, st, s));   // else: accumulated by the producer's epilogue
       return gn_apply_fwd(x, np, st, ga, be, eps, silu, round_out, y, s);
     });
@@ -788,7 +791,10 @@ int Plan::build(float* workspace) {
     const float* be = aff ? aff + n.C : (dry ? nullptr : M.w(n.beta));
     const bool has_add = addend != nullptr;
     const View add = has_add ? *addend : View();
+    const bool small = gn_small_eligible(xp) && gn_small_eligible(gy) && gx.sH == (long long)gx.W * gx.sW &&
+                       (!has_add || add.sH == (long long)add.W * add.sW);
     push_b([=](cudaStream_t s) {
+      if (small) return gn_small_vjp(xp, pstats, gy, ga, be, eps, silu, has_add ? &add : nullptr, accumulate, round_out, gx, s);
       LOCO_TRY(gn_stats_vjp(xp, pstats, gy, ga, be, eps, silu, st, s));
       return gn_apply_vjp(xp, pstats, gy, st, ga, be, eps, silu, has_add ? &add : nullptr, accumulate,
                           round_out, gx, s);

@@ -205,6 +205,44 @@ def test_groupnorm_silu_fp16_fwd_jvp_vjp(dev, C, H, silu):
     assert max(e0, e1, e2, e3, e4) < 6e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("C,H,silu", [(128, 32, True), (128, 64, True), (256, 64, True), (512, 16, False), (1024, 8, True)])
+def test_groupnorm_small_site_one_launch_kernel(dev, C, H, silu, dtype):
+    """`gn_small_kernel` (stages = 4): statistics + apply of a <= 64^2 site in one launch -- primal row,
+    tangent rows (JVP), cotangent rows (VJP, incl. addend + accumulate) against fp64, and against the
+    two-launch kernels it replaces; the stored statistics of the primal row are what the VJP pass reads."""
+    from loco_edit_b200 import ops
+    g = torch.Generator().manual_seed(C * 3 + H)
+    k = 5
+    cast = lambda t: t.to(dtype).to(dev)
+    x = cast(torch.randn(1, C, H, H, generator=g) * 1.5 + 0.3)
+    dx = cast(torch.randn(k, C, H, H, generator=g))
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev)
+    eps = 1e-6
+    f = lambda z: _gn_silu(z, gamma.double(), beta.double(), eps, silu)
+    ref = torch.cat([f(x.double())] + [torch.func.jvp(f, (x.double(),), (dx[j:j + 1].double(),))[1] for j in range(k)], 0)
+    xin = nhwc(torch.cat([x, dx], 0))
+    y, st = ops.groupnorm_silu_fwd_ex(xin, 1, gamma, beta, eps, silu, stages=4)
+    y2, st2 = ops.groupnorm_silu_fwd_ex(xin, 1, gamma, beta, eps, silu, stages=3)
+    tol = 6e-4 if dtype == torch.float16 else 2e-5
+    e0, e1 = rel_err(nchw(y.float())[:1], ref[:1]), rel_err(nchw(y.float())[1:], ref[1:])
+    assert rel_err(st[:64], st2[:64]) < 1e-6                     # primal (sum x, sum x^2); fp32 partials in another order
+    assert rel_err(y.float(), y2.float()) < tol
+    gy, add, acc = (cast(torch.randn(k, C, H, H, generator=g)) for _ in range(3))
+    xd = x.double().requires_grad_(True)
+    yy = _gn_silu(xd, gamma.double(), beta.double(), eps, silu)
+    gref = torch.cat([torch.autograd.grad(yy, xd, gy[j:j + 1].double(), retain_graph=True)[0] for j in range(k)], 0)
+    gx, _ = ops.groupnorm_silu_vjp_ex(nhwc(x), nhwc(gy), gamma, beta, eps, silu, stages=4)
+    e2 = rel_err(nchw(gx.float()), gref)
+    gx2 = nhwc(acc).clone()
+    ops.groupnorm_silu_vjp_ex(nhwc(x), nhwc(gy), gamma, beta, eps, silu, addend=nhwc(add), accumulate=True, gx=gx2, stages=4)
+    e3 = rel_err(nchw(gx2.float()), gref + add.double() + acc.double())
+    torch.cuda.synchronize()
+    print(f"gn small-site {dtype} C={C} H={H}: primal {e0:.2e} tangent {e1:.2e} vjp {e2:.2e} vjp+addend+acc {e3:.2e}")
+    assert max(e0, e1, e2, e3) < tol
+
+
 def _attn_core(qkv):   # qkv [N, T, 3C] -> o [N, T, C]   (reference ddpm/diffusion.py:950-962)
     C = qkv.shape[-1] // 3
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
@@ -217,9 +255,10 @@ def _tf32(x):
     return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-@pytest.mark.parametrize("T,C", [(64, 128), (256, 512), (128, 256), (256, 128)])
+@pytest.mark.parametrize("T,C", [(64, 128), (256, 512), (128, 256), (256, 128), (1024, 128), (2048, 64)])
 def test_attention_fwd_jvp_vjp(dev, T, C):
-    """Fused tcgen05 attention (kind::tf32) against fp64 on tf32-representable operands: the
+    """Fused tcgen05 attention (kind::tf32; T <= 256) and the long-sequence path (scores in HBM, products on
+    mma.sync tf32: the VAE decoder's 4096-token mid block) against fp64 on tf32-representable operands: the
     products are then exact, what remains is the tf32 rounding of the probabilities / of gS that
     feed the second product and of the stored results (2^-11 relative each)."""
     from loco_edit_b200 import ops
