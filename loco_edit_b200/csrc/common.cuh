@@ -73,6 +73,16 @@ inline View slice_n(const View& v, int n0, int N) {
   View r = v; r.ptr = elem_ptr(v, (long long)n0 * v.sN); r.N = N; return r;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor on the stream is still running: pdl_wait() blocks until every predecessor grid has
+// completed and its memory operations are visible (a no-op for a plain launch); pdl_trigger() lets the
+// successor's CTAs be scheduled as soon as every CTA of this grid has reached it.  The conv kernels
+// run their prologue (tensor-map prefetch, mbarrier init, TMEM allocation) before pdl_wait(), i.e.
+// under the tail of the GroupNorm / resampling kernel that produces their input.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 int num_sms();
 
 // ---- multi-device support -----------------------------------------------------------------

@@ -246,6 +246,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                            // inputs of this launch are complete and visible from here on
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -587,6 +588,7 @@ conv_gemm_tf32_wide_kernel(const __grid_constant__ ConvGemmParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                            // inputs of this launch are complete and visible from here on
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -1239,6 +1241,7 @@ conv_gemm_tf32_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   cluster_sync_all();                    // the peer's barriers and TMEM exist from here on
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   // register re-allocation between the warpgroups (launch: 65536 / 384 = 168 per thread): the
   // producer / MMA warpgroup needs few, the two epilogue warpgroups keep a residual tile in registers
@@ -1798,6 +1801,15 @@ int conv_init() {
   return 0;
 }
 
+static bool conv_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOCO_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int conv_run(const ConvLaunch& L, cudaStream_t stream) {
   LOCO_TRY(conv_init());
   {
@@ -1806,11 +1818,19 @@ int conv_run(const ConvLaunch& L, cudaStream_t stream) {
       int smem = 0;
       ConvKernel k = conv_kernel(L.p[i].nt, L.p[i].in16, L.p[i].out16, &smem);
       LOCO_REQUIRE(k != nullptr, "conv: variant %d has no fp16 instantiation", L.p[i].nt);
-      if (L.p[i].nt == 5) {
-        // the CTA-pair kernel carries __cluster_dims__(2,1,1): plain launch, even grid
-        k<<<L.grid[i], kPairThreads, smem, stream>>>(L.p[i]);
+      // (the CTA-pair kernel carries __cluster_dims__(2,1,1): no launch attribute needed for it, even grid)
+      const int threads = L.p[i].nt == 5 ? kPairThreads : kThreads;
+      if (conv_pdl_enabled()) {
+        // programmatic dependent launch: the prologue overlaps the tail of the producing kernel (pdl_wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(L.grid[i]); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LOCO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, L.p[i]));
       } else {
-        k<<<L.grid[i], kThreads, smem, stream>>>(L.p[i]);
+        k<<<L.grid[i], threads, smem, stream>>>(L.p[i]);
       }
     }
     count_launch(L.nlaunch);

@@ -536,6 +536,7 @@ gn_apply_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats
                 const float* __restrict__ beta, float eps, int silu, int round_out,
                 const float* __restrict__ addend, long long add_sN, long long add_sH,
                 long long add_sW, int accumulate, View out, int lin) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   constexpr int VEC = GnVec<F16>::value;
   constexpr int NQ = VEC / 4;
   constexpr bool EXTRA = (MODE == 1 && RC == 4);
@@ -675,6 +676,7 @@ constexpr int kGn16Unroll = 4;
 __global__ void __launch_bounds__(256)
 gn_apply_fwd16_kernel(View x, const double* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, int silu, View y, int lin) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   const int C = x.C;
   const int c8n = C >> 3;
   const int cg = C / kGroups;
@@ -763,6 +765,7 @@ __global__ void __launch_bounds__(512)
 gn_small_kernel(View x, int n_primal, View gy, const double* __restrict__ pstats, double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, int round_out,
                 const float* __restrict__ addend, long long add_sN, long long add_sW, int accumulate, View out) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   __shared__ double sh[32];
   using Elem = typename std::conditional<F16, __half, float>::type;
   const int g = blockIdx.x, n = blockIdx.y;
@@ -931,6 +934,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 thin_pad_kernel(const float* __restrict__ in, int c, View out, const float* __restrict__ mix, int bias_rows,
                 const float* __restrict__ scale_dev, int scale_from, int round_out) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   constexpr int VPP = F16 ? kThinPad / 8 : kThinPad / 4;      // 16-byte vectors per pixel
   const long long HW = (long long)out.H * out.W;
   const long long total = (long long)out.N * HW * VPP;
@@ -1003,6 +1007,7 @@ thin_extract_kernel(View in, int c, float* __restrict__ out, const float* __rest
 // ------------------------------------------------------------------------------------------------
 template <bool F16>
 __global__ void upsample2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1029,6 +1034,7 @@ __global__ void upsample2x_kernel(View in, View out, float scale, int accumulate
 template <bool F16>
 __global__ void __launch_bounds__(256)
 upsample2x_fast_kernel(View in, View out, float scale, int round_out) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   constexpr int VEC = F16 ? 8 : 4;
   const int cvn = in.C / VEC;
   const long long total = (long long)in.N * in.H * in.W * cvn;
@@ -1073,6 +1079,7 @@ upsample2x_fast_kernel(View in, View out, float scale, int round_out) {
 }
 template <bool F16>
 __global__ void sumpool2x_kernel(View in, View out, float scale, int accumulate, int round_out) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1100,6 +1107,7 @@ __global__ void sumpool2x_kernel(View in, View out, float scale, int accumulate,
 }
 template <bool F16>
 __global__ void add_views_kernel(View in, View out, int accumulate) {
+  pdl_trigger();   // a dependent conv launch may start its prologue now (it waits for this grid's completion)
   const int cvn = out.C >> 2;
   const long long total = (long long)out.N * out.H * out.W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
