@@ -128,9 +128,11 @@ def _pair_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_jointly_sharded_edit_and_null_bases_equal_two_unsharded_runs():
+@pytest.mark.parametrize("world", [2, 3])
+def test_jointly_sharded_edit_and_null_bases_equal_two_unsharded_runs(world):
     """the k + k_null probes of the edit basis (mask) and the null basis (~mask) sharded
-    jointly over 2 ranks == two separate unsharded power methods of the oracle."""
+    jointly over the ranks == two separate unsharded power methods of the oracle.  world_size 3 shards the 5
+    probes 2 / 2 / 1: the ragged (padded) all-gather of the W rows."""
     ret = mp.Manager().dict()
-    mp.spawn(_pair_worker, args=(2, 29650 + (os.getpid() % 300), ret), nprocs=2, join=True)
+    mp.spawn(_pair_worker, args=(world, 29650 + 7 * world + (os.getpid() % 300), ret), nprocs=world, join=True)
     assert ret["s_err"] < 1e-4 and ret["v_err"] < 1e-3, dict(ret)
