@@ -233,6 +233,9 @@ class B200VAEDecoder(B200UNet):
         arch["kind"] = "vae_decoder"
         arch.setdefault("in_ch", 4)
         arch.setdefault("attn_resolutions", ())
+        from .weights import hf_autoencoderkl_to_decoder, is_hf_autoencoderkl_state_dict
+        if is_hf_autoencoderkl_state_dict(state_dict):          # a diffusers AutoencoderKL checkpoint
+            state_dict = hf_autoencoderkl_to_decoder(state_dict, arch)
         super().__init__(arch, state_dict, device=device)
 
     def decode(self, z):

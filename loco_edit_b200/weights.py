@@ -439,3 +439,61 @@ def hf_unet2d_to_ddpm(sd, arch=DDPM256):
 
 def is_hf_unet2d_state_dict(sd):
     return any(k.startswith(("down_blocks.", "time_embedding.")) for k in sd)
+
+
+# ------------------------------------------------------------------------------------------------
+# Hugging Face `AutoencoderKL` checkpoints (the `vae` of a Stable Diffusion pipeline, src/utils/utils.py:217)
+# ------------------------------------------------------------------------------------------------
+def hf_autoencoderkl_to_decoder(sd, arch=SD_VAE_DECODER):
+    """diffusers `AutoencoderKL.state_dict()` -> the decoder-half names of `vae_decoder_param_shapes`
+    (encoder.* and quant_conv.* are dropped: the path only decodes, src/modules/edit.py:770).
+    up_blocks are numbered in execution order (0 = lowest resolution), the CompVis `up.{l}` by level;
+    the mid-block attention projections are Linear [C, C] (query/key/value/proj_attn in diffusers 0.11,
+    to_q/to_k/to_v/to_out.0 later) and become 1x1 convs."""
+    L = len(tuple(arch["ch_mult"]))
+    out = {}
+    for name, w in sd.items():
+        parts = name.split(".")
+        leaf = parts[-1]
+        if parts[0] in ("encoder", "quant_conv"):
+            continue
+        new = None
+        if parts[0] == "post_quant_conv":
+            new = name
+        elif parts[0] == "decoder":
+            if parts[1] in ("conv_in", "conv_out"):
+                new = name
+            elif parts[1] == "conv_norm_out":
+                new = "decoder.norm_out." + leaf
+            elif parts[1] == "mid_block":
+                kind, idx, sub = parts[2], int(parts[3]), ".".join(parts[4:-1])
+                if kind == "resnets":
+                    new = "decoder.mid.block_%d.%s.%s" % (idx + 1, _HF_RES[sub], leaf)
+                elif kind == "attentions":
+                    new = "decoder.mid.attn_1.%s.%s" % (_HF_ATTN[sub], leaf)
+                    if sub != "group_norm" and leaf == "weight" and w.dim() == 2:
+                        w = w[:, :, None, None]
+            elif parts[1] == "up_blocks" and len(parts) >= 6 and parts[4].isdigit():
+                lvl, kind, idx, sub = L - 1 - int(parts[2]), parts[3], int(parts[4]), ".".join(parts[5:-1])
+                if kind == "resnets":
+                    new = "decoder.up.%d.block.%d.%s.%s" % (lvl, idx, _HF_RES[sub], leaf)
+                elif kind == "upsamplers":
+                    new = "decoder.up.%d.upsample.conv.%s" % (lvl, leaf)
+        if new is None:
+            raise KeyError("hf_autoencoderkl_to_decoder: unexpected parameter '%s'" % name)
+        if new in out:
+            raise KeyError("hf_autoencoderkl_to_decoder: '%s' maps to '%s' twice" % (name, new))
+        out[new] = w
+    want = vae_decoder_param_shapes(arch)
+    missing = [k for k in want if k not in out]
+    extra = [k for k in out if k not in want]
+    if missing or extra:
+        raise KeyError("hf_autoencoderkl_to_decoder: missing %s, unexpected %s" % (missing[:3], extra[:3]))
+    for k, shp in want.items():
+        if tuple(out[k].shape) != tuple(shp):
+            raise ValueError("hf_autoencoderkl_to_decoder: %s has shape %s, expected %s" % (k, tuple(out[k].shape), shp))
+    return out
+
+
+def is_hf_autoencoderkl_state_dict(sd):
+    return any(k.startswith(("decoder.up_blocks.", "decoder.mid_block.")) for k in sd)

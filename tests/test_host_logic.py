@@ -164,6 +164,69 @@ def test_hf_unet2d_checkpoint_names_map_onto_the_ddpm_state_dict(legacy_attn):
             hf_unet2d_to_ddpm(short, arch)
 
 
+@pytest.mark.parametrize("legacy_attn", [True, False])
+def test_hf_autoencoderkl_checkpoint_names_map_onto_the_decoder_state_dict(legacy_attn):
+    """The `vae` of a Stable Diffusion pipeline is a diffusers AutoencoderKL (src/utils/utils.py:217); its decoder
+    half must map onto exactly the names / shapes B200VAEDecoder takes (Linear q/k/v -> 1x1 conv, up_blocks in
+    execution order -> levels), the encoder half is ignored."""
+    import re
+    from loco_edit_b200.weights import (SD_VAE_DECODER, hf_autoencoderkl_to_decoder, is_hf_autoencoderkl_state_dict,
+                                        random_state_dict, tiny_vae_decoder_arch, vae_decoder_param_shapes)
+    res = {"norm1": "norm1", "conv1": "conv1", "norm2": "norm2", "conv2": "conv2", "nin_shortcut": "conv_shortcut"}
+    attn = ({"norm": "group_norm", "q": "query", "k": "key", "v": "value", "proj_out": "proj_attn"} if legacy_attn else
+            {"norm": "group_norm", "q": "to_q", "k": "to_k", "v": "to_v", "proj_out": "to_out.0"})
+
+    def to_hf(arch):
+        L = len(arch["ch_mult"])
+        names = {}
+        for n, shp in vae_decoder_param_shapes(arch).items():
+            leaf = n.rsplit(".", 1)[1]
+            m = re.match(r"decoder\.mid\.block_(\d)\.(\w+)\.", n)
+            if m:
+                h = "decoder.mid_block.resnets.%d.%s.%s" % (int(m.group(1)) - 1, res[m.group(2)], leaf)
+            elif n.startswith("decoder.mid.attn_1."):
+                sub = n.split(".")[3]
+                h = "decoder.mid_block.attentions.0.%s.%s" % (attn[sub], leaf)
+                if sub != "norm" and leaf == "weight":
+                    shp = shp[:2]
+            elif re.match(r"decoder\.up\.(\d+)\.block\.", n):
+                m = re.match(r"decoder\.up\.(\d+)\.block\.(\d+)\.(\w+)\.", n)
+                h = "decoder.up_blocks.%d.resnets.%s.%s.%s" % (L - 1 - int(m.group(1)), m.group(2), res[m.group(3)], leaf)
+            elif ".upsample.conv." in n:
+                h = "decoder.up_blocks.%d.upsamplers.0.conv.%s" % (L - 1 - int(n.split(".")[2]), leaf)
+            elif n.startswith("decoder.norm_out."):
+                h = "decoder.conv_norm_out." + leaf
+            else:
+                h = n
+            names[n] = (h, shp)
+        return names
+
+    for arch in (tiny_vae_decoder_arch(), SD_VAE_DECODER):
+        names = to_hf(arch)
+        if arch is SD_VAE_DECODER:       # names / shapes only
+            with torch.device("meta"):
+                hf = {h: torch.empty(shp) for h, shp in names.values()}
+                hf["encoder.conv_in.weight"] = torch.empty(128, 3, 3, 3)
+                hf["quant_conv.weight"] = torch.empty(8, 8, 1, 1)
+            assert len(hf_autoencoderkl_to_decoder(hf, arch)) == len(names)
+            continue
+        sd = random_state_dict(arch, seed=5)
+        hf = {h: sd[n].reshape(shp).clone() for n, (h, shp) in names.items()}
+        assert is_hf_autoencoderkl_state_dict(hf) and not is_hf_autoencoderkl_state_dict(sd)
+        got = hf_autoencoderkl_to_decoder(hf, arch)
+        assert sorted(got) == sorted(sd)
+        for n in sd:
+            assert torch.equal(got[n], sd[n]), n
+        bad = dict(hf)
+        bad["decoder.up_blocks.0.mystery.weight"] = torch.zeros(1)
+        with pytest.raises(KeyError):
+            hf_autoencoderkl_to_decoder(bad, arch)
+        short = dict(hf)
+        short.pop("decoder.conv_out.bias")
+        with pytest.raises(KeyError):
+            hf_autoencoderkl_to_decoder(short, arch)
+
+
 def test_mask_files_and_postprocessing(tmp_path):
     """mask/mask.pt format of the SAM wrapper (src/modules/mask_segmentation.py:18-26), the row
     selection of the drivers (src/modules/edit.py:2247) and the DiffEdit formula (:1401-1402)."""
