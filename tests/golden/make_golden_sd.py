@@ -12,7 +12,7 @@ both networks are stand-ins plugged into the reference object as `self.unet` / `
 The scheduler is a stub holding Stable Diffusion's "scaled_linear" alpha_bar table, monkey-patched by the
 reference's own `get_stable_diffusion_scheduler` (src/utils/utils.py:147-157).  Everything else is the
 reference's code: _classifer_free_guidance (4 modes), get_x0 (with the decode), the latent-space power method
-local_encoder_decoder_pullback_zt (N = 1, 2; two guidance modes; mask and ~mask over the DECODED image),
+local_encoder_decoder_pullback_zt (N = 1, 2 and 6; two guidance modes; mask and ~mask over the DECODED image),
 get_delta_zt_via_grad, DDIMforwardsteps (last 9 steps + decode).
 """
 import os
@@ -95,6 +95,12 @@ def main():
                                                            max_iter=n_iter, convergence_threshold=1e-3, mask=m, mode=mode)
             out["pullback"][(mode, mname, n_iter)] = {"u": u.clone(), "s": s.clone(), "vT": vT.clone()}
             print(mode, mname, n_iter, s.tolist())
+    # depth: six iterations of the masked power method (the error of the CUDA path adds up over iterations)
+    torch.manual_seed(7)
+    u, s, vT = e.local_encoder_decoder_pullback_zt(zt, t, t_idx, *embs, pca_rank=2, chunk_size=5, min_iter=10 ** 6,
+                                                   max_iter=6, convergence_threshold=1e-3, mask=mask, mode="null+(for-null)")
+    out["pullback"][("null+(for-null)", "mask", 6)] = {"u": u.clone(), "s": s.clone(), "vT": vT.clone()}
+    print("N=6", s.tolist())
     out["delta_masked"] = e.get_delta_zt_via_grad(zt, t, t_idx, *embs, mask=mask, mode="null+(for-null)+(edit-null)").clone()
     edit.tvu.save_image = lambda *a, **k: None
     with torch.no_grad():
