@@ -280,6 +280,10 @@ def measure_bandwidth_kernels(dev, hbm_peak):
     run("ddim_step_b40_eta1", lambda i: ops.ddim_step(xb[i % 4], eb[i % 4], 0.5, 0.6, eta=1.0, noise=nb[i % 4]),
         4 * xb[0].numel() * 4, 8)
     run("axpy_b40", lambda i: ops.axpy(xb[i % 4], eb[i % 4], 0.5), 3 * xb[0].numel() * 4, 8)
+    # BASELINE config 3 (rank 64): the replicated step of the probe-sharded power method
+    del W, Vn
+    W64 = [torch.randn(64, d, device=dev, generator=g) for _ in range(4)]                # 4 x 50 MB
+    run("orthonormalise_k64", lambda i: ops.orthonormalise(W64[i % 4]), 3 * 64 * d * 4, 4)
     return out
 
 
