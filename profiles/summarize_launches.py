@@ -25,10 +25,11 @@ passes, cur = [], []
 for n, v in data:
     if n.startswith("pack_") or n.startswith("set_scalar"):
         continue
-    if n.startswith("temb_kernel") and cur:
+    # (temb_kernel until the last session of round 2, then two temb_dense_kernel launches: split at the first)
+    if (n.startswith("temb_kernel") or (n.startswith("temb_dense_kernel") and not (cur and cur[-1][0].startswith("temb_dense_kernel")))) and cur:
         passes.append(cur); cur = []
     cur.append((n, v))
-    if n.startswith("edge_reduce") and len(cur) > 50 and any(x[0].startswith("temb_kernel") for x in cur):
+    if n.startswith("edge_reduce") and len(cur) > 50 and any(x[0].startswith(("temb_kernel", "temb_dense_kernel")) for x in cur):
         passes.append(cur); cur = []
 if cur:
     passes.append(cur)
