@@ -4,7 +4,7 @@ T-LOCO class `EditDeepFloydIF` of loco_edit_b200/t2i.py on a stand-in text-condi
 to seeded prompt embeddings (the IF network and its T5 encoder are diffusers / transformers models that cannot
 be obtained here); Stable Diffusion model names run the latent-space class
 `EditStableDiffusion` of loco_edit_b200/sd.py on a stand-in latent U-Net and the SD-shaped VAE decoder (the
-decoder Jacobian sits inside every Jacobian product).  The LCM class raises NotImplementedError.
+decoder Jacobian sits inside every Jacobian product); LCM model names run `EditLatentConsistency` (same file) the same way.
 
     python -m loco_edit_b200.main --model_name LSUN_church_HF --dataset_name LSUN_church --dtype fp32 \
         --edit_t 0.6 --performance_boosting_t 0.2 --pca_rank 5 --pca_rank_null 5 \
@@ -64,10 +64,32 @@ def main_stable_diffusion(args):
     return edit
 
 
+def main_lcm(args):
+    """src/main.py:30-32, 52-62 for `--model_name *LCM*`: the latent-consistency class (z_t [4, 64, 64], 512^2 images)."""
+    import torch
+    from .sd import EditLatentConsistency, LCMB200UNet
+    from .unet import B200UNet, B200VAEDecoder
+    from .weights import SD_VAE_DECODER, random_state_dict, sd_standin_unet_arch
+    print("LCM: running the stand-in latent U-Net (w-conditioned) and a random-init VAE decoder of the SD 1.x shape "
+          "(the checkpoints / CLIP text encoder are not available offline)")
+    dev = torch.device(args.device)
+    arch = sd_standin_unet_arch(args.image_size // 8)
+    varch = dict(SD_VAE_DECODER, resolution=args.image_size // 8)
+    net = LCMB200UNet(B200UNet(arch, random_state_dict(arch, seed=1234), device=dev))
+    vae = B200VAEDecoder(varch, random_state_dict(varch, seed=4321), device=dev)
+    edit = EditLatentConsistency(args, net, vae)
+    if args.run_edit_null_space_projection_zt:
+        edit.run_edit_null_space_projection_zt(
+            op='mid', block_idx=0, mask_index=args.mask_index, vis_num=args.vis_num, vis_num_pc=args.pca_rank,
+            pca_rank=args.pca_rank, edit_prompt=args.edit_prompt, null_space_projection=args.null_space_projection,
+            pca_rank_null=args.pca_rank_null, non_semantic=getattr(args, "non_semantic", False))
+    return edit
+
+
 def main(argv=None):
     args = preset(parse_args(argv))
     if args.is_LCM:
-        raise NotImplementedError("the latent-consistency class is not part of this path (DESIGN.md, out of scope)")
+        return main_lcm(args)
     if args.is_stable_diffusion:
         return main_stable_diffusion(args)
     if args.is_DeepFloyd_IF_diffusion:

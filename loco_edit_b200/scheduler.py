@@ -105,3 +105,65 @@ class YHCustomScheduler(object):
         xn, x0 = ops.ddim_step(xt.contiguous(), et.contiguous(), at, at_next, float(eta),
                                noise=noise, want_x0=True)
         return SchedulerOutput(xn, x0)
+
+
+class LCMScheduler(object):
+    """Restatement of diffusers' `LCMScheduler` as the latent-consistency class uses it
+    (`self.scheduler.step(model_pred, t, latents, return_dict=False) -> (prev_sample, denoised)`,
+    src/modules/edit.py:140, 237, 194; that class only works with the STOCK scheduler: the custom `step` of
+    utils.py:186-213 returns an object that cannot be unpacked).  diffusers is a third-party dependency that is
+    not under /root/reference: PARITY UNPINNED for this arithmetic; what is restated is the published algorithm
+    (Luo et al., Latent Consistency Models; diffusers `scheduling_lcm.py`, epsilon prediction):
+      timesteps: every (original_steps // n)-th of the `original_steps` training-grid points k * (T // original_steps) - 1,
+                 descending;
+      boundary scalings at s = timestep_scaling * t: c_skip = sd^2 / (s^2 + sd^2), c_out = s / sqrt(s^2 + sd^2), sd = 0.5;
+      denoised = c_out * (x - sqrt(1 - a_t) eps) / sqrt(a_t) + c_skip * x;
+      prev_sample = sqrt(a_prev) * denoised + sqrt(1 - a_prev) * noise   (the last step returns `denoised`).
+    alpha_bar: Stable Diffusion's "scaled_linear" table."""
+
+    def __init__(self, device, original_inference_steps=50, timestep_scaling=10.0, sigma_data=0.5, num_train_timesteps=1000):
+        self.device = torch.device(device)
+        self.original_inference_steps = original_inference_steps
+        self.timestep_scaling, self.sigma_data, self.T = timestep_scaling, sigma_data, num_train_timesteps
+        betas = scaled_linear_betas(num_train_timesteps)
+        acp = torch.cumprod(1.0 - betas, dim=0)
+        self._acp_host = acp.tolist()
+        self.alphas_cumprod = acp.to(self.device)
+        self.timesteps = None
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        k = self.T // self.original_inference_steps
+        origin = [i * k - 1 for i in range(1, self.original_inference_steps + 1)]
+        skip = self.original_inference_steps // num_inference_steps
+        ts = origin[::-skip][:num_inference_steps]
+        self._ts_host = [int(t) for t in ts]
+        self.num_inference_steps = num_inference_steps
+        self.timesteps = torch.tensor(self._ts_host, dtype=torch.long, device=self.device if device is None else device)
+
+    def alpha_at(self, t):
+        return self._acp_host[int(t)]
+
+    def scalings(self, t):
+        """(c_skip, c_out) of the boundary condition at timestep t."""
+        s = self.timestep_scaling * float(int(t))
+        sd = self.sigma_data
+        return sd * sd / (s * s + sd * sd), s / (s * s + sd * sd) ** 0.5
+
+    def denoised_coefficients(self, t):
+        """denoised = c1 * x + c2 * eps."""
+        a = self.alpha_at(t)
+        c_skip, c_out = self.scalings(t)
+        return c_out / a ** 0.5 + c_skip, -c_out * (1.0 - a) ** 0.5 / a ** 0.5
+
+    def step(self, model_output, timestep, sample, t_idx=None, noise=None, return_dict=False, **kwargs):
+        if t_idx is None:
+            t_idx = self._ts_host.index(int(timestep))
+        c1, c2 = self.denoised_coefficients(self._ts_host[t_idx])
+        denoised = ops.combine3(sample.contiguous(), c1, model_output.contiguous(), c2)
+        if t_idx == self.num_inference_steps - 1:
+            return denoised, denoised
+        a_prev = self.alpha_at(self._ts_host[t_idx + 1])
+        if noise is None:
+            noise = torch.randn_like(sample)
+        prev = ops.combine3(denoised, a_prev ** 0.5, noise.contiguous(), (1.0 - a_prev) ** 0.5)
+        return prev, denoised

@@ -152,6 +152,11 @@ class EditStableDiffusion(EditDeepFloydIF):
         s [k] = sqrt(svdvals), vT [k, d_z]) like the reference."""
         assert mode in SD_MODES
         slots = self._cfg_slots(mode, (for_prompt_emb, edit_prompt_emb, null_prompt_emb))
+        return self._power_method(zt, t, slots, pca_rank, min_iter, max_iter, convergence_threshold, mask, v0)
+
+    def _power_method(self, zt, t, slots, pca_rank, min_iter, max_iter, convergence_threshold, mask, v0):
+        """The subspace iteration shared by the latent-space classes: `slots` = the conditionings whose noise
+        predictions combine linearly into the one the posterior mean uses."""
         k = int(pca_rank)
         d = zt[0].numel()
         z = zt.to(self.device, torch.float32).contiguous().reshape(1, -1)
@@ -305,3 +310,186 @@ class EditStableDiffusion(EditDeepFloydIF):
                            f'_select_mask{mask_index}_null_space_projection_{null_space_projection}_null_space_rank_{pca_rank_null}'
                            f'_{self.tilda_v_score_type}')
         return self._project_and_edit(zt, vT_modify, vT_null, null_space_projection, pca_rank_null, vis_num, vis_num_pc, name, kw)
+
+
+# ================================================================================================
+# Latent consistency twin
+# ================================================================================================
+def guidance_scale_embedding(w, embedding_dim=256):
+    """`pipe.get_guidance_scale_embedding(w, embedding_dim)` of diffusers' LatentConsistencyModelPipeline (called at
+    src/modules/edit.py:118, 161, 218): sinusoidal embedding of 1000 w, [sin | cos], divisor half - 1."""
+    import math
+    w = torch.as_tensor(w, dtype=torch.float32).reshape(-1) * 1000.0
+    half = embedding_dim // 2
+    emb = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    emb = w[:, None] * emb[None, :]
+    return torch.cat([torch.sin(emb), torch.cos(emb)], dim=1)
+
+
+class LCMB200UNet(object):
+    """Stand-in for the distilled LCM U-Net `unet(z, t, timestep_cond=w_embedding, encoder_hidden_states=...)`
+    (src/modules/edit.py:182-188): this package's text-conditioned latent U-Net (cross-attention to the prompt tokens)
+    whose timestep embedding additionally receives the guidance-scale embedding through a fixed seeded projection
+    (`loco_plan_set_condition`; diffusers adds `cond_proj(timestep_cond)` to the sinusoid before the time MLP)."""
+
+    def __init__(self, base, w_dim=256, seed=0):
+        from .t2i import TextB200UNet, cond_projection
+        self.text = TextB200UNet(base)
+        self.base, self.device, self.arch = base, base.device, base.arch
+        self.P = cond_projection(w_dim, 4 * base.arch["ch"], seed)
+        self.cond = None
+
+    def set_guidance(self, w_embedding):
+        """w_embedding [1, w_dim] -> the conditioning vector added to the timestep embedding of every pass."""
+        self.cond = (w_embedding.detach().to("cpu", torch.float32).reshape(-1) @ self.P).contiguous().to(self.device)
+
+    def apply_condition(self, plan, prompt_emb):
+        self.text.apply_condition(plan, prompt_emb)
+        plan.set_condition(self.cond)
+
+    def eps(self, x, t, prompt_emb):
+        x = x.contiguous()
+        plan = self.base.plan(x.shape[0])
+        self.apply_condition(plan, prompt_emb)
+        return plan.forward(x, float(t))
+
+    def __call__(self, x, t, timestep_cond=None, encoder_hidden_states=None, return_dict=False):
+        if timestep_cond is not None:
+            self.set_guidance(timestep_cond[:1])
+        return (self.eps(x, t, encoder_hidden_states[:1]),)
+
+
+class EditLatentConsistency(EditStableDiffusion):
+    """Drop-in for the hot-path methods of the reference class of the same name (src/modules/edit.py:42-480): the
+    latent-space pull-back with the consistency model's boundary-condition x0 estimate instead of the DDIM posterior
+    mean, ONE conditioning (guidance is distilled into the network through the w embedding, no CFG batch), prompts
+    passed as strings and encoded by `encode_prompt` (the CLIP text encoder is out of scope: the stand-in is
+    `synthetic_prompt_embedding`).  The scheduler is `scheduler.LCMScheduler` (parity unpinned, see there)."""
+
+    def __init__(self, args, unet, vae, encode_prompt=None, dataset=None):
+        from .scheduler import LCMScheduler
+        from .t2i import synthetic_prompt_embedding
+        self.encode_prompt = encode_prompt or (lambda p: synthetic_prompt_embedding(p, 77, unet.arch["ctx_dim"]))
+        self.for_prompt = getattr(args, "for_prompt", "")
+        self.edit_prompt = getattr(args, "edit_prompt", "")
+        embs = [self.encode_prompt(p) for p in (self.for_prompt, self.edit_prompt, "")]
+        if not hasattr(args, "edit_t"):
+            args.edit_t = 0.0
+        super().__init__(args, unet, vae, *embs, dataset=dataset)
+        self.num_inference_steps = getattr(args, "num_inference_steps", 4)
+        self.scheduler = LCMScheduler(self.device)
+        self.scheduler.set_timesteps(self.num_inference_steps, device=self.device)
+        self.edit_t_idx = int(getattr(args, "edit_t_idx", 0))                                      # :97
+        self.use_sega = getattr(args, "use_sega", False)
+        w = torch.tensor(self.guidance_scale - 1).repeat(1)                                         # :117
+        self.unet.set_guidance(guidance_scale_embedding(w, getattr(args, "time_cond_proj_dim", 256)))
+        self.step_noise = None        # optional injected noise list (parity runs; the stock scheduler draws randn)
+
+    def _emb(self, prompt):
+        return prompt if torch.is_tensor(prompt) else self.encode_prompt(prompt)
+
+    def _pmp_coefficients(self, t):
+        """denoised / scaling_factor = c1 z_t + c2 eps   (:237-238)."""
+        c1, c2 = self.scheduler.denoised_coefficients(t)
+        return c1 / VAE_SCALE, c2 / VAE_SCALE
+
+    @torch.no_grad()
+    def get_x0(self, zt, prompt, t, t_idx, mask=None, flatten=False):
+        """src/modules/edit.py:206-248."""
+        zt = zt.to(self.device, torch.float32).contiguous()
+        model_pred = self.unet.eps(zt, t, self._emb(prompt))
+        c1, c2 = self._pmp_coefficients(t)
+        x0_hat = self.vae.decode(ops.combine3(zt, c1, model_pred, c2))
+        if mask is not None:
+            return ops.gather_rows(x0_hat.reshape(x0_hat.shape[0], -1), ops.mask_indices(mask.to(self.device)))
+        if flatten:
+            return x0_hat.reshape(-1, x0_hat[0].numel())
+        return x0_hat
+
+    @torch.no_grad()
+    def LCMforwardsteps(self, zt, prompt, t_start_idx=0, t_end_idx=-1):
+        """src/modules/edit.py:148-203: multistep consistency sampling; returns (latents, t, t_idx) at t_end_idx, else
+        (latents, uint8 images) decoded from the last `denoised`."""
+        self.scheduler.set_timesteps(self.num_inference_steps, device=self.device)
+        emb = self._emb(prompt)
+        latents = zt.to(self.device, torch.float32).contiguous()
+        denoised = latents
+        for t_idx, t in enumerate(self.scheduler._ts_host):
+            if t_idx < t_start_idx:
+                continue
+            elif t_idx == t_end_idx and t_idx != t_start_idx:
+                return latents, self.scheduler.timesteps[t_idx], t_idx
+            model_pred = self.unet.eps(latents, t, emb)
+            noise = None if self.step_noise is None else self.step_noise[t_idx].to(self.device)[:latents.shape[0]]
+            latents, denoised = self.scheduler.step(model_pred, t, latents, t_idx=t_idx, noise=noise)
+        image = self.vae.decode(ops.combine3(denoised, 1.0 / VAE_SCALE))
+        self.last_images.append(image)
+        x0 = (image / 2 + 0.5).clamp(0, 1)
+        return latents, (x0 * 255).to(torch.uint8).permute(0, 2, 3, 1)
+
+    def run_LCMforward(self, zT, prompt, num_samples=1):
+        """src/modules/edit.py:103-144."""
+        return self.LCMforwardsteps(zT, prompt, t_start_idx=0, t_end_idx=-1)
+
+    def local_encoder_decoder_pullback_zt(self, zt, t, t_idx, for_prompt, op=None, block_idx=None, pca_rank=50, chunk_size=25,
+                                          min_iter=10, max_iter=100, convergence_threshold=1e-3, mask=None, v0=None):
+        """src/modules/edit.py:283-369."""
+        return self._power_method(zt, t, [(0, 1.0, self._emb(for_prompt))], pca_rank, min_iter, max_iter,
+                                  convergence_threshold, mask, v0)
+
+    @torch.no_grad()
+    def get_delta_zt_via_grad(self, zt, t, t_idx, for_prompt, edit_prompt, mask=None):
+        """src/modules/edit.py:251-280: v = normalise(J_edit^T (x0_hat(edit) - x0_hat(for))), the Jacobian taken under
+        the EDIT prompt (:271)."""
+        z = zt.to(self.device, torch.float32).contiguous()
+        x0_hat = self.get_x0(z, for_prompt, t, t_idx)
+        x0_hat_after = self.get_x0(z, edit_prompt, t, t_idx)
+        dx = x0_hat[0].numel()
+        delta = ops.combine3(x0_hat_after.reshape(1, dx), 1.0, x0_hat.reshape(1, dx), -1.0)
+        if mask is not None:
+            idx = ops.mask_indices(mask.to(self.device))
+            delta = ops.scatter_rows(ops.gather_rows(delta, idx), idx, dx)
+        slots = [(0, 1.0, self._emb(edit_prompt))]
+        self._jvp_decoded(z.reshape(1, -1), t, torch.zeros(1, z[0].numel(), device=self.device), slots)
+        v_ = self._vjp_decoded(delta, t, slots)
+        return ops.nullspace_project(v_, None, project=False)
+
+    @torch.no_grad()
+    def run_edit_null_space_projection_zt(self, op, block_idx, vis_num, mask_index=0, vis_num_pc=1, vis_vT=False, pca_rank=50,
+                                          edit_prompt=None, null_space_projection=False, pca_rank_null=50, non_semantic=False):
+        """src/modules/edit.py:374-473: text-supervised (or, `non_semantic`, unsupervised) direction at step
+        `edit_t_idx` of the consistency sampler, projected off the null basis of ~mask; masks from `mask/mask.pt`."""
+        if edit_prompt is not None:
+            self.edit_prompt = edit_prompt
+        if self.sampling_mode:
+            return None
+        self.scheduler.set_timesteps(self.num_inference_steps, device=self.device)
+        zT = self.zT if self.zT is not None else torch.randn(1, *self.latent_shape, dtype=torch.float32, device=self.device)
+        mask = load_mask(self.result_folder, mask_index).to(self.device)
+        if self.edit_t_idx > 0:
+            zt, t, t_idx = self.LCMforwardsteps(zT.to(self.device), self.for_prompt, t_start_idx=0, t_end_idx=self.edit_t_idx)
+        else:
+            zt, t_idx = zT.to(self.device), 0
+        t = int(self.scheduler._ts_host[t_idx])
+        if self.use_sega:
+            self.EXP_NAME = f'sega_{self.edit_t_idx}T-{op}-block_{block_idx}_pos-edit_prompt-{self.edit_prompt}'
+            _, imgs = self.LCMforwardsteps(zt, self.edit_prompt, t_start_idx=self.edit_t_idx, t_end_idx=-1)
+            return dict(zt=zt, images=imgs)
+        pb = dict(op=op, block_idx=block_idx, chunk_size=5, min_iter=10, max_iter=50, convergence_threshold=1e-3)
+        if non_semantic:
+            _, _, vT_modify = self.local_encoder_decoder_pullback_zt(zt, t, t_idx, self.for_prompt, pca_rank=pca_rank, mask=mask, **pb)
+        else:
+            vT_modify = self.get_delta_zt_via_grad(zt.clone(), t, t_idx, self.for_prompt, self.edit_prompt, mask=mask)
+        vT_null = None
+        if null_space_projection:
+            _, _, vT_null = self.local_encoder_decoder_pullback_zt(zt, t, t_idx, self.for_prompt, pca_rank=pca_rank_null,
+                                                                   mask=~mask, **pb)
+            vT = ops.nullspace_project(vT_modify.contiguous(), vT_null[:pca_rank_null, :].contiguous(), project=True)
+        else:
+            vT = ops.nullspace_project(vT_modify.contiguous(), None, project=False)
+        self.EXP_NAME = (f'Edit_zt-edit_{self.edit_t_idx}T-{op}-block_{block_idx}_pos-edit_prompt-{self.edit_prompt}_select_mask'
+                         f'{mask_index}_null_space_projection_{null_space_projection}_null_space_rank_{pca_rank_null}')
+        batch = self._edit_batch(zt, vT[0, :], vis_num)      # the reference edits along ALL rows at once (:445); row 0 here
+        self.last_images = []
+        _, imgs = self.LCMforwardsteps(batch, self.for_prompt, t_start_idx=self.edit_t_idx, t_end_idx=-1)
+        return dict(vT=vT, vT_modify=vT_modify, vT_null=vT_null, zt=zt, images=imgs)

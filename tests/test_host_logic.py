@@ -263,3 +263,24 @@ def test_driver_refuses_to_invent_a_mask(tmp_path):
     from loco_edit_b200.masks import save_masks
     save_masks(str(tmp_path), torch.ones(2, 8, 8, dtype=torch.bool))
     assert e._get_masks(0, use_mask=True).shape == (3, 8, 8)
+
+
+def test_lcm_scheduler_restatement(golden_dir):
+    """`scheduler.LCMScheduler`: the multistep grid of diffusers' LCMScheduler (50 original steps) and the
+    boundary-condition coefficients denoised = c1 x + c2 eps, against the CPU restatement the LCM golden was
+    generated with (tests/golden/make_golden_lcm.py)."""
+    import os
+    from loco_edit_b200.scheduler import LCMScheduler, scaled_linear_betas
+    g = torch.load(os.path.join(golden_dir, "lcm_tiny.pt"), weights_only=False)
+    s = LCMScheduler("cpu")
+    s.set_timesteps(g["steps"], device="cpu")
+    assert torch.equal(s.timesteps, g["timesteps"]) and s._ts_host == [999, 759, 519, 279]
+    s.set_timesteps(8, device="cpu")
+    assert s._ts_host == [999, 879, 759, 639, 519, 399, 279, 159]
+    acp = torch.cumprod(1.0 - scaled_linear_betas(1000), 0)
+    for t in (999, 759, 279):
+        a = float(acp[t])
+        st = 10.0 * t
+        c_skip, c_out = 0.25 / (st * st + 0.25), st / (st * st + 0.25) ** 0.5
+        c1, c2 = s.denoised_coefficients(t)
+        assert abs(c1 - (c_out / a ** 0.5 + c_skip)) < 1e-12 and abs(c2 + c_out * (1 - a) ** 0.5 / a ** 0.5) < 1e-12
