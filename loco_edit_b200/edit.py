@@ -26,19 +26,21 @@ from . import ops
 from .scheduler import YHCustomScheduler
 
 
-def _pb_workspace(unet, k):
+def _pb_workspace(unet, k, slot=0):
     """Power-method buffers for rank k, LRU-bounded (each entry pins the [k,d] iteration buffers; the
-    (1,k,k) plan behind it lives in the U-Net's own bounded plan cache)."""
+    (1,k,k) plan behind it lives in the U-Net's own bounded plan cache).  `slot` separates the buffers (and
+    plans) of power methods that run concurrently on different streams."""
     cache = unet.__dict__.setdefault("_pb_cache", collections.OrderedDict())
-    if k in cache:
-        cache.move_to_end(k)
-        if cache[k].plan.released:          # its plan was evicted meanwhile: rebuild
-            del cache[k]
-    if k not in cache:
+    key = k if slot == 0 else (k, slot)
+    if key in cache:
+        cache.move_to_end(key)
+        if cache[key].plan.released:          # its plan was evicted meanwhile: rebuild
+            del cache[key]
+    if key not in cache:
         while len(cache) >= unet.max_cached_plans:
             cache.popitem(last=False)
-        cache[k] = ops.PullbackWorkspace(unet, k)
-    return cache[k]
+        cache[key] = ops.PullbackWorkspace(unet, k, slot=slot)
+    return cache[key]
 
 
 def random_basis(d, k, device, generator=None):
@@ -145,14 +147,14 @@ def _local_basis_chunked(unet, scheduler, x, t, k, v0, min_iter, max_iter, conve
 
 
 def local_basis_pair(unet, scheduler, x, t, k, k_null, mask, v0=None, v0_null=None, n_iter=12,
-                     noise=False, align_sign=True):
+                     noise=False, align_sign=True, slot=0):
     """Edit basis (mask) and null basis (~mask) of run_edit_null_space_projection
     (src/modules/edit.py:2294-2310) computed together: both probe the Jacobian at the same x_t, so
     their k + k_null tangents share one fused JVP pass, one VJP pass and one set of primal
     activations per iteration.  Fixed iteration count (the reference's loop with min_iter >=
     max_iter).  Returns (vT_modify [k,d], s_modify, vT_null [k_null,d], s_null)."""
     kt = k + k_null
-    ws = _pb_workspace(unet, kt)
+    ws = _pb_workspace(unet, kt, slot)
     d = ws.d
     dev = unet.device
     x = x.to(device=dev, dtype=torch.float32).contiguous().reshape(1, -1)

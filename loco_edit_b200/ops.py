@@ -141,12 +141,12 @@ def gram(A, B):
 class PullbackWorkspace:
     """Buffers of one rank-k power method on a B200UNet (plan (1,k,k) + iteration scratch)."""
 
-    def __init__(self, unet, k):
+    def __init__(self, unet, k, slot=0):
         self.lib = _lib.load()
         self.unet, self.k = unet, k
         R = unet.arch["resolution"]
         self.d = 3 * R * R
-        self.plan = unet.plan(1, k, k)
+        self.plan = unet.plan(1, k, k, slot=slot)
         dev = unet.device
         self.scratch = _scratch(self.lib.loco_pullback_scratch_bytes(k, self.d), dev)
         self.u_full = torch.empty(k, self.d, dtype=torch.float32, device=dev)

@@ -11,6 +11,7 @@ runs, for one image, exactly the sequence of the reference's `run_edit_null_spac
 Nothing is written to disk here (the file-producing driver is `EditUncondDiffusion`); host tensors
 go in and come out, so the call is the unit bench.py times end to end.
 """
+import os
 import types
 
 import torch
@@ -21,8 +22,11 @@ from .edit import EditUncondDiffusion, local_basis, local_basis_pair
 
 class EditPipeline(object):
     def __init__(self, unet, k=5, k_null=5, edit_t=0.6, n_iter=12, scale=0.5, num_step=16, vis_num=2,
-                 for_steps=100, inv_steps=100, boost_t=0.2, result_folder="/tmp/loco_b200_runs"):
+                 for_steps=100, inv_steps=100, boost_t=0.2, result_folder="/tmp/loco_b200_runs", basis_streams=None):
         self.unet = unet
+        # concurrent per-image power methods in edit_batch (each stream pins one more (1, k + k_null, k + k_null) plan)
+        self.basis_streams = int(os.environ.get("LOCO_BASIS_STREAMS", "2")) if basis_streams is None else int(basis_streams)
+        self._streams = []
         self.device = unet.device
         self.k, self.k_null, self.n_iter = k, k_null, n_iter
         self.vis_num = vis_num
@@ -146,14 +150,31 @@ class EditPipeline(object):
         xt, t, t_idx = drv.DDIMforwardsteps(xt, t_start_idx=0, t_end_idx=drv.edit_t_idx, save_image=False)
         t_host = sched._ts_host[t_idx]
         batches, vTs = [], []
+        # the local bases of different images are independent: image b runs on stream b % basis_streams with its own
+        # plan slot (saved activations, split-K scratch and iteration buffers), so that the <= 32^2 layers of one
+        # image's Jacobian passes (which cannot fill 148 SMs with 11 rows) overlap with the other image's kernels
+        ns = max(1, min(self.basis_streams, B))
+        main = torch.cuda.current_stream(self.device)
+        if ns > 1:
+            if len(self._streams) < ns:
+                self._streams += [torch.cuda.Stream(self.device) for _ in range(ns - len(self._streams))]
+            for s_ in self._streams[:ns]:
+                s_.wait_stream(main)
         for b in range(B):
-            xb = xt[b:b + 1].contiguous()
-            vT_mod, _, vT_null, _ = local_basis_pair(
-                self.unet, sched, xb, t_host, self.k, self.k_null, masks[b], v0=self._v0(self.k, gen),
-                v0_null=self._v0(self.k_null, gen), n_iter=self.n_iter)
-            vT = ops.nullspace_project(vT_mod, vT_null, project=True)
-            vTs.append(vT)
-            batches.append(drv.build_edit_batch(xb, vT[pc], self.vis_num))
+            slot = b % ns
+            with torch.cuda.stream(self._streams[slot] if ns > 1 else main):
+                xb = xt[b:b + 1].contiguous()
+                vT_mod, _, vT_null, _ = local_basis_pair(
+                    self.unet, sched, xb, t_host, self.k, self.k_null, masks[b], v0=self._v0(self.k, gen),
+                    v0_null=self._v0(self.k_null, gen), n_iter=self.n_iter, slot=slot)
+                vT = ops.nullspace_project(vT_mod, vT_null, project=True)
+                vTs.append(vT)
+                batches.append(drv.build_edit_batch(xb, vT[pc], self.vis_num))
+        if ns > 1:
+            for s_ in self._streams[:ns]:
+                main.wait_stream(s_)
+            for t_ in batches + vTs:
+                t_.record_stream(main)
         per = batches[0].shape[0]
         allx = torch.cat(batches, 0).contiguous()
         drv.noise_fn = (lambda i, x: torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=gen)) \
