@@ -14,7 +14,7 @@ from loco_edit_b200.weights import DDPM256, random_state_dict
 
 dev = torch.device("cuda:0")
 net = B200UNet(DDPM256, random_state_dict(DDPM256, seed=1234), device=dev)
-k = 5
+k = int(os.environ.get("K", "5"))
 x = torch.randn(1 + k, 3, 256, 256, device=dev)
 g = torch.randn(k, 3, 256, 256, device=dev)
 p = net.plan(1, k, k)
