@@ -337,3 +337,36 @@ def test_batch_edit_concurrent_basis_streams_equal_single_stream(dev, golden_dir
     assert torch.isfinite(b["images"]).all() and a["images"].shape == b["images"].shape == (3, 5, 3, R, R)
     # the 59-step final stage amplifies the run-to-run noise of the GroupNorm atomics: loose bound
     assert rel_err(a["images"], b["images"]) < 0.2
+
+
+def test_concurrent_plan_slots_stress(dev, golden_dir):
+    """Three streams replay Jacobian passes of three plan slots of ONE network at the same time (every layer of the
+    tiny network is a split-K launch whose CTAs wait for each other): no exchange may time out, and every stream
+    must reproduce its own sequential result."""
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict
+    g = torch.load(os.path.join(golden_dir, "pullback_tiny.pt"), weights_only=False)
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    net = B200UNet(g["arch"], sd, device=dev)
+    R, k, ns = g["arch"]["resolution"], 4, 3
+    gen = torch.Generator(device=dev).manual_seed(17)
+    xs = [torch.randn(1 + k, 3, R, R, device=dev, generator=gen) for _ in range(ns)]
+    gs = [torch.randn(k, 3, R, R, device=dev, generator=gen) for _ in range(ns)]
+    plans = [net.plan(1, k, k, slot=i) for i in range(ns)]
+    ref = []
+    for i in range(ns):
+        e = plans[i].forward(xs[i], 300.0).clone()
+        ref.append((e, plans[i].vjp(gs[i]).clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev) for _ in range(ns)]
+    outs = [None] * ns
+    for s_ in streams:
+        s_.wait_stream(torch.cuda.current_stream(dev))
+    for rep in range(40):
+        for i in range(ns):
+            with torch.cuda.stream(streams[i]):
+                e = plans[i].forward(xs[i], 300.0)
+                outs[i] = (e, plans[i].vjp(gs[i]))
+    torch.cuda.synchronize()
+    for i in range(ns):
+        assert rel_err(outs[i][0], ref[i][0]) < 2e-3 and rel_err(outs[i][1], ref[i][1]) < 2e-3
