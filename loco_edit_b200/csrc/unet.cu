@@ -901,9 +901,10 @@ int Plan::build(float* workspace) {
         if (R.resample == 1) push_b([=](cudaStream_t s) { return upsample2x(ga1r, ga1, 0.25f, 0, 0, s); });
         else push_b([=](cudaStream_t s) { return sumpool2x(ga1r, ga1, 1.f, 0, 0, s); });
       }
-      const int f1 = writer_flag(x.ids);
-      const bool fuse_identity = !R.has_nin && R.resample == 0;
-      gn_bwd(row0(x.v), st1, ga1, R.n1, 1, fuse_identity ? &out.g : nullptr, f1, 1, x.g);
+      // the 1x1 shortcut's data gradient goes FIRST (a plain store), the GroupNorm rule accumulates onto it: the
+      // read-modify-write of the (up to 384-channel) input gradient then happens in the HBM-rate GroupNorm kernel
+      // instead of the K = cout conv epilogue (one epilogue warpgroup per CTA: 369 us = 2.3 TB/s for the 838 MB of the
+      // 256^2 decoder sites at rank 10, profiles/r2_launches_step_k10.csv)
       if (R.has_nin) {
         if (R.resample != 0 && err == 0) {   // (a void lambda: report through `err`)
           set_error("plan: resampling ResBlock with a 1x1 shortcut is not supported");
@@ -911,6 +912,11 @@ int Plan::build(float* workspace) {
         }
         const int f2 = writer_flag(x.ids);
         conv_bwd(CONV_1x1, out.g, x.g, R.nin, f2);
+      }
+      const int f1 = writer_flag(x.ids);
+      const bool fuse_identity = !R.has_nin && R.resample == 0;
+      gn_bwd(row0(x.v), st1, ga1, R.n1, 1, fuse_identity ? &out.g : nullptr, f1, 1, x.g);
+      if (R.has_nin) {
       } else if (R.resample != 0) {
         // identity shortcut through the resampling: x.g += resample^T(out.g)
         const int f2 = writer_flag(x.ids);
