@@ -166,6 +166,7 @@ edge_expand_mma_kernel(const float* __restrict__ in3, const float* __restrict__ 
     }
     bfrag[e] = make_uint2(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]));
   }
+  __syncthreads();                                 // the fragments are visible to every warp
   const int tiles_x = W / kTW, tiles_y = H / kTH;
   const long long ntiles = (long long)out.N * tiles_y * tiles_x;
   const uint32_t atile_s = smem_u32(atile);
@@ -174,7 +175,9 @@ edge_expand_mma_kernel(const float* __restrict__ in3, const float* __restrict__ 
     const int tx = (int)(ti % tiles_x), ty = (int)((ti / tiles_x) % tiles_y), n = (int)(ti / ((long long)tiles_x * tiles_y));
     const int x0 = tx * kTW, y0 = ty * kTH;
     const float sc = (scale_dev != nullptr && n >= scale_from) ? scale_dev[0] : 1.f;
-    __syncthreads();                               // previous tile's staging buffer drained
+    // a warp owns pixel row `warp` of the tile end to end: its 32 im2col rows, its 32 staging rows and their
+    // stores are private to it, so the warps of a CTA run through the tiles decoupled (no block barrier in the loop)
+    __syncwarp();                                  // previous tile's staging rows drained
     {
       // im2col row of pixel threadIdx.x: 27 range-scaled inputs, 5 zeros
       const int py = threadIdx.x / kTW, pxx = threadIdx.x % kTW;
@@ -195,7 +198,7 @@ edge_expand_mma_kernel(const float* __restrict__ in3, const float* __restrict__ 
         row[q] = make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
                             pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
     }
-    __syncthreads();
+    __syncwarp();
     const bool ub = bias != nullptr && n < bias_rows;
     const uint32_t lrow = (uint32_t)((lane & 15) * kAPitch + (lane >> 4) * 16);
 #pragma unroll 1
@@ -233,10 +236,10 @@ edge_expand_mma_kernel(const float* __restrict__ in3, const float* __restrict__ 
         }
       }
     }
-    __syncthreads();
-    // 256 pixels x 256 B -> NHWC, 16 bytes per thread and step (16 threads cover a pixel)
-    for (int e = threadIdx.x; e < kTH * kTW * 16; e += blockDim.x) {
-      const int p = e >> 4, chunk = e & 15;
+    __syncwarp();
+    // the warp's 32 pixels x 256 B -> NHWC, 16 bytes per thread and step (16 threads cover a pixel)
+    for (int e = lane; e < kTW * 16; e += 32) {
+      const int p = warp * kTW + (e >> 4), chunk = e & 15;
       const int y = y0 + p / kTW, x = x0 + p % kTW;
       *reinterpret_cast<uint4*>(dst + (long long)n * out.sN + (long long)y * out.sH + (long long)x * out.sW + chunk * 8) =
           *reinterpret_cast<const uint4*>(otile + p * kPitch + chunk * 16);
