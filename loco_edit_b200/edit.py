@@ -174,6 +174,61 @@ def local_basis_pair(unet, scheduler, x, t, k, k_null, mask, v0=None, v0_null=No
     return cur[:k].clone(), s[:k], cur[k:].clone(), s[k:]
 
 
+def local_basis_pair_converging(unet, scheduler, x, t, k, k_null, mask, v0=None, v0_null=None, min_iter=10,
+                                max_iter=50, convergence_threshold=1e-4, noise=False, align_sign=True,
+                                verbose=False):
+    """The two power methods of `run_edit_null_space_projection` (src/modules/edit.py:2294-2310: the edit basis
+    through `mask`, then the null basis through `~mask`, each with the loop and the stopping rule of :2440-2497)
+    advanced TOGETHER while both still iterate: their tangents probe the same Jacobian at the same x_t, so one
+    fused (1, k + k_null) pass per iteration serves both (rows are independent: each basis sees exactly the
+    iterates of its own loop).  Convergence is tested per basis with the reference's rule; when one basis stops,
+    the other finishes alone from its current iterate with the remaining iteration budget.
+    Returns (vT_modify [k,d], s_modify, vT_null [k_null,d], s_null)."""
+    kt = k + k_null
+    ws = _pb_workspace(unet, kt)
+    d = ws.d
+    dev = unet.device
+    xr = x.to(device=dev, dtype=torch.float32).contiguous().reshape(1, -1)
+    t_host = float(t)
+    at = scheduler.alpha_at(t_host)
+    mask_u8 = mask.to(device=dev).reshape(-1).to(torch.uint8).contiguous()
+    cur, nxt = ws.V
+    for v, lo, kk in ((v0, 0, k), (v0_null, k, k_null)):       # same order of draws as the two separate calls
+        if v is None:
+            v = random_basis(d, kk, dev)
+        cur[lo:lo + kk].copy_(v.reshape(kk, d))
+    stop = [False, False]
+    it = 0
+    for it in range(max_iter):
+        ws.iterate_pair(xr, t_host, at, mask_u8, noise, cur, nxt, k, k_null, align_sign=align_sign)
+        need_check = it > min_iter
+        if verbose:
+            for name, sl in (("modify", slice(0, k)), ("null", slice(k, kt))):
+                print(f'power method ({name}) : {it}-th step convergence : ', torch.dist(cur[sl], nxt[sl]).item())
+        cur, nxt = nxt, cur
+        if need_check:
+            stop = [bool(torch.allclose(nxt[:k], cur[:k], atol=convergence_threshold)),      # :2492
+                    bool(torch.allclose(nxt[k:], cur[k:], atol=convergence_threshold))]
+            if stop[0] or stop[1]:
+                break
+    ws.V = [cur, nxt]
+    vT_mod, vT_null = cur[:k].clone(), cur[k:].clone()
+    s = ws.s.clone()
+    s_mod, s_null = s[:k], s[k:]
+    left = max_iter - (it + 1)
+    if (stop[0] != stop[1]) and left > 0:
+        # one loop ended: the other one goes on by itself (its check is already active: min_iter = -1)
+        if stop[0]:
+            _, s_null, vT_null = local_basis(unet, scheduler, x, t, k_null, v0=vT_null, min_iter=-1, max_iter=left,
+                                             convergence_threshold=convergence_threshold, mask=~mask.to(dev),
+                                             noise=noise, align_sign=align_sign, verbose=verbose)
+        else:
+            _, s_mod, vT_mod = local_basis(unet, scheduler, x, t, k, v0=vT_mod, min_iter=-1, max_iter=left,
+                                           convergence_threshold=convergence_threshold, mask=mask.to(dev),
+                                           noise=noise, align_sign=align_sign, verbose=verbose)
+    return vT_mod, s_mod, vT_null, s_null
+
+
 class SyntheticDataset(object):
     """Seeded stand-in for the reference's datasets (src/utils/utils.py:472-672,
     src/dataset/celeba_hq_dataloader.py): `ds[idx] -> [1,3,R,R]` in [-1,1], `getmask -> bool[3,R,R]`.
@@ -261,6 +316,9 @@ class EditUncondDiffusion(object):
         self.save_images = getattr(args, "save_images", True)
         self.align_sign = getattr(args, "align_sign", True)
         self.v0 = None            # optional injected initial basis (parity runs)
+        # run_edit_null_space_projection: advance the edit and the null power method in one fused pass per iteration
+        # while both still iterate (same iterates and stopping rule per basis as two separate calls)
+        self.fuse_bases = bool(getattr(args, "fuse_bases", True))
         self.noise_fn = None      # optional callable(i, xt) -> eta=1 noise (parity runs)
         self.last_images = []     # outputs of the performance-boosted DDIM passes
 
@@ -364,14 +422,25 @@ class EditUncondDiffusion(object):
             os.makedirs(save_dir, exist_ok=True)
             vT_modify_path = os.path.join(save_dir, f'vT-modify-pca-rank-{pca_rank}.pt')
             vT_null_path = os.path.join(save_dir, f'vT-null-{pca_rank_null}.pt')
-            if os.path.exists(vT_modify_path):
+            vT_null_fused = None
+            if (self.fuse_bases and mask is not None and null_space_projection and not os.path.exists(vT_modify_path)
+                    and not os.path.exists(vT_null_path) and pca_rank + pca_rank_null <= 25):
+                # neither basis is cached: both power methods advance in one fused pass per iteration
+                vT_modify, vT_null_fused = self.local_encoder_decoder_pullback_xt_pair(
+                    x=xt, t=t, pca_rank=pca_rank, pca_rank_null=pca_rank_null, min_iter=10, max_iter=50,
+                    convergence_threshold=1e-4, mask=mask, noise=encoder_decoder_by_et)
+                torch.save(vT_modify, vT_modify_path)
+            elif os.path.exists(vT_modify_path):
                 vT_modify = torch.load(vT_modify_path, map_location=self.device).type(self.dtype)
             else:
                 u_modify, s_modify, vT_modify = self.local_encoder_decoder_pullback_xt(
                     x=xt, t=t, op=op, block_idx=block_idx, pca_rank=pca_rank,
                     min_iter=10, max_iter=50, convergence_threshold=1e-4, mask=mask, noise=encoder_decoder_by_et)
                 torch.save(vT_modify, vT_modify_path)
-            if null_space_projection and os.path.exists(vT_null_path):
+            if vT_null_fused is not None:
+                vT_null = vT_null_fused
+                torch.save(vT_null, vT_null_path)
+            elif null_space_projection and os.path.exists(vT_null_path):
                 vT_null = torch.load(vT_null_path, map_location=self.device).type(self.dtype)
             elif not null_space_projection:
                 vT_null = None
@@ -436,6 +505,19 @@ class EditUncondDiffusion(object):
             idx = ops.mask_indices(mask.to(self.device))
             et = ops.gather_rows(et.reshape(et.shape[0], -1), idx)
         return et
+
+    def local_encoder_decoder_pullback_xt_pair(self, x, t, pca_rank, pca_rank_null, mask, min_iter=10, max_iter=50,
+                                               convergence_threshold=1e-4, noise=False):
+        """Edit basis (mask) and null basis (~mask) of src/modules/edit.py:2294-2310 in one fused loop
+        (`local_basis_pair_converging`); returns (vT_modify, vT_null)."""
+        v0a = v0b = None
+        if isinstance(self.v0, dict):               # injected initial bases (parity runs), keyed by rank
+            v0a, v0b = self.v0.get(pca_rank), self.v0.get(pca_rank_null)
+        vm, _, vn, _ = local_basis_pair_converging(
+            self.unet, self.scheduler, x, t, pca_rank, pca_rank_null, mask, v0=v0a, v0_null=v0b, min_iter=min_iter,
+            max_iter=max_iter, convergence_threshold=convergence_threshold, noise=noise,
+            align_sign=self.align_sign, verbose=self.verbose)
+        return vm, vn
 
     def local_encoder_decoder_pullback_xt(
             self, x, t, op=None, block_idx=None,

@@ -29,7 +29,7 @@ class _Dataset:
         return self.mask
 
 
-def _make(dev, tmp, g, vT_path=""):
+def _make(dev, tmp, g, vT_path="", fuse=False):
     from loco_edit_b200.edit import EditUncondDiffusion
     from loco_edit_b200.unet import B200UNet
     from loco_edit_b200.weights import random_state_dict, tiny_arch
@@ -50,6 +50,14 @@ def _make(dev, tmp, g, vT_path=""):
         return orig(**kw)
 
     e.local_encoder_decoder_pullback_xt = capped
+    orig_pair = e.local_encoder_decoder_pullback_xt_pair
+
+    def capped_pair(**kw):
+        kw["max_iter"] = 2
+        return orig_pair(**kw)
+
+    e.local_encoder_decoder_pullback_xt_pair = capped_pair
+    e.fuse_bases = fuse
     return e
 
 
@@ -191,3 +199,68 @@ def test_group_edit_composes_directions_like_the_reference(golden_dir, tmp_path)
     p = _psnr(e.last_images[0].cpu(), ref)
     print(f"group edit (2 directions) vs oracle from the same x_t: PSNR {p:.1f} dB")
     assert p >= 40.0
+
+
+def test_driver_fused_power_methods_write_the_same_bases(golden_dir, tmp_path):
+    """run_edit_null_space_projection with the edit and the null power method advanced in one fused pass per
+    iteration (the default) writes the files of the two-separate-loops driver: same names, shapes, subspaces."""
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(golden_dir, "driver_tiny.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    d = g["x0"].numel()
+    v0a, _ = torch.linalg.qr(torch.randn(d, 2))
+    v0b, _ = torch.linalg.qr(torch.randn(d, 3))
+    noises = [torch.randn(5, 3, 32, 32) for _ in range(40)]
+    got = {}
+    for fuse in (False, True):
+        e = _make(dev, tmp_path / ("fused" if fuse else "separate"), g, fuse=fuse)
+        e.v0 = {2: v0a.T.contiguous().to(dev), 3: v0b.T.contiguous().to(dev)}
+        it = iter(noises)
+        e.noise_fn = lambda i, x: next(it).to(dev)
+        e.run_edit_null_space_projection(idx=7, vis_num=2, vis_num_pc=2, pca_rank=2, pca_rank_null=3,
+                                         null_space_projection=True, use_mask=True)
+        torch.cuda.synchronize()
+        files = {}
+        for root, _, fs in os.walk(e.result_folder):
+            for f in fs:
+                if f.endswith(".pt"):
+                    files[os.path.relpath(os.path.join(root, f), e.result_folder)] = torch.load(os.path.join(root, f)).cpu()
+        got[fuse] = files
+    assert sorted(got[True]) == sorted(got[False]) == sorted(g["files"])
+    for name, ref in got[False].items():
+        mine = got[True][name]
+        assert mine.shape == ref.shape and mine.dtype == ref.dtype, name
+        # both runs sit at the end of their own (noise-level different) x0 -> xT -> xt chain
+        assert float(principal_angles_deg(mine, ref).max()) < 5.0, name
+
+
+def test_converging_pair_equals_two_separate_loops(golden_dir):
+    """local_basis_pair_converging == two local_basis calls with the reference's stopping rule, including the
+    hand-over when one loop stops first (forced here with a loose threshold on a fast-converging rank-1 basis)."""
+    from loco_edit_b200.edit import local_basis, local_basis_pair_converging
+    from loco_edit_b200.scheduler import YHCustomScheduler
+    from loco_edit_b200.unet import B200UNet
+    from loco_edit_b200.weights import random_state_dict
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(golden_dir, "pullback_tiny.pt"), weights_only=False)
+    sd = random_state_dict(g["arch"], seed=g["seed"], perturb_norm=g["perturb_norm"])
+    net = B200UNet(g["arch"], sd, device=dev)
+    sched = YHCustomScheduler(device=dev)
+    d = g["xt"].numel()
+    gen = torch.Generator().manual_seed(5)
+    va, _ = torch.linalg.qr(torch.randn(d, 1, generator=gen))
+    vb, _ = torch.linalg.qr(torch.randn(d, 3, generator=gen))
+    va, vb = va.T.contiguous().to(dev), vb.T.contiguous().to(dev)
+    mask, xt = g["mask"].to(dev), g["xt"].to(dev)
+    for thr, max_iter in ((1e-4, 6), (3e-2, 40)):
+        kw = dict(min_iter=2, max_iter=max_iter, convergence_threshold=thr, verbose=False)
+        _, s1, v1 = local_basis(net, sched, xt, g["t"], 1, v0=va, mask=mask, **kw)
+        _, s2, v2 = local_basis(net, sched, xt, g["t"], 3, v0=vb, mask=~mask, **kw)
+        pv1, ps1, pv2, ps2 = local_basis_pair_converging(net, sched, xt, g["t"], 1, 3, mask, v0=va, v0_null=vb,
+                                                         min_iter=2, max_iter=max_iter, convergence_threshold=thr)
+        torch.cuda.synchronize()
+        assert float(((ps1 - s1).abs() / s1).max()) < 2e-3 and float(((ps2 - s2).abs() / s2).max()) < 2e-3
+        assert float(principal_angles_deg(pv1, v1).max()) < 0.5
+        assert float(principal_angles_deg(pv2, v2).max()) < 0.5

@@ -224,6 +224,7 @@ def test_p2_driver_ffhq_script_settings(dev, tmp_path):
         return orig(**kw)
 
     e.local_encoder_decoder_pullback_xt = capped
+    e.fuse_bases = False          # this test follows the two separate loops (the fused loop: test_gpu_driver.py)
     e.run_edit_null_space_projection(idx=4, vis_num=1, vis_num_pc=1, pca_rank=3, pca_rank_null=5,
                                      null_space_projection=True, use_mask=True)
     torch.cuda.synchronize()
