@@ -284,3 +284,27 @@ def test_lcm_scheduler_restatement(golden_dir):
         c_skip, c_out = 0.25 / (st * st + 0.25), st / (st * st + 0.25) ** 0.5
         c1, c2 = s.denoised_coefficients(t)
         assert abs(c1 - (c_out / a ** 0.5 + c_skip)) < 1e-12 and abs(c2 + c_out * (1 - a) ** 0.5 / a ** 0.5) < 1e-12
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/ (one B200 run each of `python bench.py` and
+    `python bench.py --impl reference`) carry every key of the measurement contract."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = json.loads(open(os.path.join(root, "profiles", "r2_bench_final4.json")).read().strip().splitlines()[-1])
+    ref = json.loads(open(os.path.join(root, "profiles", "r2_bench_ref_final4.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in ours, k
+    assert ours["warmup"] >= 3 and ours["gpu_launches"] > 0 and ours["vs_baseline"] is None
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(ours["roofline"])
+    assert abs(ours["roofline"]["frac"] - ours["roofline"]["achieved"] / ours["roofline"]["peak"]) < 1e-9
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(ours["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(ours["e2e"])
+    assert ours["e2e"]["h2d_bytes_per_step"] > 0 and ours["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(ours["clocks"])
+    assert "workload" in ours["config"] and "model" not in ours["config"]
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["config"]["workload"] == ours["config"]["workload"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
+    assert ref["cpu_baseline"]["kind"] in ("port", "reference") and ref["cpu_baseline"]["value"] == ref["value"]
