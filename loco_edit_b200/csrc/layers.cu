@@ -1411,6 +1411,20 @@ static int same_type(const View& a, const View& b, const char* what) {
   return 0;
 }
 
+__global__ void gn_stats_fold_pairs_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int group0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // (row, g < 16, which)
+  if (e >= rows * (kGroups / 2) * 2) return;
+  const int which = e & 1, g = (e >> 1) % (kGroups / 2), n = e / kGroups;
+  const double* sp = src + ((long long)n * kGroups + 2 * g) * 2 + which;
+  atomicAdd(&dst[((long long)n * kGroups + group0 + g) * 2 + which], sp[0] + sp[2]);
+}
+int gn_stats_fold_pairs(const double* src, double* dst, int rows, int group0, cudaStream_t s) {
+  LOCO_REQUIRE(src && dst && rows > 0 && group0 >= 0 && group0 + kGroups / 2 <= kGroups, "gn_stats_fold_pairs: bad arguments");
+  const int n = rows * kGroups;
+  gn_stats_fold_pairs_kernel<<<(n + 127) / 128, 128, 0, s>>>(src, dst, rows, group0);
+  count_launch(); LOCO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s) {
   LOCO_TRY(check_gn_view(x, "gn_stats_fwd"));
   const int h = x.half;

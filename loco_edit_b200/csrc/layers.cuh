@@ -55,6 +55,9 @@ int thin_extract(View in, int c, float* out_nchw, const float* mix, const float*
 // Forward/JVP: rows < n_primal accumulate (sum x, sum x^2); tangent rows (sum dx, sum x0*dx) with
 // x0 = primal row 0.  (reference: Normalize/nonlinearity, ddpm/diffusion.py:806-811)
 int gn_stats_fwd(View x, int n_primal, double* stats, cudaStream_t s);
+// Statistics of a tensor with cg channels per group, regrouped for a consumer whose groups are PAIRS of them (a decoder
+// concat buffer with as many channels again): dst[row][group0 + g] += src[row][2 g] + src[row][2 g + 1], g < 16.
+int gn_stats_fold_pairs(const double* src, double* dst, int rows, int group0, cudaStream_t s);
 int gn_apply_fwd(View x, int n_primal, const double* stats, const float* gamma, const float* beta,
                  float eps, int silu, int round_out, View y, cudaStream_t s);
 // VJP: xp = saved primal input (1 row), pstats = its (sum x, sum x^2); gy = k cotangent rows of the

@@ -851,7 +851,21 @@ int Plan::build(float* workspace) {
     const int Wo = R.resample == 1 ? W / 2 : (R.resample == 2 ? 2 * W : W);
     const float* aff = affine_site(R);
     View a1 = Tf(H, W, R.cin);
-    double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1, x.st_self.st, th_fused(x));
+    const int x_fused = th_fused(x);
+    double* st1 = gn_fwd(x.v, R.n1, 1, 1, a1, x.st_self.st, x_fused);
+    // Forward-only programs: a skip tensor no conv epilogue produced (the 3 -> C conv_in output) just had its own
+    // statistics computed; when the decoder concat buffer it also belongs to has twice its channels per group, that
+    // buffer's statistics over this slice are pair sums of them -- no second pass over the tensor, and the decoder
+    // slice's producer may then fuse its half (fused_cb) so the concat GroupNorm needs no statistics pass at all.
+    if (fuse_stats && x_fused == 0 && x.ids.size() == 1 && x.partner < 0 && x.st_cb.st != nullptr && x.st_self.st != nullptr &&
+        !fused_cb[x.ids[0]] && x.st_cb.cg == 2 * x.st_self.cg && x.st_cb.choff % x.st_cb.cg == 0 &&
+        x.st_cb.choff / x.st_cb.cg + 16 <= 32) {
+      const double* src = x.st_self.st;
+      double* dst = x.st_cb.st;
+      const int g0 = x.st_cb.choff / x.st_cb.cg, rows = NB;
+      I.fwd.push_back([=](cudaStream_t s) { return gn_stats_fold_pairs(src, dst, rows, g0, s); });
+      fused_cb[x.ids[0]] = 1;
+    }
     // guided-diffusion up/down ResBlock: both branches are resampled after GN+SiLU
     // (unet.py:238-244): avg-pool 2x2 (Downsample, use_conv = False) or nearest x2 (Upsample)
     View a1r = a1, xr = x.v;
